@@ -1,0 +1,332 @@
+"""Synthetic inputs for the RPD3D / dist2mat hot path.
+
+Everything is deterministic from a 64-bit SplitMix stream (seed 200 = RAN_SEED,
+reference src/inputs/params.h:97) so that the CPU container, the GPU box and every rank of a
+multi-GPU run build bit-identical inputs without reading any file.
+
+Mesh semantics restate reference src/IO/IO_CXX/io.cxx:238-335 (load_tet_adj_info) with a
+*compact* per-tet-edge adjacency (6 ints per tet) instead of the dense n_vert^2/2 table.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+
+import numpy as np
+
+RAN_SEED = 200  # reference src/inputs/params.h:97
+
+# faces of tet abcd opposite local vertex i (reference src/rpd3d/convex_cell.h:30-31)
+TET_FACES_LVID = np.array([[2, 1, 3], [0, 2, 3], [1, 0, 3], [0, 1, 2]], dtype=np.int64)
+# the 6 local-vertex pairs in the order of reference convex_cell.cu:194-207
+TET_EDGE_PAIRS = np.array([[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]], dtype=np.int64)
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(seed: int, n: int, stream: int = 0) -> np.ndarray:
+    """n 64-bit words of the SplitMix64 sequence for (seed, stream)."""
+    with np.errstate(over="ignore"):
+        base = np.uint64((seed * 0x9E3779B97F4A7C15 + stream * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF)
+        z = base + (np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def uniform01(seed: int, n: int, stream: int = 0) -> np.ndarray:
+    """n doubles in [0,1) from the top 53 bits of the SplitMix64 words."""
+    return (splitmix64(seed, n, stream) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+@dataclass
+class TetMesh:
+    """The TetMesh fields consumed at the boundary (reference src/inputs/input_types.h:122-133)."""
+
+    vertices: np.ndarray  # float32 [n_vert,3] AoS, coordinates in [0,1000]^3
+    indices: np.ndarray  # int32 [n_tet,4], positively oriented
+    v_adjs: np.ndarray  # int32 [n_vert]   #tets at vertex
+    e_adj6: np.ndarray  # int32 [n_tet,6]  #tets around each tet edge, TET_EDGE_PAIRS order
+    f_adjs: np.ndarray  # int32 [n_tet,4]  1 boundary / 2 interior
+    f_ids: np.ndarray  # int32 [n_tet,4]  unique face ids, boundary faces first
+    n_surf_faces: int = 0
+
+    @property
+    def n_tet(self) -> int:
+        return int(self.indices.shape[0])
+
+    @property
+    def n_vert(self) -> int:
+        return int(self.vertices.shape[0])
+
+    def dense_e_adjs(self) -> np.ndarray:
+        """The reference's dense triangular e_adjs table (io.cxx:264); small meshes only."""
+        n = self.n_vert
+        if n > 40000:
+            raise ValueError("dense e_adjs overflows int beyond ~46k vertices (io.cxx:264)")
+        out = np.full(n * (n + 1) // 2 + 1, -1, dtype=np.int32)
+        a = self.indices[:, TET_EDGE_PAIRS[:, 0]].astype(np.int64)
+        b = self.indices[:, TET_EDGE_PAIRS[:, 1]].astype(np.int64)
+        out[edge_idx(a, b, n).ravel()] = self.e_adj6.ravel()
+        return out
+
+    def tet_volumes(self) -> np.ndarray:
+        p = self.vertices.astype(np.float64)[self.indices]
+        return np.einsum("ij,ij->i", np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), p[:, 3] - p[:, 0]) / 6.0
+
+
+def edge_idx(v1, v2, n):
+    """Closed form of get_edge_idx (reference src/rpd3d/convex_cell.h:46-59)."""
+    vmin = np.minimum(v1, v2)
+    vmax = np.maximum(v1, v2)
+    return (vmin + 1) * n - vmin * (vmin + 1) // 2 - (n - vmax)
+
+
+def tet_adjacency(indices: np.ndarray, n_vert: int):
+    """v_adjs, e_adj6, f_adjs, f_ids, n_sf with the semantics of load_tet_adj_info
+    (reference io.cxx:238-335): boundary faces numbered 0..n_sf-1 in (tet, local face) scan
+    order (standing in for the surface-mesh facet ids), interior faces n_sf.. in first-visit order."""
+    idx = indices.astype(np.int64)
+    n_tet = idx.shape[0]
+    v_adjs = np.bincount(idx.ravel(), minlength=n_vert).astype(np.int32)
+
+    a = idx[:, TET_EDGE_PAIRS[:, 0]]
+    b = idx[:, TET_EDGE_PAIRS[:, 1]]
+    ekey = (np.minimum(a, b) * n_vert + np.maximum(a, b)).ravel()
+    _, inv, cnt = np.unique(ekey, return_inverse=True, return_counts=True)
+    e_adj6 = cnt[inv].reshape(n_tet, 6).astype(np.int32)
+
+    f = np.sort(idx[:, TET_FACES_LVID], axis=2)  # [n_tet,4,3]
+    fkey = ((f[..., 0] * n_vert + f[..., 1]) * n_vert + f[..., 2]).ravel()
+    _, first, inv, cnt = np.unique(fkey, return_index=True, return_inverse=True, return_counts=True)
+    f_adjs = cnt[inv].astype(np.int32)
+    boundary = f_adjs == 1
+    n_sf = int(boundary.sum())
+    f_ids = np.empty(4 * n_tet, dtype=np.int64)
+    f_ids[boundary] = np.arange(n_sf)
+    # interior faces: id = n_sf + rank of the face's first visit among interior first visits
+    interior_unique = cnt == 2
+    order = np.argsort(first[interior_unique], kind="stable")
+    rank = np.empty(order.size, dtype=np.int64)
+    rank[order] = np.arange(order.size)
+    uid = np.full(cnt.size, -1, dtype=np.int64)
+    uid[interior_unique] = n_sf + rank
+    f_ids[~boundary] = uid[inv[~boundary]]
+    return v_adjs, e_adj6, f_adjs.reshape(n_tet, 4), f_ids.reshape(n_tet, 4).astype(np.int32), n_sf
+
+
+def make_ball_mesh(n: int, seed: int = RAN_SEED, jitter: float = 0.2) -> TetMesh:
+    """n^3 cubes on [-1,1]^3, Kuhn/Freudenthal 6-tet split (conforming), interior grid vertices
+    jittered U(-jitter*h, jitter*h)^3, cube->ball map p*|p|_inf/|p|_2, affine to [0,1000]^3
+    (reference params.h:15, io.cxx:164-178), tets re-oriented positive.
+    n=15/32/70 -> 20 250 / 196 608 / 2 058 000 tets."""
+    m = n + 1
+    g = np.arange(m, dtype=np.int64)
+    I, J, K = np.meshgrid(g, g, g, indexing="ij")
+    ijk = np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1)
+    h = 2.0 / n
+    p = -1.0 + ijk.astype(np.float64) * h
+    interior = np.all((ijk > 0) & (ijk < n), axis=1)
+    u = uniform01(seed, 3 * m**3, stream=1).reshape(-1, 3)
+    p = p + np.where(interior[:, None], (2.0 * u - 1.0) * (jitter * h), 0.0)
+    linf = np.abs(p).max(axis=1)
+    l2 = np.sqrt((p * p).sum(axis=1))
+    scale = np.divide(linf, l2, out=np.ones_like(l2), where=l2 > 0)
+    p = p * scale[:, None]
+    verts = ((p + 1.0) * 500.0).astype(np.float32)
+
+    def vid(i, j, k):
+        return (i * m + j) * m + k
+
+    c = np.arange(n, dtype=np.int64)
+    CI, CJ, CK = [a.ravel() for a in np.meshgrid(c, c, c, indexing="ij")]
+    tets = []
+    unit = np.eye(3, dtype=np.int64)
+    for perm in itertools.permutations(range(3)):
+        o = np.stack([CI, CJ, CK], axis=1)
+        v0 = o
+        v1 = v0 + unit[perm[0]]
+        v2 = v1 + unit[perm[1]]
+        v3 = v2 + unit[perm[2]]
+        tets.append(np.stack([vid(*v.T) for v in (v0, v1, v2, v3)], axis=1))
+    # interleave so that the 6 tets of a cube are consecutive (locality, like a real mesher)
+    idx = np.stack(tets, axis=1).reshape(-1, 4)
+    # orientation computed on the float32 coordinates the kernels will see
+    q = verts.astype(np.float64)[idx]
+    vol = np.einsum("ij,ij->i", np.cross(q[:, 1] - q[:, 0], q[:, 2] - q[:, 0]), q[:, 3] - q[:, 0])
+    flip = vol < 0
+    idx[flip] = idx[flip][:, [0, 2, 1, 3]]
+    v_adjs, e_adj6, f_adjs, f_ids, n_sf = tet_adjacency(idx, m**3)
+    return TetMesh(verts, idx.astype(np.int32), v_adjs, e_adj6, f_adjs, f_ids, n_sf)
+
+
+@dataclass
+class Sites:
+    """RPD sites in the layout of reference rpd_api.cxx:343-379: SoA x|y|z, weight = r^2."""
+
+    site_soa: np.ndarray  # float32 [3*n_site]  x.. | y.. | z..
+    weights: np.ndarray  # float32 [n_site]    r^2
+    flags: np.ndarray  # uint32  [n_site]    SiteFlag
+    radii: np.ndarray = field(default=None)  # float32 [n_site] (dist2mat uses r, not r^2)
+
+    @property
+    def n_site(self) -> int:
+        return int(self.weights.shape[0])
+
+    def centers(self) -> np.ndarray:
+        n = self.n_site
+        return np.stack([self.site_soa[:n], self.site_soa[n : 2 * n], self.site_soa[2 * n :]], axis=1)
+
+
+def make_spheres(n_site: int, seed: int = RAN_SEED, stream: int = 2, R: float = 500.0) -> Sites:
+    """Centre uniform in the ball of radius 0.9R around (500,500,500); r = (R-|c|)*U(0.5,1.0);
+    weight r^2; all sites flagged is_selected."""
+    u = uniform01(seed, 5 * n_site, stream).reshape(n_site, 5)
+    # uniform in ball: direction from normal-free method (z, phi), radius by cube root
+    z = 2.0 * u[:, 0] - 1.0
+    phi = 2.0 * np.pi * u[:, 1]
+    rad = 0.9 * R * np.cbrt(u[:, 2])
+    s = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    c = np.stack([rad * s * np.cos(phi), rad * s * np.sin(phi), rad * z], axis=1)
+    r = (R - rad) * (0.5 + 0.5 * u[:, 3])
+    c = (c + 500.0).astype(np.float32)
+    r = r.astype(np.float32)
+    site_soa = np.ascontiguousarray(c.T).ravel()
+    return Sites(site_soa, (r * r).astype(np.float32), np.ones(n_site, dtype=np.uint32), r)
+
+
+def knn_site_lists(sites: Sites, k: int) -> tuple[np.ndarray, int]:
+    """Brute-force k nearest centres per site (Euclidean), stored in the reference's
+    (site_k+1) x n_site layout: ascending site id per column, -1 padded, last row all -1
+    (reference triangulation.cxx:237-258)."""
+    from scipy.spatial import cKDTree
+
+    c = sites.centers().astype(np.float64)
+    n = c.shape[0]
+    k = min(k, n - 1)
+    _, nn = cKDTree(c).query(c, k=k + 1)
+    out = np.full((k + 1, n), -1, dtype=np.int32)
+    for s in range(n):
+        lst = nn[s]
+        lst = np.sort(lst[lst != s][:k])
+        out[: lst.size, s] = lst
+    return out, k
+
+
+def site_lists_from_sets(nbr_sets: list, n_site: int) -> tuple[np.ndarray, int]:
+    """Pack per-site neighbour collections into the (site_k+1) x n_site, -1 padded layout."""
+    site_k = max(1, max((len(s) for s in nbr_sets), default=1))
+    out = np.full((site_k + 1, n_site), -1, dtype=np.int32)
+    for s, lst in enumerate(nbr_sets):
+        a = np.sort(np.fromiter(lst, dtype=np.int32, count=len(lst)))
+        out[: a.size, s] = a
+    return out, site_k
+
+
+# --------------------------------------------------------------------------------------------
+# dist2mat
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Dist2MatInput:
+    """Buffers of compute_closest_dist2mat (reference src/dist2mat/dist2mat.h:19-24) as filled by
+    load_and_compute_sample_dist2mat_gpubuffer (reference fix_geo_error.cxx:300-387)."""
+
+    spheres: np.ndarray  # float32 [n_sph,4]  (cx,cy,cz,r)   -- r, not r^2
+    samples: np.ndarray  # float32 [n_samples,3]
+    offset: np.ndarray  # uint32 [n_samples]
+    count: np.ndarray  # uint32 [n_samples]
+    prims: np.ndarray  # int32 [n_prims,3]  (-1,-1,s) sphere / (-1,a,b) cone / (a,b,c) slab
+    n_cones: int = 0
+    n_slabs: int = 0
+
+
+def make_dist2mat(n_samples: int, nu: int = 100, nv: int = 200, seed: int = RAN_SEED,
+                  n_slabs: int = 60000, n_cones: int = 30000) -> Dist2MatInput:
+    """nu*nv spheres on a jittered sheet z = 0.15*sin-bump inside the unit box, r in U(0.02,0.08);
+    slabs = triangles of the sheet's grid triangulation, cones = grid edges (both subsampled to the
+    requested counts by the seed); per-sample list = all prims incident to the sample's 2 nearest
+    grid spheres + those 2 spheres; samples = a prim point offset along z so that the true
+    distance is near the surface.  Lists are replicated int3 runs exactly like the reference's
+    per-sample layout (fix_geo_error.cxx:300-366)."""
+    ns = nu * nv
+    u = uniform01(seed, 3 * ns, stream=11).reshape(ns, 3)
+    gi, gj = np.meshgrid(np.arange(nu), np.arange(nv), indexing="ij")
+    x = (gi.ravel() + 0.5 + 0.6 * (u[:, 0] - 0.5)) / nu
+    y = (gj.ravel() + 0.5 + 0.6 * (u[:, 1] - 0.5)) / nv
+    z = 0.5 + 0.15 * np.sin(2 * np.pi * x) * np.sin(np.pi * y)
+    r = 0.02 + 0.06 * u[:, 2]
+    spheres = np.stack([x, y, z, r], axis=1).astype(np.float32)
+
+    def sid(i, j):
+        return i * nv + j
+
+    ii, jj = [a.ravel() for a in np.meshgrid(np.arange(nu - 1), np.arange(nv - 1), indexing="ij")]
+    qa, qb, qc, qd = sid(ii, jj), sid(ii + 1, jj), sid(ii + 1, jj + 1), sid(ii, jj + 1)
+    tri = np.concatenate([np.stack(t, axis=1) for t in
+                          ((qa, qb, qc), (qa, qc, qd), (qa, qb, qd), (qb, qc, qd))])
+    e1 = np.stack([sid(ii, jj), sid(ii + 1, jj)], axis=1)
+    e2 = np.stack([sid(ii, jj), sid(ii, jj + 1)], axis=1)
+    e3 = np.stack([sid(ii, jj), sid(ii + 1, jj + 1)], axis=1)
+    edges = np.concatenate([e1, e2, e3])
+
+    def subsample(arr, want, stream):
+        if want >= arr.shape[0]:
+            return arr
+        key = splitmix64(seed, arr.shape[0], stream)
+        return arr[np.sort(np.argsort(key, kind="stable")[:want])]
+
+    tri = subsample(tri, n_slabs, 12)
+    edges = subsample(edges, n_cones, 13)
+    n_sl, n_co = tri.shape[0], edges.shape[0]
+    prim_all = np.concatenate([
+        tri,
+        np.concatenate([np.full((n_co, 1), -1, dtype=np.int64), edges], axis=1),
+    ]).astype(np.int32)
+    n_prim = prim_all.shape[0]
+    # incidence sphere -> prims (CSR)
+    inc_s = np.concatenate([tri.ravel(), edges.ravel()])
+    inc_p = np.concatenate([np.repeat(np.arange(n_sl), 3), n_sl + np.repeat(np.arange(n_co), 2)])
+    order = np.argsort(inc_s, kind="stable")
+    inc_s, inc_p = inc_s[order], inc_p[order]
+    start = np.searchsorted(inc_s, np.arange(ns + 1))
+
+    # samples
+    w = uniform01(seed, 6 * n_samples, stream=14).reshape(n_samples, 6)
+    pick = np.minimum((w[:, 0] * n_prim).astype(np.int64), n_prim - 1)
+    pr = prim_all[pick]
+    b = w[:, 1:4] + 1e-3
+    is_cone = pr[:, 0] < 0
+    b[is_cone, 0] = 0.0
+    b = b / b.sum(axis=1, keepdims=True)
+    a0 = np.where(is_cone, pr[:, 1], pr[:, 0])
+    sp = spheres.astype(np.float64)
+    base = b[:, 0:1] * sp[a0] + b[:, 1:2] * sp[pr[:, 1]] + b[:, 2:3] * sp[pr[:, 2]]
+    side = np.where(w[:, 4] < 0.5, -1.0, 1.0)
+    off = base[:, 3] + (-0.01 + 0.06 * w[:, 5])
+    samples = base[:, :3].copy()
+    samples[:, 2] += side * off
+    samples = samples.astype(np.float32)
+
+    # two nearest grid spheres of each sample (by centre, in xy-cell neighbourhood -> use KD tree)
+    from scipy.spatial import cKDTree
+
+    _, nn = cKDTree(sp[:, :3]).query(samples.astype(np.float64), k=2)
+    nn = nn.astype(np.int64)
+    cnt_a = start[nn[:, 0] + 1] - start[nn[:, 0]]
+    cnt_b = start[nn[:, 1] + 1] - start[nn[:, 1]]
+    count = (cnt_a + cnt_b + 2).astype(np.int64)
+    offset = np.concatenate([[0], np.cumsum(count)[:-1]]).astype(np.int64)
+    total = int(count.sum())
+    prims = np.empty((total, 3), dtype=np.int32)
+    # fill runs: [prims of a][prims of b][sphere a][sphere b]
+    rep = np.repeat(np.arange(n_samples), cnt_a)
+    pos = np.arange(rep.size) - np.repeat(np.cumsum(cnt_a) - cnt_a, cnt_a)
+    prims[offset[rep] + pos] = prim_all[inc_p[start[nn[rep, 0]] + pos]]
+    rep = np.repeat(np.arange(n_samples), cnt_b)
+    pos = np.arange(rep.size) - np.repeat(np.cumsum(cnt_b) - cnt_b, cnt_b)
+    prims[offset[rep] + cnt_a[rep] + pos] = prim_all[inc_p[start[nn[rep, 1]] + pos]]
+    tail = offset + cnt_a + cnt_b
+    prims[tail] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 0]], axis=1)
+    prims[tail + 1] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 1]], axis=1)
+    return Dist2MatInput(spheres, samples, offset.astype(np.uint32), count.astype(np.uint32), prims, n_co, n_sl)

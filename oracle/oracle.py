@@ -1,0 +1,221 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes access to oracle/liboracle.so (plain-C restatement) and
+oracle/_ref/*.so (the reference's own sources compiled in place).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package libmat_b200 never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# numpy view of ConvexCellTransfer (reference src/rpd3d/convex_cell.h:189-217), 3456 bytes
+RECORD_DTYPE = np.dtype({
+    "names": ["status", "thread_id", "voro_id", "tet_id", "weight", "is_active", "nb_v", "nb_p",
+              "nb_e", "ver", "clip", "id2", "edge", "euler", "cell_vol", "id"],
+    "formats": ["<i4", "<i4", "<i4", "<i4", "<f4", "u1", "u1", "u1", "u1", ("u1", (96, 4)),
+                ("<f4", (64, 8)), ("<i4", (64, 2)), ("u1", (152, 3)), "<f4", "<f4", "<i4"],
+    "offsets": [0, 4, 8, 12, 16, 20, 21, 22, 23, 24, 416, 2464, 2976, 3432, 3436, 3440],
+    "itemsize": 3456,
+})
+
+STATUS = {"early_return": -1, "triangle_overflow": 0, "vertex_overflow": 1,
+          "inconsistent_boundary": 2, "security_radius_not_reached": 3, "success": 4,
+          "needs_exact_predicates": 5, "no_intersection": 6, "edge_overflow": 7, "needs_perturb": 8}
+
+
+def _p(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _load(path):
+    if not os.path.exists(path):
+        return None
+    return C.CDLL(path)
+
+
+_oracle = None
+_refs = {}
+
+
+def lib():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-C", HERE, "oracle"], stdout=subprocess.DEVNULL)
+        _oracle = C.CDLL(path)
+        _oracle.orc_rpd_run_pairs.restype = C.c_double
+        _oracle.orc_tet_sphere_relation.restype = C.c_long
+        _oracle.orc_dist2mat.restype = C.c_double
+        for f in ("orc_distance_to_sphere", "orc_distance_to_cone", "orc_distance_to_slab"):
+            getattr(_oracle, f).restype = C.c_float
+    return _oracle
+
+
+def ref(name):
+    """name in {'rpd','host','d2m','rpd_gpu'}; returns None if the prebuilt .so is absent."""
+    if name not in _refs:
+        l = _load(os.path.join(HERE, "_ref", f"libref_{name}.so"))
+        if l is not None:
+            if name == "rpd":
+                l.ref_rpd_run_pairs.restype = C.c_double
+            if name == "d2m":
+                l.ref_d2m_run_host.restype = C.c_double
+                l.ref_d2m_run_gpu.restype = C.c_double
+                for f in ("ref_d2m_sphere", "ref_d2m_cone", "ref_d2m_slab"):
+                    getattr(l, f).restype = C.c_float
+            if name == "rpd_gpu":
+                l.ref_rpd_gpu_run.restype = C.c_long
+        _refs[name] = l
+    return _refs[name]
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def run_pairs(mesh, sites, site_knn, site_k, pair_tet, pair_site, impl="oracle", n_threads=0,
+              want_vol=False):
+    """Run the per-(tet,site) clipping of the reference kernel body on the CPU.
+    impl='oracle' -> plain-C restatement, impl='ref' -> reference sources (oracle/_ref).
+    Returns (records[RECORD_DTYPE], stat[int32], seconds[, site_vol, site_bary])."""
+    n = int(len(pair_tet))
+    recs = np.zeros(n, dtype=RECORD_DTYPE)
+    stat = np.zeros(n, dtype=np.int32)
+    verts = _c(mesh.vertices, np.float32)
+    idx = _c(mesh.indices, np.int32)
+    v_adjs = _c(mesh.v_adjs, np.int32)
+    e6 = _c(mesh.e_adj6, np.int32)
+    fa = _c(mesh.f_adjs, np.int32)
+    fi = _c(mesh.f_ids, np.int32)
+    ss = _c(sites.site_soa, np.float32)
+    sw = _c(sites.weights, np.float32)
+    sf = _c(sites.flags, np.uint32)
+    knn = _c(site_knn, np.int32)
+    pt = _c(pair_tet, np.int32)
+    ps = _c(pair_site, np.int32)
+    vol = np.zeros(sites.n_site, dtype=np.float32)
+    bary = np.zeros(3 * sites.n_site, dtype=np.float32)
+    if impl == "oracle":
+        fn = lib().orc_rpd_run_pairs
+    else:
+        r = ref("rpd")
+        if r is None:
+            raise RuntimeError("oracle/_ref/libref_rpd.so not built")
+        fn = r.ref_rpd_run_pairs
+    sec = fn(_p(verts), _p(idx), C.c_int(mesh.n_tet), _p(v_adjs), _p(e6), _p(fa), _p(fi), _p(ss),
+             _p(sw), _p(sf), C.c_int(sites.n_site), _p(knn), C.c_int(site_k), _p(pt), _p(ps),
+             C.c_long(n), _p(recs), _p(stat), _p(vol), _p(bary), C.c_int(n_threads))
+    if want_vol:
+        return recs, stat, sec, vol, bary
+    return recs, stat, sec
+
+
+def tet_sphere_relation(mesh, sites, site_knn, site_k, cap=None):
+    """a3+a4 restated: candidate (tet, site) pairs sorted by (tet, site)."""
+    cap = cap or 16 * mesh.n_tet
+    while True:
+        pt = np.empty(cap, dtype=np.int32)
+        ps = np.empty(cap, dtype=np.int32)
+        n = lib().orc_tet_sphere_relation(
+            _p(_c(mesh.vertices, np.float32)), _p(_c(mesh.indices, np.int32)), C.c_int(mesh.n_tet),
+            _p(_c(sites.site_soa, np.float32)), _p(_c(sites.weights, np.float32)),
+            _p(_c(sites.flags, np.uint32)), C.c_int(sites.n_site), _p(_c(site_knn, np.int32)),
+            C.c_int(site_k), _p(pt), _p(ps), C.c_long(cap))
+        if n >= 0:
+            return pt[:n].copy(), ps[:n].copy()
+        cap = -n
+
+
+def reload_active(recs, impl="oracle"):
+    n = len(recs)
+    recs = np.ascontiguousarray(recs)
+    ap = np.zeros((n, 64), dtype=np.uint8)
+    ae = np.zeros((n, 152), dtype=np.uint8)
+    eu = np.zeros(n, dtype=np.float32)
+    if impl == "oracle":
+        lib().orc_reload_active(_p(recs), C.c_long(n), _p(ap), _p(ae), _p(eu))
+    else:
+        ref("host").ref_host_reload_active(_p(recs), C.c_long(n), _p(ap), _p(ae), _p(eu))
+    return ap, ae, eu
+
+
+def canonicalize(recs):
+    recs = np.ascontiguousarray(recs)
+    out = np.zeros(len(recs), dtype=RECORD_DTYPE)
+    lib().orc_canonicalize(_p(recs), C.c_long(len(recs)), _p(out))
+    return out
+
+
+def vertex_coordinates(recs, impl="oracle"):
+    recs = np.ascontiguousarray(recs)
+    out = np.zeros((len(recs), 96, 4), dtype=np.float32)
+    if impl == "oracle":
+        lib().orc_vertex_coordinates(_p(recs), C.c_long(len(recs)), _p(out))
+    else:
+        ref("host").ref_host_vertex_coordinates(_p(recs), C.c_long(len(recs)), _p(out))
+    return out
+
+
+def cell_volumes(recs):
+    recs = np.ascontiguousarray(recs)
+    out = np.zeros(len(recs), dtype=np.float64)
+    lib().orc_cell_volumes(_p(recs), C.c_long(len(recs)), _p(out))
+    return out
+
+
+def defined_equal(a, b):
+    """Compare two record arrays on the DEFINED entries only (entries < nb_v/nb_p/nb_e; the
+    reference leaves the rest uninitialised).  Returns a dict of mismatch counts."""
+    assert len(a) == len(b)
+    out = {}
+    for f in ("status", "voro_id", "tet_id"):
+        out[f] = int((a[f] != b[f]).sum())
+    ok = (a["status"] == 4) & (b["status"] == 4)
+    for f in ("nb_v", "nb_p", "nb_e", "weight"):
+        out[f] = int((a[f][ok] != b[f][ok]).sum())
+    iv = np.arange(96)[None, :] < a["nb_v"][:, None]
+    ip = np.arange(64)[None, :] < a["nb_p"][:, None]
+    ie = np.arange(152)[None, :] < a["nb_e"][:, None]
+    same_n = ok & (a["nb_v"] == b["nb_v"]) & (a["nb_p"] == b["nb_p"]) & (a["nb_e"] == b["nb_e"])
+    iv &= same_n[:, None]
+    ip &= same_n[:, None]
+    ie &= same_n[:, None]
+    out["ver"] = int(((a["ver"] != b["ver"]).any(axis=2) & iv).sum())
+    # planes: bitwise compare of the 5 floats
+    ca = a["clip"][:, :, :5].view(np.uint32)
+    cb = b["clip"][:, :, :5].view(np.uint32)
+    out["clip"] = int(((ca != cb).any(axis=2) & ip).sum())
+    out["id2"] = int(((a["id2"] != b["id2"]).any(axis=2) & ip).sum())
+    out["edge"] = int(((a["edge"] != b["edge"]).any(axis=2) & ie).sum())
+    out["cells_compared"] = int(same_n.sum())
+    return out
+
+
+def dist2mat(inp, impl="oracle", n_threads=0, n=None, want_second=False):
+    n = len(inp.samples) if n is None else n
+    res = np.full(n, 1e28, dtype=np.float32)
+    cid = np.full(n, -1, dtype=np.int32)
+    sec2 = np.zeros(n, dtype=np.float32)
+    sph = _c(inp.spheres, np.float32)
+    smp = _c(inp.samples[:n], np.float32)
+    off = _c(inp.offset[:n], np.uint32)
+    cnt = _c(inp.count[:n], np.uint32)
+    pr = _c(inp.prims, np.int32)
+    if impl == "oracle":
+        t = lib().orc_dist2mat(_p(sph), _p(smp), C.c_long(n), _p(off), _p(cnt), _p(pr), _p(res),
+                               _p(cid), _p(sec2), C.c_int(n_threads))
+    else:
+        t = ref("d2m").ref_d2m_run_host(_p(sph), _p(smp), C.c_long(n), _p(off), _p(cnt), _p(pr),
+                                        _p(res), _p(cid), C.c_int(n_threads))
+    if want_second:
+        return res, cid, t, sec2
+    return res, cid, t

@@ -1,0 +1,107 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into or called from the product path.
+//
+// The reference's src/dist2mat/dist2mat.cu compiled IN PLACE (found via -I, never copied).
+// Its distance functions are __host__ __device__ (dist2mat.cu:5-193), so this TU can call them
+// on the host (IEEE, -ffp-contract=off) as the CPU oracle / CPU baseline, and on a GPU box it
+// can also run the reference's own kernel through compute_closest_dist2mat (dist2mat.cu:280-315).
+#include "dist2mat.cu"
+
+#include <omp.h>
+#include <time.h>
+
+extern "C" {
+
+float ref_d2m_sphere(const float* p, const float* s) {
+  return distance_to_sphere(make_float3(p[0], p[1], p[2]), make_float4(s[0], s[1], s[2], s[3]));
+}
+float ref_d2m_cone(const float* p, const float* a, const float* b) {
+  return compute_distance_to_cone(make_float3(p[0], p[1], p[2]), make_float4(a[0], a[1], a[2], a[3]),
+                                  make_float4(b[0], b[1], b[2], b[3]));
+}
+float ref_d2m_slab(const float* p, const float* a, const float* b, const float* c) {
+  return compute_distance_to_slab(make_float3(p[0], p[1], p[2]), make_float4(a[0], a[1], a[2], a[3]),
+                                  make_float4(b[0], b[1], b[2], b[3]),
+                                  make_float4(c[0], c[1], c[2], c[3]));
+}
+
+// Host loop over samples with the reference's distance functions and the kernel's lane/tie rule
+// (dist2mat.cu:224-276).  Returns seconds in the loop.
+double ref_d2m_run_host(const float* spheres, const float* samples, long n_samples,
+                        const unsigned* offset, const unsigned* count, const int* prims,
+                        float* result, int* closest_id, int n_threads) {
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+  const float4* sph = reinterpret_cast<const float4*>(spheres);
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (long s = 0; s < n_samples; s++) {
+    const int num_prim = (int)count[s];
+    const long off = offset[s];
+    const float3 pos = make_float3(samples[3 * s], samples[3 * s + 1], samples[3 * s + 2]);
+    float min_distance[kWarpSize];
+    int min_id[kWarpSize];
+    for (int tid = 0; tid < kWarpSize; tid++) {
+      float local_closest_dist = 1e16f;
+      int local_closest_id = -1;
+      for (int i = tid; i < num_prim && tid < num_prim; i += kWarpSize) {
+        const int* pr = prims + 3 * (off + i);
+        int3 prim = make_int3(pr[0], pr[1], pr[2]);
+        float dist = 1e16f;
+        if (prim.x == -1 && prim.y == -1)
+          dist = distance_to_sphere(pos, sph[prim.z]);
+        else if (prim.x == -1 && prim.y != -1)
+          dist = compute_distance_to_cone(pos, sph[prim.y], sph[prim.z]);
+        else if (prim.x != -1)
+          dist = compute_distance_to_slab(pos, sph[prim.x], sph[prim.y], sph[prim.z]);
+        if (dist < local_closest_dist) {
+          local_closest_dist = fminf(local_closest_dist, dist);
+          local_closest_id = i;
+        }
+      }
+      min_distance[tid] = local_closest_dist;
+      min_id[tid] = local_closest_id;
+    }
+    float reduced = min_distance[0];
+    for (int i = 1; i < kWarpSize; i++)
+      if (min_distance[i] < reduced) reduced = min_distance[i];
+    result[s] = reduced;
+    for (int i = 0; i < kWarpSize; ++i)
+      if (fabsf(min_distance[i] - reduced) < 1e-10f) closest_id[s] = min_id[i];
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+// The reference's own GPU entry point, unmodified (needs a GPU).  Returns milliseconds of the
+// whole call (H2D + kernel + D2H, like the reference times it) or <0 without a device.
+double ref_d2m_run_gpu(const float* spheres, int n_sph, const float* samples, int n_samples,
+                       const unsigned* offset, const unsigned* count, const int* prims, long n_prims,
+                       float* result, int* closest_id) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1.0;
+  GpuBuffer<float4> b_sph(n_sph);
+  GpuBuffer<float3> b_smp(n_samples);
+  GpuBuffer<uint> b_off(n_samples), b_cnt(n_samples);
+  GpuBuffer<int3> b_pr(n_prims);
+  GpuBuffer<float> b_res(n_samples);
+  GpuBuffer<int> b_id(n_samples);
+  memcpy(b_sph.HPtr(), spheres, sizeof(float4) * (size_t)n_sph);
+  memcpy(b_smp.HPtr(), samples, sizeof(float3) * (size_t)n_samples);
+  memcpy(b_off.HPtr(), offset, sizeof(uint) * (size_t)n_samples);
+  memcpy(b_cnt.HPtr(), count, sizeof(uint) * (size_t)n_samples);
+  memcpy(b_pr.HPtr(), prims, sizeof(int3) * (size_t)n_prims);
+  for (int i = 0; i < n_samples; i++) {
+    b_res.HPtr()[i] = 1e28f;  // fix_geo_error.cxx:300-366 initial fill
+    b_id.HPtr()[i] = -1;
+  }
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  compute_closest_dist2mat(b_sph, n_samples, b_smp, b_off, b_cnt, b_pr, b_res, b_id);
+  cudaDeviceSynchronize();
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  memcpy(result, b_res.HPtr(), sizeof(float) * (size_t)n_samples);
+  memcpy(closest_id, b_id.HPtr(), sizeof(int) * (size_t)n_samples);
+  return 1e3 * ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
+}
+
+}  // extern "C"

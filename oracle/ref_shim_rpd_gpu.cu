@@ -1,0 +1,94 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into or called from the product path.
+//
+// The reference's rpd3d DEVICE build: src/rpd3d/{voronoi.cu, convex_cell.cu, kNN-CUDA/knncuda.cu}
+// and src/rpd3d_base/voronoi_defs.cxx compiled IN PLACE with the reference's own flags
+// (--use_fast_math, src/rpd3d/CMakeLists.txt:9-12) plus -DNDEBUG (convex_cell.cu:1177 otherwise
+// loops n_vert per thread).  Exposes the reference's real entry point
+// compute_clipped_voro_diagram_GPU (voronoi.cu:455-795) through a C wrapper, so that on the GPU
+// box the product can be checked against -- and timed beside -- the unmodified reference.
+// Needs a GPU at run time; memory-feasible at config 1 (and marginally config 2), SURVEY section 6.
+#include "voronoi.cu"
+#include "convex_cell.cu"
+#include "knncuda.cu"
+#include "voronoi_defs.cxx"
+
+#include <time.h>
+
+#include "oracle.h"
+
+static std::vector<ConvexCellHost> g_cells;
+
+extern "C" {
+
+// returns number of cells (kept in a static vector until ref_rpd_gpu_fetch), <0 without a device.
+// ms_out: wall milliseconds of the whole call.
+long ref_rpd_gpu_run(const float* verts_aos, int n_vert, const int* idx_aos, int n_tet,
+                     const int* v_adjs, const int* e_adjs_dense, long n_e_adjs, const int* f_adjs,
+                     const int* f_ids, const float* site_soa, const float* site_w,
+                     const unsigned* site_flags, int n_site, const int* site_knn, int site_k,
+                     double* ms_out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1;
+  std::vector<float> vertices(verts_aos, verts_aos + 3 * (size_t)n_vert);
+  std::vector<int> indices(idx_aos, idx_aos + 4 * (size_t)n_tet);
+  std::map<int, std::set<int>> v2tets;
+  std::vector<int> va(v_adjs, v_adjs + n_vert), ea(e_adjs_dense, e_adjs_dense + n_e_adjs);
+  std::vector<int> fa(f_adjs, f_adjs + 4 * (size_t)n_tet), fi(f_ids, f_ids + 4 * (size_t)n_tet);
+  std::vector<float> site(site_soa, site_soa + 3 * (size_t)n_site);
+  std::vector<float> w(site_w, site_w + n_site);
+  std::vector<uint> fl(site_flags, site_flags + n_site);
+  std::vector<int> knn(site_knn, site_knn + (size_t)(site_k + 1) * n_site);
+  std::vector<float> vol;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  g_cells = compute_clipped_voro_diagram_GPU(0, vertices, indices, v2tets, va, ea, fa, fi, site,
+                                             n_site, w, fl, knn, site_k, vol, true);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (ms_out) *ms_out = 1e3 * ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
+  return (long)g_cells.size();
+}
+
+// copy the cells out in the ConvexCellTransfer layout (orc_record)
+void ref_rpd_gpu_fetch(orc_record* out) {
+  for (size_t i = 0; i < g_cells.size(); i++) {
+    const ConvexCellHost& h = g_cells[i];
+    orc_record& r = out[i];
+    memset(&r, 0, sizeof r);
+    r.status = (int)h.status;
+    r.thread_id = h.thread_id;
+    r.voro_id = h.voro_id;
+    r.tet_id = h.tet_id;
+    r.weight = h.weight;
+    r.is_active = h.is_active;
+    r.nb_v = h.nb_v;
+    r.nb_p = h.nb_p;
+    r.nb_e = h.nb_e;
+    for (int k = 0; k < h.nb_v; k++) {
+      r.ver[k][0] = h.ver_data_trans[k].x;
+      r.ver[k][1] = h.ver_data_trans[k].y;
+      r.ver[k][2] = h.ver_data_trans[k].z;
+      r.ver[k][3] = h.ver_data_trans[k].w;
+    }
+    for (int k = 0; k < h.nb_p; k++) {
+      r.clip[k].x = h.clip_data_trans[k].x;
+      r.clip[k].y = h.clip_data_trans[k].y;
+      r.clip[k].z = h.clip_data_trans[k].z;
+      r.clip[k].w = h.clip_data_trans[k].w;
+      r.clip[k].h = h.clip_data_trans[k].h;
+      r.id2[k][0] = h.clip_id2_data_trans[k].x;
+      r.id2[k][1] = h.clip_id2_data_trans[k].y;
+    }
+    for (int k = 0; k < h.nb_e; k++) {
+      r.edge[k][0] = h.edge_data[k].x;
+      r.edge[k][1] = h.edge_data[k].y;
+      r.edge[k][2] = h.edge_data[k].z;
+    }
+    r.euler = h.euler;
+    r.cell_vol = h.cell_vol;
+    r.id = h.id;
+  }
+  g_cells.clear();
+  g_cells.shrink_to_fit();
+}
+
+}  // extern "C"
