@@ -1,0 +1,177 @@
+/* libmat_b200 -- C ABI of the B200-native RPD3D + dist2mat hot path.
+ *
+ * Plain C, POD only, every size explicit.  These entry points are what LibMAT's host code binds
+ * in place of its own CUDA layer:
+ *
+ *   reference interface                                              replaced by
+ *   ---------------------------------------------------------------  ---------------------------
+ *   compute_clipped_voro_diagram_GPU  src/rpd3d/voronoi.h:52-61      mb_set_tetmesh + mb_rpd3d +
+ *     (body src/rpd3d/voronoi.cu:455-795)                            mb_rpd_count/mb_rpd_fetch_*
+ *   copy_tet_data / load_num_adjacent_cells_and_ids                  mb_set_tetmesh
+ *     src/rpd3d/voronoi.cu:324-362, 379-415
+ *   compute_tet_sphere_relation  src/rpd3d/voronoi.cu:198-322        inside mb_rpd3d (K2)
+ *   clipped_voro_cell_test_GPU_param_tet                             inside mb_rpd3d (K3)
+ *     src/rpd3d/convex_cell.cu:1166-1337
+ *   ConvexCellTransfer D2H + copy_cc  voronoi.cu:433-449, 717-769    mb_rpd_fetch_records
+ *   reload_active / get_all_voro_info                                mb_rpd_fetch_emit (K4)
+ *     src/rpd3d_base/voronoi_defs.cxx:76-106, rpd_update.cxx:112-301
+ *   compute_closest_dist2mat  src/dist2mat/dist2mat.h:19-24          mb_dist2mat
+ *     (body src/dist2mat/dist2mat.cu:280-315)
+ *
+ * The C++ shims with the reference's exact signatures live in include/libmat_b200_shim.hpp.
+ *
+ * Conventions: every function returns 0 on success or a negative mb_status; the message is
+ * available from mb_last_error().  Nothing calls exit().  Inputs are caller-owned host memory,
+ * read-only, and may be freed as soon as the call returns.  Results are library-owned handles
+ * with explicit free; bulk results use the two-call count -> fetch pattern and the caller
+ * allocates the destination.  One mb_ctx per host thread / per GPU; no global state, no files.
+ * There is NO CPU fallback: without a usable CUDA device mb_create() fails.
+ */
+#ifndef LIBMAT_B200_H
+#define LIBMAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mb_ctx mb_ctx;
+typedef struct mb_rpd_result mb_rpd_result;
+
+enum mb_status {
+  MB_OK = 0,
+  MB_ERR_CUDA = -1,     /* a CUDA runtime call failed                      */
+  MB_ERR_ARG = -2,      /* invalid argument                                */
+  MB_ERR_STATE = -3,    /* call order (e.g. mb_rpd3d before mb_set_tetmesh) */
+  MB_ERR_NOMEM = -4,    /* host or device allocation failed                */
+  MB_ERR_NODEVICE = -5  /* no CUDA device                                  */
+};
+
+/* Per-cell status values, identical to the reference enum Status
+ * (src/rpd3d_base/voronoi_common.h:10-25). */
+enum mb_cell_status {
+  MB_CELL_early_return = -1,
+  MB_CELL_triangle_overflow = 0,
+  MB_CELL_vertex_overflow = 1,
+  MB_CELL_inconsistent_boundary = 2,
+  MB_CELL_security_radius_not_reached = 3,
+  MB_CELL_success = 4,
+  MB_CELL_needs_exact_predicates = 5,
+  MB_CELL_no_intersection = 6,
+  MB_CELL_edge_overflow = 7,
+  MB_CELL_needs_perturb = 8
+};
+
+#define MB_MAX_P 64  /* _MAX_P_ */
+#define MB_MAX_T 96  /* _MAX_T_ */
+#define MB_MAX_E 152 /* _MAX_E_ */
+#define MB_RECORD_BYTES 3456 /* sizeof(ConvexCellTransfer), src/rpd3d/convex_cell.h:189-217 */
+
+/* ---------------------------------------------------------------- context */
+/* device < 0 -> current device.  Returns NULL without a CUDA device (err may receive the code). */
+mb_ctx* mb_create(int device, int* err);
+void mb_destroy(mb_ctx* ctx);
+const char* mb_last_error(const mb_ctx* ctx);
+const char* mb_version(void);
+
+/* ---------------------------------------------------------------- tet mesh (resident in HBM) */
+/* verts_aos float[3*n_vert], idx_aos int[4*n_tet] (positively oriented), v_adjs int[n_vert],
+ * f_adjs / f_ids int[4*n_tet] in tet_faces_lvid order (convex_cell.h:30-31).
+ * Edge adjacency: either e_adjs_dense (the reference's triangular table of
+ * n_vert(n_vert+1)/2+1 ints indexed by get_edge_idx, convex_cell.h:46-66) or e_adj6
+ * (6 ints per tet in the (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) local-vertex order of
+ * convex_cell.cu:194-207); exactly one may be NULL.  Partial-tet calls (rpd_api.cxx:254-281)
+ * pass the subset as idx_aos/f_adjs/f_ids with global vertices. */
+int mb_set_tetmesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int* idx_aos, int n_tet,
+                   const int* v_adjs, const int* e_adjs_dense, const int* e_adj6,
+                   const int* f_adjs, const int* f_ids);
+/* restrict subsequent mb_rpd3d calls to tets [first, first+count) (multi-GPU tet shards). */
+int mb_set_tet_range(mb_ctx* ctx, int first, int count);
+
+/* ---------------------------------------------------------------- RPD */
+typedef struct {
+  int lanes_per_cell;   /* 0 = default; 8, 16 or 32 lanes cooperate on one (tet, site) cell */
+  int grid_k;           /* grid-kNN mode: max candidate sites kept per tet (0 = default 96) */
+  int want_volumes;     /* accumulate per-site volume / barycentre sums                       */
+  int keep_on_device;   /* reserved */
+} mb_rpd_opts;
+
+/* site_soa float[3*n_site] = x.. | y.. | z.. (rpd_api.cxx:363-365), site_w float[n_site] = r^2,
+ * site_flags unsigned[n_site] (SiteFlag), site_knn int[(site_k+1)*n_site] row = slot, -1 padded
+ * (triangulation.cxx:237-258).
+ *   site_knn != NULL : given-neighbours mode = the reference's semantics: candidate (tet, site)
+ *                      pairs by the tet_sphere_relations_dev predicate, each cell clipped by
+ *                      exactly the listed neighbours in list order.
+ *   site_knn == NULL : grid-kNN mode: uniform-grid per-tet nearest-sphere search; each cell is
+ *                      clipped by the other candidates of its tet.
+ * opts may be NULL.  *out receives a result handle (free with mb_rpd_free). */
+int mb_rpd3d(mb_ctx* ctx, const float* site_soa, const float* site_w, const unsigned* site_flags,
+             int n_site, const int* site_knn, int site_k, const mb_rpd_opts* opts,
+             mb_rpd_result** out);
+
+/* The same call split in three so that a caller can keep inputs resident and time / overlap the
+ * phases: upload the sites (H2D), run all kernels on the context's stream, synchronise. */
+int mb_rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
+                        const unsigned* site_flags, int n_site, const int* site_knn, int site_k);
+int mb_rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result** out); /* async launch */
+int mb_rpd_sync(mb_ctx* ctx, mb_rpd_result* res); /* waits, reads back the counters */
+
+void mb_rpd_free(mb_rpd_result* res);
+
+/* number of valid cells (status success), candidate pairs clipped, clip_by_plane calls */
+int mb_rpd_count(const mb_rpd_result* res, long* n_cells, long* n_pairs, long* n_clips);
+/* int[10]: index = status+1 (early_return .. needs_perturb), over all candidate pairs */
+int mb_rpd_status_histogram(const mb_rpd_result* res, long hist[10]);
+/* kernel milliseconds of the last run: [0]=candidates (K1+K2) [1]=clip (K3) [2]=emit (K4)
+ * [3]=total device time, measured with CUDA events on the context's stream */
+int mb_rpd_kernel_ms(const mb_rpd_result* res, float ms[4]);
+
+/* cells sorted by (tet, site), dst = n_cells * MB_RECORD_BYTES in the ConvexCellTransfer
+ * layout; only entries < nb_v/nb_p/nb_e are defined (others zero); id = index. */
+int mb_rpd_fetch_records(mb_rpd_result* res, void* dst);
+/* the compact form: bytes needed, then the blob + per-cell byte offsets (n_cells+1 longs). */
+int mb_rpd_compact_bytes(const mb_rpd_result* res, long* n_bytes);
+int mb_rpd_fetch_compact(mb_rpd_result* res, void* blob, long* cell_offsets);
+/* per-site volume and barycentre sums (float[n_site], float[3*n_site] SoA); needs want_volumes */
+int mb_rpd_site_volumes(mb_rpd_result* res, float* vol, float* bary_sum_soa);
+/* raw device pointers of the compact result (for NCCL gathers): blob, cell_offsets(long) */
+int mb_rpd_device_buffers(mb_rpd_result* res, void** d_blob, long* n_bytes, void** d_offsets,
+                          long* n_cells);
+
+/* K4 emission (get_all_voro_info, rpd_update.cxx:112-301): counts, then SoA arrays.
+ *   facets   : cell_id, key (neighbour site id, or tet-face id), is_tet_face
+ *   vertices : cell_id, lvid, key[3] (sorted neighbour ids, -1 = surface), pos[3], surf_fid
+ *   edges    : cell_id, key[2] (sorted neighbour ids), end vertices lvid[2]
+ * max_surf_fid = sf_mesh.facets.nb()-1 (rpd_update.cxx:606). */
+typedef struct {
+  long n_facets, n_vertices, n_edges;
+} mb_emit_counts;
+int mb_rpd_emit(mb_rpd_result* res, int max_surf_fid, mb_emit_counts* counts);
+int mb_rpd_fetch_emit(mb_rpd_result* res, int* facet_cell, int* facet_key, unsigned char* facet_is_tet,
+                      int* vert_cell, int* vert_lvid, int* vert_key3, float* vert_pos3,
+                      int* vert_surf_fid, int* edge_cell, int* edge_key2, int* edge_lvid2,
+                      float* cell_euler);
+
+/* ---------------------------------------------------------------- dist2mat */
+/* spheres float[4*n_sph] = (cx,cy,cz,r) -- r, not r^2 (fix_geo_error.cxx:324-328);
+ * samples float[3*n_samples]; offset/count unsigned[n_samples]; prims int[3*n_prims]:
+ * (-1,-1,s) sphere, (-1,a,b) cone, (a,b,c) slab (dist2mat.cu:233-246).
+ * result float[n_samples], closest_id int[n_samples] = index within the sample's list
+ * (empty list -> 1e16f, -1).  tie_flag (nullable) unsigned char[n_samples]: 1 where the two best
+ * distances differ by < 1e-6 relative (the flagged-tie class). */
+int mb_dist2mat(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples, int n_samples,
+                const unsigned* offset, const unsigned* count, const int* prims, long n_prims,
+                float* result, int* closest_id, unsigned char* tie_flag);
+/* resident variant: upload once, run many times (device-only timing), fetch */
+int mb_dist2mat_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples,
+                       int n_samples, const unsigned* offset, const unsigned* count,
+                       const int* prims, long n_prims);
+int mb_dist2mat_run(mb_ctx* ctx, float* kernel_ms);
+int mb_dist2mat_fetch(mb_ctx* ctx, float* result, int* closest_id, unsigned char* tie_flag);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBMAT_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI (include/libmat_b200.h).  The shared library is built in-tree by
+libmat_b200/build.py; a missing library is an error -- there is no CPU or Python fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmat_b200.so")
+
+# every symbol include/libmat_b200.h declares
+SYMBOLS = [
+    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_set_tetmesh", "mb_set_tet_range",
+    "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
+    "mb_rpd_status_histogram", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
+    "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
+    "mb_rpd_fetch_emit", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
+]
+
+RECORD_BYTES = 3456
+# ConvexCellTransfer layout (reference src/rpd3d/convex_cell.h:189-217)
+RECORD_DTYPE = np.dtype({
+    "names": ["status", "thread_id", "voro_id", "tet_id", "weight", "is_active", "nb_v", "nb_p",
+              "nb_e", "ver", "clip", "id2", "edge", "euler", "cell_vol", "id"],
+    "formats": ["<i4", "<i4", "<i4", "<i4", "<f4", "u1", "u1", "u1", "u1", ("u1", (96, 4)),
+                ("<f4", (64, 8)), ("<i4", (64, 2)), ("u1", (152, 3)), "<f4", "<f4", "<i4"],
+    "offsets": [0, 4, 8, 12, 16, 20, 21, 22, 23, 24, 416, 2464, 2976, 3432, 3436, 3440],
+    "itemsize": RECORD_BYTES,
+})
+
+
+class RpdOpts(C.Structure):
+    _fields_ = [("lanes_per_cell", C.c_int), ("grid_k", C.c_int), ("want_volumes", C.c_int),
+                ("keep_on_device", C.c_int)]
+
+
+class EmitCounts(C.Structure):
+    _fields_ = [("n_facets", C.c_long), ("n_vertices", C.c_long), ("n_edges", C.c_long)]
+
+
+class LibMatError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libmat_b200.so; raises if it has not been built (never falls back)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibMatError(f"{LIB_PATH} is missing: run `python -m libmat_b200.build` (needs nvcc); "
+                          "libmat_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.mb_create.restype = C.c_void_p
+    lib.mb_create.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    lib.mb_destroy.argtypes = [C.c_void_p]
+    lib.mb_destroy.restype = None
+    lib.mb_last_error.restype = C.c_char_p
+    lib.mb_last_error.argtypes = [C.c_void_p]
+    lib.mb_version.restype = C.c_char_p
+    lib.mb_rpd_free.argtypes = [C.c_void_p]
+    lib.mb_rpd_free.restype = None
+    vp = C.c_void_p
+    lib.mb_set_tetmesh.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.mb_set_tet_range.argtypes = [vp, C.c_int, C.c_int]
+    lib.mb_rpd3d.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(vp)]
+    lib.mb_rpd_upload_sites.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int]
+    lib.mb_rpd_run.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.mb_rpd_sync.argtypes = [vp, vp]
+    lib.mb_rpd_count.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    lib.mb_rpd_status_histogram.argtypes = [vp, vp]
+    lib.mb_rpd_kernel_ms.argtypes = [vp, vp]
+    lib.mb_rpd_fetch_records.argtypes = [vp, vp]
+    lib.mb_rpd_compact_bytes.argtypes = [vp, C.POINTER(C.c_long)]
+    lib.mb_rpd_fetch_compact.argtypes = [vp, vp, vp]
+    lib.mb_rpd_site_volumes.argtypes = [vp, vp, vp]
+    lib.mb_rpd_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_long), C.POINTER(vp), C.POINTER(C.c_long)]
+    lib.mb_rpd_emit.argtypes = [vp, C.c_int, C.POINTER(EmitCounts)]
+    lib.mb_rpd_fetch_emit.argtypes = [vp] + [vp] * 12
+    lib.mb_dist2mat.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_long, vp, vp, vp]
+    lib.mb_dist2mat_upload.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_long]
+    lib.mb_dist2mat_run.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.mb_dist2mat_fetch.argtypes = [vp, vp, vp, vp]
+    _lib = lib
+    return lib
+
+
+def ptr(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,367 @@
+// extern "C" entry points of libmat_b200 (see include/libmat_b200.h).  Every call is wrapped so that
+// no exception and no exit() crosses the boundary (the reference exits the process on any CUDA
+// error: include/common_cuda.h:6-7, src/rpd3d/voronoi.cu:31-37, include/cuda_utils.h:18-25).
+#include <omp.h>
+
+#include <new>
+
+#include "mb_internal.h"
+#include "rpd_device.cuh"
+
+#define MB_TRY(ctx_) \
+  mb_ctx* ctx__ = (ctx_); \
+  try {
+#define MB_CATCH                                       \
+  }                                                    \
+  catch (const MbError& e) {                           \
+    if (ctx__) ctx__->err = e.msg;                     \
+    return e.code;                                     \
+  }                                                    \
+  catch (const std::bad_alloc&) {                      \
+    if (ctx__) ctx__->err = "host allocation failed";  \
+    return MB_ERR_NOMEM;                               \
+  }                                                    \
+  catch (...) {                                        \
+    if (ctx__) ctx__->err = "unknown error";           \
+    return MB_ERR_CUDA;                                \
+  }                                                    \
+  return MB_OK;
+
+extern "C" {
+
+const char* mb_version(void) { return "libmat_b200 0.1 (sm_100a)"; }
+
+mb_ctx* mb_create(int device, int* err) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    if (err) *err = MB_ERR_NODEVICE;
+    return nullptr;  // no CPU fallback
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= ndev || cudaSetDevice(device) != cudaSuccess) {
+    if (err) *err = MB_ERR_ARG;
+    return nullptr;
+  }
+  mb_ctx* ctx = new (std::nothrow) mb_ctx();
+  if (!ctx) {
+    if (err) *err = MB_ERR_NOMEM;
+    return nullptr;
+  }
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    if (err) *err = MB_ERR_CUDA;
+    return nullptr;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (err) *err = MB_OK;
+  return ctx;
+}
+
+void mb_destroy(mb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  TetMeshDev& M = ctx->mesh;
+  M.vert4.release(); M.tet_idx.release(); M.tet_fadj.release(); M.tet_fid.release(); M.tet_e6.release();
+  SitesDev& S = ctx->sites;
+  S.site4.release(); S.flags.release(); S.nbr.release(); S.knn_staging.release(); S.soa_staging.release();
+  D2MDev& D = ctx->d2m;
+  D.spheres.release(); D.samples.release(); D.offset.release(); D.count.release(); D.prims.release();
+  D.result.release(); D.closest.release(); D.tie.release();
+  ctx->tet_cnt.release(); ctx->tet_off.release(); ctx->pair_tet.release(); ctx->pair_site.release();
+  ctx->cand_pad.release(); ctx->cand_cnt.release(); ctx->word_off.release(); ctx->pair_valid.release();
+  ctx->pair_cell.release(); ctx->pair_status.release(); ctx->pair_blob.release(); ctx->pair_words.release();
+  ctx->scratch.release(); ctx->counters.release(); ctx->cub_tmp.release();
+  ctx->grid_cnt.release(); ctx->grid_off.release(); ctx->grid_sorted_id.release(); ctx->grid_cell_of.release();
+  ctx->grid_site4.release(); ctx->grid_wmax0.release(); ctx->grid_wmax1.release();
+  ctx->pin_in.release(); ctx->pin_out.release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* mb_last_error(const mb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mb_set_tetmesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int* idx_aos, int n_tet,
+                   const int* v_adjs, const int* e_adjs_dense, const int* e_adj6,
+                   const int* f_adjs, const int* f_ids) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_REQUIRE(verts_aos && idx_aos && v_adjs && f_adjs && f_ids, MB_ERR_ARG, "null mesh array");
+  MB_REQUIRE(n_vert > 0 && n_tet > 0, MB_ERR_ARG, "empty mesh");
+  MB_REQUIRE((e_adjs_dense != nullptr) != (e_adj6 != nullptr), MB_ERR_ARG,
+             "exactly one of e_adjs_dense / e_adj6 must be given");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  rpd_upload_mesh(ctx, verts_aos, n_vert, idx_aos, n_tet, v_adjs, e_adjs_dense, e_adj6, f_adjs, f_ids);
+  MB_CATCH
+}
+
+int mb_set_tet_range(mb_ctx* ctx, int first, int count) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_REQUIRE(first >= 0 && (count < 0 || first + count <= ctx->mesh.n_tet), MB_ERR_ARG, "bad tet range");
+  ctx->mesh.range_first = first;
+  ctx->mesh.range_count = count;
+  MB_CATCH
+}
+
+int mb_rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
+                        const unsigned* site_flags, int n_site, const int* site_knn, int site_k) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_REQUIRE(site_soa && site_w && site_flags && n_site > 0, MB_ERR_ARG, "bad site arrays");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  rpd_upload_sites(ctx, site_soa, site_w, site_flags, n_site, site_knn, site_k);
+  MB_CATCH
+}
+
+int mb_rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result** out) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && out, MB_ERR_ARG, "null argument");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  mb_rpd_result* res = new mb_rpd_result();
+  *out = res;
+  try {
+    rpd_run(ctx, opts, res);
+  } catch (...) {
+    mb_rpd_free(res);
+    *out = nullptr;
+    throw;
+  }
+  MB_CATCH
+}
+
+int mb_rpd_sync(mb_ctx* ctx, mb_rpd_result* res) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && res, MB_ERR_ARG, "null argument");
+  rpd_sync(ctx, res);
+  MB_CATCH
+}
+
+int mb_rpd3d(mb_ctx* ctx, const float* site_soa, const float* site_w, const unsigned* site_flags,
+             int n_site, const int* site_knn, int site_k, const mb_rpd_opts* opts,
+             mb_rpd_result** out) {
+  int rc = mb_rpd_upload_sites(ctx, site_soa, site_w, site_flags, n_site, site_knn, site_k);
+  if (rc) return rc;
+  rc = mb_rpd_run(ctx, opts, out);
+  if (rc) return rc;
+  return mb_rpd_sync(ctx, *out);
+}
+
+void mb_rpd_free(mb_rpd_result* res) {
+  if (!res) return;
+  if (res->ctx) cudaSetDevice(res->ctx->device);
+  res->blob.release(); res->cell_off.release(); res->site_vol.release(); res->site_bary.release();
+  res->f_cell.release(); res->f_key.release(); res->v_cell.release(); res->v_lvid.release();
+  res->v_key3.release(); res->v_surf.release(); res->e_cell.release(); res->e_key2.release();
+  res->e_lvid2.release(); res->f_istet.release(); res->v_pos3.release(); res->c_euler.release();
+  for (int i = 0; i < 5; i++)
+    if (res->ev[i]) cudaEventDestroy(res->ev[i]);
+  delete res;
+}
+
+int mb_rpd_count(const mb_rpd_result* res, long* n_cells, long* n_pairs, long* n_clips) {
+  if (!res) return MB_ERR_ARG;
+  if (n_cells) *n_cells = res->n_cells;
+  if (n_pairs) *n_pairs = res->n_pairs;
+  if (n_clips) *n_clips = res->n_clips;
+  return MB_OK;
+}
+
+int mb_rpd_status_histogram(const mb_rpd_result* res, long hist[10]) {
+  if (!res || !hist) return MB_ERR_ARG;
+  for (int i = 0; i < 10; i++) hist[i] = res->hist[i];
+  return MB_OK;
+}
+
+int mb_rpd_kernel_ms(const mb_rpd_result* res, float ms[4]) {
+  if (!res || !ms) return MB_ERR_ARG;
+  for (int i = 0; i < 4; i++) ms[i] = res->ms[i];
+  return MB_OK;
+}
+
+int mb_rpd_compact_bytes(const mb_rpd_result* res, long* n_bytes) {
+  if (!res || !n_bytes) return MB_ERR_ARG;
+  *n_bytes = res->compact_bytes;
+  return MB_OK;
+}
+
+int mb_rpd_fetch_compact(mb_rpd_result* res, void* blob, long* cell_offsets) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (blob && res->compact_bytes > 0)
+    MB_CUDA(cudaMemcpyAsync(blob, res->blob.p, (size_t)res->compact_bytes, cudaMemcpyDeviceToHost, s));
+  if (cell_offsets)
+    MB_CUDA(cudaMemcpyAsync(cell_offsets, res->cell_off.p, sizeof(long long) * ((size_t)res->n_cells + 1),
+                            cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  MB_CATCH
+}
+
+// host expansion of one compact record into the ConvexCellTransfer layout
+// (reference src/rpd3d/convex_cell.h:189-217; copy() convex_cell.cu:933-949)
+static void expand_record(const uint32_t* w, unsigned char* dst, int id) {
+  memset(dst, 0, MB_RECORD_BYTES);
+  const int tet = (int)w[0], site = (int)w[1];
+  const int nb_v = w[2] & 0xff, nb_p = (w[2] >> 8) & 0xff, nb_e = (w[2] >> 16) & 0xff;
+  const int status = (int)(w[2] >> 24);
+  int32_t* di = reinterpret_cast<int32_t*>(dst);
+  di[0] = status;
+  di[1] = id;        // thread_id: debug-only in the reference; the cell index here
+  di[2] = site;      // voro_id
+  di[3] = tet;       // tet_id
+  memcpy(dst + 16, &w[3], 4);  // weight
+  dst[20] = 1;       // is_active
+  dst[21] = (unsigned char)nb_v;
+  dst[22] = (unsigned char)nb_p;
+  dst[23] = (unsigned char)nb_e;
+  const uint32_t* p = w + 4;
+  memcpy(dst + 24, p, 4 * (size_t)nb_v);
+  p += nb_v;
+  const uint32_t* pl = p;
+  p += 4 * nb_p;
+  const uint32_t* meta = p;
+  p += 3 * nb_p;
+  for (int i = 0; i < nb_p; i++) {
+    memcpy(dst + 416 + 32 * i, pl + 4 * i, 16);
+    memcpy(dst + 416 + 32 * i + 16, meta + 3 * i + 2, 4);  // h
+    memcpy(dst + 2464 + 8 * i, meta + 3 * i, 8);            // id2
+  }
+  memcpy(dst + 2976, p, 3 * (size_t)nb_e);
+  const float m1 = -1.f;
+  memcpy(dst + 3432, &m1, 4);  // euler
+  memcpy(dst + 3436, &m1, 4);  // cell_vol
+  di[3440 / 4] = id;
+}
+
+int mb_rpd_fetch_records(mb_rpd_result* res, void* dst) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx && dst, MB_ERR_ARG, "null argument");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  const long n = res->n_cells;
+  if (n == 0) return MB_OK;
+  const size_t off_bytes = sizeof(long long) * ((size_t)n + 1);
+  unsigned char* pin = (unsigned char*)ctx->pin_out.reserve((size_t)res->compact_bytes + off_bytes + 16);
+  long long* offs = reinterpret_cast<long long*>(pin);
+  uint32_t* blob = reinterpret_cast<uint32_t*>(pin + ((off_bytes + 15) / 16) * 16);
+  cudaStream_t s = ctx->stream;
+  MB_CUDA(cudaMemcpyAsync(blob, res->blob.p, (size_t)res->compact_bytes, cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaMemcpyAsync(offs, res->cell_off.p, off_bytes, cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  unsigned char* out = reinterpret_cast<unsigned char*>(dst);
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; i++)
+    expand_record(blob + offs[i] / 4, out + (size_t)i * MB_RECORD_BYTES, (int)i);
+  MB_CATCH
+}
+
+int mb_rpd_site_volumes(mb_rpd_result* res, float* vol, float* bary_sum_soa) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_REQUIRE(res->want_volumes && res->site_vol.p, MB_ERR_STATE, "run with opts.want_volumes = 1");
+  cudaStream_t s = ctx->stream;
+  if (vol) MB_CUDA(cudaMemcpyAsync(vol, res->site_vol.p, sizeof(float) * (size_t)res->n_site, cudaMemcpyDeviceToHost, s));
+  if (bary_sum_soa)
+    MB_CUDA(cudaMemcpyAsync(bary_sum_soa, res->site_bary.p, sizeof(float) * 3 * (size_t)res->n_site, cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  MB_CATCH
+}
+
+int mb_rpd_device_buffers(mb_rpd_result* res, void** d_blob, long* n_bytes, void** d_offsets,
+                          long* n_cells) {
+  if (!res) return MB_ERR_ARG;
+  if (d_blob) *d_blob = res->blob.p;
+  if (n_bytes) *n_bytes = res->compact_bytes;
+  if (d_offsets) *d_offsets = res->cell_off.p;
+  if (n_cells) *n_cells = res->n_cells;
+  return MB_OK;
+}
+
+int mb_rpd_emit(mb_rpd_result* res, int max_surf_fid, mb_emit_counts* counts) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  rpd_emit(ctx, res, max_surf_fid);
+  if (counts) *counts = res->emit_counts;
+  MB_CATCH
+}
+
+#define FETCH(dst, buf, count, T)                                                                   \
+  if ((dst) && (count) > 0)                                                                         \
+  MB_CUDA(cudaMemcpyAsync((dst), (buf).p, sizeof(T) * (size_t)(count), cudaMemcpyDeviceToHost, s))
+
+int mb_rpd_fetch_emit(mb_rpd_result* res, int* facet_cell, int* facet_key, unsigned char* facet_is_tet,
+                      int* vert_cell, int* vert_lvid, int* vert_key3, float* vert_pos3,
+                      int* vert_surf_fid, int* edge_cell, int* edge_key2, int* edge_lvid2,
+                      float* cell_euler) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_REQUIRE(res->emitted, MB_ERR_STATE, "mb_rpd_emit must be called first");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const mb_emit_counts& c = res->emit_counts;
+  FETCH(facet_cell, res->f_cell, c.n_facets, int);
+  FETCH(facet_key, res->f_key, c.n_facets, int);
+  FETCH(facet_is_tet, res->f_istet, c.n_facets, unsigned char);
+  FETCH(vert_cell, res->v_cell, c.n_vertices, int);
+  FETCH(vert_lvid, res->v_lvid, c.n_vertices, int);
+  FETCH(vert_key3, res->v_key3, 3 * c.n_vertices, int);
+  FETCH(vert_pos3, res->v_pos3, 3 * c.n_vertices, float);
+  FETCH(vert_surf_fid, res->v_surf, c.n_vertices, int);
+  FETCH(edge_cell, res->e_cell, c.n_edges, int);
+  FETCH(edge_key2, res->e_key2, 2 * c.n_edges, int);
+  FETCH(edge_lvid2, res->e_lvid2, 2 * c.n_edges, int);
+  FETCH(cell_euler, res->c_euler, res->n_cells, float);
+  MB_CUDA(cudaStreamSynchronize(s));
+  MB_CATCH
+}
+
+int mb_dist2mat_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples,
+                       int n_samples, const unsigned* offset, const unsigned* count,
+                       const int* prims, long n_prims) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_REQUIRE(spheres && n_sph > 0 && n_samples >= 0 && n_prims >= 0, MB_ERR_ARG, "bad dist2mat arguments");
+  MB_REQUIRE(n_samples == 0 || (samples && offset && count), MB_ERR_ARG, "null sample arrays");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  d2m_upload(ctx, spheres, n_sph, samples, n_samples, offset, count, prims, n_prims);
+  MB_CATCH
+}
+
+int mb_dist2mat_run(mb_ctx* ctx, float* kernel_ms) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  d2m_run(ctx, kernel_ms);
+  MB_CATCH
+}
+
+int mb_dist2mat_fetch(mb_ctx* ctx, float* result, int* closest_id, unsigned char* tie_flag) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  d2m_fetch(ctx, result, closest_id, tie_flag);
+  MB_CATCH
+}
+
+int mb_dist2mat(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples, int n_samples,
+                const unsigned* offset, const unsigned* count, const int* prims, long n_prims,
+                float* result, int* closest_id, unsigned char* tie_flag) {
+  int rc = mb_dist2mat_upload(ctx, spheres, n_sph, samples, n_samples, offset, count, prims, n_prims);
+  if (rc) return rc;
+  rc = mb_dist2mat_run(ctx, nullptr);
+  if (rc) return rc;
+  return mb_dist2mat_fetch(ctx, result, closest_id, tie_flag);
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+// K5: dist2mat -- closest medial primitive (sphere / cone / slab) per sample.
+//
+// Replaces ClosestDistanceToLocalMat + compute_closest_dist2mat (reference
+// src/dist2mat/dist2mat.cu:195-315): there, one 32-thread BLOCK per sample, a cub::BlockReduce and a
+// serial lane-0 scan for the argmin, and 7 blocking H2D + 2 D2H per call.  Here: one WARP per sample
+// in a persistent grid, lanes over the sample's primitive list (same lane <-> primitive
+// assignment i = lane, lane+32, ... so the reference's tie rule is reproduced exactly), REDUX
+// warp-min on order-preserving integer keys, ballot for the "highest lane within 1e-10" winner.
+//
+// Arithmetic: this TU is compiled with -fmad=false and the default IEEE sqrt/div, and keeps the
+// reference's three double-promoted spots (dist2mat.cu:62, :89-90), so distances are bit-identical
+// to the reference's own functions built for the host, except where the reference calls
+// powf(x, 2.f) (glibc's powf is not always correctly rounded; x*x is).
+#include "mb_internal.h"
+
+namespace {
+
+struct f3 {
+  float x, y, z;
+};
+
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ float len3(f3 v) { return sqrtf(dot3(v, v)); }
+// clamp = fmaxf(a, fminf(f, b)): a NaN f becomes b (cuda_helper_math.h:932-934)
+// Written with explicit ordered compares: nvcc turns fmaxf(0, fminf(t, 1)) into a .sat modifier,
+// and .sat maps NaN to 0 whereas the reference's host build maps it to 1 (SURVEY KAT-2b).
+__device__ __forceinline__ float clampf(float f, float a, float b) {
+  const float m = (f < b) ? f : b;  // fminf(f, b): NaN f -> b
+  return (a > m) ? a : m;           // fmaxf(a, m)
+}
+// lerp(a,b,t) = b + t*(a-b) (cuda_helper_math.h:911-913)
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return b + t * (a - b); }
+__device__ __forceinline__ float sq(float x) { return x * x; }  // powf(x, 2.f)
+
+// dist2mat.cu:5-8
+__device__ __forceinline__ float d_sphere(f3 p, float4 sp) {
+  return len3(sub3(p, f3{sp.x, sp.y, sp.z})) - sp.w;
+}
+
+// dist2mat.cu:10-15
+__device__ __forceinline__ float4 bary_lerp(float4 m1, float4 m2, float4 m3, float t1, float t2) {
+  const float t3 = 1.f - t1 - t2;
+  return make_float4(m1.x * t1 + m2.x * t2 + m3.x * t3, m1.y * t1 + m2.y * t2 + m3.y * t3,
+                     m1.z * t1 + m2.z * t2 + m3.z * t3, m1.w * t1 + m2.w * t2 + m3.w * t3);
+}
+
+// dist2mat.cu:17-36
+__device__ __forceinline__ void solve_quadratic(float A, float B, float C, float& r0, float& r1) {
+  r0 = -1.f;
+  r1 = -1.f;
+  if (A == 0.f) {
+    if (B != 0.f) {
+      r0 = -C / B;
+      r1 = r0;
+    }
+  } else {
+    const float delta = B * B - 4.f * A * C;
+    if (delta < 0.f) return;
+    const float sd = sqrtf(delta);
+    r0 = (-B - sd) / (2 * A);
+    r1 = (-B + sd) / (2 * A);
+  }
+}
+
+// dist2mat.cu:38-69
+__device__ float d_cone(f3 pos, float4 m1, float4 m2) {
+  f3 c1{m1.x, m1.y, m1.z}, c2{m2.x, m2.y, m2.z};
+  float r1 = m1.w, r2 = m2.w;
+  if (r1 > r2) {
+    f3 tc = c1;
+    c1 = c2;
+    c2 = tc;
+    float tr = r1;
+    r1 = r2;
+    r2 = tr;
+  }
+  const f3 c21 = sub3(c1, c2);
+  const f3 cq2 = sub3(c2, pos);
+  const float A = dot3(c21, c21);
+  const float D = 2.f * dot3(c21, cq2);
+  const float F = dot3(cq2, cq2);
+  const float R1 = r1 - r2;
+  // the literal 4.0 promotes the radicand to double (:62)
+  const double rad = ((double)(D * D) - 4.0 * (double)A * (double)F) * (double)(R1 * R1 - A) *
+                     (double)R1 * (double)R1;
+  float t = -(A * D - R1 * R1 * D) - sqrtf((float)rad);
+  t /= 2.f * (A * A - A * R1 * R1);
+  t = clampf(t, 0.f, 1.f);
+  const f3 sp{lerpf(c1.x, c2.x, t), lerpf(c1.y, c2.y, t), lerpf(c1.z, c2.z, t)};
+  const float lr = lerpf(r1, r2, t);
+  return len3(sub3(pos, sp)) - lr;
+}
+
+// dist2mat.cu:71-193
+__device__ float d_slab(f3 pos, float4 m1, float4 m2, float4 m3) {
+  const f3 c31{m1.x - m3.x, m1.y - m3.y, m1.z - m3.z};
+  const f3 c32{m2.x - m3.x, m2.y - m3.y, m2.z - m3.z};
+  const f3 cm3{m3.x - pos.x, m3.y - pos.y, m3.z - pos.z};
+  const float R1 = m1.w - m3.w;
+  const float R2 = m2.w - m3.w;
+  const float A = dot3(c31, c31);
+  const float B = 2.f * dot3(c31, c32);
+  const float C = dot3(c32, c32);
+  const float D = 2.f * dot3(c31, cm3);
+  const float E = 2.f * dot3(c32, cm3);
+  const float F = dot3(cm3, cm3);
+  float t1 = -1.f, t2 = -1.f;
+  if (R1 == 0.f && R2 == 0.f) {
+    const float denom = 4.f * A * C - B * B;
+    t1 = (float)(((double)(B * E) - 2.0 * (double)C * (double)D) / (double)denom);
+    t2 = (float)(((double)(B * D) - 2.0 * (double)A * (double)E) / (double)denom);
+  } else if (R1 != 0.f && R2 == 0.f) {
+    const float H2 = -B / (2.f * C);
+    const float K2 = -E / (2.f * C);
+    const float W1 = sq(2.f * A + B * H2) - 4.f * R1 * R1 * (A + B * H2 + C * H2 * H2);
+    const float W2 = 2.f * (2.f * A + B * H2) * (B * K2 + D) -
+                     4.f * R1 * R1 * (B * K2 + 2.f * C * H2 * K2 + D + E * H2);
+    const float W3 = sq(B * K2 + D) - 4.f * R1 * R1 * (C * K2 * K2 + E * K2 + F);
+    float r0, r1;
+    solve_quadratic(W1, W2, W3, r0, r1);
+    const float t21 = H2 * r0 + K2;
+    const float t22 = H2 * r1 + K2;
+    const float dis = d_sphere(pos, bary_lerp(m1, m2, m3, r0, t21));
+    t1 = r0;
+    t2 = t21;
+    const float dis2 = d_sphere(pos, bary_lerp(m1, m2, m3, r1, t22));
+    if (dis2 < dis) {
+      t1 = r1;
+      t2 = t22;
+    }
+  } else if (R1 == 0.f && R2 != 0.f) {
+    const float H1 = -B / (2.f * A);
+    const float K1 = -D / (2.f * A);
+    const float W1 = sq(2.f * C + B * H1) - 4.f * R2 * R2 * (C + B * H1 + A * H1 * H1);
+    const float W2 = 2.f * (2.f * C + B * H1) * (B * K1 + E) -
+                     4.f * R2 * R2 * (B * K1 + 2.f * A * H1 * K1 + E + D * H1);
+    const float W3 = sq(B * K1 + E) - 4.f * R2 * R2 * (A * K1 * K1 + D * K1 + F);
+    float r0, r1;
+    solve_quadratic(W1, W2, W3, r0, r1);
+    const float t11 = H1 * r0 + K1;
+    const float t12 = H1 * r1 + K1;
+    const float dis = d_sphere(pos, bary_lerp(m1, m2, m3, t11, r0));
+    t1 = t11;
+    t2 = r0;
+    const float dis2 = d_sphere(pos, bary_lerp(m1, m2, m3, t12, r1));
+    if (dis2 < dis) {
+      t1 = t12;
+      t2 = r1;
+    }
+  } else {
+    const float L1 = 2.f * A * R2 - B * R1;
+    const float L2 = 2.f * C * R1 - B * R2;
+    const float L3 = E * R1 - D * R2;
+    if (L1 == 0.f && L2 != 0.f) {
+      t2 = -L3 / L2;
+      const float W1 = 4.f * A * A - 4.f * R1 * R1 * A;
+      const float W2 = 4.f * A * (B * t2 + D) - 4.f * R1 * R1 * (B * t2 + D);
+      const float W3 = sq(B * t2 + D) - (C * t2 * t2 + E * t2 + F);
+      float r0, r1;
+      solve_quadratic(W1, W2, W3, r0, r1);
+      const float dis = d_sphere(pos, bary_lerp(m1, m2, m3, r0, t2));
+      t1 = r0;
+      if (d_sphere(pos, bary_lerp(m1, m2, m3, r1, t2)) < dis) t1 = r1;
+    } else if (L1 != 0.f && L2 == 0.f) {
+      t1 = L3 / L1;
+      const float W1 = 4.f * C * C - 4.f * R2 * R2 * C;
+      const float W2 = 4.f * C * (B * t1 + E) - 4.f * R2 * R2 * (B * t1 + E);
+      const float W3 = sq(B * t1 + E) - (A * t1 * t1 + D * t1 + F);
+      float r0, r1;
+      solve_quadratic(W1, W2, W3, r0, r1);
+      const float dis = d_sphere(pos, bary_lerp(m1, m2, m3, t1, r0));
+      t2 = r0;
+      if (d_sphere(pos, bary_lerp(m1, m2, m3, t1, r1)) < dis) t2 = r1;
+    } else {
+      const float H3 = L2 / L1;
+      const float K3 = L3 / L1;
+      const float W1 = sq(2.f * C + B * H3) - 4.f * R2 * R2 * (A * H3 * H3 + B * H3 + C);
+      const float W2 = 2.f * (2.f * C + B * H3) * (B * K3 + E) -
+                       4.f * R2 * R2 * (2.f * A * H3 * K3 + B * K3 + D * H3 + E);
+      const float W3 = sq(B * K3 + E) - 4.f * R2 * R2 * (A * K3 * K3 + D * K3 + F);
+      float r0, r1;
+      solve_quadratic(W1, W2, W3, r0, r1);
+      const float t11 = H3 * r0 + K3;
+      const float t12 = H3 * r1 + K3;
+      const float dis = d_sphere(pos, bary_lerp(m1, m2, m3, t11, r0));
+      t1 = t11;
+      t2 = r0;
+      if (d_sphere(pos, bary_lerp(m1, m2, m3, t12, r1)) < dis) {
+        t1 = t12;
+        t2 = r1;
+      }
+    }
+  }
+  if ((t1 + t2) < 1.f && t1 >= 0.f && t1 <= 1.f && t2 >= 0.f && t2 <= 1.f)
+    return d_sphere(pos, bary_lerp(m1, m2, m3, t1, t2));
+  const float dis1 = d_cone(pos, m1, m3);
+  const float dis2 = d_cone(pos, m2, m3);
+  const float dis3 = d_cone(pos, m1, m2);
+  return fminf(dis1, fminf(dis2, dis3));
+}
+
+// order-preserving float -> uint key (for REDUX min)
+__device__ __forceinline__ unsigned fkey(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float funkey(unsigned k) {
+  const unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256) k_dist2mat(const float* __restrict__ samples,
+                                                  const float4* __restrict__ spheres,
+                                                  const int* __restrict__ prims,
+                                                  const unsigned* __restrict__ offsets,
+                                                  const unsigned* __restrict__ counts, int n_samples,
+                                                  float* __restrict__ result, int* __restrict__ closest_id,
+                                                  unsigned char* __restrict__ tie) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int smp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; smp < n_samples; smp += warps_per_grid) {
+    const int num_prim = (int)counts[smp];
+    const long long off = offsets[smp];
+    const f3 pos{samples[3 * (size_t)smp], samples[3 * (size_t)smp + 1], samples[3 * (size_t)smp + 2]};
+    float best = 1e16f, second = 1e16f;
+    int best_id = -1;
+    for (int i = lane; i < num_prim; i += 32) {
+      const int* pr = prims + 3 * (off + i);
+      const int px = pr[0], py = pr[1], pz = pr[2];
+      float dist = 1e16f;
+      if (px == -1 && py == -1)
+        dist = d_sphere(pos, spheres[pz]);
+      else if (px == -1)
+        dist = d_cone(pos, spheres[py], spheres[pz]);
+      else
+        dist = d_slab(pos, spheres[px], spheres[py], spheres[pz]);
+      if (dist < best) {  // first strict minimum over the lane's stride (:248-251)
+        second = best;
+        best = fminf(best, dist);
+        best_id = i;
+      } else if (dist < second)
+        second = dist;
+    }
+    const float red = funkey(__reduce_min_sync(0xffffffffu, fkey(best)));
+    // winner = HIGHEST lane whose minimum is within 1e-10 of the block minimum (:269-276)
+    const unsigned eq = __ballot_sync(0xffffffffu, fabsf(best - red) < 1e-10f);
+    const int win = 31 - __clz(eq);
+    const int win_id = __shfl_sync(0xffffffffu, best_id, win);
+    // flagged-tie class: best distance among all OTHER primitives within 1e-6 relative
+    const float other = (lane == win) ? second : best;
+    const float sec = funkey(__reduce_min_sync(0xffffffffu, fkey(other)));
+    if (lane == 0) {
+      result[smp] = red;
+      closest_id[smp] = win_id;
+      if (tie) tie[smp] = (sec - red) <= 1e-6f * fmaxf(fabsf(red), fabsf(sec)) && sec < 1e15f;
+    }
+  }
+}
+
+}  // namespace
+
+void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples, int n_samples,
+                const unsigned* offset, const unsigned* count, const int* prims, long n_prims) {
+  D2MDev& D = ctx->d2m;
+  cudaStream_t s = ctx->stream;
+  D.spheres.reserve(n_sph);
+  D.samples.reserve(3 * (size_t)n_samples);
+  D.offset.reserve(n_samples);
+  D.count.reserve(n_samples);
+  D.prims.reserve(3 * (size_t)n_prims);
+  D.result.reserve(n_samples);
+  D.closest.reserve(n_samples);
+  D.tie.reserve(n_samples);
+  MB_CUDA(cudaMemcpyAsync(D.spheres.p, spheres, sizeof(float4) * (size_t)n_sph, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(D.samples.p, samples, sizeof(float) * 3 * (size_t)n_samples, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(D.offset.p, offset, sizeof(unsigned) * (size_t)n_samples, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(D.count.p, count, sizeof(unsigned) * (size_t)n_samples, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(D.prims.p, prims, sizeof(int) * 3 * (size_t)n_prims, cudaMemcpyHostToDevice, s));
+  D.n_sph = n_sph;
+  D.n_samples = n_samples;
+  D.n_prims = n_prims;
+}
+
+void d2m_run(mb_ctx* ctx, float* kernel_ms) {
+  D2MDev& D = ctx->d2m;
+  MB_REQUIRE(D.n_samples >= 0 && D.spheres.p, MB_ERR_STATE, "mb_dist2mat_upload must be called first");
+  cudaStream_t s = ctx->stream;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (kernel_ms) {
+    MB_CUDA(cudaEventCreate(&e0));
+    MB_CUDA(cudaEventCreate(&e1));
+    MB_CUDA(cudaEventRecord(e0, s));
+  }
+  if (D.n_samples > 0) {
+    const int warps = D.n_samples;
+    long long blocks = ((long long)warps + 7) / 8;
+    blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 32);
+    k_dist2mat<<<(unsigned)blocks, 256, 0, s>>>(D.samples.p, D.spheres.p, D.prims.p, D.offset.p, D.count.p,
+                                               D.n_samples, D.result.p, D.closest.p, D.tie.p);
+    MB_CUDA(cudaGetLastError());
+  }
+  if (kernel_ms) {
+    MB_CUDA(cudaEventRecord(e1, s));
+    MB_CUDA(cudaEventSynchronize(e1));
+    MB_CUDA(cudaEventElapsedTime(kernel_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+}
+
+void d2m_fetch(mb_ctx* ctx, float* result, int* closest_id, unsigned char* tie_flag) {
+  D2MDev& D = ctx->d2m;
+  cudaStream_t s = ctx->stream;
+  if (result) MB_CUDA(cudaMemcpyAsync(result, D.result.p, sizeof(float) * (size_t)D.n_samples, cudaMemcpyDeviceToHost, s));
+  if (closest_id) MB_CUDA(cudaMemcpyAsync(closest_id, D.closest.p, sizeof(int) * (size_t)D.n_samples, cudaMemcpyDeviceToHost, s));
+  if (tie_flag) MB_CUDA(cudaMemcpyAsync(tie_flag, D.tie.p, (size_t)D.n_samples, cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+}

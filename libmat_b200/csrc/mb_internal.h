@@ -1,0 +1,184 @@
+// Internal declarations shared by the libmat_b200 translation units (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/libmat_b200.h"
+
+struct MbError {
+  int code;
+  std::string msg;
+};
+
+#define MB_CUDA(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      throw MbError{MB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + \
+                                     " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"}; \
+    }                                                                                  \
+  } while (0)
+
+#define MB_REQUIRE(cond, code, text)        \
+  do {                                      \
+    if (!(cond)) throw MbError{code, text}; \
+  } while (0)
+
+// grow-only device buffer; contents are not preserved on growth
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) MB_CUDA(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 16;
+    MB_CUDA(cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
+// pinned host staging buffer (grow-only)
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* reserve(size_t bytes) {
+    if (bytes <= cap) return p;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    MB_CUDA(cudaMallocHost(&p, bytes + bytes / 8 + 256));
+    cap = bytes + bytes / 8 + 256;
+    return p;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// ---- device-side mesh layout (HBM-resident between calls) --------------------------------
+struct TetMeshDev {
+  int n_vert = 0, n_tet = 0;
+  DevBuf<float4> vert4;    // x,y,z, w = __int_as_float(v_adj)            16 B / vertex
+  DevBuf<int4> tet_idx;    // 4 vertex ids                                16 B / tet
+  DevBuf<int4> tet_fadj;   // f_adjs (int, exact copy)                    16 B / tet
+  DevBuf<int4> tet_fid;    // f_ids                                       16 B / tet
+  DevBuf<uint2> tet_e6;    // 6 edge adjacency counts as bytes (+2 pad)    8 B / tet
+  int range_first = 0, range_count = -1;
+};
+
+struct SitesDev {
+  int n_site = 0, site_k = 0;
+  bool given = false;      // site_knn supplied
+  DevBuf<float4> site4;    // x,y,z,w=r^2
+  DevBuf<unsigned> flags;
+  DevBuf<int> nbr;         // given mode: row-major [n_site][site_k] (transposed on device)
+  DevBuf<int> knn_staging; // raw (site_k+1) x n_site upload
+  DevBuf<float> soa_staging;
+  float w_max = 0.f;
+};
+
+// counters written by the kernels (one cache line)
+struct RpdCounters {
+  unsigned long long blob_words;   // bump cursor of the compact scratch, in 4-byte words
+  unsigned long long n_clips;      // clip_by_plane calls that reached the exact predicate
+  unsigned long long n_culled;     // neighbours rejected by the bounding filter
+  unsigned long long n_valid;      // cells with status success
+  unsigned long long n_cand_overflow;
+  unsigned long long hist[10];
+  unsigned long long pad[1];
+};
+
+struct mb_rpd_result {
+  mb_ctx* ctx = nullptr;
+  long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0;
+  long hist[10] = {0};
+  long compact_bytes = 0;
+  float ms[4] = {0, 0, 0, 0};
+  int n_site = 0;
+  bool synced = false, want_volumes = false;
+  // device results (owned)
+  DevBuf<uint32_t> blob;       // ordered compact records
+  DevBuf<long long> cell_off;  // n_cells+1 byte offsets into blob
+  DevBuf<float> site_vol, site_bary;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // emission (K4)
+  bool emitted = false;
+  mb_emit_counts emit_counts = {0, 0, 0};
+  DevBuf<int> f_cell, f_key, v_cell, v_lvid, v_key3, v_surf, e_cell, e_key2, e_lvid2;
+  DevBuf<unsigned char> f_istet;
+  DevBuf<float> v_pos3, c_euler;
+};
+
+struct D2MDev {
+  int n_sph = 0, n_samples = 0;
+  long n_prims = 0;
+  DevBuf<float4> spheres;
+  DevBuf<float> samples;  // 3 floats per sample (float3 is not 16-byte aligned; read as scalars)
+  DevBuf<unsigned> offset, count;
+  DevBuf<int> prims;
+  DevBuf<float> result;
+  DevBuf<int> closest;
+  DevBuf<unsigned char> tie;
+};
+
+struct mb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+  TetMeshDev mesh;
+  SitesDev sites;
+  D2MDev d2m;
+  PinBuf pin_in, pin_out;
+  // rpd scratch (reused across calls)
+  DevBuf<int> tet_cnt, tet_off, pair_tet, pair_site, cand_pad;
+  DevBuf<int> cand_cnt;            // grid mode: #candidates per tet (cand_pad holds the lists)
+  int cand_kcap = 0;               // grid mode: row stride of cand_pad
+  DevBuf<long long> word_off;      // ordering: exclusive scan of pair_words
+  DevBuf<int> pair_valid, pair_cell;
+  DevBuf<signed char> pair_status;
+  DevBuf<long long> pair_blob;     // per pair: word offset into scratch (or -1)
+  DevBuf<int> pair_words;          // per pair: compact size in words (0 if invalid)
+  DevBuf<uint32_t> scratch;        // unordered compact records
+  DevBuf<RpdCounters> counters;
+  DevBuf<unsigned char> cub_tmp;
+  // grid (K1)
+  DevBuf<int> grid_cnt, grid_off, grid_sorted_id, grid_cell_of;
+  DevBuf<float4> grid_site4;
+  DevBuf<float> grid_wmax0, grid_wmax1;
+  float site_bbox[6] = {0, 0, 0, 0, 0, 0};  // min xyz, max xyz of the site centres (host-computed)
+};
+
+// ---- launchers implemented in rpd_kernels.cu ---------------------------------------------
+void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int* idx_aos,
+                     int n_tet, const int* v_adjs, const int* e_adjs_dense, const int* e_adj6,
+                     const int* f_adjs, const int* f_ids);
+void rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
+                      const unsigned* site_flags, int n_site, const int* site_knn, int site_k);
+void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res);
+void rpd_sync(mb_ctx* ctx, mb_rpd_result* res);
+void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
+
+// ---- dist2mat_kernels.cu -------------------------------------------------------------------
+void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples, int n_samples,
+                const unsigned* offset, const unsigned* count, const int* prims, long n_prims);
+void d2m_run(mb_ctx* ctx, float* kernel_ms);
+void d2m_fetch(mb_ctx* ctx, float* result, int* closest_id, unsigned char* tie_flag);

@@ -1,0 +1,247 @@
+// K4 (second half): stream compaction of power-cell facets, vertices and edges from the ordered
+// compact records.  Device counterpart of the per-cell part of the reference's CPU post-processing:
+//   reload_active          src/rpd3d_base/voronoi_defs.cxx:76-106
+//   cal_cell_euler         src/rpd3d_base/voronoi_defs.cxx:190-222
+//   compute_vertex_coordinates  voronoi_defs.cxx:33-74
+//   get_all_voro_info      src/rpd3d_base/rpd_update.cxx:112-301 (facet / vertex / edge keys)
+// Deterministic two-pass count -> scan -> write; items are ordered by (cell, local index).
+#include <cub/cub.cuh>
+
+#include "mb_internal.h"
+#include "rpd_device.cuh"
+
+namespace {
+
+struct CellView {
+  int tet, site, nb_v, nb_p, nb_e;
+  const uint32_t* ver;    // nb_v words (uchar4)
+  const uint32_t* plane;  // 4*nb_p words
+  const uint32_t* meta;   // 3*nb_p words: id2.x, id2.y, h
+  const unsigned char* edge;
+};
+
+__device__ __forceinline__ CellView view(const uint32_t* w) {
+  CellView c;
+  c.tet = (int)w[0];
+  c.site = (int)w[1];
+  c.nb_v = w[2] & 0xff;
+  c.nb_p = (w[2] >> 8) & 0xff;
+  c.nb_e = (w[2] >> 16) & 0xff;
+  c.ver = w + 4;
+  c.plane = c.ver + c.nb_v;
+  c.meta = c.plane + 4 * c.nb_p;
+  c.edge = reinterpret_cast<const unsigned char*>(c.meta + 3 * c.nb_p);
+  return c;
+}
+
+__device__ __forceinline__ int neigh_of(const CellView& c, int p) {
+  // neigh(plane) = (id2.x == voro_id) ? id2.y : id2.x  (rpd_update.cxx:126)
+  const int a = (int)c.meta[3 * p], b = (int)c.meta[3 * p + 1];
+  return a == c.site ? b : a;
+}
+__device__ __forceinline__ bool is_bisector(const CellView& c, int p) { return (int)c.meta[3 * p + 1] != -1; }
+
+// active planes as a 64-bit mask (a plane is active iff some vertex references it)
+__device__ __forceinline__ unsigned long long active_planes(const CellView& c) {
+  unsigned long long m = 0;
+  for (int t = 0; t < c.nb_v; t++) {
+    const uint32_t v = c.ver[t];
+    m |= 1ull << (v & 0xff);
+    m |= 1ull << ((v >> 8) & 0xff);
+    m |= 1ull << ((v >> 16) & 0xff);
+  }
+  return m;
+}
+
+// an edge is active iff both planes are active and they share >= 2 vertices; returns the two
+// smallest shared vertex ids (ascending) in v0, v1
+__device__ __forceinline__ bool edge_active(const CellView& c, unsigned long long ap, int e, int& v0, int& v1) {
+  const int a = c.edge[3 * e], b = c.edge[3 * e + 1];
+  if (!((ap >> a) & 1ull) || !((ap >> b) & 1ull)) return false;
+  int n = 0;
+  v0 = v1 = -1;
+  for (int t = 0; t < c.nb_v; t++) {
+    const uint32_t v = c.ver[t];
+    const int x = v & 0xff, y = (v >> 8) & 0xff, z = (v >> 16) & 0xff;
+    const bool ha = (x == a) | (y == a) | (z == a), hb = (x == b) | (y == b) | (z == b);
+    if (ha && hb) {
+      if (n == 0) v0 = t;
+      if (n == 1) v1 = t;
+      n++;
+    }
+  }
+  return n >= 2;
+}
+
+// vertex key: sorted neighbour ids of its bisector planes (set semantics), -1 appended when only 2
+__device__ __forceinline__ bool vertex_key(const CellView& c, int t, int max_surf_fid, int key[3], int& surf) {
+  const uint32_t v = c.ver[t];
+  const int pl[3] = {(int)(v & 0xff), (int)((v >> 8) & 0xff), (int)((v >> 16) & 0xff)};
+  int n = 0;
+  surf = -1;
+  int ks[3];
+  for (int i = 0; i < 3; i++) {
+    if (is_bisector(c, pl[i])) {
+      const int nb = neigh_of(c, pl[i]);
+      bool dup = false;
+      for (int j = 0; j < n; j++) dup |= (ks[j] == nb);
+      if (!dup) ks[n++] = nb;
+    } else {
+      const int fid = (int)c.meta[3 * pl[i]];
+      if (fid <= max_surf_fid) surf = fid;  // last one wins (rpd_update.cxx:161-163)
+    }
+  }
+  if (n < 2) return false;
+  if (n == 2) ks[n++] = -1;
+  // sort 3
+  if (ks[0] > ks[1]) { int s = ks[0]; ks[0] = ks[1]; ks[1] = s; }
+  if (ks[1] > ks[2]) { int s = ks[1]; ks[1] = ks[2]; ks[2] = s; }
+  if (ks[0] > ks[1]) { int s = ks[0]; ks[0] = ks[1]; ks[1] = s; }
+  key[0] = ks[0];
+  key[1] = ks[1];
+  key[2] = ks[2];
+  return true;
+}
+
+template <bool WRITE>
+__global__ void k_emit(const uint32_t* __restrict__ blob, const long long* __restrict__ cell_off, long n_cells,
+                       int max_surf_fid, int* __restrict__ cnt_f, int* __restrict__ cnt_v, int* __restrict__ cnt_e,
+                       const long long* __restrict__ off_f, const long long* __restrict__ off_v,
+                       const long long* __restrict__ off_e, int* __restrict__ f_cell, int* __restrict__ f_key,
+                       unsigned char* __restrict__ f_istet, int* __restrict__ v_cell, int* __restrict__ v_lvid,
+                       int* __restrict__ v_key3, float* __restrict__ v_pos3, int* __restrict__ v_surf,
+                       int* __restrict__ e_cell, int* __restrict__ e_key2, int* __restrict__ e_lvid2,
+                       float* __restrict__ c_euler) {
+  const long cell = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  const CellView c = view(blob + cell_off[cell] / 4);
+  const unsigned long long ap = active_planes(c);
+  int nf = 0, nv = 0, ne = 0;
+  long long of = 0, ov = 0, oe = 0;
+  if (WRITE) {
+    of = off_f[cell];
+    ov = off_v[cell];
+    oe = off_e[cell];
+  }
+  // facets (rpd_update.cxx:121-140)
+  for (int p = 0; p < c.nb_p; p++) {
+    if (!((ap >> p) & 1ull)) continue;
+    if (WRITE) {
+      const bool bis = is_bisector(c, p);
+      f_cell[of + nf] = (int)cell;
+      f_key[of + nf] = bis ? neigh_of(c, p) : (int)c.meta[3 * p];
+      f_istet[of + nf] = bis ? 0 : 1;
+    }
+    nf++;
+  }
+  // vertices (rpd_update.cxx:147-191)
+  for (int t = 0; t < c.nb_v; t++) {
+    int key[3], surf;
+    if (!vertex_key(c, t, max_surf_fid, key, surf)) continue;
+    if (WRITE) {
+      const uint32_t v = c.ver[t];
+      const float* P = reinterpret_cast<const float*>(c.plane);
+      const float* p1 = P + 4 * (v & 0xff);
+      const float* p2 = P + 4 * ((v >> 8) & 0xff);
+      const float* p3 = P + 4 * ((v >> 16) & 0xff);
+      // compute_vertex_coordinates, voronoi_defs.cxx:33-49 (exact float operation order)
+      const float rx = -det3_exact(p1[3], p1[1], p1[2], p2[3], p2[1], p2[2], p3[3], p3[1], p3[2]);
+      const float ry = -det3_exact(p1[0], p1[3], p1[2], p2[0], p2[3], p2[2], p3[0], p3[3], p3[2]);
+      const float rz = -det3_exact(p1[0], p1[1], p1[3], p2[0], p2[1], p2[3], p3[0], p3[1], p3[3]);
+      const float rw = det3_exact(p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+      v_cell[ov + nv] = (int)cell;
+      v_lvid[ov + nv] = t;
+      v_key3[3 * (ov + nv) + 0] = key[0];
+      v_key3[3 * (ov + nv) + 1] = key[1];
+      v_key3[3 * (ov + nv) + 2] = key[2];
+      v_pos3[3 * (ov + nv) + 0] = __fdiv_rn(rx, rw);
+      v_pos3[3 * (ov + nv) + 1] = __fdiv_rn(ry, rw);
+      v_pos3[3 * (ov + nv) + 2] = __fdiv_rn(rz, rw);
+      v_surf[ov + nv] = surf;
+    }
+    nv++;
+  }
+  // edges between two bisectors (rpd_update.cxx:195-200, 261-295) + Euler edge sum
+  double sum_e = 0.0;
+  for (int e = 0; e < c.nb_e; e++) {
+    int v0, v1;
+    if (!edge_active(c, ap, e, v0, v1)) continue;
+    if (WRITE) sum_e += 1. / (double)c.edge[3 * e + 2];
+    const int a = c.edge[3 * e], b = c.edge[3 * e + 1];
+    if (!is_bisector(c, a) || !is_bisector(c, b)) continue;
+    if (WRITE) {
+      int k0 = neigh_of(c, a), k1 = neigh_of(c, b);
+      if (k0 > k1) { int s = k0; k0 = k1; k1 = s; }
+      e_cell[oe + ne] = (int)cell;
+      e_key2[2 * (oe + ne) + 0] = k0;
+      e_key2[2 * (oe + ne) + 1] = k1;
+      e_lvid2[2 * (oe + ne) + 0] = v0;
+      e_lvid2[2 * (oe + ne) + 1] = v1;
+    }
+    ne++;
+  }
+  if (WRITE) {
+    // cal_cell_euler (voronoi_defs.cxx:190-222): Scalar = double accumulators, float result
+    double sum_v = 0.0, sum_f = 0.0;
+    for (int t = 0; t < c.nb_v; t++) sum_v += (double)__fdiv_rn(1.f, (float)(int)(c.ver[t] >> 24));
+    for (int p = 0; p < c.nb_p; p++)
+      if ((ap >> p) & 1ull) sum_f += 1. / (double)__uint_as_float(c.meta[3 * p + 2]);
+    c_euler[cell] = (float)(sum_v - sum_e + sum_f);
+  } else {
+    cnt_f[cell] = nf;
+    cnt_v[cell] = nv;
+    cnt_e[cell] = ne;
+  }
+}
+
+void scan_ll(mb_ctx* ctx, const int* in, long long* out, long n) {
+  size_t tmp = 0;
+  MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, ctx->stream));
+  ctx->cub_tmp.reserve(tmp);
+  MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, out, n, ctx->stream));
+}
+
+}  // namespace
+
+void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid) {
+  cudaStream_t s = ctx->stream;
+  const long n = res->n_cells;
+  res->emit_counts = {0, 0, 0};
+  res->emitted = true;
+  if (n == 0) return;
+  DevBuf<int> cf, cv, ce;
+  DevBuf<long long> of, ov, oe;
+  cf.reserve(n + 1); cv.reserve(n + 1); ce.reserve(n + 1);
+  of.reserve(n + 1); ov.reserve(n + 1); oe.reserve(n + 1);
+  MB_CUDA(cudaMemsetAsync(cf.p + n, 0, sizeof(int), s));
+  MB_CUDA(cudaMemsetAsync(cv.p + n, 0, sizeof(int), s));
+  MB_CUDA(cudaMemsetAsync(ce.p + n, 0, sizeof(int), s));
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  k_emit<false><<<blocks, 128, 0, s>>>(res->blob.p, res->cell_off.p, n, max_surf_fid, cf.p, cv.p, ce.p, nullptr,
+                                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  MB_CUDA(cudaGetLastError());
+  scan_ll(ctx, cf.p, of.p, n + 1);
+  scan_ll(ctx, cv.p, ov.p, n + 1);
+  scan_ll(ctx, ce.p, oe.p, n + 1);
+  long long tot[3];
+  MB_CUDA(cudaMemcpyAsync(&tot[0], of.p + n, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaMemcpyAsync(&tot[1], ov.p + n, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaMemcpyAsync(&tot[2], oe.p + n, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  res->emit_counts.n_facets = (long)tot[0];
+  res->emit_counts.n_vertices = (long)tot[1];
+  res->emit_counts.n_edges = (long)tot[2];
+  res->f_cell.reserve(tot[0] + 1); res->f_key.reserve(tot[0] + 1); res->f_istet.reserve(tot[0] + 1);
+  res->v_cell.reserve(tot[1] + 1); res->v_lvid.reserve(tot[1] + 1); res->v_key3.reserve(3 * tot[1] + 1);
+  res->v_pos3.reserve(3 * tot[1] + 1); res->v_surf.reserve(tot[1] + 1);
+  res->e_cell.reserve(tot[2] + 1); res->e_key2.reserve(2 * tot[2] + 1); res->e_lvid2.reserve(2 * tot[2] + 1);
+  res->c_euler.reserve(n + 1);
+  k_emit<true><<<blocks, 128, 0, s>>>(res->blob.p, res->cell_off.p, n, max_surf_fid, nullptr, nullptr, nullptr,
+                                      of.p, ov.p, oe.p, res->f_cell.p, res->f_key.p, res->f_istet.p,
+                                      res->v_cell.p, res->v_lvid.p, res->v_key3.p, res->v_pos3.p, res->v_surf.p,
+                                      res->e_cell.p, res->e_key2.p, res->e_lvid2.p, res->c_euler.p);
+  MB_CUDA(cudaGetLastError());
+  MB_CUDA(cudaStreamSynchronize(s));
+  cf.release(); cv.release(); ce.release(); of.release(); ov.release(); oe.release();
+}

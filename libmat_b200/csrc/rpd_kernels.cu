@@ -1,0 +1,526 @@
+// RPD3D device pipeline: mesh / site upload, candidate generation (K1/K2), clipping (K3),
+// ordering + compaction (first half of K4).  Host orchestration on one CUDA stream.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+
+#include "mb_internal.h"
+#include "rpd_clip.cuh"
+#include "rpd_grid.cuh"
+
+// =============================================================================================
+// uploads
+// =============================================================================================
+// closed form of get_edge_idx (reference src/rpd3d/convex_cell.h:46-59)
+static inline long long edge_idx_closed(long long v1, long long v2, long long n) {
+  long long vmin = std::min(v1, v2), vmax = std::max(v1, v2);
+  return (vmin + 1) * n - vmin * (vmin + 1) / 2 - (n - vmax);
+}
+
+void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int* idx_aos,
+                     int n_tet, const int* v_adjs, const int* e_adjs_dense, const int* e_adj6,
+                     const int* f_adjs, const int* f_ids) {
+  TetMeshDev& M = ctx->mesh;
+  M.vert4.reserve(n_vert);
+  M.tet_idx.reserve(n_tet);
+  M.tet_fadj.reserve(n_tet);
+  M.tet_fid.reserve(n_tet);
+  M.tet_e6.reserve(n_tet);
+  // pack on the host into pinned memory (replaces copy_tet_data voronoi.cu:324-362 and
+  // load_num_adjacent_cells_and_ids :379-415: no pitched SoA, no dense e_adjs on the device)
+  const size_t bytes_v = sizeof(float4) * (size_t)n_vert;
+  const size_t bytes_e = sizeof(uint2) * (size_t)n_tet;
+  unsigned char* pin = (unsigned char*)ctx->pin_in.reserve(bytes_v + bytes_e);
+  float4* hv = (float4*)pin;
+  uint2* he = (uint2*)(pin + bytes_v);
+  for (int v = 0; v < n_vert; v++) {
+    float w;
+    int a = v_adjs[v];
+    memcpy(&w, &a, 4);
+    hv[v] = make_float4(verts_aos[3 * (size_t)v], verts_aos[3 * (size_t)v + 1],
+                        verts_aos[3 * (size_t)v + 2], w);
+  }
+  static const int ep[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+  for (int t = 0; t < n_tet; t++) {
+    unsigned long long pk = 0;
+    for (int e = 0; e < 6; e++) {
+      int val;
+      if (e_adj6)
+        val = e_adj6[6 * (size_t)t + e];
+      else
+        val = e_adjs_dense[edge_idx_closed(idx_aos[4 * (size_t)t + ep[e][0]],
+                                           idx_aos[4 * (size_t)t + ep[e][1]], n_vert)];
+      pk |= (unsigned long long)((unsigned char)val) << (8 * e);  // make_uchar3(.., e_adj) truncation
+    }
+    he[t] = make_uint2((unsigned)(pk & 0xffffffffull), (unsigned)(pk >> 32));
+  }
+  cudaStream_t s = ctx->stream;
+  MB_CUDA(cudaMemcpyAsync(M.vert4.p, hv, bytes_v, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(M.tet_e6.p, he, bytes_e, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(M.tet_idx.p, idx_aos, sizeof(int4) * (size_t)n_tet, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(M.tet_fadj.p, f_adjs, sizeof(int4) * (size_t)n_tet, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(M.tet_fid.p, f_ids, sizeof(int4) * (size_t)n_tet, cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  M.n_vert = n_vert;
+  M.n_tet = n_tet;
+  M.range_first = 0;
+  M.range_count = -1;
+}
+
+// SoA x|y|z + w -> float4; (site_k+1) x n_site slot-major knn -> row-major [n_site][site_k]
+__global__ void k_prep_sites(const float* __restrict__ soa, const float* __restrict__ w, int n_site,
+                             float4* __restrict__ site4) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_site) site4[s] = make_float4(soa[s], soa[s + n_site], soa[s + 2 * (size_t)n_site], w[s]);
+}
+
+__global__ void k_transpose_knn(const int* __restrict__ knn, int n_site, int site_k,
+                                int* __restrict__ nbr) {
+  __shared__ int tile[32][33];
+  // in: [slot][site], out: [site][slot]
+  int s0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int k = k0 + r, s = s0 + threadIdx.x;
+    tile[r][threadIdx.x] = (k < site_k && s < n_site) ? knn[(size_t)k * n_site + s] : -1;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int s = s0 + r, k = k0 + threadIdx.x;
+    if (s < n_site && k < site_k) nbr[(size_t)s * site_k + k] = tile[threadIdx.x][r];
+  }
+}
+
+void rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
+                      const unsigned* site_flags, int n_site, const int* site_knn, int site_k) {
+  SitesDev& S = ctx->sites;
+  cudaStream_t s = ctx->stream;
+  S.site4.reserve(n_site);
+  S.flags.reserve(n_site);
+  S.soa_staging.reserve(4 * (size_t)n_site);
+  MB_CUDA(cudaMemcpyAsync(S.soa_staging.p, site_soa, sizeof(float) * 3 * (size_t)n_site,
+                          cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(S.soa_staging.p + 3 * (size_t)n_site, site_w, sizeof(float) * (size_t)n_site,
+                          cudaMemcpyHostToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(S.flags.p, site_flags, sizeof(unsigned) * (size_t)n_site,
+                          cudaMemcpyHostToDevice, s));
+  k_prep_sites<<<(n_site + 255) / 256, 256, 0, s>>>(S.soa_staging.p, S.soa_staging.p + 3 * (size_t)n_site,
+                                                    n_site, S.site4.p);
+  S.given = site_knn != nullptr;
+  S.site_k = site_k;
+  if (S.given) {
+    MB_REQUIRE(site_k > 0, MB_ERR_ARG, "site_k must be > 0 when site_knn is given");
+    S.knn_staging.reserve((size_t)(site_k + 1) * n_site);
+    S.nbr.reserve((size_t)site_k * n_site);
+    // the last row (slot site_k) is always -1 and never read (triangulation.cxx:245-256,
+    // convex_cell.cu:1225,1255): only rows 0..site_k-1 are uploaded
+    MB_CUDA(cudaMemcpyAsync(S.knn_staging.p, site_knn, sizeof(int) * (size_t)site_k * n_site,
+                            cudaMemcpyHostToDevice, s));
+    dim3 grid((n_site + 31) / 32, (site_k + 31) / 32), block(32, 8);
+    k_transpose_knn<<<grid, block, 0, s>>>(S.knn_staging.p, n_site, site_k, S.nbr.p);
+  }
+  float wmax = 0.f;
+  float* bb = ctx->site_bbox;
+  bb[0] = bb[1] = bb[2] = INFINITY;
+  bb[3] = bb[4] = bb[5] = -INFINITY;
+  for (int i = 0; i < n_site; i++) {
+    wmax = std::max(wmax, site_w[i]);
+    for (int c = 0; c < 3; c++) {
+      const float v = site_soa[(size_t)c * n_site + i];
+      bb[c] = std::min(bb[c], v);
+      bb[3 + c] = std::max(bb[3 + c], v);
+    }
+  }
+  S.w_max = wmax;
+  S.n_site = n_site;
+  MB_CUDA(cudaGetLastError());
+}
+
+// =============================================================================================
+// K2 (given-neighbours mode): the tet-sphere relation of the reference, evaluated sparsely.
+//   reference: compute_distances + dist_minus_weight (kNN-CUDA/knncuda.cu:21-94,130-160) build a
+//   dense n_site x n_vert matrix, tet_sphere_relations_dev (voronoi.cu:154-193) a dense
+//   n_site x n_tet matrix, both copied to the host and compacted there (:266-317).
+//   here: one warp per tet, lanes over sites, early exit over the neighbour list, ballot-ordered
+//   compaction -> per-tet candidate lists in ascending site id (the reference's tet_knn order).
+// =============================================================================================
+__device__ __forceinline__ float pdist_exact(float4 S, float4 p) {
+  // ssd = ((dx*dx + dy*dy) + dz*dz) - w with dx = site - vertex (knncuda.cu:78-81, :153-156)
+  const float dx = xfsub(S.x, p.x), dy = xfsub(S.y, p.y), dz = xfsub(S.z, p.z);
+  const float ssd = xfadd(xfadd(xfadd(0.f, xfmul(dx, dx)), xfmul(dy, dy)), xfmul(dz, dz));
+  return xfsub(ssd, S.w);
+}
+
+__device__ __forceinline__ bool relate_exact(const float4* __restrict__ site4,
+                                             const unsigned* __restrict__ flags,
+                                             const int* __restrict__ nbr, int site_k, int s,
+                                             const float4* p) {
+  if (flags[s] != 1u) return false;  // SiteFlag::is_selected, voronoi.cu:165-169
+  const float4 S = site4[s];
+  float pd_i[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++) pd_i[l] = pdist_exact(S, p[l]);
+  const int* row = nbr + (size_t)s * site_k;
+  for (int sm = 0; sm < site_k; sm++) {
+    const int m = row[sm];
+    if (m == -1) continue;  // voronoi.cu:175
+    const float4 Mq = site4[m];
+    bool any = false;
+#pragma unroll
+    for (int l = 0; l < 4; l++) any = any || (pdist_exact(Mq, p[l]) > pd_i[l]);
+    if (!any) return false;
+  }
+  return true;
+}
+
+#define CAND_PAD 32
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_cand_given(const float4* __restrict__ vert4,
+                                                    const int4* __restrict__ tet_idx, int tet_first,
+                                                    int tet_count, const float4* __restrict__ site4,
+                                                    const unsigned* __restrict__ flags, int n_site,
+                                                    const int* __restrict__ nbr, int site_k,
+                                                    int* __restrict__ tet_cnt, int* __restrict__ cand_pad,
+                                                    const int* __restrict__ tet_off,
+                                                    int* __restrict__ pair_tet, int* __restrict__ pair_site) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= tet_count) return;
+  const int t = tet_first + warp;
+  int count = 0;
+  if (FILL) {
+    // second pass: copy the padded list, or recompute when it overflowed CAND_PAD
+    const int n = tet_cnt[warp];
+    const int off = tet_off[warp];
+    if (n <= CAND_PAD) {
+      if (lane < n) {
+        pair_tet[off + lane] = t;
+        pair_site[off + lane] = cand_pad[(size_t)warp * CAND_PAD + lane];
+      }
+      return;
+    }
+  }
+  const int4 vi = tet_idx[t];
+  const float4 p[4] = {vert4[vi.x], vert4[vi.y], vert4[vi.z], vert4[vi.w]};
+  for (int base = 0; base < n_site; base += 32) {
+    const int s = base + lane;
+    const bool ok = (s < n_site) && relate_exact(site4, flags, nbr, site_k, s, p);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int pos = count + __popc(m & ((1u << lane) - 1u));
+      if (FILL) {
+        const int off = tet_off[warp];
+        pair_tet[off + pos] = t;
+        pair_site[off + pos] = s;
+      } else if (pos < CAND_PAD) {
+        cand_pad[(size_t)warp * CAND_PAD + pos] = s;
+      }
+    }
+    count += __popc(m);
+  }
+  if (!FILL && lane == 0) tet_cnt[warp] = count;
+}
+
+// =============================================================================================
+// ordering + compaction: records leave K3 in arbitrary order in the scratch; two exclusive scans
+// (record words, valid flags) give each valid cell its slot in (tet, site) order.
+// =============================================================================================
+__global__ void k_valid_flags(const int* __restrict__ pair_words, long long n, int* __restrict__ valid) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) valid[i] = pair_words[i] > 0;
+}
+
+__global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* __restrict__ pair_blob,
+                         const int* __restrict__ pair_words, const long long* __restrict__ word_off,
+                         const int* __restrict__ cell_idx, long long n_pairs,
+                         uint32_t* __restrict__ blob, long long* __restrict__ cell_off,
+                         long long total_words, long long n_cells) {
+  // 8 lanes per record
+  const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int lane = threadIdx.x & 7;
+  if (g >= n_pairs) return;
+  const int words = pair_words[g];
+  if (words == 0) return;
+  const long long dst = word_off[g];
+  const uint32_t* src = scratch + pair_blob[g];
+  for (int i = lane; i < words; i += 8) blob[dst + i] = src[i];
+  if (lane == 0) {
+    const int c = cell_idx[g];
+    cell_off[c] = dst * 4;
+    if (c == n_cells - 1) cell_off[n_cells] = total_words * 4;
+  }
+}
+
+
+// =============================================================================================
+// K1 host side: grid build (counting sort by cell + max-weight pyramid), K2 launch
+// =============================================================================================
+static GridDev grid_build(mb_ctx* ctx) {
+  SitesDev& S = ctx->sites;
+  cudaStream_t s = ctx->stream;
+  GridDev G;
+  int R = (int)std::ceil(std::cbrt(std::max(1.0, S.n_site / 2.0)));
+  R = ((R + 3) / 4) * 4;
+  R = std::max(4, std::min(128, R));
+  G.R = R;
+  G.R1 = R / 4;
+  const float* bb = ctx->site_bbox;
+  const float ext = std::max(std::max(bb[3] - bb[0], bb[4] - bb[1]), std::max(bb[5] - bb[2], 1e-3f));
+  G.h = ext * 1.0001f / R;
+  G.inv_h = 1.f / G.h;
+  G.minx = bb[0];
+  G.miny = bb[1];
+  G.minz = bb[2];
+  const int nc = R * R * R, n1 = G.R1 * G.R1 * G.R1;
+  ctx->grid_cnt.reserve((size_t)nc + 1);
+  ctx->grid_off.reserve((size_t)nc + 1);
+  ctx->grid_cell_of.reserve(S.n_site);
+  ctx->grid_sorted_id.reserve(S.n_site);
+  ctx->grid_site4.reserve(S.n_site);
+  ctx->grid_wmax0.reserve(nc);
+  ctx->grid_wmax1.reserve(n1);
+  MB_CUDA(cudaMemsetAsync(ctx->grid_cnt.p, 0, sizeof(int) * ((size_t)nc + 1), s));
+  k_grid_count<<<(S.n_site + 255) / 256, 256, 0, s>>>(S.site4.p, S.n_site, G, ctx->grid_cnt.p, ctx->grid_cell_of.p);
+  {
+    size_t tmp = 0;
+    MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->grid_cnt.p, ctx->grid_off.p, nc + 1, s));
+    ctx->cub_tmp.reserve(tmp);
+    MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, ctx->grid_cnt.p, ctx->grid_off.p, nc + 1, s));
+  }
+  MB_CUDA(cudaMemsetAsync(ctx->grid_cnt.p, 0, sizeof(int) * ((size_t)nc + 1), s));
+  k_grid_scatter<<<(S.n_site + 255) / 256, 256, 0, s>>>(S.site4.p, S.n_site, ctx->grid_cell_of.p,
+                                                        ctx->grid_off.p, ctx->grid_cnt.p, ctx->grid_sorted_id.p);
+  k_grid_finalize<<<(nc + 127) / 128, 128, 0, s>>>(S.site4.p, ctx->grid_off.p, nc, ctx->grid_sorted_id.p,
+                                                   ctx->grid_site4.p, ctx->grid_wmax0.p);
+  k_grid_pyramid<<<(n1 + 127) / 128, 128, 0, s>>>(ctx->grid_wmax0.p, R, G.R1, ctx->grid_wmax1.p);
+  MB_CUDA(cudaGetLastError());
+  G.site4 = ctx->grid_site4.p;
+  G.sorted_id = ctx->grid_sorted_id.p;
+  G.cell_off = ctx->grid_off.p;
+  G.wmax0 = ctx->grid_wmax0.p;
+  G.wmax1 = ctx->grid_wmax1.p;
+  return G;
+}
+
+// fills cand_pad / cand_cnt (all candidates) and tet_cnt (flagged candidates = pairs)
+static void grid_candidates(mb_ctx* ctx, int t_first, int t_count, int grid_k) {
+  TetMeshDev& M = ctx->mesh;
+  SitesDev& S = ctx->sites;
+  cudaStream_t s = ctx->stream;
+  GridDev G = grid_build(ctx);
+  const int kcap = (grid_k > 96) ? 256 : 96;
+  ctx->cand_kcap = kcap;
+  ctx->cand_pad.reserve((size_t)t_count * kcap);
+  ctx->cand_cnt.reserve((size_t)t_count + 1);
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->counters.p);
+  const int blocks = (t_count + 3) / 4;
+  if (kcap == 96)
+    k_grid_candidates<96><<<blocks, 128, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, G, S.flags.p,
+                                                 ctx->cand_pad.p, ctx->cand_cnt.p, ctx->tet_cnt.p, cnt);
+  else
+    k_grid_candidates<256><<<blocks, 128, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, G, S.flags.p,
+                                                  ctx->cand_pad.p, ctx->cand_cnt.p, ctx->tet_cnt.p, cnt);
+  MB_CUDA(cudaGetLastError());
+}
+
+static void grid_fill_pairs(mb_ctx* ctx, int t_first, int t_count, long long n_pairs) {
+  (void)n_pairs;
+  cudaStream_t s = ctx->stream;
+  const int blocks = (t_count + 7) / 8;
+  k_grid_fill<<<blocks, 256, 0, s>>>(t_first, t_count, ctx->cand_kcap, ctx->cand_pad.p, ctx->cand_cnt.p,
+                                     ctx->tet_off.p, ctx->sites.flags.p, ctx->pair_tet.p, ctx->pair_site.p);
+  MB_CUDA(cudaGetLastError());
+}
+
+// =============================================================================================
+// host orchestration
+// =============================================================================================
+template <typename T>
+static void exclusive_scan(mb_ctx* ctx, const int* in, T* out, long long n) {
+  size_t tmp = 0;
+  MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, ctx->stream));
+  ctx->cub_tmp.reserve(tmp);
+  MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, out, n, ctx->stream));
+}
+
+template <int G>
+static void launch_clip(mb_ctx* ctx, const ClipArgs& A) {
+  constexpr int groups = 128 / G;
+  const size_t smem = sizeof(CellS) * groups;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MB_CUDA(cudaFuncSetAttribute(k_clip<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int per_sm = 0;
+  MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip<G>, 128, smem));
+  if (per_sm < 1) per_sm = 1;
+  // persistent-style grid: a multiple of the SM count, grid-stride over pairs
+  long long want = (A.n_pairs + groups - 1) / groups;
+  long long grid = std::min<long long>(want, (long long)ctx->sm_count * per_sm * 4);
+  if (grid < 1) grid = 1;
+  k_clip<G><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
+  MB_CUDA(cudaGetLastError());
+}
+
+void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
+  TetMeshDev& M = ctx->mesh;
+  SitesDev& S = ctx->sites;
+  cudaStream_t s = ctx->stream;
+  MB_REQUIRE(M.n_tet > 0, MB_ERR_STATE, "mb_set_tetmesh must be called before mb_rpd3d");
+  MB_REQUIRE(S.n_site > 0, MB_ERR_STATE, "no sites uploaded");
+  const int t_first = M.range_first;
+  const int t_count = M.range_count < 0 ? M.n_tet - t_first : M.range_count;
+  MB_REQUIRE(t_first >= 0 && t_count >= 0 && t_first + t_count <= M.n_tet, MB_ERR_ARG, "bad tet range");
+  int G = opts && opts->lanes_per_cell ? opts->lanes_per_cell : 8;
+  MB_REQUIRE(G == 8 || G == 16 || G == 32, MB_ERR_ARG, "lanes_per_cell must be 8, 16 or 32");
+  res->ctx = ctx;
+  res->n_site = S.n_site;
+  res->want_volumes = opts && opts->want_volumes;
+  for (int i = 0; i < 5; i++)
+    if (!res->ev[i]) MB_CUDA(cudaEventCreate(&res->ev[i]));
+  ctx->counters.reserve(1);
+  MB_CUDA(cudaMemsetAsync(ctx->counters.p, 0, sizeof(RpdCounters), s));
+  MB_CUDA(cudaEventRecord(res->ev[0], s));
+
+  // ---- K1/K2: candidate (tet, site) pairs ----------------------------------------------------
+  long long n_pairs = 0;
+  ctx->tet_cnt.reserve((size_t)t_count + 1);
+  ctx->tet_off.reserve((size_t)t_count + 1);
+  if (t_count > 0) {
+    if (S.given) {
+      ctx->cand_pad.reserve((size_t)t_count * CAND_PAD);
+      const int blocks = (t_count + 7) / 8;
+      k_cand_given<false><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, S.site4.p,
+                                                 S.flags.p, S.n_site, S.nbr.p, S.site_k, ctx->tet_cnt.p,
+                                                 ctx->cand_pad.p, nullptr, nullptr, nullptr);
+      MB_CUDA(cudaGetLastError());
+    } else {
+      grid_candidates(ctx, t_first, t_count, opts ? opts->grid_k : 0);  // fills tet_cnt + cand_list pad
+    }
+    MB_CUDA(cudaMemsetAsync(ctx->tet_cnt.p + t_count, 0, sizeof(int), s));
+    exclusive_scan<int>(ctx, ctx->tet_cnt.p, ctx->tet_off.p, (long long)t_count + 1);
+    int total = 0;
+    MB_CUDA(cudaMemcpyAsync(&total, ctx->tet_off.p + t_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    n_pairs = total;
+    ctx->pair_tet.reserve((size_t)n_pairs + 1);
+    ctx->pair_site.reserve((size_t)n_pairs + 1);
+    if (n_pairs > 0) {
+      if (S.given) {
+        const int blocks = (t_count + 7) / 8;
+        k_cand_given<true><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, S.site4.p,
+                                                  S.flags.p, S.n_site, S.nbr.p, S.site_k, ctx->tet_cnt.p,
+                                                  ctx->cand_pad.p, ctx->tet_off.p, ctx->pair_tet.p,
+                                                  ctx->pair_site.p);
+        MB_CUDA(cudaGetLastError());
+      } else {
+        grid_fill_pairs(ctx, t_first, t_count, n_pairs);
+      }
+    }
+  }
+  MB_CUDA(cudaEventRecord(res->ev[1], s));
+  res->n_pairs = n_pairs;
+
+  // ---- K3: clip ---------------------------------------------------------------------------------
+  ctx->pair_status.reserve((size_t)n_pairs + 1);
+  ctx->pair_blob.reserve((size_t)n_pairs + 1);
+  ctx->pair_words.reserve((size_t)n_pairs + 1);
+  // scratch: typical record ~80 words; retried with the exact need if it overflows
+  size_t scratch_words = std::max<size_t>((size_t)n_pairs * 96 + (1u << 20), ctx->scratch.cap);
+  RpdCounters hc;
+  for (int attempt = 0; attempt < 2 && n_pairs > 0; attempt++) {
+    ctx->scratch.reserve(scratch_words);
+    ClipArgs A;
+    A.vert4 = M.vert4.p;
+    A.tet_idx = M.tet_idx.p;
+    A.tet_fadj = M.tet_fadj.p;
+    A.tet_fid = M.tet_fid.p;
+    A.tet_e6 = M.tet_e6.p;
+    A.site4 = S.site4.p;
+    A.n_site = S.n_site;
+    if (S.given) {
+      A.nbr = S.nbr.p;
+      A.nbr_stride = S.site_k;
+      A.nbr_cnt = nullptr;
+    } else {
+      A.nbr = ctx->cand_pad.p;
+      A.nbr_stride = ctx->cand_kcap;
+      A.nbr_cnt = ctx->cand_cnt.p;
+    }
+    A.tet_first = t_first;
+    A.pair_tet = ctx->pair_tet.p;
+    A.pair_site = ctx->pair_site.p;
+    A.n_pairs = n_pairs;
+    A.pair_status = ctx->pair_status.p;
+    A.pair_blob = ctx->pair_blob.p;
+    A.pair_words = ctx->pair_words.p;
+    A.scratch = ctx->scratch.p;
+    A.scratch_words = ctx->scratch.cap;
+    A.counters = reinterpret_cast<unsigned long long*>(ctx->counters.p);
+    if (G == 8)
+      launch_clip<8>(ctx, A);
+    else if (G == 16)
+      launch_clip<16>(ctx, A);
+    else
+      launch_clip<32>(ctx, A);
+    MB_CUDA(cudaEventRecord(res->ev[2], s));
+    MB_CUDA(cudaMemcpyAsync(&hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    if (hc.blob_words <= ctx->scratch.cap) break;
+    // scratch too small: rerun K3 with the measured need (rare; statuses are recomputed)
+    scratch_words = (size_t)hc.blob_words + (1u << 20);
+    MB_REQUIRE(attempt == 0, MB_ERR_NOMEM, "compact scratch overflow after resize");
+    MB_CUDA(cudaMemsetAsync(ctx->counters.p, 0, sizeof(RpdCounters), s));
+    MB_CUDA(cudaEventRecord(res->ev[1], s));
+  }
+  if (n_pairs == 0) {
+    memset(&hc, 0, sizeof hc);
+    MB_CUDA(cudaEventRecord(res->ev[2], s));
+  }
+  res->n_cells = (long)hc.n_valid;
+  res->n_clips = (long)hc.n_clips;
+  res->n_culled = (long)hc.n_culled;
+  for (int i = 0; i < 10; i++) res->hist[i] = (long)hc.hist[i];
+
+  // ---- ordering: scan + gather into (tet, site) order -------------------------------------------
+  res->cell_off.reserve((size_t)res->n_cells + 1);
+  long long total_words = 0;
+  if (n_pairs > 0) {
+    DevBuf<long long>& word_off = ctx->word_off;
+    word_off.reserve((size_t)n_pairs + 1);
+    DevBuf<int>& valid = ctx->pair_valid;
+    valid.reserve((size_t)n_pairs + 1);
+    DevBuf<int>& cell_idx = ctx->pair_cell;
+    cell_idx.reserve((size_t)n_pairs + 1);
+    MB_CUDA(cudaMemsetAsync(ctx->pair_words.p + n_pairs, 0, sizeof(int), s));
+    k_valid_flags<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, s>>>(ctx->pair_words.p, n_pairs + 1, valid.p);
+    exclusive_scan<long long>(ctx, ctx->pair_words.p, word_off.p, n_pairs + 1);
+    exclusive_scan<int>(ctx, valid.p, cell_idx.p, n_pairs + 1);
+    MB_CUDA(cudaMemcpyAsync(&total_words, word_off.p + n_pairs, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    res->blob.reserve((size_t)total_words + 4);
+    if (total_words > 0) {
+      k_gather<<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
+          ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, word_off.p, cell_idx.p, n_pairs,
+          res->blob.p, res->cell_off.p, total_words, res->n_cells);
+      MB_CUDA(cudaGetLastError());
+    }
+  }
+  if (res->n_cells == 0) MB_CUDA(cudaMemsetAsync(res->cell_off.p, 0, sizeof(long long), s));
+  res->compact_bytes = (long)(total_words * 4);
+  MB_CUDA(cudaEventRecord(res->ev[3], s));
+  res->synced = false;
+}
+
+void rpd_sync(mb_ctx* ctx, mb_rpd_result* res) {
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!res->synced && res->ev[0]) {
+    MB_CUDA(cudaEventElapsedTime(&res->ms[0], res->ev[0], res->ev[1]));
+    MB_CUDA(cudaEventElapsedTime(&res->ms[1], res->ev[1], res->ev[2]));
+    MB_CUDA(cudaEventElapsedTime(&res->ms[2], res->ev[2], res->ev[3]));
+    MB_CUDA(cudaEventElapsedTime(&res->ms[3], res->ev[0], res->ev[3]));
+    res->synced = true;
+  }
+}

@@ -1,0 +1,192 @@
+"""Host-side mirror of the reference interface for the hot path, in Python over the C ABI.
+
+`Context.compute_clipped_voro_diagram` keeps the argument meaning of the reference's
+compute_clipped_voro_diagram_GPU (src/rpd3d/voronoi.h:52-61) and `Context.compute_closest_dist2mat`
+that of compute_closest_dist2mat (src/dist2mat/dist2mat.h:19-24); the C++ shims with the exact
+C++ signatures are in include/libmat_b200_shim.hpp.  All compute happens in libmat_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import LibMatError, RECORD_DTYPE, ptr
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class RpdResult:
+    """Handle on the device-resident result of one RPD run (mb_rpd_result)."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx = ctx
+        self._h = handle
+        lib = ctx.lib
+        a, b, c = C.c_long(), C.c_long(), C.c_long()
+        ctx._check(lib.mb_rpd_count(handle, C.byref(a), C.byref(b), C.byref(c)))
+        self.n_cells, self.n_pairs, self.n_clips = a.value, b.value, c.value
+        hist = (C.c_long * 10)()
+        ctx._check(lib.mb_rpd_status_histogram(handle, hist))
+        self.status_histogram = np.array(list(hist), dtype=np.int64)  # index = status + 1
+        ms = (C.c_float * 4)()
+        ctx._check(lib.mb_rpd_kernel_ms(handle, ms))
+        self.kernel_ms = {"candidates": ms[0], "clip": ms[1], "order": ms[2], "total": ms[3]}
+        nb = C.c_long()
+        ctx._check(lib.mb_rpd_compact_bytes(handle, C.byref(nb)))
+        self.compact_bytes = nb.value
+
+    def records(self) -> np.ndarray:
+        """Cells sorted by (tet, site) in the ConvexCellTransfer layout (id = index)."""
+        out = np.zeros(self.n_cells, dtype=RECORD_DTYPE)
+        if self.n_cells:
+            self.ctx._check(self.ctx.lib.mb_rpd_fetch_records(self._h, ptr(out)))
+        return out
+
+    def compact(self):
+        blob = np.zeros(max(1, self.compact_bytes // 4), dtype=np.uint32)
+        offs = np.zeros(self.n_cells + 1, dtype=np.int64)
+        self.ctx._check(self.ctx.lib.mb_rpd_fetch_compact(self._h, ptr(blob), ptr(offs)))
+        return blob, offs
+
+    def device_buffers(self):
+        b, o = C.c_void_p(), C.c_void_p()
+        nb, nc = C.c_long(), C.c_long()
+        self.ctx._check(self.ctx.lib.mb_rpd_device_buffers(self._h, C.byref(b), C.byref(nb), C.byref(o), C.byref(nc)))
+        return b.value, nb.value, o.value, nc.value
+
+    def emit(self, max_surf_fid: int) -> dict:
+        """K4: facets / vertices / edges of every cell (get_all_voro_info keys)."""
+        cnt = capi.EmitCounts()
+        self.ctx._check(self.ctx.lib.mb_rpd_emit(self._h, int(max_surf_fid), C.byref(cnt)))
+        nf, nv, ne = cnt.n_facets, cnt.n_vertices, cnt.n_edges
+        out = {
+            "facet_cell": np.zeros(nf, np.int32), "facet_key": np.zeros(nf, np.int32),
+            "facet_is_tet": np.zeros(nf, np.uint8),
+            "vert_cell": np.zeros(nv, np.int32), "vert_lvid": np.zeros(nv, np.int32),
+            "vert_key": np.zeros((nv, 3), np.int32), "vert_pos": np.zeros((nv, 3), np.float32),
+            "vert_surf_fid": np.zeros(nv, np.int32),
+            "edge_cell": np.zeros(ne, np.int32), "edge_key": np.zeros((ne, 2), np.int32),
+            "edge_lvid": np.zeros((ne, 2), np.int32),
+            "cell_euler": np.zeros(self.n_cells, np.float32),
+        }
+        order = ["facet_cell", "facet_key", "facet_is_tet", "vert_cell", "vert_lvid", "vert_key",
+                 "vert_pos", "vert_surf_fid", "edge_cell", "edge_key", "edge_lvid", "cell_euler"]
+        self.ctx._check(self.ctx.lib.mb_rpd_fetch_emit(self._h, *[ptr(out[k]) for k in order]))
+        return out
+
+    def free(self):
+        if self._h:
+            self.ctx.lib.mb_rpd_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One mb_ctx: one CUDA device, one stream, the tet mesh resident in HBM."""
+
+    def __init__(self, device: int = -1):
+        self.lib = capi.load()
+        err = C.c_int(0)
+        self._ctx = self.lib.mb_create(int(device), C.byref(err))
+        if not self._ctx:
+            raise LibMatError(f"mb_create failed (code {err.value}): no usable CUDA device; "
+                              "libmat_b200 has no CPU fallback")
+        self.mesh_n_tet = 0
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.mb_last_error(self._ctx)
+            raise LibMatError(f"libmat_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._ctx:
+            self.lib.mb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ mesh
+    def set_tetmesh(self, vertices, indices, v_adjs, f_adjs, f_ids, e_adj6=None, e_adjs_dense=None):
+        v = _c(vertices, np.float32).reshape(-1)
+        idx = _c(indices, np.int32).reshape(-1)
+        va = _c(v_adjs, np.int32)
+        fa = _c(f_adjs, np.int32).reshape(-1)
+        fi = _c(f_ids, np.int32).reshape(-1)
+        e6 = None if e_adj6 is None else _c(e_adj6, np.int32).reshape(-1)
+        ed = None if e_adjs_dense is None else _c(e_adjs_dense, np.int32)
+        self._check(self.lib.mb_set_tetmesh(self._ctx, ptr(v), v.size // 3, ptr(idx), idx.size // 4,
+                                            ptr(va), ptr(ed), ptr(e6), ptr(fa), ptr(fi)))
+        self.mesh_n_tet = idx.size // 4
+
+    def set_mesh(self, mesh):
+        self.set_tetmesh(mesh.vertices, mesh.indices, mesh.v_adjs, mesh.f_adjs, mesh.f_ids, e_adj6=mesh.e_adj6)
+
+    def set_tet_range(self, first: int, count: int):
+        self._check(self.lib.mb_set_tet_range(self._ctx, int(first), int(count)))
+
+    # ------------------------------------------------------------------ RPD
+    def upload_sites(self, site_soa, site_weights, site_flags, site_knn=None, site_k=0):
+        ss = _c(site_soa, np.float32).reshape(-1)
+        sw = _c(site_weights, np.float32)
+        sf = _c(site_flags, np.uint32)
+        knn = None if site_knn is None else _c(site_knn, np.int32).reshape(-1)
+        self._keep = (ss, sw, sf, knn)
+        self._check(self.lib.mb_rpd_upload_sites(self._ctx, ptr(ss), ptr(sw), ptr(sf), sw.size, ptr(knn), int(site_k)))
+
+    def run(self, lanes_per_cell=0, grid_k=0, want_volumes=False) -> RpdResult:
+        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), int(want_volumes), 0)
+        h = C.c_void_p()
+        self._check(self.lib.mb_rpd_run(self._ctx, C.byref(opts), C.byref(h)))
+        self._check(self.lib.mb_rpd_sync(self._ctx, h))
+        return RpdResult(self, h)
+
+    def compute_clipped_voro_diagram(self, site, site_weights, site_flags, site_knn=None, site_k=0,
+                                     **opts) -> RpdResult:
+        """site: SoA x|y|z float[3*n_site]; site_weights r^2; site_knn (site_k+1) x n_site or None
+        (None = grid-kNN mode).  Returns the device-resident result (cells sorted by (tet, site))."""
+        self.upload_sites(site, site_weights, site_flags, site_knn, site_k)
+        return self.run(**opts)
+
+    # ------------------------------------------------------------------ dist2mat
+    def dist2mat_upload(self, spheres, samples, offset, count, prims):
+        sp = _c(spheres, np.float32).reshape(-1)
+        sm = _c(samples, np.float32).reshape(-1)
+        of = _c(offset, np.uint32)
+        cn = _c(count, np.uint32)
+        pr = _c(prims, np.int32).reshape(-1)
+        self._d2m_n = of.size
+        self._check(self.lib.mb_dist2mat_upload(self._ctx, ptr(sp), sp.size // 4, ptr(sm), of.size, ptr(of),
+                                                ptr(cn), ptr(pr), pr.size // 3))
+
+    def dist2mat_run(self) -> float:
+        ms = C.c_float(0)
+        self._check(self.lib.mb_dist2mat_run(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def dist2mat_fetch(self, want_tie=True):
+        n = self._d2m_n
+        res = np.zeros(n, np.float32)
+        cid = np.zeros(n, np.int32)
+        tie = np.zeros(n, np.uint8) if want_tie else None
+        self._check(self.lib.mb_dist2mat_fetch(self._ctx, ptr(res), ptr(cid), ptr(tie)))
+        return res, cid, tie
+
+    def compute_closest_dist2mat(self, spheres, samples, offset, count, prims, want_tie=True):
+        """Argument meaning of compute_closest_dist2mat (reference dist2mat.h:19-24):
+        returns (results, closest_mat_id[, tie_flag])."""
+        self.dist2mat_upload(spheres, samples, offset, count, prims)
+        self.dist2mat_run()
+        return self.dist2mat_fetch(want_tie)

@@ -313,20 +313,26 @@ def make_dist2mat(n_samples: int, nu: int = 100, nv: int = 200, seed: int = RAN_
 
     _, nn = cKDTree(sp[:, :3]).query(samples.astype(np.float64), k=2)
     nn = nn.astype(np.int64)
+    # per-sample list = unique prims incident to either sphere (ascending prim id), then the 2 spheres
     cnt_a = start[nn[:, 0] + 1] - start[nn[:, 0]]
     cnt_b = start[nn[:, 1] + 1] - start[nn[:, 1]]
-    count = (cnt_a + cnt_b + 2).astype(np.int64)
+    rep_a = np.repeat(np.arange(n_samples), cnt_a)
+    pos_a = np.arange(rep_a.size) - np.repeat(np.cumsum(cnt_a) - cnt_a, cnt_a)
+    rep_b = np.repeat(np.arange(n_samples), cnt_b)
+    pos_b = np.arange(rep_b.size) - np.repeat(np.cumsum(cnt_b) - cnt_b, cnt_b)
+    key = np.concatenate([rep_a * n_prim + inc_p[start[nn[rep_a, 0]] + pos_a],
+                          rep_b * n_prim + inc_p[start[nn[rep_b, 1]] + pos_b]])
+    key = np.unique(key)
+    smp = key // n_prim
+    pid = key % n_prim
+    cnt_u = np.bincount(smp, minlength=n_samples)
+    count = (cnt_u + 2).astype(np.int64)
     offset = np.concatenate([[0], np.cumsum(count)[:-1]]).astype(np.int64)
     total = int(count.sum())
     prims = np.empty((total, 3), dtype=np.int32)
-    # fill runs: [prims of a][prims of b][sphere a][sphere b]
-    rep = np.repeat(np.arange(n_samples), cnt_a)
-    pos = np.arange(rep.size) - np.repeat(np.cumsum(cnt_a) - cnt_a, cnt_a)
-    prims[offset[rep] + pos] = prim_all[inc_p[start[nn[rep, 0]] + pos]]
-    rep = np.repeat(np.arange(n_samples), cnt_b)
-    pos = np.arange(rep.size) - np.repeat(np.cumsum(cnt_b) - cnt_b, cnt_b)
-    prims[offset[rep] + cnt_a[rep] + pos] = prim_all[inc_p[start[nn[rep, 1]] + pos]]
-    tail = offset + cnt_a + cnt_b
+    pos_u = np.arange(key.size) - np.repeat(np.cumsum(cnt_u) - cnt_u, cnt_u)
+    prims[offset[smp] + pos_u] = prim_all[pid]
+    tail = offset + cnt_u
     prims[tail] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 0]], axis=1)
     prims[tail + 1] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 1]], axis=1)
     return Dist2MatInput(spheres, samples, offset.astype(np.uint32), count.astype(np.uint32), prims, n_co, n_sl)
