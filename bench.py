@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the RPD3D hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--mode grid|given] [--workload cfg2|cfg4|weak]
+
+A "step" = one full restricted power diagram of the workload: candidate search (K1+K2), clipping (K3),
+ordering/compaction (K4 first half), all in libmat_b200.so through the C ABI.
+
+  N = 1   workload = BASELINE.json configs[1]: synthetic Kuhn ball mesh n=32 (196 608 tets, 35 937
+          vertices), 10 000 medial spheres, k=80 (given mode: 80 nearest-centre neighbour lists, the
+          reference's semantics; grid mode: the library's own uniform-grid search).
+  N > 1   weak scaling: the global mesh has ~196 608 tets PER GPU (n = 32 / 40 / 51 / 64 for N = 1/2/4/8),
+          10 000*N spheres replicated on every rank, tets sharded in contiguous blocks; every rank
+          runs its shard, then the compact results are gathered on rank 0 with NCCL (grouped
+          send/recv) inside the timed region.  `value` = cells of all ranks / max-over-ranks time.
+
+`value`  : valid cells per second with the inputs resident in HBM (device time, CUDA events on the
+           stream the kernels run on, L2 flushed between timed steps).
+`e2e`    : the same through the C ABI with HOST buffers: mb_set_tetmesh + mb_rpd_upload_sites (H2D from
+           pinned memory) + mb_rpd_run + mb_rpd_fetch_compact (D2H) every step, wall clock.
+`--impl reference` : the reference's own clipping code (oracle/_ref = /root/reference's convex_cell.cu
+           compiled for the host; else the oracle port) on all host threads, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rpd_tet_cells_clipped_per_sec"
+UNIT = "cells/s"
+N_FOR_GPUS = {1: 32, 2: 40, 4: 51, 8: 64}
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def make_workload(workload: str, n_gpus: int):
+    from libmat_b200 import synth
+
+    if workload == "cfg4":
+        n, ns = 70, 100000
+    elif workload == "cfg1":
+        n, ns = 15, 1000
+    else:
+        n = N_FOR_GPUS.get(n_gpus, int(round(32 * n_gpus ** (1 / 3))))
+        ns = 10000 * n_gpus
+    mesh = synth.make_ball_mesh(n)
+    sites = synth.make_spheres(ns)
+    return mesh, sites, n, ns
+
+
+def shard(n_tet: int, rank: int, world: int):
+    """contiguous tet blocks: rank r owns [first, first+count)"""
+    base, rem = divmod(n_tet, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def algorithmic_bytes(mesh_n_tet, mesh_n_vert, n_site, n_pairs, n_listed, recs_bytes):
+    """B_rpd = n_tet*72 + n_vert*16 + n_site*16 + C*4 + N*4 + sum(compact records)."""
+    return mesh_n_tet * 72 + mesh_n_vert * 16 + n_site * 16 + n_pairs * 4 + n_listed * 4 + recs_bytes
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(mesh, sites, knn, k, pt, ps, repeats=2):
+    """the reference's clipping code on the host cores (oracle/_ref if built, else the oracle port)"""
+    from oracle import oracle as O
+
+    kind = "reference" if O.ref("rpd") is not None else "port"
+    impl = "ref" if kind == "reference" else "oracle"
+    best, cells = None, 0
+    for _ in range(repeats):
+        recs, stat, sec = O.run_pairs(mesh, sites, knn, k, pt, ps, impl=impl, n_threads=0)
+        cells = int((recs["status"] == 4).sum())
+        best = sec if best is None else min(best, sec)
+    return kind, cells, best
+
+
+def run_reference_arm(args):
+    """--impl reference: CPU only, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from libmat_b200 import synth
+    from oracle import oracle as O
+
+    mesh, sites, n, ns = make_workload(args.workload, args.gpus)
+    knn, k = synth.knn_site_lists(sites, 80)
+    # bounded sample: every `stride`-th cube of 6 tets (representative of the whole ball)
+    target_tets = int(min(24576, max(1536, 2.5e8 / ns)))  # bounds the (untimed) candidate generation
+    stride = max(1, mesh.n_tet // target_tets)
+    cubes = np.arange(mesh.n_tet // 6)[::stride]
+    sel = (cubes[:, None] * 6 + np.arange(6)[None, :]).ravel()
+    sub = synth.TetMesh(mesh.vertices, mesh.indices[sel], mesh.v_adjs, mesh.e_adj6[sel], mesh.f_adjs[sel],
+                        mesh.f_ids[sel], mesh.n_surf_faces)
+    pt, ps = O.tet_sphere_relation(sub, sites, knn, k)  # candidate generation: not timed
+    kind = "reference" if O.ref("rpd") is not None else "port"
+    impl = "ref" if kind == "reference" else "oracle"
+    cores = os.cpu_count() or 1
+    cells = 0
+    for _ in range(args.warmup):
+        O.run_pairs(sub, sites, knn, k, pt, ps, impl=impl)
+    t_total = 0.0
+    for _ in range(args.steps):
+        recs, stat, sec = O.run_pairs(sub, sites, knn, k, pt, ps, impl=impl)
+        cells = int((recs["status"] == 4).sum())
+        t_total += sec
+    value = cells * args.steps / t_total
+    sample = (f"{len(sel)} of {mesh.n_tet} tets (every {stride}th cube), {len(pt)} candidate pairs, {cells} cells "
+              f"per step; per-pair clipping loop + record copy timed, candidate generation excluded")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args, n, ns, mesh), "mode": "given-neighbours k=80 (reference semantics)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args, n, ns, mesh):
+    return (f"{args.workload}: synthetic Kuhn ball mesh n={n} ({mesh.n_tet} tets, {mesh.n_vert} verts), "
+            f"{ns} medial spheres, k=80")
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="grid", choices=["grid", "given"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4"])
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from libmat_b200 import synth
+    from libmat_b200.rpd import Context
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmat_b200 has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    mesh, sites, n, ns = make_workload(args.workload, n_gpus)
+    mode = args.mode if world == 1 else "grid"
+    knn, k = (synth.knn_site_lists(sites, 80) if (mode == "given" or (rank == 0 and world == 1)) else (None, 0))
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = Context(local_rank)
+    ctx.set_stream(stream.cuda_stream)
+
+    # host inputs in pinned memory (the e2e leg copies from here every step)
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+
+    keep = []
+    h = {}
+    for name, arr in (("verts", mesh.vertices), ("idx", mesh.indices), ("v_adjs", mesh.v_adjs),
+                      ("e6", mesh.e_adj6), ("f_adjs", mesh.f_adjs), ("f_ids", mesh.f_ids),
+                      ("site", sites.site_soa), ("w", sites.weights), ("flags", sites.flags)):
+        h[name], t = pinned(arr)
+        keep.append(t)
+    if mode == "given":
+        h["knn"], t = pinned(knn)
+        keep.append(t)
+    else:
+        h["knn"] = None
+    site_k = k if mode == "given" else 0
+
+    def set_mesh():
+        ctx.set_tetmesh(h["verts"], h["idx"], h["v_adjs"], h["f_adjs"], h["f_ids"], e_adj6=h["e6"])
+        first, count = shard(mesh.n_tet, rank, world)
+        if world > 1:
+            ctx.set_tet_range(first, count)
+
+    def upload_sites():
+        ctx.upload_sites(h["site"], h["w"], h["flags"], h["knn"], site_k)
+
+    set_mesh()
+    upload_sites()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # ---- NCCL gather of the compact results on rank 0 (grouped send/recv) ------------------------
+    class DevView:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    gather_buf = {}
+
+    def gather(res):
+        if world == 1:
+            return 0
+        d_blob, n_bytes, d_off, n_cells = res.device_buffers()
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        mine = torch.tensor([n_bytes], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, mine)
+        sz = sizes.tolist()
+        src = torch.as_tensor(DevView(d_blob, max(n_bytes, 1)), device=dev)[:n_bytes]
+        ops = []
+        if rank == 0:
+            total = sum(sz)
+            if gather_buf.get("cap", 0) < total:
+                gather_buf["t"] = torch.empty(int(total * 1.1) + 16, dtype=torch.uint8, device=dev)
+                gather_buf["cap"] = gather_buf["t"].numel()
+            out = gather_buf["t"]
+            out[:sz[0]].copy_(src, non_blocking=True)
+            off = sz[0]
+            for r in range(1, world):
+                ops.append(dist.P2POp(dist.irecv, out[off:off + sz[r]], r))
+                off += sz[r]
+        else:
+            ops.append(dist.P2POp(dist.isend, src, 0))
+        if ops:
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+        return sum(sz) if rank == 0 else 0
+
+    def step():
+        res = ctx.run(lanes_per_cell=args.lanes)
+        gathered = gather(res)
+        return res, gathered
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            res, _ = step()
+            res.free()
+        barrier()
+        launches0 = ctx.launch_count()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        clip_ms, cand_ms, order_ms = [], [], []
+        cells = pairs = listed = rec_bytes = 0
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            ev[i][0].record(stream)
+            res, _ = step()
+            ev[i][1].record(stream)
+            ev[i][1].synchronize()
+            clip_ms.append(res.kernel_ms["clip"])
+            cand_ms.append(res.kernel_ms["candidates"])
+            order_ms.append(res.kernel_ms["order"])
+            cells, pairs, rec_bytes = res.n_cells, res.n_pairs, res.compact_bytes
+            listed = res.n_clips + res.n_culled
+            res.free()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop() if rank == 0 else None
+        launches = ctx.launch_count() - launches0
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        t_dev = sum(step_ms) / 1e3
+
+        # ---- e2e: host buffers in, compact records out, every step ------------------------------
+        e2e_steps = max(3, min(args.steps, 10))
+        blob_host = None
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            set_mesh()
+            upload_sites()
+            res, _ = step()
+            if world == 1 or rank == 0:
+                if blob_host is None or blob_host[0].size * 4 < res.compact_bytes:
+                    tb = torch.empty(int(res.compact_bytes * 1.05) // 4 + 16, dtype=torch.int32).pin_memory()
+                    to = torch.empty(res.n_cells + 16, dtype=torch.int64).pin_memory()
+                    blob_host = (tb.numpy().view(np.uint32), to.numpy(), tb, to)
+                ctx._check(ctx.lib.mb_rpd_fetch_compact(res._h, blob_host[0].ctypes.data, blob_host[1].ctypes.data))
+            d2h = res.compact_bytes + 8 * (res.n_cells + 1)
+            res.free()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+
+    # ---- max over ranks, totals ------------------------------------------------------------------
+    tot = torch.tensor([float(cells), float(pairs), float(rec_bytes), float(listed)], dtype=torch.float64, device=dev)
+    mx = torch.tensor([t_dev, t_e2e, t_wall, float(np.mean(clip_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    total_cells, total_pairs = int(tot[0].item()), int(tot[1].item())
+    t_dev, t_e2e, t_wall, clip_ms_max = mx.tolist()
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        first, count = shard(mesh.n_tet, rank, world)
+        b_alg = algorithmic_bytes(count, mesh.n_vert, ns, pairs, listed, rec_bytes)  # rank 0's launch
+        clip_avg_ms = float(np.mean(clip_ms))
+        achieved = b_alg / (clip_avg_ms * 1e-3) / 1e9
+        h2d = sum(h[x].nbytes for x in ("verts", "idx", "v_adjs", "e6", "f_adjs", "f_ids", "site", "w", "flags"))
+        if h["knn"] is not None:
+            h2d += h["knn"].nbytes
+        line = {
+            "metric": METRIC, "value": total_cells * args.steps / t_dev, "unit": UNIT, "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args, n, ns, mesh),
+                       "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else "given-neighbours k=80",
+                       "parallelism": f"tet-shards x{world}, sites replicated" + (", NCCL gather to rank 0" if world > 1 else ""),
+                       "l2": "flushed (512 MB write) between timed steps",
+                       "cells_per_step": total_cells, "candidate_pairs_per_step": total_pairs,
+                       "pairs_per_sec": total_pairs * args.steps / t_dev},
+            "stage_ms": {"candidates": float(np.mean(cand_ms)), "clip": clip_avg_ms, "order": float(np.mean(order_ms)),
+                         "step_wall_ms": 1e3 * t_wall / args.steps},
+            "roofline": {"kernel": "k_clip", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": b_alg,
+                         "note": "latency/FP64-bound irregular kernel; see DESIGN.md and profiles/"},
+            "e2e": {"value": total_cells * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "path": "mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run + mb_rpd_fetch_compact"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            # CPU baseline: the reference's clipping code on the candidate pairs of a given-mode run
+            ctx.upload_sites(h["site"], h["w"], h["flags"], knn, k)
+            rg = ctx.run()
+            pt, ps, _ = rg.pairs()
+            gpu_cells = rg.n_cells
+            rg.free()
+            kind, cpu_cells, sec = cpu_reference_run(mesh, sites, knn, k, pt, ps)
+            line["cpu_baseline"] = {
+                "value": cpu_cells / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+                "sample": f"all {len(pt)} candidate pairs of the workload (given-neighbours k=80), {cpu_cells} cells, "
+                          f"best of 2, {sec:.2f} s; clipping loop + record copy timed, candidate generation excluded",
+                "cells_match_gpu_given_mode": bool(cpu_cells == gpu_cells)}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,8 +73,19 @@ enum mb_cell_status {
 /* device < 0 -> current device.  Returns NULL without a CUDA device (err may receive the code). */
 mb_ctx* mb_create(int device, int* err);
 void mb_destroy(mb_ctx* ctx);
+/* run all subsequent work of this context on the caller's CUDA stream (cudaStream_t passed as
+ * void*; NULL = back to the context's own stream).  Lets a host framework (e.g. torch + NCCL) order
+ * its own work and events against the library's kernels. */
+int mb_set_stream(mb_ctx* ctx, void* cuda_stream);
 const char* mb_last_error(const mb_ctx* ctx);
 const char* mb_version(void);
+/* the static-filter error bounds of the conflict predicate, as printed by the reference's
+ * src/predicate_generator/main.cpp:52-78 and consumed at convex_cell.cu:421,486 */
+#define MB_FILTER_BOUND_F64 1.2466136531027298e-13
+#define MB_FILTER_BOUND_F32 6.6876506e-05f
+void mb_predicate_bounds(double* bound_f64, float* bound_f32);
+/* number of CUDA kernels this context has launched since mb_create (instrumentation) */
+int mb_launch_count(const mb_ctx* ctx, unsigned long long* n_launches);
 
 /* ---------------------------------------------------------------- tet mesh (resident in HBM) */
 /* verts_aos float[3*n_vert], idx_aos int[4*n_tet] (positively oriented), v_adjs int[n_vert],
@@ -127,6 +138,11 @@ int mb_rpd_status_histogram(const mb_rpd_result* res, long hist[10]);
 /* kernel milliseconds of the last run: [0]=candidates (K1+K2) [1]=clip (K3) [2]=emit (K4)
  * [3]=total device time, measured with CUDA events on the context's stream */
 int mb_rpd_kernel_ms(const mb_rpd_result* res, float ms[4]);
+
+/* the candidate (tet, site) pairs the run clipped, sorted by (tet, site) -- the reference's tet_knn
+ * (voronoi.cu:266-317) in pair form -- and the per-pair Status; n_pairs entries each, any may be
+ * NULL.  Valid until the next mb_rpd_run on the same context. */
+int mb_rpd_fetch_pairs(mb_rpd_result* res, int* pair_tet, int* pair_site, signed char* pair_status);
 
 /* cells sorted by (tet, site), dst = n_cells * MB_RECORD_BYTES in the ConvexCellTransfer
  * layout; only entries < nb_v/nb_p/nb_e are defined (others zero); id = index. */

@@ -12,12 +12,16 @@ LIB_PATH = os.path.join(HERE, "libmat_b200.so")
 
 # every symbol include/libmat_b200.h declares
 SYMBOLS = [
-    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_set_tetmesh", "mb_set_tet_range",
+    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range",
     "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
     "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
     "mb_rpd_fetch_emit", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
 ]
+
+# static-filter bounds (reference src/predicate_generator/main.cpp output; include/libmat_b200.h)
+FILTER_BOUND_F64 = 1.2466136531027298e-13
+FILTER_BOUND_F32 = 6.6876506e-05
 
 RECORD_BYTES = 3456
 # ConvexCellTransfer layout (reference src/rpd3d/convex_cell.h:189-217)
@@ -63,6 +67,8 @@ def load() -> C.CDLL:
     lib.mb_last_error.restype = C.c_char_p
     lib.mb_last_error.argtypes = [C.c_void_p]
     lib.mb_version.restype = C.c_char_p
+    lib.mb_predicate_bounds.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    lib.mb_predicate_bounds.restype = None
     lib.mb_rpd_free.argtypes = [C.c_void_p]
     lib.mb_rpd_free.restype = None
     vp = C.c_void_p
@@ -76,6 +82,9 @@ def load() -> C.CDLL:
     lib.mb_rpd_status_histogram.argtypes = [vp, vp]
     lib.mb_rpd_kernel_ms.argtypes = [vp, vp]
     lib.mb_rpd_fetch_records.argtypes = [vp, vp]
+    lib.mb_rpd_fetch_pairs.argtypes = [vp, vp, vp, vp]
+    lib.mb_set_stream.argtypes = [vp, vp]
+    lib.mb_launch_count.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     lib.mb_rpd_compact_bytes.argtypes = [vp, C.POINTER(C.c_long)]
     lib.mb_rpd_fetch_compact.argtypes = [vp, vp, vp]
     lib.mb_rpd_site_volumes.argtypes = [vp, vp, vp]

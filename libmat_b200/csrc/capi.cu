@@ -31,6 +31,11 @@ extern "C" {
 
 const char* mb_version(void) { return "libmat_b200 0.1 (sm_100a)"; }
 
+void mb_predicate_bounds(double* bound_f64, float* bound_f32) {
+  if (bound_f64) *bound_f64 = MB_FILTER_BOUND_F64;
+  if (bound_f32) *bound_f32 = MB_FILTER_BOUND_F32;
+}
+
 mb_ctx* mb_create(int device, int* err) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -51,11 +56,12 @@ mb_ctx* mb_create(int device, int* err) {
     return nullptr;
   }
   ctx->device = device;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     if (err) *err = MB_ERR_CUDA;
     return nullptr;
   }
+  ctx->stream = ctx->own_stream;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (err) *err = MB_OK;
   return ctx;
@@ -79,8 +85,16 @@ void mb_destroy(mb_ctx* ctx) {
   ctx->grid_cnt.release(); ctx->grid_off.release(); ctx->grid_sorted_id.release(); ctx->grid_cell_of.release();
   ctx->grid_site4.release(); ctx->grid_wmax0.release(); ctx->grid_wmax1.release();
   ctx->pin_in.release(); ctx->pin_out.release();
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
+}
+
+int mb_set_stream(mb_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return MB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return MB_OK;
 }
 
 const char* mb_last_error(const mb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -181,6 +195,28 @@ int mb_rpd_kernel_ms(const mb_rpd_result* res, float ms[4]) {
   if (!res || !ms) return MB_ERR_ARG;
   for (int i = 0; i < 4; i++) ms[i] = res->ms[i];
   return MB_OK;
+}
+
+int mb_launch_count(const mb_ctx* ctx, unsigned long long* n_launches) {
+  if (!ctx || !n_launches) return MB_ERR_ARG;
+  *n_launches = ctx->n_launches;
+  return MB_OK;
+}
+
+int mb_rpd_fetch_pairs(mb_rpd_result* res, int* pair_tet, int* pair_site, signed char* pair_status) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t n = (size_t)res->n_pairs;
+  if (n > 0) {
+    if (pair_tet) MB_CUDA(cudaMemcpyAsync(pair_tet, ctx->pair_tet.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    if (pair_site) MB_CUDA(cudaMemcpyAsync(pair_site, ctx->pair_site.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    if (pair_status) MB_CUDA(cudaMemcpyAsync(pair_status, ctx->pair_status.p, n, cudaMemcpyDeviceToHost, s));
+  }
+  MB_CUDA(cudaStreamSynchronize(s));
+  MB_CATCH
 }
 
 int mb_rpd_compact_bytes(const mb_rpd_result* res, long* n_bytes) {

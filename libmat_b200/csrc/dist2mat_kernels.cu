@@ -296,6 +296,7 @@ void d2m_run(mb_ctx* ctx, float* kernel_ms) {
     const int warps = D.n_samples;
     long long blocks = ((long long)warps + 7) / 8;
     blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 32);
+    ctx->n_launches++;
     k_dist2mat<<<(unsigned)blocks, 256, 0, s>>>(D.samples.p, D.spheres.p, D.prims.p, D.offset.p, D.count.p,
                                                D.n_samples, D.result.p, D.closest.p, D.tie.p);
     MB_CUDA(cudaGetLastError());

@@ -141,9 +141,11 @@ struct D2MDev {
 
 struct mb_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream in use (own_stream unless mb_set_stream)
+  cudaStream_t own_stream = nullptr;
   std::string err;
   int sm_count = 148;
+  unsigned long long n_launches = 0;  // kernels launched by this context (bench: gpu_launches)
   TetMeshDev mesh;
   SitesDev sites;
   D2MDev d2m;

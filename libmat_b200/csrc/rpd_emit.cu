@@ -198,6 +198,7 @@ void scan_ll(mb_ctx* ctx, const int* in, long long* out, long n) {
   size_t tmp = 0;
   MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, ctx->stream));
   ctx->cub_tmp.reserve(tmp);
+  ctx->n_launches += 2;  // DeviceScanInitKernel + DeviceScanKernel
   MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, out, n, ctx->stream));
 }
 
@@ -217,6 +218,7 @@ void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid) {
   MB_CUDA(cudaMemsetAsync(cv.p + n, 0, sizeof(int), s));
   MB_CUDA(cudaMemsetAsync(ce.p + n, 0, sizeof(int), s));
   const unsigned blocks = (unsigned)((n + 127) / 128);
+  ctx->n_launches++;
   k_emit<false><<<blocks, 128, 0, s>>>(res->blob.p, res->cell_off.p, n, max_surf_fid, cf.p, cv.p, ce.p, nullptr,
                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -237,6 +239,7 @@ void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid) {
   res->v_pos3.reserve(3 * tot[1] + 1); res->v_surf.reserve(tot[1] + 1);
   res->e_cell.reserve(tot[2] + 1); res->e_key2.reserve(2 * tot[2] + 1); res->e_lvid2.reserve(2 * tot[2] + 1);
   res->c_euler.reserve(n + 1);
+  ctx->n_launches++;
   k_emit<true><<<blocks, 128, 0, s>>>(res->blob.p, res->cell_off.p, n, max_surf_fid, nullptr, nullptr, nullptr,
                                       of.p, ov.p, oe.p, res->f_cell.p, res->f_key.p, res->f_istet.p,
                                       res->v_cell.p, res->v_lvid.p, res->v_key3.p, res->v_pos3.p, res->v_surf.p,

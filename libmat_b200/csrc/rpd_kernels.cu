@@ -104,6 +104,7 @@ void rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
                           cudaMemcpyHostToDevice, s));
   MB_CUDA(cudaMemcpyAsync(S.flags.p, site_flags, sizeof(unsigned) * (size_t)n_site,
                           cudaMemcpyHostToDevice, s));
+  ctx->n_launches++;
   k_prep_sites<<<(n_site + 255) / 256, 256, 0, s>>>(S.soa_staging.p, S.soa_staging.p + 3 * (size_t)n_site,
                                                     n_site, S.site4.p);
   S.given = site_knn != nullptr;
@@ -117,6 +118,7 @@ void rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
     MB_CUDA(cudaMemcpyAsync(S.knn_staging.p, site_knn, sizeof(int) * (size_t)site_k * n_site,
                             cudaMemcpyHostToDevice, s));
     dim3 grid((n_site + 31) / 32, (site_k + 31) / 32), block(32, 8);
+    ctx->n_launches++;
     k_transpose_knn<<<grid, block, 0, s>>>(S.knn_staging.p, n_site, site_k, S.nbr.p);
   }
   float wmax = 0.f;
@@ -281,18 +283,23 @@ static GridDev grid_build(mb_ctx* ctx) {
   ctx->grid_wmax0.reserve(nc);
   ctx->grid_wmax1.reserve(n1);
   MB_CUDA(cudaMemsetAsync(ctx->grid_cnt.p, 0, sizeof(int) * ((size_t)nc + 1), s));
+  ctx->n_launches++;
   k_grid_count<<<(S.n_site + 255) / 256, 256, 0, s>>>(S.site4.p, S.n_site, G, ctx->grid_cnt.p, ctx->grid_cell_of.p);
   {
     size_t tmp = 0;
     MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->grid_cnt.p, ctx->grid_off.p, nc + 1, s));
     ctx->cub_tmp.reserve(tmp);
+    ctx->n_launches += 2;  // DeviceScanInitKernel + DeviceScanKernel
     MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, ctx->grid_cnt.p, ctx->grid_off.p, nc + 1, s));
   }
   MB_CUDA(cudaMemsetAsync(ctx->grid_cnt.p, 0, sizeof(int) * ((size_t)nc + 1), s));
+  ctx->n_launches++;
   k_grid_scatter<<<(S.n_site + 255) / 256, 256, 0, s>>>(S.site4.p, S.n_site, ctx->grid_cell_of.p,
                                                         ctx->grid_off.p, ctx->grid_cnt.p, ctx->grid_sorted_id.p);
+  ctx->n_launches++;
   k_grid_finalize<<<(nc + 127) / 128, 128, 0, s>>>(S.site4.p, ctx->grid_off.p, nc, ctx->grid_sorted_id.p,
                                                    ctx->grid_site4.p, ctx->grid_wmax0.p);
+  ctx->n_launches++;
   k_grid_pyramid<<<(n1 + 127) / 128, 128, 0, s>>>(ctx->grid_wmax0.p, R, G.R1, ctx->grid_wmax1.p);
   MB_CUDA(cudaGetLastError());
   G.site4 = ctx->grid_site4.p;
@@ -315,12 +322,15 @@ static void grid_candidates(mb_ctx* ctx, int t_first, int t_count, int grid_k) {
   ctx->cand_cnt.reserve((size_t)t_count + 1);
   unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->counters.p);
   const int blocks = (t_count + 3) / 4;
-  if (kcap == 96)
+  if (kcap == 96) {
+    ctx->n_launches++;
     k_grid_candidates<96><<<blocks, 128, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, G, S.flags.p,
                                                  ctx->cand_pad.p, ctx->cand_cnt.p, ctx->tet_cnt.p, cnt);
-  else
+  } else {
+    ctx->n_launches++;
     k_grid_candidates<256><<<blocks, 128, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, G, S.flags.p,
                                                   ctx->cand_pad.p, ctx->cand_cnt.p, ctx->tet_cnt.p, cnt);
+  }
   MB_CUDA(cudaGetLastError());
 }
 
@@ -328,6 +338,7 @@ static void grid_fill_pairs(mb_ctx* ctx, int t_first, int t_count, long long n_p
   (void)n_pairs;
   cudaStream_t s = ctx->stream;
   const int blocks = (t_count + 7) / 8;
+  ctx->n_launches++;
   k_grid_fill<<<blocks, 256, 0, s>>>(t_first, t_count, ctx->cand_kcap, ctx->cand_pad.p, ctx->cand_cnt.p,
                                      ctx->tet_off.p, ctx->sites.flags.p, ctx->pair_tet.p, ctx->pair_site.p);
   MB_CUDA(cudaGetLastError());
@@ -341,6 +352,7 @@ static void exclusive_scan(mb_ctx* ctx, const int* in, T* out, long long n) {
   size_t tmp = 0;
   MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, ctx->stream));
   ctx->cub_tmp.reserve(tmp);
+  ctx->n_launches += 2;  // DeviceScanInitKernel + DeviceScanKernel
   MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, out, n, ctx->stream));
 }
 
@@ -360,6 +372,7 @@ static void launch_clip(mb_ctx* ctx, const ClipArgs& A) {
   long long want = (A.n_pairs + groups - 1) / groups;
   long long grid = std::min<long long>(want, (long long)ctx->sm_count * per_sm * 4);
   if (grid < 1) grid = 1;
+  ctx->n_launches++;
   k_clip<G><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
   MB_CUDA(cudaGetLastError());
 }
@@ -392,6 +405,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     if (S.given) {
       ctx->cand_pad.reserve((size_t)t_count * CAND_PAD);
       const int blocks = (t_count + 7) / 8;
+      ctx->n_launches++;
       k_cand_given<false><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, S.site4.p,
                                                  S.flags.p, S.n_site, S.nbr.p, S.site_k, ctx->tet_cnt.p,
                                                  ctx->cand_pad.p, nullptr, nullptr, nullptr);
@@ -410,6 +424,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     if (n_pairs > 0) {
       if (S.given) {
         const int blocks = (t_count + 7) / 8;
+        ctx->n_launches++;
         k_cand_given<true><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, S.site4.p,
                                                   S.flags.p, S.n_site, S.nbr.p, S.site_k, ctx->tet_cnt.p,
                                                   ctx->cand_pad.p, ctx->tet_off.p, ctx->pair_tet.p,
@@ -495,6 +510,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     DevBuf<int>& cell_idx = ctx->pair_cell;
     cell_idx.reserve((size_t)n_pairs + 1);
     MB_CUDA(cudaMemsetAsync(ctx->pair_words.p + n_pairs, 0, sizeof(int), s));
+    ctx->n_launches++;
     k_valid_flags<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, s>>>(ctx->pair_words.p, n_pairs + 1, valid.p);
     exclusive_scan<long long>(ctx, ctx->pair_words.p, word_off.p, n_pairs + 1);
     exclusive_scan<int>(ctx, valid.p, cell_idx.p, n_pairs + 1);
@@ -502,6 +518,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     MB_CUDA(cudaStreamSynchronize(s));
     res->blob.reserve((size_t)total_words + 4);
     if (total_words > 0) {
+      ctx->n_launches++;
       k_gather<<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
           ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, word_off.p, cell_idx.p, n_pairs,
           res->blob.p, res->cell_off.p, total_words, res->n_cells);

@@ -46,6 +46,14 @@ class RpdResult:
             self.ctx._check(self.ctx.lib.mb_rpd_fetch_records(self._h, ptr(out)))
         return out
 
+    def pairs(self):
+        """candidate (tet, site) pairs of the run (the reference's tet_knn in pair form) + Status"""
+        pt = np.zeros(self.n_pairs, np.int32)
+        ps = np.zeros(self.n_pairs, np.int32)
+        st = np.zeros(self.n_pairs, np.int8)
+        self.ctx._check(self.ctx.lib.mb_rpd_fetch_pairs(self._h, ptr(pt), ptr(ps), ptr(st)))
+        return pt, ps, st
+
     def compact(self):
         blob = np.zeros(max(1, self.compact_bytes // 4), dtype=np.uint32)
         offs = np.zeros(self.n_cells + 1, dtype=np.int64)
@@ -106,6 +114,15 @@ class Context:
         if rc != 0:
             msg = self.lib.mb_last_error(self._ctx)
             raise LibMatError(f"libmat_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    def set_stream(self, cuda_stream: int | None):
+        """run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)"""
+        self._check(self.lib.mb_set_stream(self._ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def launch_count(self) -> int:
+        n = C.c_ulonglong(0)
+        self._check(self.lib.mb_launch_count(self._ctx, C.byref(n)))
+        return n.value
 
     def close(self):
         if self._ctx:

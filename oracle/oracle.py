@@ -219,3 +219,50 @@ def dist2mat(inp, impl="oracle", n_threads=0, n=None, want_second=False):
     if want_second:
         return res, cid, t, sec2
     return res, cid, t
+
+
+def zero_undefined(recs):
+    """Zero every entry the reference leaves uninitialised (entries >= nb_v/nb_p/nb_e, padding,
+    whole records that are not `success`), so that records can be stored and compared bytewise."""
+    out = np.zeros(len(recs), dtype=RECORD_DTYPE)
+    for f in ("status", "voro_id", "tet_id"):
+        out[f] = recs[f]
+    ok = recs["status"] == 4
+    for f in ("weight", "nb_v", "nb_p", "nb_e", "is_active"):
+        out[f][ok] = recs[f][ok]
+    iv = (np.arange(96)[None, :] < recs["nb_v"][:, None]) & ok[:, None]
+    ip = (np.arange(64)[None, :] < recs["nb_p"][:, None]) & ok[:, None]
+    ie = (np.arange(152)[None, :] < recs["nb_e"][:, None]) & ok[:, None]
+    out["ver"][iv] = recs["ver"][iv]
+    clip = np.zeros_like(recs["clip"])
+    clip[..., :5] = recs["clip"][..., :5]
+    out["clip"][ip] = clip[ip]
+    out["id2"][ip] = recs["id2"][ip]
+    out["edge"][ie] = recs["edge"][ie]
+    return out
+
+
+def emit(recs, max_surf_fid):
+    """get_all_voro_info's per-cell emission (restated, rpd_update.cxx:112-301) for success records."""
+    recs = np.ascontiguousarray(recs)
+    n = len(recs)
+    cap = max(16, 40 * n)
+    out = {
+        "facet_cell": np.zeros(cap, np.int32), "facet_key": np.zeros(cap, np.int32),
+        "facet_is_tet": np.zeros(cap, np.uint8), "facet_centroid": np.zeros((cap, 3), np.float32),
+        "vert_cell": np.zeros(cap, np.int32), "vert_lvid": np.zeros(cap, np.int32),
+        "vert_key": np.zeros((cap, 3), np.int32), "vert_pos": np.zeros((cap, 3), np.float32),
+        "vert_surf_fid": np.zeros(cap, np.int32),
+        "edge_cell": np.zeros(cap, np.int32), "edge_key": np.zeros((cap, 2), np.int32),
+        "edge_lvid": np.zeros((cap, 2), np.int32),
+    }
+    cnt = np.zeros(3, np.int64)
+    order = ["facet_cell", "facet_key", "facet_is_tet", "facet_centroid", "vert_cell", "vert_lvid", "vert_key",
+             "vert_pos", "vert_surf_fid", "edge_cell", "edge_key", "edge_lvid"]
+    rc = lib().orc_emit(_p(recs), C.c_long(n), C.c_int(int(max_surf_fid)), C.c_long(cap), _p(cnt),
+                        *[_p(out[k]) for k in order])
+    assert rc == 0
+    for k in order:
+        m = cnt[0] if k.startswith("facet") else (cnt[1] if k.startswith("vert") else cnt[2])
+        out[k] = out[k][:m].copy()
+    return out

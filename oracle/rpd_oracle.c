@@ -739,3 +739,131 @@ void orc_cell_volumes(const orc_record* recs, long n, double* vol) {
     vol[i] = V;
   }
 }
+
+/* ---- a14 second half: reload_pc_explicit (voronoi_defs.cxx:108-188) + the per-cell part of
+ * get_all_voro_info (rpd_update.cxx:112-301) ------------------------------------------------- */
+/* face loop of an active plane: vertices referencing it, in the cyclic order of the walk at
+ * voronoi_defs.cxx:163-182.  Returns the loop length. */
+static int face_loop(const orc_record* r, int plane, int* loop) {
+  int tab_v[ORC_MAX_T], tab_lp[ORC_MAX_T], m = 0;
+  for (int t = 0; t < r->nb_v; t++) {
+    if (r->ver[t][0] == plane) { tab_v[m] = t; tab_lp[m++] = 0; }
+    else if (r->ver[t][1] == plane) { tab_v[m] = t; tab_lp[m++] = 1; }
+    else if (r->ver[t][2] == plane) { tab_v[m] = t; tab_lp[m++] = 2; }
+  }
+  int i = 0, n = 0;
+  while (n < m) {
+    int ind_i = (tab_lp[i] + 1) % 3;
+    int found = 0;
+    for (int j = 0; j < m && !found; j++) {
+      int ind_j = (tab_lp[j] + 2) % 3;
+      if (r->ver[tab_v[i]][ind_i] == r->ver[tab_v[j]][ind_j]) {
+        loop[n++] = tab_v[i];
+        found = 1;
+        i = j;
+      }
+    }
+    if (!found) break; /* the reference would run off the table here */
+  }
+  return n;
+}
+
+static int cmp_int(const void* a, const void* b) { return *(const int*)a - *(const int*)b; }
+
+long orc_emit(const orc_record* recs, long n, int max_surf_fid, long cap, long* counts,
+              int* f_cell, int* f_key, uint8_t* f_istet, float* f_centroid3, int* v_cell,
+              int* v_lvid, int* v_key3, float* v_pos3, int* v_surf, int* e_cell, int* e_key2,
+              int* e_lvid2) {
+  long nf = 0, nv = 0, ne = 0;
+  for (long c = 0; c < n; c++) {
+    const orc_record* r = recs + c;
+    if (r->status != ORC_success) continue;
+    uint8_t ap[ORC_MAX_P], ae[ORC_MAX_E];
+    reload_active_one(r, ap, ae, 0);
+    float pos[ORC_MAX_T][3];
+    for (int t = 0; t < r->nb_v; t++) {
+      const orc_float5 *p1 = &r->clip[r->ver[t][0]], *p2 = &r->clip[r->ver[t][1]],
+                       *p3 = &r->clip[r->ver[t][2]];
+      float x = -det3x3f(p1->w, p1->y, p1->z, p2->w, p2->y, p2->z, p3->w, p3->y, p3->z);
+      float y = -det3x3f(p1->x, p1->w, p1->z, p2->x, p2->w, p2->z, p3->x, p3->w, p3->z);
+      float z = -det3x3f(p1->x, p1->y, p1->w, p2->x, p2->y, p2->w, p3->x, p3->y, p3->w);
+      float w = det3x3f(p1->x, p1->y, p1->z, p2->x, p2->y, p2->z, p3->x, p3->y, p3->z);
+      pos[t][0] = x / w; pos[t][1] = y / w; pos[t][2] = z / w;
+    }
+    /* facets, rpd_update.cxx:121-140 */
+    for (int p = 0; p < r->nb_p; p++) {
+      if (!ap[p]) continue;
+      if (nf < cap) {
+        f_cell[nf] = (int)c;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        if (r->id2[p][1] != -1) {
+          f_key[nf] = r->id2[p][0] == r->voro_id ? r->id2[p][1] : r->id2[p][0];
+          f_istet[nf] = 0;
+        } else {
+          f_key[nf] = r->id2[p][0];
+          f_istet[nf] = 1;
+          if (r->id2[p][0] <= max_surf_fid) { /* get_cell_v2surffid, rpd_update.cxx:20-42 */
+            int loop[ORC_MAX_T];
+            int m = face_loop(r, p, loop);
+            for (int k = 0; k < m; k++) { cx = cx + pos[loop[k]][0]; cy = cy + pos[loop[k]][1]; cz = cz + pos[loop[k]][2]; }
+            cx = cx / (float)m; cy = cy / (float)m; cz = cz / (float)m;
+          }
+        }
+        f_centroid3[3 * nf] = cx; f_centroid3[3 * nf + 1] = cy; f_centroid3[3 * nf + 2] = cz;
+      }
+      nf++;
+    }
+    /* vertices, rpd_update.cxx:147-191 */
+    for (int t = 0; t < r->nb_v; t++) {
+      int seeds[3], ns = 0, surf = -1;
+      for (int i = 0; i < 3; i++) {
+        int lf = r->ver[t][i];
+        if (r->id2[lf][1] != -1) {
+          int nb = r->id2[lf][0] == r->voro_id ? r->id2[lf][1] : r->id2[lf][0];
+          int dup = 0;
+          for (int q = 0; q < ns; q++) dup |= seeds[q] == nb;
+          if (!dup) seeds[ns++] = nb;
+        } else if (r->id2[lf][0] <= max_surf_fid)
+          surf = r->id2[lf][0];
+      }
+      if (ns < 2) continue;
+      if (ns == 2) seeds[ns++] = -1;
+      qsort(seeds, 3, sizeof(int), cmp_int);
+      if (nv < cap) {
+        v_cell[nv] = (int)c; v_lvid[nv] = t;
+        memcpy(v_key3 + 3 * nv, seeds, sizeof seeds);
+        memcpy(v_pos3 + 3 * nv, pos[t], 3 * sizeof(float));
+        v_surf[nv] = surf;
+      }
+      nv++;
+    }
+    /* edges between two bisectors, rpd_update.cxx:195-200, 261-295 */
+    for (int e = 0; e < r->nb_e; e++) {
+      if (!ae[e]) continue;
+      int a = r->edge[e][0], b = r->edge[e][1];
+      if (r->id2[a][1] == -1 || r->id2[b][1] == -1) continue;
+      int k[2] = {r->id2[a][0] == r->voro_id ? r->id2[a][1] : r->id2[a][0],
+                  r->id2[b][0] == r->voro_id ? r->id2[b][1] : r->id2[b][0]};
+      if (k[0] > k[1]) { int s = k[0]; k[0] = k[1]; k[1] = s; }
+      /* end vertices = sorted intersection of the two face loops' vertex sets */
+      int la[ORC_MAX_T], lb[ORC_MAX_T];
+      int ma = face_loop(r, a, la), mb = face_loop(r, b, lb);
+      qsort(la, ma, sizeof(int), cmp_int);
+      qsort(lb, mb, sizeof(int), cmp_int);
+      int ends[2] = {-1, -1}, m = 0;
+      for (int i = 0, j = 0; i < ma && j < mb;) {
+        if (la[i] < lb[j]) i++;
+        else if (la[i] > lb[j]) j++;
+        else { if (m < 2) ends[m] = la[i]; m++; i++; j++; }
+      }
+      if (ne < cap) {
+        e_cell[ne] = (int)c;
+        e_key2[2 * ne] = k[0]; e_key2[2 * ne + 1] = k[1];
+        e_lvid2[2 * ne] = ends[0]; e_lvid2[2 * ne + 1] = ends[1];
+      }
+      ne++;
+    }
+  }
+  counts[0] = nf; counts[1] = nv; counts[2] = ne;
+  return (nf <= cap && nv <= cap && ne <= cap) ? 0 : -1;
+}

@@ -1,0 +1,74 @@
+"""GPU parity tests of dist2mat through the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_kat2_golden(ctx):
+    """each KAT as a 1-primitive list"""
+    cases = golden("kat2_dist2mat.json")
+    for c in cases:
+        sph = np.asarray(c["prims"], np.float32)
+        n = len(sph)
+        prim = {1: [-1, -1, 0], 2: [-1, 0, 1], 3: [0, 1, 2]}[n]
+        r, cid, _ = ctx.compute_closest_dist2mat(sph, np.asarray([c["pos"]], np.float32), np.zeros(1, np.uint32),
+                                                 np.ones(1, np.uint32), np.asarray([prim], np.int32))
+        want = np.uint32(c["bits"]).view(np.float32)
+        assert cid[0] == 0
+        assert r[0] == want or abs(float(r[0]) - float(want)) <= 1e-6 * max(1e-3, abs(float(want))), c
+
+
+def test_mini_golden(ctx, synth):
+    g = golden("mini_dist2mat.npz")
+    d = synth.make_dist2mat(2000, nu=20, nv=40, n_slabs=2400, n_cones=1200)
+    r, cid, tie = ctx.compute_closest_dist2mat(d.spheres, d.samples, d.offset, d.count, d.prims)
+    rel = np.abs(r - g["result"]) / np.maximum(np.abs(g["result"]), 1e-3)
+    assert rel.max() <= 1e-6
+    assert not np.any((cid != g["closest_id"]) & (tie == 0))
+
+
+def test_vs_oracle_200k(ctx, O, synth):
+    d = synth.make_dist2mat(200000)
+    r, cid, tie = ctx.compute_closest_dist2mat(d.spheres, d.samples, d.offset, d.count, d.prims)
+    ro, co, _ = O.dist2mat(d, "oracle")
+    rel = np.abs(r - ro) / np.maximum(np.abs(ro), 1e-3)
+    assert rel.max() <= 1e-6  # north_star tolerance
+    assert np.mean(r.view(np.uint32) == ro.view(np.uint32)) > 0.999
+    assert not np.any((cid != co) & (tie == 0))  # argmin ids equal apart from flagged exact ties
+    assert tie.mean() < 0.01
+
+
+def test_vs_reference_build(ctx, O, synth):
+    if O.ref("d2m") is None:
+        pytest.skip("oracle/_ref not built")
+    d = synth.make_dist2mat(50000)
+    r, cid, tie = ctx.compute_closest_dist2mat(d.spheres, d.samples, d.offset, d.count, d.prims)
+    rr, cr, _ = O.dist2mat(d, "ref")
+    rel = np.abs(r - rr) / np.maximum(np.abs(rr), 1e-3)
+    assert rel.max() <= 1e-6
+    assert not np.any((cid != cr) & (tie == 0))
+
+
+def test_empty_and_ragged_lists(ctx, synth):
+    """empty list -> (1e16f, -1) (dist2mat.cu:224-231); lists longer than one warp stride"""
+    sph = np.array([[0, 0, 0, 1], [3, 0, 0, 0.5], [0, 4, 0, 0.25]], np.float32)
+    samples = np.array([[0, 0, 2], [3, 0, 1], [9, 9, 9]], np.float32)
+    prims = np.array([[-1, -1, 0]] + [[-1, -1, 1]] * 40 + [[-1, -1, 2]], np.int32)
+    offset = np.array([0, 1, 0], np.uint32)
+    count = np.array([1, 41, 0], np.uint32)
+    r, cid, tie = ctx.compute_closest_dist2mat(sph, samples, offset, count, prims)
+    assert r[0] == 1.0 and cid[0] == 0
+    # 40 identical spheres then a farther one: winner = highest lane among exact ties (dist2mat.cu:269-276)
+    assert r[1] == 0.5 and cid[1] == 31 and tie[1] == 1
+    assert r[2] == np.float32(1e16) and cid[2] == -1
+
+
+def test_nan_swallowing_clamp(ctx):
+    """coincident centres: t = 0/0 -> clamp gives 1 -> distance to the smaller sphere (KAT-2b)"""
+    sph = np.array([[0, 0, 0, 0.1], [0, 0, 0, 0.2]], np.float32)
+    r, cid, _ = ctx.compute_closest_dist2mat(sph, np.array([[0.3, 0.4, 0]], np.float32), np.zeros(1, np.uint32),
+                                             np.ones(1, np.uint32), np.array([[-1, 0, 1]], np.int32))
+    assert abs(r[0] - 0.4) < 1e-6

@@ -1,0 +1,242 @@
+"""GPU parity tests of the RPD path, through the C ABI (libmat_b200.so) against the oracle, the
+reference build (oracle/_ref, when present) and the committed golden vectors."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle.gen_golden import kat1_inputs, mini_inputs
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("status", "voro_id", "tet_id", "weight", "nb_v", "nb_p", "nb_e", "ver", "id2", "edge")
+
+
+def assert_defined_equal(O, a, b):
+    d = O.defined_equal(a, b)
+    assert all(v == 0 for f, v in d.items() if f != "cells_compared"), d
+    assert d["cells_compared"] == len(a)
+
+
+def run_given(ctx, mesh, sites, knn, k, **kw):
+    ctx.set_mesh(mesh)
+    return ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, knn, k, **kw)
+
+
+def test_kat1_golden(ctx, O):
+    g = golden("kat1_rpd.npz")
+    mesh, sites, knn, k = kat1_inputs()
+    res = run_given(ctx, mesh, sites, knn, k)
+    recs = res.records()
+    assert res.n_cells == 2 and res.n_pairs == 2
+    for f in FIELDS:
+        assert np.array_equal(recs[f], g[f]), f
+    assert np.array_equal(recs["clip"][..., :5].view(np.uint32), g["clip"][..., :5].view(np.uint32))
+    assert recs["id"].tolist() == [0, 1] and (recs["is_active"] == 1).all()
+    assert (recs["euler"] == -1).all() and (recs["cell_vol"] == -1).all()  # copy(), convex_cell.cu:933-949
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_mini_golden(ctx, O, lanes):
+    g = golden("mini_rpd.npz")
+    mesh, sites, knn, k = mini_inputs()
+    res = run_given(ctx, mesh, sites, knn, k, lanes_per_cell=lanes)
+    ok = g["status"] == 4
+    assert res.n_pairs == len(g["pair_tet"])
+    assert res.n_cells == int(ok.sum())
+    recs = res.records()
+    for f in FIELDS:
+        assert np.array_equal(recs[f], g[f][ok]), f
+    assert np.array_equal(recs["clip"][..., :5].view(np.uint32), g["clip"][ok][..., :5].view(np.uint32))
+    # per-pair status histogram (index = status + 1) equals the reference's record statuses
+    assert np.array_equal(res.status_histogram, np.bincount(g["status"] + 1, minlength=10))
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_cfg1_given_vs_oracle(ctx, O, cfg1, cfg1_oracle, lanes):
+    """BASELINE configs[0] (20 250 tets, 1 000 spheres, k=80): byte-identical on defined entries."""
+    mesh, sites, knn, k = cfg1
+    pt, ps, ra, sa = cfg1_oracle
+    res = run_given(ctx, mesh, sites, knn, k, lanes_per_cell=lanes)
+    assert res.n_pairs == len(pt)
+    want = ra[ra["status"] == 4]
+    assert res.n_cells == len(want)
+    recs = res.records()
+    assert_defined_equal(O, want, recs)
+    assert np.array_equal(recs["id"], np.arange(len(recs)))
+    key = recs["tet_id"].astype(np.int64) * sites.n_site + recs["voro_id"]
+    assert (np.diff(key) > 0).all()  # sorted by (tet, site), voronoi.cu:744-769
+    assert np.array_equal(res.status_histogram, np.bincount(ra["status"] + 1, minlength=10))
+
+
+def test_cfg1_given_vs_reference_build(ctx, O, cfg1, cfg1_oracle):
+    if O.ref("rpd") is None:
+        pytest.skip("oracle/_ref not built")
+    mesh, sites, knn, k = cfg1
+    pt, ps, _, _ = cfg1_oracle
+    rb, sb, _ = O.run_pairs(mesh, sites, knn, k, pt, ps, impl="ref")
+    res = run_given(ctx, mesh, sites, knn, k)
+    assert_defined_equal(O, rb[rb["status"] == 4], res.records())
+
+
+def test_overflow_classes(ctx, O, synth):
+    """dense sites on a tiny mesh: plane / triangle / edge overflow cells are dropped like the
+    reference drops them (status parity per pair)."""
+    mesh = synth.make_ball_mesh(2)
+    sites = synth.make_spheres(400, stream=5)
+    knn, k = synth.knn_site_lists(sites, 120)
+    pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
+    ra, sa, _ = O.run_pairs(mesh, sites, knn, k, pt, ps, impl="oracle")
+    res = run_given(ctx, mesh, sites, knn, k)
+    assert res.n_pairs == len(pt)
+    assert np.array_equal(res.status_histogram, np.bincount(ra["status"] + 1, minlength=10))
+    assert_defined_equal(O, ra[ra["status"] == 4], res.records())
+
+
+def test_tet_range_shards_concatenate(ctx, O, cfg1):
+    """tet shards (multi-GPU partition): the concatenation of shard results == the full result."""
+    mesh, sites, knn, k = cfg1
+    full = run_given(ctx, mesh, sites, knn, k).records()
+    parts = []
+    cuts = [0, 5000, 5001, 13000, mesh.n_tet]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ctx.set_tet_range(a, b - a)
+        parts.append(ctx.run().records())
+    ctx.set_tet_range(0, -1)
+    cat = np.concatenate(parts)
+    cat["id"] = np.arange(len(cat))
+    cat["thread_id"] = cat["id"]
+    assert cat.tobytes() == full.tobytes()
+
+
+def test_empty_range_and_unselected(ctx, O, cfg1):
+    mesh, sites, knn, k = cfg1
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, knn, k)
+    ctx.set_tet_range(10, 0)
+    r = ctx.run()
+    assert r.n_cells == 0 and r.n_pairs == 0 and len(r.records()) == 0
+    ctx.set_tet_range(0, -1)
+    # no site selected -> no cells (voronoi.cu:165-169)
+    r = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, np.zeros(sites.n_site, np.uint32), knn, k)
+    assert r.n_cells == 0
+
+
+def test_partially_selected_sites(ctx, O, cfg1, synth):
+    """N+1ring selected, 2-ring clipped against only (rpd_api.cxx:371-373)."""
+    mesh, sites, knn, k = cfg1
+    flags = (np.arange(sites.n_site) % 3 != 0).astype(np.uint32)
+    s2 = synth.Sites(sites.site_soa, sites.weights, flags, sites.radii)
+    pt, ps = O.tet_sphere_relation(mesh, s2, knn, k)
+    assert flags[ps].all()
+    ra, _, _ = O.run_pairs(mesh, s2, knn, k, pt, ps)
+    res = run_given(ctx, mesh, s2, knn, k)
+    assert res.n_pairs == len(pt)
+    assert_defined_equal(O, ra[ra["status"] == 4], res.records())
+
+
+def test_partial_tets_and_dense_e_adjs(ctx, O, synth):
+    """partial-tet call (rpd_api.cxx:254-281): subset idx/f_adjs/f_ids with GLOBAL vertices, and
+    the reference's dense e_adjs table instead of the compact 6-per-tet form."""
+    mesh = synth.make_ball_mesh(6)
+    sites = synth.make_spheres(120)
+    knn, k = synth.knn_site_lists(sites, 60)
+    sel = np.arange(mesh.n_tet)[::3]
+    sub = synth.TetMesh(mesh.vertices, mesh.indices[sel], mesh.v_adjs, mesh.e_adj6[sel], mesh.f_adjs[sel],
+                        mesh.f_ids[sel], mesh.n_surf_faces)
+    pt, ps = O.tet_sphere_relation(sub, sites, knn, k)
+    ra, _, _ = O.run_pairs(sub, sites, knn, k, pt, ps)
+    want = ra[ra["status"] == 4]
+    ctx.set_tetmesh(sub.vertices, sub.indices, sub.v_adjs, sub.f_adjs, sub.f_ids, e_adjs_dense=mesh.dense_e_adjs())
+    res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, knn, k)
+    assert_defined_equal(O, want, res.records())
+
+
+def test_site_without_neighbours(ctx, O, synth):
+    """a site with zero real neighbours relates to every tet and owns every tet whole (voronoi.cu:171-190)."""
+    mesh = synth.make_ball_mesh(3)
+    sites = synth.make_spheres(1)
+    knn = np.full((2, 1), -1, np.int32)
+    res = run_given(ctx, mesh, sites, knn, 1)
+    assert res.n_cells == mesh.n_tet
+    recs = res.records()
+    assert (recs["nb_v"] == 4).all() and (recs["nb_p"] == 4).all() and (recs["nb_e"] == 6).all()
+    pt, ps = O.tet_sphere_relation(mesh, sites, knn, 1)
+    ra, _, _ = O.run_pairs(mesh, sites, knn, 1, pt, ps)
+    assert_defined_equal(O, ra, recs)
+
+
+def test_compact_blob_round_trip(ctx, O, cfg1):
+    """the compact result (what NCCL gathers) expands to exactly the fetched records"""
+    mesh, sites, knn, k = cfg1
+    res = run_given(ctx, mesh, sites, knn, k)
+    blob, offs = res.compact()
+    assert offs[0] == 0 and offs[-1] == res.compact_bytes and (np.diff(offs) > 0).all()
+    recs = res.records()
+    w = blob[offs[:-1] // 4 + 2]
+    assert np.array_equal(w & 0xff, recs["nb_v"]) and np.array_equal((w >> 8) & 0xff, recs["nb_p"])
+    assert np.array_equal(blob[offs[:-1] // 4].astype(np.int32), recs["tet_id"])
+    sizes = 4 * (4 + recs["nb_v"].astype(np.int64) + 7 * recs["nb_p"] + (3 * recs["nb_e"].astype(np.int64) + 3) // 4)
+    assert np.array_equal(np.diff(offs), sizes)
+
+
+def test_error_paths(ctx):
+    from libmat_b200.rpd import Context, LibMatError
+    c = Context(0)
+    with pytest.raises(LibMatError, match="mb_set_tetmesh"):
+        c.upload_sites(np.zeros(3, np.float32), np.ones(1, np.float32), np.ones(1, np.uint32))
+        c.run()
+    with pytest.raises(LibMatError):
+        c.run(lanes_per_cell=5)
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# grid-kNN mode
+# ------------------------------------------------------------------------------------------------
+def canon_equal(O, a, b):
+    ca, cb = O.canonicalize(a), O.canonicalize(b)
+    d = O.defined_equal(ca, cb)
+    return d
+
+
+@pytest.mark.parametrize("n,ns", [(4, 40), (8, 150)])
+def test_grid_mode_canonical_parity(ctx, O, synth, n, ns):
+    """grid-kNN mode vs the reference semantics given ALL other sites as neighbours (a sufficient
+    list): same cells, same canonical combinatorics (SURVEY 8a parity form)."""
+    mesh = synth.make_ball_mesh(n)
+    sites = synth.make_spheres(ns)
+    knn, k = synth.site_lists_from_sets([[m for m in range(ns) if m != s] for s in range(ns)], ns)
+    pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
+    ra, sa, _ = O.run_pairs(mesh, sites, knn, k, pt, ps)
+    want = ra[ra["status"] == 4]
+    ctx.set_mesh(mesh)
+    res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
+    got = res.records()
+    ka = want["tet_id"].astype(np.int64) * ns + want["voro_id"]
+    kb = got["tet_id"].astype(np.int64) * ns + got["voro_id"]
+    # cells whose volume is at rounding level may appear on one side only (flagged class)
+    common = np.intersect1d(ka, kb)
+    only_a, only_b = np.setdiff1d(ka, kb), np.setdiff1d(kb, ka)
+    va = O.cell_volumes(want[np.isin(ka, only_a)])
+    vb = O.cell_volumes(got[np.isin(kb, only_b)])
+    assert (va < 1e-2).all() and (vb < 1e-2).all(), (va, vb)
+    assert len(common) > 0.99 * len(ka)
+    d = canon_equal(O, want[np.isin(ka, common)], got[np.isin(kb, common)])
+    n_bad = max(v for f, v in d.items() if f != "cells_compared")
+    assert n_bad <= 0.002 * len(common), d  # degenerate (|det| at rounding level) cells only
+
+
+def test_grid_mode_tiles_every_tet(ctx, O, cfg1):
+    """property at config-1 size: the cells of each tet tile it (volume conservation), and every
+    bisector facet (s, m) of a tet has its mirror (m, s) in the same tet."""
+    mesh, sites, _, _ = cfg1
+    ctx.set_mesh(mesh)
+    res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
+    recs = res.records()
+    cv = O.cell_volumes(recs)
+    pv = np.zeros(mesh.n_tet)
+    np.add.at(pv, recs["tet_id"], cv)
+    tv = mesh.tet_volumes()
+    assert np.max(np.abs(pv - tv) / tv) < 2e-3
+    assert abs(pv.sum() - tv.sum()) / tv.sum() < 1e-5
+    assert res.status_histogram[[1, 2, 3, 8, 9]].sum() == 0  # no overflow / inconsistent cells

@@ -1,0 +1,114 @@
+"""The plain-C oracle against the committed golden vectors (generated from the reference's own
+code by oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle.gen_golden import kat1_inputs, mini_inputs
+
+
+def _cmp(recs, g):
+    for f in ("status", "voro_id", "tet_id", "weight", "nb_v", "nb_p", "nb_e", "ver", "id2", "edge"):
+        assert np.array_equal(recs[f], g[f]), f
+    assert np.array_equal(recs["clip"].view(np.uint32), g["clip"].view(np.uint32)), "clip (bitwise)"
+
+
+def test_kat1_single_tet(O):
+    """cell(A) nb_v 6 nb_p 5 nb_e 9, cell(B) nb_v 4; volumes add up to the tet."""
+    g = golden("kat1_rpd.npz")
+    mesh, sites, knn, k = kat1_inputs()
+    recs, stat, _, vol, _ = O.run_pairs(mesh, sites, knn, k, np.array([0, 0], np.int32),
+                                        np.array([0, 1], np.int32), impl="oracle", want_vol=True)
+    recs = O.zero_undefined(recs)
+    _cmp(recs, g)
+    assert np.array_equal(stat, g["stat"])
+    assert recs["nb_v"].tolist() == [6, 4] and recs["nb_p"].tolist() == [5, 5] and recs["nb_e"][0] == 9
+    assert recs["clip"][0, 4, :4].tolist() == [-500.0, -100.0, -50.0, 194300.0]
+    assert recs["clip"][0, 0, :4].tolist() == [-1e6, -1e6, -1e6, 1e9]
+    assert recs["ver"][0, :6, :3].tolist() == [[1, 3, 2], [0, 1, 2], [0, 3, 1], [4, 0, 2], [4, 2, 3], [4, 3, 0]]
+    assert np.array_equal(vol.view(np.uint32), g["site_vol"].view(np.uint32))
+    assert abs(float(vol.sum()) - 1e9 / 6) < 1e9 / 6 * 1e-5
+
+
+def test_mini_records(O):
+    g = golden("mini_rpd.npz")
+    mesh, sites, knn, k = mini_inputs()
+    pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
+    assert np.array_equal(pt, g["pair_tet"]) and np.array_equal(ps, g["pair_site"])
+    recs, stat, _, vol, bary = O.run_pairs(mesh, sites, knn, k, pt, ps, impl="oracle", n_threads=1, want_vol=True)
+    recs = O.zero_undefined(recs)
+    _cmp(recs, g)
+    assert np.array_equal(stat, g["stat"])
+    assert np.array_equal(vol.view(np.uint32), g["site_vol"].view(np.uint32))
+    assert np.array_equal(bary.view(np.uint32), g["site_bary"].view(np.uint32))
+    ok = recs["status"] == 4
+    ap, ae, eu = O.reload_active(recs[ok], "oracle")
+    assert np.array_equal(np.packbits(ap, axis=1), g["active_planes"])
+    assert np.array_equal(np.packbits(ae, axis=1), g["active_edges"])
+    assert np.array_equal(eu.view(np.uint32), g["euler"].view(np.uint32))
+    vc = O.vertex_coordinates(recs[ok], "oracle")
+    assert np.array_equal(vc[..., :3].view(np.uint32), g["vertex_xyzw"][..., :3].view(np.uint32))  # .w: oracle keeps the det, the reference returns 1
+
+
+def test_mini_volume_conservation(O, synth):
+    """property: the cells of a tet tile it (sum of cell volumes == tet volume)."""
+    g = golden("mini_rpd.npz")
+    mesh, _, _, _ = mini_inputs()
+    recs = np.zeros(len(g["status"]), dtype=O.RECORD_DTYPE)
+    for f in ("status", "voro_id", "tet_id", "weight", "nb_v", "nb_p", "nb_e", "ver", "clip", "id2", "edge"):
+        recs[f] = g[f]
+    recs = recs[recs["status"] == 4]
+    cv = O.cell_volumes(recs)
+    pv = np.zeros(mesh.n_tet)
+    np.add.at(pv, recs["tet_id"], cv)
+    tv = mesh.tet_volumes()
+    assert np.max(np.abs(pv - tv) / tv) < 1e-4
+
+
+def test_kat2_dist2mat_functions(O):
+    cases = golden("kat2_dist2mat.json")
+    lib = O.lib()
+    for c in cases:
+        p = np.asarray(c["pos"], np.float32)
+        pr = [np.asarray(x, np.float32) for x in c["prims"]]
+        if c["kind"] == "sphere":
+            v = lib.orc_distance_to_sphere(O._p(p), O._p(pr[0]))
+        elif c["kind"] == "cone":
+            v = lib.orc_distance_to_cone(O._p(p), O._p(pr[0]), O._p(pr[1]))
+        else:
+            v = lib.orc_distance_to_slab(O._p(p), O._p(pr[0]), O._p(pr[1]), O._p(pr[2]))
+        got = np.float32(v)
+        want = np.uint32(c["bits"]).view(np.float32)
+        # bit-exact except where the reference calls powf(x, 2.f) (glibc powf vs x*x: <= 1 ulp
+        # on an intermediate); tolerance = north_star's 1e-6 relative
+        assert got == want or abs(float(got) - float(want)) <= 1e-6 * max(1e-3, abs(float(want))), c
+
+
+def test_kat2_known_values():
+    """the values quoted in SURVEY 8c"""
+    cases = golden("kat2_dist2mat.json")
+    vals = [c["value"] for c in cases]
+    for got, want in zip(vals[:9], [0.346616089, 0.348769188, 0.348769188, 0.467810512, 0.389207929,
+                                     0.578708768, 0.699999988, 0.400000006, 0.400000006]):
+        assert abs(got - want) < 1e-8
+
+
+def test_mini_dist2mat(O, synth):
+    g = golden("mini_dist2mat.npz")
+    d = synth.make_dist2mat(2000, nu=20, nv=40, n_slabs=2400, n_cones=1200)
+    res, cid, _, sec = O.dist2mat(d, "oracle", n_threads=1, want_second=True)
+    want = g["result"]
+    rel = np.abs(res - want) / np.maximum(np.abs(want), 1e-3)
+    assert rel.max() <= 1e-6
+    bad = cid != g["closest_id"]
+    # argmin ids may differ only on flagged ties (two best distances within 1e-6 relative)
+    tie = (sec - res) <= 1e-6 * np.maximum(np.abs(res), np.abs(sec))
+    assert not np.any(bad & ~tie)
+
+
+def test_kat3_predicate_bounds():
+    """the static-filter bounds the product carries are the predicate_generator's outputs"""
+    g = golden("kat3_predicates.json")
+    from libmat_b200 import capi
+    assert float(g["bound_double"]) == capi.FILTER_BOUND_F64 == 1.2466136531027298e-13
+    assert np.float32(g["bound_float"]) == np.float32(capi.FILTER_BOUND_F32) == np.float32(6.6876506e-05)
