@@ -1,0 +1,109 @@
+// libmat_b200 -- C++ shim with the reference's exact host signature for the RPD path.
+//
+// Header-only; compile it INSIDE LibMAT (it includes LibMAT's own voronoi_defs.h, so the
+// ConvexCellHost it fills is the caller's type, whatever its std::vector ABI) and link
+// libmat_b200.so.  It replaces the body of
+//     compute_clipped_voro_diagram_GPU      reference src/rpd3d/voronoi.cu:455-795
+//                                           (declaration src/rpd3d/voronoi.h:52-61)
+// and is what RPD3D_GPU::calculate / calculate_partial call (src/rpd3d_api/rpd_api.cxx:117-123,
+// 275-281).  Everything below the signature goes through the C ABI of include/libmat_b200.h.
+//
+// Behaviour kept: returns the valid cells sorted by (tet, site) with ConvexCellHost::id = index
+// (voronoi.cu:744-769) filled by the copy_cc rule (:433-449: is_active = true, euler/weight/
+// counts/arrays copied, cell_vol left at its default); never throws; site_cell_vol is resized and
+// zero-filled like the reference leaves it (:501-502, never written back).  v2tets,
+// num_itr_global, nb_Lloyd_iter and preferred_tet_k are accepted and unused, as in the reference.
+// Behaviour changed on purpose: no process exit() on CUDA errors (an empty vector is returned and
+// the message is printed to stderr), no record.csv appended in the CWD (:571-579), no device 0
+// hard-wiring (MB_DEVICE environment variable, default: current device).
+#pragma once
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <vector>
+
+#include "libmat_b200.h"
+#include "voronoi_defs.h"  // LibMAT's own header (src/rpd3d_base/voronoi_defs.h)
+
+#include "libmat_b200_shim_ctx.hpp"
+
+namespace libmat_b200 {
+
+// compact record (see DESIGN.md "compact cell record") -> ConvexCellHost, the copy_cc rule
+inline void expand_cell(const uint32_t* w, int id, ConvexCellHost& c) {
+  const int nb_v = w[2] & 0xff, nb_p = (w[2] >> 8) & 0xff, nb_e = (w[2] >> 16) & 0xff;
+  c.is_active = true;
+  c.status = static_cast<Status>((int)(w[2] >> 24));
+  c.thread_id = id;
+  c.voro_id = (int)w[1];
+  c.tet_id = (int)w[0];
+  c.euler = -1.f;
+  std::memcpy(&c.weight, &w[3], 4);
+  c.nb_v = (uchar)nb_v;
+  c.nb_p = (uchar)nb_p;
+  c.nb_e = (uchar)nb_e;
+  const uint32_t* p = w + 4;
+  std::memcpy(c.ver_data_trans, p, 4 * (size_t)nb_v);
+  p += nb_v;
+  const float* pl = reinterpret_cast<const float*>(p);
+  p += 4 * nb_p;
+  for (int i = 0; i < nb_p; i++) {
+    float h;
+    std::memcpy(&h, &p[3 * i + 2], 4);
+    c.clip_data_trans[i] = cmake_float5(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3], h);
+    c.clip_id2_data_trans[i] = cmake_int2((int)p[3 * i], (int)p[3 * i + 1]);
+  }
+  p += 3 * nb_p;
+  std::memcpy(c.edge_data, p, 3 * (size_t)nb_e);
+  c.id = id;
+}
+
+}  // namespace libmat_b200
+
+#ifndef LIBMAT_B200_NO_REFERENCE_NAMES
+inline std::vector<ConvexCellHost> compute_clipped_voro_diagram_GPU(
+    const int num_itr_global, const std::vector<float>& vertices, const std::vector<int>& indices,
+    const std::map<int, std::set<int>>& v2tets, const std::vector<int>& v_adjs,
+    const std::vector<int>& e_adjs, const std::vector<int>& f_adjs, const std::vector<int>& f_ids,
+    std::vector<float>& site, const int n_site, const std::vector<float>& site_weights,
+    const std::vector<uint>& site_flags, const std::vector<int>& site_knn, const int site_k,
+    std::vector<float>& site_cell_vol, const bool site_is_transposed, int nb_Lloyd_iter = 1,
+    int preferred_tet_k = 0) {
+  (void)num_itr_global; (void)v2tets; (void)site_is_transposed; (void)nb_Lloyd_iter; (void)preferred_tet_k;
+  std::vector<ConvexCellHost> out;
+  site_cell_vol.assign((size_t)n_site, 0.f);  // voronoi.cu:501-502
+  mb_ctx* ctx = libmat_b200::thread_ctx();
+  if (!ctx) return out;
+  const int n_vert = (int)(vertices.size() / 3), n_tet = (int)(indices.size() / 4);
+  auto fail = [&](const char* what) {
+    std::fprintf(stderr, "[libmat_b200] %s: %s\n", what, mb_last_error(ctx));
+    return std::vector<ConvexCellHost>();
+  };
+  // the reference's dense triangular e_adjs (io.cxx:264) is accepted as given
+  if (mb_set_tetmesh(ctx, vertices.data(), n_vert, indices.data(), n_tet, v_adjs.data(), e_adjs.data(), nullptr,
+                     f_adjs.data(), f_ids.data()))
+    return fail("mb_set_tetmesh");
+  mb_rpd_result* res = nullptr;
+  // an empty site_knn selects the library's own uniform-grid neighbour search
+  const int* knn = site_knn.empty() ? nullptr : site_knn.data();
+  if (mb_rpd3d(ctx, site.data(), site_weights.data(), site_flags.data(), n_site, knn, site_k, nullptr, &res))
+    return fail("mb_rpd3d");
+  long n_cells = 0, n_bytes = 0;
+  mb_rpd_count(res, &n_cells, nullptr, nullptr);
+  mb_rpd_compact_bytes(res, &n_bytes);
+  std::vector<uint32_t> blob((size_t)n_bytes / 4 + 1);
+  std::vector<long> offs((size_t)n_cells + 1);
+  if (mb_rpd_fetch_compact(res, blob.data(), offs.data())) {
+    mb_rpd_free(res);
+    return fail("mb_rpd_fetch_compact");
+  }
+  mb_rpd_free(res);
+  out.resize((size_t)n_cells);
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n_cells; i++) libmat_b200::expand_cell(blob.data() + offs[i] / 4, (int)i, out[(size_t)i]);
+  return out;
+}
+#endif

@@ -185,6 +185,18 @@ int mb_rpd_count(const mb_rpd_result* res, long* n_cells, long* n_pairs, long* n
   return MB_OK;
 }
 
+int mb_rpd_stats(const mb_rpd_result* res, long stats[8]) {
+  if (!res || !stats) return MB_ERR_ARG;
+  stats[0] = res->n_cells;
+  stats[1] = res->n_pairs;
+  stats[2] = res->n_clips;
+  stats[3] = res->n_culled;
+  stats[4] = res->n_cand_overflow;
+  stats[5] = res->compact_bytes;
+  stats[6] = stats[7] = 0;
+  return MB_OK;
+}
+
 int mb_rpd_status_histogram(const mb_rpd_result* res, long hist[10]) {
   if (!res || !hist) return MB_ERR_ARG;
   for (int i = 0; i < 10; i++) hist[i] = res->hist[i];

@@ -108,7 +108,7 @@ struct RpdCounters {
 
 struct mb_rpd_result {
   mb_ctx* ctx = nullptr;
-  long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0;
+  long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0, n_cand_overflow = 0;
   long hist[10] = {0};
   long compact_bytes = 0;
   float ms[4] = {0, 0, 0, 0};

@@ -497,6 +497,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   res->n_cells = (long)hc.n_valid;
   res->n_clips = (long)hc.n_clips;
   res->n_culled = (long)hc.n_culled;
+  res->n_cand_overflow = (long)hc.n_cand_overflow;
   for (int i = 0; i < 10; i++) res->hist[i] = (long)hc.hist[i];
 
   // ---- ordering: scan + gather into (tet, site) order -------------------------------------------

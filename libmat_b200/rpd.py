@@ -29,6 +29,9 @@ class RpdResult:
         a, b, c = C.c_long(), C.c_long(), C.c_long()
         ctx._check(lib.mb_rpd_count(handle, C.byref(a), C.byref(b), C.byref(c)))
         self.n_cells, self.n_pairs, self.n_clips = a.value, b.value, c.value
+        st = (C.c_long * 8)()
+        ctx._check(lib.mb_rpd_stats(handle, st))
+        self.n_culled, self.n_cand_overflow = st[3], st[4]
         hist = (C.c_long * 10)()
         ctx._check(lib.mb_rpd_status_histogram(handle, hist))
         self.status_histogram = np.array(list(hist), dtype=np.int64)  # index = status + 1

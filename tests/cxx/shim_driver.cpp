@@ -1,0 +1,112 @@
+// Test driver for the C++ shims (include/libmat_b200_shim.hpp, libmat_b200_dist2mat_shim.hpp):
+// a host program that calls compute_clipped_voro_diagram_GPU / compute_closest_dist2mat with the
+// reference's exact signatures and the reference's own types (ConvexCellHost, GpuBuffer from
+// /root/reference, included in place at build time), then runs the reference's own
+// ConvexCellHost::reload_active / cal_cell_euler on the returned cells.
+//   shim_driver rpd <in.bin> <out.bin>     |   shim_driver d2m <in.bin> <out.bin>
+// Built by tests/cxx/Makefile into tests/cxx/_build/ (git-ignored, travels to the GPU box).
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "libmat_b200_dist2mat_shim.hpp"
+#include "libmat_b200_shim.hpp"
+
+template <typename T>
+static std::vector<T> rd(FILE* f) {
+  int64_t n = 0;
+  if (fread(&n, 8, 1, f) != 1) n = 0;
+  std::vector<T> v((size_t)n);
+  if (n && fread(v.data(), sizeof(T), (size_t)n, f) != (size_t)n) v.clear();
+  return v;
+}
+template <typename T>
+static void wr(FILE* f, const T* p, int64_t n) {
+  fwrite(&n, 8, 1, f);
+  if (n) fwrite(p, sizeof(T), (size_t)n, f);
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) return 2;
+  FILE* in = fopen(argv[2], "rb");
+  FILE* out = fopen(argv[3], "wb");
+  if (!in || !out) return 3;
+  if (std::string(argv[1]) == "rpd") {
+    auto vertices = rd<float>(in);
+    auto indices = rd<int>(in);
+    auto v_adjs = rd<int>(in);
+    auto e_adjs = rd<int>(in);
+    auto f_adjs = rd<int>(in);
+    auto f_ids = rd<int>(in);
+    auto site = rd<float>(in);
+    auto w = rd<float>(in);
+    auto flags = rd<uint>(in);
+    auto knn = rd<int>(in);
+    auto meta = rd<int>(in);  // n_site, site_k
+    std::map<int, std::set<int>> v2tets;
+    std::vector<float> vol;
+    std::vector<ConvexCellHost> cells = compute_clipped_voro_diagram_GPU(
+        0, vertices, indices, v2tets, v_adjs, e_adjs, f_adjs, f_ids, site, meta[0], w, flags, knn, meta[1], vol, true);
+    // dump the POD tail of every cell + the reference's own euler
+    const int64_t n = (int64_t)cells.size();
+    std::vector<int> hdr(8 * (size_t)n);
+    std::vector<float> euler((size_t)n);
+    std::vector<unsigned char> ver(4 * _MAX_T_ * (size_t)n, 0), edge(3 * _MAX_E_ * (size_t)n, 0);
+    std::vector<float> clip(5 * _MAX_P_ * (size_t)n, 0.f);
+    std::vector<int> id2(2 * _MAX_P_ * (size_t)n, 0);
+    for (int64_t i = 0; i < n; i++) {
+      ConvexCellHost& c = cells[(size_t)i];
+      int* h = &hdr[8 * (size_t)i];
+      h[0] = (int)c.status; h[1] = c.voro_id; h[2] = c.tet_id; h[3] = c.id; h[4] = c.nb_v; h[5] = c.nb_p; h[6] = c.nb_e;
+      h[7] = c.is_active ? 1 : 0;
+      for (int t = 0; t < c.nb_v; t++) memcpy(&ver[4 * (_MAX_T_ * (size_t)i + t)], &c.ver_data_trans[t], 4);
+      for (int p = 0; p < c.nb_p; p++) {
+        float* q = &clip[5 * (_MAX_P_ * (size_t)i + p)];
+        q[0] = c.clip_data_trans[p].x; q[1] = c.clip_data_trans[p].y; q[2] = c.clip_data_trans[p].z;
+        q[3] = c.clip_data_trans[p].w; q[4] = c.clip_data_trans[p].h;
+        id2[2 * (_MAX_P_ * (size_t)i + p)] = c.clip_id2_data_trans[p].x;
+        id2[2 * (_MAX_P_ * (size_t)i + p) + 1] = c.clip_id2_data_trans[p].y;
+      }
+      for (int e = 0; e < c.nb_e; e++) memcpy(&edge[3 * (_MAX_E_ * (size_t)i + e)], &c.edge_data[e], 3);
+      c.reload_active();                      // the reference's own post-processing on our cells
+      euler[(size_t)i] = (float)c.cal_cell_euler();
+    }
+    wr(out, hdr.data(), (int64_t)hdr.size());
+    wr(out, ver.data(), (int64_t)ver.size());
+    wr(out, clip.data(), (int64_t)clip.size());
+    wr(out, id2.data(), (int64_t)id2.size());
+    wr(out, edge.data(), (int64_t)edge.size());
+    wr(out, euler.data(), (int64_t)euler.size());
+    wr(out, vol.data(), (int64_t)vol.size());
+  } else {
+    auto sph = rd<float>(in);
+    auto smp = rd<float>(in);
+    auto off = rd<uint>(in);
+    auto cnt = rd<uint>(in);
+    auto pr = rd<int>(in);
+    const int n = (int)off.size();
+    GpuBuffer<float4> b_sph(sph.size() / 4);
+    GpuBuffer<float3> b_smp((size_t)n);
+    GpuBuffer<uint> b_off((size_t)n), b_cnt((size_t)n);
+    GpuBuffer<int3> b_pr(pr.size() / 3);
+    GpuBuffer<float> b_res((size_t)n);
+    GpuBuffer<int> b_id((size_t)n);
+    memcpy(b_sph.HPtr(), sph.data(), sph.size() * 4);
+    memcpy(b_smp.HPtr(), smp.data(), smp.size() * 4);
+    memcpy(b_off.HPtr(), off.data(), off.size() * 4);
+    memcpy(b_cnt.HPtr(), cnt.data(), cnt.size() * 4);
+    memcpy(b_pr.HPtr(), pr.data(), pr.size() * 4);
+    for (int i = 0; i < n; i++) {
+      b_res.HPtr()[i] = 1e28f;  // fix_geo_error.cxx:300-366 initial fill
+      b_id.HPtr()[i] = -1;
+    }
+    compute_closest_dist2mat(b_sph, n, b_smp, b_off, b_cnt, b_pr, b_res, b_id);
+    wr(out, b_res.HPtr(), (int64_t)n);
+    wr(out, b_id.HPtr(), (int64_t)n);
+  }
+  fclose(in);
+  fclose(out);
+  return 0;
+}

@@ -38,7 +38,9 @@ def test_vs_oracle_200k(ctx, O, synth):
     assert rel.max() <= 1e-6  # north_star tolerance
     assert np.mean(r.view(np.uint32) == ro.view(np.uint32)) > 0.999
     assert not np.any((cid != co) & (tie == 0))  # argmin ids equal apart from flagged exact ties
-    assert tie.mean() < 0.01
+    # the tie rule itself is reproduced (same lane <-> primitive assignment): ids differ only where a
+    # distance differs in its last bit (powf vs x*x)
+    assert np.mean(cid != co) < 1e-3
 
 
 def test_vs_reference_build(ctx, O, synth):
