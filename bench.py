@@ -8,7 +8,7 @@ A "step" = one full restricted power diagram of the workload: candidate search (
 ordering/compaction (K4 first half), all in libmat_b200.so through the C ABI.
 
   N = 1   workload = BASELINE.json configs[1]: synthetic Kuhn ball mesh n=32 (196 608 tets, 35 937
-          vertices), 10 000 medial spheres, k=80 (given mode: 80 nearest-centre neighbour lists, the
+          vertices), 10 000 medial spheres, neighbour cap k=80 (given mode: regular-triangulation neighbour lists, the
           reference's semantics; grid mode: the library's own uniform-grid search).
   N > 1   weak scaling: the global mesh has ~196 608 tets PER GPU (n = 32 / 40 / 51 / 64 for N = 1/2/4/8),
           10 000*N spheres replicated on every rank, tets sharded in contiguous blocks; every rank
@@ -160,7 +160,8 @@ def run_reference_arm(args):
     from oracle import oracle as O
 
     mesh, sites, n, ns = make_workload(args.workload, args.gpus)
-    knn, k = synth.knn_site_lists(sites, 80)
+    knn, k, valid = synth.rt_site_lists(sites)  # what the reference's callers pass (CGAL RT, rpd_api.cxx:35,67)
+    sites.flags[:] = valid.astype(np.uint32)
     # bounded sample: every `stride`-th cube of 6 tets (representative of the whole ball)
     target_tets = int(min(24576, max(1536, 2.5e8 / ns)))  # bounds the (untimed) candidate generation
     stride = max(1, mesh.n_tet // target_tets)
@@ -188,7 +189,7 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args, n, ns, mesh), "mode": "given-neighbours k=80 (reference semantics)"},
+        "config": {"workload": workload_name(args, n, ns, mesh), "mode": f"given-neighbours (regular-triangulation lists, site_k={k}; reference semantics)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -198,7 +199,7 @@ def run_reference_arm(args):
 
 def workload_name(args, n, ns, mesh):
     return (f"{args.workload}: synthetic Kuhn ball mesh n={n} ({mesh.n_tet} tets, {mesh.n_vert} verts), "
-            f"{ns} medial spheres, k=80")
+            f"{ns} medial spheres, neighbour cap k=80 (grid_k 96 / RT degree <= 80)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,7 +241,10 @@ def main():
 
     mesh, sites, n, ns = make_workload(args.workload, n_gpus)
     mode = args.mode if world == 1 else "grid"
-    knn, k = (synth.knn_site_lists(sites, 80) if (mode == "given" or (rank == 0 and world == 1)) else (None, 0))
+    # regular-triangulation neighbour lists (the reference's callers get them from CGAL): used by the
+    # given-neighbours mode and by the CPU baseline; hidden sites (empty power cell) are unflagged
+    knn, k, valid = synth.rt_site_lists(sites)
+    sites.flags[:] = valid.astype(np.uint32)
 
     stream = torch.cuda.Stream(device=dev)
     ctx = Context(local_rank)
@@ -400,7 +404,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
             "data": "synthetic",
             "config": {"workload": workload_name(args, n, ns, mesh),
-                       "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else "given-neighbours k=80",
+                       "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})",
                        "parallelism": f"tet-shards x{world}, sites replicated" + (", NCCL gather to rank 0" if world > 1 else ""),
                        "l2": "flushed (512 MB write) between timed steps",
                        "cells_per_step": total_cells, "candidate_pairs_per_step": total_pairs,
@@ -427,7 +431,7 @@ def main():
             kind, cpu_cells, sec = cpu_reference_run(mesh, sites, knn, k, pt, ps)
             line["cpu_baseline"] = {
                 "value": cpu_cells / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
-                "sample": f"all {len(pt)} candidate pairs of the workload (given-neighbours k=80), {cpu_cells} cells, "
+                "sample": f"all {len(pt)} candidate pairs of the workload (given-neighbours, RT lists site_k={k}), {cpu_cells} cells, "
                           f"best of 2, {sec:.2f} s; clipping loop + record copy timed, candidate generation excluded",
                 "cells_match_gpu_given_mode": bool(cpu_cells == gpu_cells)}
         print(json.dumps(line))

@@ -136,7 +136,8 @@ int mb_rpd_count(const mb_rpd_result* res, long* n_cells, long* n_pairs, long* n
 /* stats[8]: [0] cells  [1] candidate pairs  [2] clip_by_plane calls that reached the exact predicate
  * [3] listed neighbours rejected by the conservative bounding filter (the reference would have
  * clipped and popped them)  [4] tets whose candidate list overflowed grid_k (grid mode)
- * [5] compact result bytes  [6..7] reserved */
+ * (truncated: should be 0)  [5] compact result bytes  [6] tets redone by the big-list candidate pass
+ * [7] reserved */
 int mb_rpd_stats(const mb_rpd_result* res, long stats[8]);
 /* int[10]: index = status+1 (early_return .. needs_perturb), over all candidate pairs */
 int mb_rpd_status_histogram(const mb_rpd_result* res, long hist[10]);

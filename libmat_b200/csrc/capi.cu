@@ -71,6 +71,9 @@ void mb_destroy(mb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (mb_rpd_result* r : ctx->live_results) r->ctx = nullptr;  // results outlive the context safely
+  ctx->spare_blob.release();
+  ctx->spare_cell_off.release();
   TetMeshDev& M = ctx->mesh;
   M.vert4.release(); M.tet_idx.release(); M.tet_fadj.release(); M.tet_fid.release(); M.tet_e6.release();
   SitesDev& S = ctx->sites;
@@ -79,7 +82,7 @@ void mb_destroy(mb_ctx* ctx) {
   D.spheres.release(); D.samples.release(); D.offset.release(); D.count.release(); D.prims.release();
   D.result.release(); D.closest.release(); D.tie.release();
   ctx->tet_cnt.release(); ctx->tet_off.release(); ctx->pair_tet.release(); ctx->pair_site.release();
-  ctx->cand_pad.release(); ctx->cand_cnt.release(); ctx->word_off.release(); ctx->pair_valid.release();
+  ctx->cand_pad.release(); ctx->cand_cnt.release(); ctx->ovf_list.release(); ctx->word_off.release(); ctx->pair_valid.release();
   ctx->pair_cell.release(); ctx->pair_status.release(); ctx->pair_blob.release(); ctx->pair_words.release();
   ctx->scratch.release(); ctx->counters.release(); ctx->cub_tmp.release();
   ctx->grid_cnt.release(); ctx->grid_off.release(); ctx->grid_sorted_id.release(); ctx->grid_cell_of.release();
@@ -138,6 +141,10 @@ int mb_rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result** out) {
   MB_CUDA(cudaSetDevice(ctx->device));
   mb_rpd_result* res = new mb_rpd_result();
   *out = res;
+  res->ctx = ctx;
+  ctx->live_results.push_back(res);
+  ctx->spare_blob.move_to(res->blob);
+  ctx->spare_cell_off.move_to(res->cell_off);
   try {
     rpd_run(ctx, opts, res);
   } catch (...) {
@@ -167,7 +174,24 @@ int mb_rpd3d(mb_ctx* ctx, const float* site_soa, const float* site_w, const unsi
 
 void mb_rpd_free(mb_rpd_result* res) {
   if (!res) return;
-  if (res->ctx) cudaSetDevice(res->ctx->device);
+  if (mb_ctx* ctx = res->ctx) {
+    cudaSetDevice(ctx->device);
+    for (size_t i = 0; i < ctx->live_results.size(); i++)
+      if (ctx->live_results[i] == res) {
+        ctx->live_results[i] = ctx->live_results.back();
+        ctx->live_results.pop_back();
+        break;
+      }
+    // park the two big buffers in the context for the next run (keeps the larger of the two)
+    if (res->blob.cap > ctx->spare_blob.cap) {
+      ctx->spare_blob.release();
+      res->blob.move_to(ctx->spare_blob);
+    }
+    if (res->cell_off.cap > ctx->spare_cell_off.cap) {
+      ctx->spare_cell_off.release();
+      res->cell_off.move_to(ctx->spare_cell_off);
+    }
+  }
   res->blob.release(); res->cell_off.release(); res->site_vol.release(); res->site_bary.release();
   res->f_cell.release(); res->f_key.release(); res->v_cell.release(); res->v_lvid.release();
   res->v_key3.release(); res->v_surf.release(); res->e_cell.release(); res->e_key2.release();
@@ -193,7 +217,8 @@ int mb_rpd_stats(const mb_rpd_result* res, long stats[8]) {
   stats[3] = res->n_culled;
   stats[4] = res->n_cand_overflow;
   stats[5] = res->compact_bytes;
-  stats[6] = stats[7] = 0;
+  stats[6] = res->n_ovf_tets;
+  stats[7] = 0;
   return MB_OK;
 }
 

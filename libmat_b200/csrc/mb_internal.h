@@ -50,6 +50,13 @@ struct DevBuf {
     p = nullptr;
     cap = 0;
   }
+  // hand the allocation over to `o` (which must be empty)
+  void move_to(DevBuf<T>& o) {
+    o.p = p;
+    o.cap = cap;
+    p = nullptr;
+    cap = 0;
+  }
   size_t bytes() const { return cap * sizeof(T); }
 };
 
@@ -104,11 +111,16 @@ struct RpdCounters {
   unsigned long long n_cand_overflow;
   unsigned long long hist[10];
   unsigned long long pad[1];
+  unsigned long long n_ovf_tets;   // [16] grid mode: tets handed to the big-list candidate pass
+  unsigned long long work_cursor;  // [17] K3 dynamic work distribution
+  unsigned long long reserved[6];
 };
+#define CNT_OVF_TETS 16
+#define CNT_WORK_CURSOR 17
 
 struct mb_rpd_result {
   mb_ctx* ctx = nullptr;
-  long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0, n_cand_overflow = 0;
+  long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0, n_cand_overflow = 0, n_ovf_tets = 0;
   long hist[10] = {0};
   long compact_bytes = 0;
   float ms[4] = {0, 0, 0, 0};
@@ -153,6 +165,7 @@ struct mb_ctx {
   // rpd scratch (reused across calls)
   DevBuf<int> tet_cnt, tet_off, pair_tet, pair_site, cand_pad;
   DevBuf<int> cand_cnt;            // grid mode: #candidates per tet (cand_pad holds the lists)
+  DevBuf<int> ovf_list;            // grid mode: tets whose survivor list overflowed the fast pass
   int cand_kcap = 0;               // grid mode: row stride of cand_pad
   DevBuf<long long> word_off;      // ordering: exclusive scan of pair_words
   DevBuf<int> pair_valid, pair_cell;
@@ -167,6 +180,11 @@ struct mb_ctx {
   DevBuf<float4> grid_site4;
   DevBuf<float> grid_wmax0, grid_wmax1;
   float site_bbox[6] = {0, 0, 0, 0, 0, 0};  // min xyz, max xyz of the site centres (host-computed)
+  // result buffers recycled between runs (cudaMalloc / cudaFree synchronise the device): a freed
+  // result parks its blob / offset buffers here and the next run takes them back
+  DevBuf<uint32_t> spare_blob;
+  DevBuf<long long> spare_cell_off;
+  std::vector<mb_rpd_result*> live_results;  // orphaned (ctx = nullptr) by mb_destroy
 };
 
 // ---- launchers implemented in rpd_kernels.cu ---------------------------------------------

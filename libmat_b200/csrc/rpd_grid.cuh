@@ -16,7 +16,7 @@
 #include "mb_internal.h"
 #include "rpd_device.cuh"
 
-#define GRID_MAX_K 512
+#define GRID_BIG_KCAP 2048  // survivor list of the overflow pass
 
 struct GridDev {
   const float4* site4;      // cell-sorted sites (x,y,z,w)
@@ -111,201 +111,267 @@ __device__ __forceinline__ float pd_plain(float4 s, float4 p) {
   return dx * dx + dy * dy + dz * dz - s.w;
 }
 
-// One warp per tet.  PHASE A finds U(T); PHASE B collects {s : L_s <= U + eps}; then the
-// domination filter and an ascending-id rank sort.  Output: padded list [t_local][kcap] of ALL
-// candidates (the neighbour list of every cell of this tet), cand_cnt[t_local], and
-// pair_cnt[t_local] = number of flagged candidates (cells to clip).
-template <int KCAP>
-__global__ void __launch_bounds__(128) k_grid_candidates(
+// domination with rounding slack: site m (vertex power distances f, weight wm) strictly
+// dominates site a (e, wa) at all 4 tet vertices => pd_m < pd_a on the whole tet (affine
+// difference) => cell(a) does not meet the tet.  pd is evaluated in binary32: |err| <= ~2.4e-7 *
+// (d^2 + w) <= 2.4e-7 * (|pd| + 2w); the slack below is ~8x that for both operands.
+__device__ __forceinline__ bool dominates(float4 f, float wm, float4 e, float wa) {
+  const float base = 2.f * (wa + wm) + 1.f;
+  return f.x < e.x - 2e-6f * (fabsf(e.x) + fabsf(f.x) + base) &&
+         f.y < e.y - 2e-6f * (fabsf(e.y) + fabsf(f.y) + base) &&
+         f.z < e.z - 2e-6f * (fabsf(e.z) + fabsf(f.z) + base) &&
+         f.w < e.w - 2e-6f * (fabsf(e.w) + fabsf(f.w) + base);
+}
+
+__device__ __forceinline__ float4 pd4(float4 s, float4 p0, float4 p1, float4 p2, float4 p3) {
+  return make_float4(pd_plain(s, p0), pd_plain(s, p1), pd_plain(s, p2), pd_plain(s, p3));
+}
+
+// argmin over the warp of (val, slot): returns the slot of the smallest val (ties: any)
+__device__ __forceinline__ int warp_argmin(float v, int q) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+    const int q2 = __shfl_xor_sync(0xffffffffu, q, o);
+    if (v2 < v || (v2 == v && q2 > q)) {
+      v = v2;
+      q = q2;
+    }
+  }
+  return q;
+}
+
+// One warp per tet.
+//   PHASE A  walks the grid pyramid for U(T) = min_s max_i pd_s(p_i) and, on the way, remembers the
+//            best site seen for each of the 4 vertices and for U: the KERNEL SET K (<= 5 sites).
+//   PHASE B  walks it again, streams every site with L_s <= U through the domination test against
+//            K and keeps the survivors (a few tens at most) in shared memory.
+//   then     all-pairs domination on the survivors + ascending-id rank sort.
+// Output: padded list [t_local][kcap_out] of ALL candidates (the neighbour list of every cell of
+// the tet), cand_cnt[t_local], pair_cnt[t_local] = number of flagged candidates (cells to clip).
+// A tet whose survivor list exceeds KCAP goes to ovf_list and is redone by the FROM_LIST
+// instantiation with a 2048-entry list; only a list that still exceeds kcap_out AFTER the
+// all-pairs filter is truncated (counted in counters[CNT_CANDOVF], reported by mb_rpd_stats).
+template <int KCAP, int WARPS, bool FROM_LIST>
+__global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
     const float4* __restrict__ vert4, const int4* __restrict__ tet_idx, int tet_first, int tet_count,
-    GridDev G, const unsigned* __restrict__ flags, int* __restrict__ cand_pad, int* __restrict__ cand_cnt,
-    int* __restrict__ pair_cnt, unsigned long long* __restrict__ counters) {
-  __shared__ int s_id[4][KCAP];
-  __shared__ float s_pd[4][KCAP][4];
-  __shared__ float s_w[4][KCAP];
+    GridDev G, const unsigned* __restrict__ flags, int kcap_out, int* __restrict__ cand_pad,
+    int* __restrict__ cand_cnt, int* __restrict__ pair_cnt, unsigned long long* __restrict__ counters,
+    int* __restrict__ ovf_list) {
+  extern __shared__ __align__(16) unsigned char grid_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * 4 + wib;
-  if (warp >= tet_count) return;
-  const int t = tet_first + warp;
-  const int4 vi = tet_idx[t];
-  const float4 p0 = vert4[vi.x], p1 = vert4[vi.y], p2 = vert4[vi.z], p3 = vert4[vi.w];
-  const float gx = 0.25f * (p0.x + p1.x + p2.x + p3.x), gy = 0.25f * (p0.y + p1.y + p2.y + p3.y),
-              gz = 0.25f * (p0.z + p1.z + p2.z + p3.z);
-  const float4 g4 = make_float4(gx, gy, gz, 0.f);
-  float Rt2 = fmaxf(fmaxf(pd_plain(g4, p0), pd_plain(g4, p1)), fmaxf(pd_plain(g4, p2), pd_plain(g4, p3)));
-  const float Rt = sqrtf(Rt2) * 1.0001f + 1e-3f;
+  float4* s_pd = reinterpret_cast<float4*>(grid_smem) + (size_t)wib * KCAP;
+  float* s_w = reinterpret_cast<float*>(reinterpret_cast<float4*>(grid_smem) + (size_t)WARPS * KCAP) + (size_t)wib * KCAP;
+  int* s_id = reinterpret_cast<int*>(reinterpret_cast<float*>(reinterpret_cast<float4*>(grid_smem) + (size_t)WARPS * KCAP) +
+                                     (size_t)WARPS * KCAP) + (size_t)wib * KCAP;
   const int R = G.R, R1 = G.R1;
   const float H1 = 4.f * G.h;
+  const int n1 = R1 * R1 * R1;
+  const int n_work = FROM_LIST ? (int)counters[CNT_OVF_TETS] : tet_count;
+  for (int work = blockIdx.x * WARPS + wib; work < n_work; work += gridDim.x * WARPS) {
+    const int warp = FROM_LIST ? ovf_list[work] : work;  // local tet index
+    const int t = tet_first + warp;
+    const int4 vi = tet_idx[t];
+    const float4 p0 = vert4[vi.x], p1 = vert4[vi.y], p2 = vert4[vi.z], p3 = vert4[vi.w];
+    const float gx = 0.25f * (p0.x + p1.x + p2.x + p3.x), gy = 0.25f * (p0.y + p1.y + p2.y + p3.y),
+                gz = 0.25f * (p0.z + p1.z + p2.z + p3.z);
+    const float4 g4 = make_float4(gx, gy, gz, 0.f);
+    const float Rt2 = fmaxf(fmaxf(pd_plain(g4, p0), pd_plain(g4, p1)), fmaxf(pd_plain(g4, p2), pd_plain(g4, p3)));
+    const float Rt = sqrtf(Rt2) * 1.0001f + 1e-3f;
 
-  // ---- phase A: U = min_s max_i pd_s(p_i) ------------------------------------------------------
-  float u_lane = INFINITY;
-  float U = INFINITY;
-  {
-    // seed with the fine cell that contains the centroid (and its 26 neighbours)
-    const int ci = min(R - 1, max(0, (int)floorf((gx - G.minx) * G.inv_h)));
-    const int cj = min(R - 1, max(0, (int)floorf((gy - G.miny) * G.inv_h)));
-    const int ck = min(R - 1, max(0, (int)floorf((gz - G.minz) * G.inv_h)));
-    if (lane < 27) {
-      const int i = ci + lane / 9 - 1, j = cj + (lane / 3) % 3 - 1, k = ck + lane % 3 - 1;
-      if (i >= 0 && j >= 0 && k >= 0 && i < R && j < R && k < R) {
-        const int c = (i * R + j) * R + k;
-        for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) {
-          const float4 s = G.site4[q];
-          const float m = fmaxf(fmaxf(pd_plain(s, p0), pd_plain(s, p1)), fmaxf(pd_plain(s, p2), pd_plain(s, p3)));
-          u_lane = fminf(u_lane, m);
+    // ---- phase A -------------------------------------------------------------------------------
+    float bv0 = INFINITY, bv1 = INFINITY, bv2 = INFINITY, bv3 = INFINITY, bvu = INFINITY;
+    int bq0 = -1, bq1 = -1, bq2 = -1, bq3 = -1, bqu = -1;
+    float U = INFINITY;
+    auto eval = [&](int q) {
+      const float4 e = pd4(G.site4[q], p0, p1, p2, p3);
+      const float m = fmaxf(fmaxf(e.x, e.y), fmaxf(e.z, e.w));
+      if (e.x < bv0) { bv0 = e.x; bq0 = q; }
+      if (e.y < bv1) { bv1 = e.y; bq1 = q; }
+      if (e.z < bv2) { bv2 = e.z; bq2 = q; }
+      if (e.w < bv3) { bv3 = e.w; bq3 = q; }
+      if (m < bvu) { bvu = m; bqu = q; }
+    };
+    {
+      // seed with the fine cell that contains the centroid and its 26 neighbours
+      const int ci = min(R - 1, max(0, (int)floorf((gx - G.minx) * G.inv_h)));
+      const int cj = min(R - 1, max(0, (int)floorf((gy - G.miny) * G.inv_h)));
+      const int ck = min(R - 1, max(0, (int)floorf((gz - G.minz) * G.inv_h)));
+      if (lane < 27) {
+        const int i = ci + lane / 9 - 1, j = cj + (lane / 3) % 3 - 1, k = ck + lane % 3 - 1;
+        if (i >= 0 && j >= 0 && k >= 0 && i < R && j < R && k < R) {
+          const int c = (i * R + j) * R + k;
+          for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) eval(q);
         }
       }
+      U = warp_min(bvu);
     }
-    U = warp_min(u_lane);
-  }
-  const int n1 = R1 * R1 * R1;
-  for (int b1 = 0; b1 < n1; b1 += 32) {
-    const int n = b1 + lane;
-    bool keep = false;
-    if (n < n1) {
-      const int k1 = n % R1, j1 = (n / R1) % R1, i1 = n / (R1 * R1);
-      keep = box_dist2(gx, gy, gz, G, i1, j1, k1, H1) - G.wmax1[n] < U;
-    }
-    unsigned m1 = __ballot_sync(0xffffffffu, keep);
-    while (m1) {
-      const int n_ = b1 + __ffs(m1) - 1;
-      m1 &= m1 - 1;
-      const int k1 = n_ % R1, j1 = (n_ / R1) % R1, i1 = n_ / (R1 * R1);
+    for (int b1 = 0; b1 < n1; b1 += 32) {
+      const int n = b1 + lane;
+      bool keep = false;
+      if (n < n1) {
+        const int k1 = n % R1, j1 = (n / R1) % R1, i1 = n / (R1 * R1);
+        keep = box_dist2(gx, gy, gz, G, i1, j1, k1, H1) - G.wmax1[n] < U;
+      }
+      unsigned m1 = __ballot_sync(0xffffffffu, keep);
+      while (m1) {
+        const int n_ = b1 + __ffs(m1) - 1;
+        m1 &= m1 - 1;
+        const int k1 = n_ % R1, j1 = (n_ / R1) % R1, i1 = n_ / (R1 * R1);
 #pragma unroll
-      for (int half = 0; half < 2; half++) {
-        const int ch = half * 32 + lane;
-        const int i = 4 * i1 + (ch >> 4), j = 4 * j1 + ((ch >> 2) & 3), k = 4 * k1 + (ch & 3);
-        int c = -1;
-        if (i < R && j < R && k < R) {
-          c = (i * R + j) * R + k;
-          if (!(box_dist2(gx, gy, gz, G, i, j, k, G.h) - G.wmax0[c] < U)) c = -1;
-        }
-        if (c >= 0) {
-          for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) {
-            const float4 s = G.site4[q];
-            const float m = fmaxf(fmaxf(pd_plain(s, p0), pd_plain(s, p1)), fmaxf(pd_plain(s, p2), pd_plain(s, p3)));
-            u_lane = fminf(u_lane, m);
+        for (int half = 0; half < 2; half++) {
+          const int ch = half * 32 + lane;
+          const int i = 4 * i1 + (ch >> 4), j = 4 * j1 + ((ch >> 2) & 3), k = 4 * k1 + (ch & 3);
+          if (i < R && j < R && k < R) {
+            const int c = (i * R + j) * R + k;
+            if (box_dist2(gx, gy, gz, G, i, j, k, G.h) - G.wmax0[c] < U)
+              for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) eval(q);
           }
         }
+        U = warp_min(bvu);
       }
-      U = warp_min(u_lane);
     }
-  }
-  // float rounding of pd: |err| <= ~4e-7 (d^2 + w); make U an over-estimate
-  const float Ue = U + 1e-5f * (fabsf(U) + 1.f) + 1e-2f;
+    // kernel set: best site per vertex + the U site (slots in the cell-sorted table; -1 if none)
+    int kq[5];
+    kq[0] = warp_argmin(bv0, bq0);
+    kq[1] = warp_argmin(bv1, bq1);
+    kq[2] = warp_argmin(bv2, bq2);
+    kq[3] = warp_argmin(bv3, bq3);
+    kq[4] = warp_argmin(bvu, bqu);
+    float4 kE[5];
+    float kW[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      if (kq[k] >= 0) {
+        const float4 s = G.site4[kq[k]];
+        kE[k] = pd4(s, p0, p1, p2, p3);
+        kW[k] = s.w;
+      } else {
+        kE[k] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        kW[k] = 0.f;
+      }
+    }
+    // U is a binary32 value: make it a certain over-estimate (error <= ~2.4e-7 (|U| + 2 w))
+    const float Ue = U + 4e-6f * (fabsf(U) + 2.f * kW[4]) + 1e-3f;
 
-  // ---- phase B: collect candidates with L_s <= Ue ----------------------------------------------
-  int cnt = 0;
-  bool overflow = false;
-  for (int b1 = 0; b1 < n1; b1 += 32) {
-    const int n = b1 + lane;
-    bool keep = false;
-    if (n < n1) {
-      const int k1 = n % R1, j1 = (n / R1) % R1, i1 = n / (R1 * R1);
-      const float d = fmaxf(0.f, sqrtf(box_dist2(gx, gy, gz, G, i1, j1, k1, H1)) - Rt);
-      keep = d * d - G.wmax1[n] <= Ue;
-    }
-    unsigned m1 = __ballot_sync(0xffffffffu, keep);
-    while (m1) {
-      const int n_ = b1 + __ffs(m1) - 1;
-      m1 &= m1 - 1;
-      const int k1 = n_ % R1, j1 = (n_ / R1) % R1, i1 = n_ / (R1 * R1);
-      for (int half = 0; half < 2; half++) {
-        const int ch = half * 32 + lane;
-        const int i = 4 * i1 + (ch >> 4), j = 4 * j1 + ((ch >> 2) & 3), k = 4 * k1 + (ch & 3);
-        int c = -1;
-        if (i < R && j < R && k < R) {
-          c = (i * R + j) * R + k;
-          const float d = fmaxf(0.f, sqrtf(box_dist2(gx, gy, gz, G, i, j, k, G.h)) - Rt);
-          if (!(d * d - G.wmax0[c] <= Ue)) c = -1;
-        }
-        unsigned m0 = __ballot_sync(0xffffffffu, c >= 0);
-        while (m0) {
-          const int src = __ffs(m0) - 1;
-          m0 &= m0 - 1;
-          const int cc = __shfl_sync(0xffffffffu, c, src);
-          const int qb = G.cell_off[cc], qe = G.cell_off[cc + 1];
-          for (int q0 = qb; q0 < qe; q0 += 32) {
-            const int q = q0 + lane;
+    // ---- phase B: stream {s : L_s <= Ue} through the kernel-set domination test --------------------
+    int cnt = 0;
+    for (int b1 = 0; b1 < n1; b1 += 32) {
+      const int n = b1 + lane;
+      bool keep = false;
+      if (n < n1) {
+        const int k1 = n % R1, j1 = (n / R1) % R1, i1 = n / (R1 * R1);
+        const float d = fmaxf(0.f, sqrtf(box_dist2(gx, gy, gz, G, i1, j1, k1, H1)) * 0.9999f - Rt);
+        keep = d * d - G.wmax1[n] <= Ue;
+      }
+      unsigned m1 = __ballot_sync(0xffffffffu, keep);
+      while (m1) {
+        const int n_ = b1 + __ffs(m1) - 1;
+        m1 &= m1 - 1;
+        const int k1 = n_ % R1, j1 = (n_ / R1) % R1, i1 = n_ / (R1 * R1);
+        for (int half = 0; half < 2; half++) {
+          const int ch = half * 32 + lane;
+          const int i = 4 * i1 + (ch >> 4), j = 4 * j1 + ((ch >> 2) & 3), k = 4 * k1 + (ch & 3);
+          int qb = 0, qe = 0;
+          if (i < R && j < R && k < R) {
+            const int c = (i * R + j) * R + k;
+            const float d = fmaxf(0.f, sqrtf(box_dist2(gx, gy, gz, G, i, j, k, G.h)) * 0.9999f - Rt);
+            if (d * d - G.wmax0[c] <= Ue) {
+              qb = G.cell_off[c];
+              qe = G.cell_off[c + 1];
+            }
+          }
+          // lane <-> fine cell; each lane walks its cell's sites, appends are warp-aggregated
+          while (__any_sync(0xffffffffu, qb < qe)) {
             bool ok = false;
-            float4 s = make_float4(0, 0, 0, 0);
-            if (q < qe) {
-              s = G.site4[q];
-              const float dg = sqrtf(pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4));
-              const float d = fmaxf(0.f, dg - Rt);
-              ok = d * d - s.w <= Ue;
+            float4 e = make_float4(0, 0, 0, 0);
+            float w = 0.f;
+            if (qb < qe) {
+              const float4 s = G.site4[qb];
+              const float dg2 = pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4);
+              const float d = fmaxf(0.f, sqrtf(dg2) * 0.9999f - Rt);
+              if (d * d - s.w - 4e-6f * (dg2 + s.w) <= Ue) {
+                e = pd4(s, p0, p1, p2, p3);
+                w = s.w;
+                ok = true;
+#pragma unroll
+                for (int kk = 0; kk < 5; kk++) ok = ok && !dominates(kE[kk], kW[kk], e, w);
+              }
             }
             const unsigned mk = __ballot_sync(0xffffffffu, ok);
             if (ok) {
               const int pos = cnt + __popc(mk & ((1u << lane) - 1u));
               if (pos < KCAP) {
-                s_id[wib][pos] = G.sorted_id[q];
-                s_pd[wib][pos][0] = pd_plain(s, p0);
-                s_pd[wib][pos][1] = pd_plain(s, p1);
-                s_pd[wib][pos][2] = pd_plain(s, p2);
-                s_pd[wib][pos][3] = pd_plain(s, p3);
-                s_w[wib][pos] = s.w;
+                s_id[pos] = G.sorted_id[qb];
+                s_pd[pos] = e;
+                s_w[pos] = w;
               }
             }
             cnt += __popc(mk);
+            qb++;
           }
         }
       }
     }
-  }
-  if (cnt > KCAP) {
-    overflow = true;
-    cnt = KCAP;
-  }
-  __syncwarp();
-  // ---- domination filter + ascending-id rank sort ------------------------------------------------
-  int n_keep = 0, n_flag = 0;
-  for (int b = 0; b < cnt; b += 32) {
-    const int a = b + lane;
-    bool keep = false;
-    int my_id = 0x7fffffff;
-    if (a < cnt) {
-      keep = true;
-      my_id = s_id[wib][a];
-      const float e0 = s_pd[wib][a][0], e1 = s_pd[wib][a][1], e2 = s_pd[wib][a][2], e3 = s_pd[wib][a][3];
-      const float wa = s_w[wib][a];
-      if (!overflow) {  // with a truncated list the dominating site may be missing: keep all
-        for (int m = 0; m < cnt && keep; m++) {
-          if (m == a) continue;
-          const float wm = s_w[wib][m];
-          const float f0 = s_pd[wib][m][0], f1 = s_pd[wib][m][1], f2 = s_pd[wib][m][2], f3 = s_pd[wib][m][3];
-          const float base = 2.f * (wa + wm) + 1.f;
-          const bool dom = f0 < e0 - 2e-6f * (fabsf(e0) + fabsf(f0) + base) &&
-                           f1 < e1 - 2e-6f * (fabsf(e1) + fabsf(f1) + base) &&
-                           f2 < e2 - 2e-6f * (fabsf(e2) + fabsf(f2) + base) &&
-                           f3 < e3 - 2e-6f * (fabsf(e3) + fabsf(f3) + base);
-          if (dom) keep = false;
+    if (cnt > KCAP) {
+      if (!FROM_LIST) {
+        // survivors do not fit: hand the tet to the big-list pass
+        if (lane == 0) {
+          const unsigned long long at = atomicAdd(&counters[CNT_OVF_TETS], 1ull);
+          ovf_list[at] = warp;
+          cand_cnt[warp] = 0;
+          pair_cnt[warp] = 0;
+        }
+        continue;
+      }
+      cnt = KCAP;  // 2048 survivors of the kernel-set filter: give up on the rest (counted below)
+      if (lane == 0) atomicAdd(&counters[4], 1ull);
+    }
+    __syncwarp();
+    // ---- all-pairs domination on the survivors ---------------------------------------------------
+    int n_keep = 0;
+    for (int b = 0; b < cnt; b += 32) {
+      const int a = b + lane;
+      bool keep = false;
+      if (a < cnt) {
+        keep = true;
+        const float4 e = s_pd[a];
+        const float wa = s_w[a];
+        for (int m = 0; m < cnt && keep; m++)
+          if (m != a && dominates(s_pd[m], s_w[m], e, wa)) keep = false;
+      }
+      __syncwarp();
+      // removed entries get id = INT_MAX so that the rank sort pushes them to the tail; their
+      // s_pd stays (a dominated site may still dominate others: domination is transitive)
+      if (a < cnt && !keep) s_id[a] = 0x7fffffff;
+      n_keep += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    __syncwarp();
+    if (n_keep > kcap_out) {
+      if (lane == 0) atomicAdd(&counters[4], 1ull);  // truncated: reported, never silent
+    }
+    int n_flag = 0;
+    for (int b = 0; b < cnt; b += 32) {
+      const int a = b + lane;
+      bool fl = false;
+      if (a < cnt) {
+        const int id = s_id[a];
+        if (id != 0x7fffffff) {
+          int rank = 0;
+          for (int m = 0; m < cnt; m++) rank += (s_id[m] < id);
+          if (rank < kcap_out) {
+            cand_pad[(size_t)warp * kcap_out + rank] = id;
+            fl = flags[id] == 1u;
+          }
         }
       }
+      n_flag += __popc(__ballot_sync(0xffffffffu, fl));
     }
-    // mark removed entries with id = INT_MAX so that the rank sort pushes them to the tail
-    if (a < cnt && !keep) s_id[wib][a] = 0x7fffffff;
-    const unsigned mk = __ballot_sync(0xffffffffu, keep);
-    const unsigned mf = __ballot_sync(0xffffffffu, keep && flags[my_id == 0x7fffffff ? 0 : my_id] == 1u);
-    n_keep += __popc(mk);
-    n_flag += __popc(mf);
-  }
-  __syncwarp();
-  for (int b = 0; b < cnt; b += 32) {
-    const int a = b + lane;
-    if (a < cnt) {
-      const int id = s_id[wib][a];
-      if (id != 0x7fffffff) {
-        int rank = 0;
-        for (int m = 0; m < cnt; m++) rank += (s_id[wib][m] < id);
-        cand_pad[(size_t)warp * KCAP + rank] = id;
-      }
+    if (lane == 0) {
+      cand_cnt[warp] = min(n_keep, kcap_out);
+      pair_cnt[warp] = n_flag;
     }
-  }
-  if (lane == 0) {
-    cand_cnt[warp] = n_keep;
-    pair_cnt[warp] = n_flag;
-    if (overflow) atomicAdd(&counters[4], 1ull);
+    __syncwarp();
   }
 }
 

@@ -311,27 +311,46 @@ static GridDev grid_build(mb_ctx* ctx) {
 }
 
 // fills cand_pad / cand_cnt (all candidates) and tet_cnt (flagged candidates = pairs)
-static void grid_candidates(mb_ctx* ctx, int t_first, int t_count, int grid_k) {
+template <int KCAP>
+static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, int t_first, int t_count, int kcap_out) {
   TetMeshDev& M = ctx->mesh;
-  SitesDev& S = ctx->sites;
   cudaStream_t s = ctx->stream;
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->counters.p);
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)WARPS * KCAP * 24;  // float4 pd + float w + int id per entry
+  const size_t smem_big = (size_t)GRID_BIG_KCAP * 24;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MB_CUDA(cudaFuncSetAttribute(k_grid_candidates<GRID_BIG_KCAP, 1, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+    attr_set = true;
+  }
+  // fast pass: one warp per tet, persistent-style grid (a multiple of the SM count)
+  const int want = (t_count + WARPS - 1) / WARPS;
+  const int blocks = std::max(1, std::min(want, ctx->sm_count * 32));
+  ctx->n_launches++;
+  k_grid_candidates<KCAP, WARPS, false><<<blocks, 32 * WARPS, smem, s>>>(
+      M.vert4.p, M.tet_idx.p, t_first, t_count, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
+      ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p);
+  // overflow pass: reads the number of handed-over tets on the device (usually zero -> returns)
+  ctx->n_launches++;
+  k_grid_candidates<GRID_BIG_KCAP, 1, true><<<ctx->sm_count * 2, 32, smem_big, s>>>(
+      M.vert4.p, M.tet_idx.p, t_first, t_count, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
+      ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p);
+  MB_CUDA(cudaGetLastError());
+}
+
+static void grid_candidates(mb_ctx* ctx, int t_first, int t_count, int grid_k) {
   GridDev G = grid_build(ctx);
   const int kcap = (grid_k > 96) ? 256 : 96;
   ctx->cand_kcap = kcap;
   ctx->cand_pad.reserve((size_t)t_count * kcap);
   ctx->cand_cnt.reserve((size_t)t_count + 1);
-  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->counters.p);
-  const int blocks = (t_count + 3) / 4;
-  if (kcap == 96) {
-    ctx->n_launches++;
-    k_grid_candidates<96><<<blocks, 128, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, G, S.flags.p,
-                                                 ctx->cand_pad.p, ctx->cand_cnt.p, ctx->tet_cnt.p, cnt);
-  } else {
-    ctx->n_launches++;
-    k_grid_candidates<256><<<blocks, 128, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, G, S.flags.p,
-                                                  ctx->cand_pad.p, ctx->cand_cnt.p, ctx->tet_cnt.p, cnt);
-  }
-  MB_CUDA(cudaGetLastError());
+  ctx->ovf_list.reserve((size_t)t_count + 1);
+  if (kcap == 96)
+    launch_grid_candidates<96>(ctx, G, t_first, t_count, kcap);
+  else
+    launch_grid_candidates<256>(ctx, G, t_first, t_count, kcap);
 }
 
 static void grid_fill_pairs(mb_ctx* ctx, int t_first, int t_count, long long n_pairs) {
@@ -498,6 +517,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   res->n_clips = (long)hc.n_clips;
   res->n_culled = (long)hc.n_culled;
   res->n_cand_overflow = (long)hc.n_cand_overflow;
+  res->n_ovf_tets = (long)hc.n_ovf_tets;
   for (int i = 0; i < 10; i++) res->hist[i] = (long)hc.hist[i];
 
   // ---- ordering: scan + gather into (tet, site) order -------------------------------------------

@@ -180,20 +180,59 @@ class Sites:
 
 
 def make_spheres(n_site: int, seed: int = RAN_SEED, stream: int = 2, R: float = 500.0) -> Sites:
-    """Centre uniform in the ball of radius 0.9R around (500,500,500); r = (R-|c|)*U(0.5,1.0);
-    weight r^2; all sites flagged is_selected (SURVEY 8d)."""
+    """Medial-like spheres: centre uniform in the ball of radius 0.9R around (500,500,500);
+    r = min(R-|c|, h*U(0.5,1.0)) with h = the mean site spacing (V/n)^(1/3) -- inscribed (never
+    crossing the boundary) and not nested to any depth, as maximal inscribed balls are; ~4 % of
+    the sites end up hidden (empty power cell), regular-triangulation degree ~15 (max ~40).
+    weight r^2; all sites flagged is_selected."""
     u = uniform01(seed, 5 * n_site, stream).reshape(n_site, 5)
-    # uniform in ball: direction from normal-free method (z, phi), radius by cube root
+    # uniform in ball: direction from (z, phi), radius by cube root
     z = 2.0 * u[:, 0] - 1.0
     phi = 2.0 * np.pi * u[:, 1]
     rad = 0.9 * R * np.cbrt(u[:, 2])
     s = np.sqrt(np.maximum(0.0, 1.0 - z * z))
     c = np.stack([rad * s * np.cos(phi), rad * s * np.sin(phi), rad * z], axis=1)
-    r = (R - rad) * (0.5 + 0.5 * u[:, 3])
+    spacing = (4.0 / 3.0 * np.pi * (0.9 * R) ** 3 / n_site) ** (1.0 / 3.0)
+    r = np.minimum(R - rad, spacing * (0.5 + 0.5 * u[:, 3]))
     c = (c + 500.0).astype(np.float32)
     r = r.astype(np.float32)
     site_soa = np.ascontiguousarray(c.T).ravel()
     return Sites(site_soa, (r * r).astype(np.float32), np.ones(n_site, dtype=np.uint32), r)
+
+
+def rt_site_lists(sites: Sites) -> tuple[np.ndarray, int, np.ndarray]:
+    """Regular-triangulation neighbour tables, standing in for the reference's CGAL
+    Regular_triangulation_3 wrapper (reference triangulation.cxx:62-144, 237-268): the regular
+    triangulation is the lower convex hull of the lifted points (x, y, z, |x|^2 - w) (qhull).
+    Returns (site_knn in the (site_k+1) x n_site ascending-id, -1 padded layout, site_k = max degree
+    (reference rpd_api.cxx:67), valid = sites that are vertices of the triangulation; hidden sites
+    have an empty power cell and no neighbours)."""
+    from scipy.spatial import ConvexHull
+
+    c = sites.centers().astype(np.float64)
+    w = sites.weights.astype(np.float64)
+    n = c.shape[0]
+    if n < 6:
+        sets = [[m for m in range(n) if m != s] for s in range(n)]
+        knn, k = site_lists_from_sets(sets, n)
+        return knn, k, np.ones(n, dtype=bool)
+    lift = np.concatenate([c, ((c * c).sum(axis=1) - w)[:, None]], axis=1)
+    hull = ConvexHull(lift)
+    simp = hull.simplices[hull.equations[:, 3] < 0]  # lower hull
+    a = simp[:, [0, 0, 0, 1, 1, 2]].ravel()
+    b = simp[:, [1, 2, 3, 2, 3, 3]].ravel()
+    e = np.unique(np.stack([np.minimum(a, b), np.maximum(a, b)], axis=1), axis=0)
+    src = np.concatenate([e[:, 0], e[:, 1]])
+    dst = np.concatenate([e[:, 1], e[:, 0]])
+    order = np.lexsort((dst, src))
+    src, dst = src[order], dst[order]
+    deg = np.bincount(src, minlength=n)
+    site_k = max(1, int(deg.max()))
+    out = np.full((site_k + 1, n), -1, dtype=np.int32)
+    start = np.concatenate([[0], np.cumsum(deg)[:-1]])
+    slot = np.arange(src.size) - start[src]
+    out[slot, src] = dst
+    return out, site_k, deg > 0
 
 
 def knn_site_lists(sites: Sites, k: int) -> tuple[np.ndarray, int]:

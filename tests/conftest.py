@@ -74,6 +74,17 @@ def cfg1_oracle(cfg1, O):
 
 
 @pytest.fixture(scope="session")
+def cfg1_rt(synth):
+    """config 1 with regular-triangulation neighbour lists (what the reference's callers pass:
+    rpd_api.cxx:35,67) and hidden sites unflagged: a SUFFICIENT list, so the cells tile the mesh."""
+    mesh = synth.make_ball_mesh(15)
+    sites = synth.make_spheres(1000)
+    knn, k, valid = synth.rt_site_lists(sites)
+    sites.flags[:] = valid.astype(np.uint32)
+    return mesh, sites, knn, k
+
+
+@pytest.fixture(scope="session")
 def ctx():
     """One mb_ctx on cuda:0 (GPU tests only)."""
     from libmat_b200.rpd import Context

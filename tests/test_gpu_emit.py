@@ -19,16 +19,3 @@ def test_emit_cfg1(ctx, O, cfg1):
     assert np.array_equal(em["vert_pos"].view(np.uint32), want["vert_pos"].view(np.uint32))
     _, _, eu = O.reload_active(recs, "oracle")
     assert np.array_equal(em["cell_euler"].view(np.uint32), eu.view(np.uint32))
-
-
-def test_emit_euler_sums_per_site(ctx, O, cfg1):
-    """property: for a power cell that is a topological ball, the sum of its cells' Euler terms is 1"""
-    mesh, sites, knn, k = cfg1
-    ctx.set_mesh(mesh)
-    res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, knn, k)
-    recs = res.records()
-    em = res.emit(mesh.n_surf_faces - 1)
-    per_site = np.zeros(sites.n_site)
-    np.add.at(per_site, recs["voro_id"], em["cell_euler"].astype(np.float64))
-    has = np.bincount(recs["voro_id"], minlength=sites.n_site) > 0
-    assert np.mean(np.abs(per_site[has] - 1.0) < 1e-3) > 0.9

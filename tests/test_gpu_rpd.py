@@ -11,6 +11,14 @@ pytestmark = pytest.mark.gpu
 FIELDS = ("status", "voro_id", "tet_id", "weight", "nb_v", "nb_p", "nb_e", "ver", "id2", "edge")
 
 
+def expected_hist(recs, stat):
+    """per-pair Status histogram (index = status+1): `success` where the reference copied a valid record
+    (records of cells with |vol| < 0.1 stay valid although gpu_stat flips afterwards, convex_cell.cu:1040),
+    else the reference's gpu_stat value."""
+    st = np.where(recs["status"] == 4, 4, stat)
+    return np.bincount(st + 1, minlength=10)
+
+
 def assert_defined_equal(O, a, b):
     d = O.defined_equal(a, b)
     assert all(v == 0 for f, v in d.items() if f != "cells_compared"), d
@@ -47,8 +55,8 @@ def test_mini_golden(ctx, O, lanes):
     for f in FIELDS:
         assert np.array_equal(recs[f], g[f][ok]), f
     assert np.array_equal(recs["clip"][..., :5].view(np.uint32), g["clip"][ok][..., :5].view(np.uint32))
-    # per-pair status histogram (index = status + 1) equals the reference's record statuses
-    assert np.array_equal(res.status_histogram, np.bincount(g["status"] + 1, minlength=10))
+    # per-pair status histogram (index = status + 1) equals the reference's
+    assert np.array_equal(res.status_histogram, expected_hist(g, g["stat"]))
 
 
 @pytest.mark.parametrize("lanes", [8, 16, 32])
@@ -65,7 +73,7 @@ def test_cfg1_given_vs_oracle(ctx, O, cfg1, cfg1_oracle, lanes):
     assert np.array_equal(recs["id"], np.arange(len(recs)))
     key = recs["tet_id"].astype(np.int64) * sites.n_site + recs["voro_id"]
     assert (np.diff(key) > 0).all()  # sorted by (tet, site), voronoi.cu:744-769
-    assert np.array_equal(res.status_histogram, np.bincount(ra["status"] + 1, minlength=10))
+    assert np.array_equal(res.status_histogram, expected_hist(ra, sa))
 
 
 def test_cfg1_given_vs_reference_build(ctx, O, cfg1, cfg1_oracle):
@@ -88,7 +96,8 @@ def test_overflow_classes(ctx, O, synth):
     ra, sa, _ = O.run_pairs(mesh, sites, knn, k, pt, ps, impl="oracle")
     res = run_given(ctx, mesh, sites, knn, k)
     assert res.n_pairs == len(pt)
-    assert np.array_equal(res.status_histogram, np.bincount(ra["status"] + 1, minlength=10))
+    assert np.array_equal(res.status_histogram, expected_hist(ra, sa))
+    assert res.status_histogram[[1, 2, 8]].sum() > 0  # the config really exercises overflow statuses
     assert_defined_equal(O, ra[ra["status"] == 4], res.records())
 
 
@@ -103,9 +112,12 @@ def test_tet_range_shards_concatenate(ctx, O, cfg1):
         parts.append(ctx.run().records())
     ctx.set_tet_range(0, -1)
     cat = np.concatenate(parts)
-    cat["id"] = np.arange(len(cat))
-    cat["thread_id"] = cat["id"]
-    assert cat.tobytes() == full.tobytes()
+    assert len(cat) == len(full)
+    assert np.array_equal(np.concatenate([p["id"] for p in parts]),
+                          np.concatenate([np.arange(len(p)) for p in parts]))  # ids restart per shard
+    for f in full.dtype.names:
+        if f not in ("id", "thread_id"):
+            assert np.array_equal(cat[f].view(np.uint8), full[f].view(np.uint8)), f
 
 
 def test_empty_range_and_unselected(ctx, O, cfg1):
@@ -199,37 +211,70 @@ def canon_equal(O, a, b):
     return d
 
 
-@pytest.mark.parametrize("n,ns", [(4, 40), (8, 150)])
-def test_grid_mode_canonical_parity(ctx, O, synth, n, ns):
-    """grid-kNN mode vs the reference semantics given ALL other sites as neighbours (a sufficient
-    list): same cells, same canonical combinatorics (SURVEY 8a parity form)."""
-    mesh = synth.make_ball_mesh(n)
-    sites = synth.make_spheres(ns)
-    knn, k = synth.site_lists_from_sets([[m for m in range(ns) if m != s] for s in range(ns)], ns)
+def grid_vs_given(ctx, O, mesh, sites, knn, k, **kw):
+    """grid-kNN mode against the reference semantics with a sufficient neighbour list"""
+    ns = sites.n_site
     pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
     ra, sa, _ = O.run_pairs(mesh, sites, knn, k, pt, ps)
     want = ra[ra["status"] == 4]
     ctx.set_mesh(mesh)
-    res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
+    res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0, **kw)
+    assert res.n_cand_overflow == 0
     got = res.records()
     ka = want["tet_id"].astype(np.int64) * ns + want["voro_id"]
     kb = got["tet_id"].astype(np.int64) * ns + got["voro_id"]
-    # cells whose volume is at rounding level may appear on one side only (flagged class)
     common = np.intersect1d(ka, kb)
     only_a, only_b = np.setdiff1d(ka, kb), np.setdiff1d(kb, ka)
+    # cells whose volume is at rounding level may appear on one side only (flagged class)
     va = O.cell_volumes(want[np.isin(ka, only_a)])
     vb = O.cell_volumes(got[np.isin(kb, only_b)])
     assert (va < 1e-2).all() and (vb < 1e-2).all(), (va, vb)
-    assert len(common) > 0.99 * len(ka)
+    assert len(only_a) + len(only_b) <= 1e-4 * len(ka) + 2
     d = canon_equal(O, want[np.isin(ka, common)], got[np.isin(kb, common)])
     n_bad = max(v for f, v in d.items() if f != "cells_compared")
-    assert n_bad <= 0.002 * len(common), d  # degenerate (|det| at rounding level) cells only
+    assert n_bad <= 1e-4 * len(common), d  # degenerate (|det| at rounding level) cells only
+    return want, got
 
 
-def test_grid_mode_tiles_every_tet(ctx, O, cfg1):
-    """property at config-1 size: the cells of each tet tile it (volume conservation), and every
-    bisector facet (s, m) of a tet has its mirror (m, s) in the same tet."""
-    mesh, sites, _, _ = cfg1
+@pytest.mark.parametrize("n,ns", [(4, 40), (8, 150)])
+def test_grid_mode_canonical_parity_all_neighbours(ctx, O, synth, n, ns):
+    """grid-kNN mode vs the reference semantics given ALL other sites as neighbours: same cells,
+    same canonical combinatorics (SURVEY 8a parity form)."""
+    mesh = synth.make_ball_mesh(n)
+    sites = synth.make_spheres(ns)
+    knn, k = synth.site_lists_from_sets([[m for m in range(ns) if m != s] for s in range(ns)], ns)
+    grid_vs_given(ctx, O, mesh, sites, knn, k)
+
+
+def test_grid_mode_canonical_parity_cfg1_rt(ctx, O, cfg1_rt):
+    """config 1 with regular-triangulation lists: the library's own neighbour search must give the
+    cells the reference computes from the RT neighbours."""
+    mesh, sites, knn, k = cfg1_rt
+    want, got = grid_vs_given(ctx, O, mesh, sites, knn, k)
+    assert len(got) > 3 * mesh.n_tet
+
+
+def test_grid_mode_overflow_pass(ctx, O, synth):
+    """many more sites than tets: per-tet survivor lists overflow the fast pass and are redone by the
+    big-list pass; results must not change."""
+    mesh = synth.make_ball_mesh(2)
+    used_big_pass = False
+    for ns in (500, 800, 1100):
+        sites = synth.make_spheres(ns, stream=7)
+        knn, k, valid = synth.rt_site_lists(sites)
+        sites.flags[:] = valid.astype(np.uint32)
+        ctx.set_mesh(mesh)
+        res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
+        if res.n_cand_overflow:
+            continue  # more than grid_k true candidates per tet: that is the documented truncation
+        grid_vs_given(ctx, O, mesh, sites, knn, k)
+        used_big_pass |= res.n_big_pass_tets > 0
+    assert used_big_pass
+
+
+def test_grid_mode_tiles_every_tet(ctx, O, cfg1_rt):
+    """property: the cells of each tet tile it (volume conservation), no dropped cells."""
+    mesh, sites, _, _ = cfg1_rt
     ctx.set_mesh(mesh)
     res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
     recs = res.records()
@@ -237,6 +282,7 @@ def test_grid_mode_tiles_every_tet(ctx, O, cfg1):
     pv = np.zeros(mesh.n_tet)
     np.add.at(pv, recs["tet_id"], cv)
     tv = mesh.tet_volumes()
-    assert np.max(np.abs(pv - tv) / tv) < 2e-3
-    assert abs(pv.sum() - tv.sum()) / tv.sum() < 1e-5
+    rel = np.abs(pv - tv) / tv
+    assert np.mean(rel) < 1e-4 and np.max(rel) < 0.1  # float planes of sliver tets dominate the max
+    assert abs(pv.sum() - tv.sum()) / tv.sum() < 1e-6
     assert res.status_histogram[[1, 2, 3, 8, 9]].sum() == 0  # no overflow / inconsistent cells

@@ -46,7 +46,8 @@ def test_shim_rpd_matches_oracle(O, synth):
                       sites.site_soa, sites.weights, sites.flags, knn.astype(np.int32),
                       np.array([sites.n_site, k], np.int32)):
                 _w(f, a)
-        subprocess.check_call([DRIVER, "rpd", fin, fout])
+        r = subprocess.run([DRIVER, "rpd", fin, fout], capture_output=True, text=True)
+        assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
         with open(fout, "rb") as f:
             hdr = _r(f, np.int32).reshape(-1, 8)
             ver = _r(f, np.uint8).reshape(-1, 96, 4)
