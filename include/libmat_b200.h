@@ -104,7 +104,9 @@ int mb_set_tet_range(mb_ctx* ctx, int first, int count);
 /* ---------------------------------------------------------------- RPD */
 typedef struct {
   int lanes_per_cell;   /* 0 = default; 8, 16 or 32 lanes cooperate on one (tet, site) cell */
-  int grid_k;           /* grid-kNN mode: max candidate sites kept per tet (0 = default 96) */
+  int grid_k;           /* grid-kNN mode: expected candidate sites per tet (0 = default 96): <=32 / <=96 /
+                           >96 pick the fast-path list capacity 32 / 96 / 256; longer lists are redone
+                           by a 2048-entry pass; at most 96 (256 if grid_k > 96) are kept per tet */
   int want_volumes;     /* accumulate per-site volume / barycentre sums                       */
   int keep_on_device;   /* reserved */
 } mb_rpd_opts;
@@ -137,7 +139,7 @@ int mb_rpd_count(const mb_rpd_result* res, long* n_cells, long* n_pairs, long* n
  * [3] listed neighbours rejected by the conservative bounding filter (the reference would have
  * clipped and popped them)  [4] tets whose candidate list overflowed grid_k (grid mode)
  * (truncated: should be 0)  [5] compact result bytes  [6] tets redone by the big-list candidate pass
- * [7] reserved */
+ * [7] conflict tests the FP32 filter could not decide (evaluated with the FP64 determinant) */
 int mb_rpd_stats(const mb_rpd_result* res, long stats[8]);
 /* int[10]: index = status+1 (early_return .. needs_perturb), over all candidate pairs */
 int mb_rpd_status_histogram(const mb_rpd_result* res, long hist[10]);

@@ -57,7 +57,9 @@ inline void expand_cell(const uint32_t* w, int id, ConvexCellHost& c) {
     c.clip_id2_data_trans[i] = cmake_int2((int)p[3 * i], (int)p[3 * i + 1]);
   }
   p += 3 * nb_p;
-  std::memcpy(c.edge_data, p, 3 * (size_t)nb_e);
+  // the compact record packs edges as 3 bytes; the host cuchar3 is aligned(4) (common_cxx.h:29-31)
+  const unsigned char* eb = reinterpret_cast<const unsigned char*>(p);
+  for (int i = 0; i < nb_e; i++) c.edge_data[i] = cmake_uchar3(eb[3 * i], eb[3 * i + 1], eb[3 * i + 2]);
   c.id = id;
 }
 

@@ -218,7 +218,7 @@ int mb_rpd_stats(const mb_rpd_result* res, long stats[8]) {
   stats[4] = res->n_cand_overflow;
   stats[5] = res->compact_bytes;
   stats[6] = res->n_ovf_tets;
-  stats[7] = 0;
+  stats[7] = res->n_exact;
   return MB_OK;
 }
 

@@ -110,7 +110,7 @@ struct RpdCounters {
   unsigned long long n_valid;      // cells with status success
   unsigned long long n_cand_overflow;
   unsigned long long hist[10];
-  unsigned long long pad[1];
+  unsigned long long pad[1];       // [15] conflict tests that needed the FP64 determinant
   unsigned long long n_ovf_tets;   // [16] grid mode: tets handed to the big-list candidate pass
   unsigned long long work_cursor;  // [17] K3 dynamic work distribution
   unsigned long long reserved[6];
@@ -120,7 +120,7 @@ struct RpdCounters {
 
 struct mb_rpd_result {
   mb_ctx* ctx = nullptr;
-  long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0, n_cand_overflow = 0, n_ovf_tets = 0;
+  long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0, n_cand_overflow = 0, n_ovf_tets = 0, n_exact = 0;
   long hist[10] = {0};
   long compact_bytes = 0;
   float ms[4] = {0, 0, 0, 0};

@@ -1,18 +1,28 @@
 // K3: sub-warp-cooperative convex-cell clipping (one group of G lanes per (tet, site) cell).
 //
 // Replaces clipped_voro_cell_test_GPU_param_tet (reference src/rpd3d/convex_cell.cu:1166-1337),
-// which runs ONE THREAD per cell with 3 KB of shared memory per thread (64 threads / SM).
-// Here G in {8,16,32} lanes share one 2.3 KB polytope in shared memory:
-//   * lanes scan the neighbour list G at a time: float4 gather of the neighbour sphere, exact
-//     bisector, then a conservative FP32 filter against the 4 vertices of the initial tet (any
-//     plane that provably removes nothing is skipped -- the reference would pop it again,
-//     convex_cell.cu:741-744);
-//   * surviving planes are handled in list order: lanes evaluate the reference's FP64 det4x4
-//     predicate on the cell vertices in parallel (bit-exact), one lane replays the reference's
-//     order-defining bookkeeping (swap partition :706-721, cavity boundary walk :618-678) on the
-//     shared-memory state, then lanes create the new edges / vertices in parallel (:756-773).
-// Array positions therefore equal the reference's, so records are byte-identical on the
-// defined entries in given-neighbours mode.
+// which runs ONE THREAD per cell with 3 KB of shared memory per thread (64 threads / SM) and
+// evaluates a 4x4 FP64 determinant for every (vertex, plane) pair.
+//
+// Here G in {4,8,16,32} lanes share one polytope in shared memory and the 32/G groups of a warp
+// advance in LOCKSTEP through a small state machine (fetch pair -> scan G neighbours -> clip by one
+// plane -> ... -> write record), so that the order-defining serial bookkeeping of the groups
+// co-issues instead of serialising the warp:
+//   * scan: lanes gather G neighbour spheres (float4), build the exact bisector, and cull planes
+//     that provably remove nothing with a conservative FP32 test against the 4 tet vertices (the
+//     reference would clip and pop them again, convex_cell.cu:741-744);
+//   * clip: lanes evaluate the conflict predicate of the cell vertices in parallel.  FILTERED
+//     PREDICATE: every vertex caches the cofactor vector of its three planes (the FP64 minors of
+//     det4x4, rounded to FP32) when it is created; sign(cofactors . plane) is accepted when it
+//     exceeds a rigorous error bound, otherwise the reference's FP64 det4x4 is evaluated in its
+//     literal operation order (common_cuda.h:195-213) -- decisions are bit-identical to the
+//     reference's in both cases;
+//   * one lane per group replays the reference's order-defining bookkeeping (swap partition
+//     :706-721, cavity boundary walk :618-678) on the shared-memory state, then lanes create the
+//     new edges / vertices (+ their cofactors) in parallel (:756-773).
+// Array positions therefore equal the reference's, so records are byte-identical on the defined
+// entries in given-neighbours mode.  Work is distributed dynamically (warp-level chunks from a
+// global cursor) because the cost per cell varies by an order of magnitude.
 #pragma once
 
 #include "rpd_device.cuh"
@@ -28,10 +38,10 @@ struct ClipArgs {
   const float4* site4;
   int n_site;
   // neighbour lists
-  const int* nbr;        // given mode: [n_site][nbr_stride]; grid mode: [local tet][nbr_stride]
-  int nbr_stride;        // given mode: site_k; grid mode: kcap
-  const int* nbr_cnt;    // grid mode: #candidates per local tet (nullptr in given mode)
-  int tet_first;         // first tet of the processed range (grid-mode lists are relative to it)
+  const int* nbr;        // per-site lists: [n_site][nbr_stride]; per-tet lists: [local tet][nbr_stride]
+  int nbr_stride;        // per-site: site_k; per-tet: kcap
+  const int* nbr_cnt;    // per-tet lists: #candidates per local tet (nullptr for per-site lists)
+  int tet_first;         // first tet of the processed range (per-tet lists are relative to it)
   // pairs
   const int* pair_tet;
   const int* pair_site;
@@ -52,6 +62,8 @@ struct ClipArgs {
 #define CNT_VALID 3
 #define CNT_CANDOVF 4
 #define CNT_HIST 5
+#define CNT_EXACT 15  // conflict tests that fell through the FP32 filter to the FP64 determinant
+#define CNT_WORK_CURSOR_IDX 17
 
 template <int G>
 __device__ __forceinline__ unsigned group_ballot(unsigned gmask, int gshift, bool pred) {
@@ -61,308 +73,419 @@ __device__ __forceinline__ unsigned group_ballot(unsigned gmask, int gshift, boo
 
 // z of the edge between planes a < b (closed form of what new_edge stored, convex_cell.cu:604-616,
 // and of the 6 initial tet edges :194-210)
-__device__ __forceinline__ unsigned char edge_z(int a, int b, const float* hf, unsigned long long e6) {
+__device__ __forceinline__ unsigned char edge_z(int a, int b, unsigned hf4, unsigned long long e6) {
   if (b < 4) {
     // face pair -> index in e_adj6 order: (2,3)->0 (1,3)->1 (1,2)->2 (0,3)->3 (0,2)->4 (0,1)->5
     int idx = (a == 2) ? 0 : (a == 1 ? (b == 3 ? 1 : 2) : (b == 3 ? 3 : (b == 2 ? 4 : 5)));
     return (unsigned char)((e6 >> (8 * idx)) & 0xff);
   }
-  const float ha = a == 0 ? hf[0] : (a == 1 ? hf[1] : (a == 2 ? hf[2] : (a == 3 ? hf[3] : 1.f)));
-  return (unsigned char)fmaxf(ha, 1.f);
+  // max(h_a, h_b) with h = 1 for bisectors; h_a = (uchar) f_adj of tet face a
+  const unsigned ha = a < 4 ? ((hf4 >> (8 * a)) & 0xffu) : 1u;
+  return (unsigned char)max(ha, 1u);
 }
 
 #define CLIP_CHUNK_WORDS 1024u  // scratch is bump-allocated per group in 4 KB chunks
 
+enum : int { GS_IDLE = 0, GS_NEW = 1, GS_RUN = 2, GS_FINISH = 3, GS_EXIT = 4 };
+
+// cofactor vector of a vertex (p1,p2,p3): det4x4(p1,p2,p3,e) = c . e with
+// c = (m234, -m134, m124, -m123)
+__device__ __forceinline__ float4 cofactors_f32(const Minors& m) {
+  return make_float4((float)m.m234, (float)(-m.m134), (float)m.m124, (float)(-m.m123));
+}
+
 template <int G>
-__device__ void clip_cell(const ClipArgs& A, long long pair, CellS& S, int lane, unsigned gmask,
-                          int gshift, unsigned long long& chunk_at, unsigned& chunk_left,
-                          unsigned long long* blk_cnt) {
-  const int t = A.pair_tet[pair];
-  const int seed_id = A.pair_site[pair];
+__global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CellS* cells = reinterpret_cast<CellS*>(smem_raw);
+  constexpr int NG = 32 / G;  // groups per warp
+  const int lane = threadIdx.x % G;
+  const int wl = threadIdx.x & 31;
+  const int gshift = (wl / G) * G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gshift);
   const int src = gshift;  // warp lane of the group's rank 0
+  CellS& S = cells[threadIdx.x / G];
+  __shared__ unsigned long long blk_cnt[16];  // block-aggregated counters (RpdCounters layout)
+  if (threadIdx.x < 16) blk_cnt[threadIdx.x] = 0;
+  __syncthreads();
 
-  // ---- load tet + seed (all lanes; same addresses -> one transaction, broadcast) -------------
-  const int4 vi = A.tet_idx[t];
-  const float4 q0 = A.vert4[vi.x], q1 = A.vert4[vi.y], q2 = A.vert4[vi.z], q3 = A.vert4[vi.w];
-  const int4 fadj = A.tet_fadj[t];
-  const int4 fid = A.tet_fid[t];
-  const uint2 e6u = A.tet_e6[t];
-  const unsigned long long e6 = ((unsigned long long)e6u.y << 32) | e6u.x;
-  const float4 seed = A.site4[seed_id];
-  float hf[4] = {(float)fadj.x, (float)fadj.y, (float)fadj.z, (float)fadj.w};
+  // warp-level work queue (chunks of pairs from the global cursor) and per-group scratch chunk
+  long long wq_next = 0, wq_end = 0;
+  bool wq_dry = false;
+  unsigned long long chunk_at = 0;
+  unsigned chunk_left = 0;
+  unsigned n_clips = 0, n_culled = 0, n_valid = 0, n_exact = 0;
 
-  // ---- initial polytope: ConvexCell ctor, convex_cell.cu:116-214 ----------------------------------
-  if (lane < 4) {
-    // face i is opposite local vertex i: {2,1,3},{0,2,3},{1,0,3},{0,1,2} (convex_cell.h:30-31)
-    float3 p[4] = {make_float3(q0.x, q0.y, q0.z), make_float3(q1.x, q1.y, q1.z),
-                   make_float3(q2.x, q2.y, q2.z), make_float3(q3.x, q3.y, q3.z)};
-    const int f0 = lane == 0 ? 2 : (lane == 1 ? 0 : (lane == 2 ? 1 : 0));
-    const int f1 = lane == 0 ? 1 : (lane == 1 ? 2 : (lane == 2 ? 0 : 1));
-    const int f2 = lane == 3 ? 2 : 3;
-    float3 a = f0 == 0 ? p[0] : (f0 == 1 ? p[1] : p[2]);
-    float3 b = f1 == 0 ? p[0] : (f1 == 1 ? p[1] : p[2]);
-    float3 c = f2 == 2 ? p[2] : p[3];
-    S.plane[lane] = tri2plane_exact(a, b, c);
-    S.pnb[lane] = lane == 0 ? fid.x : (lane == 1 ? fid.y : (lane == 2 ? fid.z : fid.w));
-    // dual triangles (1,3,2) (0,2,3) (0,3,1) (0,1,2) with w = (uchar)v_adjs (:186-189)
-    const float4 qq = lane == 0 ? q0 : (lane == 1 ? q1 : (lane == 2 ? q2 : q3));
-    const unsigned char w = (unsigned char)__float_as_int(qq.w);
-    S.ver[lane] = lane == 0 ? make_uchar4(1, 3, 2, w)
-                            : (lane == 1 ? make_uchar4(0, 2, 3, w)
-                                         : (lane == 2 ? make_uchar4(0, 3, 1, w) : make_uchar4(0, 1, 2, w)));
-  }
-  if (lane < 6) {
-    // edges (2,3)(1,3)(1,2)(0,3)(0,2)(0,1) with the e_adj of vertex pairs (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
-    const unsigned char ea = lane < 3 ? (lane == 0 ? 2 : 1) : 0;
-    const unsigned char eb = lane == 0 ? 3 : (lane == 1 ? 3 : (lane == 2 ? 2 : (lane == 3 ? 3 : (lane == 4 ? 2 : 1))));
-    S.edge[3 * lane + 0] = ea;
-    S.edge[3 * lane + 1] = eb;
-    S.edge[3 * lane + 2] = (unsigned char)((e6 >> (8 * lane)) & 0xff);
-  }
-  __syncwarp(gmask);
+  // group state (identical in all lanes of a group unless noted)
+  int state = GS_IDLE;
+  long long pair = 0;
+  int t = 0, seed_id = 0;
+  float4 seed = make_float4(0, 0, 0, 0);
+  unsigned hf4 = 0;  // (uchar) f_adjs of the 4 tet faces
+  unsigned long long e6 = 0;
+  const int* list = nullptr;
+  int list_len = 0, base = 0;
+  bool per_tet = A.nbr_cnt != nullptr, list_done = false, cull_ok = false;
+  unsigned todo = 0, valid = 0, cvalid = 0;
+  int nb = -1;                                // per lane: the neighbour of this lane's slot
+  float4 eqn = make_float4(0, 0, 0, 0);       // per lane: its bisector
+  int nb_v = 0, nb_p = 0, nb_e = 0, status = ST_success;
 
-  // ---- filter data: cofactor vectors of the 4 initial vertices -------------------------------
-  bool cull_ok = true;
-  if (lane < 4) {
-    const uchar4 v = S.ver[lane];
-    const Minors m = minors_exact(S.plane[v.x], S.plane[v.y], S.plane[v.z]);
-    // det4x4(p1,p2,p3,e) = m234*e.x - m134*e.y + m124*e.z - m123*e.w
-    const float4 c = make_float4((float)m.m234, (float)(-m.m134), (float)m.m124, (float)(-m.m123));
-    S.c0[lane] = c;
-    S.a0[lane] = fabsf(c.x) + fabsf(c.y) + fabsf(c.z);
-    // a proper vertex has c.w < 0 (conflict <=> det > 0 <=> vertex on the negative side)
-    cull_ok = (c.w < 0.f) && isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w);
-  }
-  cull_ok = group_ballot<G>(gmask, gshift, !cull_ok) == 0;
-  __syncwarp(gmask);
-  float4 c0[4] = {S.c0[0], S.c0[1], S.c0[2], S.c0[3]};
-  float a0[4] = {S.a0[0], S.a0[1], S.a0[2], S.a0[3]};
-
-  int nb_v = 4, nb_p = 4, nb_e = 6;
-  int status = ST_success;
-  unsigned long long n_clips = 0, n_culled = 0;
-
-  // ---- neighbour list --------------------------------------------------------------------------
-  const int* list;
-  int list_len;
-  if (A.nbr_cnt) {
-    list = A.nbr + (size_t)(t - A.tet_first) * A.nbr_stride;
-    list_len = A.nbr_cnt[t - A.tet_first];
-  } else {
-    list = A.nbr + (size_t)seed_id * A.nbr_stride;
-    list_len = A.nbr_stride;
-  }
-
-  bool done = false;
-  for (int base = 0; base < list_len && !done; base += G) {
-    // ---- stage 1: G neighbours in parallel ---------------------------------------------------
-    const int j = base + lane;
-    int nb = (j < list_len) ? list[j] : -1;
-    bool is_end = false, cand = false, valid_nb = false;
-    float4 eqn = make_float4(0, 0, 0, 0);
-    if (A.nbr_cnt) {
-      // grid mode: the list is the tet's candidate set; skip the seed itself
-      cand = (nb >= 0 && nb != seed_id);
-      valid_nb = cand;
-    } else {
-      // given mode: the first -1 terminates the list (convex_cell.cu:1259)
-      is_end = (j < list_len) && (nb == -1);
-      cand = (nb >= 0);
-      valid_nb = cand;
+  for (;;) {
+    __syncwarp();
+    // ================= A: hand pairs to idle groups =========================================
+    {
+      const unsigned idle = __ballot_sync(0xffffffffu, state == GS_IDLE && lane == 0);
+      if (idle) {
+        if (wq_next >= wq_end && !wq_dry) {
+          unsigned long long b = 0;
+          if (wl == 0) b = atomicAdd(&A.counters[CNT_WORK_CURSOR_IDX], (unsigned long long)(8 * NG));
+          b = __shfl_sync(0xffffffffu, b, 0);
+          wq_next = (long long)b;
+          wq_end = min((long long)b + 8 * NG, A.n_pairs);
+          if (wq_next >= A.n_pairs) wq_dry = true;
+        }
+        if (state == GS_IDLE) {
+          const int r = __popc(idle & ((1u << src) - 1u));
+          if (wq_next + r < wq_end) {
+            pair = wq_next + r;
+            state = GS_NEW;
+          } else if (wq_dry) {
+            state = GS_EXIT;
+          }
+        }
+        const long long avail = wq_end > wq_next ? wq_end - wq_next : 0;
+        wq_next += min((long long)__popc(idle), avail);
+      }
+      if (__ballot_sync(0xffffffffu, state != GS_EXIT) == 0) break;
     }
-    if (cand) {
-      const float4 B = A.site4[nb];
-      eqn = bisector_exact(seed, B);
-      if (cull_ok) {
-        const float n1 = fabsf(eqn.x) + fabsf(eqn.y) + fabsf(eqn.z);
-        const float nmax = fmaxf(fabsf(eqn.x), fmaxf(fabsf(eqn.y), fabsf(eqn.z)));
-        bool all_out = true;
+    // ================= A2: initialise new cells (ConvexCell ctor, convex_cell.cu:116-214) =======
+    if (state == GS_NEW) {
+      t = A.pair_tet[pair];
+      seed_id = A.pair_site[pair];
+      const int4 vi = A.tet_idx[t];
+      const float4 q0 = A.vert4[vi.x], q1 = A.vert4[vi.y], q2 = A.vert4[vi.z], q3 = A.vert4[vi.w];
+      const int4 fadj = A.tet_fadj[t];
+      const int4 fid = A.tet_fid[t];
+      const uint2 e6u = A.tet_e6[t];
+      e6 = ((unsigned long long)e6u.y << 32) | e6u.x;
+      seed = A.site4[seed_id];
+      hf4 = (unsigned)(unsigned char)fadj.x | ((unsigned)(unsigned char)fadj.y << 8) |
+            ((unsigned)(unsigned char)fadj.z << 16) | ((unsigned)(unsigned char)fadj.w << 24);
+      if (lane < 4) {
+        // face i is opposite local vertex i: {2,1,3},{0,2,3},{1,0,3},{0,1,2} (convex_cell.h:30-31)
+        const float3 p0 = make_float3(q0.x, q0.y, q0.z), p1 = make_float3(q1.x, q1.y, q1.z),
+                     p2 = make_float3(q2.x, q2.y, q2.z), p3 = make_float3(q3.x, q3.y, q3.z);
+        const float3 a = lane == 0 ? p2 : (lane == 2 ? p1 : p0);
+        const float3 b = lane == 0 ? p1 : (lane == 1 ? p2 : (lane == 2 ? p0 : p1));
+        const float3 c = lane == 3 ? p2 : p3;
+        S.plane[lane] = tri2plane_exact(a, b, c);
+        S.pnb[lane] = lane == 0 ? fid.x : (lane == 1 ? fid.y : (lane == 2 ? fid.z : fid.w));
+        // dual triangles (1,3,2) (0,2,3) (0,3,1) (0,1,2) with w = (uchar)v_adjs (:186-189)
+        const float4 qq = lane == 0 ? q0 : (lane == 1 ? q1 : (lane == 2 ? q2 : q3));
+        const unsigned char w = (unsigned char)__float_as_int(qq.w);
+        S.ver[lane] = lane == 0 ? make_uchar4(1, 3, 2, w)
+                                : (lane == 1 ? make_uchar4(0, 2, 3, w)
+                                             : (lane == 2 ? make_uchar4(0, 3, 1, w) : make_uchar4(0, 1, 2, w)));
+      }
+      if (lane >= G - 6 || G < 8) {
+        // edges (2,3)(1,3)(1,2)(0,3)(0,2)(0,1) with the e_adj of vertex pairs (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
+        for (int q = (G < 8 ? lane : lane - (G - 6)); q < 6; q += (G < 8 ? G : 6)) {
+          const unsigned char ea = q < 3 ? (q == 0 ? 2 : 1) : 0;
+          const unsigned char eb = q == 0 ? 3 : (q == 1 ? 3 : (q == 2 ? 2 : (q == 3 ? 3 : (q == 4 ? 2 : 1))));
+          S.edge[3 * q + 0] = ea;
+          S.edge[3 * q + 1] = eb;
+          S.edge[3 * q + 2] = (unsigned char)((e6 >> (8 * q)) & 0xff);
+        }
+      }
+      __syncwarp(gmask);
+      // cofactor vectors of the 4 initial vertices: the tet-level cull filter (c0) and the first
+      // four entries of the per-vertex filter cache
+      bool ok0 = true;
+      if (lane < 4) {
+        const uchar4 v = S.ver[lane];
+        const float4 c = cofactors_f32(minors_exact(S.plane[v.x], S.plane[v.y], S.plane[v.z]));
+        S.c0[lane] = c;
+        S.cof[lane] = c;
+        // a proper vertex has c.w < 0 (conflict <=> det > 0 <=> vertex on the negative side)
+        ok0 = (c.w < 0.f) && isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w);
+      }
+      cull_ok = group_ballot<G>(gmask, gshift, !ok0) == 0;
+      cvalid = 0xfu;
+      nb_v = 4;
+      nb_p = 4;
+      nb_e = 6;
+      status = ST_success;
+      if (per_tet) {
+        list = A.nbr + (size_t)(t - A.tet_first) * A.nbr_stride;
+        list_len = A.nbr_cnt[t - A.tet_first];
+      } else {
+        list = A.nbr + (size_t)seed_id * A.nbr_stride;
+        list_len = A.nbr_stride;
+      }
+      base = 0;
+      todo = 0;
+      valid = 0;
+      list_done = false;
+      state = GS_RUN;
+      __syncwarp(gmask);
+    }
+    // ================= B: scan the next G listed neighbours =====================================
+    if (state == GS_RUN && todo == 0) {
+      if (list_done || base >= list_len) {
+        state = GS_FINISH;
+      } else {
+        const int j = base + lane;
+        nb = (j < list_len) ? list[j] : -1;
+        bool is_end = false, cand = false;
+        if (per_tet) {
+          cand = (nb >= 0 && nb != seed_id);  // the list is the tet's candidate set; skip the seed
+        } else {
+          is_end = (j < list_len) && (nb == -1);  // the first -1 terminates the list (:1259)
+          cand = (nb >= 0);
+        }
+        const bool valid_nb = cand;
+        if (cand) {
+          eqn = bisector_exact(seed, A.site4[nb]);
+          if (cull_ok) {
+            const float n1 = fabsf(eqn.x) + fabsf(eqn.y) + fabsf(eqn.z);
+            const float nmax = fmaxf(fabsf(eqn.x), fmaxf(fabsf(eqn.y), fabsf(eqn.z)));
+            bool all_out = true;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float cw = c0[i].w * eqn.w;
-          const float s = fmaf(c0[i].x, eqn.x, fmaf(c0[i].y, eqn.y, fmaf(c0[i].z, eqn.z, cw)));
-          const float T = fmaf(a0[i], nmax, fabsf(cw));
-          const float margin = fmaxf(4e-6f * T, 1e-3f * n1 * fabsf(c0[i].w));
-          all_out = all_out && (s < -margin);
+            for (int i = 0; i < 4; i++) {
+              const float4 c = S.c0[i];
+              const float cw = c.w * eqn.w;
+              const float s = fmaf(c.x, eqn.x, fmaf(c.y, eqn.y, fmaf(c.z, eqn.z, cw)));
+              const float T = fmaf(fabsf(c.x) + fabsf(c.y) + fabsf(c.z), nmax, fabsf(cw));
+              const float margin = fmaxf(4e-6f * T, 1e-3f * n1 * fabsf(c.w));
+              all_out = all_out && (s < -margin);
+            }
+            if (all_out) {
+              cand = false;  // certainly removes no vertex: the reference would pop this plane
+              n_culled++;
+            }
+          }
         }
-        if (all_out) {
-          cand = false;  // certainly removes no vertex: the reference would pop this plane
-          n_culled++;
+        const unsigned end_mask = group_ballot<G>(gmask, gshift, is_end);
+        todo = group_ballot<G>(gmask, gshift, cand);
+        // every listed neighbour (culled or not) makes the reference call new_plane, which refuses
+        // a 65th plane (vertex_overflow, convex_cell.cu:562-565)
+        valid = group_ballot<G>(gmask, gshift, valid_nb);
+        if (end_mask) {
+          const unsigned before = (1u << (__ffs(end_mask) - 1)) - 1u;
+          todo &= before;
+          valid &= before;
+          list_done = true;
+        }
+        base += G;
+        if (nb_p >= MBK_MAX_P && valid) {
+          status = ST_vertex_overflow;
+          todo = 0;
+          state = GS_FINISH;
         }
       }
     }
-    unsigned end_mask = group_ballot<G>(gmask, gshift, is_end);
-    unsigned todo = group_ballot<G>(gmask, gshift, cand);
-    // every listed neighbour (culled or not) makes the reference call new_plane, which refuses
-    // a 65th plane (vertex_overflow, convex_cell.cu:562-565)
-    unsigned valid = group_ballot<G>(gmask, gshift, valid_nb);
-    if (end_mask) {
-      const unsigned before = (1u << (__ffs(end_mask) - 1)) - 1u;
-      todo &= before;
-      valid &= before;
-      done = true;
-    }
-    if (nb_p >= MBK_MAX_P && valid) {
-      status = ST_vertex_overflow;
-      break;
-    }
-    // ---- stage 2: survivors in list order ----------------------------------------------------
-    while (todo) {
-      const int k = __ffs(todo) - 1;
-      todo &= todo - 1;
-      if (nb_p >= MBK_MAX_P) {
-        status = ST_vertex_overflow;
-        break;
+    // ================= C: clip by the next surviving plane (clip_by_plane, :680-774) ============
+    // Every sub-phase below sits at the top level of the loop with warp-uniform trip counts and a
+    // full-warp barrier in front, so that the groups of the warp execute it TOGETHER.
+    const bool c_act = (state == GS_RUN && todo != 0);
+    int k = 0, nbk = -1;
+    float4 e = make_float4(0, 0, 0, 0);
+    {
+      // all lanes shuffle (the source index is per lane; idle groups read garbage they never use)
+      k = c_act ? (__ffs(todo) - 1) : 0;
+      nbk = __shfl_sync(0xffffffffu, nb, src + k);
+      e.x = __shfl_sync(0xffffffffu, eqn.x, src + k);
+      e.y = __shfl_sync(0xffffffffu, eqn.y, src + k);
+      e.z = __shfl_sync(0xffffffffu, eqn.z, src + k);
+      e.w = __shfl_sync(0xffffffffu, eqn.w, src + k);
+      if (c_act) {
+        todo &= todo - 1;
+        if (lane == 0) n_clips++;
       }
-      const int nbk = __shfl_sync(gmask, nb, src + k);
-      float4 e;
-      e.x = __shfl_sync(gmask, eqn.x, src + k);
-      e.y = __shfl_sync(gmask, eqn.y, src + k);
-      e.z = __shfl_sync(gmask, eqn.z, src + k);
-      e.w = __shfl_sync(gmask, eqn.w, src + k);
-      n_clips++;
-      // conflict flags of all vertices (lanes strided over vertices)
-      unsigned long long f0 = 0;
-      unsigned f1 = 0;
-      int nb_r = 0;
-      for (int vb = 0; vb < nb_v; vb += G) {
+    }
+    // ---- C1: conflict flags of all vertices (lanes strided over vertices) ----------------------
+    unsigned long long f0 = 0;
+    unsigned f1 = 0;
+    int nb_r = 0;
+    {
+      const int vmax = __reduce_max_sync(0xffffffffu, c_act ? nb_v : 0);
+      const float nmax = fmaxf(fabsf(e.x), fmaxf(fabsf(e.y), fabsf(e.z)));
+      for (int vb = 0; vb < vmax; vb += G) {
         const int v = vb + lane;
         bool cf = false;
-        if (v < nb_v) {
-          const uchar4 tv = S.ver[v];
-          cf = conflict_exact(S.plane[tv.x], S.plane[tv.y], S.plane[tv.z], e);
+        if (c_act && v < nb_v) {
+          bool decided = false;
+          if (v < MBK_CV && ((cvalid >> v) & 1u)) {
+            // filtered predicate: |s - det_fp64| <= ~3e-7 * T, accepted beyond 4e-6 * T
+            const float4 c = S.cof[v];
+            const float cw = c.w * e.w;
+            const float s = fmaf(c.x, e.x, fmaf(c.y, e.y, fmaf(c.z, e.z, cw)));
+            const float T = fmaf(fabsf(c.x) + fabsf(c.y) + fabsf(c.z), nmax, fabsf(cw));
+            if (fabsf(s) > 4e-6f * T) {
+              cf = s > 0.f;
+              decided = true;
+            }
+          }
+          if (!decided) {
+            const uchar4 tv = S.ver[v];
+            cf = conflict_exact(S.plane[tv.x], S.plane[tv.y], S.plane[tv.z], e);
+            n_exact++;
+          }
         }
-        const unsigned m = group_ballot<G>(gmask, gshift, cf);
+        const unsigned m = (__ballot_sync(0xffffffffu, cf) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
         nb_r += __popc(m);
         if (vb < 64)  // G divides 64: a round never straddles the two words
           f0 |= (unsigned long long)m << vb;
         else
           f1 |= m << (vb - 64);
       }
-      if (nb_r == 0) continue;  // plane removes nothing: dropped (:741-744)
-      if (nb_r == nb_v) {
-        status = ST_no_intersection;  // :746-749
-        break;
-      }
-      // ---- one lane replays the order-defining serial bookkeeping ---------------------------
-      int L = 0;
-      int st2 = ST_success;
-      if (lane == 0) {
-        const int cur_p = nb_p;
-        S.plane[cur_p] = e;
-        S.pnb[cur_p] = nbk;
-        // swap partition, convex_cell.cu:706-721
-        int nv = nb_v, i = 0;
-        while (i < nv) {
-          const bool fi = i < 64 ? ((f0 >> i) & 1ull) : ((f1 >> (i - 64)) & 1u);
-          if (fi) {
-            nv--;
-            const bool fn = nv < 64 ? ((f0 >> nv) & 1ull) : ((f1 >> (nv - 64)) & 1u);
-            const uchar4 tmp = S.ver[i];
-            S.ver[i] = S.ver[nv];
-            S.ver[nv] = tmp;
-            if (i < 64)
-              f0 = (f0 & ~(1ull << i)) | ((unsigned long long)fn << i);
-            else
-              f1 = (f1 & ~(1u << (i - 64))) | ((unsigned)fn << (i - 64));
-          } else
-            i++;
-        }
-        // cavity boundary, compute_boundary convex_cell.cu:618-678
-        for (int p = 0; p <= cur_p; p++) S.bnext[p] = MBK_END;
-        int first = MBK_END;
-        int r = nb_r, tt = nv, fails = 0;
-        while (r > 0) {
-          const uchar4 tv = S.ver[tt];
-          const unsigned char pl[3] = {tv.x, tv.y, tv.z};
-          bool in_border[3], opp[3];
-#pragma unroll
-          for (int q = 0; q < 3; q++) in_border[q] = S.bnext[pl[q]] != MBK_END;
-#pragma unroll
-          for (int q = 0; q < 3; q++) opp[q] = S.bnext[pl[(q + 1) % 3]] == pl[q];
-          bool simple = true;
-#pragma unroll
-          for (int q = 0; q < 3; q++)
-            if (!opp[q] && !opp[(q + 1) % 3] && in_border[(q + 1) % 3]) simple = false;
-          if (!opp[0] && !opp[1] && !opp[2]) {
-            if (first == MBK_END) {
-#pragma unroll
-              for (int q = 0; q < 3; q++) S.bnext[pl[q]] = pl[(q + 1) % 3];
-              first = pl[0];
-            } else
-              simple = false;
-          }
-          if (!simple) {
-            tt++;
-            if (tt == nv + r) tt = nv;
-            if (++fails >= r) {  // a full round without progress: the reference spins until
-              st2 = ST_inconsistent_boundary;  // nb_iter > 65535 (:626-629)
-              break;
-            }
-            continue;
-          }
-          fails = 0;
-#pragma unroll
-          for (int q = 0; q < 3; q++)
-            if (!opp[q]) S.bnext[pl[q]] = pl[(q + 1) % 3];
-#pragma unroll
-          for (int q = 0; q < 3; q++)
-            if (opp[q] && opp[(q + 1) % 3]) {
-              const unsigned char pm = pl[(q + 1) % 3];
-              if (first == pm) first = S.bnext[pm];
-              S.bnext[pm] = MBK_END;
-            }
-          const uchar4 tmp = S.ver[tt];
-          S.ver[tt] = S.ver[nv + r - 1];
-          S.ver[nv + r - 1] = tmp;
-          tt = nv;
-          r--;
-        }
-        if (st2 == ST_success && first != MBK_END) {
-          int cir = first;
-          do {
-            S.cyc[L++] = (unsigned char)cir;
-            cir = S.bnext[cir];
-          } while (cir != first && cir != MBK_END && L < MBK_MAX_P);
-        }
-      }
-      L = __shfl_sync(gmask, L, src);
-      st2 = __shfl_sync(gmask, st2, src);
-      __syncwarp(gmask);
+    }
+    // 0: nothing to do (idle, or the plane removes nothing and is dropped, :741-744)
+    // 1: clip   2: the plane removes everything (:746-749)
+    const int act2 = !c_act ? 0 : (nb_r == nb_v ? 2 : (nb_r != 0 ? 1 : 0));
+    if (act2 == 2) {
+      status = ST_no_intersection;
+      todo = 0;
+      state = GS_FINISH;
+    }
+    __syncwarp();
+    // ---- C2: one lane per group replays the order-defining serial bookkeeping -----------------
+    int L = 0;
+    int st2 = ST_success;
+    unsigned cv = cvalid;
+    if (act2 == 1 && lane == 0) {
       const int cur_p = nb_p;
+      S.plane[cur_p] = e;
+      S.pnb[cur_p] = nbk;
+      // swap partition, convex_cell.cu:706-721 (the filter cache follows the kept vertices)
+      int nv = nb_v, i = 0;
+      while (i < nv) {
+        const bool fi = i < 64 ? ((f0 >> i) & 1ull) : ((f1 >> (i - 64)) & 1u);
+        if (fi) {
+          nv--;
+          const bool fn = nv < 64 ? ((f0 >> nv) & 1ull) : ((f1 >> (nv - 64)) & 1u);
+          const uchar4 tmp = S.ver[i];
+          S.ver[i] = S.ver[nv];
+          S.ver[nv] = tmp;
+          if (i < MBK_CV) {
+            const bool vn = nv < MBK_CV && ((cv >> nv) & 1u);
+            if (vn) S.cof[i] = S.cof[nv];
+            cv = (cv & ~(1u << i)) | ((unsigned)vn << i);
+          }
+          if (i < 64)
+            f0 = (f0 & ~(1ull << i)) | ((unsigned long long)fn << i);
+          else
+            f1 = (f1 & ~(1u << (i - 64))) | ((unsigned)fn << (i - 64));
+        } else
+          i++;
+      }
+      // cavity boundary, compute_boundary convex_cell.cu:618-678
+      for (int p = 0; p <= cur_p; p++) S.bnext[p] = MBK_END;
+      int first = MBK_END;
+      int r = nb_r, tt = nv, fails = 0;
+      while (r > 0) {
+        const uchar4 tv = S.ver[tt];
+        const unsigned char pl[3] = {tv.x, tv.y, tv.z};
+        bool in_border[3], opp[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) in_border[q] = S.bnext[pl[q]] != MBK_END;
+#pragma unroll
+        for (int q = 0; q < 3; q++) opp[q] = S.bnext[pl[(q + 1) % 3]] == pl[q];
+        bool simple = true;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+          if (!opp[q] && !opp[(q + 1) % 3] && in_border[(q + 1) % 3]) simple = false;
+        if (!opp[0] && !opp[1] && !opp[2]) {
+          if (first == MBK_END) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) S.bnext[pl[q]] = pl[(q + 1) % 3];
+            first = pl[0];
+          } else
+            simple = false;
+        }
+        if (!simple) {
+          tt++;
+          if (tt == nv + r) tt = nv;
+          if (++fails >= r) {  // a full round without progress: the reference spins until
+            st2 = ST_inconsistent_boundary;  // nb_iter > 65535 (:626-629)
+            break;
+          }
+          continue;
+        }
+        fails = 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+          if (!opp[q]) S.bnext[pl[q]] = pl[(q + 1) % 3];
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+          if (opp[q] && opp[(q + 1) % 3]) {
+            const unsigned char pm = pl[(q + 1) % 3];
+            if (first == pm) first = S.bnext[pm];
+            S.bnext[pm] = MBK_END;
+          }
+        const uchar4 tmp = S.ver[tt];
+        S.ver[tt] = S.ver[nv + r - 1];
+        S.ver[nv + r - 1] = tmp;
+        tt = nv;
+        r--;
+      }
+      if (st2 == ST_success && first != MBK_END) {
+        int cir = first;
+        do {
+          S.cyc[L++] = (unsigned char)cir;
+          cir = S.bnext[cir];
+        } while (cir != first && cir != MBK_END && L < MBK_MAX_P);
+      }
+    }
+    __syncwarp();
+    L = __shfl_sync(0xffffffffu, L, src);
+    st2 = __shfl_sync(0xffffffffu, st2, src);
+    cv = __shfl_sync(0xffffffffu, cv, src);
+    const int cur_p = nb_p;
+    bool do_new = false;
+    if (act2 == 1) {
       nb_p++;
       nb_v -= nb_r;
-      if (st2 != ST_success) {
+      // slots >= nb_v no longer hold live vertices
+      cvalid = nb_v >= 32 ? cv : (cv & ((1u << nb_v) - 1u));
+      if (st2 != ST_success)
         status = st2;
-        break;
+      else if (L != 0) {  // first_boundary_ != END_OF_LIST (:754)
+        if (nb_e + L > MBK_MAX_E)
+          status = ST_edge_overflow;
+        else
+          do_new = true;
       }
-      if (L == 0) continue;  // first_boundary_ == END_OF_LIST (:754)
-      // ---- new edges (:756-762) and new vertices (:764-773), lanes over the cycle -----------
-      if (nb_e + L > MBK_MAX_E) {
-        status = ST_edge_overflow;
-        break;
-      }
+    }
+    // ---- C3: new edges (:756-762) and new vertices (:764-773), lanes over the cycle -----------
+    {
+      const int Lmax = __reduce_max_sync(0xffffffffu, do_new ? L : 0);
       bool perturb = false;
-      for (int jb = 0; jb < L; jb += G) {
+      for (int jb = 0; jb < Lmax; jb += G) {
         const int jj = jb + lane;
         bool pj = false;
-        if (jj < L) {
+        if (do_new && jj < L) {
           const int cir = S.cyc[jj];
           const int nxt = S.cyc[jj + 1 == L ? 0 : jj + 1];
-          const unsigned char z1 = edge_z(cir, cur_p, hf, e6);
+          const unsigned char z1 = edge_z(cir, cur_p, hf4, e6);
           S.edge[3 * (nb_e + jj) + 0] = (unsigned char)cir;
           S.edge[3 * (nb_e + jj) + 1] = (unsigned char)cur_p;
           S.edge[3 * (nb_e + jj) + 2] = z1;
-          const unsigned char z2 = edge_z(nxt, cur_p, hf, e6);
-          const unsigned char z3 = edge_z(min(cir, nxt), max(cir, nxt), hf, e6);
+          const unsigned char z2 = edge_z(nxt, cur_p, hf4, e6);
+          const unsigned char z3 = edge_z(min(cir, nxt), max(cir, nxt), hf4, e6);
           const unsigned char w = max(max(z1, z2), z3);
-          if (nb_v + jj + 1 < MBK_MAX_T) S.ver[nb_v + jj] = make_uchar4(cur_p, cir, nxt, w);
+          const float4 p2 = S.plane[cir], p3 = S.plane[nxt];
+          const int slot = nb_v + jj;
+          if (slot + 1 < MBK_MAX_T) {
+            S.ver[slot] = make_uchar4(cur_p, cir, nxt, w);
+            if (slot < MBK_CV) S.cof[slot] = cofactors_f32(minors_exact(e, p2, p3));
+          }
           // is_vertex_perturb (:274-316): w-component of the vertex == 0
-          const float4 p1 = e, p2 = S.plane[cir], p3 = S.plane[nxt];
-          const float wdet = det3_exact(p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z);
+          const float wdet = det3_exact(e.x, e.y, e.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z);
           pj = (wdet == 0.f);
         }
-        const unsigned pm = group_ballot<G>(gmask, gshift, pj);
+        const unsigned pm = (__ballot_sync(0xffffffffu, pj) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
         if (pm && !perturb) {
           perturb = true;
           const int jp = jb + __ffs(pm) - 1;          // first perturbed vertex
@@ -370,116 +493,101 @@ __device__ void clip_cell(const ClipArgs& A, long long pair, CellS& S, int lane,
           status = (jo < L && jo < jp) ? ST_triangle_overflow : ST_needs_perturb;
         }
       }
-      if (!perturb && nb_v + L + 1 > MBK_MAX_T) status = ST_triangle_overflow;  // nb_v+1 >= 96 (:525)
-      nb_e += L;
-      nb_v += L;
-      __syncwarp(gmask);
-      if (status != ST_success) break;
-      // a later listed neighbour in this chunk would be refused by new_plane
-      if (nb_p >= MBK_MAX_P && (valid & ~((2u << k) - 1u))) {
-        status = ST_vertex_overflow;
-        break;
+      if (do_new) {
+        if (!perturb && nb_v + L + 1 > MBK_MAX_T) status = ST_triangle_overflow;  // nb_v+1 >= 96 (:525)
+        // the new vertices occupy slots [nb_v, nb_v+L): their cache entries are fresh
+        const int lo = min(nb_v, 32), hi = min(nb_v + L, 32);
+        const unsigned add = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((lo >= 32) ? 0xffffffffu : ((1u << lo) - 1u));
+        cvalid |= add;
+        nb_e += L;
+        nb_v += L;
       }
     }
-    if (status != ST_success) break;
-  }
-  __syncwarp(gmask);
-
-  // ---- output: copy() convex_cell.cu:933-949 into the compact record ---------------------------
-  long long blob_at = -1;
-  int words = 0;
-  if (status == ST_success) {
-    words = compact_words(nb_v, nb_p, nb_e);
-    unsigned long long at = 0;
-    if (lane == 0) {
-      if ((unsigned)words > chunk_left) {  // one global atomic per ~13 cells instead of per cell
-        const unsigned grab = max(CLIP_CHUNK_WORDS, (unsigned)words);
-        chunk_at = atomicAdd(&A.counters[CNT_BLOB], (unsigned long long)grab);
-        chunk_left = grab;
+    if (act2 == 1) {
+      // a later listed neighbour of this batch would be refused by new_plane (:562-565)
+      if (status == ST_success && nb_p >= MBK_MAX_P && (todo || (valid & ~((2u << k) - 1u)))) status = ST_vertex_overflow;
+      if (status != ST_success) {
+        todo = 0;
+        state = GS_FINISH;
       }
-      at = chunk_at;
-      chunk_at += words;
-      chunk_left -= words;
     }
-    at = __shfl_sync(gmask, at, src);
-    if (at + (unsigned long long)words <= A.scratch_words) {
-      blob_at = (long long)at;
-      uint32_t* o = A.scratch + at;
-      if (lane == 0) {
-        o[0] = (uint32_t)t;
-        o[1] = (uint32_t)seed_id;
-        o[2] = (uint32_t)nb_v | ((uint32_t)nb_p << 8) | ((uint32_t)nb_e << 16) | ((uint32_t)status << 24);
-        o[3] = __float_as_uint(seed.w);
-      }
-      o += 4;
-      const uint32_t* sv = reinterpret_cast<const uint32_t*>(S.ver);
-      for (int i = lane; i < nb_v; i += G) o[i] = sv[i];
-      o += nb_v;
-      // planes are written word-wise: the record is only 4-byte aligned
-      for (int i = lane; i < 4 * nb_p; i += G)
-        o[i] = reinterpret_cast<const uint32_t*>(S.plane)[i];
-      o += 4 * nb_p;
-      for (int i = lane; i < nb_p; i += G) {
-        int ida, idb;
-        float h;
-        if (i < 4) {
-          ida = S.pnb[i];
-          idb = -1;
-          h = hf[i];
-        } else {
-          const int nbid = S.pnb[i];
-          ida = min(seed_id, nbid);
-          idb = max(seed_id, nbid);
-          h = 1.f;
+    __syncwarp();
+    // ================= D: write the record (copy(), convex_cell.cu:933-949) =======================
+    if (state == GS_FINISH) {
+      long long blob_at = -1;
+      int words = 0;
+      if (status == ST_success) {
+        words = compact_words(nb_v, nb_p, nb_e);
+        unsigned long long at = 0;
+        if (lane == 0) {
+          if ((unsigned)words > chunk_left) {  // one global atomic per ~13 cells instead of per cell
+            const unsigned grab = max(CLIP_CHUNK_WORDS, (unsigned)words);
+            chunk_at = atomicAdd(&A.counters[CNT_BLOB], (unsigned long long)grab);
+            chunk_left = grab;
+          }
+          at = chunk_at;
+          chunk_at += words;
+          chunk_left -= words;
         }
-        o[3 * i + 0] = (uint32_t)ida;
-        o[3 * i + 1] = (uint32_t)idb;
-        o[3 * i + 2] = __float_as_uint(h);
+        at = __shfl_sync(gmask, at, src);
+        if (at + (unsigned long long)words <= A.scratch_words) {
+          blob_at = (long long)at;
+          uint32_t* o = A.scratch + at;
+          if (lane == 0) {
+            o[0] = (uint32_t)t;
+            o[1] = (uint32_t)seed_id;
+            o[2] = (uint32_t)nb_v | ((uint32_t)nb_p << 8) | ((uint32_t)nb_e << 16) | ((uint32_t)status << 24);
+            o[3] = __float_as_uint(seed.w);
+          }
+          o += 4;
+          const uint32_t* sv = reinterpret_cast<const uint32_t*>(S.ver);
+          for (int i = lane; i < nb_v; i += G) o[i] = sv[i];
+          o += nb_v;
+          // planes are written word-wise: the record is only 4-byte aligned
+          for (int i = lane; i < 4 * nb_p; i += G) o[i] = reinterpret_cast<const uint32_t*>(S.plane)[i];
+          o += 4 * nb_p;
+          for (int i = lane; i < nb_p; i += G) {
+            int ida, idb;
+            float h;
+            if (i < 4) {
+              ida = S.pnb[i];
+              idb = -1;
+              h = (float)((hf4 >> (8 * i)) & 0xffu);
+            } else {
+              const int nbid = S.pnb[i];
+              ida = min(seed_id, nbid);
+              idb = max(seed_id, nbid);
+              h = 1.f;
+            }
+            o[3 * i + 0] = (uint32_t)ida;
+            o[3 * i + 1] = (uint32_t)idb;
+            o[3 * i + 2] = __float_as_uint(h);
+          }
+          o += 3 * nb_p;
+          const int ew = (3 * nb_e + 3) / 4;
+          const uint32_t* se = reinterpret_cast<const uint32_t*>(S.edge);
+          for (int i = lane; i < ew; i += G) o[i] = se[i];
+        }
       }
-      o += 3 * nb_p;
-      const int ew = (3 * nb_e + 3) / 4;
-      const uint32_t* se = reinterpret_cast<const uint32_t*>(S.edge);
-      for (int i = lane; i < ew; i += G) o[i] = se[i];
+      if (lane == 0) {
+        A.pair_status[pair] = (signed char)status;
+        A.pair_blob[pair] = blob_at;
+        A.pair_words[pair] = (blob_at >= 0) ? words : 0;
+        if (status == ST_success && blob_at >= 0)
+          n_valid++;
+        if (status != ST_success) atomicAdd(&blk_cnt[CNT_HIST + status + 1], 1ull);
+      }
+      state = GS_IDLE;
+      __syncwarp(gmask);
     }
   }
+  // ---- statistics: per-lane registers -> block -> global -------------------------------------
+  atomicAdd(&blk_cnt[CNT_CULLED], (unsigned long long)n_culled);
+  atomicAdd(&blk_cnt[CNT_EXACT], (unsigned long long)n_exact);
   if (lane == 0) {
-    A.pair_status[pair] = (signed char)status;
-    A.pair_blob[pair] = blob_at;
-    A.pair_words[pair] = (blob_at >= 0) ? words : 0;
-    atomicAdd(&blk_cnt[CNT_HIST + status + 1], 1ull);
-    if (status == ST_success && blob_at >= 0) atomicAdd(&blk_cnt[CNT_VALID], 1ull);
-  }
-  // per-lane statistics
-  for (int o = G / 2; o > 0; o >>= 1) {
-    n_culled += __shfl_down_sync(gmask, n_culled, o, G);
-  }
-  if (lane == 0) {
-    atomicAdd(&blk_cnt[CNT_CLIPS], n_clips);
-    atomicAdd(&blk_cnt[CNT_CULLED], n_culled);
-  }
-  __syncwarp(gmask);
-}
-
-template <int G>
-__global__ void __launch_bounds__(128) k_clip(ClipArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CellS* cells = reinterpret_cast<CellS*>(smem_raw);
-  constexpr int GROUPS_PER_BLOCK = 128 / G;
-  const int g_in_block = threadIdx.x / G;
-  const int lane = threadIdx.x % G;
-  const int wl = threadIdx.x & 31;
-  const int gshift = (wl / G) * G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gshift);
-  CellS& S = cells[g_in_block];
-  __shared__ unsigned long long blk_cnt[16];  // block-aggregated counters (RpdCounters layout)
-  if (threadIdx.x < 16) blk_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  unsigned long long chunk_at = 0;
-  unsigned chunk_left = 0;
-  const long long n_groups = (long long)gridDim.x * GROUPS_PER_BLOCK;
-  for (long long pair = (long long)blockIdx.x * GROUPS_PER_BLOCK + g_in_block; pair < A.n_pairs;
-       pair += n_groups) {
-    clip_cell<G>(A, pair, S, lane, gmask, gshift, chunk_at, chunk_left, blk_cnt);
+    atomicAdd(&blk_cnt[CNT_CLIPS], (unsigned long long)n_clips);
+    atomicAdd(&blk_cnt[CNT_VALID], (unsigned long long)n_valid);
+    atomicAdd(&blk_cnt[CNT_HIST + ST_success + 1], (unsigned long long)n_valid);
   }
   __syncthreads();
   if (threadIdx.x >= 1 && threadIdx.x < 16 && blk_cnt[threadIdx.x])

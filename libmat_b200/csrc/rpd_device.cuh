@@ -15,6 +15,7 @@
 #define MBK_MAX_T 96
 #define MBK_MAX_E 152
 #define MBK_END 255
+#define MBK_CV 32  // vertices with an FP32 cofactor-filter cache entry (the rest take the FP64 path)
 
 enum : int {
   ST_early_return = -1,
@@ -120,8 +121,8 @@ __device__ __forceinline__ bool conflict_exact(float4 p1, float4 p2, float4 p3, 
 // ---- per-cell shared-memory state ---------------------------------------------------------------
 struct __align__(16) CellS {
   float4 plane[MBK_MAX_P];          // plane equations (a,b,c,d)
-  float4 c0[4];                     // filter: cofactor vectors of the 4 initial vertices
-  float a0[4];                      // filter: |c.x|+|c.y|+|c.z| of the above
+  float4 c0[4];                     // cull filter: cofactor vectors of the 4 initial (tet) vertices
+  float4 cof[MBK_CV];               // conflict filter: cofactor vector of live vertex v (v < MBK_CV)
   int pnb[MBK_MAX_P];               // p<4: tet-face id; p>=4: neighbour site id of the bisector
   uchar4 ver[MBK_MAX_T];            // dual triangles (3 plane ids, #adjacent cells)
   unsigned char edge[MBK_MAX_E * 3];  // (plane a, plane b, #adjacent cells)

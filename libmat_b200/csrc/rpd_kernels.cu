@@ -342,12 +342,16 @@ static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, int t_first, i
 
 static void grid_candidates(mb_ctx* ctx, int t_first, int t_count, int grid_k) {
   GridDev G = grid_build(ctx);
+  // grid_k = expected candidates per tet: capacity of the fast pass's shared-memory survivor list
+  // (32 / 96 / 256; longer lists go through the big-list pass) and row stride of the output
   const int kcap = (grid_k > 96) ? 256 : 96;
   ctx->cand_kcap = kcap;
   ctx->cand_pad.reserve((size_t)t_count * kcap);
   ctx->cand_cnt.reserve((size_t)t_count + 1);
   ctx->ovf_list.reserve((size_t)t_count + 1);
-  if (kcap == 96)
+  if (grid_k > 0 && grid_k <= 32)
+    launch_grid_candidates<32>(ctx, G, t_first, t_count, kcap);
+  else if (kcap == 96)
     launch_grid_candidates<96>(ctx, G, t_first, t_count, kcap);
   else
     launch_grid_candidates<256>(ctx, G, t_first, t_count, kcap);
@@ -387,9 +391,9 @@ static void launch_clip(mb_ctx* ctx, const ClipArgs& A) {
   int per_sm = 0;
   MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip<G>, 128, smem));
   if (per_sm < 1) per_sm = 1;
-  // persistent-style grid: a multiple of the SM count, grid-stride over pairs
+  // persistent grid: every SM fully resident, warps pull chunks of pairs from a global cursor
   long long want = (A.n_pairs + groups - 1) / groups;
-  long long grid = std::min<long long>(want, (long long)ctx->sm_count * per_sm * 4);
+  long long grid = std::min<long long>(want, (long long)ctx->sm_count * per_sm);
   if (grid < 1) grid = 1;
   ctx->n_launches++;
   k_clip<G><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
@@ -406,7 +410,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   const int t_count = M.range_count < 0 ? M.n_tet - t_first : M.range_count;
   MB_REQUIRE(t_first >= 0 && t_count >= 0 && t_first + t_count <= M.n_tet, MB_ERR_ARG, "bad tet range");
   int G = opts && opts->lanes_per_cell ? opts->lanes_per_cell : 8;
-  MB_REQUIRE(G == 8 || G == 16 || G == 32, MB_ERR_ARG, "lanes_per_cell must be 8, 16 or 32");
+  MB_REQUIRE(G == 4 || G == 8 || G == 16 || G == 32, MB_ERR_ARG, "lanes_per_cell must be 4, 8, 16 or 32");
   res->ctx = ctx;
   res->n_site = S.n_site;
   res->want_volumes = opts && opts->want_volumes;
@@ -493,7 +497,9 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     A.scratch = ctx->scratch.p;
     A.scratch_words = ctx->scratch.cap;
     A.counters = reinterpret_cast<unsigned long long*>(ctx->counters.p);
-    if (G == 8)
+    if (G == 4)
+      launch_clip<4>(ctx, A);
+    else if (G == 8)
       launch_clip<8>(ctx, A);
     else if (G == 16)
       launch_clip<16>(ctx, A);
@@ -506,7 +512,12 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     // scratch too small: rerun K3 with the measured need (rare; statuses are recomputed)
     scratch_words = (size_t)hc.blob_words + (1u << 20);
     MB_REQUIRE(attempt == 0, MB_ERR_NOMEM, "compact scratch overflow after resize");
-    MB_CUDA(cudaMemsetAsync(ctx->counters.p, 0, sizeof(RpdCounters), s));
+    {  // reset K3's counters only (the candidate-stage counters [4] and [16] stay)
+      unsigned long long* c = reinterpret_cast<unsigned long long*>(ctx->counters.p);
+      MB_CUDA(cudaMemsetAsync(c, 0, 4 * sizeof(unsigned long long), s));
+      MB_CUDA(cudaMemsetAsync(c + 5, 0, 11 * sizeof(unsigned long long), s));
+      MB_CUDA(cudaMemsetAsync(c + CNT_WORK_CURSOR, 0, sizeof(unsigned long long), s));
+    }
     MB_CUDA(cudaEventRecord(res->ev[1], s));
   }
   if (n_pairs == 0) {
@@ -516,6 +527,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   res->n_cells = (long)hc.n_valid;
   res->n_clips = (long)hc.n_clips;
   res->n_culled = (long)hc.n_culled;
+  res->n_exact = (long)hc.pad[0];
   res->n_cand_overflow = (long)hc.n_cand_overflow;
   res->n_ovf_tets = (long)hc.n_ovf_tets;
   for (int i = 0; i < 10; i++) res->hist[i] = (long)hc.hist[i];

@@ -32,6 +32,7 @@ class RpdResult:
         st = (C.c_long * 8)()
         ctx._check(lib.mb_rpd_stats(handle, st))
         self.n_culled, self.n_cand_overflow, self.n_big_pass_tets = st[3], st[4], st[6]
+        self.n_exact = st[7]
         hist = (C.c_long * 10)()
         ctx._check(lib.mb_rpd_status_histogram(handle, hist))
         self.status_histogram = np.array(list(hist), dtype=np.int64)  # index = status + 1

@@ -69,7 +69,10 @@ int main(int argc, char** argv) {
         id2[2 * (_MAX_P_ * (size_t)i + p)] = c.clip_id2_data_trans[p].x;
         id2[2 * (_MAX_P_ * (size_t)i + p) + 1] = c.clip_id2_data_trans[p].y;
       }
-      for (int e = 0; e < c.nb_e; e++) memcpy(&edge[3 * (_MAX_E_ * (size_t)i + e)], &c.edge_data[e], 3);
+      for (int e = 0; e < c.nb_e; e++) {
+        unsigned char* q = &edge[3 * (_MAX_E_ * (size_t)i + e)];
+        q[0] = c.edge_data[e].x; q[1] = c.edge_data[e].y; q[2] = c.edge_data[e].z;
+      }
       c.reload_active();                      // the reference's own post-processing on our cells
       euler[(size_t)i] = (float)c.cal_cell_euler();
     }
