@@ -72,11 +72,7 @@ def make_workload(workload: str, n_gpus: int):
     return mesh, sites, n, ns
 
 
-def shard(n_tet: int, rank: int, world: int):
-    """contiguous tet blocks: rank r owns [first, first+count)"""
-    base, rem = divmod(n_tet, world)
-    first = rank * base + min(rank, rem)
-    return first, base + (1 if rank < rem else 0)
+from libmat_b200.dist import as_u8_tensor, gather_varlen, shard  # noqa: E402
 
 
 def algorithmic_bytes(mesh_n_tet, mesh_n_vert, n_site, n_pairs, n_listed, recs_bytes):
@@ -282,39 +278,19 @@ def main():
     upload_sites()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    # ---- NCCL gather of the compact results on rank 0 (grouped send/recv) ------------------------
-    class DevView:
-        def __init__(self, ptr, nbytes):
-            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-
-    gather_buf = {}
+    # ---- NCCL gather of the compact results on rank 0 (libmat_b200.dist: all-gather of the sizes, then a
+    # grouped send/recv over NVLink) -------------------------------------------------------------
+    gather_buf = {"t": None}
 
     def gather(res):
         if world == 1:
             return 0
         d_blob, n_bytes, d_off, n_cells = res.device_buffers()
-        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-        mine = torch.tensor([n_bytes], dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(sizes, mine)
-        sz = sizes.tolist()
-        src = torch.as_tensor(DevView(d_blob, max(n_bytes, 1)), device=dev)[:n_bytes]
-        ops = []
-        if rank == 0:
-            total = sum(sz)
-            if gather_buf.get("cap", 0) < total:
-                gather_buf["t"] = torch.empty(int(total * 1.1) + 16, dtype=torch.uint8, device=dev)
-                gather_buf["cap"] = gather_buf["t"].numel()
-            out = gather_buf["t"]
-            out[:sz[0]].copy_(src, non_blocking=True)
-            off = sz[0]
-            for r in range(1, world):
-                ops.append(dist.P2POp(dist.irecv, out[off:off + sz[r]], r))
-                off += sz[r]
-        else:
-            ops.append(dist.P2POp(dist.isend, src, 0))
-        if ops:
-            for w_ in dist.batch_isend_irecv(ops):
-                w_.wait()
+        src = as_u8_tensor(d_blob, n_bytes, dev)
+        if rank == 0 and gather_buf["t"] is None:
+            gather_buf["t"] = torch.empty(int(n_bytes * world * 1.25) + 1024, dtype=torch.uint8, device=dev)
+        out, sz = gather_varlen(src, dst=0, out=gather_buf["t"])
+        gather_buf["last"] = out
         return sum(sz) if rank == 0 else 0
 
     def step():
@@ -368,8 +344,17 @@ def main():
         for i in range(e2e_steps):
             set_mesh()
             upload_sites()
-            res, _ = step()
-            if world == 1 or rank == 0:
+            res, gathered = step()
+            if world > 1:
+                # the gathered result of all ranks leaves rank 0's GPU
+                if rank == 0:
+                    if blob_host is None or blob_host[0].numel() < gathered:
+                        blob_host = (torch.empty(int(gathered * 1.05) + 16, dtype=torch.uint8).pin_memory(),)
+                    blob_host[0][:gathered].copy_(gather_buf["last"], non_blocking=False)
+                d2h = gathered
+                res.free()
+                continue
+            if True:
                 if blob_host is None or blob_host[0].size * 4 < res.compact_bytes:
                     tb = torch.empty(int(res.compact_bytes * 1.05) // 4 + 16, dtype=torch.int32).pin_memory()
                     to = torch.empty(res.n_cells + 16, dtype=torch.int64).pin_memory()
