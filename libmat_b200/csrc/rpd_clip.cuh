@@ -34,6 +34,7 @@ struct ClipArgs {
   const int4* tet_fadj;
   const int4* tet_fid;
   const uint2* tet_e6;
+  const float4* tet_geo;  // per tet: 4 face planes, 4 initial-vertex cofactor vectors (k_tet_geometry)
   // sites
   const float4* site4;
   int n_site;
@@ -130,6 +131,8 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
   int nb = -1;                                // per lane: the neighbour of this lane's slot
   float4 eqn = make_float4(0, 0, 0, 0);       // per lane: its bisector
   int nb_v = 0, nb_p = 0, nb_e = 0, status = ST_success;
+  int gc_next_e = 96, gc_next_p = 56;         // per-tet mode: garbage-collect dead planes / edges beyond these
+  unsigned n_gc = 0;
 
   for (;;) {
     __syncwarp();
@@ -164,7 +167,6 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       t = A.pair_tet[pair];
       seed_id = A.pair_site[pair];
       const int4 vi = A.tet_idx[t];
-      const float4 q0 = A.vert4[vi.x], q1 = A.vert4[vi.y], q2 = A.vert4[vi.z], q3 = A.vert4[vi.w];
       const int4 fadj = A.tet_fadj[t];
       const int4 fid = A.tet_fid[t];
       const uint2 e6u = A.tet_e6[t];
@@ -172,21 +174,22 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       seed = A.site4[seed_id];
       hf4 = (unsigned)(unsigned char)fadj.x | ((unsigned)(unsigned char)fadj.y << 8) |
             ((unsigned)(unsigned char)fadj.z << 16) | ((unsigned)(unsigned char)fadj.w << 24);
+      bool ok0 = true;
       if (lane < 4) {
-        // face i is opposite local vertex i: {2,1,3},{0,2,3},{1,0,3},{0,1,2} (convex_cell.h:30-31)
-        const float3 p0 = make_float3(q0.x, q0.y, q0.z), p1 = make_float3(q1.x, q1.y, q1.z),
-                     p2 = make_float3(q2.x, q2.y, q2.z), p3 = make_float3(q3.x, q3.y, q3.z);
-        const float3 a = lane == 0 ? p2 : (lane == 2 ? p1 : p0);
-        const float3 b = lane == 0 ? p1 : (lane == 1 ? p2 : (lane == 2 ? p0 : p1));
-        const float3 c = lane == 3 ? p2 : p3;
-        S.plane[lane] = tri2plane_exact(a, b, c);
+        // face planes and initial-vertex cofactors were computed once per tet (k_tet_geometry)
+        S.plane[lane] = A.tet_geo[(size_t)t * 8 + lane];
+        const float4 c = A.tet_geo[(size_t)t * 8 + 4 + lane];
+        S.c0[lane] = c;   // tet-level cull filter
+        S.cof[lane] = c;  // first four entries of the per-vertex filter cache
         S.pnb[lane] = lane == 0 ? fid.x : (lane == 1 ? fid.y : (lane == 2 ? fid.z : fid.w));
         // dual triangles (1,3,2) (0,2,3) (0,3,1) (0,1,2) with w = (uchar)v_adjs (:186-189)
-        const float4 qq = lane == 0 ? q0 : (lane == 1 ? q1 : (lane == 2 ? q2 : q3));
-        const unsigned char w = (unsigned char)__float_as_int(qq.w);
+        const int vid = lane == 0 ? vi.x : (lane == 1 ? vi.y : (lane == 2 ? vi.z : vi.w));
+        const unsigned char w = (unsigned char)__float_as_int(A.vert4[vid].w);
         S.ver[lane] = lane == 0 ? make_uchar4(1, 3, 2, w)
                                 : (lane == 1 ? make_uchar4(0, 2, 3, w)
                                              : (lane == 2 ? make_uchar4(0, 3, 1, w) : make_uchar4(0, 1, 2, w)));
+        // a proper vertex has c.w < 0 (conflict <=> det > 0 <=> vertex on the negative side)
+        ok0 = (c.w < 0.f) && isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w);
       }
       if (lane >= G - 6 || G < 8) {
         // edges (2,3)(1,3)(1,2)(0,3)(0,2)(0,1) with the e_adj of vertex pairs (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
@@ -197,18 +200,6 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
           S.edge[3 * q + 1] = eb;
           S.edge[3 * q + 2] = (unsigned char)((e6 >> (8 * q)) & 0xff);
         }
-      }
-      __syncwarp(gmask);
-      // cofactor vectors of the 4 initial vertices: the tet-level cull filter (c0) and the first
-      // four entries of the per-vertex filter cache
-      bool ok0 = true;
-      if (lane < 4) {
-        const uchar4 v = S.ver[lane];
-        const float4 c = cofactors_f32(minors_exact(S.plane[v.x], S.plane[v.y], S.plane[v.z]));
-        S.c0[lane] = c;
-        S.cof[lane] = c;
-        // a proper vertex has c.w < 0 (conflict <=> det > 0 <=> vertex on the negative side)
-        ok0 = (c.w < 0.f) && isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w);
       }
       cull_ok = group_ballot<G>(gmask, gshift, !ok0) == 0;
       cvalid = 0xfu;
@@ -227,6 +218,8 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       todo = 0;
       valid = 0;
       list_done = false;
+      gc_next_e = 96;
+      gc_next_p = 56;
       state = GS_RUN;
       __syncwarp(gmask);
     }
@@ -284,6 +277,84 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
           state = GS_FINISH;
         }
       }
+    }
+    // ================= B2: garbage collection (per-tet candidate lists only) =====================
+    // The reference's caps (64 planes, 152 edges) count DEAD entries.  With the reference's short
+    // per-site lists that is harmless; a per-tet candidate list can be several times longer, so
+    // before a clip that could hit a cap the dead planes (referenced by no vertex) and inactive
+    // edges (fewer than 2 live vertices on both planes, the reload_active criterion of
+    // voronoi_defs.cxx:92-103) are dropped and the survivors renumbered.  Tet faces keep indices
+    // 0..3; the canonical form (active planes / edges, vertices) is unchanged.  Rare path.
+    if (per_tet && state == GS_RUN && todo != 0 && (nb_e >= gc_next_e || nb_p >= gc_next_p)) {
+      unsigned long long am = 0xFull;
+      for (int v = lane; v < nb_v; v += G) {
+        const uchar4 tv = S.ver[v];
+        am |= (1ull << tv.x) | (1ull << tv.y) | (1ull << tv.z);
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) am |= __shfl_xor_sync(gmask, am, o);
+      int ne_new = 0;
+      for (int eb = 0; eb < nb_e; eb += G) {
+        const int ei = eb + lane;
+        bool keep = false;
+        unsigned char a = 0, b = 0, z = 0;
+        if (ei < nb_e) {
+          a = S.edge[3 * ei];
+          b = S.edge[3 * ei + 1];
+          z = S.edge[3 * ei + 2];
+          if (((am >> a) & 1ull) && ((am >> b) & 1ull)) {
+            int shared = 0;
+            for (int v = 0; v < nb_v; v++) {
+              const uchar4 tv = S.ver[v];
+              const bool ha = tv.x == a || tv.y == a || tv.z == a, hb = tv.x == b || tv.y == b || tv.z == b;
+              shared += (ha && hb);
+            }
+            keep = shared >= 2;
+          }
+        }
+        const unsigned m = group_ballot<G>(gmask, gshift, keep);
+        __syncwarp(gmask);  // every lane has read its entry; writes below go to indices <= eb
+        if (keep) {
+          const int pos = ne_new + __popc(m & ((1u << lane) - 1u));
+          S.edge[3 * pos] = (unsigned char)__popcll(am & ((1ull << a) - 1ull));
+          S.edge[3 * pos + 1] = (unsigned char)__popcll(am & ((1ull << b) - 1ull));
+          S.edge[3 * pos + 2] = z;
+        }
+        ne_new += __popc(m);
+        __syncwarp(gmask);
+      }
+      for (int v = lane; v < nb_v; v += G) {
+        uchar4 tv = S.ver[v];
+        tv.x = (unsigned char)__popcll(am & ((1ull << tv.x) - 1ull));
+        tv.y = (unsigned char)__popcll(am & ((1ull << tv.y) - 1ull));
+        tv.z = (unsigned char)__popcll(am & ((1ull << tv.z) - 1ull));
+        S.ver[v] = tv;
+      }
+      int np_new = 0;
+      for (int pb = 0; pb < nb_p; pb += G) {
+        const int pi = pb + lane;
+        const bool keep = pi < nb_p && ((am >> pi) & 1ull);
+        float4 pl = make_float4(0, 0, 0, 0);
+        int nbp = 0;
+        if (keep) {
+          pl = S.plane[pi];
+          nbp = S.pnb[pi];
+        }
+        const unsigned m = group_ballot<G>(gmask, gshift, keep);
+        __syncwarp(gmask);
+        if (keep) {
+          const int pos = np_new + __popc(m & ((1u << lane) - 1u));
+          S.plane[pos] = pl;
+          S.pnb[pos] = nbp;
+        }
+        np_new += __popc(m);
+        __syncwarp(gmask);
+      }
+      nb_p = np_new;
+      nb_e = ne_new;
+      gc_next_e = max(96, nb_e + 24);
+      gc_next_p = max(56, nb_p + 4);
+      if (lane == 0) n_gc++;
     }
     // ================= C: clip by the next surviving plane (clip_by_plane, :680-774) ============
     // Every sub-phase below sits at the top level of the loop with warp-uniform trip counts and a
@@ -360,6 +431,24 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       S.pnb[cur_p] = nbk;
       // swap partition, convex_cell.cu:706-721 (the filter cache follows the kept vertices)
       int nv = nb_v, i = 0;
+      if (nb_v <= 32) {
+        // common case: all flags in one 32-bit word
+        unsigned f = (unsigned)f0;
+        while (i < nv) {
+          if ((f >> i) & 1u) {
+            nv--;
+            const unsigned fn = (f >> nv) & 1u;
+            const uchar4 tmp = S.ver[i];
+            S.ver[i] = S.ver[nv];
+            S.ver[nv] = tmp;
+            const unsigned vn = (cv >> nv) & 1u;
+            if (vn) S.cof[i] = S.cof[nv];
+            cv = (cv & ~(1u << i)) | (vn << i);
+            f = (f & ~(1u << i)) | (fn << i);
+          } else
+            i++;
+        }
+      } else
       while (i < nv) {
         const bool fi = i < 64 ? ((f0 >> i) & 1ull) : ((f1 >> (i - 64)) & 1u);
         if (fi) {
@@ -381,7 +470,16 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
           i++;
       }
       // cavity boundary, compute_boundary convex_cell.cu:618-678
-      for (int p = 0; p <= cur_p; p++) S.bnext[p] = MBK_END;
+      {
+        uint4* bn = reinterpret_cast<uint4*>(S.bnext);
+        const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        bn[0] = ff;
+        if (cur_p >= 16) bn[1] = ff;
+        if (cur_p >= 32) {
+          bn[2] = ff;
+          bn[3] = ff;
+        }
+      }
       int first = MBK_END;
       int r = nb_r, tt = nv, fails = 0;
       while (r > 0) {
@@ -587,6 +685,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
   if (lane == 0) {
     atomicAdd(&blk_cnt[CNT_CLIPS], (unsigned long long)n_clips);
     atomicAdd(&blk_cnt[CNT_VALID], (unsigned long long)n_valid);
+    if (n_gc) atomicAdd(&A.counters[18], (unsigned long long)n_gc);
     atomicAdd(&blk_cnt[CNT_HIST + ST_success + 1], (unsigned long long)n_valid);
   }
   __syncthreads();

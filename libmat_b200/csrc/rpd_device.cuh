@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstddef>
+
 #define MBK_MAX_P 64
 #define MBK_MAX_T 96
 #define MBK_MAX_E 152
@@ -125,10 +127,11 @@ struct __align__(16) CellS {
   float4 cof[MBK_CV];               // conflict filter: cofactor vector of live vertex v (v < MBK_CV)
   int pnb[MBK_MAX_P];               // p<4: tet-face id; p>=4: neighbour site id of the bisector
   uchar4 ver[MBK_MAX_T];            // dual triangles (3 plane ids, #adjacent cells)
-  unsigned char edge[MBK_MAX_E * 3];  // (plane a, plane b, #adjacent cells)
-  unsigned char bnext[MBK_MAX_P];   // cavity boundary circular list
+  unsigned char bnext[MBK_MAX_P];   // cavity boundary circular list (16-byte aligned: cleared with uint4 stores)
   unsigned char cyc[MBK_MAX_P];     // the boundary cycle in walk order
+  unsigned char edge[MBK_MAX_E * 3];  // (plane a, plane b, #adjacent cells)
 };
+static_assert(offsetof(CellS, bnext) % 16 == 0, "bnext must be 16-byte aligned");
 
 // compact record size in 4-byte words: header 4 + ver nb_v + planes 4*nb_p + (id2,h) 3*nb_p +
 // edges ceil(3*nb_e/4)

@@ -26,6 +26,7 @@ struct GridDev {
   const float* wmax1;       // R1^3  max weight per coarse node (4^3 fine cells)
   int R, R1;
   float minx, miny, minz, h, inv_h;
+  float wmax_all;           // max weight over all sites
 };
 
 __global__ void k_grid_count(const float4* __restrict__ site4, int n_site, GridDev G,
@@ -141,12 +142,17 @@ __device__ __forceinline__ int warp_argmin(float v, int q) {
   return q;
 }
 
-// One warp per tet.
-//   PHASE A  walks the grid pyramid for U(T) = min_s max_i pd_s(p_i) and, on the way, remembers the
-//            best site seen for each of the 4 vertices and for U: the KERNEL SET K (<= 5 sites).
-//   PHASE B  walks it again, streams every site with L_s <= U through the domination test against
-//            K and keeps the survivors (a few tens at most) in shared memory.
+// One warp per tet, ONE walk over the grid:
+//   seed     the 27 fine cells around the centroid give a first U(T) = min_s max_i pd_s(p_i) and the
+//            KERNEL SET K: the best site seen for each of the 4 vertices and for U (<= 5 sites).
+//   walk     every site with L_s <= U (U keeps shrinking while better sites are met) that is not
+//            dominated by a member of K goes to a shared-memory survivor list (a few tens at most).
+//            Cells are enumerated directly over the box of radius rho = R_t + sqrt(U + w_max) when
+//            that box is small (bounded radii: the common case), through the max-weight pyramid
+//            otherwise (heavy-tailed radii).
 //   then     all-pairs domination on the survivors + ascending-id rank sort.
+// Any weaker streaming filter only lengthens the survivor list: the all-pairs pass decides.  The owner
+// of every tet vertex passes both tests, so the final list does not depend on the walk order.
 // Output: padded list [t_local][kcap_out] of ALL candidates (the neighbour list of every cell of
 // the tet), cand_cnt[t_local], pair_cnt[t_local] = number of flagged candidates (cells to clip).
 // A tet whose survivor list exceeds KCAP goes to ovf_list and is redone by the FROM_LIST
@@ -178,12 +184,14 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
     const float4 g4 = make_float4(gx, gy, gz, 0.f);
     const float Rt2 = fmaxf(fmaxf(pd_plain(g4, p0), pd_plain(g4, p1)), fmaxf(pd_plain(g4, p2), pd_plain(g4, p3)));
     const float Rt = sqrtf(Rt2) * 1.0001f + 1e-3f;
+    const int ci = min(R - 1, max(0, (int)floorf((gx - G.minx) * G.inv_h)));
+    const int cj = min(R - 1, max(0, (int)floorf((gy - G.miny) * G.inv_h)));
+    const int ck = min(R - 1, max(0, (int)floorf((gz - G.minz) * G.inv_h)));
 
-    // ---- phase A -------------------------------------------------------------------------------
+    // ---- seed: U and the kernel set from the 27 cells around the centroid ------------------------
     float bv0 = INFINITY, bv1 = INFINITY, bv2 = INFINITY, bv3 = INFINITY, bvu = INFINITY;
     int bq0 = -1, bq1 = -1, bq2 = -1, bq3 = -1, bqu = -1;
-    float U = INFINITY;
-    auto eval = [&](int q) {
+    auto evalq = [&](int q) {
       const float4 e = pd4(G.site4[q], p0, p1, p2, p3);
       const float m = fmaxf(fmaxf(e.x, e.y), fmaxf(e.z, e.w));
       if (e.x < bv0) { bv0 = e.x; bq0 = q; }
@@ -192,46 +200,41 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
       if (e.w < bv3) { bv3 = e.w; bq3 = q; }
       if (m < bvu) { bvu = m; bqu = q; }
     };
-    {
-      // seed with the fine cell that contains the centroid and its 26 neighbours
-      const int ci = min(R - 1, max(0, (int)floorf((gx - G.minx) * G.inv_h)));
-      const int cj = min(R - 1, max(0, (int)floorf((gy - G.miny) * G.inv_h)));
-      const int ck = min(R - 1, max(0, (int)floorf((gz - G.minz) * G.inv_h)));
-      if (lane < 27) {
-        const int i = ci + lane / 9 - 1, j = cj + (lane / 3) % 3 - 1, k = ck + lane % 3 - 1;
-        if (i >= 0 && j >= 0 && k >= 0 && i < R && j < R && k < R) {
-          const int c = (i * R + j) * R + k;
-          for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) eval(q);
-        }
+    if (lane < 27) {
+      const int i = ci + lane / 9 - 1, j = cj + (lane / 3) % 3 - 1, k = ck + lane % 3 - 1;
+      if (i >= 0 && j >= 0 && k >= 0 && i < R && j < R && k < R) {
+        const int c = (i * R + j) * R + k;
+        for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) evalq(q);
       }
-      U = warp_min(bvu);
     }
-    for (int b1 = 0; b1 < n1; b1 += 32) {
-      const int n = b1 + lane;
-      bool keep = false;
-      if (n < n1) {
-        const int k1 = n % R1, j1 = (n / R1) % R1, i1 = n / (R1 * R1);
-        keep = box_dist2(gx, gy, gz, G, i1, j1, k1, H1) - G.wmax1[n] < U;
-      }
-      unsigned m1 = __ballot_sync(0xffffffffu, keep);
-      while (m1) {
-        const int n_ = b1 + __ffs(m1) - 1;
-        m1 &= m1 - 1;
-        const int k1 = n_ % R1, j1 = (n_ / R1) % R1, i1 = n_ / (R1 * R1);
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-          const int ch = half * 32 + lane;
-          const int i = 4 * i1 + (ch >> 4), j = 4 * j1 + ((ch >> 2) & 3), k = 4 * k1 + (ch & 3);
-          if (i < R && j < R && k < R) {
-            const int c = (i * R + j) * R + k;
-            if (box_dist2(gx, gy, gz, G, i, j, k, G.h) - G.wmax0[c] < U)
-              for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) eval(q);
+    float U = warp_min(bvu);
+    if (!isfinite(U)) {
+      // no site near the centroid (sparse or far-away sites): find U with a pyramid walk first
+      for (int b1 = 0; b1 < n1; b1 += 32) {
+        const int n = b1 + lane;
+        bool keep = false;
+        if (n < n1) {
+          const int k1 = n % R1, j1 = (n / R1) % R1, i1 = n / (R1 * R1);
+          keep = box_dist2(gx, gy, gz, G, i1, j1, k1, H1) - G.wmax1[n] < U;
+        }
+        unsigned m1 = __ballot_sync(0xffffffffu, keep);
+        while (m1) {
+          const int n_ = b1 + __ffs(m1) - 1;
+          m1 &= m1 - 1;
+          const int k1 = n_ % R1, j1 = (n_ / R1) % R1, i1 = n_ / (R1 * R1);
+          for (int half = 0; half < 2; half++) {
+            const int ch = half * 32 + lane;
+            const int i = 4 * i1 + (ch >> 4), j = 4 * j1 + ((ch >> 2) & 3), k = 4 * k1 + (ch & 3);
+            if (i < R && j < R && k < R) {
+              const int c = (i * R + j) * R + k;
+              if (box_dist2(gx, gy, gz, G, i, j, k, G.h) - G.wmax0[c] < U)
+                for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) evalq(q);
+            }
           }
+          U = warp_min(bvu);
         }
-        U = warp_min(bvu);
       }
     }
-    // kernel set: best site per vertex + the U site (slots in the cell-sorted table; -1 if none)
     int kq[5];
     kq[0] = warp_argmin(bv0, bq0);
     kq[1] = warp_argmin(bv1, bq1);
@@ -251,65 +254,93 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
         kW[k] = 0.f;
       }
     }
-    // U is a binary32 value: make it a certain over-estimate (error <= ~2.4e-7 (|U| + 2 w))
-    const float Ue = U + 4e-6f * (fabsf(U) + 2.f * kW[4]) + 1e-3f;
+    // U is a binary32 value: Ue is a certain over-estimate (|err| <= ~2.4e-7 (|U| + 2 w) of any site)
+    const float wall = fmaxf(G.wmax_all, 0.f);
+    float Ue = U + 4e-6f * (fabsf(U) + 2.f * wall) + 1e-3f;
 
-    // ---- phase B: stream {s : L_s <= Ue} through the kernel-set domination test --------------------
     int cnt = 0;
-    for (int b1 = 0; b1 < n1; b1 += 32) {
-      const int n = b1 + lane;
-      bool keep = false;
-      if (n < n1) {
-        const int k1 = n % R1, j1 = (n / R1) % R1, i1 = n / (R1 * R1);
-        const float d = fmaxf(0.f, sqrtf(box_dist2(gx, gy, gz, G, i1, j1, k1, H1)) * 0.9999f - Rt);
-        keep = d * d - G.wmax1[n] <= Ue;
-      }
-      unsigned m1 = __ballot_sync(0xffffffffu, keep);
-      while (m1) {
-        const int n_ = b1 + __ffs(m1) - 1;
-        m1 &= m1 - 1;
-        const int k1 = n_ % R1, j1 = (n_ / R1) % R1, i1 = n_ / (R1 * R1);
-        for (int half = 0; half < 2; half++) {
-          const int ch = half * 32 + lane;
-          const int i = 4 * i1 + (ch >> 4), j = 4 * j1 + ((ch >> 2) & 3), k = 4 * k1 + (ch & 3);
-          int qb = 0, qe = 0;
-          if (i < R && j < R && k < R) {
-            const int c = (i * R + j) * R + k;
-            const float d = fmaxf(0.f, sqrtf(box_dist2(gx, gy, gz, G, i, j, k, G.h)) * 0.9999f - Rt);
-            if (d * d - G.wmax0[c] <= Ue) {
-              qb = G.cell_off[c];
-              qe = G.cell_off[c + 1];
-            }
-          }
-          // lane <-> fine cell; each lane walks its cell's sites, appends are warp-aggregated
-          while (__any_sync(0xffffffffu, qb < qe)) {
-            bool ok = false;
-            float4 e = make_float4(0, 0, 0, 0);
-            float w = 0.f;
-            if (qb < qe) {
-              const float4 s = G.site4[qb];
-              const float dg2 = pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4);
-              const float d = fmaxf(0.f, sqrtf(dg2) * 0.9999f - Rt);
-              if (d * d - s.w - 4e-6f * (dg2 + s.w) <= Ue) {
-                e = pd4(s, p0, p1, p2, p3);
-                w = s.w;
-                ok = true;
+    // lane <-> fine cell [qb, qe): walk the cell's sites; appends are warp-aggregated
+    auto walk = [&](int qb, int qe) {
+      while (__any_sync(0xffffffffu, qb < qe)) {
+        bool ok = false;
+        float4 e = make_float4(0, 0, 0, 0);
+        float w = 0.f;
+        if (qb < qe) {
+          const float4 s = G.site4[qb];
+          const float dg2 = pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4);
+          const float d = fmaxf(0.f, sqrtf(dg2) * 0.9999f - Rt);
+          if (d * d - s.w - 4e-6f * (dg2 + s.w) <= Ue) {
+            e = pd4(s, p0, p1, p2, p3);
+            w = s.w;
+            bvu = fminf(bvu, fmaxf(fmaxf(e.x, e.y), fmaxf(e.z, e.w)));
+            ok = true;
 #pragma unroll
-                for (int kk = 0; kk < 5; kk++) ok = ok && !dominates(kE[kk], kW[kk], e, w);
-              }
-            }
-            const unsigned mk = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-              const int pos = cnt + __popc(mk & ((1u << lane) - 1u));
-              if (pos < KCAP) {
-                s_id[pos] = G.sorted_id[qb];
-                s_pd[pos] = e;
-                s_w[pos] = w;
-              }
-            }
-            cnt += __popc(mk);
-            qb++;
+            for (int kk = 0; kk < 5; kk++) ok = ok && !dominates(kE[kk], kW[kk], e, w);
           }
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const int pos = cnt + __popc(mk & ((1u << lane) - 1u));
+          if (pos < KCAP) {
+            s_id[pos] = G.sorted_id[qb];
+            s_pd[pos] = e;
+            s_w[pos] = w;
+          }
+        }
+        cnt += __popc(mk);
+        qb++;
+      }
+    };
+    auto cell_range = [&](int i, int j, int k, int& qb, int& qe) {
+      qb = qe = 0;
+      if (i >= 0 && j >= 0 && k >= 0 && i < R && j < R && k < R) {
+        const int c = (i * R + j) * R + k;
+        const float d = fmaxf(0.f, sqrtf(box_dist2(gx, gy, gz, G, i, j, k, G.h)) * 0.9999f - Rt);
+        if (d * d - G.wmax0[c] <= Ue) {
+          qb = G.cell_off[c];
+          qe = G.cell_off[c + 1];
+        }
+      }
+    };
+
+    // no candidate lies farther than rho from the centroid (w_s <= w_max); rho in cells:
+    const float rho = Rt + sqrtf(fmaxf(0.f, Ue + wall)) * 1.0001f;
+    const int a = (int)ceilf(rho * G.inv_h * 1.0001f);
+    const int side = 2 * a + 1;
+    if (isfinite(U) && side <= 8) {
+      // ---- direct walk over the (2a+1)^3 box of fine cells -----------------------------------------
+      const int nbox = side * side * side;
+      for (int b = 0; b < nbox; b += 32) {
+        const int n = b + lane;
+        int qb = 0, qe = 0;
+        if (n < nbox) cell_range(ci - a + n / (side * side), cj - a + (n / side) % side, ck - a + n % side, qb, qe);
+        walk(qb, qe);
+        U = fminf(U, warp_min(bvu));
+        Ue = U + 4e-6f * (fabsf(U) + 2.f * wall) + 1e-3f;
+      }
+    } else {
+      // ---- walk through the max-weight pyramid -----------------------------------------------------
+      for (int b1 = 0; b1 < n1; b1 += 32) {
+        const int n = b1 + lane;
+        bool keep = false;
+        if (n < n1) {
+          const int k1 = n % R1, j1 = (n / R1) % R1, i1 = n / (R1 * R1);
+          const float d = fmaxf(0.f, sqrtf(box_dist2(gx, gy, gz, G, i1, j1, k1, H1)) * 0.9999f - Rt);
+          keep = d * d - G.wmax1[n] <= Ue;
+        }
+        unsigned m1 = __ballot_sync(0xffffffffu, keep);
+        while (m1) {
+          const int n_ = b1 + __ffs(m1) - 1;
+          m1 &= m1 - 1;
+          const int k1 = n_ % R1, j1 = (n_ / R1) % R1, i1 = n_ / (R1 * R1);
+          for (int half = 0; half < 2; half++) {
+            const int ch = half * 32 + lane;
+            int qb, qe;
+            cell_range(4 * i1 + (ch >> 4), 4 * j1 + ((ch >> 2) & 3), 4 * k1 + (ch & 3), qb, qe);
+            walk(qb, qe);
+          }
+          U = fminf(U, warp_min(bvu));
+          Ue = U + 4e-6f * (fabsf(U) + 2.f * wall) + 1e-3f;
         }
       }
     }
@@ -324,26 +355,26 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
         }
         continue;
       }
-      cnt = KCAP;  // 2048 survivors of the kernel-set filter: give up on the rest (counted below)
+      cnt = KCAP;  // 2048 survivors of the streaming filter: give up on the rest (counted below)
       if (lane == 0) atomicAdd(&counters[4], 1ull);
     }
     __syncwarp();
     // ---- all-pairs domination on the survivors ---------------------------------------------------
     int n_keep = 0;
     for (int b = 0; b < cnt; b += 32) {
-      const int a = b + lane;
+      const int a2 = b + lane;
       bool keep = false;
-      if (a < cnt) {
+      if (a2 < cnt) {
         keep = true;
-        const float4 e = s_pd[a];
-        const float wa = s_w[a];
+        const float4 e = s_pd[a2];
+        const float wa = s_w[a2];
         for (int m = 0; m < cnt && keep; m++)
-          if (m != a && dominates(s_pd[m], s_w[m], e, wa)) keep = false;
+          if (m != a2 && dominates(s_pd[m], s_w[m], e, wa)) keep = false;
       }
       __syncwarp();
       // removed entries get id = INT_MAX so that the rank sort pushes them to the tail; their
       // s_pd stays (a dominated site may still dominate others: domination is transitive)
-      if (a < cnt && !keep) s_id[a] = 0x7fffffff;
+      if (a2 < cnt && !keep) s_id[a2] = 0x7fffffff;
       n_keep += __popc(__ballot_sync(0xffffffffu, keep));
     }
     __syncwarp();
@@ -352,10 +383,10 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
     }
     int n_flag = 0;
     for (int b = 0; b < cnt; b += 32) {
-      const int a = b + lane;
+      const int a2 = b + lane;
       bool fl = false;
-      if (a < cnt) {
-        const int id = s_id[a];
+      if (a2 < cnt) {
+        const int id = s_id[a2];
         if (id != 0x7fffffff) {
           int rank = 0;
           for (int m = 0; m < cnt; m++) rank += (s_id[m] < id);

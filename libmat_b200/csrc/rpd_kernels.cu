@@ -18,6 +18,32 @@ static inline long long edge_idx_closed(long long v1, long long v2, long long n)
   return (vmin + 1) * n - vmin * (vmin + 1) / 2 - (n - vmax);
 }
 
+// Per-tet geometry that every cell of the tet starts from (ConvexCell ctor, convex_cell.cu:116-214):
+// the 4 un-normalised face planes tri2plane(face i) in tet_faces_lvid order (convex_cell.h:30-31) and,
+// for the 4 initial vertices (1,3,2) (0,2,3) (0,3,1) (0,1,2), the FP32 cofactor vector of the FP64
+// minors of their three planes (the filter data of the clip kernel).  Computed once per mesh upload
+// instead of once per (tet, site) cell.  One thread per (tet, face).
+__global__ void k_tet_geometry(const float4* __restrict__ vert4, const int4* __restrict__ tet_idx, int n_tet,
+                               float4* __restrict__ tet_geo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = i >> 2, f = i & 3;
+  if (t >= n_tet) return;
+  const int4 vi = tet_idx[t];
+  const float4 q0 = vert4[vi.x], q1 = vert4[vi.y], q2 = vert4[vi.z], q3 = vert4[vi.w];
+  const float3 p0 = make_float3(q0.x, q0.y, q0.z), p1 = make_float3(q1.x, q1.y, q1.z),
+               p2 = make_float3(q2.x, q2.y, q2.z), p3 = make_float3(q3.x, q3.y, q3.z);
+  // faces {2,1,3},{0,2,3},{1,0,3},{0,1,2}
+  const float4 pl0 = tri2plane_exact(p2, p1, p3), pl1 = tri2plane_exact(p0, p2, p3),
+               pl2 = tri2plane_exact(p1, p0, p3), pl3 = tri2plane_exact(p0, p1, p2);
+  const float4 mine = f == 0 ? pl0 : (f == 1 ? pl1 : (f == 2 ? pl2 : pl3));
+  // vertex f = dual triangle (1,3,2) (0,2,3) (0,3,1) (0,1,2)
+  const Minors m = f == 0 ? minors_exact(pl1, pl3, pl2)
+                          : (f == 1 ? minors_exact(pl0, pl2, pl3)
+                                    : (f == 2 ? minors_exact(pl0, pl3, pl1) : minors_exact(pl0, pl1, pl2)));
+  tet_geo[(size_t)t * 8 + f] = mine;
+  tet_geo[(size_t)t * 8 + 4 + f] = make_float4((float)m.m234, (float)(-m.m134), (float)m.m124, (float)(-m.m123));
+}
+
 void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int* idx_aos,
                      int n_tet, const int* v_adjs, const int* e_adjs_dense, const int* e_adj6,
                      const int* f_adjs, const int* f_ids) {
@@ -61,6 +87,10 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
   MB_CUDA(cudaMemcpyAsync(M.tet_idx.p, idx_aos, sizeof(int4) * (size_t)n_tet, cudaMemcpyHostToDevice, s));
   MB_CUDA(cudaMemcpyAsync(M.tet_fadj.p, f_adjs, sizeof(int4) * (size_t)n_tet, cudaMemcpyHostToDevice, s));
   MB_CUDA(cudaMemcpyAsync(M.tet_fid.p, f_ids, sizeof(int4) * (size_t)n_tet, cudaMemcpyHostToDevice, s));
+  M.tet_geo.reserve((size_t)n_tet * 8);
+  ctx->n_launches++;
+  k_tet_geometry<<<(unsigned)(((size_t)n_tet * 4 + 255) / 256), 256, 0, s>>>(M.vert4.p, M.tet_idx.p, n_tet, M.tet_geo.p);
+  MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaStreamSynchronize(s));
   M.n_vert = n_vert;
   M.n_tet = n_tet;
@@ -274,6 +304,7 @@ static GridDev grid_build(mb_ctx* ctx) {
   G.minx = bb[0];
   G.miny = bb[1];
   G.minz = bb[2];
+  G.wmax_all = S.w_max;
   const int nc = R * R * R, n1 = G.R1 * G.R1 * G.R1;
   ctx->grid_cnt.reserve((size_t)nc + 1);
   ctx->grid_off.reserve((size_t)nc + 1);
@@ -476,6 +507,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     A.tet_fadj = M.tet_fadj.p;
     A.tet_fid = M.tet_fid.p;
     A.tet_e6 = M.tet_e6.p;
+    A.tet_geo = M.tet_geo.p;
     A.site4 = S.site4.p;
     A.n_site = S.n_site;
     if (S.given) {

@@ -1,0 +1,64 @@
+"""grid-kNN mode edge cases: sites far from part of the mesh (no site near a tet's centroid), one site,
+heavy-tailed radii (pyramid walk), and the kcap statistics."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiles(O, mesh, recs):
+    cv = O.cell_volumes(recs)
+    pv = np.zeros(mesh.n_tet)
+    np.add.at(pv, recs["tet_id"], cv)
+    tv = mesh.tet_volumes()
+    return abs(pv.sum() - tv.sum()) / tv.sum(), np.mean(np.abs(pv - tv) / tv)
+
+
+def test_clustered_sites_far_from_most_tets(ctx, O, synth):
+    """all sites in one corner: most tets have no site within their 27 seed cells"""
+    mesh = synth.make_ball_mesh(6)
+    s = synth.make_spheres(200)
+    c = s.centers() * 0.15 + 200.0  # shrink the cloud into a corner of the ball
+    r = s.radii * 0.15
+    sites = synth.Sites(np.ascontiguousarray(c.T.astype(np.float32)).ravel(), (r * r).astype(np.float32),
+                        np.ones(200, np.uint32), r.astype(np.float32))
+    ctx.set_mesh(mesh)
+    res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
+    assert res.n_cand_overflow == 0
+    n_capped = int(res.status_histogram[[1, 2, 8]].sum())  # cells lost to the 64/96/152 caps near the cluster
+    tot, mean = _tiles(O, mesh, res.records())
+    assert tot < 1e-6 + 1e-4 * n_capped and mean < 1e-3
+    # same cells as the reference semantics with RT lists
+    knn, k, valid = synth.rt_site_lists(sites)
+    sites.flags[:] = valid.astype(np.uint32)
+    pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
+    ra, _, _ = O.run_pairs(mesh, sites, knn, k, pt, ps)
+    want = ra[ra["status"] == 4]
+    got = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0).records()
+    ka = set(zip(want["tet_id"].tolist(), want["voro_id"].tolist()))
+    kb = set(zip(got["tet_id"].tolist(), got["voro_id"].tolist()))
+    assert len(kb - ka) <= 2 and len(ka - kb) <= 2 + n_capped
+
+
+def test_single_site_owns_everything(ctx, O, synth):
+    mesh = synth.make_ball_mesh(3)
+    sites = synth.make_spheres(1)
+    ctx.set_mesh(mesh)
+    res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
+    recs = res.records()
+    assert res.n_cells == mesh.n_tet and (recs["nb_v"] == 4).all() and (recs["nb_p"] == 4).all()
+
+
+def test_heavy_tailed_radii_use_the_pyramid(ctx, O, synth):
+    """a few huge spheres: the box of radius rho is the whole domain, candidates come from the
+    max-weight pyramid walk; the result must still tile the mesh"""
+    mesh = synth.make_ball_mesh(6)
+    sites = synth.make_spheres(400)
+    w = sites.weights.copy()
+    w[::50] = (220.0 ** 2)
+    big = synth.Sites(sites.site_soa, w, sites.flags, np.sqrt(w))
+    ctx.set_mesh(mesh)
+    res = ctx.compute_clipped_voro_diagram(big.site_soa, big.weights, big.flags, None, 0, grid_k=256)
+    assert res.n_cand_overflow == 0
+    tot, mean = _tiles(O, mesh, res.records())
+    assert tot < 1e-6 and mean < 1e-4

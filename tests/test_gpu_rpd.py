@@ -221,6 +221,10 @@ def grid_vs_given(ctx, O, mesh, sites, knn, k, **kw):
     res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0, **kw)
     assert res.n_cand_overflow == 0
     got = res.records()
+    # cells that ran into the 64-plane / 96-vertex / 152-edge caps (dead entries count) are dropped with
+    # the reference's status; with per-tet candidate lists that can happen where the reference's
+    # shorter per-site lists do not overflow
+    n_capped = int(res.status_histogram[[1, 2, 8]].sum())
     ka = want["tet_id"].astype(np.int64) * ns + want["voro_id"]
     kb = got["tet_id"].astype(np.int64) * ns + got["voro_id"]
     common = np.intersect1d(ka, kb)
@@ -228,8 +232,8 @@ def grid_vs_given(ctx, O, mesh, sites, knn, k, **kw):
     # cells whose volume is at rounding level may appear on one side only (flagged class)
     va = O.cell_volumes(want[np.isin(ka, only_a)])
     vb = O.cell_volumes(got[np.isin(kb, only_b)])
-    assert (va < 1e-2).all() and (vb < 1e-2).all(), (va, vb)
-    assert len(only_a) + len(only_b) <= 1e-4 * len(ka) + 2
+    assert (vb < 1e-2).all() and int((va >= 1e-2).sum()) <= n_capped, (va, vb, n_capped)
+    assert len(only_a) + len(only_b) <= 1e-4 * len(ka) + 2 + n_capped
     d = canon_equal(O, want[np.isin(ka, common)], got[np.isin(kb, common)])
     n_bad = max(v for f, v in d.items() if f != "cells_compared")
     assert n_bad <= 1e-4 * len(common), d  # degenerate (|det| at rounding level) cells only
@@ -269,8 +273,6 @@ def test_grid_mode_overflow_pass(ctx, O, synth):
         log.append((ns, res.n_cand_overflow, res.n_big_pass_tets, res.n_cells, str(res.status_histogram.tolist())))
         if res.n_cand_overflow:
             continue  # more than 96 true candidates per tet: that is the documented truncation
-        if res.status_histogram[[1, 2, 8]].sum():
-            continue  # cells that ran into the reference's 64-plane / 96-vertex / 152-edge caps
         grid_vs_given(ctx, O, mesh, sites, knn, k, grid_k=32)
         used_big_pass |= res.n_big_pass_tets > 0
     assert used_big_pass, log
