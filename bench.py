@@ -151,6 +151,61 @@ def cpu_reference_run(mesh, sites, knn, k, pt, ps, repeats=2):
     return kind, cells, best
 
 
+def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
+    """config 3 shape: 20 000 spheres, 60 000 slabs, 30 000 cones, replicated per-sample int3 lists
+    (fix_geo_error.cxx:300-366).  Returns the dist2mat sub-object of the bench line."""
+    import torch
+
+    from libmat_b200 import synth
+
+    d = synth.make_dist2mat(n_samples)
+    n_prims = int(d.prims.shape[0])
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    tp = [pin(x) for x in (d.spheres, d.samples, d.offset, d.count, d.prims)]
+    hp = [t.numpy() for t in tp]
+    ctx.dist2mat_upload(*hp)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(warmup):
+        ctx.dist2mat_run()
+    ms = []
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ms.append(ctx.dist2mat_run())  # CUDA events on the library's stream around the kernel
+    k_ms = float(np.mean(ms))
+    b_alg = n_samples * (12 + 8 + 8) + n_prims * 12 + len(d.spheres) * 16
+    peak, peak_src = hbm_peak()
+    # e2e: the reference-facing call with host buffers (7 H2D + kernel + 2 D2H, like dist2mat.cu:287-307)
+    res_h = torch.empty(n_samples, dtype=torch.float32).pin_memory()
+    cid_h = torch.empty(n_samples, dtype=torch.int32).pin_memory()
+    e_steps = max(3, min(steps, 5))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        ctx._check(ctx.lib.mb_dist2mat(ctx._ctx, hp[0].ctypes.data, len(d.spheres), hp[1].ctypes.data, n_samples,
+                                       hp[2].ctypes.data, hp[3].ctypes.data, hp[4].ctypes.data, n_prims,
+                                       res_h.numpy().ctypes.data, cid_h.numpy().ctypes.data, None))
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / e_steps
+    out = {"metric": "dist2mat_queries_per_sec", "value": n_samples / (k_ms * 1e-3), "unit": "queries/s",
+           "ms_per_step": k_ms,
+           "config": {"workload": f"config 3 shape: {n_samples} samples, {len(d.spheres)} spheres, {d.n_slabs} slabs, "
+                                  f"{d.n_cones} cones, {n_prims / n_samples:.1f} prims/sample (replicated int3 lists)"},
+           "roofline": {"kernel": "k_dist2mat", "bound": "hbm", "achieved": b_alg / (k_ms * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": b_alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg},
+           "e2e": {"value": n_samples / t_e2e, "unit": "queries/s",
+                   "h2d_bytes_per_step": int(sum(x.nbytes for x in hp)), "d2h_bytes_per_step": int(8 * n_samples)}}
+    if with_cpu:
+        from oracle import oracle as O
+        n_cpu = min(n_samples, 400000)
+        kind = "reference" if O.ref("d2m") is not None else "port"
+        _, _, sec = O.dist2mat(d, "ref" if kind == "reference" else "oracle", n=n_cpu)
+        out["cpu_baseline"] = {"value": n_cpu / sec, "unit": "queries/s", "cores": os.cpu_count(), "kind": kind,
+                               "sample": f"first {n_cpu} samples, reference distance functions + tie rule on all host threads, {sec:.2f} s"}
+    return out
+
+
 def run_reference_arm(args):
     """--impl reference: CPU only, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -210,8 +265,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="grid", choices=["grid", "given"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "d2m"])
+    ap.add_argument("--samples", type=int, default=0, help="dist2mat samples (config 3 is 10 000 000)")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -238,6 +295,24 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
+
+    if args.workload == "d2m":
+        # dist2mat stand-alone: samples sharded across ranks, medial mesh replicated, no collective
+        ctx = Context(local_rank)
+        n_s = (args.samples or 2000000)
+        sub = bench_dist2mat(ctx, n_s, args.steps, args.warmup, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        vals = torch.tensor([sub["ms_per_step"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            sub.update({"value": n_s * world / (vals.item() * 1e-3), "n_gpus": world, "steps": args.steps,
+                        "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                        "dtype": "f32", "data": "synthetic", "gpu_launches": args.steps})
+            print(json.dumps(sub))
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     mesh, sites, n, ns = make_workload(args.workload, n_gpus)
     mode = args.mode if world == 1 else "grid"
@@ -298,7 +373,7 @@ def main():
         return sum(sz) if rank == 0 else 0
 
     def step():
-        res = ctx.run(lanes_per_cell=args.lanes)
+        res = ctx.run(lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates)
         gathered = gather(res)
         return res, gathered
 
@@ -401,7 +476,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
             "data": "synthetic",
             "config": {"workload": workload_name(args, n, ns, mesh),
-                       "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})",
+                       "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})" + (", grid candidates" if args.grid_candidates else ", reference relation predicate"),
                        "parallelism": f"tet-shards x{world}, sites replicated" + (", NCCL gather to rank 0" if world > 1 else ""),
                        "l2": "flushed (512 MB write) between timed steps",
                        "cells_per_step": total_cells, "candidate_pairs_per_step": total_pairs,
@@ -431,6 +506,12 @@ def main():
                 "sample": f"all {len(pt)} candidate pairs of the workload (given-neighbours, RT lists site_k={k}), {cpu_cells} cells, "
                           f"best of 2, {sec:.2f} s; clipping loop + record copy timed, candidate generation excluded",
                 "cells_match_gpu_given_mode": bool(cpu_cells == gpu_cells)}
+            # second metric of BASELINE.json: dist2mat queries/s (config 3 shape at 1M samples by default;
+            # `--workload d2m --samples 10000000` runs the full config)
+            try:
+                line["dist2mat"] = bench_dist2mat(ctx, args.samples or 1000000, max(3, args.steps // 2), 3)
+            except Exception as exc:  # never lose the headline line
+                line["dist2mat"] = {"error": str(exc)}
         print(json.dumps(line))
     ctx.close()
     if world > 1:

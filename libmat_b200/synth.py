@@ -352,25 +352,34 @@ def make_dist2mat(n_samples: int, nu: int = 100, nv: int = 200, seed: int = RAN_
 
     _, nn = cKDTree(sp[:, :3]).query(samples.astype(np.float64), k=2)
     nn = nn.astype(np.int64)
-    # per-sample list = unique prims incident to either sphere (ascending prim id), then the 2 spheres
-    cnt_a = start[nn[:, 0] + 1] - start[nn[:, 0]]
-    cnt_b = start[nn[:, 1] + 1] - start[nn[:, 1]]
-    rep_a = np.repeat(np.arange(n_samples), cnt_a)
+    # per-sample list = unique prims incident to either sphere (ascending prim id), then the 2 spheres.
+    # The prim part depends on the unordered sphere pair only: build it once per distinct pair, then
+    # replicate it per sample (the reference replicates too, fix_geo_error.cxx:300-366).
+    lo = np.minimum(nn[:, 0], nn[:, 1])
+    hi = np.maximum(nn[:, 0], nn[:, 1])
+    upair, pinv = np.unique(lo * ns + hi, return_inverse=True)
+    ua, ub = upair // ns, upair % ns
+    n_up = upair.size
+    cnt_a = start[ua + 1] - start[ua]
+    cnt_b = start[ub + 1] - start[ub]
+    rep_a = np.repeat(np.arange(n_up), cnt_a)
     pos_a = np.arange(rep_a.size) - np.repeat(np.cumsum(cnt_a) - cnt_a, cnt_a)
-    rep_b = np.repeat(np.arange(n_samples), cnt_b)
+    rep_b = np.repeat(np.arange(n_up), cnt_b)
     pos_b = np.arange(rep_b.size) - np.repeat(np.cumsum(cnt_b) - cnt_b, cnt_b)
-    key = np.concatenate([rep_a * n_prim + inc_p[start[nn[rep_a, 0]] + pos_a],
-                          rep_b * n_prim + inc_p[start[nn[rep_b, 1]] + pos_b]])
-    key = np.unique(key)
-    smp = key // n_prim
-    pid = key % n_prim
-    cnt_u = np.bincount(smp, minlength=n_samples)
+    key = np.unique(np.concatenate([rep_a * n_prim + inc_p[start[ua[rep_a]] + pos_a],
+                                    rep_b * n_prim + inc_p[start[ub[rep_b]] + pos_b]]))
+    pl_pair = key // n_prim            # sorted by (pair, prim id)
+    pl_prim = key % n_prim
+    pl_cnt = np.bincount(pl_pair, minlength=n_up)
+    pl_start = np.concatenate([[0], np.cumsum(pl_cnt)[:-1]])
+    cnt_u = pl_cnt[pinv]
     count = (cnt_u + 2).astype(np.int64)
     offset = np.concatenate([[0], np.cumsum(count)[:-1]]).astype(np.int64)
     total = int(count.sum())
     prims = np.empty((total, 3), dtype=np.int32)
-    pos_u = np.arange(key.size) - np.repeat(np.cumsum(cnt_u) - cnt_u, cnt_u)
-    prims[offset[smp] + pos_u] = prim_all[pid]
+    smp = np.repeat(np.arange(n_samples), cnt_u)
+    pos_u = np.arange(smp.size) - np.repeat(np.cumsum(cnt_u) - cnt_u, cnt_u)
+    prims[offset[smp] + pos_u] = prim_all[pl_prim[pl_start[pinv[smp]] + pos_u]]
     tail = offset + cnt_u
     prims[tail] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 0]], axis=1)
     prims[tail + 1] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 1]], axis=1)

@@ -292,3 +292,19 @@ def test_grid_mode_tiles_every_tet(ctx, O, cfg1_rt):
     assert np.mean(rel) < 1e-4 and np.max(rel) < 0.1  # float planes of sliver tets dominate the max
     assert abs(pv.sum() - tv.sum()) / tv.sum() < 1e-6
     assert res.status_histogram[[1, 2, 3, 8, 9]].sum() == 0  # no overflow / inconsistent cells
+
+
+def test_given_lists_with_grid_candidates(ctx, O, cfg1_rt):
+    """opts.grid_candidates: pairs from the uniform-grid search, clipping by the given (RT) lists in list
+    order -> the valid cells are byte-identical to the reference semantics; only empty pairs differ."""
+    mesh, sites, knn, k = cfg1_rt
+    ctx.set_mesh(mesh)
+    ref = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, knn, k)
+    fast = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, knn, k, grid_candidates=True)
+    a, b = ref.records(), fast.records()
+    assert fast.n_pairs <= ref.n_pairs and fast.n_cells == ref.n_cells
+    for f in a.dtype.names:
+        assert np.ascontiguousarray(a[f]).tobytes() == np.ascontiguousarray(b[f]).tobytes(), f
+    pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
+    ra, _, _ = O.run_pairs(mesh, sites, knn, k, pt, ps)
+    assert_defined_equal(O, ra[ra["status"] == 4], b)
