@@ -265,7 +265,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="grid", choices=["grid", "given"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "d2m"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5", "d2m"])
     ap.add_argument("--samples", type=int, default=0, help="dist2mat samples (config 3 is 10 000 000)")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
@@ -312,6 +312,42 @@ def main():
         ctx.close()
         if world > 1:
             dist.destroy_process_group()
+        return
+
+    if args.workload == "cfg5":
+        # MATTopo-style loop (BASELINE.json configs[4]): 20 successive recomputes with sphere insertion /
+        # update on the resident config-2 mesh; per-iteration end-to-end latency (H2D sites + RPD + D2H)
+        from libmat_b200.loop import RpdLoop, evolve_sites
+        mesh, sites, n, ns = make_workload("cfg2", 1)
+        ctx = Context(local_rank)
+        loop = RpdLoop(ctx, mesh)
+        res, _ = loop.step(sites)
+        tb = torch.empty(int(res.compact_bytes * 1.3) // 4 + 1024, dtype=torch.int32).pin_memory()
+        to = torch.empty(int(res.n_cells * 1.3) + 1024, dtype=torch.int64).pin_memory()
+        fetch = (tb.numpy().view(np.uint32), to.numpy())
+        for _ in range(args.warmup):
+            loop.step(sites, fetch=fetch)
+        lat, dev_ms, cells = [], [], []
+        iters = 20
+        for it in range(iters):
+            sites, changed = evolve_sites(sites, it)  # host-side edit (the caller's fix_topo / fix_geo step), untimed
+            res, dt = loop.step(sites, fetch=fetch)
+            lat.append(dt * 1e3)
+            dev_ms.append(res.kernel_ms["total"])
+            cells.append(res.n_cells)
+        line = {"metric": "rpd_loop_iteration_latency_ms", "value": float(np.median(lat)), "unit": "ms", "n_gpus": 1,
+                "steps": iters, "warmup": args.warmup, "ms_per_step": float(np.mean(lat)), "higher_is_better": False,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": f"cfg5: 20 iterations on the resident config-2 mesh ({mesh.n_tet} tets), "
+                                       f"{ns} -> {sites.n_site} spheres (0.5 % inserted + 0.5 % updated per iteration), "
+                                       "full exact recompute in grid-kNN mode every iteration",
+                           "latency_ms": {"min": float(np.min(lat)), "median": float(np.median(lat)), "max": float(np.max(lat))},
+                           "device_ms_median": float(np.median(dev_ms)), "cells_last": int(cells[-1])},
+                "e2e": {"value": float(np.median(lat)), "unit": "ms", "h2d_bytes_per_step": int(16 * sites.n_site + 4 * sites.n_site),
+                        "d2h_bytes_per_step": int(res.compact_bytes + 8 * (res.n_cells + 1))},
+                "gpu_launches": int(ctx.launch_count())}
+        print(json.dumps(line))
+        ctx.close()
         return
 
     mesh, sites, n, ns = make_workload(args.workload, n_gpus)

@@ -100,6 +100,10 @@ int mb_set_tetmesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int* i
                    const int* f_adjs, const int* f_ids);
 /* restrict subsequent mb_rpd3d calls to tets [first, first+count) (multi-GPU tet shards). */
 int mb_set_tet_range(mb_ctx* ctx, int first, int count);
+/* restrict subsequent mb_rpd3d calls to the listed tets (strictly ascending ids of the resident mesh),
+ * the device-side counterpart of load_partial_tet_given_spheres (rpd_api.cxx:482-535): a partial
+ * recompute without re-uploading a sub-mesh; cells keep the GLOBAL tet id.  n = 0 clears the subset. */
+int mb_set_tet_subset(mb_ctx* ctx, const int* tet_ids, int n);
 
 /* ---------------------------------------------------------------- RPD */
 typedef struct {
@@ -165,6 +169,8 @@ int mb_rpd_compact_bytes(const mb_rpd_result* res, long* n_bytes);
 int mb_rpd_fetch_compact(mb_rpd_result* res, void* blob, long* cell_offsets);
 /* per-site volume and barycentre sums (float[n_site], float[3*n_site] SoA); needs want_volumes */
 int mb_rpd_site_volumes(mb_rpd_result* res, float* vol, float* bary_sum_soa);
+/* per-cell volume (the value the reference accumulates per site, convex_cell.cu:1008-1069); float[n_cells] */
+int mb_rpd_cell_volumes(mb_rpd_result* res, float* cell_vol);
 /* raw device pointers of the compact result (for NCCL gathers): blob, cell_offsets(long) */
 int mb_rpd_device_buffers(mb_rpd_result* res, void** d_blob, long* n_bytes, void** d_offsets,
                           long* n_cells);

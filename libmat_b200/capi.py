@@ -12,10 +12,10 @@ LIB_PATH = os.path.join(HERE, "libmat_b200.so")
 
 # every symbol include/libmat_b200.h declares
 SYMBOLS = [
-    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range",
+    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_subset",
     "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
-    "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
+    "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_cell_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
     "mb_rpd_fetch_emit", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
 ]
 
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     vp = C.c_void_p
     lib.mb_set_tetmesh.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]
     lib.mb_set_tet_range.argtypes = [vp, C.c_int, C.c_int]
+    lib.mb_set_tet_subset.argtypes = [vp, vp, C.c_int]
     lib.mb_rpd3d.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(vp)]
     lib.mb_rpd_upload_sites.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int]
     lib.mb_rpd_run.argtypes = [vp, vp, C.POINTER(vp)]
@@ -89,6 +90,7 @@ def load() -> C.CDLL:
     lib.mb_rpd_compact_bytes.argtypes = [vp, C.POINTER(C.c_long)]
     lib.mb_rpd_fetch_compact.argtypes = [vp, vp, vp]
     lib.mb_rpd_site_volumes.argtypes = [vp, vp, vp]
+    lib.mb_rpd_cell_volumes.argtypes = [vp, vp]
     lib.mb_rpd_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_long), C.POINTER(vp), C.POINTER(C.c_long)]
     lib.mb_rpd_emit.argtypes = [vp, C.c_int, C.POINTER(EmitCounts)]
     lib.mb_rpd_fetch_emit.argtypes = [vp] + [vp] * 12

@@ -75,13 +75,13 @@ void mb_destroy(mb_ctx* ctx) {
   ctx->spare_blob.release();
   ctx->spare_cell_off.release();
   TetMeshDev& M = ctx->mesh;
-  M.vert4.release(); M.tet_idx.release(); M.tet_fadj.release(); M.tet_fid.release(); M.tet_e6.release(); M.tet_geo.release();
+  M.vert4.release(); M.tet_idx.release(); M.tet_fadj.release(); M.tet_fid.release(); M.tet_e6.release(); M.tet_geo.release(); M.tet_sel.release();
   SitesDev& S = ctx->sites;
   S.site4.release(); S.flags.release(); S.nbr.release(); S.knn_staging.release(); S.soa_staging.release();
   D2MDev& D = ctx->d2m;
   D.spheres.release(); D.samples.release(); D.offset.release(); D.count.release(); D.prims.release();
   D.result.release(); D.closest.release(); D.tie.release();
-  ctx->tet_cnt.release(); ctx->tet_off.release(); ctx->pair_tet.release(); ctx->pair_site.release();
+  ctx->tet_cnt.release(); ctx->tet_off.release(); ctx->pair_tet.release(); ctx->pair_site.release(); ctx->pair_local.release();
   ctx->cand_pad.release(); ctx->cand_cnt.release(); ctx->ovf_list.release(); ctx->word_off.release(); ctx->pair_valid.release();
   ctx->pair_cell.release(); ctx->pair_status.release(); ctx->pair_blob.release(); ctx->pair_words.release();
   ctx->scratch.release(); ctx->counters.release(); ctx->cub_tmp.release();
@@ -122,6 +122,24 @@ int mb_set_tet_range(mb_ctx* ctx, int first, int count) {
   MB_REQUIRE(first >= 0 && (count < 0 || first + count <= ctx->mesh.n_tet), MB_ERR_ARG, "bad tet range");
   ctx->mesh.range_first = first;
   ctx->mesh.range_count = count;
+  MB_CATCH
+}
+
+int mb_set_tet_subset(mb_ctx* ctx, const int* tet_ids, int n) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_REQUIRE(n >= 0 && (n == 0 || tet_ids), MB_ERR_ARG, "bad subset");
+  TetMeshDev& M = ctx->mesh;
+  for (int i = 0; i < n; i++)
+    MB_REQUIRE(tet_ids[i] >= 0 && tet_ids[i] < M.n_tet && (i == 0 || tet_ids[i] > tet_ids[i - 1]), MB_ERR_ARG,
+               "tet subset must be strictly ascending ids of the resident mesh");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  if (n > 0) {
+    M.tet_sel.reserve((size_t)n);
+    MB_CUDA(cudaMemcpyAsync(M.tet_sel.p, tet_ids, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  M.n_sel = n;
   MB_CATCH
 }
 
@@ -192,7 +210,7 @@ void mb_rpd_free(mb_rpd_result* res) {
       res->cell_off.move_to(ctx->spare_cell_off);
     }
   }
-  res->blob.release(); res->cell_off.release(); res->site_vol.release(); res->site_bary.release();
+  res->blob.release(); res->cell_off.release(); res->site_vol.release(); res->site_bary.release(); res->cell_vol.release();
   res->f_cell.release(); res->f_key.release(); res->v_cell.release(); res->v_lvid.release();
   res->v_key3.release(); res->v_surf.release(); res->e_cell.release(); res->e_key2.release();
   res->e_lvid2.release(); res->f_istet.release(); res->v_pos3.release(); res->c_euler.release();
@@ -345,6 +363,17 @@ int mb_rpd_site_volumes(mb_rpd_result* res, float* vol, float* bary_sum_soa) {
   if (bary_sum_soa)
     MB_CUDA(cudaMemcpyAsync(bary_sum_soa, res->site_bary.p, sizeof(float) * 3 * (size_t)res->n_site, cudaMemcpyDeviceToHost, s));
   MB_CUDA(cudaStreamSynchronize(s));
+  MB_CATCH
+}
+
+int mb_rpd_cell_volumes(mb_rpd_result* res, float* cell_vol) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx && cell_vol, MB_ERR_ARG, "null argument");
+  MB_REQUIRE(res->want_volumes && res->cell_vol.p, MB_ERR_STATE, "run with opts.want_volumes = 1");
+  if (res->n_cells > 0)
+    MB_CUDA(cudaMemcpyAsync(cell_vol, res->cell_vol.p, sizeof(float) * (size_t)res->n_cells, cudaMemcpyDeviceToHost, ctx->stream));
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
   MB_CATCH
 }
 

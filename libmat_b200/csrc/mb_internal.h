@@ -90,6 +90,9 @@ struct TetMeshDev {
   DevBuf<uint2> tet_e6;    // 6 edge adjacency counts as bytes (+2 pad)    8 B / tet
   DevBuf<float4> tet_geo;  // per tet: 4 face planes + 4 vertex cofactor vectors (k_tet_geometry)  128 B / tet
   int range_first = 0, range_count = -1;
+  DevBuf<int> tet_sel;     // optional ascending list of tet ids to process (mb_set_tet_subset)
+  int n_sel = 0;
+  const int* sel_ptr() const { return n_sel > 0 ? tet_sel.p : nullptr; }
 };
 
 struct SitesDev {
@@ -131,7 +134,7 @@ struct mb_rpd_result {
   // device results (owned)
   DevBuf<uint32_t> blob;       // ordered compact records
   DevBuf<long long> cell_off;  // n_cells+1 byte offsets into blob
-  DevBuf<float> site_vol, site_bary;
+  DevBuf<float> site_vol, site_bary, cell_vol;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // emission (K4)
   bool emitted = false;
@@ -165,7 +168,7 @@ struct mb_ctx {
   D2MDev d2m;
   PinBuf pin_in, pin_out;
   // rpd scratch (reused across calls)
-  DevBuf<int> tet_cnt, tet_off, pair_tet, pair_site, cand_pad;
+  DevBuf<int> tet_cnt, tet_off, pair_tet, pair_site, pair_local, cand_pad;
   DevBuf<int> cand_cnt;            // grid mode: #candidates per tet (cand_pad holds the lists)
   DevBuf<int> ovf_list;            // grid mode: tets whose survivor list overflowed the fast pass
   int cand_kcap = 0;               // grid mode: row stride of cand_pad
@@ -198,6 +201,7 @@ void rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
 void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res);
 void rpd_sync(mb_ctx* ctx, mb_rpd_result* res);
 void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
+void rpd_volumes(mb_ctx* ctx, mb_rpd_result* res);  // a12: per-cell / per-site volume + barycentre sums
 
 // ---- dist2mat_kernels.cu -------------------------------------------------------------------
 void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples, int n_samples,

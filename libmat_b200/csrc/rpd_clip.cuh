@@ -46,6 +46,7 @@ struct ClipArgs {
   // pairs
   const int* pair_tet;
   const int* pair_site;
+  const int* pair_local;  // local index of the pair's tet in the processed range / subset (per-tet lists)
   long long n_pairs;
   // outputs
   signed char* pair_status;
@@ -208,8 +209,9 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       nb_e = 6;
       status = ST_success;
       if (per_tet) {
-        list = A.nbr + (size_t)(t - A.tet_first) * A.nbr_stride;
-        list_len = A.nbr_cnt[t - A.tet_first];
+        const int tl = A.pair_local[pair];
+        list = A.nbr + (size_t)tl * A.nbr_stride;
+        list_len = A.nbr_cnt[tl];
       } else {
         list = A.nbr + (size_t)seed_id * A.nbr_stride;
         list_len = A.nbr_stride;

@@ -194,6 +194,85 @@ __global__ void k_emit(const uint32_t* __restrict__ blob, const long long* __res
   }
 }
 
+// ---- a12: per-cell volume and barycentre sums (atomic_add_bary_and_volume, convex_cell.cu:1008-1069,
+// with get_tet_decomposition_of_vertex :986-1006): every vertex contributes 6 tets built from the
+// projections of the seed on the vertex's three planes; the literal float expressions (this TU is
+// compiled with -fmad=false).  Per-cell values are deterministic; the per-site sums are accumulated
+// with float atomics like the reference (:1045-1054), so their last bits depend on the order.
+struct V4 {
+  float x, y, z, w;
+};
+__device__ __forceinline__ V4 v_minus(V4 A, V4 B) { return {A.x - B.x, A.y - B.y, A.z - B.z, A.w - B.w}; }
+__device__ __forceinline__ V4 v_plus(V4 A, V4 B) { return {A.x + B.x, A.y + B.y, A.z + B.z, A.w + B.w}; }
+__device__ __forceinline__ V4 v_mul3(float s, V4 A) { return {s * A.x, s * A.y, s * A.z, 1.f}; }
+__device__ __forceinline__ float v_dot4(V4 A, V4 B) { return A.x * B.x + A.y * B.y + A.z * B.z + A.w * B.w; }
+__device__ __forceinline__ float v_dot3(V4 A, V4 B) { return A.x * B.x + A.y * B.y + A.z * B.z; }
+__device__ __forceinline__ V4 v_cross3(V4 A, V4 B) {
+  return {A.y * B.z - A.z * B.y, A.z * B.x - A.x * B.z, A.x * B.y - A.y * B.x, 0.f};
+}
+// common_cuda.h:235-240
+__device__ __forceinline__ V4 project_on_plane(V4 P, V4 plane) {
+  const V4 n = {plane.x, plane.y, plane.z, 0.f};
+  const float n_2 = v_dot4(n, n);
+  const float lambda = (double)n_2 > 1e-2 ? (v_dot4(n, P) + plane.w) / n_2 : 0.0f;
+  return v_plus(P, v_mul3(-lambda, n));
+}
+
+__global__ void k_cell_volumes(const uint32_t* __restrict__ blob, const long long* __restrict__ cell_off,
+                               long n_cells, const float4* __restrict__ site4, int n_site,
+                               float* __restrict__ cell_vol, float* __restrict__ site_vol,
+                               float* __restrict__ site_bary) {
+  const long cell = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  const CellView c = view(blob + cell_off[cell] / 4);
+  const float4 sd = site4[c.site];
+  const V4 C = {sd.x, sd.y, sd.z, sd.w};
+  const float* PL = reinterpret_cast<const float*>(c.plane);
+  V4 bary_sum = {0.f, 0.f, 0.f, 0.f};
+  float cur = 0.f;
+  for (int t = 0; t < c.nb_v; t++) {
+    const uint32_t v = c.ver[t];
+    const int pi[3] = {(int)(v & 0xff), (int)((v >> 8) & 0xff), (int)((v >> 16) & 0xff)};
+    const float* p1 = PL + 4 * pi[0];
+    const float* p2 = PL + 4 * pi[1];
+    const float* p3 = PL + 4 * pi[2];
+    // compute_vertex_coordinates with perspective divide (convex_cell.cu:319-351)
+    const float rx = -det3_exact(p1[3], p1[1], p1[2], p2[3], p2[1], p2[2], p3[3], p3[1], p3[2]);
+    const float ry = -det3_exact(p1[0], p1[3], p1[2], p2[0], p2[3], p2[2], p3[0], p3[3], p3[2]);
+    const float rz = -det3_exact(p1[0], p1[1], p1[3], p2[0], p2[1], p2[3], p3[0], p3[1], p3[3]);
+    const float rw = det3_exact(p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+    const V4 A = {rx / rw, ry / rw, rz / rw, 1.f};
+    V4 P[6];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float* q = PL + 4 * pi[i];
+      P[2 * i] = project_on_plane(C, V4{q[0], q[1], q[2], q[3]});
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const V4 n = v_cross3(v_minus(P[2 * i], C), v_minus(P[(2 * (i + 1)) % 6], C));
+      const V4 pl = {n.x, n.y, n.z, -v_dot3(C, n)};
+      P[2 * i + 1] = project_on_plane(A, pl);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const V4 a = v_minus(P[i], A), b = v_minus(P[(i + 1) % 6], A), cc = v_minus(C, A);
+      const float tv = (float)((double)(-det3_exact(a.x, a.y, a.z, b.x, b.y, b.z, cc.x, cc.y, cc.z)) / 6.);
+      const V4 q0 = P[i], q1 = P[(i + 1) % 6];
+      const V4 tb = {.25f * (q0.x + q1.x + C.x + A.x), .25f * (q0.y + q1.y + C.y + A.y),
+                     .25f * (q0.z + q1.z + C.z + A.z), 1.0f};
+      bary_sum = v_plus(bary_sum, v_mul3(tv, tb));
+      cur += tv;
+    }
+  }
+  cell_vol[cell] = cur;
+  if ((double)fabsf(cur) < 0.1) return;  // the reference flips the status and adds nothing (:1040)
+  atomicAdd(&site_bary[c.site], bary_sum.x);
+  atomicAdd(&site_bary[c.site + n_site], bary_sum.y);
+  atomicAdd(&site_bary[c.site + 2 * (size_t)n_site], bary_sum.z);
+  atomicAdd(&site_vol[c.site], cur);
+}
+
 void scan_ll(mb_ctx* ctx, const int* in, long long* out, long n) {
   size_t tmp = 0;
   MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, ctx->stream));
@@ -203,6 +282,22 @@ void scan_ll(mb_ctx* ctx, const int* in, long long* out, long n) {
 }
 
 }  // namespace
+
+void rpd_volumes(mb_ctx* ctx, mb_rpd_result* res) {
+  cudaStream_t s = ctx->stream;
+  const long n = res->n_cells;
+  res->site_vol.reserve((size_t)res->n_site + 1);
+  res->site_bary.reserve(3 * (size_t)res->n_site + 1);
+  res->cell_vol.reserve((size_t)n + 1);
+  MB_CUDA(cudaMemsetAsync(res->site_vol.p, 0, sizeof(float) * (size_t)res->n_site, s));
+  MB_CUDA(cudaMemsetAsync(res->site_bary.p, 0, sizeof(float) * 3 * (size_t)res->n_site, s));
+  if (n == 0) return;
+  ctx->n_launches++;
+  k_cell_volumes<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(res->blob.p, res->cell_off.p, n, ctx->sites.site4.p,
+                                                           res->n_site, res->cell_vol.p, res->site_vol.p,
+                                                           res->site_bary.p);
+  MB_CUDA(cudaGetLastError());
+}
 
 void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid) {
   cudaStream_t s = ctx->stream;

@@ -161,7 +161,7 @@ __device__ __forceinline__ int warp_argmin(float v, int q) {
 template <int KCAP, int WARPS, bool FROM_LIST>
 __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
     const float4* __restrict__ vert4, const int4* __restrict__ tet_idx, int tet_first, int tet_count,
-    GridDev G, const unsigned* __restrict__ flags, int kcap_out, int* __restrict__ cand_pad,
+    const int* __restrict__ tet_sel, GridDev G, const unsigned* __restrict__ flags, int kcap_out, int* __restrict__ cand_pad,
     int* __restrict__ cand_cnt, int* __restrict__ pair_cnt, unsigned long long* __restrict__ counters,
     int* __restrict__ ovf_list) {
   extern __shared__ __align__(16) unsigned char grid_smem[];
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
   const int n_work = FROM_LIST ? (int)counters[CNT_OVF_TETS] : tet_count;
   for (int work = blockIdx.x * WARPS + wib; work < n_work; work += gridDim.x * WARPS) {
     const int warp = FROM_LIST ? ovf_list[work] : work;  // local tet index
-    const int t = tet_first + warp;
+    const int t = tet_sel ? tet_sel[warp] : tet_first + warp;  // global tet id
     const int4 vi = tet_idx[t];
     const float4 p0 = vert4[vi.x], p1 = vert4[vi.y], p2 = vert4[vi.z], p3 = vert4[vi.w];
     const float gx = 0.25f * (p0.x + p1.x + p2.x + p3.x), gy = 0.25f * (p0.y + p1.y + p2.y + p3.y),
@@ -407,10 +407,10 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
 }
 
 // pairs (flagged candidates only) in (tet, site) order + compact CSR copy of the neighbour lists
-__global__ void k_grid_fill(int tet_first, int tet_count, int kcap, const int* __restrict__ cand_pad,
+__global__ void k_grid_fill(int tet_first, int tet_count, const int* __restrict__ tet_sel, int kcap, const int* __restrict__ cand_pad,
                             const int* __restrict__ cand_cnt, const int* __restrict__ pair_off,
                             const unsigned* __restrict__ flags, int* __restrict__ pair_tet,
-                            int* __restrict__ pair_site) {
+                            int* __restrict__ pair_site, int* __restrict__ pair_local) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= tet_count) return;
   const int n = cand_cnt[warp];
@@ -426,7 +426,8 @@ __global__ void k_grid_fill(int tet_first, int tet_count, int kcap, const int* _
     const unsigned m = __ballot_sync(0xffffffffu, f);
     if (f) {
       const int pos = o + __popc(m & ((1u << lane) - 1u));
-      pair_tet[pos] = tet_first + warp;
+      pair_tet[pos] = tet_sel ? tet_sel[warp] : tet_first + warp;
+      pair_local[pos] = warp;
       pair_site[pos] = id;
     }
     o += __popc(m);

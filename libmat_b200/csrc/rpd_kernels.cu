@@ -96,6 +96,7 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
   M.n_tet = n_tet;
   M.range_first = 0;
   M.range_count = -1;
+  M.n_sel = 0;
 }
 
 // SoA x|y|z + w -> float4; (site_k+1) x n_site slot-major knn -> row-major [n_site][site_k]
@@ -210,7 +211,7 @@ __device__ __forceinline__ bool relate_exact(const float4* __restrict__ site4,
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_cand_given(const float4* __restrict__ vert4,
                                                     const int4* __restrict__ tet_idx, int tet_first,
-                                                    int tet_count, const float4* __restrict__ site4,
+                                                    int tet_count, const int* __restrict__ tet_sel, const float4* __restrict__ site4,
                                                     const unsigned* __restrict__ flags, int n_site,
                                                     const int* __restrict__ nbr, int site_k,
                                                     int* __restrict__ tet_cnt, int* __restrict__ cand_pad,
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) k_cand_given(const float4* __restrict__ v
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= tet_count) return;
-  const int t = tet_first + warp;
+  const int t = tet_sel ? tet_sel[warp] : tet_first + warp;
   int count = 0;
   if (FILL) {
     // second pass: copy the padded list, or recompute when it overflowed CAND_PAD
@@ -361,12 +362,12 @@ static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, int t_first, i
   const int blocks = std::max(1, std::min(want, ctx->sm_count * 32));
   ctx->n_launches++;
   k_grid_candidates<KCAP, WARPS, false><<<blocks, 32 * WARPS, smem, s>>>(
-      M.vert4.p, M.tet_idx.p, t_first, t_count, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
+      M.vert4.p, M.tet_idx.p, t_first, t_count, ctx->mesh.sel_ptr(), G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
       ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p);
   // overflow pass: reads the number of handed-over tets on the device (usually zero -> returns)
   ctx->n_launches++;
   k_grid_candidates<GRID_BIG_KCAP, 1, true><<<ctx->sm_count * 2, 32, smem_big, s>>>(
-      M.vert4.p, M.tet_idx.p, t_first, t_count, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
+      M.vert4.p, M.tet_idx.p, t_first, t_count, ctx->mesh.sel_ptr(), G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
       ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p);
   MB_CUDA(cudaGetLastError());
 }
@@ -393,8 +394,9 @@ static void grid_fill_pairs(mb_ctx* ctx, int t_first, int t_count, long long n_p
   cudaStream_t s = ctx->stream;
   const int blocks = (t_count + 7) / 8;
   ctx->n_launches++;
-  k_grid_fill<<<blocks, 256, 0, s>>>(t_first, t_count, ctx->cand_kcap, ctx->cand_pad.p, ctx->cand_cnt.p,
-                                     ctx->tet_off.p, ctx->sites.flags.p, ctx->pair_tet.p, ctx->pair_site.p);
+  k_grid_fill<<<blocks, 256, 0, s>>>(t_first, t_count, ctx->mesh.sel_ptr(), ctx->cand_kcap, ctx->cand_pad.p,
+                                     ctx->cand_cnt.p, ctx->tet_off.p, ctx->sites.flags.p, ctx->pair_tet.p,
+                                     ctx->pair_site.p, ctx->pair_local.p);
   MB_CUDA(cudaGetLastError());
 }
 
@@ -437,9 +439,9 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   cudaStream_t s = ctx->stream;
   MB_REQUIRE(M.n_tet > 0, MB_ERR_STATE, "mb_set_tetmesh must be called before mb_rpd3d");
   MB_REQUIRE(S.n_site > 0, MB_ERR_STATE, "no sites uploaded");
-  const int t_first = M.range_first;
-  const int t_count = M.range_count < 0 ? M.n_tet - t_first : M.range_count;
-  MB_REQUIRE(t_first >= 0 && t_count >= 0 && t_first + t_count <= M.n_tet, MB_ERR_ARG, "bad tet range");
+  const int t_first = M.n_sel > 0 ? 0 : M.range_first;
+  const int t_count = M.n_sel > 0 ? M.n_sel : (M.range_count < 0 ? M.n_tet - t_first : M.range_count);
+  MB_REQUIRE(t_first >= 0 && t_count >= 0 && (M.n_sel > 0 || t_first + t_count <= M.n_tet), MB_ERR_ARG, "bad tet range");
   int G = opts && opts->lanes_per_cell ? opts->lanes_per_cell : 8;
   MB_REQUIRE(G == 4 || G == 8 || G == 16 || G == 32, MB_ERR_ARG, "lanes_per_cell must be 4, 8, 16 or 32");
   res->ctx = ctx;
@@ -461,7 +463,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
       ctx->cand_pad.reserve((size_t)t_count * CAND_PAD);
       const int blocks = (t_count + 7) / 8;
       ctx->n_launches++;
-      k_cand_given<false><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, S.site4.p,
+      k_cand_given<false><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, M.sel_ptr(), S.site4.p,
                                                  S.flags.p, S.n_site, S.nbr.p, S.site_k, ctx->tet_cnt.p,
                                                  ctx->cand_pad.p, nullptr, nullptr, nullptr);
       MB_CUDA(cudaGetLastError());
@@ -476,11 +478,12 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     n_pairs = total;
     ctx->pair_tet.reserve((size_t)n_pairs + 1);
     ctx->pair_site.reserve((size_t)n_pairs + 1);
+    ctx->pair_local.reserve((size_t)n_pairs + 1);
     if (n_pairs > 0) {
       if (!grid_cands) {
         const int blocks = (t_count + 7) / 8;
         ctx->n_launches++;
-        k_cand_given<true><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, S.site4.p,
+        k_cand_given<true><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, M.sel_ptr(), S.site4.p,
                                                   S.flags.p, S.n_site, S.nbr.p, S.site_k, ctx->tet_cnt.p,
                                                   ctx->cand_pad.p, ctx->tet_off.p, ctx->pair_tet.p,
                                                   ctx->pair_site.p);
@@ -523,6 +526,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     A.tet_first = t_first;
     A.pair_tet = ctx->pair_tet.p;
     A.pair_site = ctx->pair_site.p;
+    A.pair_local = ctx->pair_local.p;
     A.n_pairs = n_pairs;
     A.pair_status = ctx->pair_status.p;
     A.pair_blob = ctx->pair_blob.p;
@@ -594,6 +598,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   if (res->n_cells == 0) MB_CUDA(cudaMemsetAsync(res->cell_off.p, 0, sizeof(long long), s));
   res->compact_bytes = (long)(total_words * 4);
   MB_CUDA(cudaEventRecord(res->ev[3], s));
+  if (res->want_volumes) rpd_volumes(ctx, res);
   res->synced = false;
 }
 

@@ -64,6 +64,20 @@ class RpdResult:
         self.ctx._check(self.ctx.lib.mb_rpd_fetch_compact(self._h, ptr(blob), ptr(offs)))
         return blob, offs
 
+    def site_volumes(self):
+        """per-site volume and barycentre sums (needs want_volumes=True); bary is SoA x|y|z"""
+        n = self.ctx._n_site
+        vol = np.zeros(n, np.float32)
+        bary = np.zeros(3 * n, np.float32)
+        self.ctx._check(self.ctx.lib.mb_rpd_site_volumes(self._h, ptr(vol), ptr(bary)))
+        return vol, bary
+
+    def cell_volumes(self):
+        out = np.zeros(self.n_cells, np.float32)
+        if self.n_cells:
+            self.ctx._check(self.ctx.lib.mb_rpd_cell_volumes(self._h, ptr(out)))
+        return out
+
     def device_buffers(self):
         b, o = C.c_void_p(), C.c_void_p()
         nb, nc = C.c_long(), C.c_long()
@@ -158,6 +172,14 @@ class Context:
     def set_tet_range(self, first: int, count: int):
         self._check(self.lib.mb_set_tet_range(self._ctx, int(first), int(count)))
 
+    def set_tet_subset(self, tet_ids=None):
+        """process only the listed tets (ascending global ids); None / empty clears the subset"""
+        if tet_ids is None or len(tet_ids) == 0:
+            self._check(self.lib.mb_set_tet_subset(self._ctx, None, 0))
+        else:
+            ids = _c(tet_ids, np.int32)
+            self._check(self.lib.mb_set_tet_subset(self._ctx, ptr(ids), ids.size))
+
     # ------------------------------------------------------------------ RPD
     def upload_sites(self, site_soa, site_weights, site_flags, site_knn=None, site_k=0):
         ss = _c(site_soa, np.float32).reshape(-1)
@@ -165,6 +187,7 @@ class Context:
         sf = _c(site_flags, np.uint32)
         knn = None if site_knn is None else _c(site_knn, np.int32).reshape(-1)
         self._keep = (ss, sw, sf, knn)
+        self._n_site = sw.size
         self._check(self.lib.mb_rpd_upload_sites(self._ctx, ptr(ss), ptr(sw), ptr(sf), sw.size, ptr(knn), int(site_k)))
 
     def run(self, lanes_per_cell=0, grid_k=0, want_volumes=False, grid_candidates=False) -> RpdResult:

@@ -308,3 +308,50 @@ def test_given_lists_with_grid_candidates(ctx, O, cfg1_rt):
     pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
     ra, _, _ = O.run_pairs(mesh, sites, knn, k, pt, ps)
     assert_defined_equal(O, ra[ra["status"] == 4], b)
+
+
+def test_site_volumes_and_barycentres(ctx, O, cfg1_rt):
+    """a12 (atomic_add_bary_and_volume): per-site sums agree with the oracle's within float-atomic
+    reordering; the volumes tile the mesh."""
+    mesh, sites, knn, k = cfg1_rt
+    pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
+    _, _, _, vol_o, bary_o = O.run_pairs(mesh, sites, knn, k, pt, ps, n_threads=1, want_vol=True)
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, knn, k)
+    res = ctx.run(want_volumes=True)
+    vol, bary = res.site_volumes()
+    assert np.allclose(vol, vol_o, rtol=2e-5, atol=1e-2)
+    assert np.allclose(bary, bary_o, rtol=2e-5, atol=20.0)
+    assert abs(float(vol.astype(np.float64).sum()) - mesh.tet_volumes().sum()) / mesh.tet_volumes().sum() < 2e-3  # the FP32 formula of a12 itself
+    cv = res.cell_volumes()
+    assert len(cv) == res.n_cells and np.isfinite(cv).all()
+    per_site = np.zeros(sites.n_site)
+    recs = res.records()
+    np.add.at(per_site, recs["voro_id"][np.abs(cv) >= 0.1], cv[np.abs(cv) >= 0.1].astype(np.float64))
+    assert np.allclose(per_site, vol, rtol=1e-4, atol=1e-1)
+
+
+@pytest.mark.parametrize("mode", ["given", "grid"])
+def test_tet_subset_equals_full_restricted(ctx, O, cfg1_rt, mode):
+    """mb_set_tet_subset (device-side partial-tet recompute): the cells of the listed tets equal the
+    full run's cells of those tets, with global tet ids and (tet, site) order."""
+    mesh, sites, knn, k = cfg1_rt
+    ctx.set_mesh(mesh)
+    args = (sites.site_soa, sites.weights, sites.flags) + ((knn, k) if mode == "given" else (None, 0))
+    full = ctx.compute_clipped_voro_diagram(*args).records()
+    rng = np.random.default_rng(5)
+    sel = np.sort(rng.choice(mesh.n_tet, size=3000, replace=False)).astype(np.int32)
+    ctx.set_tet_subset(sel)
+    part = ctx.compute_clipped_voro_diagram(*args).records()
+    ctx.set_tet_subset(None)
+    want = full[np.isin(full["tet_id"], sel)]
+    assert len(part) == len(want) > 0
+    for f in full.dtype.names:
+        if f not in ("id", "thread_id"):
+            assert np.ascontiguousarray(part[f]).tobytes() == np.ascontiguousarray(want[f]).tobytes(), f
+    assert np.array_equal(part["id"], np.arange(len(part)))
+    from libmat_b200.rpd import LibMatError
+    with pytest.raises(LibMatError):
+        ctx.set_tet_subset(np.array([5, 3], np.int32))
+    again = ctx.compute_clipped_voro_diagram(*args)
+    assert again.n_cells == len(full)
