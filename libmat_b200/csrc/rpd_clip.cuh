@@ -96,7 +96,11 @@ __device__ __forceinline__ float4 cofactors_f32(const Minors& m) {
   return make_float4((float)m.m234, (float)(-m.m134), (float)m.m124, (float)(-m.m123));
 }
 
-template <int G>
+// PT = per-tet candidate lists (grid-kNN mode).  There array positions are not part of the contract
+// (SURVEY 8a canonical form), so the order-defining serial replay of C2 is replaced by a
+// group-cooperative partition + adjacency-bit-matrix cavity boundary; every predicate decision and
+// every stored triple (cur_p, cir, next) is unchanged.
+template <int G, bool PT>
 __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CellS* cells = reinterpret_cast<CellS*>(smem_raw);
@@ -109,6 +113,10 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
   CellS& S = cells[threadIdx.x / G];
   __shared__ unsigned long long blk_cnt[16];  // block-aggregated counters (RpdCounters layout)
   if (threadIdx.x < 16) blk_cnt[threadIdx.x] = 0;
+  if (PT) {
+    // the cavity adjacency matrix is all-zero between clips (rows are cleared by their writers)
+    for (int i = lane; i < MBK_MAX_P; i += G) S.adj[i] = 0ull;
+  }
   __syncthreads();
 
   // warp-level work queue (chunks of pairs from the global cursor) and per-group scratch chunk
@@ -127,7 +135,8 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
   unsigned long long e6 = 0;
   const int* list = nullptr;
   int list_len = 0, base = 0;
-  bool per_tet = A.nbr_cnt != nullptr, list_done = false, cull_ok = false;
+  constexpr bool per_tet = PT;
+  bool list_done = false, cull_ok = false;
   unsigned todo = 0, valid = 0, cvalid = 0;
   int nb = -1;                                // per lane: the neighbour of this lane's slot
   float4 eqn = make_float4(0, 0, 0, 0);       // per lane: its bisector
@@ -427,6 +436,118 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
     int L = 0;
     int st2 = ST_success;
     unsigned cv = cvalid;
+    if (PT) {
+      // ---- C2 (grid-kNN mode): group-cooperative, no order replay ------------------------------
+      const bool a1 = (act2 == 1);
+      const int nv_new = nb_v - nb_r;
+      if (a1 && lane == 0) {
+        S.plane[nb_p] = e;
+        S.pnb[nb_p] = nbk;
+      }
+      // (i) partition: the i-th removed vertex of the head [0, nv_new) trades places with the i-th
+      // kept vertex of the tail [nv_new, nb_v).  Pairs are disjoint: no barrier between read and write.
+      {
+        const int hmax = __reduce_max_sync(0xffffffffu, a1 ? nv_new : 0);
+        // kept vertices of the tail
+        unsigned long long k0 = ~f0;
+        unsigned k1 = ~f1;
+        if (nv_new < 64) k0 &= ~((1ull << nv_new) - 1ull); else { k0 = 0; k1 &= ~((1u << (nv_new - 64)) - 1u); }
+        if (nb_v < 64) { k0 &= (1ull << nb_v) - 1ull; k1 = 0; } else if (nb_v < 96) k1 &= (1u << (nb_v - 64)) - 1u;
+        for (int vb = 0; vb < hmax; vb += G) {
+          const int v = vb + lane;
+          const bool fv = v < 64 ? ((f0 >> v) & 1ull) : ((f1 >> (v - 64)) & 1u);
+          const bool mv = a1 && v < nv_new && fv;
+          bool pvalid = false;
+          if (mv) {
+            // rank among the removed vertices of the head
+            int i = v < 64 ? __popcll(f0 & ((1ull << v) - 1ull)) : (__popcll(f0) + __popc(f1 & ((1u << (v - 64)) - 1u)));
+            int partner;
+            const int pc0 = __popcll(k0);
+            if (i < pc0) {
+              unsigned long long kk = k0;
+              for (; i > 0; i--) kk &= kk - 1ull;
+              partner = __ffsll((long long)kk) - 1;
+            } else {
+              unsigned kk = k1;
+              for (i -= pc0; i > 0; i--) kk &= kk - 1u;
+              partner = 64 + __ffs((int)kk) - 1;
+            }
+            const uchar4 tv = S.ver[v], tp = S.ver[partner];
+            pvalid = partner < MBK_CV && ((cv >> partner) & 1u);
+            S.ver[v] = tp;
+            S.ver[partner] = tv;
+            if (pvalid && v < MBK_CV) S.cof[v] = S.cof[partner];
+          }
+          if (vb < 32) {
+            const unsigned mm = (__ballot_sync(0xffffffffu, mv) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+            const unsigned ms = (__ballot_sync(0xffffffffu, mv && pvalid) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+            cv = (cv & ~(mm << vb)) | (ms << vb);
+          }
+        }
+      }
+      __syncwarp();
+      // (ii) cavity boundary: directed dual edges a->b of the removed triangles go into a 64x64 bit
+      // matrix; an edge is on the boundary iff its twin b->a is absent (compute_boundary :618-678
+      // builds the same circular list one triangle at a time)
+      const int rmax = __reduce_max_sync(0xffffffffu, a1 ? nb_r : 0);
+      for (int rb = 0; rb < rmax; rb += G) {
+        const int r = rb + lane;
+        if (a1 && r < nb_r) {
+          const uchar4 tv = S.ver[nv_new + r];
+          unsigned* m32 = reinterpret_cast<unsigned*>(S.adj);
+          atomicOr(&m32[2 * tv.x + (tv.y >> 5)], 1u << (tv.y & 31));
+          atomicOr(&m32[2 * tv.y + (tv.z >> 5)], 1u << (tv.z & 31));
+          atomicOr(&m32[2 * tv.z + (tv.x >> 5)], 1u << (tv.x & 31));
+        }
+      }
+      if (a1) {  // clear the circular list (64 bytes per cell)
+        if (G >= 8) { if (lane < 8) reinterpret_cast<uint2*>(S.bnext)[lane] = make_uint2(0xffffffffu, 0xffffffffu); }
+        else { reinterpret_cast<uint4*>(S.bnext)[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu); }
+      }
+      __syncwarp();
+      int nbnd = 0, first = MBK_END;
+      for (int rb = 0; rb < rmax; rb += G) {
+        const int r = rb + lane;
+        if (a1 && r < nb_r) {
+          const uchar4 tv = S.ver[nv_new + r];
+          const unsigned char pl[3] = {tv.x, tv.y, tv.z};
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            const int a = pl[q], b = pl[(q + 1) % 3];
+            if (!((S.adj[b] >> a) & 1ull)) {
+              S.bnext[a] = (unsigned char)b;
+              nbnd++;
+              first = min(first, a);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        nbnd += __shfl_xor_sync(0xffffffffu, nbnd, o);
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+      }
+      __syncwarp();
+      for (int rb = 0; rb < rmax; rb += G) {
+        const int r = rb + lane;
+        if (a1 && r < nb_r) {
+          const uchar4 tv = S.ver[nv_new + r];
+          S.adj[tv.x] = 0ull;
+          S.adj[tv.y] = 0ull;
+          S.adj[tv.z] = 0ull;
+        }
+      }
+      // (iii) the cycle, from its smallest plane id (deterministic); a cavity whose boundary is not
+      // one simple cycle is the reference's inconsistent_boundary (:626-629)
+      if (a1 && lane == 0 && first != MBK_END) {
+        int cir = first;
+        do {
+          S.cyc[L++] = (unsigned char)cir;
+          cir = S.bnext[cir];
+        } while (cir != first && cir != MBK_END && L < nbnd && L < MBK_MAX_P);
+        if (cir != first || L != nbnd) st2 = ST_inconsistent_boundary;
+      }
+    } else
     if (act2 == 1 && lane == 0) {
       const int cur_p = nb_p;
       S.plane[cur_p] = e;

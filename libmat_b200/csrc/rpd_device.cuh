@@ -130,6 +130,7 @@ struct __align__(16) CellS {
   unsigned char bnext[MBK_MAX_P];   // cavity boundary circular list (16-byte aligned: cleared with uint4 stores)
   unsigned char cyc[MBK_MAX_P];     // the boundary cycle in walk order
   unsigned char edge[MBK_MAX_E * 3];  // (plane a, plane b, #adjacent cells)
+  unsigned long long adj[MBK_MAX_P];  // grid-kNN mode: directed dual-edge bit matrix of the cavity (zero between clips)
 };
 static_assert(offsetof(CellS, bnext) % 16 == 0, "bnext must be 16-byte aligned");
 

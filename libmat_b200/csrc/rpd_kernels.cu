@@ -412,24 +412,24 @@ static void exclusive_scan(mb_ctx* ctx, const int* in, T* out, long long n) {
   MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, out, n, ctx->stream));
 }
 
-template <int G>
+template <int G, bool PT>
 static void launch_clip(mb_ctx* ctx, const ClipArgs& A) {
   constexpr int groups = 128 / G;
   const size_t smem = sizeof(CellS) * groups;
   static bool attr_set = false;
   if (!attr_set) {
-    MB_CUDA(cudaFuncSetAttribute(k_clip<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MB_CUDA(cudaFuncSetAttribute(k_clip<G, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   int per_sm = 0;
-  MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip<G>, 128, smem));
+  MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip<G, PT>, 128, smem));
   if (per_sm < 1) per_sm = 1;
   // persistent grid: every SM fully resident, warps pull chunks of pairs from a global cursor
   long long want = (A.n_pairs + groups - 1) / groups;
   long long grid = std::min<long long>(want, (long long)ctx->sm_count * per_sm);
   if (grid < 1) grid = 1;
   ctx->n_launches++;
-  k_clip<G><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
+  k_clip<G, PT><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
   MB_CUDA(cudaGetLastError());
 }
 
@@ -534,14 +534,15 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     A.scratch = ctx->scratch.p;
     A.scratch_words = ctx->scratch.cap;
     A.counters = reinterpret_cast<unsigned long long*>(ctx->counters.p);
+    const bool pt = A.nbr_cnt != nullptr;
     if (G == 4)
-      launch_clip<4>(ctx, A);
+      pt ? launch_clip<4, true>(ctx, A) : launch_clip<4, false>(ctx, A);
     else if (G == 8)
-      launch_clip<8>(ctx, A);
+      pt ? launch_clip<8, true>(ctx, A) : launch_clip<8, false>(ctx, A);
     else if (G == 16)
-      launch_clip<16>(ctx, A);
+      pt ? launch_clip<16, true>(ctx, A) : launch_clip<16, false>(ctx, A);
     else
-      launch_clip<32>(ctx, A);
+      pt ? launch_clip<32, true>(ctx, A) : launch_clip<32, false>(ctx, A);
     MB_CUDA(cudaEventRecord(res->ev[2], s));
     MB_CUDA(cudaMemcpyAsync(&hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
     MB_CUDA(cudaStreamSynchronize(s));
