@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5", "d2m"])
     ap.add_argument("--samples", type=int, default=0, help="dist2mat samples (config 3 is 10 000 000)")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--chunks", type=int, default=0, help="e2e leg: tet spans of the streamed run (0 = automatic)")
     ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -454,21 +455,26 @@ def main():
         # ---- e2e: host buffers in, compact records out, every step ------------------------------
         e2e_steps = max(3, min(args.steps, 10))
         # destination buffers are allocated (pinned) once, outside the timed region
+        e2e_chunks = 1
         if world == 1:
-            tb = torch.empty(int(rec_bytes * 1.1) // 4 + 1024, dtype=torch.int32).pin_memory()
-            to = torch.empty(int(cells * 1.1) + 1024, dtype=torch.int64).pin_memory()
-            blob_host = (tb.numpy().view(np.uint32), to.numpy(), tb, to)
+            # the library's own pinned destination is sized by an untimed first streamed run
+            ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates).free()
+            blob_host = None
         elif rank == 0:
             blob_host = (torch.empty(int(tot_bytes_guess(rec_bytes, world)), dtype=torch.uint8).pin_memory(),)
         else:
             blob_host = None
         barrier()
+        e2e_parts = np.zeros(3)
         t0 = time.perf_counter()
         for i in range(e2e_steps):
+            ta = time.perf_counter()
             set_mesh()
+            tb_ = time.perf_counter()
             upload_sites()
-            res, gathered = step()
+            tc = time.perf_counter()
             if world > 1:
+                res, gathered = step()
                 # the gathered result of all ranks leaves rank 0's GPU
                 if rank == 0:
                     if blob_host is None or blob_host[0].numel() < gathered:
@@ -477,14 +483,13 @@ def main():
                 d2h = gathered
                 res.free()
                 continue
-            if True:
-                if blob_host is None or blob_host[0].size * 4 < res.compact_bytes:
-                    tb = torch.empty(int(res.compact_bytes * 1.05) // 4 + 16, dtype=torch.int32).pin_memory()
-                    to = torch.empty(res.n_cells + 16, dtype=torch.int64).pin_memory()
-                    blob_host = (tb.numpy().view(np.uint32), to.numpy(), tb, to)
-                ctx._check(ctx.lib.mb_rpd_fetch_compact(res._h, blob_host[0].ctypes.data, blob_host[1].ctypes.data))
+            # streamed run: the D2H of tet span c overlaps the kernels of span c+1; on return the complete
+            # compact result (records + offsets) is in pinned host memory
+            res = ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates)
             d2h = res.compact_bytes + 8 * (res.n_cells + 1)
+            e2e_chunks = int(res.n_spans)
             res.free()
+            e2e_parts += (tb_ - ta, tc - tb_, time.perf_counter() - tc)
         barrier()
         t_e2e = time.perf_counter() - t0
 
@@ -525,7 +530,11 @@ def main():
                          "note": "latency/FP64-bound irregular kernel; see DESIGN.md and profiles/"},
             "e2e": {"value": total_cells * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "path": "mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run + mb_rpd_fetch_compact"},
+                    "path": ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_host (%d tet spans, D2H of span c "
+                             "overlapped with the kernels of span c+1)" % e2e_chunks) if world == 1 else
+                            "mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run + NCCL gather + D2H on rank 0",
+                    "stage_ms": {"set_tetmesh": 1e3 * e2e_parts[0] / e2e_steps, "upload_sites": 1e3 * e2e_parts[1] / e2e_steps,
+                                 "run_to_host": 1e3 * e2e_parts[2] / e2e_steps}},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -140,6 +140,22 @@ int mb_rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
 int mb_rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result** out); /* async launch */
 int mb_rpd_sync(mb_ctx* ctx, mb_rpd_result* res); /* waits, reads back the counters */
 
+/* Streamed variant of mb_rpd_run + mb_rpd_sync + mb_rpd_fetch_compact for callers that want the result in
+ * HOST memory (what compute_clipped_voro_diagram_GPU returns, voronoi.cu:717-769): the processed tets are
+ * cut into n_chunks contiguous spans (0 = automatic, ~48k tets each) and the ordered compact records of
+ * span c are copied to library-owned pinned host memory on a second stream while span c+1 is searched and
+ * clipped, so the PCIe transfer hides behind the kernels.  On return the complete result -- identical to
+ * the one-shot run's mb_rpd_fetch_compact output -- is at *host_blob / *host_cell_offsets (n_cells+1 byte
+ * offsets), valid until the next streamed run on this context or mb_destroy.  The result handle carries the
+ * counters (mb_rpd_count / _stats / _kernel_ms) and serves mb_rpd_fetch_records / mb_rpd_fetch_compact from
+ * the host copy; it keeps nothing on the device (mb_rpd_emit, mb_rpd_device_buffers, mb_rpd_fetch_pairs
+ * return MB_ERR_STATE). */
+int mb_rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result** out,
+                       const void** host_blob, const long** host_cell_offsets);
+
+/* number of tet spans the run was cut into (1 for mb_rpd_run); negative mb_status on a NULL handle */
+int mb_rpd_spans(const mb_rpd_result* res);
+
 void mb_rpd_free(mb_rpd_result* res);
 
 /* number of valid cells (status success), candidate pairs clipped, clip_by_plane calls */

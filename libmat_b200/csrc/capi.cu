@@ -3,6 +3,7 @@
 // error: include/common_cuda.h:6-7, src/rpd3d/voronoi.cu:31-37, include/cuda_utils.h:18-25).
 #include <omp.h>
 
+#include <cstdlib>
 #include <new>
 
 #include "mb_internal.h"
@@ -63,6 +64,7 @@ mb_ctx* mb_create(int device, int* err) {
   }
   ctx->stream = ctx->own_stream;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (const char* v = getenv("MB_D2M_VARIANT")) ctx->d2m_variant = atoi(v);
   if (err) *err = MB_OK;
   return ctx;
 }
@@ -87,7 +89,16 @@ void mb_destroy(mb_ctx* ctx) {
   ctx->scratch.release(); ctx->counters.release(); ctx->cub_tmp.release();
   ctx->grid_cnt.release(); ctx->grid_off.release(); ctx->grid_sorted_id.release(); ctx->grid_cell_of.release();
   ctx->grid_site4.release(); ctx->grid_wmax0.release(); ctx->grid_wmax1.release();
-  ctx->pin_in.release(); ctx->pin_out.release();
+  ctx->pin_in.release(); ctx->pin_out.release(); ctx->pin_blob.release(); ctx->pin_off.release();
+  for (int b = 0; b < 2; b++) {
+    ctx->span_blob[b].release();
+    ctx->span_off[b].release();
+    if (ctx->ev_gathered[b]) cudaEventDestroy(ctx->ev_gathered[b]);
+    if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+  }
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->hs) cudaFreeHost(ctx->hs);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -180,6 +191,28 @@ int mb_rpd_sync(mb_ctx* ctx, mb_rpd_result* res) {
   MB_CATCH
 }
 
+int mb_rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result** out,
+                       const void** host_blob, const long** host_cell_offsets) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && out, MB_ERR_ARG, "null argument");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  mb_rpd_result* res = new mb_rpd_result();
+  *out = res;
+  res->ctx = ctx;
+  ctx->live_results.push_back(res);
+  try {
+    rpd_run_to_host(ctx, opts, n_chunks, res);
+    rpd_sync(ctx, res);
+  } catch (...) {
+    mb_rpd_free(res);
+    *out = nullptr;
+    throw;
+  }
+  if (host_blob) *host_blob = res->host_blob;
+  if (host_cell_offsets) *host_cell_offsets = reinterpret_cast<const long*>(res->host_off);
+  MB_CATCH
+}
+
 int mb_rpd3d(mb_ctx* ctx, const float* site_soa, const float* site_w, const unsigned* site_flags,
              int n_site, const int* site_knn, int site_k, const mb_rpd_opts* opts,
              mb_rpd_result** out) {
@@ -214,8 +247,12 @@ void mb_rpd_free(mb_rpd_result* res) {
   res->f_cell.release(); res->f_key.release(); res->v_cell.release(); res->v_lvid.release();
   res->v_key3.release(); res->v_surf.release(); res->e_cell.release(); res->e_key2.release();
   res->e_lvid2.release(); res->f_istet.release(); res->v_pos3.release(); res->c_euler.release();
-  for (int i = 0; i < 5; i++)
-    if (res->ev[i]) cudaEventDestroy(res->ev[i]);
+  for (cudaEvent_t e : res->evs) {
+    if (res->ctx)
+      res->ctx->ev_pool.push_back(e);  // recycled by the next run
+    else
+      cudaEventDestroy(e);
+  }
   delete res;
 }
 
@@ -226,6 +263,8 @@ int mb_rpd_count(const mb_rpd_result* res, long* n_cells, long* n_pairs, long* n
   if (n_clips) *n_clips = res->n_clips;
   return MB_OK;
 }
+
+int mb_rpd_spans(const mb_rpd_result* res) { return res ? res->n_spans : MB_ERR_ARG; }
 
 int mb_rpd_stats(const mb_rpd_result* res, long stats[8]) {
   if (!res || !stats) return MB_ERR_ARG;
@@ -262,6 +301,7 @@ int mb_rpd_fetch_pairs(mb_rpd_result* res, int* pair_tet, int* pair_site, signed
   mb_ctx* ctx = res ? res->ctx : nullptr;
   MB_TRY(ctx)
   MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_REQUIRE(!res->host_only, MB_ERR_STATE, "pairs are not kept by a streamed run (mb_rpd_run_to_host)");
   MB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   const size_t n = (size_t)res->n_pairs;
@@ -286,6 +326,12 @@ int mb_rpd_fetch_compact(mb_rpd_result* res, void* blob, long* cell_offsets) {
   MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
   MB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
+  if (res->host_only) {  // streamed run: the records are already in pinned host memory
+    MB_REQUIRE(res->host_blob == ctx->pin_blob.p, MB_ERR_STATE, "streamed result superseded by a later run");
+    if (blob && res->compact_bytes > 0) memcpy(blob, res->host_blob, (size_t)res->compact_bytes);
+    if (cell_offsets) memcpy(cell_offsets, res->host_off, sizeof(long long) * ((size_t)res->n_cells + 1));
+    return MB_OK;
+  }
   if (blob && res->compact_bytes > 0)
     MB_CUDA(cudaMemcpyAsync(blob, res->blob.p, (size_t)res->compact_bytes, cudaMemcpyDeviceToHost, s));
   if (cell_offsets)
@@ -339,13 +385,23 @@ int mb_rpd_fetch_records(mb_rpd_result* res, void* dst) {
   const long n = res->n_cells;
   if (n == 0) return MB_OK;
   const size_t off_bytes = sizeof(long long) * ((size_t)n + 1);
-  unsigned char* pin = (unsigned char*)ctx->pin_out.reserve((size_t)res->compact_bytes + off_bytes + 16);
-  long long* offs = reinterpret_cast<long long*>(pin);
-  uint32_t* blob = reinterpret_cast<uint32_t*>(pin + ((off_bytes + 15) / 16) * 16);
-  cudaStream_t s = ctx->stream;
-  MB_CUDA(cudaMemcpyAsync(blob, res->blob.p, (size_t)res->compact_bytes, cudaMemcpyDeviceToHost, s));
-  MB_CUDA(cudaMemcpyAsync(offs, res->cell_off.p, off_bytes, cudaMemcpyDeviceToHost, s));
-  MB_CUDA(cudaStreamSynchronize(s));
+  const long long* offs;
+  const uint32_t* blob;
+  if (res->host_only) {
+    MB_REQUIRE(res->host_blob == ctx->pin_blob.p, MB_ERR_STATE, "streamed result superseded by a later run");
+    offs = res->host_off;
+    blob = res->host_blob;
+  } else {
+    unsigned char* pin = (unsigned char*)ctx->pin_out.reserve((size_t)res->compact_bytes + off_bytes + 16);
+    long long* o = reinterpret_cast<long long*>(pin);
+    uint32_t* b = reinterpret_cast<uint32_t*>(pin + ((off_bytes + 15) / 16) * 16);
+    cudaStream_t s = ctx->stream;
+    MB_CUDA(cudaMemcpyAsync(b, res->blob.p, (size_t)res->compact_bytes, cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaMemcpyAsync(o, res->cell_off.p, off_bytes, cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    offs = o;
+    blob = b;
+  }
   unsigned char* out = reinterpret_cast<unsigned char*>(dst);
 #pragma omp parallel for schedule(static)
   for (long i = 0; i < n; i++)
@@ -380,6 +436,7 @@ int mb_rpd_cell_volumes(mb_rpd_result* res, float* cell_vol) {
 int mb_rpd_device_buffers(mb_rpd_result* res, void** d_blob, long* n_bytes, void** d_offsets,
                           long* n_cells) {
   if (!res) return MB_ERR_ARG;
+  if (res->host_only) return MB_ERR_STATE;  // a streamed run keeps nothing on the device
   if (d_blob) *d_blob = res->blob.p;
   if (n_bytes) *n_bytes = res->compact_bytes;
   if (d_offsets) *d_offsets = res->cell_off.p;
@@ -391,6 +448,7 @@ int mb_rpd_emit(mb_rpd_result* res, int max_surf_fid, mb_emit_counts* counts) {
   mb_ctx* ctx = res ? res->ctx : nullptr;
   MB_TRY(ctx)
   MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_REQUIRE(!res->host_only, MB_ERR_STATE, "K4 emission needs a device-resident result (mb_rpd_run)");
   MB_CUDA(cudaSetDevice(ctx->device));
   rpd_emit(ctx, res, max_surf_fid);
   if (counts) *counts = res->emit_counts;

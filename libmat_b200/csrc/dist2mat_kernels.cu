@@ -92,8 +92,9 @@ __device__ float d_cone(f3 pos, float4 m1, float4 m2) {
   return len3(sub3(pos, sp)) - lr;
 }
 
-// dist2mat.cu:71-193
-__device__ float d_slab(f3 pos, float4 m1, float4 m2, float4 m3) {
+// dist2mat.cu:71-193, cut in two: the interior solve (sets `inside`) and the boundary-cone fallback, so
+// that the queue kernel can run each part with converged lanes
+__device__ float d_slab_main(f3 pos, float4 m1, float4 m2, float4 m3, bool& inside) {
   const f3 c31{m1.x - m3.x, m1.y - m3.y, m1.z - m3.z};
   const f3 c32{m2.x - m3.x, m2.y - m3.y, m2.z - m3.z};
   const f3 cm3{m3.x - pos.x, m3.y - pos.y, m3.z - pos.z};
@@ -192,12 +193,26 @@ __device__ float d_slab(f3 pos, float4 m1, float4 m2, float4 m3) {
       }
     }
   }
-  if ((t1 + t2) < 1.f && t1 >= 0.f && t1 <= 1.f && t2 >= 0.f && t2 <= 1.f)
+  if ((t1 + t2) < 1.f && t1 >= 0.f && t1 <= 1.f && t2 >= 0.f && t2 <= 1.f) {
+    inside = true;
     return d_sphere(pos, bary_lerp(m1, m2, m3, t1, t2));
+  }
+  inside = false;
+  return 0.f;
+}
+
+// the slab's fallback when the foot point leaves the triangle: its three boundary cones (:186-192)
+__device__ __forceinline__ float d_slab_boundary(f3 pos, float4 m1, float4 m2, float4 m3) {
   const float dis1 = d_cone(pos, m1, m3);
   const float dis2 = d_cone(pos, m2, m3);
   const float dis3 = d_cone(pos, m1, m2);
   return fminf(dis1, fminf(dis2, dis3));
+}
+
+__device__ __forceinline__ float d_slab(f3 pos, float4 m1, float4 m2, float4 m3) {
+  bool inside;
+  const float d = d_slab_main(pos, m1, m2, m3, inside);
+  return inside ? d : d_slab_boundary(pos, m1, m2, m3);
 }
 
 // order-preserving float -> uint key (for REDUX min)
@@ -258,6 +273,225 @@ __global__ void __launch_bounds__(256) k_dist2mat(const float* __restrict__ samp
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Queue-compacted variant (the one launched).  The warp-per-sample kernel above runs ~13 of 32 lanes
+// per instruction: a sample's list (~22 primitives) does not fill the warp and its spheres, cones and
+// slabs take different code paths, as does the slab's boundary-cone fallback.  Here a warp takes a
+// BATCH of up to 32 consecutive samples and
+//   A  classifies their primitives (spheres are evaluated on the spot), pushing cones to the front and
+//      slabs to the back of a shared-memory queue; entry = (sample-in-batch << 16 | index in its list)
+//   B  evaluates the cone queue, 32 converged lanes at a time
+//   C  evaluates the slab interior solve the same way; slabs whose foot point leaves the triangle are
+//      re-queued in place
+//   D  evaluates the boundary-cone fallbacks, converged
+//   E  one LANE per sample reduces that sample's distances, reproducing the reference's block-level
+//      tie rule (lane l keeps the first strict minimum over i = l, l+32, ...; the winner is the highest
+//      lane within 1e-10 of the minimum, dist2mat.cu:248-276) from the stored per-primitive distances.
+// Every distance is computed by the same device functions as above: results are bit-identical.
+// ---------------------------------------------------------------------------------------------
+template <int CAP>
+__device__ __forceinline__ void d2m_sample_direct(int smp, int lane, const float* __restrict__ samples,
+                                                  const float4* __restrict__ spheres, const int* __restrict__ prims,
+                                                  const unsigned* __restrict__ offsets, const unsigned* __restrict__ counts,
+                                                  float* __restrict__ result, int* __restrict__ closest_id,
+                                                  unsigned char* __restrict__ tie) {
+  const int num_prim = (int)counts[smp];
+  const long long off = offsets[smp];
+  const f3 pos{samples[3 * (size_t)smp], samples[3 * (size_t)smp + 1], samples[3 * (size_t)smp + 2]};
+  float best = 1e16f, second = 1e16f;
+  int best_id = -1;
+  for (int i = lane; i < num_prim; i += 32) {
+    const int* pr = prims + 3 * (off + i);
+    const int px = pr[0], py = pr[1], pz = pr[2];
+    float dist;
+    if (px == -1 && py == -1)
+      dist = d_sphere(pos, spheres[pz]);
+    else if (px == -1)
+      dist = d_cone(pos, spheres[py], spheres[pz]);
+    else
+      dist = d_slab(pos, spheres[px], spheres[py], spheres[pz]);
+    if (dist < best) {
+      second = best;
+      best = fminf(best, dist);
+      best_id = i;
+    } else if (dist < second)
+      second = dist;
+  }
+  const float red = funkey(__reduce_min_sync(0xffffffffu, fkey(best)));
+  const unsigned eq = __ballot_sync(0xffffffffu, fabsf(best - red) < 1e-10f);
+  const int win = 31 - __clz(eq);
+  const int win_id = __shfl_sync(0xffffffffu, best_id, win);
+  const float other = (lane == win) ? second : best;
+  const float sec = funkey(__reduce_min_sync(0xffffffffu, fkey(other)));
+  if (lane == 0) {
+    result[smp] = red;
+    closest_id[smp] = win_id;
+    if (tie) tie[smp] = (sec - red) <= 1e-6f * fmaxf(fabsf(red), fabsf(sec)) && sec < 1e15f;
+  }
+}
+
+template <int CAP, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_dist2mat_q(const float* __restrict__ samples,
+                                                          const float4* __restrict__ spheres,
+                                                          const int* __restrict__ prims,
+                                                          const unsigned* __restrict__ offsets,
+                                                          const unsigned* __restrict__ counts, int n_samples,
+                                                          float* __restrict__ result, int* __restrict__ closest_id,
+                                                          unsigned char* __restrict__ tie) {
+  extern __shared__ __align__(16) unsigned char d2m_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* sd = reinterpret_cast<float*>(d2m_smem) + (size_t)wib * CAP;                       // distance per slot
+  unsigned* sq = reinterpret_cast<unsigned*>(d2m_smem) + (size_t)WARPS * CAP + (size_t)wib * CAP;  // queue
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_batches = (n_samples + 31) >> 5;
+  for (int batch = blockIdx.x * WARPS + wib; batch < n_batches; batch += gridDim.x * WARPS) {
+    const int smp = batch * 32 + lane;
+    const bool have = smp < n_samples;
+    const int cnt = have ? (int)counts[smp] : 0;
+    const unsigned off = have ? offsets[smp] : 0u;
+    f3 pos{0.f, 0.f, 0.f};
+    if (have) pos = f3{samples[3 * (size_t)smp], samples[3 * (size_t)smp + 1], samples[3 * (size_t)smp + 2]};
+    // inclusive prefix of the list lengths
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int excl = incl - cnt;
+    const int n_have = min(32, n_samples - batch * 32);
+    int s0 = 0;
+    while (s0 < n_have) {
+      // sub-batch [s0, s1): as many samples as fit the CAP slots
+      const int ex0 = __shfl_sync(0xffffffffu, excl, s0);
+      const unsigned fits = __ballot_sync(0xffffffffu, lane >= s0 && lane < n_have && incl - ex0 <= CAP);
+      int s1 = s0 + __popc(fits);
+      if (s1 == s0) {  // a single list longer than CAP: the whole warp walks it directly
+        d2m_sample_direct<CAP>(batch * 32 + s0, lane, samples, spheres, prims, offsets, counts, result, closest_id, tie);
+        s0++;
+        continue;
+      }
+      const int base = excl - ex0;  // first slot of this lane's sample (valid for lanes in [s0, s1))
+      // ---- A: classify; spheres on the spot -----------------------------------------------------
+      int n_cone = 0, n_slab = 0;
+      for (int s = s0; s < s1; s++) {
+        const int c = __shfl_sync(0xffffffffu, cnt, s);
+        const unsigned o = __shfl_sync(0xffffffffu, off, s);
+        const int bs = __shfl_sync(0xffffffffu, base, s);
+        const f3 p{__shfl_sync(0xffffffffu, pos.x, s), __shfl_sync(0xffffffffu, pos.y, s),
+                   __shfl_sync(0xffffffffu, pos.z, s)};
+        for (int i0 = 0; i0 < c; i0 += 32) {
+          const int i = i0 + lane;
+          int kind = 0;  // 0 none / sphere (done), 1 cone, 2 slab
+          if (i < c) {
+            const int* pr = prims + 3 * ((size_t)o + i);
+            const int px = pr[0], py = pr[1], pz = pr[2];
+            if (px == -1 && py == -1)
+              sd[bs + i] = d_sphere(p, spheres[pz]);
+            else
+              kind = (px == -1) ? 1 : 2;
+          }
+          const unsigned mc = __ballot_sync(0xffffffffu, kind == 1), ms = __ballot_sync(0xffffffffu, kind == 2);
+          const unsigned e = ((unsigned)s << 16) | (unsigned)i;
+          if (kind == 1) sq[n_cone + __popc(mc & lt)] = e;
+          if (kind == 2) sq[CAP - 1 - (n_slab + __popc(ms & lt))] = e;
+          n_cone += __popc(mc);
+          n_slab += __popc(ms);
+        }
+      }
+      __syncwarp();
+      // ---- B: cones -----------------------------------------------------------------------------
+      for (int n0 = 0; n0 < n_cone; n0 += 32) {
+        const int n = n0 + lane;
+        const bool act = n < n_cone;
+        const unsigned e = sq[act ? n : 0];
+        const int sm = (int)(e >> 16), i = (int)(e & 0xffffu);
+        const unsigned o = __shfl_sync(0xffffffffu, off, sm);
+        const int bs = __shfl_sync(0xffffffffu, base, sm);
+        const f3 p{__shfl_sync(0xffffffffu, pos.x, sm), __shfl_sync(0xffffffffu, pos.y, sm),
+                   __shfl_sync(0xffffffffu, pos.z, sm)};
+        if (act) {
+          const int* pr = prims + 3 * ((size_t)o + i);
+          sd[bs + i] = d_cone(p, spheres[pr[1]], spheres[pr[2]]);
+        }
+      }
+      // ---- C: slab interior solve; boundary cases re-queued in place ----------------------------
+      int n_fb = 0;
+      for (int n0 = 0; n0 < n_slab; n0 += 32) {
+        const int n = n0 + lane;
+        const bool act = n < n_slab;
+        const unsigned e = sq[CAP - 1 - (act ? n : 0)];
+        const int sm = (int)(e >> 16), i = (int)(e & 0xffffu);
+        const unsigned o = __shfl_sync(0xffffffffu, off, sm);
+        const int bs = __shfl_sync(0xffffffffu, base, sm);
+        const f3 p{__shfl_sync(0xffffffffu, pos.x, sm), __shfl_sync(0xffffffffu, pos.y, sm),
+                   __shfl_sync(0xffffffffu, pos.z, sm)};
+        bool inside = true;
+        if (act) {
+          const int* pr = prims + 3 * ((size_t)o + i);
+          const float d = d_slab_main(p, spheres[pr[0]], spheres[pr[1]], spheres[pr[2]], inside);
+          if (inside) sd[bs + i] = d;
+        }
+        const unsigned mf = __ballot_sync(0xffffffffu, !inside);  // also orders this round's queue reads
+        if (!inside) sq[CAP - 1 - (n_fb + __popc(mf & lt))] = e;  // n_fb + rank <= n: never ahead of a reader
+        n_fb += __popc(mf);
+      }
+      __syncwarp();
+      // ---- D: boundary cones of the re-queued slabs ---------------------------------------------
+      for (int n0 = 0; n0 < n_fb; n0 += 32) {
+        const int n = n0 + lane;
+        const bool act = n < n_fb;
+        const unsigned e = sq[CAP - 1 - (act ? n : 0)];
+        const int sm = (int)(e >> 16), i = (int)(e & 0xffffu);
+        const unsigned o = __shfl_sync(0xffffffffu, off, sm);
+        const int bs = __shfl_sync(0xffffffffu, base, sm);
+        const f3 p{__shfl_sync(0xffffffffu, pos.x, sm), __shfl_sync(0xffffffffu, pos.y, sm),
+                   __shfl_sync(0xffffffffu, pos.z, sm)};
+        if (act) {
+          const int* pr = prims + 3 * ((size_t)o + i);
+          sd[bs + i] = d_slab_boundary(p, spheres[pr[0]], spheres[pr[1]], spheres[pr[2]]);
+        }
+      }
+      __syncwarp();
+      // ---- E: one lane per sample, the reference's tie rule from the stored distances -----------
+      if (lane >= s0 && lane < s1) {
+        const float* d = sd + base;
+        float m = 1e16f;
+        for (int i = 0; i < cnt; i++) {
+          const float v = d[i];
+          if (v < m) m = v;
+        }
+        int id = -1;
+        float sec = 1e16f;
+        if (m < 1e16f) {
+          // winning lane class L = highest (i mod 32) holding a value within 1e-10 of the minimum
+          int L = -1;
+          for (int i = 0; i < cnt; i++)
+            if (fabsf(d[i] - m) < 1e-10f) L = max(L, i & 31);
+          // that lane's first strict minimum over i = L, L+32, ...
+          float b = 1e16f;
+          for (int i = L; i < cnt; i += 32) {
+            const float v = d[i];
+            if (v < b) {
+              b = v;
+              id = i;
+            }
+          }
+          for (int i = 0; i < cnt; i++) {
+            const float v = d[i];
+            if (i != id && v < sec) sec = v;
+          }
+        }
+        result[smp] = m;
+        closest_id[smp] = id;
+        if (tie) tie[smp] = (sec - m) <= 1e-6f * fmaxf(fabsf(m), fabsf(sec)) && sec < 1e15f;
+      }
+      __syncwarp();
+      s0 = s1;
+    }
+  }
+}
+
 }  // namespace
 
 void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples, int n_samples,
@@ -293,12 +527,32 @@ void d2m_run(mb_ctx* ctx, float* kernel_ms) {
     MB_CUDA(cudaEventRecord(e0, s));
   }
   if (D.n_samples > 0) {
-    const int warps = D.n_samples;
-    long long blocks = ((long long)warps + 7) / 8;
-    blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 32);
     ctx->n_launches++;
-    k_dist2mat<<<(unsigned)blocks, 256, 0, s>>>(D.samples.p, D.spheres.p, D.prims.p, D.offset.p, D.count.p,
-                                               D.n_samples, D.result.p, D.closest.p, D.tie.p);
+    if (ctx->d2m_variant == 1) {  // warp-per-sample kernel (kept for A/B measurements)
+      long long blocks = ((long long)D.n_samples + 7) / 8;
+      blocks = std::min<long long>(blocks, (long long)ctx->sm_count * 32);
+      k_dist2mat<<<(unsigned)blocks, 256, 0, s>>>(D.samples.p, D.spheres.p, D.prims.p, D.offset.p, D.count.p,
+                                                 D.n_samples, D.result.p, D.closest.p, D.tie.p);
+    } else {
+      constexpr int CAP = 768, WARPS = 8;
+      const size_t smem = (size_t)WARPS * CAP * 8;
+      static bool attr_set = false;
+      if (!attr_set) {
+        MB_CUDA(cudaFuncSetAttribute(k_dist2mat_q<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      static int per_sm = 0;
+      if (per_sm < 1) {
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dist2mat_q<CAP, WARPS>, 32 * WARPS, smem));
+        if (per_sm < 1) per_sm = 1;
+      }
+      const long long batches = ((long long)D.n_samples + 31) / 32;
+      long long blocks = (batches + WARPS - 1) / WARPS;
+      blocks = std::min<long long>(blocks, (long long)ctx->sm_count * per_sm);  // persistent: every SM full
+      k_dist2mat_q<CAP, WARPS><<<(unsigned)blocks, 32 * WARPS, smem, s>>>(D.samples.p, D.spheres.p, D.prims.p, D.offset.p,
+                                                                         D.count.p, D.n_samples, D.result.p,
+                                                                         D.closest.p, D.tie.p);
+    }
     MB_CUDA(cudaGetLastError());
   }
   if (kernel_ms) {

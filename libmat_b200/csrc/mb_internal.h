@@ -73,6 +73,18 @@ struct PinBuf {
     cap = bytes + bytes / 8 + 256;
     return p;
   }
+  // grow while keeping the first `keep` bytes (streamed results whose total size is only known at the end)
+  void* reserve_keep(size_t bytes, size_t keep) {
+    if (bytes <= cap) return p;
+    void* q = nullptr;
+    const size_t want = bytes + bytes / 4 + 256;
+    MB_CUDA(cudaMallocHost(&q, want));
+    if (p && keep) memcpy(q, p, keep);
+    if (p) cudaFreeHost(p);
+    p = q;
+    cap = want;
+    return p;
+  }
   void release() {
     if (p) cudaFreeHost(p);
     p = nullptr;
@@ -93,6 +105,18 @@ struct TetMeshDev {
   DevBuf<int> tet_sel;     // optional ascending list of tet ids to process (mb_set_tet_subset)
   int n_sel = 0;
   const int* sel_ptr() const { return n_sel > 0 ? tet_sel.p : nullptr; }
+};
+
+// K1 uniform grid over the sites (rpd_grid.cuh)
+struct GridDev {
+  const float4* site4;      // cell-sorted sites (x,y,z,w)
+  const int* sorted_id;     // original site id of sorted slot
+  const int* cell_off;      // R^3 + 1
+  const float* wmax0;       // R^3   max weight per fine cell (-inf if empty)
+  const float* wmax1;       // R1^3  max weight per coarse node (4^3 fine cells)
+  int R, R1;
+  float minx, miny, minz, h, inv_h;
+  float wmax_all;           // max weight over all sites
 };
 
 struct SitesDev {
@@ -123,6 +147,14 @@ struct RpdCounters {
 #define CNT_OVF_TETS 16
 #define CNT_WORK_CURSOR 17
 
+// mapped pinned host memory the kernels publish stage scalars into (rpd_kernels.cu: publish)
+struct HostScalars {
+  int n_pairs;
+  int pad_;
+  long long total_words;
+  RpdCounters counters;
+};
+
 struct mb_rpd_result {
   mb_ctx* ctx = nullptr;
   long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0, n_cand_overflow = 0, n_ovf_tets = 0, n_exact = 0;
@@ -135,7 +167,12 @@ struct mb_rpd_result {
   DevBuf<uint32_t> blob;       // ordered compact records
   DevBuf<long long> cell_off;  // n_cells+1 byte offsets into blob
   DevBuf<float> site_vol, site_bary, cell_vol;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> evs;  // 4 per processed tet span: start, after K2, after K3, after ordering
+  // streamed run (mb_rpd_run_to_host): the ordered records live in the context's pinned host buffers only
+  bool host_only = false;
+  const uint32_t* host_blob = nullptr;
+  const long long* host_off = nullptr;
+  int n_spans = 1;
   // emission (K4)
   bool emitted = false;
   mb_emit_counts emit_counts = {0, 0, 0};
@@ -166,7 +203,16 @@ struct mb_ctx {
   TetMeshDev mesh;
   SitesDev sites;
   D2MDev d2m;
+  int d2m_variant = 0;  // 0 = queue-compacted kernel, 1 = warp-per-sample kernel (MB_D2M_VARIANT, A/B only)
   PinBuf pin_in, pin_out;
+  // streamed runs: second stream + double-buffered span results + pinned destination
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_gathered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  DevBuf<uint32_t> span_blob[2];
+  DevBuf<long long> span_off[2];
+  PinBuf pin_blob, pin_off;
+  HostScalars* hs = nullptr;
+  std::vector<cudaEvent_t> ev_pool;   // timing events recycled between runs
   // rpd scratch (reused across calls)
   DevBuf<int> tet_cnt, tet_off, pair_tet, pair_site, pair_local, cand_pad;
   DevBuf<int> cand_cnt;            // grid mode: #candidates per tet (cand_pad holds the lists)
@@ -199,6 +245,7 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
 void rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
                       const unsigned* site_flags, int n_site, const int* site_knn, int site_k);
 void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res);
+void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res);
 void rpd_sync(mb_ctx* ctx, mb_rpd_result* res);
 void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
 void rpd_volumes(mb_ctx* ctx, mb_rpd_result* res);  // a12: per-cell / per-site volume + barycentre sums

@@ -787,7 +787,9 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
           o += 3 * nb_p;
           const int ew = (3 * nb_e + 3) / 4;
           const uint32_t* se = reinterpret_cast<const uint32_t*>(S.edge);
-          for (int i = lane; i < ew; i += G) o[i] = se[i];
+          // the pad bytes of the last word are zeroed: the blob is deterministic byte for byte
+          const uint32_t tail_mask = (3 * nb_e) & 3 ? (0xffffffffu >> (8 * (4 - ((3 * nb_e) & 3)))) : 0xffffffffu;
+          for (int i = lane; i < ew; i += G) o[i] = (i == ew - 1) ? (se[i] & tail_mask) : se[i];
         }
       }
       if (lane == 0) {

@@ -18,17 +18,6 @@
 
 #define GRID_BIG_KCAP 2048  // survivor list of the overflow pass
 
-struct GridDev {
-  const float4* site4;      // cell-sorted sites (x,y,z,w)
-  const int* sorted_id;     // original site id of sorted slot
-  const int* cell_off;      // R^3 + 1
-  const float* wmax0;       // R^3   max weight per fine cell (-inf if empty)
-  const float* wmax1;       // R1^3  max weight per coarse node (4^3 fine cells)
-  int R, R1;
-  float minx, miny, minz, h, inv_h;
-  float wmax_all;           // max weight over all sites
-};
-
 __global__ void k_grid_count(const float4* __restrict__ site4, int n_site, GridDev G,
                              int* __restrict__ cnt, int* __restrict__ cell_of) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,14 +189,26 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
       if (e.w < bv3) { bv3 = e.w; bq3 = q; }
       if (m < bvu) { bvu = m; bqu = q; }
     };
-    if (lane < 27) {
-      const int i = ci + lane / 9 - 1, j = cj + (lane / 3) % 3 - 1, k = ck + lane % 3 - 1;
-      if (i >= 0 && j >= 0 && k >= 0 && i < R && j < R && k < R) {
-        const int c = (i * R + j) * R + k;
-        for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) evalq(q);
+    // rings of growing radius around the centroid's cell until a site is met (tets of the boundary
+    // layer can lie a few cells away from the nearest medial sphere)
+    float U = INFINITY;
+    for (int ar = 1; ar <= 4 && !isfinite(U); ar++) {
+      const int sd = 2 * ar + 1, nb = sd * sd * sd;
+      for (int b = 0; b < nb; b += 32) {
+        const int n = b + lane;
+        if (n < nb) {
+          const int di = n / (sd * sd) - ar, dj = (n / sd) % sd - ar, dk = n % sd - ar;
+          const int i = ci + di, j = cj + dj, k = ck + dk;
+          // the inner box was scanned (and found empty) by the previous ring
+          if (max(abs(di), max(abs(dj), abs(dk))) == ar || ar == 1)
+            if (i >= 0 && j >= 0 && k >= 0 && i < R && j < R && k < R) {
+              const int c = (i * R + j) * R + k;
+              for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) evalq(q);
+            }
+        }
       }
+      U = warp_min(bvu);
     }
-    float U = warp_min(bvu);
     if (!isfinite(U)) {
       // no site near the centroid (sparse or far-away sites): find U with a pyramid walk first
       for (int b1 = 0; b1 < n1; b1 += 32) {
@@ -319,18 +320,29 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
         Ue = U + 4e-6f * (fabsf(U) + 2.f * wall) + 1e-3f;
       }
     } else {
-      // ---- walk through the max-weight pyramid -----------------------------------------------------
-      for (int b1 = 0; b1 < n1; b1 += 32) {
+      // ---- walk through the max-weight pyramid, restricted to the coarse nodes that meet the box of
+      // radius rho (all of them when rho is not finite) ---------------------------------------------
+      int lo1i = 0, lo1j = 0, lo1k = 0, hi1i = R1 - 1, hi1j = R1 - 1, hi1k = R1 - 1;
+      if (isfinite(rho) && a < 2 * R) {
+        lo1i = max(0, (ci - a) >> 2); hi1i = min(R1 - 1, (ci + a) >> 2);
+        lo1j = max(0, (cj - a) >> 2); hi1j = min(R1 - 1, (cj + a) >> 2);
+        lo1k = max(0, (ck - a) >> 2); hi1k = min(R1 - 1, (ck + a) >> 2);
+      }
+      const int s1j = hi1j - lo1j + 1, s1k = hi1k - lo1k + 1;
+      const int nb1 = (hi1i - lo1i + 1) * s1j * s1k;
+      for (int b1 = 0; b1 < nb1; b1 += 32) {
         const int n = b1 + lane;
         bool keep = false;
-        if (n < n1) {
-          const int k1 = n % R1, j1 = (n / R1) % R1, i1 = n / (R1 * R1);
+        int node = 0;
+        if (n < nb1) {
+          const int i1 = lo1i + n / (s1j * s1k), j1 = lo1j + (n / s1k) % s1j, k1 = lo1k + n % s1k;
+          node = (i1 * R1 + j1) * R1 + k1;
           const float d = fmaxf(0.f, sqrtf(box_dist2(gx, gy, gz, G, i1, j1, k1, H1)) * 0.9999f - Rt);
-          keep = d * d - G.wmax1[n] <= Ue;
+          keep = d * d - G.wmax1[node] <= Ue;
         }
         unsigned m1 = __ballot_sync(0xffffffffu, keep);
         while (m1) {
-          const int n_ = b1 + __ffs(m1) - 1;
+          const int n_ = __shfl_sync(0xffffffffu, node, __ffs(m1) - 1);
           m1 &= m1 - 1;
           const int k1 = n_ % R1, j1 = (n_ / R1) % R1, i1 = n_ / (R1 * R1);
           for (int half = 0; half < 2; half++) {

@@ -268,7 +268,7 @@ __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* 
                          const int* __restrict__ pair_words, const long long* __restrict__ word_off,
                          const int* __restrict__ cell_idx, long long n_pairs,
                          uint32_t* __restrict__ blob, long long* __restrict__ cell_off,
-                         long long total_words, long long n_cells) {
+                         long long total_words, long long n_cells, long long base_bytes) {
   // 8 lanes per record
   const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int lane = threadIdx.x & 7;
@@ -280,8 +280,8 @@ __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* 
   for (int i = lane; i < words; i += 8) blob[dst + i] = src[i];
   if (lane == 0) {
     const int c = cell_idx[g];
-    cell_off[c] = dst * 4;
-    if (c == n_cells - 1) cell_off[n_cells] = total_words * 4;
+    cell_off[c] = base_bytes + dst * 4;
+    if (c == n_cells - 1) cell_off[n_cells] = base_bytes + total_words * 4;
   }
 }
 
@@ -342,9 +342,16 @@ static GridDev grid_build(mb_ctx* ctx) {
   return G;
 }
 
+// a contiguous piece of the processed tets: [first, first+count) of the mesh, or count entries of a
+// device-resident id list (mb_set_tet_subset); all per-tet scratch is indexed relative to it
+struct TetSpan {
+  int first, count;
+  const int* sel;
+};
+
 // fills cand_pad / cand_cnt (all candidates) and tet_cnt (flagged candidates = pairs)
 template <int KCAP>
-static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, int t_first, int t_count, int kcap_out) {
+static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan& sp, int kcap_out) {
   TetMeshDev& M = ctx->mesh;
   cudaStream_t s = ctx->stream;
   unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->counters.p);
@@ -358,43 +365,41 @@ static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, int t_first, i
     attr_set = true;
   }
   // fast pass: one warp per tet, persistent-style grid (a multiple of the SM count)
-  const int want = (t_count + WARPS - 1) / WARPS;
+  const int want = (sp.count + WARPS - 1) / WARPS;
   const int blocks = std::max(1, std::min(want, ctx->sm_count * 32));
   ctx->n_launches++;
   k_grid_candidates<KCAP, WARPS, false><<<blocks, 32 * WARPS, smem, s>>>(
-      M.vert4.p, M.tet_idx.p, t_first, t_count, ctx->mesh.sel_ptr(), G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
+      M.vert4.p, M.tet_idx.p, sp.first, sp.count, sp.sel, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
       ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p);
   // overflow pass: reads the number of handed-over tets on the device (usually zero -> returns)
   ctx->n_launches++;
   k_grid_candidates<GRID_BIG_KCAP, 1, true><<<ctx->sm_count * 2, 32, smem_big, s>>>(
-      M.vert4.p, M.tet_idx.p, t_first, t_count, ctx->mesh.sel_ptr(), G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
+      M.vert4.p, M.tet_idx.p, sp.first, sp.count, sp.sel, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
       ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p);
   MB_CUDA(cudaGetLastError());
 }
 
-static void grid_candidates(mb_ctx* ctx, int t_first, int t_count, int grid_k) {
-  GridDev G = grid_build(ctx);
+static void grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan& sp, int grid_k) {
   // grid_k = expected candidates per tet: capacity of the fast pass's shared-memory survivor list
   // (32 / 96 / 256; longer lists go through the big-list pass) and row stride of the output
   const int kcap = (grid_k > 96) ? 256 : 96;
   ctx->cand_kcap = kcap;
-  ctx->cand_pad.reserve((size_t)t_count * kcap);
-  ctx->cand_cnt.reserve((size_t)t_count + 1);
-  ctx->ovf_list.reserve((size_t)t_count + 1);
+  ctx->cand_pad.reserve((size_t)sp.count * kcap);
+  ctx->cand_cnt.reserve((size_t)sp.count + 1);
+  ctx->ovf_list.reserve((size_t)sp.count + 1);
   if (grid_k > 0 && grid_k <= 32)
-    launch_grid_candidates<32>(ctx, G, t_first, t_count, kcap);
+    launch_grid_candidates<32>(ctx, G, sp, kcap);
   else if (kcap == 96)
-    launch_grid_candidates<96>(ctx, G, t_first, t_count, kcap);
+    launch_grid_candidates<96>(ctx, G, sp, kcap);
   else
-    launch_grid_candidates<256>(ctx, G, t_first, t_count, kcap);
+    launch_grid_candidates<256>(ctx, G, sp, kcap);
 }
 
-static void grid_fill_pairs(mb_ctx* ctx, int t_first, int t_count, long long n_pairs) {
-  (void)n_pairs;
+static void grid_fill_pairs(mb_ctx* ctx, const TetSpan& sp) {
   cudaStream_t s = ctx->stream;
-  const int blocks = (t_count + 7) / 8;
+  const int blocks = (sp.count + 7) / 8;
   ctx->n_launches++;
-  k_grid_fill<<<blocks, 256, 0, s>>>(t_first, t_count, ctx->mesh.sel_ptr(), ctx->cand_kcap, ctx->cand_pad.p,
+  k_grid_fill<<<blocks, 256, 0, s>>>(sp.first, sp.count, sp.sel, ctx->cand_kcap, ctx->cand_pad.p,
                                      ctx->cand_cnt.p, ctx->tet_off.p, ctx->sites.flags.p, ctx->pair_tet.p,
                                      ctx->pair_site.p, ctx->pair_local.p);
   MB_CUDA(cudaGetLastError());
@@ -421,9 +426,11 @@ static void launch_clip(mb_ctx* ctx, const ClipArgs& A) {
     MB_CUDA(cudaFuncSetAttribute(k_clip<G, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  int per_sm = 0;
-  MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip<G, PT>, 128, smem));
-  if (per_sm < 1) per_sm = 1;
+  static int per_sm = 0;
+  if (per_sm < 1) {
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip<G, PT>, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
   // persistent grid: every SM fully resident, warps pull chunks of pairs from a global cursor
   long long want = (A.n_pairs + groups - 1) / groups;
   long long grid = std::min<long long>(want, (long long)ctx->sm_count * per_sm);
@@ -433,49 +440,85 @@ static void launch_clip(mb_ctx* ctx, const ClipArgs& A) {
   MB_CUDA(cudaGetLastError());
 }
 
-void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
+// Scalars the host needs between stages (pair count, K3 counters, record words) are PUBLISHED by a tiny
+// kernel into mapped pinned host memory instead of being fetched with cudaMemcpy: a D2H copy on the
+// compute stream would queue behind the streamed run's bulk record copies on the copy engine and
+// serialise the two streams.
+__global__ void k_publish_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst_mapped, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst_mapped[i] = src[i];
+  __threadfence_system();
+}
+
+static void publish(mb_ctx* ctx, const void* src, void* dst_mapped, size_t bytes) {
+  ctx->n_launches++;
+  k_publish_words<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(src),
+                                             reinterpret_cast<uint32_t*>(dst_mapped), (int)(bytes / 4));
+  MB_CUDA(cudaGetLastError());
+}
+
+static HostScalars* host_scalars(mb_ctx* ctx) {
+  if (!ctx->hs) MB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->hs), sizeof(HostScalars), cudaHostAllocMapped));
+  return ctx->hs;
+}
+
+static cudaEvent_t take_event(mb_ctx* ctx) {
+  cudaEvent_t e = nullptr;
+  if (!ctx->ev_pool.empty()) {
+    e = ctx->ev_pool.back();
+    ctx->ev_pool.pop_back();
+  } else {
+    MB_CUDA(cudaEventCreate(&e));
+  }
+  return e;
+}
+
+struct SpanStats {
+  long long n_pairs = 0, n_cells = 0, total_words = 0;
+};
+
+// One span through K2 -> K3 -> ordering.  The ordered compact records go to `blob`, the per-cell byte
+// offsets (+ base_bytes) to `cell_off`; counters are added to `res`.  Four timing events are appended
+// to res->evs.  Returns with the ordering kernels enqueued (not synchronised).
+static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res, const TetSpan& sp,
+                              const GridDev* grid, DevBuf<uint32_t>& blob, DevBuf<long long>& cell_off,
+                              long long base_bytes) {
   TetMeshDev& M = ctx->mesh;
   SitesDev& S = ctx->sites;
   cudaStream_t s = ctx->stream;
-  MB_REQUIRE(M.n_tet > 0, MB_ERR_STATE, "mb_set_tetmesh must be called before mb_rpd3d");
-  MB_REQUIRE(S.n_site > 0, MB_ERR_STATE, "no sites uploaded");
-  const int t_first = M.n_sel > 0 ? 0 : M.range_first;
-  const int t_count = M.n_sel > 0 ? M.n_sel : (M.range_count < 0 ? M.n_tet - t_first : M.range_count);
-  MB_REQUIRE(t_first >= 0 && t_count >= 0 && (M.n_sel > 0 || t_first + t_count <= M.n_tet), MB_ERR_ARG, "bad tet range");
-  int G = opts && opts->lanes_per_cell ? opts->lanes_per_cell : 8;
-  MB_REQUIRE(G == 4 || G == 8 || G == 16 || G == 32, MB_ERR_ARG, "lanes_per_cell must be 4, 8, 16 or 32");
-  res->ctx = ctx;
-  res->n_site = S.n_site;
-  res->want_volumes = opts && opts->want_volumes;
-  for (int i = 0; i < 5; i++)
-    if (!res->ev[i]) MB_CUDA(cudaEventCreate(&res->ev[i]));
+  const int t_count = sp.count;
+  const int G = opts && opts->lanes_per_cell ? opts->lanes_per_cell : 8;
+  HostScalars* hs = host_scalars(ctx);
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; i++) {
+    ev[i] = take_event(ctx);
+    res->evs.push_back(ev[i]);
+  }
   ctx->counters.reserve(1);
   MB_CUDA(cudaMemsetAsync(ctx->counters.p, 0, sizeof(RpdCounters), s));
-  MB_CUDA(cudaEventRecord(res->ev[0], s));
+  MB_CUDA(cudaEventRecord(ev[0], s));
 
-  // ---- K1/K2: candidate (tet, site) pairs ----------------------------------------------------
+  // ---- K2: candidate (tet, site) pairs ---------------------------------------------------------
   long long n_pairs = 0;
   ctx->tet_cnt.reserve((size_t)t_count + 1);
   ctx->tet_off.reserve((size_t)t_count + 1);
-  const bool grid_cands = !S.given || (opts && opts->grid_candidates);
+  const bool grid_cands = grid != nullptr;
   if (t_count > 0) {
     if (!grid_cands) {
       ctx->cand_pad.reserve((size_t)t_count * CAND_PAD);
       const int blocks = (t_count + 7) / 8;
       ctx->n_launches++;
-      k_cand_given<false><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, M.sel_ptr(), S.site4.p,
+      k_cand_given<false><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, sp.first, t_count, sp.sel, S.site4.p,
                                                  S.flags.p, S.n_site, S.nbr.p, S.site_k, ctx->tet_cnt.p,
                                                  ctx->cand_pad.p, nullptr, nullptr, nullptr);
       MB_CUDA(cudaGetLastError());
     } else {
-      grid_candidates(ctx, t_first, t_count, opts ? opts->grid_k : 0);  // fills tet_cnt + cand_list pad
+      grid_candidates(ctx, *grid, sp, opts ? opts->grid_k : 0);  // fills tet_cnt + cand_list pad
     }
     MB_CUDA(cudaMemsetAsync(ctx->tet_cnt.p + t_count, 0, sizeof(int), s));
     exclusive_scan<int>(ctx, ctx->tet_cnt.p, ctx->tet_off.p, (long long)t_count + 1);
-    int total = 0;
-    MB_CUDA(cudaMemcpyAsync(&total, ctx->tet_off.p + t_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    publish(ctx, ctx->tet_off.p + t_count, &hs->n_pairs, sizeof(int));
     MB_CUDA(cudaStreamSynchronize(s));
-    n_pairs = total;
+    n_pairs = hs->n_pairs;
     ctx->pair_tet.reserve((size_t)n_pairs + 1);
     ctx->pair_site.reserve((size_t)n_pairs + 1);
     ctx->pair_local.reserve((size_t)n_pairs + 1);
@@ -483,18 +526,17 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
       if (!grid_cands) {
         const int blocks = (t_count + 7) / 8;
         ctx->n_launches++;
-        k_cand_given<true><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, t_first, t_count, M.sel_ptr(), S.site4.p,
+        k_cand_given<true><<<blocks, 256, 0, s>>>(M.vert4.p, M.tet_idx.p, sp.first, t_count, sp.sel, S.site4.p,
                                                   S.flags.p, S.n_site, S.nbr.p, S.site_k, ctx->tet_cnt.p,
                                                   ctx->cand_pad.p, ctx->tet_off.p, ctx->pair_tet.p,
                                                   ctx->pair_site.p);
         MB_CUDA(cudaGetLastError());
       } else {
-        grid_fill_pairs(ctx, t_first, t_count, n_pairs);
+        grid_fill_pairs(ctx, sp);
       }
     }
   }
-  MB_CUDA(cudaEventRecord(res->ev[1], s));
-  res->n_pairs = n_pairs;
+  MB_CUDA(cudaEventRecord(ev[1], s));
 
   // ---- K3: clip ---------------------------------------------------------------------------------
   ctx->pair_status.reserve((size_t)n_pairs + 1);
@@ -523,7 +565,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
       A.nbr_stride = ctx->cand_kcap;
       A.nbr_cnt = ctx->cand_cnt.p;
     }
-    A.tet_first = t_first;
+    A.tet_first = sp.first;
     A.pair_tet = ctx->pair_tet.p;
     A.pair_site = ctx->pair_site.p;
     A.pair_local = ctx->pair_local.p;
@@ -543,9 +585,10 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
       pt ? launch_clip<16, true>(ctx, A) : launch_clip<16, false>(ctx, A);
     else
       pt ? launch_clip<32, true>(ctx, A) : launch_clip<32, false>(ctx, A);
-    MB_CUDA(cudaEventRecord(res->ev[2], s));
-    MB_CUDA(cudaMemcpyAsync(&hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaEventRecord(ev[2], s));
+    publish(ctx, ctx->counters.p, &hs->counters, sizeof(RpdCounters));
     MB_CUDA(cudaStreamSynchronize(s));
+    hc = hs->counters;
     if (hc.blob_words <= ctx->scratch.cap) break;
     // scratch too small: rerun K3 with the measured need (rare; statuses are recomputed)
     scratch_words = (size_t)hc.blob_words + (1u << 20);
@@ -556,22 +599,32 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
       MB_CUDA(cudaMemsetAsync(c + 5, 0, 11 * sizeof(unsigned long long), s));
       MB_CUDA(cudaMemsetAsync(c + CNT_WORK_CURSOR, 0, sizeof(unsigned long long), s));
     }
-    MB_CUDA(cudaEventRecord(res->ev[1], s));
+    MB_CUDA(cudaEventRecord(ev[1], s));
   }
   if (n_pairs == 0) {
-    memset(&hc, 0, sizeof hc);
-    MB_CUDA(cudaEventRecord(res->ev[2], s));
+    if (t_count > 0) {  // candidate-stage counters of a span without pairs
+      publish(ctx, ctx->counters.p, &hs->counters, sizeof(RpdCounters));
+      MB_CUDA(cudaStreamSynchronize(s));
+      hc = hs->counters;
+    } else {
+      memset(&hc, 0, sizeof hc);
+    }
+    MB_CUDA(cudaEventRecord(ev[2], s));
   }
-  res->n_cells = (long)hc.n_valid;
-  res->n_clips = (long)hc.n_clips;
-  res->n_culled = (long)hc.n_culled;
-  res->n_exact = (long)hc.pad[0];
-  res->n_cand_overflow = (long)hc.n_cand_overflow;
-  res->n_ovf_tets = (long)hc.n_ovf_tets;
-  for (int i = 0; i < 10; i++) res->hist[i] = (long)hc.hist[i];
+  SpanStats st;
+  st.n_pairs = n_pairs;
+  st.n_cells = (long long)hc.n_valid;
+  res->n_pairs += (long)n_pairs;
+  res->n_cells += (long)hc.n_valid;
+  res->n_clips += (long)hc.n_clips;
+  res->n_culled += (long)hc.n_culled;
+  res->n_exact += (long)hc.pad[0];
+  res->n_cand_overflow += (long)hc.n_cand_overflow;
+  res->n_ovf_tets += (long)hc.n_ovf_tets;
+  for (int i = 0; i < 10; i++) res->hist[i] += (long)hc.hist[i];
 
   // ---- ordering: scan + gather into (tet, site) order -------------------------------------------
-  res->cell_off.reserve((size_t)res->n_cells + 1);
+  cell_off.reserve((size_t)st.n_cells + 1);
   long long total_words = 0;
   if (n_pairs > 0) {
     DevBuf<long long>& word_off = ctx->word_off;
@@ -585,31 +638,151 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
     k_valid_flags<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, s>>>(ctx->pair_words.p, n_pairs + 1, valid.p);
     exclusive_scan<long long>(ctx, ctx->pair_words.p, word_off.p, n_pairs + 1);
     exclusive_scan<int>(ctx, valid.p, cell_idx.p, n_pairs + 1);
-    MB_CUDA(cudaMemcpyAsync(&total_words, word_off.p + n_pairs, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    publish(ctx, word_off.p + n_pairs, &hs->total_words, sizeof(long long));
     MB_CUDA(cudaStreamSynchronize(s));
-    res->blob.reserve((size_t)total_words + 4);
+    total_words = hs->total_words;
+    blob.reserve((size_t)total_words + 4);
     if (total_words > 0) {
       ctx->n_launches++;
       k_gather<<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
           ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, word_off.p, cell_idx.p, n_pairs,
-          res->blob.p, res->cell_off.p, total_words, res->n_cells);
+          blob.p, cell_off.p, total_words, st.n_cells, base_bytes);
       MB_CUDA(cudaGetLastError());
     }
   }
-  if (res->n_cells == 0) MB_CUDA(cudaMemsetAsync(res->cell_off.p, 0, sizeof(long long), s));
-  res->compact_bytes = (long)(total_words * 4);
-  MB_CUDA(cudaEventRecord(res->ev[3], s));
+  if (st.n_cells == 0) MB_CUDA(cudaMemcpyAsync(cell_off.p, &base_bytes, sizeof(long long), cudaMemcpyHostToDevice, s));
+  st.total_words = total_words;
+  MB_CUDA(cudaEventRecord(ev[3], s));
+  return st;
+}
+
+static void run_prologue(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res, int& t_first, int& t_count) {
+  TetMeshDev& M = ctx->mesh;
+  SitesDev& S = ctx->sites;
+  MB_REQUIRE(M.n_tet > 0, MB_ERR_STATE, "mb_set_tetmesh must be called before mb_rpd3d");
+  MB_REQUIRE(S.n_site > 0, MB_ERR_STATE, "no sites uploaded");
+  t_first = M.n_sel > 0 ? 0 : M.range_first;
+  t_count = M.n_sel > 0 ? M.n_sel : (M.range_count < 0 ? M.n_tet - t_first : M.range_count);
+  MB_REQUIRE(t_first >= 0 && t_count >= 0 && (M.n_sel > 0 || t_first + t_count <= M.n_tet), MB_ERR_ARG, "bad tet range");
+  const int G = opts && opts->lanes_per_cell ? opts->lanes_per_cell : 8;
+  MB_REQUIRE(G == 4 || G == 8 || G == 16 || G == 32, MB_ERR_ARG, "lanes_per_cell must be 4, 8, 16 or 32");
+  res->ctx = ctx;
+  res->n_site = S.n_site;
+  res->want_volumes = opts && opts->want_volumes;
+  res->n_pairs = res->n_cells = res->n_clips = res->n_culled = res->n_exact = 0;
+  res->n_cand_overflow = res->n_ovf_tets = 0;
+  for (int i = 0; i < 10; i++) res->hist[i] = 0;
+}
+
+void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
+  int t_first, t_count;
+  run_prologue(ctx, opts, res, t_first, t_count);
+  const bool grid_cands = !ctx->sites.given || (opts && opts->grid_candidates);
+  GridDev G;
+  // K1 is timed with the span's candidate stage: the span's first event is recorded after it, so
+  // record an extra leading event here
+  cudaEvent_t e0 = take_event(ctx);
+  MB_CUDA(cudaEventRecord(e0, ctx->stream));
+  if (grid_cands && t_count > 0) G = grid_build(ctx);
+  const TetSpan sp = {t_first, t_count, ctx->mesh.sel_ptr()};
+  const SpanStats st = rpd_run_span(ctx, opts, res, sp, (grid_cands && t_count > 0) ? &G : nullptr, res->blob,
+                                    res->cell_off, 0);
+  // fold K1 into the candidate stage: replace the span's start event by e0
+  ctx->ev_pool.push_back(res->evs[0]);
+  res->evs[0] = e0;
+  res->n_spans = 1;
+  res->host_only = false;
+  res->compact_bytes = (long)(st.total_words * 4);
   if (res->want_volumes) rpd_volumes(ctx, res);
+  res->synced = false;
+}
+
+// Streamed run: the processed tets are cut into n_chunks spans; while span c+1 is searched and clipped
+// on the compute stream, the ordered records of span c travel to pinned host memory on a second
+// stream (PCIe D2H overlapped with K2/K3).  Spans are contiguous in tet order, so the concatenation
+// is the global (tet, site) order and the offsets / ids are those of the one-shot run.
+void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res) {
+  int t_first, t_count;
+  run_prologue(ctx, opts, res, t_first, t_count);
+  MB_REQUIRE(!res->want_volumes, MB_ERR_ARG, "want_volumes is not available in the streamed run");
+  cudaStream_t s = ctx->stream;
+  if (!ctx->copy_stream) {
+    MB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+      MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_gathered[b], cudaEventDisableTiming));
+      MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t cs = ctx->copy_stream;
+  if (n_chunks <= 0) n_chunks = std::max(1, std::min(32, (t_count + 49151) / 49152));
+  n_chunks = std::max(1, std::min(n_chunks, std::max(1, t_count)));
+  const bool grid_cands = !ctx->sites.given || (opts && opts->grid_candidates);
+  GridDev G;
+  cudaEvent_t e0 = take_event(ctx);
+  MB_CUDA(cudaEventRecord(e0, s));
+  if (grid_cands && t_count > 0) G = grid_build(ctx);
+  long long acc_bytes = 0, acc_cells = 0;
+  // destination: kept from the previous run; first run sizes it from the first span
+  if (!ctx->pin_off.p) ctx->pin_off.reserve_keep(sizeof(long long) * 1024, 0);
+  reinterpret_cast<long long*>(ctx->pin_off.p)[0] = 0;
+  for (int c = 0; c < n_chunks; c++) {
+    const int c_first = (int)((long long)t_count * c / n_chunks);
+    const int c_count = (int)((long long)t_count * (c + 1) / n_chunks) - c_first;
+    const TetSpan sp = ctx->mesh.n_sel > 0 ? TetSpan{0, c_count, ctx->mesh.tet_sel.p + c_first}
+                                           : TetSpan{t_first + c_first, c_count, nullptr};
+    const int b = c & 1;
+    if (c >= 2) MB_CUDA(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));  // span c-2 has left the buffer
+    const SpanStats st = rpd_run_span(ctx, opts, res, sp, (grid_cands && c_count > 0) ? &G : nullptr,
+                                      ctx->span_blob[b], ctx->span_off[b], acc_bytes);
+    if (c == 0) {
+      ctx->ev_pool.push_back(res->evs[0]);
+      res->evs[0] = e0;
+    }
+    const long long bytes = st.total_words * 4;
+    // pinned destination large enough for this span (first run: extrapolate from the spans so far)
+    const size_t need_blob = (size_t)(acc_bytes + bytes), need_off = sizeof(long long) * (size_t)(acc_cells + st.n_cells + 1);
+    if (need_blob > ctx->pin_blob.cap || need_off > ctx->pin_off.cap) {
+      MB_CUDA(cudaStreamSynchronize(cs));  // earlier spans have landed: safe to move them
+      const double scale = 1.1 * (double)t_count / (double)std::max(1, c_first + c_count);
+      ctx->pin_blob.reserve_keep(std::max(need_blob, (size_t)(need_blob * scale)), (size_t)acc_bytes);
+      ctx->pin_off.reserve_keep(std::max(need_off, (size_t)(need_off * scale)), sizeof(long long) * (size_t)(acc_cells + 1));
+    }
+    MB_CUDA(cudaEventRecord(ctx->ev_gathered[b], s));
+    MB_CUDA(cudaStreamWaitEvent(cs, ctx->ev_gathered[b], 0));
+    if (bytes > 0)
+      MB_CUDA(cudaMemcpyAsync((unsigned char*)ctx->pin_blob.p + acc_bytes, ctx->span_blob[b].p, (size_t)bytes,
+                              cudaMemcpyDeviceToHost, cs));
+    if (st.n_cells > 0)
+      MB_CUDA(cudaMemcpyAsync(reinterpret_cast<long long*>(ctx->pin_off.p) + acc_cells, ctx->span_off[b].p,
+                              sizeof(long long) * (size_t)(st.n_cells + 1), cudaMemcpyDeviceToHost, cs));
+    MB_CUDA(cudaEventRecord(ctx->ev_copied[b], cs));
+    acc_bytes += bytes;
+    acc_cells += st.n_cells;
+  }
+  MB_CUDA(cudaStreamSynchronize(cs));
+  MB_CUDA(cudaStreamSynchronize(s));
+  res->n_spans = n_chunks;
+  res->host_only = true;
+  res->host_blob = reinterpret_cast<const uint32_t*>(ctx->pin_blob.p);
+  res->host_off = reinterpret_cast<const long long*>(ctx->pin_off.p);
+  res->compact_bytes = (long)acc_bytes;
   res->synced = false;
 }
 
 void rpd_sync(mb_ctx* ctx, mb_rpd_result* res) {
   MB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (!res->synced && res->ev[0]) {
-    MB_CUDA(cudaEventElapsedTime(&res->ms[0], res->ev[0], res->ev[1]));
-    MB_CUDA(cudaEventElapsedTime(&res->ms[1], res->ev[1], res->ev[2]));
-    MB_CUDA(cudaEventElapsedTime(&res->ms[2], res->ev[2], res->ev[3]));
-    MB_CUDA(cudaEventElapsedTime(&res->ms[3], res->ev[0], res->ev[3]));
+  if (!res->synced && !res->evs.empty()) {
+    float acc[3] = {0, 0, 0};
+    for (size_t i = 0; i + 3 < res->evs.size(); i += 4)
+      for (int k = 0; k < 3; k++) {
+        float ms = 0.f;
+        MB_CUDA(cudaEventElapsedTime(&ms, res->evs[i + k], res->evs[i + k + 1]));
+        acc[k] += ms;
+      }
+    res->ms[0] = acc[0];
+    res->ms[1] = acc[1];
+    res->ms[2] = acc[2];
+    MB_CUDA(cudaEventElapsedTime(&res->ms[3], res->evs.front(), res->evs.back()));
     res->synced = true;
   }
 }

@@ -22,9 +22,10 @@ def _c(a, dt):
 class RpdResult:
     """Handle on the device-resident result of one RPD run (mb_rpd_result)."""
 
-    def __init__(self, ctx: "Context", handle):
+    def __init__(self, ctx: "Context", handle, host_ptrs=None):
         self.ctx = ctx
         self._h = handle
+        self._host_ptrs = host_ptrs  # streamed run: (blob address, offsets address) in pinned host memory
         lib = ctx.lib
         a, b, c = C.c_long(), C.c_long(), C.c_long()
         ctx._check(lib.mb_rpd_count(handle, C.byref(a), C.byref(b), C.byref(c)))
@@ -42,6 +43,7 @@ class RpdResult:
         nb = C.c_long()
         ctx._check(lib.mb_rpd_compact_bytes(handle, C.byref(nb)))
         self.compact_bytes = nb.value
+        self.n_spans = int(lib.mb_rpd_spans(handle))
 
     def records(self) -> np.ndarray:
         """Cells sorted by (tet, site) in the ConvexCellTransfer layout (id = index)."""
@@ -62,6 +64,16 @@ class RpdResult:
         blob = np.zeros(max(1, self.compact_bytes // 4), dtype=np.uint32)
         offs = np.zeros(self.n_cells + 1, dtype=np.int64)
         self.ctx._check(self.ctx.lib.mb_rpd_fetch_compact(self._h, ptr(blob), ptr(offs)))
+        return blob, offs
+
+    def host_compact(self):
+        """streamed run: zero-copy numpy views (blob uint32, offsets int64) of the library's pinned host
+        result; valid until the next streamed run on the context"""
+        assert self._host_ptrs is not None, "not a streamed result"
+        bp, op = self._host_ptrs
+        nw = self.compact_bytes // 4
+        blob = np.ctypeslib.as_array(C.cast(bp, C.POINTER(C.c_uint32)), shape=(max(nw, 1),))[:nw]
+        offs = np.ctypeslib.as_array(C.cast(op, C.POINTER(C.c_int64)), shape=(self.n_cells + 1,))
         return blob, offs
 
     def site_volumes(self):
@@ -196,6 +208,14 @@ class Context:
         self._check(self.lib.mb_rpd_run(self._ctx, C.byref(opts), C.byref(h)))
         self._check(self.lib.mb_rpd_sync(self._ctx, h))
         return RpdResult(self, h)
+
+    def run_to_host(self, n_chunks=0, lanes_per_cell=0, grid_k=0, grid_candidates=False) -> RpdResult:
+        """streamed run (mb_rpd_run_to_host): D2H of span c overlaps the kernels of span c+1; the complete
+        compact result is in pinned host memory on return (RpdResult.host_compact())"""
+        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), 0, int(grid_candidates))
+        h, bp, op = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.mb_rpd_run_to_host(self._ctx, C.byref(opts), int(n_chunks), C.byref(h), C.byref(bp), C.byref(op)))
+        return RpdResult(self, h, host_ptrs=(bp.value, op.value))
 
     def compute_clipped_voro_diagram(self, site, site_weights, site_flags, site_knn=None, site_k=0,
                                      **opts) -> RpdResult:

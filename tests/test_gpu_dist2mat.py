@@ -74,3 +74,35 @@ def test_nan_swallowing_clamp(ctx):
     r, cid, _ = ctx.compute_closest_dist2mat(sph, np.array([[0.3, 0.4, 0]], np.float32), np.zeros(1, np.uint32),
                                              np.ones(1, np.uint32), np.array([[-1, 0, 1]], np.int32))
     assert abs(r[0] - 0.4) < 1e-6
+
+
+def test_queue_kernel_equals_warp_per_sample_kernel(synth, monkeypatch):
+    """the queue-compacted kernel (default) and the warp-per-sample kernel (MB_D2M_VARIANT=1, the
+    reference's lane <-> primitive layout literally) must agree bit for bit: distances, argmin ids under
+    the block tie rule, tie flags -- including lists longer than a warp stride, longer than the
+    shared-memory batch (768 slots -> direct path), empty lists and ragged offsets."""
+    from libmat_b200.rpd import Context
+
+    d = synth.make_dist2mat(30000)
+    rng = np.random.default_rng(7)
+    n_prim = d.prims.shape[0]
+    # ragged / long lists appended: counts 0, 1, 33, 70, 700, 800, 2000 at random offsets
+    extra_cnt = np.array([0, 1, 33, 70, 700, 800, 2000, 5, 0, 64, 32, 31] * 8, np.uint32)
+    extra_off = rng.integers(0, n_prim - 2100, len(extra_cnt)).astype(np.uint32)
+    pos = d.samples[rng.integers(0, len(d.samples), len(extra_cnt))]
+    samples = np.concatenate([d.samples, pos]).astype(np.float32)
+    offset = np.concatenate([d.offset, extra_off]).astype(np.uint32)
+    count = np.concatenate([d.count, extra_cnt]).astype(np.uint32)
+    perm = rng.permutation(len(samples))  # long lists scattered through the batches
+    samples, offset, count = samples[perm], offset[perm], count[perm]
+    out = []
+    for variant in ("0", "1"):
+        monkeypatch.setenv("MB_D2M_VARIANT", variant)
+        c = Context(0)
+        out.append(c.compute_closest_dist2mat(d.spheres, samples, offset, count, d.prims))
+        c.close()
+    (r0, c0, t0), (r1, c1, t1) = out
+    assert np.array_equal(r0.view(np.uint32), r1.view(np.uint32))
+    assert np.array_equal(c0, c1)
+    assert np.array_equal(t0, t1)
+    assert (c0[count == 0] == -1).all() and (r0[count == 0] == np.float32(1e16)).all()

@@ -1,0 +1,93 @@
+"""Streamed run (mb_rpd_run_to_host): the chunked, D2H-overlapped pipeline must deliver exactly the
+one-shot result -- same blob bytes, same offsets, same counters -- for any chunk count, in both modes,
+for tet ranges and tet subsets."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def one_shot(ctx, **kw):
+    res = ctx.run(**kw)
+    blob, offs = res.compact()
+    out = (blob[: res.compact_bytes // 4].copy(), offs.copy(), res.n_cells, res.n_pairs, res.status_histogram.copy())
+    res.free()
+    return out
+
+
+def streamed(ctx, n_chunks, want_records=False, **kw):
+    res = ctx.run_to_host(n_chunks=n_chunks, **kw)
+    blob, offs = res.host_compact()
+    out = (blob.copy(), offs.copy(), res.n_cells, res.n_pairs, res.status_histogram.copy())
+    recs = res.records() if want_records else None
+    res.free()
+    return out, recs
+
+
+def same(a, b):
+    assert a[2] == b[2] and a[3] == b[3], (a[2:4], b[2:4])
+    assert np.array_equal(a[4], b[4])
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(a[0], b[0])
+
+
+@pytest.mark.parametrize("n_chunks", [1, 2, 3, 7, 0])
+def test_stream_grid_mode(ctx, cfg1_rt, n_chunks):
+    mesh, sites, knn, k = cfg1_rt
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, None, 0)
+    want = one_shot(ctx)
+    got, _ = streamed(ctx, n_chunks)
+    same(want, got)
+    got2, _ = streamed(ctx, n_chunks)  # second run reuses the pinned destination
+    same(want, got2)
+
+
+@pytest.mark.parametrize("n_chunks", [1, 4])
+def test_stream_given_mode_records(ctx, O, cfg1, cfg1_oracle, n_chunks):
+    mesh, sites, knn, k = cfg1
+    pt, ps, ra, sa = cfg1_oracle
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, knn, k)
+    want = one_shot(ctx)
+    got, recs = streamed(ctx, n_chunks, want_records=True)
+    same(want, got)
+    ref = ra[ra["status"] == 4]
+    d = O.defined_equal(ref, recs)
+    assert all(v == 0 for f, v in d.items() if f != "cells_compared"), d
+    assert np.array_equal(recs["id"], np.arange(len(recs)))
+
+
+def test_stream_range_and_subset(ctx, cfg1_rt):
+    mesh, sites, knn, k = cfg1_rt
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, None, 0)
+    ctx.set_tet_range(1000, 7001)
+    want = one_shot(ctx)
+    got, _ = streamed(ctx, 5)
+    same(want, got)
+    ctx.set_tet_range(0, -1)
+    ids = np.unique(np.random.default_rng(5).integers(0, mesh.n_tet, 3000)).astype(np.int32)
+    ctx.set_tet_subset(ids)
+    want = one_shot(ctx)
+    got, _ = streamed(ctx, 3)
+    same(want, got)
+    ctx.set_tet_subset(None)
+
+
+def test_stream_more_chunks_than_tets_and_guards(ctx, cfg1_rt):
+    from libmat_b200.capi import LibMatError
+    mesh, sites, knn, k = cfg1_rt
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, None, 0)
+    ctx.set_tet_range(10, 3)
+    want = one_shot(ctx)
+    res = ctx.run_to_host(n_chunks=9)
+    blob, offs = res.host_compact()
+    assert np.array_equal(want[0], blob) and np.array_equal(want[1], offs)
+    with pytest.raises(LibMatError):
+        res.pairs()
+    with pytest.raises(LibMatError):
+        res.emit(mesh.n_surf_faces - 1)
+    res.free()
+    ctx.set_tet_range(0, -1)
