@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5", "d2m"])
     ap.add_argument("--samples", type=int, default=0, help="dist2mat samples (config 3 is 10 000 000)")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the shards reach rank 0")
     ap.add_argument("--chunks", type=int, default=0, help="e2e leg: tet spans of the streamed run (0 = automatic)")
     ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -294,6 +295,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -394,13 +397,36 @@ def main():
     upload_sites()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    # ---- NCCL gather of the compact results on rank 0 (libmat_b200.dist: all-gather of the sizes, then a
-    # grouped send/recv over NVLink) -------------------------------------------------------------
+    # ---- multi-GPU result gather on rank 0 -----------------------------------------------------------------
+    # default ("p2p"): every rank's streamed run writes its ordered shard straight into rank 0's HBM through a
+    # CUDA-IPC peer mapping -- tet span c crosses NVLink by copy-engine DMA while span c+1 is clipped -- and
+    # one 16-byte-per-rank NCCL all-gather exchanges the shard directory (and is the completion barrier).
+    # "nccl": one-shot run, then an all-gather of the sizes + grouped NCCL send/recv (libmat_b200.dist).
     gather_buf = {"t": None}
+    sink_dev = sink_host = None
+    gather_mode = args.gather if world > 1 else "none"
+    if world > 1:
+        from libmat_b200.dist import ShardSink
+        r0 = ctx.run(lanes_per_cell=args.lanes)
+        t = torch.tensor([r0.compact_bytes, r0.n_cells], dtype=torch.int64, device=dev)
+        r0.free()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cap_b, cap_c = int(t[0].item() * 1.25) + 65536, int(t[1].item() * 1.25) + 4096
+        if gather_mode == "p2p":
+            try:
+                sink_dev = ShardSink(ctx, cap_b, cap_c, kind="device")
+            except RuntimeError as exc:
+                if rank == 0:
+                    print(f"[bench] peer sink unavailable ({exc}); falling back to the NCCL gather", file=sys.stderr)
+                gather_mode = "nccl"
+        try:
+            sink_host = ShardSink(ctx, cap_b, cap_c, kind="host", tag=f"mb_bench_{os.environ.get('MASTER_PORT', '0')}")
+        except Exception as exc:  # noqa: BLE001  (every rank fails alike: /dev/shm or cudaHostRegister)
+            if rank == 0:
+                print(f"[bench] shared host sink unavailable ({exc})", file=sys.stderr)
+            sink_host = None
 
     def gather(res):
-        if world == 1:
-            return 0
         d_blob, n_bytes, d_off, n_cells = res.device_buffers()
         src = as_u8_tensor(d_blob, n_bytes, dev)
         if rank == 0 and gather_buf["t"] is None:
@@ -410,9 +436,13 @@ def main():
         return sum(sz) if rank == 0 else 0
 
     def step():
+        if world == 1:
+            return ctx.run(lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates), 0
+        if gather_mode == "p2p":
+            res, directory = sink_dev.run(n_chunks=args.chunks, lanes_per_cell=args.lanes)
+            return res, int(directory[:, 0].sum())
         res = ctx.run(lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates)
-        gathered = gather(res)
-        return res, gathered
+        return res, gather(res)
 
     def barrier():
         if world > 1:
@@ -474,14 +504,31 @@ def main():
             upload_sites()
             tc = time.perf_counter()
             if world > 1:
-                res, gathered = step()
-                # the gathered result of all ranks leaves rank 0's GPU
+                if sink_host is not None:
+                    # every rank streams its shard into the shared pinned host segment (all PCIe links in
+                    # parallel); after the directory all-gather the whole result is in rank 0's address space
+                    res, directory = sink_host.run(n_chunks=args.chunks, lanes_per_cell=args.lanes)
+                    d2h = int(directory[:, 0].sum() + 8 * (directory[:, 1].sum() + world))
+                    e2e_chunks = int(res.n_spans)
+                    res.free()
+                    e2e_parts += (tb_ - ta, tc - tb_, time.perf_counter() - tc)
+                    continue
+                # no shared host segment: gather on rank 0's GPU, then one D2H from there
+                if gather_mode == "p2p":
+                    res, directory = sink_dev.run(n_chunks=args.chunks, lanes_per_cell=args.lanes)
+                    gathered = int(directory[:, 0].sum())
+                else:
+                    res, gathered = step()
                 if rank == 0:
                     if blob_host is None or blob_host[0].numel() < gathered:
                         blob_host = (torch.empty(int(gathered * 1.05) + 16, dtype=torch.uint8).pin_memory(),)
-                    blob_host[0][:gathered].copy_(gather_buf["last"], non_blocking=False)
+                    if gather_mode == "p2p":
+                        sink_dev.read_host(directory, blob_host[0].numpy())
+                    else:
+                        blob_host[0][:gathered].copy_(gather_buf["last"], non_blocking=False)
                 d2h = gathered
                 res.free()
+                e2e_parts += (tb_ - ta, tc - tb_, time.perf_counter() - tc)
                 continue
             # streamed run: the D2H of tet span c overlaps the kernels of span c+1; on return the complete
             # compact result (records + offsets) is in pinned host memory
@@ -518,7 +565,10 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args, n, ns, mesh),
                        "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})" + (", grid candidates" if args.grid_candidates else ", reference relation predicate"),
-                       "parallelism": f"tet-shards x{world}, sites replicated" + (", NCCL gather to rank 0" if world > 1 else ""),
+                       "parallelism": f"tet-shards x{world}, sites replicated" + (
+                           "" if world == 1 else (", shards streamed into rank 0's HBM over NVLink peer memory (CUDA IPC, copy-engine DMA "
+                                                  "overlapped with the next tet span) + directory all-gather (NCCL)" if gather_mode == "p2p"
+                                                  else ", NCCL gather to rank 0 (all-gather of sizes + grouped send/recv)")),
                        "l2": "flushed (512 MB write) between timed steps",
                        "cells_per_step": total_cells, "candidate_pairs_per_step": total_pairs,
                        "pairs_per_sec": total_pairs * args.steps / t_dev},
@@ -532,7 +582,9 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "path": ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_host (%d tet spans, D2H of span c "
                              "overlapped with the kernels of span c+1)" % e2e_chunks) if world == 1 else
-                            "mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run + NCCL gather + D2H on rank 0",
+                            ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_sink into a shared page-locked host segment "
+                             "(every rank streams its tet shard over its own PCIe link, %d spans each) + directory all-gather" % e2e_chunks
+                             if sink_host is not None else "mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run + gather + D2H on rank 0"),
                     "stage_ms": {"set_tetmesh": 1e3 * e2e_parts[0] / e2e_steps, "upload_sites": 1e3 * e2e_parts[1] / e2e_steps,
                                  "run_to_host": 1e3 * e2e_parts[2] / e2e_steps}},
             "gpu_launches": int(launches),
@@ -558,6 +610,9 @@ def main():
             except Exception as exc:  # never lose the headline line
                 line["dist2mat"] = {"error": str(exc)}
         print(json.dumps(line))
+    for sk in (sink_dev, sink_host):
+        if sk is not None:
+            sk.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

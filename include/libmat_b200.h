@@ -153,6 +153,25 @@ int mb_rpd_sync(mb_ctx* ctx, mb_rpd_result* res); /* waits, reads back the count
 int mb_rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result** out,
                        const void** host_blob, const long** host_cell_offsets);
 
+/* The same streamed run into CALLER memory of fixed capacity (MB_ERR_NOMEM if it does not fit): sink_blob /
+ * sink_cell_offsets may be pinned or registered host memory (mb_host_register: e.g. a shared-memory segment
+ * that every rank of a multi-GPU job writes its tet shard into, all PCIe links in parallel), device memory of
+ * this GPU, or device memory of a PEER GPU opened with mb_sink_open.  In the last case span c crosses NVLink
+ * by copy-engine DMA while span c+1 is clipped: the multi-GPU gather of SURVEY 8e happens inside the run
+ * instead of as a collective after it.  Offsets start at 0 (rebase by the preceding shards' sizes). */
+int mb_rpd_run_to_sink(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, void* sink_blob, size_t sink_cap_bytes,
+                       long* sink_cell_offsets, size_t sink_cap_cells, mb_rpd_result** out);
+/* sink memory: a device buffer on this context's GPU that other processes / GPUs of the box can write into
+ * (64-byte CUDA IPC handle, ship it to the peers by any means), the peer-side mapping, and page-locking of
+ * caller host memory.  mb_copy_to_host: blocking D2H of any device-visible range (sink readout). */
+int mb_sink_create(mb_ctx* ctx, size_t bytes, void** d_ptr, unsigned char ipc_handle[64]);
+int mb_sink_destroy(mb_ctx* ctx, void* d_ptr);
+int mb_sink_open(mb_ctx* ctx, const unsigned char ipc_handle[64], void** d_peer_ptr);
+int mb_sink_close(mb_ctx* ctx, void* d_peer_ptr);
+int mb_host_register(mb_ctx* ctx, void* host_ptr, size_t bytes);
+int mb_host_unregister(mb_ctx* ctx, void* host_ptr);
+int mb_copy_to_host(mb_ctx* ctx, void* host_dst, const void* d_src, size_t bytes);
+
 /* number of tet spans the run was cut into (1 for mb_rpd_run); negative mb_status on a NULL handle */
 int mb_rpd_spans(const mb_rpd_result* res);
 

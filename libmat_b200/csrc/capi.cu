@@ -65,6 +65,10 @@ mb_ctx* mb_create(int device, int* err) {
   ctx->stream = ctx->own_stream;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char* v = getenv("MB_D2M_VARIANT")) ctx->d2m_variant = atoi(v);
+  if (const char* v = getenv("MB_TRACE")) {
+    ctx->trace_level = atoi(v);
+    ctx->trace_on = ctx->trace_level != 0;
+  }
   if (err) *err = MB_OK;
   return ctx;
 }
@@ -73,6 +77,9 @@ void mb_destroy(mb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->trace_level == 1)
+    fprintf(stderr, "[libmat_b200 trace] host us: launchK2 %.0f waitK2 %.0f launchK3+scans %.0f waitK3 %.0f launchGather %.0f\n",
+            ctx->trace_us[0], ctx->trace_us[1], ctx->trace_us[2], ctx->trace_us[3], ctx->trace_us[6]);
   for (mb_rpd_result* r : ctx->live_results) r->ctx = nullptr;  // results outlive the context safely
   ctx->spare_blob.release();
   ctx->spare_cell_off.release();
@@ -191,9 +198,8 @@ int mb_rpd_sync(mb_ctx* ctx, mb_rpd_result* res) {
   MB_CATCH
 }
 
-int mb_rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result** out,
-                       const void** host_blob, const long** host_cell_offsets) {
-  MB_TRY(ctx)
+static void run_streamed(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result** out, void* dst_blob,
+                         size_t cap_bytes, long long* dst_off, size_t cap_cells) {
   MB_REQUIRE(ctx && out, MB_ERR_ARG, "null argument");
   MB_CUDA(cudaSetDevice(ctx->device));
   mb_rpd_result* res = new mb_rpd_result();
@@ -201,15 +207,102 @@ int mb_rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rp
   res->ctx = ctx;
   ctx->live_results.push_back(res);
   try {
-    rpd_run_to_host(ctx, opts, n_chunks, res);
+    rpd_run_to_host(ctx, opts, n_chunks, res, dst_blob, cap_bytes, dst_off, cap_cells);
     rpd_sync(ctx, res);
   } catch (...) {
     mb_rpd_free(res);
     *out = nullptr;
     throw;
   }
-  if (host_blob) *host_blob = res->host_blob;
-  if (host_cell_offsets) *host_cell_offsets = reinterpret_cast<const long*>(res->host_off);
+}
+
+int mb_rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result** out,
+                       const void** host_blob, const long** host_cell_offsets) {
+  MB_TRY(ctx)
+  run_streamed(ctx, opts, n_chunks, out, nullptr, 0, nullptr, 0);
+  if (host_blob) *host_blob = (*out)->host_blob;
+  if (host_cell_offsets) *host_cell_offsets = reinterpret_cast<const long*>((*out)->host_off);
+  MB_CATCH
+}
+
+int mb_rpd_run_to_sink(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, void* sink_blob, size_t sink_cap_bytes,
+                       long* sink_cell_offsets, size_t sink_cap_cells, mb_rpd_result** out) {
+  MB_TRY(ctx)
+  MB_REQUIRE(sink_blob && sink_cell_offsets, MB_ERR_ARG, "null sink");
+  run_streamed(ctx, opts, n_chunks, out, sink_blob, sink_cap_bytes, reinterpret_cast<long long*>(sink_cell_offsets),
+               sink_cap_cells);
+  MB_CATCH
+}
+
+// ---- memory a sink can live in ---------------------------------------------------------------------------
+int mb_sink_create(mb_ctx* ctx, size_t bytes, void** d_ptr, unsigned char ipc_handle[64]) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && d_ptr && bytes > 0, MB_ERR_ARG, "bad sink arguments");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  MB_CUDA(cudaMalloc(&p, bytes));
+  if (ipc_handle) {
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+      cudaFree(p);
+      throw MbError{MB_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)};
+    }
+    memcpy(ipc_handle, &h, 64);
+  }
+  *d_ptr = p;
+  MB_CATCH
+}
+
+int mb_sink_destroy(mb_ctx* ctx, void* d_ptr) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  if (d_ptr) MB_CUDA(cudaFree(d_ptr));
+  MB_CATCH
+}
+
+int mb_sink_open(mb_ctx* ctx, const unsigned char ipc_handle[64], void** d_peer_ptr) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && ipc_handle && d_peer_ptr, MB_ERR_ARG, "null argument");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, 64);
+  MB_CUDA(cudaIpcOpenMemHandle(d_peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  MB_CATCH
+}
+
+int mb_sink_close(mb_ctx* ctx, void* d_peer_ptr) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  if (d_peer_ptr) MB_CUDA(cudaIpcCloseMemHandle(d_peer_ptr));
+  MB_CATCH
+}
+
+int mb_host_register(mb_ctx* ctx, void* host_ptr, size_t bytes) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && host_ptr && bytes > 0, MB_ERR_ARG, "bad arguments");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  MB_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+  MB_CATCH
+}
+
+int mb_host_unregister(mb_ctx* ctx, void* host_ptr) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && host_ptr, MB_ERR_ARG, "bad arguments");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  MB_CUDA(cudaHostUnregister(host_ptr));
+  MB_CATCH
+}
+
+int mb_copy_to_host(mb_ctx* ctx, void* host_dst, const void* d_src, size_t bytes) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && host_dst && d_src, MB_ERR_ARG, "bad arguments");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  MB_CUDA(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
   MB_CATCH
 }
 
@@ -327,7 +420,8 @@ int mb_rpd_fetch_compact(mb_rpd_result* res, void* blob, long* cell_offsets) {
   MB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   if (res->host_only) {  // streamed run: the records are already in pinned host memory
-    MB_REQUIRE(res->host_blob == ctx->pin_blob.p, MB_ERR_STATE, "streamed result superseded by a later run");
+    MB_REQUIRE(res->host_blob, MB_ERR_STATE, "the result lives in a device sink");
+    MB_REQUIRE(!res->sink_owned || res->host_blob == ctx->pin_blob.p, MB_ERR_STATE, "streamed result superseded by a later run");
     if (blob && res->compact_bytes > 0) memcpy(blob, res->host_blob, (size_t)res->compact_bytes);
     if (cell_offsets) memcpy(cell_offsets, res->host_off, sizeof(long long) * ((size_t)res->n_cells + 1));
     return MB_OK;
@@ -388,7 +482,8 @@ int mb_rpd_fetch_records(mb_rpd_result* res, void* dst) {
   const long long* offs;
   const uint32_t* blob;
   if (res->host_only) {
-    MB_REQUIRE(res->host_blob == ctx->pin_blob.p, MB_ERR_STATE, "streamed result superseded by a later run");
+    MB_REQUIRE(res->host_blob, MB_ERR_STATE, "the result lives in a device sink");
+    MB_REQUIRE(!res->sink_owned || res->host_blob == ctx->pin_blob.p, MB_ERR_STATE, "streamed result superseded by a later run");
     offs = res->host_off;
     blob = res->host_blob;
   } else {

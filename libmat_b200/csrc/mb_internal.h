@@ -153,6 +153,7 @@ struct HostScalars {
   int pad_;
   long long total_words;
   RpdCounters counters;
+  long long zero;
 };
 
 struct mb_rpd_result {
@@ -173,6 +174,7 @@ struct mb_rpd_result {
   const uint32_t* host_blob = nullptr;
   const long long* host_off = nullptr;
   int n_spans = 1;
+  bool sink_owned = true;  // host_blob points into the context's own pinned buffer (else caller memory)
   // emission (K4)
   bool emitted = false;
   mb_emit_counts emit_counts = {0, 0, 0};
@@ -212,6 +214,9 @@ struct mb_ctx {
   DevBuf<long long> span_off[2];
   PinBuf pin_blob, pin_off;
   HostScalars* hs = nullptr;
+  int trace_level = 0;
+  bool trace_on = false;       // MB_TRACE=1: host-side stage timers, printed by mb_destroy
+  double trace_us[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<cudaEvent_t> ev_pool;   // timing events recycled between runs
   // rpd scratch (reused across calls)
   DevBuf<int> tet_cnt, tet_off, pair_tet, pair_site, pair_local, cand_pad;
@@ -245,7 +250,8 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
 void rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
                       const unsigned* site_flags, int n_site, const int* site_knn, int site_k);
 void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res);
-void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res);
+void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res, void* dst_blob,
+                     size_t dst_cap_bytes, long long* dst_off, size_t dst_cap_cells);
 void rpd_sync(mb_ctx* ctx, mb_rpd_result* res);
 void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
 void rpd_volumes(mb_ctx* ctx, mb_rpd_result* res);  // a12: per-cell / per-site volume + barycentre sums

@@ -48,6 +48,7 @@ struct ClipArgs {
   const int* pair_site;
   const int* pair_local;  // local index of the pair's tet in the processed range / subset (per-tet lists)
   long long n_pairs;
+  int grab;              // pairs a warp takes from the global cursor at a time (multiple of 32/G)
   // outputs
   signed char* pair_status;
   long long* pair_blob;
@@ -152,10 +153,10 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       if (idle) {
         if (wq_next >= wq_end && !wq_dry) {
           unsigned long long b = 0;
-          if (wl == 0) b = atomicAdd(&A.counters[CNT_WORK_CURSOR_IDX], (unsigned long long)(8 * NG));
+          if (wl == 0) b = atomicAdd(&A.counters[CNT_WORK_CURSOR_IDX], (unsigned long long)A.grab);
           b = __shfl_sync(0xffffffffu, b, 0);
           wq_next = (long long)b;
-          wq_end = min((long long)b + 8 * NG, A.n_pairs);
+          wq_end = min((long long)b + A.grab, A.n_pairs);
           if (wq_next >= A.n_pairs) wq_dry = true;
         }
         if (state == GS_IDLE) {

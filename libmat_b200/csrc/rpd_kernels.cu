@@ -3,6 +3,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 
 #include "mb_internal.h"
@@ -259,15 +260,17 @@ __global__ void __launch_bounds__(256) k_cand_given(const float4* __restrict__ v
 // ordering + compaction: records leave K3 in arbitrary order in the scratch; two exclusive scans
 // (record words, valid flags) give each valid cell its slot in (tet, site) order.
 // =============================================================================================
-__global__ void k_valid_flags(const int* __restrict__ pair_words, long long n, int* __restrict__ valid) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) valid[i] = pair_words[i] > 0;
-}
+#define PACK_SHIFT 40
+#define PACK_MASK ((1ull << PACK_SHIFT) - 1ull)
+struct PackWords {
+  __host__ __device__ unsigned long long operator()(int words) const {
+    return (unsigned long long)words | ((unsigned long long)(words > 0) << PACK_SHIFT);
+  }
+};
 
 __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* __restrict__ pair_blob,
-                         const int* __restrict__ pair_words, const long long* __restrict__ word_off,
-                         const int* __restrict__ cell_idx, long long n_pairs,
-                         uint32_t* __restrict__ blob, long long* __restrict__ cell_off,
+                         const int* __restrict__ pair_words, const unsigned long long* __restrict__ packed_off,
+                         long long n_pairs, uint32_t* __restrict__ blob, long long* __restrict__ cell_off,
                          long long total_words, long long n_cells, long long base_bytes) {
   // 8 lanes per record
   const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -275,16 +278,25 @@ __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* 
   if (g >= n_pairs) return;
   const int words = pair_words[g];
   if (words == 0) return;
-  const long long dst = word_off[g];
+  const unsigned long long pk = packed_off[g];
+  const long long dst = (long long)(pk & PACK_MASK);
   const uint32_t* src = scratch + pair_blob[g];
   for (int i = lane; i < words; i += 8) blob[dst + i] = src[i];
   if (lane == 0) {
-    const int c = cell_idx[g];
+    const long long c = (long long)(pk >> PACK_SHIFT);
     cell_off[c] = base_bytes + dst * 4;
     if (c == n_cells - 1) cell_off[n_cells] = base_bytes + total_words * 4;
   }
 }
 
+// K3's counters and the packed scan total reach the host through mapped memory in one launch
+__global__ void k_publish_k3(const uint32_t* __restrict__ counters, const unsigned long long* __restrict__ total,
+                             HostScalars* __restrict__ hs) {
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&hs->counters);
+  for (int i = threadIdx.x; i < (int)(sizeof(RpdCounters) / 4); i += blockDim.x) dst[i] = counters[i];
+  if (threadIdx.x == 0) hs->total_words = (long long)*total;
+  __threadfence_system();
+}
 
 // =============================================================================================
 // K1 host side: grid build (counting sort by cell + max-weight pyramid), K2 launch
@@ -364,9 +376,10 @@ static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan&
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
     attr_set = true;
   }
-  // fast pass: one warp per tet, persistent-style grid (a multiple of the SM count)
+  // fast pass: one warp per tet.  The cost per tet varies several-fold, so the hardware block scheduler
+  // balances better than a static stride: plain grid up to 64 waves, strided beyond
   const int want = (sp.count + WARPS - 1) / WARPS;
-  const int blocks = std::max(1, std::min(want, ctx->sm_count * 32));
+  const int blocks = std::max(1, std::min(want, ctx->sm_count * 6 * 64));
   ctx->n_launches++;
   k_grid_candidates<KCAP, WARPS, false><<<blocks, 32 * WARPS, smem, s>>>(
       M.vert4.p, M.tet_idx.p, sp.first, sp.count, sp.sel, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
@@ -418,7 +431,7 @@ static void exclusive_scan(mb_ctx* ctx, const int* in, T* out, long long n) {
 }
 
 template <int G, bool PT>
-static void launch_clip(mb_ctx* ctx, const ClipArgs& A) {
+static void launch_clip(mb_ctx* ctx, ClipArgs A) {
   constexpr int groups = 128 / G;
   const size_t smem = sizeof(CellS) * groups;
   static bool attr_set = false;
@@ -435,6 +448,15 @@ static void launch_clip(mb_ctx* ctx, const ClipArgs& A) {
   long long want = (A.n_pairs + groups - 1) / groups;
   long long grid = std::min<long long>(want, (long long)ctx->sm_count * per_sm);
   if (grid < 1) grid = 1;
+  // cursor granularity: 8 rounds of pairs per grab for large runs, finer for small spans so that every
+  // warp still gets >= ~16 grabs (a persistent kernel's tail is one grab long)
+  {
+    constexpr int NG = 32 / G;
+    const long long warps = grid * 4;
+    long long g = A.n_pairs / (warps * 16);
+    g = (g / NG) * NG;
+    A.grab = (int)std::max<long long>(NG, std::min<long long>(8 * NG, g));
+  }
   ctx->n_launches++;
   k_clip<G, PT><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
   MB_CUDA(cudaGetLastError());
@@ -472,6 +494,26 @@ static cudaEvent_t take_event(mb_ctx* ctx) {
   return e;
 }
 
+// host-side stage timers (MB_TRACE=1): where the host thread spends a span -- launching or waiting
+static inline double now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#define TRACE(slot)                                  \
+  do {                                               \
+    if (ctx->trace_on) {                             \
+      const double t_ = now_us();                    \
+      ctx->trace_us[slot] += t_ - tr_;               \
+      tr_ = t_;                                      \
+    }                                                \
+  } while (0)
+
+static void trace_flush(mb_ctx* ctx, const char* what) {
+  if (ctx->trace_level < 2) return;
+  fprintf(stderr, "[libmat_b200 trace] %s host us: launchK2 %.0f waitK2 %.0f launchK3+scans %.0f waitK3 %.0f launchGather %.0f\n",
+          what, ctx->trace_us[0], ctx->trace_us[1], ctx->trace_us[2], ctx->trace_us[3], ctx->trace_us[6]);
+  for (double& v : ctx->trace_us) v = 0.0;
+}
+
 struct SpanStats {
   long long n_pairs = 0, n_cells = 0, total_words = 0;
 };
@@ -488,6 +530,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   const int t_count = sp.count;
   const int G = opts && opts->lanes_per_cell ? opts->lanes_per_cell : 8;
   HostScalars* hs = host_scalars(ctx);
+  double tr_ = ctx->trace_on ? now_us() : 0.0;
   cudaEvent_t ev[4];
   for (int i = 0; i < 4; i++) {
     ev[i] = take_event(ctx);
@@ -517,7 +560,9 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     MB_CUDA(cudaMemsetAsync(ctx->tet_cnt.p + t_count, 0, sizeof(int), s));
     exclusive_scan<int>(ctx, ctx->tet_cnt.p, ctx->tet_off.p, (long long)t_count + 1);
     publish(ctx, ctx->tet_off.p + t_count, &hs->n_pairs, sizeof(int));
+    TRACE(0);  // launch K2
     MB_CUDA(cudaStreamSynchronize(s));
+    TRACE(1);  // wait K2
     n_pairs = hs->n_pairs;
     ctx->pair_tet.reserve((size_t)n_pairs + 1);
     ctx->pair_site.reserve((size_t)n_pairs + 1);
@@ -545,6 +590,8 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   // scratch: typical record ~80 words; retried with the exact need if it overflows
   size_t scratch_words = std::max<size_t>((size_t)n_pairs * 96 + (1u << 20), ctx->scratch.cap);
   RpdCounters hc;
+  long long total_words = 0;
+  DevBuf<long long>& word_off = ctx->word_off;  // packed: cell index << 40 | word offset
   for (int attempt = 0; attempt < 2 && n_pairs > 0; attempt++) {
     ctx->scratch.reserve(scratch_words);
     ClipArgs A;
@@ -586,9 +633,30 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     else
       pt ? launch_clip<32, true>(ctx, A) : launch_clip<32, false>(ctx, A);
     MB_CUDA(cudaEventRecord(ev[2], s));
-    publish(ctx, ctx->counters.p, &hs->counters, sizeof(RpdCounters));
+    // ordering scans are enqueued right behind K3; K3's counters and the record total reach the host
+    // with ONE synchronisation
+    // one exclusive scan over packed (valid count << 40 | record words) gives every pair both its cell
+    // index and its word offset in (tet, site) order
+    word_off.reserve((size_t)n_pairs + 1);
+    MB_CUDA(cudaMemsetAsync(ctx->pair_words.p + n_pairs, 0, sizeof(int), s));
+    {
+      cub::TransformInputIterator<unsigned long long, PackWords, const int*> in(ctx->pair_words.p, PackWords());
+      unsigned long long* outp = reinterpret_cast<unsigned long long*>(word_off.p);
+      size_t tmp = 0;
+      MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, outp, n_pairs + 1, s));
+      ctx->cub_tmp.reserve(tmp);
+      ctx->n_launches += 2;
+      MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, outp, n_pairs + 1, s));
+    }
+    ctx->n_launches++;
+    k_publish_k3<<<1, 64, 0, s>>>(reinterpret_cast<const uint32_t*>(ctx->counters.p),
+                                  reinterpret_cast<const unsigned long long*>(word_off.p) + n_pairs, hs);
+    MB_CUDA(cudaGetLastError());
+    TRACE(2);  // launch fill + K3 + ordering scans
     MB_CUDA(cudaStreamSynchronize(s));
+    TRACE(3);  // wait K3 + scans
     hc = hs->counters;
+    total_words = hs->total_words & PACK_MASK;
     if (hc.blob_words <= ctx->scratch.cap) break;
     // scratch too small: rerun K3 with the measured need (rare; statuses are recomputed)
     scratch_words = (size_t)hc.blob_words + (1u << 20);
@@ -623,36 +691,22 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   res->n_ovf_tets += (long)hc.n_ovf_tets;
   for (int i = 0; i < 10; i++) res->hist[i] += (long)hc.hist[i];
 
-  // ---- ordering: scan + gather into (tet, site) order -------------------------------------------
+  // ---- gather into (tet, site) order -------------------------------------------------------------
   cell_off.reserve((size_t)st.n_cells + 1);
-  long long total_words = 0;
   if (n_pairs > 0) {
-    DevBuf<long long>& word_off = ctx->word_off;
-    word_off.reserve((size_t)n_pairs + 1);
-    DevBuf<int>& valid = ctx->pair_valid;
-    valid.reserve((size_t)n_pairs + 1);
-    DevBuf<int>& cell_idx = ctx->pair_cell;
-    cell_idx.reserve((size_t)n_pairs + 1);
-    MB_CUDA(cudaMemsetAsync(ctx->pair_words.p + n_pairs, 0, sizeof(int), s));
-    ctx->n_launches++;
-    k_valid_flags<<<(unsigned)((n_pairs + 1 + 255) / 256), 256, 0, s>>>(ctx->pair_words.p, n_pairs + 1, valid.p);
-    exclusive_scan<long long>(ctx, ctx->pair_words.p, word_off.p, n_pairs + 1);
-    exclusive_scan<int>(ctx, valid.p, cell_idx.p, n_pairs + 1);
-    publish(ctx, word_off.p + n_pairs, &hs->total_words, sizeof(long long));
-    MB_CUDA(cudaStreamSynchronize(s));
-    total_words = hs->total_words;
     blob.reserve((size_t)total_words + 4);
     if (total_words > 0) {
       ctx->n_launches++;
       k_gather<<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
-          ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, word_off.p, cell_idx.p, n_pairs,
-          blob.p, cell_off.p, total_words, st.n_cells, base_bytes);
+          ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, reinterpret_cast<const unsigned long long*>(word_off.p),
+          n_pairs, blob.p, cell_off.p, total_words, st.n_cells, base_bytes);
       MB_CUDA(cudaGetLastError());
     }
   }
   if (st.n_cells == 0) MB_CUDA(cudaMemcpyAsync(cell_off.p, &base_bytes, sizeof(long long), cudaMemcpyHostToDevice, s));
   st.total_words = total_words;
   MB_CUDA(cudaEventRecord(ev[3], s));
+  TRACE(6);  // launch gather
   return st;
 }
 
@@ -690,6 +744,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   // fold K1 into the candidate stage: replace the span's start event by e0
   ctx->ev_pool.push_back(res->evs[0]);
   res->evs[0] = e0;
+  trace_flush(ctx, "run");
   res->n_spans = 1;
   res->host_only = false;
   res->compact_bytes = (long)(st.total_words * 4);
@@ -701,7 +756,15 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
 // on the compute stream, the ordered records of span c travel to pinned host memory on a second
 // stream (PCIe D2H overlapped with K2/K3).  Spans are contiguous in tet order, so the concatenation
 // is the global (tet, site) order and the offsets / ids are those of the one-shot run.
-void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res) {
+//
+// The destination is the library's own growable pinned host buffer (dst_blob == nullptr), or caller memory
+// of fixed capacity reachable by cudaMemcpyDefault: pinned / registered host memory (e.g. a shared-memory
+// segment every rank of a multi-GPU job writes its shard into), device memory of this GPU, or device
+// memory of a PEER GPU opened through CUDA IPC -- then span c crosses NVLink by copy-engine DMA while
+// span c+1 is clipped (the multi-GPU gather, fused into the run instead of a collective after it).
+void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res, void* dst_blob,
+                     size_t dst_cap_bytes, long long* dst_off, size_t dst_cap_cells) {
+  const bool own = dst_blob == nullptr;
   int t_first, t_count;
   run_prologue(ctx, opts, res, t_first, t_count);
   MB_REQUIRE(!res->want_volumes, MB_ERR_ARG, "want_volumes is not available in the streamed run");
@@ -722,9 +785,16 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
   MB_CUDA(cudaEventRecord(e0, s));
   if (grid_cands && t_count > 0) G = grid_build(ctx);
   long long acc_bytes = 0, acc_cells = 0;
-  // destination: kept from the previous run; first run sizes it from the first span
-  if (!ctx->pin_off.p) ctx->pin_off.reserve_keep(sizeof(long long) * 1024, 0);
-  reinterpret_cast<long long*>(ctx->pin_off.p)[0] = 0;
+  // own destination: kept from the previous run; first run sizes it from the first span
+  if (own) {
+    if (!ctx->pin_off.p) ctx->pin_off.reserve_keep(sizeof(long long) * 1024, 0);
+    reinterpret_cast<long long*>(ctx->pin_off.p)[0] = 0;
+  } else {
+    MB_REQUIRE(dst_off && dst_cap_cells >= 1, MB_ERR_ARG, "sink offsets buffer missing");
+    HostScalars* hs = host_scalars(ctx);
+    hs->zero = 0;
+    MB_CUDA(cudaMemcpyAsync(dst_off, &hs->zero, sizeof(long long), cudaMemcpyDefault, cs));
+  }
   for (int c = 0; c < n_chunks; c++) {
     const int c_first = (int)((long long)t_count * c / n_chunks);
     const int c_count = (int)((long long)t_count * (c + 1) / n_chunks) - c_first;
@@ -741,7 +811,14 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     const long long bytes = st.total_words * 4;
     // pinned destination large enough for this span (first run: extrapolate from the spans so far)
     const size_t need_blob = (size_t)(acc_bytes + bytes), need_off = sizeof(long long) * (size_t)(acc_cells + st.n_cells + 1);
-    if (need_blob > ctx->pin_blob.cap || need_off > ctx->pin_off.cap) {
+    if (!own) {
+      if (need_blob > dst_cap_bytes || (size_t)(acc_cells + st.n_cells + 1) > dst_cap_cells) {
+        MB_CUDA(cudaStreamSynchronize(cs));
+        MB_CUDA(cudaStreamSynchronize(s));
+        throw MbError{MB_ERR_NOMEM, "sink too small: needs more than " + std::to_string(need_blob) + " bytes / " +
+                                        std::to_string(acc_cells + st.n_cells + 1) + " offsets"};
+      }
+    } else if (need_blob > ctx->pin_blob.cap || need_off > ctx->pin_off.cap) {
       MB_CUDA(cudaStreamSynchronize(cs));  // earlier spans have landed: safe to move them
       const double scale = 1.1 * (double)t_count / (double)std::max(1, c_first + c_count);
       ctx->pin_blob.reserve_keep(std::max(need_blob, (size_t)(need_blob * scale)), (size_t)acc_bytes);
@@ -749,22 +826,36 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     }
     MB_CUDA(cudaEventRecord(ctx->ev_gathered[b], s));
     MB_CUDA(cudaStreamWaitEvent(cs, ctx->ev_gathered[b], 0));
+    unsigned char* out_blob = own ? (unsigned char*)ctx->pin_blob.p : (unsigned char*)dst_blob;
+    long long* out_off = own ? reinterpret_cast<long long*>(ctx->pin_off.p) : dst_off;
     if (bytes > 0)
-      MB_CUDA(cudaMemcpyAsync((unsigned char*)ctx->pin_blob.p + acc_bytes, ctx->span_blob[b].p, (size_t)bytes,
-                              cudaMemcpyDeviceToHost, cs));
+      MB_CUDA(cudaMemcpyAsync(out_blob + acc_bytes, ctx->span_blob[b].p, (size_t)bytes, cudaMemcpyDefault, cs));
     if (st.n_cells > 0)
-      MB_CUDA(cudaMemcpyAsync(reinterpret_cast<long long*>(ctx->pin_off.p) + acc_cells, ctx->span_off[b].p,
-                              sizeof(long long) * (size_t)(st.n_cells + 1), cudaMemcpyDeviceToHost, cs));
+      MB_CUDA(cudaMemcpyAsync(out_off + acc_cells, ctx->span_off[b].p, sizeof(long long) * (size_t)(st.n_cells + 1),
+                              cudaMemcpyDefault, cs));
     MB_CUDA(cudaEventRecord(ctx->ev_copied[b], cs));
     acc_bytes += bytes;
     acc_cells += st.n_cells;
   }
   MB_CUDA(cudaStreamSynchronize(cs));
   MB_CUDA(cudaStreamSynchronize(s));
+  trace_flush(ctx, "run_to_host");
   res->n_spans = n_chunks;
   res->host_only = true;
-  res->host_blob = reinterpret_cast<const uint32_t*>(ctx->pin_blob.p);
-  res->host_off = reinterpret_cast<const long long*>(ctx->pin_off.p);
+  res->host_blob = nullptr;
+  res->host_off = nullptr;
+  if (own) {
+    res->host_blob = reinterpret_cast<const uint32_t*>(ctx->pin_blob.p);
+    res->host_off = reinterpret_cast<const long long*>(ctx->pin_off.p);
+  } else {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, dst_blob) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+      res->host_blob = reinterpret_cast<const uint32_t*>(dst_blob);
+      res->host_off = dst_off;
+    }
+    (void)cudaGetLastError();
+  }
+  res->sink_owned = own;
   res->compact_bytes = (long)acc_bytes;
   res->synced = false;
 }

@@ -66,6 +66,135 @@ def gather_varlen(local: torch.Tensor, dst: int = 0, group=None, out: torch.Tens
     return result, sz
 
 
+class ShardSink:
+    """Destination of a sharded run: one slab per rank, [blob bytes | cell offsets], in memory every rank can
+    write -- device memory of rank `dst`'s GPU shared through CUDA IPC (kind="device": each rank's ordered
+    records cross NVLink by copy-engine DMA while its next tet span is clipped), or a POSIX shared-memory
+    segment page-locked by every rank (kind="host": the shards reach host memory over all PCIe links in
+    parallel).  The slab directory (bytes, cells per rank) is exchanged with one small all-gather per run.
+
+    Layout: slab r starts at r * slab_bytes; its offsets array (cap_cells + 1 int64) sits at the slab's end."""
+
+    def __init__(self, ctx, cap_bytes: int, cap_cells: int, kind: str = "device", dst: int = 0, group=None, tag="mb"):
+        import mmap
+        import os
+        self.ctx, self.kind, self.dst, self.group = ctx, kind, dst, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.cap_bytes = (int(cap_bytes) + 255) // 256 * 256
+        self.cap_cells = int(cap_cells)
+        self.off_bytes = (8 * (self.cap_cells + 1) + 255) // 256 * 256
+        self.slab_bytes = self.cap_bytes + self.off_bytes
+        total = self.slab_bytes * self.world
+        self._mm = None
+        if kind == "device":
+            # failures (IPC not permitted in this container, no peer access) must surface on EVERY rank, or
+            # the others would wait in the next collective: agree on the outcome before going on
+            box, ok, err = [None], 1, ""
+            self.base = None
+            if self.rank == dst:
+                try:
+                    self.base, handle = ctx.sink_create(total)
+                    box = [handle]
+                except Exception as exc:  # noqa: BLE001
+                    ok, err = 0, str(exc)
+            if self.world > 1:
+                dist.broadcast_object_list(box, src=dst, group=group)
+            if self.rank != dst:
+                try:
+                    if box[0] is None:
+                        raise RuntimeError("owner could not create the sink")
+                    self.base = ctx.sink_open(box[0])
+                except Exception as exc:  # noqa: BLE001
+                    ok, err = 0, str(exc)
+            if self.world > 1:
+                oks = [None] * self.world
+                dist.all_gather_object(oks, (ok, err), group=group)
+                bad = [e for o, e in oks if not o]
+                if bad:
+                    if self.base is not None:
+                        (ctx.sink_destroy if self.rank == dst else ctx.sink_close)(self.base)
+                    raise RuntimeError("peer sink unavailable: " + bad[0])
+            elif not ok:
+                raise RuntimeError(err)
+        else:
+            box = [None]
+            if self.rank == dst:
+                path = f"/dev/shm/{tag}_{os.getpid()}"
+                with open(path, "wb") as fh:
+                    fh.truncate(total)
+                box = [path]
+            if self.world > 1:
+                dist.broadcast_object_list(box, src=dst, group=group)
+            self.path = box[0]
+            fd = os.open(self.path, os.O_RDWR)
+            self._mm = mmap.mmap(fd, total)
+            os.close(fd)
+            self.host = np.frombuffer(self._mm, dtype=np.uint8)
+            self.base = self.host.ctypes.data
+            ctx.host_register(self.base, total)
+            if self.world > 1:
+                dist.barrier(group=group)
+            if self.rank == dst:
+                os.unlink(self.path)  # the mappings keep the segment alive
+
+    def slab(self, r: int):
+        b = self.base + r * self.slab_bytes
+        return b, b + self.cap_bytes
+
+    def run(self, n_chunks=0, **kw):
+        """every rank: streamed run of its shard into its slab; returns (result handle, directory [world, 2])"""
+        blob_ptr, off_ptr = self.slab(self.rank)
+        res = self.ctx.run_to_sink(blob_ptr, self.cap_bytes, off_ptr, self.cap_cells + 1, n_chunks=n_chunks, **kw)
+        mine = torch.tensor([res.compact_bytes, res.n_cells], dtype=torch.int64)
+        if self.world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else "cpu"
+            table = torch.zeros(self.world, 2, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(table.view(-1), mine.to(dev), group=self.group)  # also the completion barrier
+            table = table.cpu()
+        else:
+            table = mine.view(1, 2)
+        return res, table.numpy()
+
+    def read_host(self, directory, out_blob: np.ndarray | None = None):
+        """rank dst: the shards concatenated in rank order (= global (tet, site) order) + rebased offsets"""
+        tot = int(directory[:, 0].sum())
+        blob = out_blob if out_blob is not None else np.empty(tot, np.uint8)
+        offs, at = [], 0
+        for r in range(self.world):
+            nb, nc = int(directory[r, 0]), int(directory[r, 1])
+            bp, op = self.slab(r)
+            o = np.empty(nc + 1, np.int64)
+            if self.kind == "device":
+                if nb:
+                    self.ctx.copy_to_host(blob[at:at + nb], bp, nb)
+                self.ctx.copy_to_host(o, op, 8 * (nc + 1))
+            else:
+                s0 = r * self.slab_bytes
+                blob[at:at + nb] = self.host[s0:s0 + nb]
+                o[:] = self.host[s0 + self.cap_bytes:s0 + self.cap_bytes + 8 * (nc + 1)].view(np.int64)
+            offs.append(o)
+            at += nb
+        return blob[:tot], rebase_offsets(offs, [int(x) for x in directory[:, 0]])
+
+    def close(self):
+        if self.kind == "device":
+            if self.rank == self.dst:
+                if self.world > 1:
+                    dist.barrier(group=self.group)
+                self.ctx.sink_destroy(self.base)
+            else:
+                self.ctx.sink_close(self.base)
+                dist.barrier(group=self.group)
+        else:
+            self.ctx.host_unregister(self.base)
+            self.host = None
+            try:
+                self._mm.close()
+            except BufferError:
+                pass
+
+
 def rebase_offsets(cell_offsets: list[np.ndarray], blob_sizes: list[int]) -> np.ndarray:
     """per-rank cell byte offsets (each n_cells_r + 1 long, starting at 0) -> global offsets"""
     out = [np.zeros(1, dtype=np.int64)]

@@ -217,6 +217,44 @@ class Context:
         self._check(self.lib.mb_rpd_run_to_host(self._ctx, C.byref(opts), int(n_chunks), C.byref(h), C.byref(bp), C.byref(op)))
         return RpdResult(self, h, host_ptrs=(bp.value, op.value))
 
+    def run_to_sink(self, sink_blob_ptr: int, cap_bytes: int, sink_off_ptr: int, cap_cells: int, n_chunks=0,
+                    lanes_per_cell=0, grid_k=0, grid_candidates=False) -> RpdResult:
+        """streamed run into caller memory (mb_rpd_run_to_sink): pinned / registered host memory, device memory
+        of this GPU or of a peer GPU (mb_sink_open) -- the multi-GPU gather fused into the run"""
+        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), 0, int(grid_candidates))
+        h = C.c_void_p()
+        self._check(self.lib.mb_rpd_run_to_sink(self._ctx, C.byref(opts), int(n_chunks), C.c_void_p(sink_blob_ptr),
+                                                int(cap_bytes), C.c_void_p(sink_off_ptr), int(cap_cells), C.byref(h)))
+        return RpdResult(self, h)
+
+    # sink memory (multi-GPU gather): device buffer + CUDA IPC handle, peer mapping, host page-locking
+    def sink_create(self, nbytes: int):
+        p = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self._check(self.lib.mb_sink_create(self._ctx, int(nbytes), C.byref(p), handle))
+        return p.value, bytes(handle)
+
+    def sink_destroy(self, ptr_: int):
+        self._check(self.lib.mb_sink_destroy(self._ctx, C.c_void_p(ptr_)))
+
+    def sink_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self.lib.mb_sink_open(self._ctx, buf, C.byref(p)))
+        return p.value
+
+    def sink_close(self, ptr_: int):
+        self._check(self.lib.mb_sink_close(self._ctx, C.c_void_p(ptr_)))
+
+    def host_register(self, ptr_: int, nbytes: int):
+        self._check(self.lib.mb_host_register(self._ctx, C.c_void_p(ptr_), int(nbytes)))
+
+    def host_unregister(self, ptr_: int):
+        self._check(self.lib.mb_host_unregister(self._ctx, C.c_void_p(ptr_)))
+
+    def copy_to_host(self, host_array: np.ndarray, d_src: int, nbytes: int):
+        self._check(self.lib.mb_copy_to_host(self._ctx, ptr(host_array), C.c_void_p(d_src), int(nbytes)))
+
     def compute_clipped_voro_diagram(self, site, site_weights, site_flags, site_knn=None, site_k=0,
                                      **opts) -> RpdResult:
         """site: SoA x|y|z float[3*n_site]; site_weights r^2; site_knn (site_k+1) x n_site or None
