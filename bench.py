@@ -43,6 +43,19 @@ N_FOR_GPUS = {1: 32, 2: 40, 4: 51, 8: 64}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def measured_traffic(kernel: str, key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+    (profiles/traffic.json, written by scripts/ncu_traffic.py from an `ncu --set full` report); None when no
+    capture exists for this kernel / workload."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        e = d.get(kernel, {}).get(key)
+        return (int(e["dram_bytes"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -192,10 +205,46 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
            "config": {"workload": f"config 3 shape: {n_samples} samples, {len(d.spheres)} spheres, {d.n_slabs} slabs, "
                                   f"{d.n_cones} cones, {n_prims / n_samples:.1f} prims/sample (replicated int3 lists)"},
            "roofline": {"kernel": "k_dist2mat", "bound": "hbm", "achieved": b_alg / (k_ms * 1e-3) / 1e9, "peak": peak,
-                        "unit": "GB/s", "frac": b_alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                        "unit": "GB/s", "frac": b_alg / (k_ms * 1e-3) / 1e9 / peak,
+                        "traffic": measured_traffic("k_dist2mat_q", f"d2m-{n_samples}")[0],
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg},
            "e2e": {"value": n_samples / t_e2e, "unit": "queries/s",
                    "h2d_bytes_per_step": int(sum(x.nbytes for x in hp)), "d2h_bytes_per_step": int(8 * n_samples)}}
+    # the same query with every distinct list stored once (samples of one surface face share their list:
+    # fix_geo_error.cxx:149-215 builds one list per face and :300-366 replicates it per sample).  Offsets may
+    # point anywhere, so this needs no new entry point -- only a caller that stops replicating.
+    try:
+        r_rep = ctx.dist2mat_fetch(want_tie=False)
+        ds = synth.share_lists(d)
+        tps = [pin(x) for x in (ds.spheres, ds.samples, ds.offset, ds.count, ds.prims)]
+        hps = [t.numpy() for t in tps]
+        ctx.dist2mat_upload(*hps)
+        for _ in range(warmup):
+            ctx.dist2mat_run()
+        ms2 = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ms2.append(ctx.dist2mat_run())
+        r_sh = ctx.dist2mat_fetch(want_tie=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            ctx._check(ctx.lib.mb_dist2mat(ctx._ctx, hps[0].ctypes.data, len(ds.spheres), hps[1].ctypes.data, n_samples,
+                                           hps[2].ctypes.data, hps[3].ctypes.data, hps[4].ctypes.data, int(ds.prims.shape[0]),
+                                           res_h.numpy().ctypes.data, cid_h.numpy().ctypes.data, None))
+        torch.cuda.synchronize()
+        t_sh = (time.perf_counter() - t0) / e_steps
+        k2 = float(np.mean(ms2))
+        out["shared_lists"] = {
+            "value": n_samples / (k2 * 1e-3), "unit": "queries/s", "ms_per_step": k2,
+            "distinct_list_entries": int(ds.prims.shape[0]), "replicated_list_entries": n_prims,
+            "results_identical_to_replicated": bool(np.array_equal(r_rep[0].view(np.uint32), r_sh[0].view(np.uint32))
+                                                    and np.array_equal(r_rep[1], r_sh[1])),
+            "e2e": {"value": n_samples / t_sh, "unit": "queries/s", "h2d_bytes_per_step": int(sum(x.nbytes for x in hps)),
+                    "d2h_bytes_per_step": int(8 * n_samples)}}
+    except Exception as exc:  # noqa: BLE001
+        out["shared_lists"] = {"error": str(exc)}
     if with_cpu:
         from oracle import oracle as O
         n_cpu = min(n_samples, 400000)
@@ -390,6 +439,13 @@ def main():
         if world > 1:
             ctx.set_tet_range(first, count)
 
+    def set_mesh_shard():
+        """e2e leg, N > 1: a rank uploads only ITS tets (global vertices) and keeps global tet ids"""
+        first, count = shard(mesh.n_tet, rank, world)
+        ctx.set_tetmesh(h["verts"], h["idx"][first:first + count], h["v_adjs"], h["f_adjs"][first:first + count],
+                        h["f_ids"][first:first + count], e_adj6=h["e6"][first:first + count])
+        ctx.set_tet_id_base(first)
+
     def upload_sites():
         ctx.upload_sites(h["site"], h["w"], h["flags"], h["knn"], site_k)
 
@@ -499,7 +555,7 @@ def main():
         t0 = time.perf_counter()
         for i in range(e2e_steps):
             ta = time.perf_counter()
-            set_mesh()
+            set_mesh() if world == 1 else set_mesh_shard()
             tb_ = time.perf_counter()
             upload_sites()
             tc = time.perf_counter()
@@ -555,6 +611,7 @@ def main():
         b_alg = algorithmic_bytes(count, mesh.n_vert, ns, pairs, listed, rec_bytes)  # rank 0's launch
         clip_avg_ms = float(np.mean(clip_ms))
         achieved = b_alg / (clip_avg_ms * 1e-3) / 1e9
+        clip_traffic, clip_traffic_src = measured_traffic("k_clip", f"{args.workload}-{mode}") if world == 1 else (None, None)
         h2d = sum(h[x].nbytes for x in ("verts", "idx", "v_adjs", "e6", "f_adjs", "f_ids", "site", "w", "flags"))
         if h["knn"] is not None:
             h2d += h["knn"].nbytes
@@ -575,7 +632,8 @@ def main():
             "stage_ms": {"candidates": float(np.mean(cand_ms)), "clip": clip_avg_ms, "order": float(np.mean(order_ms)),
                          "step_wall_ms": 1e3 * t_wall / args.steps},
             "roofline": {"kernel": "k_clip", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": clip_traffic, "traffic_source": clip_traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_alg,
                          "note": "latency/FP64-bound irregular kernel; see DESIGN.md and profiles/"},
             "e2e": {"value": total_cells * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),

@@ -100,6 +100,10 @@ int mb_set_tetmesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int* i
                    const int* f_adjs, const int* f_ids);
 /* restrict subsequent mb_rpd3d calls to tets [first, first+count) (multi-GPU tet shards). */
 int mb_set_tet_range(mb_ctx* ctx, int first, int count);
+/* the tet ids stored in the result become (index in the uploaded arrays + base): a rank of a multi-GPU job
+ * uploads only ITS contiguous shard of idx_aos / f_adjs / f_ids / e_adj6 (with the global vertex array, like
+ * the partial-tet calls of rpd_api.cxx:254-281) and still returns global tet ids.  Reset by mb_set_tetmesh. */
+int mb_set_tet_id_base(mb_ctx* ctx, int base);
 /* restrict subsequent mb_rpd3d calls to the listed tets (strictly ascending ids of the resident mesh),
  * the device-side counterpart of load_partial_tet_given_spheres (rpd_api.cxx:482-535): a partial
  * recompute without re-uploading a sub-mesh; cells keep the GLOBAL tet id.  n = 0 clears the subset. */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libmat_b200.so")
 
 # every symbol include/libmat_b200.h declares
 SYMBOLS = [
-    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_subset",
+    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_id_base", "mb_set_tet_subset",
     "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_run_to_host", "mb_rpd_run_to_sink", "mb_rpd_spans", "mb_sink_create", "mb_sink_destroy", "mb_sink_open",
     "mb_sink_close", "mb_host_register", "mb_host_unregister", "mb_copy_to_host", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     vp = C.c_void_p
     lib.mb_set_tetmesh.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]
     lib.mb_set_tet_range.argtypes = [vp, C.c_int, C.c_int]
+    lib.mb_set_tet_id_base.argtypes = [vp, C.c_int]
     lib.mb_set_tet_subset.argtypes = [vp, vp, C.c_int]
     lib.mb_rpd3d.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(vp)]
     lib.mb_rpd_upload_sites.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int]

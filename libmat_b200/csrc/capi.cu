@@ -84,7 +84,7 @@ void mb_destroy(mb_ctx* ctx) {
   ctx->spare_blob.release();
   ctx->spare_cell_off.release();
   TetMeshDev& M = ctx->mesh;
-  M.vert4.release(); M.tet_idx.release(); M.tet_fadj.release(); M.tet_fid.release(); M.tet_e6.release(); M.tet_geo.release(); M.tet_sel.release();
+  M.vert4.release(); M.tet_idx.release(); M.tet_fadj.release(); M.tet_fid.release(); M.tet_e6.release(); M.tet_geo.release(); M.tet_vadj.release(); M.tet_sel.release();
   SitesDev& S = ctx->sites;
   S.site4.release(); S.flags.release(); S.nbr.release(); S.knn_staging.release(); S.soa_staging.release();
   D2MDev& D = ctx->d2m;
@@ -140,6 +140,14 @@ int mb_set_tet_range(mb_ctx* ctx, int first, int count) {
   MB_REQUIRE(first >= 0 && (count < 0 || first + count <= ctx->mesh.n_tet), MB_ERR_ARG, "bad tet range");
   ctx->mesh.range_first = first;
   ctx->mesh.range_count = count;
+  MB_CATCH
+}
+
+int mb_set_tet_id_base(mb_ctx* ctx, int base) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_REQUIRE(ctx->mesh.n_tet > 0, MB_ERR_STATE, "mb_set_tetmesh first (it resets the base to 0)");
+  ctx->mesh.tet_id_base = base;
   MB_CATCH
 }
 
@@ -404,6 +412,8 @@ int mb_rpd_fetch_pairs(mb_rpd_result* res, int* pair_tet, int* pair_site, signed
     if (pair_status) MB_CUDA(cudaMemcpyAsync(pair_status, ctx->pair_status.p, n, cudaMemcpyDeviceToHost, s));
   }
   MB_CUDA(cudaStreamSynchronize(s));
+  if (pair_tet && ctx->mesh.tet_id_base)
+    for (size_t i = 0; i < n; i++) pair_tet[i] += ctx->mesh.tet_id_base;
   MB_CATCH
 }
 

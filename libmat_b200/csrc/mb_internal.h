@@ -100,8 +100,10 @@ struct TetMeshDev {
   DevBuf<int4> tet_fadj;   // f_adjs (int, exact copy)                    16 B / tet
   DevBuf<int4> tet_fid;    // f_ids                                       16 B / tet
   DevBuf<uint2> tet_e6;    // 6 edge adjacency counts as bytes (+2 pad)    8 B / tet
+  DevBuf<unsigned> tet_vadj;  // (uchar) v_adjs of the tet's 4 vertices, packed                    4 B / tet
   DevBuf<float4> tet_geo;  // per tet: 4 face planes + 4 vertex cofactor vectors (k_tet_geometry)  128 B / tet
   int range_first = 0, range_count = -1;
+  int tet_id_base = 0;     // records carry tet id + base (a rank that uploaded only its shard of the tets)
   DevBuf<int> tet_sel;     // optional ascending list of tet ids to process (mb_set_tet_subset)
   int n_sel = 0;
   const int* sel_ptr() const { return n_sel > 0 ? tet_sel.p : nullptr; }

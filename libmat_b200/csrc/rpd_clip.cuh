@@ -35,6 +35,7 @@ struct ClipArgs {
   const int4* tet_fid;
   const uint2* tet_e6;
   const float4* tet_geo;  // per tet: 4 face planes, 4 initial-vertex cofactor vectors (k_tet_geometry)
+  const unsigned* tet_vadj;  // per tet: (uchar) v_adjs of its 4 vertices, packed
   // sites
   const float4* site4;
   int n_site;
@@ -43,6 +44,7 @@ struct ClipArgs {
   int nbr_stride;        // per-site: site_k; per-tet: kcap
   const int* nbr_cnt;    // per-tet lists: #candidates per local tet (nullptr for per-site lists)
   int tet_first;         // first tet of the processed range (per-tet lists are relative to it)
+  int tet_id_base;       // added to the tet id stored in the records (mb_set_tet_id_base: sharded uploads)
   // pairs
   const int* pair_tet;
   const int* pair_site;
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
     if (state == GS_NEW) {
       t = A.pair_tet[pair];
       seed_id = A.pair_site[pair];
-      const int4 vi = A.tet_idx[t];
+      const unsigned vadj4 = A.tet_vadj[t];
       const int4 fadj = A.tet_fadj[t];
       const int4 fid = A.tet_fid[t];
       const uint2 e6u = A.tet_e6[t];
@@ -194,8 +196,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
         S.cof[lane] = c;  // first four entries of the per-vertex filter cache
         S.pnb[lane] = lane == 0 ? fid.x : (lane == 1 ? fid.y : (lane == 2 ? fid.z : fid.w));
         // dual triangles (1,3,2) (0,2,3) (0,3,1) (0,1,2) with w = (uchar)v_adjs (:186-189)
-        const int vid = lane == 0 ? vi.x : (lane == 1 ? vi.y : (lane == 2 ? vi.z : vi.w));
-        const unsigned char w = (unsigned char)__float_as_int(A.vert4[vid].w);
+        const unsigned char w = (unsigned char)((vadj4 >> (8 * lane)) & 0xffu);
         S.ver[lane] = lane == 0 ? make_uchar4(1, 3, 2, w)
                                 : (lane == 1 ? make_uchar4(0, 2, 3, w)
                                              : (lane == 2 ? make_uchar4(0, 3, 1, w) : make_uchar4(0, 1, 2, w)));
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
           blob_at = (long long)at;
           uint32_t* o = A.scratch + at;
           if (lane == 0) {
-            o[0] = (uint32_t)t;
+            o[0] = (uint32_t)(t + A.tet_id_base);
             o[1] = (uint32_t)seed_id;
             o[2] = (uint32_t)nb_v | ((uint32_t)nb_p << 8) | ((uint32_t)nb_e << 16) | ((uint32_t)status << 24);
             o[3] = __float_as_uint(seed.w);

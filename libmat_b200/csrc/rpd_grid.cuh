@@ -309,12 +309,31 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
     const int a = (int)ceilf(rho * G.inv_h * 1.0001f);
     const int side = 2 * a + 1;
     if (isfinite(U) && side <= 8) {
-      // ---- direct walk over the (2a+1)^3 box of fine cells -----------------------------------------
-      const int nbox = side * side * side;
-      for (int b = 0; b < nbox; b += 32) {
+      // ---- direct walk over the (2a+1)^3 box of fine cells, one lane per ROW of cells along k: the
+      // sites are sorted by cell and k is the fastest cell index, so a row is one contiguous run of the
+      // sorted site array (a handful of sites per lane instead of a lane per mostly-empty cell).  Rows
+      // wholly farther than rho are skipped; every site still takes its own L_s <= U test in walk().
+      const int nrows = side * side;
+      const int k0 = max(0, ck - a), k1 = min(R - 1, ck + a);
+      const float lz = G.minz + k0 * G.h, hz = G.minz + (k1 + 1) * G.h;
+      const float dz = fmaxf(0.f, fmaxf(lz - gz, gz - hz));
+      for (int b = 0; b < nrows; b += 32) {
         const int n = b + lane;
         int qb = 0, qe = 0;
-        if (n < nbox) cell_range(ci - a + n / (side * side), cj - a + (n / side) % side, ck - a + n % side, qb, qe);
+        if (n < nrows) {
+          const int i = ci - a + n / side, j = cj - a + n % side;
+          if (i >= 0 && j >= 0 && i < R && j < R) {
+            const float lx = G.minx + i * G.h, ly = G.miny + j * G.h;
+            const float dx = fmaxf(0.f, fmaxf(lx - gx, gx - (lx + G.h)));
+            const float dy = fmaxf(0.f, fmaxf(ly - gy, gy - (ly + G.h)));
+            const float d = fmaxf(0.f, sqrtf(dx * dx + dy * dy + dz * dz) * 0.9999f - Rt);
+            if (d * d - wall <= Ue) {
+              const int c0 = (i * R + j) * R + k0;
+              qb = G.cell_off[c0];
+              qe = G.cell_off[c0 + (k1 - k0) + 1];
+            }
+          }
+        }
         walk(qb, qe);
         U = fminf(U, warp_min(bvu));
         Ue = U + 4e-6f * (fabsf(U) + 2.f * wall) + 1e-3f;

@@ -25,7 +25,7 @@ static inline long long edge_idx_closed(long long v1, long long v2, long long n)
 // minors of their three planes (the filter data of the clip kernel).  Computed once per mesh upload
 // instead of once per (tet, site) cell.  One thread per (tet, face).
 __global__ void k_tet_geometry(const float4* __restrict__ vert4, const int4* __restrict__ tet_idx, int n_tet,
-                               float4* __restrict__ tet_geo) {
+                               float4* __restrict__ tet_geo, unsigned* __restrict__ tet_vadj) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = i >> 2, f = i & 3;
   if (t >= n_tet) return;
@@ -41,6 +41,9 @@ __global__ void k_tet_geometry(const float4* __restrict__ vert4, const int4* __r
   const Minors m = f == 0 ? minors_exact(pl1, pl3, pl2)
                           : (f == 1 ? minors_exact(pl0, pl2, pl3)
                                     : (f == 2 ? minors_exact(pl0, pl3, pl1) : minors_exact(pl0, pl1, pl2)));
+  if (f == 0)  // (uchar) v_adjs of the 4 vertices = w of the 4 initial cell vertices (convex_cell.cu:186-189)
+    tet_vadj[t] = ((unsigned)__float_as_int(q0.w) & 0xffu) | (((unsigned)__float_as_int(q1.w) & 0xffu) << 8) |
+                  (((unsigned)__float_as_int(q2.w) & 0xffu) << 16) | (((unsigned)__float_as_int(q3.w) & 0xffu) << 24);
   tet_geo[(size_t)t * 8 + f] = mine;
   tet_geo[(size_t)t * 8 + 4 + f] = make_float4((float)m.m234, (float)(-m.m134), (float)m.m124, (float)(-m.m123));
 }
@@ -89,8 +92,10 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
   MB_CUDA(cudaMemcpyAsync(M.tet_fadj.p, f_adjs, sizeof(int4) * (size_t)n_tet, cudaMemcpyHostToDevice, s));
   MB_CUDA(cudaMemcpyAsync(M.tet_fid.p, f_ids, sizeof(int4) * (size_t)n_tet, cudaMemcpyHostToDevice, s));
   M.tet_geo.reserve((size_t)n_tet * 8);
+  M.tet_vadj.reserve((size_t)n_tet);
   ctx->n_launches++;
-  k_tet_geometry<<<(unsigned)(((size_t)n_tet * 4 + 255) / 256), 256, 0, s>>>(M.vert4.p, M.tet_idx.p, n_tet, M.tet_geo.p);
+  k_tet_geometry<<<(unsigned)(((size_t)n_tet * 4 + 255) / 256), 256, 0, s>>>(M.vert4.p, M.tet_idx.p, n_tet, M.tet_geo.p,
+                                                                              M.tet_vadj.p);
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaStreamSynchronize(s));
   M.n_vert = n_vert;
@@ -98,6 +103,7 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
   M.range_first = 0;
   M.range_count = -1;
   M.n_sel = 0;
+  M.tet_id_base = 0;
 }
 
 // SoA x|y|z + w -> float4; (site_k+1) x n_site slot-major knn -> row-major [n_site][site_k]
@@ -601,6 +607,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     A.tet_fid = M.tet_fid.p;
     A.tet_e6 = M.tet_e6.p;
     A.tet_geo = M.tet_geo.p;
+    A.tet_vadj = M.tet_vadj.p;
     A.site4 = S.site4.p;
     A.n_site = S.n_site;
     if (S.given) {
@@ -613,6 +620,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
       A.nbr_cnt = ctx->cand_cnt.p;
     }
     A.tet_first = sp.first;
+    A.tet_id_base = M.tet_id_base;
     A.pair_tet = ctx->pair_tet.p;
     A.pair_site = ctx->pair_site.p;
     A.pair_local = ctx->pair_local.p;
@@ -777,7 +785,7 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     }
   }
   cudaStream_t cs = ctx->copy_stream;
-  if (n_chunks <= 0) n_chunks = std::max(1, std::min(32, (t_count + 49151) / 49152));
+  if (n_chunks <= 0) n_chunks = std::max(1, std::min(32, (t_count + 32767) / 32768));
   n_chunks = std::max(1, std::min(n_chunks, std::max(1, t_count)));
   const bool grid_cands = !ctx->sites.given || (opts && opts->grid_candidates);
   GridDev G;

@@ -184,6 +184,10 @@ class Context:
     def set_tet_range(self, first: int, count: int):
         self._check(self.lib.mb_set_tet_range(self._ctx, int(first), int(count)))
 
+    def set_tet_id_base(self, base: int):
+        """records carry (uploaded tet index + base): for ranks that upload only their shard of the tets"""
+        self._check(self.lib.mb_set_tet_id_base(self._ctx, int(base)))
+
     def set_tet_subset(self, tet_ids=None):
         """process only the listed tets (ascending global ids); None / empty clears the subset"""
         if tet_ids is None or len(tet_ids) == 0:

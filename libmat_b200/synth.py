@@ -384,3 +384,34 @@ def make_dist2mat(n_samples: int, nu: int = 100, nv: int = 200, seed: int = RAN_
     prims[tail] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 0]], axis=1)
     prims[tail + 1] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 1]], axis=1)
     return Dist2MatInput(spheres, samples, offset.astype(np.uint32), count.astype(np.uint32), prims, n_co, n_sl)
+
+
+def share_lists(d: Dist2MatInput) -> Dist2MatInput:
+    """The same dist2mat input with every DISTINCT primitive list stored once: samples whose lists are
+    identical (in the reference: samples on the same surface face, fix_geo_error.cxx:149-215) point their
+    (offset, count) at one shared run instead of a private replica (fix_geo_error.cxx:300-366).  The kernel
+    interface already allows it -- offsets are arbitrary -- and results are identical; what changes is the
+    H2D volume (12 B per replicated entry -> 8 B per sample) and the DRAM traffic of the kernel."""
+    off = d.offset.astype(np.int64)
+    cnt = d.count.astype(np.int64)
+    p = d.prims.astype(np.int64)
+    n = len(off)
+    rows = np.repeat(np.arange(n), cnt)
+    pos = np.arange(rows.size) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    src = off[rows] + pos
+    with np.errstate(over="ignore"):
+        h = ((p[src, 0] * 1000003 + p[src, 1]) * 1000003 + p[src, 2]) * (pos * 2654435761 + 12345)
+        per = np.zeros(n, np.int64)
+        np.add.at(per, rows, h)
+        key = per * 4096 + cnt
+    _, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    ucnt = cnt[first]
+    uoff = np.concatenate([[0], np.cumsum(ucnt)[:-1]]).astype(np.int64)
+    urows = np.repeat(np.arange(first.size), ucnt)
+    upos = np.arange(urows.size) - np.repeat(uoff, ucnt)
+    prims = d.prims[off[first][urows] + upos]
+    new_off = uoff[inv]
+    # hash collisions would silently change a list: verify entry by entry
+    assert np.array_equal(prims[new_off[rows] + pos], d.prims[src])
+    return Dist2MatInput(d.spheres, d.samples, new_off.astype(np.uint32), d.count.copy(), np.ascontiguousarray(prims),
+                         d.n_cones, d.n_slabs)

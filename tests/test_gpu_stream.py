@@ -91,3 +91,24 @@ def test_stream_more_chunks_than_tets_and_guards(ctx, cfg1_rt):
         res.emit(mesh.n_surf_faces - 1)
     res.free()
     ctx.set_tet_range(0, -1)
+
+
+def test_shard_upload_with_tet_id_base(ctx, cfg1_rt):
+    """a rank that uploads only its contiguous shard of the tets (global vertices) + mb_set_tet_id_base returns
+    exactly the corresponding slice of the full run, global tet ids included"""
+    mesh, sites, knn, k = cfg1_rt
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, None, 0)
+    first, count = 5000, 9000
+    ctx.set_tet_range(first, count)
+    want = one_shot(ctx)
+    ctx.set_tetmesh(mesh.vertices, mesh.indices[first:first + count], mesh.v_adjs, mesh.f_adjs[first:first + count],
+                    mesh.f_ids[first:first + count], e_adj6=mesh.e_adj6[first:first + count])
+    ctx.set_tet_id_base(first)
+    got = one_shot(ctx)
+    same(want, got)
+    got2, recs = streamed(ctx, 3, want_records=True)
+    same(want, got2)
+    assert recs["tet_id"].min() >= first and recs["tet_id"].max() < first + count
+    pt, ps, st = ctx.run().pairs()
+    assert pt.min() >= first and pt.max() < first + count
