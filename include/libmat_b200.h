@@ -228,6 +228,24 @@ int mb_rpd_fetch_emit(mb_rpd_result* res, int* facet_cell, int* facet_key, unsig
                       int* vert_surf_fid, int* edge_cell, int* edge_key2, int* edge_lvid2,
                       float* cell_euler);
 
+/* K6 power-cell topology summary = the rest of update_power_cells after get_all_voro_info
+ * (rpd_update.cxx:303-316 cell_neighbors, :497-503 cc_cells, :439-470 facet_cc_cells) and the sums
+ * check_cc_and_euler consumes (fix_topo.cxx:81-144, 150-235, 310-380); needs mb_rpd_emit first.
+ *   cell_cc[n_cells]     smallest cell id of the cell's connected component inside its power cell (two cells
+ *                        of a power cell are neighbours iff they share a tet-face id)
+ *   facet_cc[n_facets]   for a half-plane facet (site, neigh) of a cell: smallest FACET index of its component
+ *                        among the cells carrying that half-plane; -1 for tet-face facets
+ *   site_n_cells / site_n_cc / site_euler_sum [n_site]   cells, cell components, double sum of the per-cell
+ *                        Euler values in ascending cell id (euler = sum - n_cells, fix_topo.cxx:128-131)
+ *   pair_site / pair_neigh / pair_n_cc [n_halfplane_pairs]   one entry per half-plane, sorted by (site, neigh):
+ *                        number of components of that facet (is_to_fix_facet_cc: > 1 needs fixing) */
+typedef struct {
+  long n_cells, n_facets, n_sites, n_halfplane_pairs;
+} mb_topo_counts;
+int mb_rpd_topology(mb_rpd_result* res, mb_topo_counts* counts);
+int mb_rpd_fetch_topology(mb_rpd_result* res, int* cell_cc, int* facet_cc, int* site_n_cells, int* site_n_cc,
+                          double* site_euler_sum, int* pair_site, int* pair_neigh, int* pair_n_cc);
+
 /* ---------------------------------------------------------------- dist2mat */
 /* spheres float[4*n_sph] = (cx,cy,cz,r) -- r, not r^2 (fix_geo_error.cxx:324-328);
  * samples float[3*n_samples]; offset/count unsigned[n_samples]; prims int[3*n_prims]:

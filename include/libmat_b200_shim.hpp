@@ -98,21 +98,21 @@ inline std::vector<ConvexCellHost> compute_clipped_voro_diagram_GPU(
     if (std::strcmp(cm, "reference") == 0) opts.grid_candidates = 0;
   // an empty site_knn selects the library's own uniform-grid neighbour search
   const int* knn = site_knn.empty() ? nullptr : site_knn.data();
-  if (mb_rpd3d(ctx, site.data(), site_weights.data(), site_flags.data(), n_site, knn, site_k, &opts, &res))
-    return fail("mb_rpd3d");
-  long n_cells = 0, n_bytes = 0;
+  if (mb_rpd_upload_sites(ctx, site.data(), site_weights.data(), site_flags.data(), n_site, knn, site_k))
+    return fail("mb_rpd_upload_sites");
+  // streamed run: the compact records of tet span c cross PCIe while span c+1 is clipped; on return the whole
+  // result sits in the library's pinned host memory (replaces the D2H of n_tet*tet_k ConvexCellTransfer
+  // records + the std::map dedup of voronoi.cu:717-769)
+  const void* blob_v = nullptr;
+  const long* offs = nullptr;
+  if (mb_rpd_run_to_host(ctx, &opts, 0, &res, &blob_v, &offs)) return fail("mb_rpd_run_to_host");
+  long n_cells = 0;
   mb_rpd_count(res, &n_cells, nullptr, nullptr);
-  mb_rpd_compact_bytes(res, &n_bytes);
-  std::vector<uint32_t> blob((size_t)n_bytes / 4 + 1);
-  std::vector<long> offs((size_t)n_cells + 1);
-  if (mb_rpd_fetch_compact(res, blob.data(), offs.data())) {
-    mb_rpd_free(res);
-    return fail("mb_rpd_fetch_compact");
-  }
-  mb_rpd_free(res);
+  const uint32_t* blob = static_cast<const uint32_t*>(blob_v);
   out.resize((size_t)n_cells);
 #pragma omp parallel for schedule(static)
-  for (long i = 0; i < n_cells; i++) libmat_b200::expand_cell(blob.data() + offs[i] / 4, (int)i, out[(size_t)i]);
+  for (long i = 0; i < n_cells; i++) libmat_b200::expand_cell(blob + offs[i] / 4, (int)i, out[(size_t)i]);
+  mb_rpd_free(res);
   return out;
 }
 #endif

@@ -17,7 +17,7 @@ SYMBOLS = [
     "mb_sink_close", "mb_host_register", "mb_host_unregister", "mb_copy_to_host", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
     "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_cell_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
-    "mb_rpd_fetch_emit", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
+    "mb_rpd_fetch_emit", "mb_rpd_topology", "mb_rpd_fetch_topology", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
 ]
 
 # static-filter bounds (reference src/predicate_generator/main.cpp output; include/libmat_b200.h)
@@ -43,6 +43,10 @@ class RpdOpts(C.Structure):
 
 class EmitCounts(C.Structure):
     _fields_ = [("n_facets", C.c_long), ("n_vertices", C.c_long), ("n_edges", C.c_long)]
+
+
+class TopoCounts(C.Structure):
+    _fields_ = [("n_cells", C.c_long), ("n_facets", C.c_long), ("n_sites", C.c_long), ("n_halfplane_pairs", C.c_long)]
 
 
 class LibMatError(RuntimeError):
@@ -106,6 +110,8 @@ def load() -> C.CDLL:
     lib.mb_rpd_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_long), C.POINTER(vp), C.POINTER(C.c_long)]
     lib.mb_rpd_emit.argtypes = [vp, C.c_int, C.POINTER(EmitCounts)]
     lib.mb_rpd_fetch_emit.argtypes = [vp] + [vp] * 12
+    lib.mb_rpd_topology.argtypes = [vp, C.POINTER(TopoCounts)]
+    lib.mb_rpd_fetch_topology.argtypes = [vp] + [vp] * 8
     lib.mb_dist2mat.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_long, vp, vp, vp]
     lib.mb_dist2mat_upload.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_long]
     lib.mb_dist2mat_run.argtypes = [vp, C.POINTER(C.c_float)]

@@ -348,6 +348,8 @@ void mb_rpd_free(mb_rpd_result* res) {
   res->f_cell.release(); res->f_key.release(); res->v_cell.release(); res->v_lvid.release();
   res->v_key3.release(); res->v_surf.release(); res->e_cell.release(); res->e_key2.release();
   res->e_lvid2.release(); res->f_istet.release(); res->v_pos3.release(); res->c_euler.release();
+  res->t_cell_cc.release(); res->t_facet_cc.release(); res->t_site_n_cells.release(); res->t_site_n_cc.release();
+  res->t_pair_site.release(); res->t_pair_neigh.release(); res->t_pair_ncc.release(); res->t_site_euler.release();
   for (cudaEvent_t e : res->evs) {
     if (res->ctx)
       res->ctx->ev_pool.push_back(e);  // recycled by the next run
@@ -587,6 +589,45 @@ int mb_rpd_fetch_emit(mb_rpd_result* res, int* facet_cell, int* facet_key, unsig
   FETCH(edge_key2, res->e_key2, 2 * c.n_edges, int);
   FETCH(edge_lvid2, res->e_lvid2, 2 * c.n_edges, int);
   FETCH(cell_euler, res->c_euler, res->n_cells, float);
+  MB_CUDA(cudaStreamSynchronize(s));
+  MB_CATCH
+}
+
+int mb_rpd_topology(mb_rpd_result* res, mb_topo_counts* counts) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_REQUIRE(res->emitted, MB_ERR_STATE, "mb_rpd_emit must be called first");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  rpd_topology(ctx, res);
+  if (counts) {
+    counts->n_cells = res->n_cells;
+    counts->n_facets = res->emit_counts.n_facets;
+    counts->n_sites = res->n_site;
+    counts->n_halfplane_pairs = res->topo_pairs;
+  }
+  MB_CATCH
+}
+
+int mb_rpd_fetch_topology(mb_rpd_result* res, int* cell_cc, int* facet_cc, int* site_n_cells, int* site_n_cc,
+                          double* site_euler_sum, int* pair_site, int* pair_neigh, int* pair_n_cc) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_REQUIRE(res->topo_done, MB_ERR_STATE, "mb_rpd_topology must be called first");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const bool have = res->n_cells > 0 && res->emit_counts.n_facets > 0;
+  if (have) {
+    FETCH(cell_cc, res->t_cell_cc, res->n_cells, int);
+    FETCH(facet_cc, res->t_facet_cc, res->emit_counts.n_facets, int);
+    FETCH(pair_site, res->t_pair_site, res->topo_pairs, int);
+    FETCH(pair_neigh, res->t_pair_neigh, res->topo_pairs, int);
+    FETCH(pair_n_cc, res->t_pair_ncc, res->topo_pairs, int);
+  }
+  FETCH(site_n_cells, res->t_site_n_cells, res->n_site, int);
+  FETCH(site_n_cc, res->t_site_n_cc, res->n_site, int);
+  FETCH(site_euler_sum, res->t_site_euler, res->n_site, double);
   MB_CUDA(cudaStreamSynchronize(s));
   MB_CATCH
 }

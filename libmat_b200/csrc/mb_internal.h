@@ -183,6 +183,11 @@ struct mb_rpd_result {
   DevBuf<int> f_cell, f_key, v_cell, v_lvid, v_key3, v_surf, e_cell, e_key2, e_lvid2;
   DevBuf<unsigned char> f_istet;
   DevBuf<float> v_pos3, c_euler;
+  // topology summary (K6)
+  bool topo_done = false;
+  long topo_pairs = 0;
+  DevBuf<int> t_cell_cc, t_facet_cc, t_site_n_cells, t_site_n_cc, t_pair_site, t_pair_neigh, t_pair_ncc;
+  DevBuf<double> t_site_euler;
 };
 
 struct D2MDev {
@@ -256,6 +261,7 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
                      size_t dst_cap_bytes, long long* dst_off, size_t dst_cap_cells);
 void rpd_sync(mb_ctx* ctx, mb_rpd_result* res);
 void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
+void rpd_topology(mb_ctx* ctx, mb_rpd_result* res);  // K6: cell / facet components + Euler sums per power cell
 void rpd_volumes(mb_ctx* ctx, mb_rpd_result* res);  // a12: per-cell / per-site volume + barycentre sums
 
 // ---- dist2mat_kernels.cu -------------------------------------------------------------------

@@ -55,15 +55,17 @@ class RpdLoop:
         ctx.set_mesh(mesh)
         self.last = None
 
-    def step(self, sites: synth.Sites, tet_subset=None, fetch=None, **opts):
-        """upload the sites (H2D), recompute (all tets, or `tet_subset`), optionally fetch the compact
-        result into the caller's pinned buffers (blob_u32, offsets_i64)"""
+    def step(self, sites: synth.Sites, tet_subset=None, fetch=None, to_host=False, **opts):
+        """upload the sites (H2D), recompute (all tets, or `tet_subset`), and deliver the result to the host:
+        to_host=True streams it (mb_rpd_run_to_host: the D2H of tet span c overlaps the kernels of span c+1; the
+        compact result is in the library's pinned memory on return, RpdResult.host_compact()); otherwise the
+        result stays on the device and `fetch` = (blob_u32, offsets_i64) optionally copies it afterwards"""
         ctx = self.ctx
         t0 = time.perf_counter()
         ctx.set_tet_subset(tet_subset)
         ctx.upload_sites(sites.site_soa, sites.weights, sites.flags)
-        res = ctx.run(**opts)
-        if fetch is not None:
+        res = ctx.run_to_host(**opts) if to_host else ctx.run(**opts)
+        if fetch is not None and not to_host:
             ctx._check(ctx.lib.mb_rpd_fetch_compact(res._h, fetch[0].ctypes.data, fetch[1].ctypes.data))
         dt = time.perf_counter() - t0
         if self.last is not None:

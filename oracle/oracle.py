@@ -266,3 +266,83 @@ def emit(recs, max_surf_fid):
         m = cnt[0] if k.startswith("facet") else (cnt[1] if k.startswith("vert") else cnt[2])
         out[k] = out[k][:m].copy()
     return out
+
+
+def topology(em, cell_site, cell_euler):
+    """TEST INFRASTRUCTURE.  Restates the remainder of update_power_cells per power cell, literally with
+    dict / set / BFS like the reference:
+      * tfid_to_cells -> cell_neighbors: the first and last cell of a tet-face id's set become neighbours
+        (rpd_update.cxx:303-316);
+      * get_CC_given_neighbors (include/common_cxx.h:447-489): BFS over cell_neighbors restricted to the
+        visited set -- on all cells of the power cell (update_pc_cc_info, rpd_update.cxx:497-503) and on the
+        cells of every half-plane facet_neigh_to_cells[neigh] (update_pc_facet_cc_info, :439-470);
+      * msphere.euler_sum = double sum of ConvexCellHost::euler over cell_ids in ascending order
+        (is_to_fix_voro_euler, fix_topo.cxx:117-131).
+    `em` is the facet emission of emit() (facet_cell, facet_key, facet_is_tet), cell_site the voro_id of every
+    cell, cell_euler the float per-cell Euler values.  Labels: smallest member of the component."""
+    from collections import defaultdict, deque
+
+    f_cell, f_key, f_tet = em["facet_cell"], em["facet_key"], em["facet_is_tet"]
+    n_cells = len(cell_site)
+    tfid_to_cells = defaultdict(list)          # (site, tfid) -> cells (ascending: facets come cell by cell)
+    facet_neigh_to_cells = defaultdict(dict)   # (site, neigh) -> {cell: facet index}
+    for f in range(len(f_cell)):
+        c = int(f_cell[f])
+        s = int(cell_site[c])
+        if f_tet[f]:
+            tfid_to_cells[(s, int(f_key[f]))].append(c)
+        else:
+            facet_neigh_to_cells[(s, int(f_key[f]))].setdefault(c, f)
+    cell_neighbors = defaultdict(set)
+    for cells in tfid_to_cells.values():
+        if len(cells) == 1:
+            continue
+        c1, c2 = cells[0], cells[-1]
+        if c1 != c2:
+            cell_neighbors[c1].add(c2)
+            cell_neighbors[c2].add(c1)
+
+    def cc_given_neighbors(to_visit):
+        unvisited = set(to_visit)
+        out = []
+        for start in sorted(to_visit):
+            if start not in unvisited:
+                continue
+            comp, q = set(), deque([start])
+            while q:
+                c = q.popleft()
+                if c in comp:
+                    continue
+                comp.add(c)
+                unvisited.discard(c)
+                for nb in cell_neighbors.get(c, ()):
+                    if nb in to_visit and nb not in comp:
+                        q.append(nb)
+            out.append(comp)
+        return out
+
+    cells_of_site = defaultdict(list)
+    for c in range(n_cells):
+        cells_of_site[int(cell_site[c])].append(c)
+    cell_cc = np.full(n_cells, -1, np.int64)
+    site_stats = {}
+    for s, cells in cells_of_site.items():
+        comps = cc_given_neighbors(set(cells))
+        for comp in comps:
+            m = min(comp)
+            for c in comp:
+                cell_cc[c] = m
+        esum = 0.0
+        for c in cells:  # std::set<int> order
+            esum += float(np.float32(cell_euler[c]))
+        site_stats[s] = (len(cells), len(comps), esum)
+    facet_cc = np.full(len(f_cell), -1, np.int64)
+    pairs = {}
+    for (s, n), c2f in facet_neigh_to_cells.items():
+        comps = cc_given_neighbors(set(c2f.keys()))
+        pairs[(s, n)] = len(comps)
+        for comp in comps:
+            m = min(c2f[c] for c in comp)
+            for c in comp:
+                facet_cc[c2f[c]] = m
+    return {"cell_cc": cell_cc, "facet_cc": facet_cc, "site_stats": site_stats, "pairs": pairs}

@@ -57,3 +57,22 @@ def test_loop_partial_subset_matches_full(O, synth):
     for f in ("tet_id", "voro_id", "nb_v", "nb_p", "nb_e", "ver", "id2", "edge"):
         assert np.array_equal(rp[f], want[f]), f
     c.close()
+
+
+def test_loop_streamed_step_equals_device_step(synth):
+    """RpdLoop.step(to_host=True) (streamed D2H) delivers the same compact result as the device-resident step"""
+    from libmat_b200.loop import RpdLoop, evolve_sites
+    from libmat_b200.rpd import Context
+    mesh = synth.make_ball_mesh(10)
+    sites = synth.make_spheres(600)
+    c = Context(0)
+    loop = RpdLoop(c, mesh)
+    for it in range(2):
+        sites, _ = evolve_sites(sites, it)
+        res, _ = loop.step(sites)
+        blob, offs = res.compact()
+        want = (blob[: res.compact_bytes // 4].copy(), offs.copy())
+        res2, _ = loop.step(sites, to_host=True, n_chunks=3)
+        b2, o2 = res2.host_compact()
+        assert np.array_equal(want[0], b2) and np.array_equal(want[1], o2)
+    c.close()

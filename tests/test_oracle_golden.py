@@ -112,3 +112,28 @@ def test_kat3_predicate_bounds():
     from libmat_b200 import capi
     assert float(g["bound_double"]) == capi.FILTER_BOUND_F64 == 1.2466136531027298e-13
     assert np.float32(g["bound_float"]) == np.float32(capi.FILTER_BOUND_F32) == np.float32(6.6876506e-05)
+
+
+def test_topology_oracle_mini(O):
+    """oracle.topology (the dict / set / BFS restatement of update_power_cells' remainder) on the mini config:
+    labels are component minima, components never mix power cells, the neighbour relation is symmetric"""
+    from oracle.gen_golden import mini_inputs
+    mesh, sites, knn, k = mini_inputs()
+    pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
+    ra, _, _ = O.run_pairs(mesh, sites, knn, k, pt, ps, impl="oracle")
+    recs = ra[ra["status"] == 4]
+    em = O.emit(recs, mesh.n_surf_faces - 1)
+    tp = O.topology(em, recs["voro_id"], np.ones(len(recs), np.float32))
+    cc = tp["cell_cc"]
+    assert (cc <= np.arange(len(recs))).all() and (cc[cc] == cc).all()
+    assert np.array_equal(recs["voro_id"][cc], recs["voro_id"])
+    for s, (n_cells, n_cc, esum) in tp["site_stats"].items():
+        sel = recs["voro_id"] == s
+        assert n_cells == int(sel.sum()) and n_cc == len(np.unique(cc[sel])) and esum == float(n_cells)
+    fcc = tp["facet_cc"]
+    hp = em["facet_is_tet"] == 0
+    assert (fcc[~hp] == -1).all() and (fcc[hp] >= 0).all()
+    # a facet component never leaves its (site, neigh) half-plane
+    assert np.array_equal(em["facet_key"][fcc[hp]], em["facet_key"][hp])
+    for (s, n), ncc in tp["pairs"].items():
+        assert ncc >= 1
