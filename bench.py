@@ -337,6 +337,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner on rank 0)
+    # goes to stderr instead; the line itself is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit_line(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libmat_b200 has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
@@ -361,7 +371,7 @@ def main():
             sub.update({"value": n_s * world / (vals.item() * 1e-3), "n_gpus": world, "steps": args.steps,
                         "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                         "dtype": "f32", "data": "synthetic", "gpu_launches": args.steps})
-            print(json.dumps(sub))
+            emit_line(sub)
         ctx.close()
         if world > 1:
             dist.destroy_process_group()
@@ -395,7 +405,7 @@ def main():
                 "e2e": {"value": float(np.median(lat)), "unit": "ms", "h2d_bytes_per_step": int(16 * sites.n_site + 4 * sites.n_site),
                         "d2h_bytes_per_step": int(res.compact_bytes + 8 * (res.n_cells + 1))},
                 "gpu_launches": int(ctx.launch_count())}
-        print(json.dumps(line))
+        emit_line(line)
         ctx.close()
         return
 
@@ -637,7 +647,8 @@ def main():
                     "path": ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_host (%d tet spans, D2H of span c "
                              "overlapped with the kernels of span c+1)" % e2e_chunks) if world == 1 else
                             ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_sink into a shared page-locked host segment "
-                             "(every rank streams its tet shard over its own PCIe link, %d spans each) + directory all-gather" % e2e_chunks
+                             "(every rank streams its tet shard over its own PCIe link, %d spans each%s) + directory all-gather"
+                             % (e2e_chunks, ", slabs first-touched on the GPU's NUMA node" if getattr(sink_host, "numa_pinned", False) else "")
                              if sink_host is not None else "mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run + gather + D2H on rank 0"),
                     "stage_ms": {"set_tetmesh": 1e3 * e2e_parts[0] / e2e_steps, "upload_sites": 1e3 * e2e_parts[1] / e2e_steps,
                                  "run_to_host": 1e3 * e2e_parts[2] / e2e_steps}},
@@ -663,7 +674,7 @@ def main():
                 line["dist2mat"] = bench_dist2mat(ctx, args.samples or 1000000, max(3, args.steps // 2), 3)
             except Exception as exc:  # never lose the headline line
                 line["dist2mat"] = {"error": str(exc)}
-        print(json.dumps(line))
+        emit_line(line)
     for sk in (sink_dev, sink_host):
         if sk is not None:
             sk.close()

@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
   float* s_w = reinterpret_cast<float*>(reinterpret_cast<float4*>(grid_smem) + (size_t)WARPS * KCAP) + (size_t)wib * KCAP;
   int* s_id = reinterpret_cast<int*>(reinterpret_cast<float*>(reinterpret_cast<float4*>(grid_smem) + (size_t)WARPS * KCAP) +
                                      (size_t)WARPS * KCAP) + (size_t)wib * KCAP;
+  int* s_pend = reinterpret_cast<int*>(reinterpret_cast<float*>(reinterpret_cast<float4*>(grid_smem) + (size_t)WARPS * KCAP) +
+                                       2 * (size_t)WARPS * KCAP) + (size_t)wib * 64;  // queue of sites awaiting evaluation
   const int R = G.R, R1 = G.R1;
   const float H1 = 4.f * G.h;
   const int n1 = R1 * R1 * R1;
@@ -259,38 +261,59 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
     const float wall = fmaxf(G.wmax_all, 0.f);
     float Ue = U + 4e-6f * (fabsf(U) + 2.f * wall) + 1e-3f;
 
-    int cnt = 0;
-    // lane <-> fine cell [qb, qe): walk the cell's sites; appends are warp-aggregated
-    auto walk = [&](int qb, int qe) {
-      while (__any_sync(0xffffffffu, qb < qe)) {
+    int cnt = 0, npend = 0;
+    // Sites that pass the cheap L_s <= U test (a few lanes per step) are only QUEUED; the expensive part --
+    // the 4 vertex power distances and the domination tests against the kernel set -- runs on the queue with
+    // converged lanes, 32 sites at a time.
+    auto flush = [&]() {
+      __syncwarp();
+      while (npend > 0) {
+        const int take = min(npend, 32);
         bool ok = false;
         float4 e = make_float4(0, 0, 0, 0);
         float w = 0.f;
-        if (qb < qe) {
-          const float4 s = G.site4[qb];
-          const float dg2 = pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4);
-          const float d = fmaxf(0.f, sqrtf(dg2) * 0.9999f - Rt);
-          if (d * d - s.w - 4e-6f * (dg2 + s.w) <= Ue) {
-            e = pd4(s, p0, p1, p2, p3);
-            w = s.w;
-            bvu = fminf(bvu, fmaxf(fmaxf(e.x, e.y), fmaxf(e.z, e.w)));
-            ok = true;
+        int q = 0;
+        if (lane < take) {
+          q = s_pend[npend - take + lane];
+          const float4 s = G.site4[q];
+          e = pd4(s, p0, p1, p2, p3);
+          w = s.w;
+          bvu = fminf(bvu, fmaxf(fmaxf(e.x, e.y), fmaxf(e.z, e.w)));
+          ok = true;
 #pragma unroll
-            for (int kk = 0; kk < 5; kk++) ok = ok && !dominates(kE[kk], kW[kk], e, w);
-          }
+          for (int kk = 0; kk < 5; kk++) ok = ok && !dominates(kE[kk], kW[kk], e, w);
         }
         const unsigned mk = __ballot_sync(0xffffffffu, ok);
         if (ok) {
           const int pos = cnt + __popc(mk & ((1u << lane) - 1u));
           if (pos < KCAP) {
-            s_id[pos] = G.sorted_id[qb];
+            s_id[pos] = G.sorted_id[q];
             s_pd[pos] = e;
             s_w[pos] = w;
           }
         }
         cnt += __popc(mk);
-        qb++;
+        npend -= take;
       }
+      __syncwarp();
+    };
+    // lane <-> run [qb, qe) of the cell-sorted site array
+    auto walk = [&](int qb, int qe) {
+      while (__any_sync(0xffffffffu, qb < qe)) {
+        bool pass = false;
+        if (qb < qe) {
+          const float4 s = G.site4[qb];
+          const float dg2 = pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4);
+          const float d = fmaxf(0.f, sqrtf(dg2) * 0.9999f - Rt);
+          pass = d * d - s.w - 4e-6f * (dg2 + s.w) <= Ue;
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, pass);
+        if (pass) s_pend[npend + __popc(mk & ((1u << lane) - 1u))] = qb;
+        npend += __popc(mk);
+        qb++;
+        if (npend >= 32) flush();
+      }
+      flush();
     };
     auto cell_range = [&](int i, int j, int k, int& qb, int& qe) {
       qb = qe = 0;

@@ -64,6 +64,7 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
   unsigned char* pin = (unsigned char*)ctx->pin_in.reserve(bytes_v + bytes_e);
   float4* hv = (float4*)pin;
   uint2* he = (uint2*)(pin + bytes_v);
+#pragma omp parallel for schedule(static) if (n_vert > 20000)
   for (int v = 0; v < n_vert; v++) {
     float w;
     int a = v_adjs[v];
@@ -72,6 +73,7 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
                         verts_aos[3 * (size_t)v + 2], w);
   }
   static const int ep[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+#pragma omp parallel for schedule(static) if (n_tet > 20000)
   for (int t = 0; t < n_tet; t++) {
     unsigned long long pk = 0;
     for (int e = 0; e < 6; e++) {
@@ -374,8 +376,8 @@ static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan&
   cudaStream_t s = ctx->stream;
   unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ctx->counters.p);
   constexpr int WARPS = 4;
-  const size_t smem = (size_t)WARPS * KCAP * 24;  // float4 pd + float w + int id per entry
-  const size_t smem_big = (size_t)GRID_BIG_KCAP * 24;
+  const size_t smem = (size_t)WARPS * (KCAP * 24 + 256);  // float4 pd + float w + int id per entry, + 64-entry queue
+  const size_t smem_big = (size_t)GRID_BIG_KCAP * 24 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     MB_CUDA(cudaFuncSetAttribute(k_grid_candidates<GRID_BIG_KCAP, 1, true>,

@@ -66,6 +66,32 @@ def gather_varlen(local: torch.Tensor, dst: int = 0, group=None, out: torch.Tens
     return result, sz
 
 
+def _gpu_numa_cpus(device_index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None when that cannot be determined"""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        if all(hasattr(props, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            bdf = bus.lower()[-12:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class ShardSink:
     """Destination of a sharded run: one slab per rank, [blob bytes | cell offsets], in memory every rank can
     write -- device memory of rank `dst`'s GPU shared through CUDA IPC (kind="device": each rank's ordered
@@ -132,6 +158,20 @@ class ShardSink:
             os.close(fd)
             self.host = np.frombuffer(self._mm, dtype=np.uint8)
             self.base = self.host.ctypes.data
+            # first touch: every rank faults in ITS slab from a CPU of its GPU's NUMA node, so that the shard's
+            # D2H stays on the local socket (page-locking untouched pages would place them all on one node)
+            saved = os.sched_getaffinity(0)
+            cpus = _gpu_numa_cpus(torch.cuda.current_device()) if torch.cuda.is_available() else None
+            try:
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                s0 = self.rank * self.slab_bytes
+                self.host[s0:s0 + self.slab_bytes:4096] = 0
+            finally:
+                os.sched_setaffinity(0, saved)
+            self.numa_pinned = bool(cpus)
+            if self.world > 1:
+                dist.barrier(group=group)
             ctx.host_register(self.base, total)
             if self.world > 1:
                 dist.barrier(group=group)

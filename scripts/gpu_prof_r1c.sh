@@ -4,10 +4,11 @@ set -u
 mkdir -p gpurun_out
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
   --log-file gpurun_out/r1c_launches_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-for K in k_clip k_grid_candidates; do
+for K in k_clip; do
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 \
   -o gpurun_out/r1c_prof_$K -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$K.log 2>&1
 done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_grid_candidates -s 4 -c 1 -o gpurun_out/r1c_prof_k_grid_candidates -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_k2.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dist2mat_q -s 2 -c 1 \
   -o gpurun_out/r1c_prof_k_dist2mat_q -f python bench.py --workload d2m --samples 2000000 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_d2m.log 2>&1
 timeout 900 python bench.py --workload cfg4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r1c_bench_cfg4.json 2> gpurun_out/bench_cfg4.err
