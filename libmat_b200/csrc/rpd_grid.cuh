@@ -90,10 +90,17 @@ __device__ __forceinline__ float box_dist2(float gx, float gy, float gz, const G
   return dx * dx + dy * dy + dz * dz;
 }
 
+// order-preserving float <-> uint key: warp minima go through one REDUX instruction instead of a 5-step
+// shuffle butterfly (inf maps above every finite value; NaN never occurs in these reductions' inputs)
+__device__ __forceinline__ unsigned grid_fkey(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float grid_funkey(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 __device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+  return grid_funkey(__reduce_min_sync(0xffffffffu, grid_fkey(v)));
 }
 
 __device__ __forceinline__ float pd_plain(float4 s, float4 p) {
@@ -117,18 +124,12 @@ __device__ __forceinline__ float4 pd4(float4 s, float4 p0, float4 p1, float4 p2,
   return make_float4(pd_plain(s, p0), pd_plain(s, p1), pd_plain(s, p2), pd_plain(s, p3));
 }
 
-// argmin over the warp of (val, slot): returns the slot of the smallest val (ties: any)
+// argmin over the warp of (val, slot): the slot of the smallest val (ties: the lowest lane holding it)
 __device__ __forceinline__ int warp_argmin(float v, int q) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
-    const int q2 = __shfl_xor_sync(0xffffffffu, q, o);
-    if (v2 < v || (v2 == v && q2 > q)) {
-      v = v2;
-      q = q2;
-    }
-  }
-  return q;
+  const unsigned k = grid_fkey(v);
+  const unsigned m = __reduce_min_sync(0xffffffffu, k);
+  const unsigned who = __ballot_sync(0xffffffffu, k == m);
+  return __shfl_sync(0xffffffffu, q, __ffs(who) - 1);
 }
 
 // One warp per tet, ONE walk over the grid:
@@ -297,20 +298,40 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
       }
       __syncwarp();
     };
-    // lane <-> run [qb, qe) of the cell-sorted site array
+    // every lane brings one run [qb, qe) of the cell-sorted site array; the runs are walked FLATTENED, 32 sites
+    // per step whatever their lengths (owner of flat index f by binary search over the inclusive scan)
     auto walk = [&](int qb, int qe) {
-      while (__any_sync(0xffffffffu, qb < qe)) {
+      const int len = max(qe - qb, 0);
+      int incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      for (int f0 = 0; f0 < total; f0 += 32) {
+        const int f = f0 + lane;
+        int lo = 0;  // smallest lane whose inclusive count exceeds f
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const int v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+          if (v <= f) lo += step;
+        }
+        lo = min(lo, 31);
+        const int o_incl = __shfl_sync(0xffffffffu, incl, lo), o_len = __shfl_sync(0xffffffffu, len, lo);
+        const int o_qb = __shfl_sync(0xffffffffu, qb, lo);
         bool pass = false;
-        if (qb < qe) {
-          const float4 s = G.site4[qb];
+        int q = 0;
+        if (f < total) {
+          q = o_qb + (f - (o_incl - o_len));
+          const float4 s = G.site4[q];
           const float dg2 = pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4);
           const float d = fmaxf(0.f, sqrtf(dg2) * 0.9999f - Rt);
           pass = d * d - s.w - 4e-6f * (dg2 + s.w) <= Ue;
         }
         const unsigned mk = __ballot_sync(0xffffffffu, pass);
-        if (pass) s_pend[npend + __popc(mk & ((1u << lane) - 1u))] = qb;
+        if (pass) s_pend[npend + __popc(mk & ((1u << lane) - 1u))] = q;
         npend += __popc(mk);
-        qb++;
         if (npend >= 32) flush();
       }
       flush();
