@@ -221,6 +221,7 @@ struct mb_ctx {
   DevBuf<long long> span_off[2];
   PinBuf pin_blob, pin_off;
   HostScalars* hs = nullptr;
+  double pairs_per_tet_hint = 0.0;  // grid mode: 1.5 x the largest pairs-per-tet seen (speculative span launches)
   int trace_level = 0;
   bool trace_on = false;       // MB_TRACE=1: host-side stage timers, printed by mb_destroy
   double trace_us[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -49,8 +49,9 @@ struct ClipArgs {
   const int* pair_tet;
   const int* pair_site;
   const int* pair_local;  // local index of the pair's tet in the processed range / subset (per-tet lists)
-  long long n_pairs;
-  int grab;              // pairs a warp takes from the global cursor at a time (multiple of 32/G)
+  long long n_pairs;     // number of pairs; an upper bound (the arrays' capacity) when n_pairs_dev is set
+  const int* n_pairs_dev;  // device-resident pair count (speculative launch: the host has not read it yet)
+  int grab;              // pairs a warp takes from the global cursor at a time (multiple of 32/G); 0 = derive
   // outputs
   signed char* pair_status;
   long long* pair_blob;
@@ -122,6 +123,14 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
   }
   __syncthreads();
 
+  // pair count and cursor granularity (device-side when the launch was speculative)
+  const long long NP = A.n_pairs_dev ? min((long long)*A.n_pairs_dev, A.n_pairs) : A.n_pairs;
+  int GRAB = A.grab;
+  if (GRAB == 0) {
+    long long g = NP / ((long long)gridDim.x * 4 * 16);
+    g = (g / NG) * NG;
+    GRAB = (int)max((long long)NG, min((long long)(8 * NG), g));
+  }
   // warp-level work queue (chunks of pairs from the global cursor) and per-group scratch chunk
   long long wq_next = 0, wq_end = 0;
   bool wq_dry = false;
@@ -155,11 +164,11 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       if (idle) {
         if (wq_next >= wq_end && !wq_dry) {
           unsigned long long b = 0;
-          if (wl == 0) b = atomicAdd(&A.counters[CNT_WORK_CURSOR_IDX], (unsigned long long)A.grab);
+          if (wl == 0) b = atomicAdd(&A.counters[CNT_WORK_CURSOR_IDX], (unsigned long long)GRAB);
           b = __shfl_sync(0xffffffffu, b, 0);
           wq_next = (long long)b;
-          wq_end = min((long long)b + A.grab, A.n_pairs);
-          if (wq_next >= A.n_pairs) wq_dry = true;
+          wq_end = min((long long)b + GRAB, NP);
+          if (wq_next >= NP) wq_dry = true;
         }
         if (state == GS_IDLE) {
           const int r = __popc(idle & ((1u << src) - 1u));

@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_grid_candidates(
 __global__ void k_grid_fill(int tet_first, int tet_count, const int* __restrict__ tet_sel, int kcap, const int* __restrict__ cand_pad,
                             const int* __restrict__ cand_cnt, const int* __restrict__ pair_off,
                             const unsigned* __restrict__ flags, int* __restrict__ pair_tet,
-                            int* __restrict__ pair_site, int* __restrict__ pair_local) {
+                            int* __restrict__ pair_site, int* __restrict__ pair_local, long long cap_pairs) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= tet_count) return;
   const int n = cand_cnt[warp];
@@ -499,8 +499,8 @@ __global__ void k_grid_fill(int tet_first, int tet_count, const int* __restrict_
       f = flags[id] == 1u;
     }
     const unsigned m = __ballot_sync(0xffffffffu, f);
-    if (f) {
-      const int pos = o + __popc(m & ((1u << lane) - 1u));
+    const int pos = o + __popc(m & ((1u << lane) - 1u));
+    if (f && pos < cap_pairs) {  // cap_pairs: speculative capacity (the host checks the true count afterwards)
       pair_tet[pos] = tet_sel ? tet_sel[warp] : tet_first + warp;
       pair_local[pos] = warp;
       pair_site[pos] = id;

@@ -299,10 +299,11 @@ __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* 
 
 // K3's counters and the packed scan total reach the host through mapped memory in one launch
 __global__ void k_publish_k3(const uint32_t* __restrict__ counters, const unsigned long long* __restrict__ total,
-                             HostScalars* __restrict__ hs) {
+                             const int* __restrict__ n_pairs_dev, HostScalars* __restrict__ hs) {
   uint32_t* dst = reinterpret_cast<uint32_t*>(&hs->counters);
   for (int i = threadIdx.x; i < (int)(sizeof(RpdCounters) / 4); i += blockDim.x) dst[i] = counters[i];
   if (threadIdx.x == 0) hs->total_words = (long long)*total;
+  if (threadIdx.x == 1 && n_pairs_dev) hs->n_pairs = *n_pairs_dev;
   __threadfence_system();
 }
 
@@ -416,13 +417,13 @@ static void grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan& sp, in
     launch_grid_candidates<256>(ctx, G, sp, kcap);
 }
 
-static void grid_fill_pairs(mb_ctx* ctx, const TetSpan& sp) {
+static void grid_fill_pairs(mb_ctx* ctx, const TetSpan& sp, long long cap_pairs) {
   cudaStream_t s = ctx->stream;
   const int blocks = (sp.count + 7) / 8;
   ctx->n_launches++;
   k_grid_fill<<<blocks, 256, 0, s>>>(sp.first, sp.count, sp.sel, ctx->cand_kcap, ctx->cand_pad.p,
                                      ctx->cand_cnt.p, ctx->tet_off.p, ctx->sites.flags.p, ctx->pair_tet.p,
-                                     ctx->pair_site.p, ctx->pair_local.p);
+                                     ctx->pair_site.p, ctx->pair_local.p, cap_pairs);
   MB_CUDA(cudaGetLastError());
 }
 
@@ -463,7 +464,7 @@ static void launch_clip(mb_ctx* ctx, ClipArgs A) {
     const long long warps = grid * 4;
     long long g = A.n_pairs / (warps * 16);
     g = (g / NG) * NG;
-    A.grab = (int)std::max<long long>(NG, std::min<long long>(8 * NG, g));
+    A.grab = A.n_pairs_dev ? 0 : (int)std::max<long long>(NG, std::min<long long>(8 * NG, g));  // 0: derived on the device
   }
   ctx->n_launches++;
   k_clip<G, PT><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
@@ -531,7 +532,7 @@ struct SpanStats {
 // to res->evs.  Returns with the ordering kernels enqueued (not synchronised).
 static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res, const TetSpan& sp,
                               const GridDev* grid, DevBuf<uint32_t>& blob, DevBuf<long long>& cell_off,
-                              long long base_bytes) {
+                              long long base_bytes, bool force_sync = false) {
   TetMeshDev& M = ctx->mesh;
   SitesDev& S = ctx->sites;
   cudaStream_t s = ctx->stream;
@@ -553,6 +554,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   ctx->tet_cnt.reserve((size_t)t_count + 1);
   ctx->tet_off.reserve((size_t)t_count + 1);
   const bool grid_cands = grid != nullptr;
+  const bool spec = grid_cands && !force_sync && t_count > 0 && ctx->pairs_per_tet_hint > 0.0;
   if (t_count > 0) {
     if (!grid_cands) {
       ctx->cand_pad.reserve((size_t)t_count * CAND_PAD);
@@ -567,11 +569,19 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     }
     MB_CUDA(cudaMemsetAsync(ctx->tet_cnt.p + t_count, 0, sizeof(int), s));
     exclusive_scan<int>(ctx, ctx->tet_cnt.p, ctx->tet_off.p, (long long)t_count + 1);
-    publish(ctx, ctx->tet_off.p + t_count, &hs->n_pairs, sizeof(int));
-    TRACE(0);  // launch K2
-    MB_CUDA(cudaStreamSynchronize(s));
-    TRACE(1);  // wait K2
-    n_pairs = hs->n_pairs;
+    if (spec) {
+      // SPECULATIVE: the pair count stays on the device; arrays are sized by the pairs-per-tet seen so far
+      // (x1.5) and K3 / the ordering scan are launched without waiting.  The true count comes back with K3's
+      // counters in the span's single synchronisation; a span that exceeded the capacity is redone.
+      n_pairs = (long long)((double)t_count * ctx->pairs_per_tet_hint) + 4096;
+      TRACE(0);
+    } else {
+      publish(ctx, ctx->tet_off.p + t_count, &hs->n_pairs, sizeof(int));
+      TRACE(0);  // launch K2
+      MB_CUDA(cudaStreamSynchronize(s));
+      TRACE(1);  // wait K2
+      n_pairs = hs->n_pairs;
+    }
     ctx->pair_tet.reserve((size_t)n_pairs + 1);
     ctx->pair_site.reserve((size_t)n_pairs + 1);
     ctx->pair_local.reserve((size_t)n_pairs + 1);
@@ -585,7 +595,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
                                                   ctx->pair_site.p);
         MB_CUDA(cudaGetLastError());
       } else {
-        grid_fill_pairs(ctx, sp);
+        grid_fill_pairs(ctx, sp, n_pairs);
       }
     }
   }
@@ -602,6 +612,8 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   DevBuf<long long>& word_off = ctx->word_off;  // packed: cell index << 40 | word offset
   for (int attempt = 0; attempt < 2 && n_pairs > 0; attempt++) {
     ctx->scratch.reserve(scratch_words);
+    if (spec)  // entries beyond the true pair count are never written by K3: they must read as "no record"
+      MB_CUDA(cudaMemsetAsync(ctx->pair_words.p, 0, sizeof(int) * (size_t)(n_pairs + 1), s));
     ClipArgs A;
     A.vert4 = M.vert4.p;
     A.tet_idx = M.tet_idx.p;
@@ -627,6 +639,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     A.pair_site = ctx->pair_site.p;
     A.pair_local = ctx->pair_local.p;
     A.n_pairs = n_pairs;
+    A.n_pairs_dev = spec ? ctx->tet_off.p + t_count : nullptr;
     A.pair_status = ctx->pair_status.p;
     A.pair_blob = ctx->pair_blob.p;
     A.pair_words = ctx->pair_words.p;
@@ -660,13 +673,23 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     }
     ctx->n_launches++;
     k_publish_k3<<<1, 64, 0, s>>>(reinterpret_cast<const uint32_t*>(ctx->counters.p),
-                                  reinterpret_cast<const unsigned long long*>(word_off.p) + n_pairs, hs);
+                                  reinterpret_cast<const unsigned long long*>(word_off.p) + n_pairs,
+                                  spec ? ctx->tet_off.p + t_count : nullptr, hs);
     MB_CUDA(cudaGetLastError());
     TRACE(2);  // launch fill + K3 + ordering scans
     MB_CUDA(cudaStreamSynchronize(s));
     TRACE(3);  // wait K3 + scans
     hc = hs->counters;
     total_words = hs->total_words & PACK_MASK;
+    if (spec && (long long)hs->n_pairs > n_pairs) {
+      // the speculative capacity was too small for this span: raise the estimate and redo it the safe way
+      ctx->pairs_per_tet_hint = 1.5 * (double)hs->n_pairs / (double)t_count;
+      for (int i = 0; i < 4; i++) {
+        ctx->ev_pool.push_back(res->evs.back());
+        res->evs.pop_back();
+      }
+      return rpd_run_span(ctx, opts, res, sp, grid, blob, cell_off, base_bytes, true);
+    }
     if (hc.blob_words <= ctx->scratch.cap) break;
     // scratch too small: rerun K3 with the measured need (rare; statuses are recomputed)
     scratch_words = (size_t)hc.blob_words + (1u << 20);
@@ -689,6 +712,9 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     }
     MB_CUDA(cudaEventRecord(ev[2], s));
   }
+  if (spec) n_pairs = hs->n_pairs;  // the true count (<= capacity)
+  if (grid_cands && t_count > 0)
+    ctx->pairs_per_tet_hint = std::max(ctx->pairs_per_tet_hint, 1.5 * (double)n_pairs / (double)t_count);
   SpanStats st;
   st.n_pairs = n_pairs;
   st.n_cells = (long long)hc.n_valid;
