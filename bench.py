@@ -317,6 +317,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5", "d2m"])
     ap.add_argument("--samples", type=int, default=0, help="dist2mat samples (config 3 is 10 000 000)")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--full-records", action="store_true",
+                    help="streamed legs: ship the records WITH their plane equations (default: lean transport format, "
+                         "mb_rpd_opts.lean_records: equations are recomputed from the ids on expansion)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the shards reach rank 0")
     ap.add_argument("--chunks", type=int, default=0, help="e2e leg: tet spans of the streamed run (0 = automatic)")
     ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
@@ -466,6 +469,7 @@ def main():
     # "nccl": one-shot run, then an all-gather of the sizes + grouped NCCL send/recv (libmat_b200.dist).
     gather_buf = {"t": None}
     sink_dev = sink_host = None
+    lean = not args.full_records
     gather_mode = args.gather if world > 1 else "none"
     if world > 1:
         from libmat_b200.dist import ShardSink
@@ -501,7 +505,7 @@ def main():
         if world == 1:
             return ctx.run(lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates), 0
         if gather_mode == "p2p":
-            res, directory = sink_dev.run(n_chunks=args.chunks, lanes_per_cell=args.lanes)
+            res, directory = sink_dev.run(n_chunks=args.chunks, lanes_per_cell=args.lanes, lean=lean)
             return res, int(directory[:, 0].sum())
         res = ctx.run(lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates)
         return res, gather(res)
@@ -550,7 +554,7 @@ def main():
         e2e_chunks = 1
         if world == 1:
             # the library's own pinned destination is sized by an untimed first streamed run
-            ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates).free()
+            ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates, lean=lean).free()
             blob_host = None
         elif rank == 0:
             blob_host = (torch.empty(int(tot_bytes_guess(rec_bytes, world)), dtype=torch.uint8).pin_memory(),)
@@ -569,7 +573,7 @@ def main():
                 if sink_host is not None:
                     # every rank streams its shard into the shared pinned host segment (all PCIe links in
                     # parallel); after the directory all-gather the whole result is in rank 0's address space
-                    res, directory = sink_host.run(n_chunks=args.chunks, lanes_per_cell=args.lanes)
+                    res, directory = sink_host.run(n_chunks=args.chunks, lanes_per_cell=args.lanes, lean=lean)
                     d2h = int(directory[:, 0].sum() + 8 * (directory[:, 1].sum() + world))
                     e2e_chunks = int(res.n_spans)
                     res.free()
@@ -577,7 +581,7 @@ def main():
                     continue
                 # no shared host segment: gather on rank 0's GPU, then one D2H from there
                 if gather_mode == "p2p":
-                    res, directory = sink_dev.run(n_chunks=args.chunks, lanes_per_cell=args.lanes)
+                    res, directory = sink_dev.run(n_chunks=args.chunks, lanes_per_cell=args.lanes, lean=lean)
                     gathered = int(directory[:, 0].sum())
                 else:
                     res, gathered = step()
@@ -594,7 +598,7 @@ def main():
                 continue
             # streamed run: the D2H of tet span c overlaps the kernels of span c+1; on return the complete
             # compact result (records + offsets) is in pinned host memory
-            res = ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates)
+            res = ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates, lean=lean)
             d2h = res.compact_bytes + 8 * (res.n_cells + 1)
             e2e_chunks = int(res.n_spans)
             res.free()
@@ -630,7 +634,7 @@ def main():
                        "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})" + (", grid candidates" if args.grid_candidates else ", reference relation predicate"),
                        "parallelism": f"tet-shards x{world}, sites replicated" + (
                            "" if world == 1 else (", shards streamed into rank 0's HBM over NVLink peer memory (CUDA IPC, copy-engine DMA "
-                                                  "overlapped with the next tet span) + directory all-gather (NCCL)" if gather_mode == "p2p"
+                                                  "overlapped with the next tet span%s) + directory all-gather (NCCL)" % (", lean records" if lean else "") if gather_mode == "p2p"
                                                   else ", NCCL gather to rank 0 (all-gather of sizes + grouped send/recv)")),
                        "l2": "flushed (512 MB write) between timed steps",
                        "cells_per_step": total_cells, "candidate_pairs_per_step": total_pairs,
@@ -644,6 +648,8 @@ def main():
                          "note": "latency/FP64-bound irregular kernel; see DESIGN.md and profiles/"},
             "e2e": {"value": total_cells * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "records": "lean transport format (ids without plane equations; expansion recomputes them bit-exactly)" if lean
+                               else "full compact records",
                     "path": ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_host (%d tet spans, D2H of span c "
                              "overlapped with the kernels of span c+1)" % e2e_chunks) if world == 1 else
                             ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_sink into a shared page-locked host segment "

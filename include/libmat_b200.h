@@ -122,6 +122,13 @@ typedef struct {
                            the listed neighbours in list order, so valid cells are byte-identical
                            whenever the lists contain every true power neighbour (regular-triangulation
                            lists do); only the set of empty no_intersection pairs differs */
+  int lean_records;     /* streamed runs only (mb_rpd_run_to_host / _to_sink): 1 = the records travel WITHOUT their
+                           plane equations (16 of ~28 bytes per plane, ~38 % of a record): a tet-face plane is a
+                           function of (tet, face), a power bisector of (seed, neighbour) -- the ids stay.  Bit 31
+                           of record word 2 marks the format; mb_rpd_fetch_records / mb_rpd_expand_compact
+                           recompute the equations on the host with the reference's literal arithmetic
+                           (tri2plane common_cuda.h:248-254, new_plane convex_cell.cu:561-592): expanded records
+                           are byte-identical to the full format's */
 } mb_rpd_opts;
 
 /* site_soa float[3*n_site] = x.. | y.. | z.. (rpd_api.cxx:363-365), site_w float[n_site] = r^2,
@@ -175,6 +182,11 @@ int mb_sink_close(mb_ctx* ctx, void* d_peer_ptr);
 int mb_host_register(mb_ctx* ctx, void* host_ptr, size_t bytes);
 int mb_host_unregister(mb_ctx* ctx, void* host_ptr);
 int mb_copy_to_host(mb_ctx* ctx, void* host_dst, const void* d_src, size_t bytes);
+
+/* expand n_cells compact records (full or lean format, as delivered by a streamed run or gathered from several
+ * ranks' sinks) into n_cells * MB_RECORD_BYTES ConvexCellTransfer records; id = first_id + index.  The context
+ * must hold the tet mesh and the sites the records were computed from. */
+int mb_rpd_expand_compact(mb_ctx* ctx, const void* blob, const long* cell_offsets, long n_cells, long first_id, void* dst);
 
 /* number of tet spans the run was cut into (1 for mb_rpd_run); negative mb_status on a NULL handle */
 int mb_rpd_spans(const mb_rpd_result* res);

@@ -93,7 +93,7 @@ inline std::vector<ConvexCellHost> compute_clipped_voro_diagram_GPU(
   // predicate of voronoi.cu:154-193); cells are still clipped by exactly the listed neighbours, so the
   // returned cells are identical whenever site_knn holds every true power neighbour -- the CGAL
   // regular-triangulation lists of rpd_api.cxx do.  MB_CANDIDATES=reference restores the dense predicate.
-  mb_rpd_opts opts = {0, 0, 0, 1};
+  mb_rpd_opts opts = {0, 0, 0, 1, 0};
   if (const char* cm = std::getenv("MB_CANDIDATES"))
     if (std::strcmp(cm, "reference") == 0) opts.grid_candidates = 0;
   // an empty site_knn selects the library's own uniform-grid neighbour search

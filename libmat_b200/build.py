@@ -17,7 +17,7 @@ HEADERS = ["mb_internal.h", "rpd_device.cuh", "rpd_clip.cuh", "rpd_grid.cuh",
            os.path.join("..", "..", "include", "libmat_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-fmad=false", "-Xcompiler", "-fPIC,-fopenmp,-O2", "-Xptxas", "-v"]
+              "-fmad=false", "-Xcompiler", "-fPIC,-fopenmp,-O2,-ffp-contract=off", "-Xptxas", "-v"]
 
 
 def needs_build() -> bool:

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libmat_b200.so")
 # every symbol include/libmat_b200.h declares
 SYMBOLS = [
     "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_id_base", "mb_set_tet_subset",
-    "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_run_to_host", "mb_rpd_run_to_sink", "mb_rpd_spans", "mb_sink_create", "mb_sink_destroy", "mb_sink_open",
+    "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_run_to_host", "mb_rpd_run_to_sink", "mb_rpd_expand_compact", "mb_rpd_spans", "mb_sink_create", "mb_sink_destroy", "mb_sink_open",
     "mb_sink_close", "mb_host_register", "mb_host_unregister", "mb_copy_to_host", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
     "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_cell_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
@@ -38,7 +38,7 @@ RECORD_DTYPE = np.dtype({
 
 class RpdOpts(C.Structure):
     _fields_ = [("lanes_per_cell", C.c_int), ("grid_k", C.c_int), ("want_volumes", C.c_int),
-                ("grid_candidates", C.c_int)]
+                ("grid_candidates", C.c_int), ("lean_records", C.c_int)]
 
 
 class EmitCounts(C.Structure):
@@ -86,6 +86,7 @@ def load() -> C.CDLL:
     lib.mb_rpd_run.argtypes = [vp, vp, C.POINTER(vp)]
     lib.mb_rpd_sync.argtypes = [vp, vp]
     lib.mb_rpd_spans.argtypes = [vp]
+    lib.mb_rpd_expand_compact.argtypes = [vp, vp, vp, C.c_long, C.c_long, vp]
     lib.mb_rpd_run_to_sink.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]
     lib.mb_sink_create.argtypes = [vp, C.c_size_t, C.POINTER(vp), vp]
     lib.mb_sink_destroy.argtypes = [vp, vp]

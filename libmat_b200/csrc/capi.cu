@@ -447,13 +447,52 @@ int mb_rpd_fetch_compact(mb_rpd_result* res, void* blob, long* cell_offsets) {
   MB_CATCH
 }
 
+// ---- host side of the lean transport format: plane equations from the ids ---------------------------------
+// Same operations in the same order as the device code (rpd_device.cuh: tri2plane_exact is evaluated once per tet
+// on the device and fetched; bisector_exact is restated here).  This TU's host code is compiled without FMA
+// contraction (-ffp-contract=off), so every operation rounds like the device's __f*_rn intrinsics.
+static inline float4 bisector_host(const float4& A, const float4& B) {
+  const float dx = A.x - B.x, dy = A.y - B.y, dz = A.z - B.z;
+  const float sx = A.x + B.x, sy = A.y + B.y, sz = A.z + B.z;
+  const float dot = ((sx * dx + sy * dy) + sz * dz) + (B.w - A.w);
+  return make_float4(dx, dy, dz, -dot / 2.f);
+}
+
+struct LeanTables {
+  const float4* tet_planes = nullptr;  // 4 per tet of the resident mesh
+  const float4* site4 = nullptr;
+  int n_tet = 0, n_site = 0, tet_id_base = 0;
+};
+
+// the face planes live on the device (k_tet_geometry); fetched once per mesh upload, on first use
+static LeanTables lean_tables(mb_ctx* ctx) {
+  TetMeshDev& M = ctx->mesh;
+  if (!ctx->h_tet_planes_valid) {
+    ctx->h_tet_planes.resize((size_t)M.n_tet * 4);
+    if (M.n_tet > 0) {
+      MB_CUDA(cudaMemcpy2DAsync(ctx->h_tet_planes.data(), 4 * sizeof(float4), M.tet_geo.p, 8 * sizeof(float4),
+                                4 * sizeof(float4), (size_t)M.n_tet, cudaMemcpyDeviceToHost, ctx->stream));
+      MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->h_tet_planes_valid = true;
+  }
+  LeanTables T;
+  T.tet_planes = ctx->h_tet_planes.data();
+  T.site4 = ctx->h_site4.data();
+  T.n_tet = M.n_tet;
+  T.n_site = (int)ctx->h_site4.size();
+  T.tet_id_base = M.tet_id_base;
+  return T;
+}
+
 // host expansion of one compact record into the ConvexCellTransfer layout
 // (reference src/rpd3d/convex_cell.h:189-217; copy() convex_cell.cu:933-949)
-static void expand_record(const uint32_t* w, unsigned char* dst, int id) {
+static bool expand_record(const uint32_t* w, unsigned char* dst, int id, const LeanTables* T) {
   memset(dst, 0, MB_RECORD_BYTES);
   const int tet = (int)w[0], site = (int)w[1];
   const int nb_v = w[2] & 0xff, nb_p = (w[2] >> 8) & 0xff, nb_e = (w[2] >> 16) & 0xff;
-  const int status = (int)(w[2] >> 24);
+  const bool lean = (w[2] & MB_LEAN_FLAG) != 0;
+  const int status = (int)((w[2] >> 24) & 0x7f);
   int32_t* di = reinterpret_cast<int32_t*>(dst);
   di[0] = status;
   di[1] = id;        // thread_id: debug-only in the reference; the cell index here
@@ -468,11 +507,29 @@ static void expand_record(const uint32_t* w, unsigned char* dst, int id) {
   memcpy(dst + 24, p, 4 * (size_t)nb_v);
   p += nb_v;
   const uint32_t* pl = p;
-  p += 4 * nb_p;
+  if (!lean) p += 4 * nb_p;
   const uint32_t* meta = p;
   p += 3 * nb_p;
+  if (lean) {
+    if (!T) return false;
+    const int tl = tet - T->tet_id_base;
+    if (tl < 0 || tl >= T->n_tet || site < 0 || site >= T->n_site) return false;
+  }
   for (int i = 0; i < nb_p; i++) {
-    memcpy(dst + 416 + 32 * i, pl + 4 * i, 16);
+    if (lean) {
+      float4 eq;
+      if (i < 4) {
+        eq = T->tet_planes[(size_t)(tet - T->tet_id_base) * 4 + i];
+      } else {
+        const int a = (int)meta[3 * i], b = (int)meta[3 * i + 1];
+        const int nb = (a == site) ? b : a;  // id2 = (min, max) of (seed, neighbour)
+        if (nb < 0 || nb >= T->n_site) return false;
+        eq = bisector_host(T->site4[site], T->site4[nb]);
+      }
+      memcpy(dst + 416 + 32 * i, &eq, 16);
+    } else {
+      memcpy(dst + 416 + 32 * i, pl + 4 * i, 16);
+    }
     memcpy(dst + 416 + 32 * i + 16, meta + 3 * i + 2, 4);  // h
     memcpy(dst + 2464 + 8 * i, meta + 3 * i, 8);            // id2
   }
@@ -481,6 +538,27 @@ static void expand_record(const uint32_t* w, unsigned char* dst, int id) {
   memcpy(dst + 3432, &m1, 4);  // euler
   memcpy(dst + 3436, &m1, 4);  // cell_vol
   di[3440 / 4] = id;
+  return true;
+}
+
+static void expand_all(mb_ctx* ctx, const uint32_t* blob, const long long* offs, long n, long first_id, unsigned char* out) {
+  const LeanTables T = lean_tables(ctx);
+  long bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+  for (long i = 0; i < n; i++)
+    bad += expand_record(blob + offs[i] / 4, out + (size_t)i * MB_RECORD_BYTES, (int)(first_id + i), &T) ? 0 : 1;
+  MB_REQUIRE(bad == 0, MB_ERR_STATE,
+             "lean records refer to tets / sites outside the context's resident mesh and sites: expand them with the "
+             "context (mesh, tet id base, sites) they were computed from");
+}
+
+int mb_rpd_expand_compact(mb_ctx* ctx, const void* blob, const long* cell_offsets, long n_cells, long first_id, void* dst) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && blob && cell_offsets && dst && n_cells >= 0, MB_ERR_ARG, "bad arguments");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  expand_all(ctx, static_cast<const uint32_t*>(blob), reinterpret_cast<const long long*>(cell_offsets), n_cells, first_id,
+             static_cast<unsigned char*>(dst));
+  MB_CATCH
 }
 
 int mb_rpd_fetch_records(mb_rpd_result* res, void* dst) {
@@ -509,10 +587,7 @@ int mb_rpd_fetch_records(mb_rpd_result* res, void* dst) {
     offs = o;
     blob = b;
   }
-  unsigned char* out = reinterpret_cast<unsigned char*>(dst);
-#pragma omp parallel for schedule(static)
-  for (long i = 0; i < n; i++)
-    expand_record(blob + offs[i] / 4, out + (size_t)i * MB_RECORD_BYTES, (int)i);
+  expand_all(ctx, blob, offs, n, 0, reinterpret_cast<unsigned char*>(dst));
   MB_CATCH
 }
 

@@ -146,6 +146,7 @@ struct RpdCounters {
   unsigned long long n_gc;         // [18] K3 per-tet mode: dead plane / edge garbage collections
   unsigned long long reserved[5];
 };
+#define MB_LEAN_FLAG 0x80000000u  // bit 31 of a record's word 2: lean transport format
 #define CNT_OVF_TETS 16
 #define CNT_WORK_CURSOR 17
 
@@ -176,6 +177,7 @@ struct mb_rpd_result {
   const uint32_t* host_blob = nullptr;
   const long long* host_off = nullptr;
   int n_spans = 1;
+  bool lean = false;       // records travel without plane equations (mb_rpd_opts.lean_records)
   bool sink_owned = true;  // host_blob points into the context's own pinned buffer (else caller memory)
   // emission (K4)
   bool emitted = false;
@@ -221,6 +223,9 @@ struct mb_ctx {
   DevBuf<long long> span_off[2];
   PinBuf pin_blob, pin_off;
   HostScalars* hs = nullptr;
+  std::vector<float4> h_site4;      // host copy of the sites (lean records: bisectors are recomputed on expansion)
+  std::vector<float4> h_tet_planes; // host copy of the 4 face planes per tet, fetched on first use
+  bool h_tet_planes_valid = false;
   double pairs_per_tet_hint = 0.0;  // grid mode: 1.5 x the largest pairs-per-tet seen (speculative span launches)
   int trace_level = 0;
   bool trace_on = false;       // MB_TRACE=1: host-side stage timers, printed by mb_destroy

@@ -806,7 +806,8 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       if (lane == 0) {
         A.pair_status[pair] = (signed char)status;
         A.pair_blob[pair] = blob_at;
-        A.pair_words[pair] = (blob_at >= 0) ? words : 0;
+        // low 16 bits: record words; high 16 bits: nb_p (the lean transport format drops 4 * nb_p words)
+        A.pair_words[pair] = (blob_at >= 0) ? (words | (nb_p << 16)) : 0;
         if (status == ST_success && blob_at >= 0)
           n_valid++;
         if (status != ST_success) atomicAdd(&blk_cnt[CNT_HIST + status + 1], 1ull);

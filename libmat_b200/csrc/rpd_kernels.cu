@@ -106,6 +106,7 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
   M.range_count = -1;
   M.n_sel = 0;
   M.tet_id_base = 0;
+  ctx->h_tet_planes_valid = false;
 }
 
 // SoA x|y|z + w -> float4; (site_k+1) x n_site slot-major knn -> row-major [n_site][site_k]
@@ -161,6 +162,9 @@ void rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
     ctx->n_launches++;
     k_transpose_knn<<<grid, block, 0, s>>>(S.knn_staging.p, n_site, site_k, S.nbr.p);
   }
+  ctx->h_site4.resize((size_t)n_site);
+  for (int i = 0; i < n_site; i++)
+    ctx->h_site4[(size_t)i] = make_float4(site_soa[i], site_soa[(size_t)n_site + i], site_soa[2 * (size_t)n_site + i], site_w[i]);
   float wmax = 0.f;
   float* bb = ctx->site_bbox;
   bb[0] = bb[1] = bb[2] = INFINITY;
@@ -270,12 +274,18 @@ __global__ void __launch_bounds__(256) k_cand_given(const float4* __restrict__ v
 // =============================================================================================
 #define PACK_SHIFT 40
 #define PACK_MASK ((1ull << PACK_SHIFT) - 1ull)
+// pair_words = record words | nb_p << 16 (0 = no record).  LEAN: the transport format without the 4 * nb_p
+// plane-equation words (recomputable from the ids: tet face planes, power bisectors)
+template <bool LEAN>
 struct PackWords {
-  __host__ __device__ unsigned long long operator()(int words) const {
-    return (unsigned long long)words | ((unsigned long long)(words > 0) << PACK_SHIFT);
+  __host__ __device__ unsigned long long operator()(int pw) const {
+    const int words = pw & 0xffff;
+    const int out = LEAN ? words - 4 * (pw >> 16) : words;
+    return (unsigned long long)out | ((unsigned long long)(words > 0) << PACK_SHIFT);
   }
 };
 
+template <bool LEAN>
 __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* __restrict__ pair_blob,
                          const int* __restrict__ pair_words, const unsigned long long* __restrict__ packed_off,
                          long long n_pairs, uint32_t* __restrict__ blob, long long* __restrict__ cell_off,
@@ -284,12 +294,22 @@ __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* 
   const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int lane = threadIdx.x & 7;
   if (g >= n_pairs) return;
-  const int words = pair_words[g];
+  const int pw = pair_words[g];
+  const int words = pw & 0xffff;
   if (words == 0) return;
   const unsigned long long pk = packed_off[g];
   const long long dst = (long long)(pk & PACK_MASK);
   const uint32_t* src = scratch + pair_blob[g];
-  for (int i = lane; i < words; i += 8) blob[dst + i] = src[i];
+  if (LEAN) {
+    // [4 header | nb_v vertices] [4*nb_p plane equations: dropped] [3*nb_p ids | edges]
+    const int nb_p = pw >> 16;
+    const int head = 4 + (int)(src[2] & 0xffu);
+    const int skip = 4 * nb_p;
+    for (int i = lane; i < head; i += 8) blob[dst + i] = (i == 2) ? (src[2] | MB_LEAN_FLAG) : src[i];
+    for (int i = head + skip + lane; i < words; i += 8) blob[dst + i - skip] = src[i];
+  } else {
+    for (int i = lane; i < words; i += 8) blob[dst + i] = src[i];
+  }
   if (lane == 0) {
     const long long c = (long long)(pk >> PACK_SHIFT);
     cell_off[c] = base_bytes + dst * 4;
@@ -532,7 +552,7 @@ struct SpanStats {
 // to res->evs.  Returns with the ordering kernels enqueued (not synchronised).
 static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res, const TetSpan& sp,
                               const GridDev* grid, DevBuf<uint32_t>& blob, DevBuf<long long>& cell_off,
-                              long long base_bytes, bool force_sync = false) {
+                              long long base_bytes, bool lean, bool force_sync = false) {
   TetMeshDev& M = ctx->mesh;
   SitesDev& S = ctx->sites;
   cudaStream_t s = ctx->stream;
@@ -663,13 +683,20 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     word_off.reserve((size_t)n_pairs + 1);
     MB_CUDA(cudaMemsetAsync(ctx->pair_words.p + n_pairs, 0, sizeof(int), s));
     {
-      cub::TransformInputIterator<unsigned long long, PackWords, const int*> in(ctx->pair_words.p, PackWords());
       unsigned long long* outp = reinterpret_cast<unsigned long long*>(word_off.p);
       size_t tmp = 0;
-      MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, outp, n_pairs + 1, s));
-      ctx->cub_tmp.reserve(tmp);
       ctx->n_launches += 2;
-      MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, outp, n_pairs + 1, s));
+      if (lean) {
+        cub::TransformInputIterator<unsigned long long, PackWords<true>, const int*> in(ctx->pair_words.p, PackWords<true>());
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, outp, n_pairs + 1, s));
+        ctx->cub_tmp.reserve(tmp);
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, outp, n_pairs + 1, s));
+      } else {
+        cub::TransformInputIterator<unsigned long long, PackWords<false>, const int*> in(ctx->pair_words.p, PackWords<false>());
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, outp, n_pairs + 1, s));
+        ctx->cub_tmp.reserve(tmp);
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, outp, n_pairs + 1, s));
+      }
     }
     ctx->n_launches++;
     k_publish_k3<<<1, 64, 0, s>>>(reinterpret_cast<const uint32_t*>(ctx->counters.p),
@@ -688,7 +715,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
         ctx->ev_pool.push_back(res->evs.back());
         res->evs.pop_back();
       }
-      return rpd_run_span(ctx, opts, res, sp, grid, blob, cell_off, base_bytes, true);
+      return rpd_run_span(ctx, opts, res, sp, grid, blob, cell_off, base_bytes, lean, true);
     }
     if (hc.blob_words <= ctx->scratch.cap) break;
     // scratch too small: rerun K3 with the measured need (rare; statuses are recomputed)
@@ -733,9 +760,14 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     blob.reserve((size_t)total_words + 4);
     if (total_words > 0) {
       ctx->n_launches++;
-      k_gather<<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
-          ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, reinterpret_cast<const unsigned long long*>(word_off.p),
-          n_pairs, blob.p, cell_off.p, total_words, st.n_cells, base_bytes);
+      if (lean)
+        k_gather<true><<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
+            ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, reinterpret_cast<const unsigned long long*>(word_off.p),
+            n_pairs, blob.p, cell_off.p, total_words, st.n_cells, base_bytes);
+      else
+        k_gather<false><<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
+            ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, reinterpret_cast<const unsigned long long*>(word_off.p),
+            n_pairs, blob.p, cell_off.p, total_words, st.n_cells, base_bytes);
       MB_CUDA(cudaGetLastError());
     }
   }
@@ -775,8 +807,10 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   MB_CUDA(cudaEventRecord(e0, ctx->stream));
   if (grid_cands && t_count > 0) G = grid_build(ctx);
   const TetSpan sp = {t_first, t_count, ctx->mesh.sel_ptr()};
+  MB_REQUIRE(!(opts && opts->lean_records), MB_ERR_ARG,
+             "lean_records is a transport format of the streamed runs (mb_rpd_run_to_host / mb_rpd_run_to_sink)");
   const SpanStats st = rpd_run_span(ctx, opts, res, sp, (grid_cands && t_count > 0) ? &G : nullptr, res->blob,
-                                    res->cell_off, 0);
+                                    res->cell_off, 0, false);
   // fold K1 into the candidate stage: replace the span's start event by e0
   ctx->ev_pool.push_back(res->evs[0]);
   res->evs[0] = e0;
@@ -801,6 +835,8 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
 void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res, void* dst_blob,
                      size_t dst_cap_bytes, long long* dst_off, size_t dst_cap_cells) {
   const bool own = dst_blob == nullptr;
+  const bool lean = opts && opts->lean_records;
+  res->lean = lean;
   int t_first, t_count;
   run_prologue(ctx, opts, res, t_first, t_count);
   MB_REQUIRE(!res->want_volumes, MB_ERR_ARG, "want_volumes is not available in the streamed run");
@@ -839,7 +875,7 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     const int b = c & 1;
     if (c >= 2) MB_CUDA(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));  // span c-2 has left the buffer
     const SpanStats st = rpd_run_span(ctx, opts, res, sp, (grid_cands && c_count > 0) ? &G : nullptr,
-                                      ctx->span_blob[b], ctx->span_off[b], acc_bytes);
+                                      ctx->span_blob[b], ctx->span_off[b], acc_bytes, lean);
     if (c == 0) {
       ctx->ev_pool.push_back(res->evs[0]);
       res->evs[0] = e0;

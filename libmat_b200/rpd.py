@@ -220,25 +220,25 @@ class Context:
         self._check(self.lib.mb_rpd_upload_sites(self._ctx, ptr(ss), ptr(sw), ptr(sf), sw.size, ptr(knn), int(site_k)))
 
     def run(self, lanes_per_cell=0, grid_k=0, want_volumes=False, grid_candidates=False) -> RpdResult:
-        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), int(want_volumes), int(grid_candidates))
+        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), int(want_volumes), int(grid_candidates), 0)
         h = C.c_void_p()
         self._check(self.lib.mb_rpd_run(self._ctx, C.byref(opts), C.byref(h)))
         self._check(self.lib.mb_rpd_sync(self._ctx, h))
         return RpdResult(self, h)
 
-    def run_to_host(self, n_chunks=0, lanes_per_cell=0, grid_k=0, grid_candidates=False) -> RpdResult:
+    def run_to_host(self, n_chunks=0, lanes_per_cell=0, grid_k=0, grid_candidates=False, lean=False) -> RpdResult:
         """streamed run (mb_rpd_run_to_host): D2H of span c overlaps the kernels of span c+1; the complete
         compact result is in pinned host memory on return (RpdResult.host_compact())"""
-        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), 0, int(grid_candidates))
+        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), 0, int(grid_candidates), int(lean))
         h, bp, op = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self.lib.mb_rpd_run_to_host(self._ctx, C.byref(opts), int(n_chunks), C.byref(h), C.byref(bp), C.byref(op)))
         return RpdResult(self, h, host_ptrs=(bp.value, op.value))
 
     def run_to_sink(self, sink_blob_ptr: int, cap_bytes: int, sink_off_ptr: int, cap_cells: int, n_chunks=0,
-                    lanes_per_cell=0, grid_k=0, grid_candidates=False) -> RpdResult:
+                    lanes_per_cell=0, grid_k=0, grid_candidates=False, lean=False) -> RpdResult:
         """streamed run into caller memory (mb_rpd_run_to_sink): pinned / registered host memory, device memory
         of this GPU or of a peer GPU (mb_sink_open) -- the multi-GPU gather fused into the run"""
-        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), 0, int(grid_candidates))
+        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), 0, int(grid_candidates), int(lean))
         h = C.c_void_p()
         self._check(self.lib.mb_rpd_run_to_sink(self._ctx, C.byref(opts), int(n_chunks), C.c_void_p(sink_blob_ptr),
                                                 int(cap_bytes), C.c_void_p(sink_off_ptr), int(cap_cells), C.byref(h)))
@@ -271,6 +271,16 @@ class Context:
 
     def copy_to_host(self, host_array: np.ndarray, d_src: int, nbytes: int):
         self._check(self.lib.mb_copy_to_host(self._ctx, ptr(host_array), C.c_void_p(d_src), int(nbytes)))
+
+    def expand_compact(self, blob: np.ndarray, offsets: np.ndarray, first_id: int = 0) -> np.ndarray:
+        """compact records (full or lean, e.g. gathered from several ranks) -> ConvexCellTransfer records; the
+        context must hold the mesh and sites they were computed from"""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = len(offsets) - 1
+        out = np.zeros(n, dtype=RECORD_DTYPE)
+        if n:
+            self._check(self.lib.mb_rpd_expand_compact(self._ctx, ptr(np.ascontiguousarray(blob)), ptr(offsets), n, int(first_id), ptr(out)))
+        return out
 
     def compute_clipped_voro_diagram(self, site, site_weights, site_flags, site_knn=None, site_k=0,
                                      **opts) -> RpdResult:

@@ -46,6 +46,14 @@ def _worker(rank, world, port, kind, out_dir):
             blob, offs = sink.read_host(directory)
             np.savez(os.path.join(out_dir, f"got_{kind}_{n_chunks}.npz"), blob=blob, offs=offs)
         dist.barrier()
+    # lean transport format through the sink; rank 0 (which holds the whole mesh + sites) expands all shards
+    res, directory = sink.run(n_chunks=2, lean=True)
+    res.free()
+    if rank == 0:
+        blob, offs = sink.read_host(directory)
+        recs = ctx.expand_compact(blob.view(np.uint32) if blob.size % 4 == 0 else blob, offs)
+        np.save(os.path.join(out_dir, f"lean_{kind}.npy"), recs)
+    dist.barrier()
     # a sink that is too small is an error, not a truncation
     small = ShardSink(ctx, 4096, 8, kind=kind, tag=f"mb_test_small_{port}")
     try:
@@ -71,6 +79,7 @@ def test_two_rank_sink_equals_single_process(ctx, synth, tmp_path, kind):
     blob, offs = res.compact()
     want_blob = blob[: res.compact_bytes // 4].view(np.uint8).copy()
     want_offs = offs.copy()
+    want_recs = res.records()
     res.free()
     mpc = mp.get_context("spawn")
     port = _free_port()
@@ -88,3 +97,5 @@ def test_two_rank_sink_equals_single_process(ctx, synth, tmp_path, kind):
         got = np.load(tmp_path / f"got_{kind}_{n_chunks}.npz")
         assert np.array_equal(got["offs"], want_offs)
         assert np.array_equal(got["blob"], want_blob)
+    lean = np.load(tmp_path / f"lean_{kind}.npy")
+    assert lean.tobytes() == want_recs.tobytes()

@@ -112,3 +112,33 @@ def test_shard_upload_with_tet_id_base(ctx, cfg1_rt):
     assert recs["tet_id"].min() >= first and recs["tet_id"].max() < first + count
     pt, ps, st = ctx.run().pairs()
     assert pt.min() >= first and pt.max() < first + count
+
+
+@pytest.mark.parametrize("mode", ["grid", "given"])
+def test_lean_records_expand_to_the_full_records(ctx, cfg1, cfg1_rt, mode):
+    """lean transport format (records without plane equations): the host expansion recomputes tet-face planes and
+    power bisectors from the ids and must reproduce the full-format records byte for byte -- plane equations
+    included -- in both modes, through fetch_records and through expand_compact"""
+    mesh, sites, knn, k = cfg1_rt if mode == "grid" else cfg1
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, None if mode == "grid" else knn, 0 if mode == "grid" else k)
+    full = ctx.run()
+    want = full.records()
+    full_bytes = full.compact_bytes
+    full.free()
+    res = ctx.run_to_host(n_chunks=3, lean=True)
+    assert res.n_cells == len(want)
+    assert res.compact_bytes < 0.75 * full_bytes
+    got = res.records()
+    blob, offs = res.host_compact()
+    got2 = ctx.expand_compact(blob, offs)
+    res.free()
+    for f in want.dtype.names:
+        assert np.ascontiguousarray(want[f]).tobytes() == np.ascontiguousarray(got[f]).tobytes(), f
+        assert np.ascontiguousarray(want[f]).tobytes() == np.ascontiguousarray(got2[f]).tobytes(), f
+    # the one-shot, device-resident run refuses the transport format
+    from libmat_b200 import capi
+    import ctypes as C
+    opts = capi.RpdOpts(0, 0, 0, 0, 1)
+    h = C.c_void_p()
+    assert ctx.lib.mb_rpd_run(ctx._ctx, C.byref(opts), C.byref(h)) != 0
