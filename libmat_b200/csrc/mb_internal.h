@@ -157,6 +157,7 @@ struct HostScalars {
   long long total_words;
   RpdCounters counters;
   long long zero;
+  unsigned long long seq;  // written last by every publish kernel; the host spins on it
 };
 
 struct mb_rpd_result {
@@ -223,6 +224,7 @@ struct mb_ctx {
   DevBuf<long long> span_off[2];
   PinBuf pin_blob, pin_off;
   HostScalars* hs = nullptr;
+  unsigned long long publish_seq = 0;
   std::vector<float4> h_site4;      // host copy of the sites (lean records: bisectors are recomputed on expansion)
   std::vector<float4> h_tet_planes; // host copy of the 4 face planes per tet, fetched on first use
   bool h_tet_planes_valid = false;

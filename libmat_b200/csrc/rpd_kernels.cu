@@ -3,6 +3,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 
@@ -319,12 +320,14 @@ __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* 
 
 // K3's counters and the packed scan total reach the host through mapped memory in one launch
 __global__ void k_publish_k3(const uint32_t* __restrict__ counters, const unsigned long long* __restrict__ total,
-                             const int* __restrict__ n_pairs_dev, HostScalars* __restrict__ hs) {
+                             const int* __restrict__ n_pairs_dev, HostScalars* __restrict__ hs, unsigned long long seq) {
   uint32_t* dst = reinterpret_cast<uint32_t*>(&hs->counters);
   for (int i = threadIdx.x; i < (int)(sizeof(RpdCounters) / 4); i += blockDim.x) dst[i] = counters[i];
   if (threadIdx.x == 0) hs->total_words = (long long)*total;
   if (threadIdx.x == 1 && n_pairs_dev) hs->n_pairs = *n_pairs_dev;
   __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(&hs->seq) = seq;
 }
 
 // =============================================================================================
@@ -495,20 +498,54 @@ static void launch_clip(mb_ctx* ctx, ClipArgs A) {
 // kernel into mapped pinned host memory instead of being fetched with cudaMemcpy: a D2H copy on the
 // compute stream would queue behind the streamed run's bulk record copies on the copy engine and
 // serialise the two streams.
-__global__ void k_publish_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst_mapped, int n) {
+__global__ void k_publish_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst_mapped, int n,
+                                volatile unsigned long long* seq_mapped, unsigned long long seq) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst_mapped[i] = src[i];
   __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *seq_mapped = seq;  // the host spins on this word (wait_published)
+}
+
+static HostScalars* host_scalars(mb_ctx* ctx);
+static inline double now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 static void publish(mb_ctx* ctx, const void* src, void* dst_mapped, size_t bytes) {
+  HostScalars* hs = host_scalars(ctx);
   ctx->n_launches++;
   k_publish_words<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(src),
-                                             reinterpret_cast<uint32_t*>(dst_mapped), (int)(bytes / 4));
+                                             reinterpret_cast<uint32_t*>(dst_mapped), (int)(bytes / 4), &hs->seq,
+                                             ++ctx->publish_seq);
+  MB_CUDA(cudaGetLastError());
+}
+
+// Wait for the last publish on the stream.  The publish kernel is the last operation enqueued before the wait and
+// writes the sequence word after its payload (system-scope fence), so seeing the word means everything before
+// it on the stream has completed.  Spinning on mapped memory wakes the host within a microsecond or two of the
+// write crossing PCIe; cudaStreamSynchronize is interrupt-driven and costs tens of microseconds per wake-up,
+// paid once per tet span.  Falls back to the runtime's wait after 2 ms of spinning (long kernels) and to report
+// errors.
+static void wait_published(mb_ctx* ctx) {
+  HostScalars* hs = host_scalars(ctx);
+  const volatile unsigned long long* seq = &hs->seq;
+  const unsigned long long want = ctx->publish_seq;
+  const double t0 = now_us();
+  while (*seq != want) {
+    if (now_us() - t0 > 2000.0) {
+      MB_CUDA(cudaStreamSynchronize(ctx->stream));
+      break;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);  // payload reads stay behind the sequence-word read
   MB_CUDA(cudaGetLastError());
 }
 
 static HostScalars* host_scalars(mb_ctx* ctx) {
-  if (!ctx->hs) MB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->hs), sizeof(HostScalars), cudaHostAllocMapped));
+  if (!ctx->hs) {
+    MB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->hs), sizeof(HostScalars), cudaHostAllocMapped));
+    memset(ctx->hs, 0, sizeof(HostScalars));
+  }
   return ctx->hs;
 }
 
@@ -524,9 +561,6 @@ static cudaEvent_t take_event(mb_ctx* ctx) {
 }
 
 // host-side stage timers (MB_TRACE=1): where the host thread spends a span -- launching or waiting
-static inline double now_us() {
-  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
 #define TRACE(slot)                                  \
   do {                                               \
     if (ctx->trace_on) {                             \
@@ -598,7 +632,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     } else {
       publish(ctx, ctx->tet_off.p + t_count, &hs->n_pairs, sizeof(int));
       TRACE(0);  // launch K2
-      MB_CUDA(cudaStreamSynchronize(s));
+      wait_published(ctx);
       TRACE(1);  // wait K2
       n_pairs = hs->n_pairs;
     }
@@ -701,10 +735,10 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     ctx->n_launches++;
     k_publish_k3<<<1, 64, 0, s>>>(reinterpret_cast<const uint32_t*>(ctx->counters.p),
                                   reinterpret_cast<const unsigned long long*>(word_off.p) + n_pairs,
-                                  spec ? ctx->tet_off.p + t_count : nullptr, hs);
+                                  spec ? ctx->tet_off.p + t_count : nullptr, hs, ++ctx->publish_seq);
     MB_CUDA(cudaGetLastError());
     TRACE(2);  // launch fill + K3 + ordering scans
-    MB_CUDA(cudaStreamSynchronize(s));
+    wait_published(ctx);
     TRACE(3);  // wait K3 + scans
     hc = hs->counters;
     total_words = hs->total_words & PACK_MASK;
@@ -732,7 +766,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   if (n_pairs == 0) {
     if (t_count > 0) {  // candidate-stage counters of a span without pairs
       publish(ctx, ctx->counters.p, &hs->counters, sizeof(RpdCounters));
-      MB_CUDA(cudaStreamSynchronize(s));
+      wait_published(ctx);
       hc = hs->counters;
     } else {
       memset(&hc, 0, sizeof hc);
