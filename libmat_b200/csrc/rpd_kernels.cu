@@ -65,7 +65,7 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
   unsigned char* pin = (unsigned char*)ctx->pin_in.reserve(bytes_v + bytes_e);
   float4* hv = (float4*)pin;
   uint2* he = (uint2*)(pin + bytes_v);
-#pragma omp parallel for schedule(static) if (n_vert > 20000)
+#pragma omp parallel for schedule(static) num_threads(4) if (n_vert > 100000)
   for (int v = 0; v < n_vert; v++) {
     float w;
     int a = v_adjs[v];
@@ -74,7 +74,7 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
                         verts_aos[3 * (size_t)v + 2], w);
   }
   static const int ep[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
-#pragma omp parallel for schedule(static) if (n_tet > 20000)
+#pragma omp parallel for schedule(static) num_threads(4) if (n_tet > 100000)
   for (int t = 0; t < n_tet; t++) {
     unsigned long long pk = 0;
     for (int e = 0; e < 6; e++) {
