@@ -201,6 +201,10 @@ int mb_rpd_count(const mb_rpd_result* res, long* n_cells, long* n_pairs, long* n
  * (truncated: should be 0)  [5] compact result bytes  [6] tets redone by the big-list candidate pass
  * [7] conflict tests the FP32 filter could not decide (evaluated with the FP64 determinant) */
 int mb_rpd_stats(const mb_rpd_result* res, long stats[8]);
+/* grid-kNN mode internals: cells that outgrew the compact caps of K3's first pass (48 planes / 72 vertices /
+ * 120 edges) and were recomputed by the second pass at the reference's caps (64 / 96 / 152), and dead plane /
+ * edge garbage collections */
+int mb_rpd_clip_passes(const mb_rpd_result* res, long* n_second_pass_cells, long* n_garbage_collections);
 /* int[10]: index = status+1 (early_return .. needs_perturb), over all candidate pairs */
 int mb_rpd_status_histogram(const mb_rpd_result* res, long hist[10]);
 /* kernel milliseconds of the last run: [0]=candidates (K1+K2) [1]=clip (K3) [2]=emit (K4)

@@ -91,7 +91,7 @@ void mb_destroy(mb_ctx* ctx) {
   D.spheres.release(); D.samples.release(); D.offset.release(); D.count.release(); D.prims.release();
   D.result.release(); D.closest.release(); D.tie.release();
   ctx->tet_cnt.release(); ctx->tet_off.release(); ctx->pair_tet.release(); ctx->pair_site.release(); ctx->pair_local.release();
-  ctx->cand_pad.release(); ctx->cand_cnt.release(); ctx->ovf_list.release(); ctx->word_off.release(); ctx->pair_valid.release();
+  ctx->cand_pad.release(); ctx->redo_list.release(); ctx->cand_cnt.release(); ctx->ovf_list.release(); ctx->word_off.release(); ctx->pair_valid.release();
   ctx->pair_cell.release(); ctx->pair_status.release(); ctx->pair_blob.release(); ctx->pair_words.release();
   ctx->scratch.release(); ctx->counters.release(); ctx->cub_tmp.release();
   ctx->grid_cnt.release(); ctx->grid_off.release(); ctx->grid_sorted_id.release(); ctx->grid_cell_of.release();
@@ -379,6 +379,13 @@ int mb_rpd_stats(const mb_rpd_result* res, long stats[8]) {
   stats[5] = res->compact_bytes;
   stats[6] = res->n_ovf_tets;
   stats[7] = res->n_exact;
+  return MB_OK;
+}
+
+int mb_rpd_clip_passes(const mb_rpd_result* res, long* n_second_pass_cells, long* n_garbage_collections) {
+  if (!res) return MB_ERR_ARG;
+  if (n_second_pass_cells) *n_second_pass_cells = res->n_redo;
+  if (n_garbage_collections) *n_garbage_collections = res->n_gc;
   return MB_OK;
 }
 

@@ -144,7 +144,9 @@ struct RpdCounters {
   unsigned long long n_ovf_tets;   // [16] grid mode: tets handed to the big-list candidate pass
   unsigned long long work_cursor;  // [17] K3 dynamic work distribution
   unsigned long long n_gc;         // [18] K3 per-tet mode: dead plane / edge garbage collections
-  unsigned long long reserved[5];
+  unsigned long long n_redo;       // [19] grid mode: cells recomputed at the reference's caps by K3's second pass
+  unsigned long long work_cursor2; // [20] second pass work distribution
+  unsigned long long reserved[3];
 };
 #define MB_LEAN_FLAG 0x80000000u  // bit 31 of a record's word 2: lean transport format
 #define CNT_OVF_TETS 16
@@ -163,6 +165,7 @@ struct HostScalars {
 struct mb_rpd_result {
   mb_ctx* ctx = nullptr;
   long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0, n_cand_overflow = 0, n_ovf_tets = 0, n_exact = 0;
+  long n_redo = 0, n_gc = 0;
   long hist[10] = {0};
   long compact_bytes = 0;
   float ms[4] = {0, 0, 0, 0};
@@ -235,6 +238,7 @@ struct mb_ctx {
   std::vector<cudaEvent_t> ev_pool;   // timing events recycled between runs
   // rpd scratch (reused across calls)
   DevBuf<int> tet_cnt, tet_off, pair_tet, pair_site, pair_local, cand_pad;
+  DevBuf<int> redo_list;           // grid mode: pairs whose cell outgrew the compact caps of K3's first pass
   DevBuf<int> cand_cnt;            // grid mode: #candidates per tet (cand_pad holds the lists)
   DevBuf<int> ovf_list;            // grid mode: tets whose survivor list overflowed the fast pass
   int cand_kcap = 0;               // grid mode: row stride of cand_pad

@@ -59,6 +59,10 @@ struct ClipArgs {
   uint32_t* scratch;
   unsigned long long scratch_words;
   unsigned long long* counters;  // RpdCounters as u64 array
+  // compact-caps first pass -> full-caps second pass (grid-kNN mode)
+  int* redo_out;                          // first pass: pairs whose cell outgrew the compact caps
+  const int* work_list;                   // second pass: work item -> pair (nullptr: identity)
+  const unsigned long long* work_count;   // second pass: number of work items (device-resident)
 };
 
 // indices into RpdCounters viewed as u64[]
@@ -70,6 +74,8 @@ struct ClipArgs {
 #define CNT_HIST 5
 #define CNT_EXACT 15  // conflict tests that fell through the FP32 filter to the FP64 determinant
 #define CNT_WORK_CURSOR_IDX 17
+#define CNT_REDO 19               // cells handed from the compact-caps pass to the full-caps pass
+#define CNT_WORK_CURSOR2_IDX 20   // work cursor of the second pass
 
 template <int G>
 __device__ __forceinline__ unsigned group_ballot(unsigned gmask, int gshift, bool pred) {
@@ -104,8 +110,12 @@ __device__ __forceinline__ float4 cofactors_f32(const Minors& m) {
 // (SURVEY 8a canonical form), so the order-defining serial replay of C2 is replaced by a
 // group-cooperative partition + adjacency-bit-matrix cavity boundary; every predicate decision and
 // every stored triple (cur_p, cir, next) is unchanged.
-template <int G, bool PT>
-__global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
+template <int G, bool PT, bool SMALL>
+__global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
+  constexpr int KP = SMALL ? MBK_SMALL_P : MBK_MAX_P, KT = SMALL ? MBK_SMALL_T : MBK_MAX_T,
+                KE = SMALL ? MBK_SMALL_E : MBK_MAX_E;
+  constexpr int GC_P0 = KP - 8, GC_E0 = SMALL ? 80 : 96;  // first garbage-collection thresholds (per-tet mode)
+  typedef CellT<KP, KT, KE> CellS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CellS* cells = reinterpret_cast<CellS*>(smem_raw);
   constexpr int NG = 32 / G;  // groups per warp
@@ -119,12 +129,14 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
   if (threadIdx.x < 16) blk_cnt[threadIdx.x] = 0;
   if (PT) {
     // the cavity adjacency matrix is all-zero between clips (rows are cleared by their writers)
-    for (int i = lane; i < MBK_MAX_P; i += G) S.adj[i] = 0ull;
+    for (int i = lane; i < KP; i += G) S.adj[i] = 0ull;
   }
   __syncthreads();
 
   // pair count and cursor granularity (device-side when the launch was speculative)
-  const long long NP = A.n_pairs_dev ? min((long long)*A.n_pairs_dev, A.n_pairs) : A.n_pairs;
+  const long long NP = A.work_count ? (long long)*A.work_count
+                                    : (A.n_pairs_dev ? min((long long)*A.n_pairs_dev, A.n_pairs) : A.n_pairs);
+  const int cursor_idx = A.work_list ? CNT_WORK_CURSOR2_IDX : CNT_WORK_CURSOR_IDX;
   int GRAB = A.grab;
   if (GRAB == 0) {
     long long g = NP / ((long long)gridDim.x * 4 * 16);
@@ -153,7 +165,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
   int nb = -1;                                // per lane: the neighbour of this lane's slot
   float4 eqn = make_float4(0, 0, 0, 0);       // per lane: its bisector
   int nb_v = 0, nb_p = 0, nb_e = 0, status = ST_success;
-  int gc_next_e = 96, gc_next_p = 56;         // per-tet mode: garbage-collect dead planes / edges beyond these
+  int gc_next_e = GC_E0, gc_next_p = GC_P0;         // per-tet mode: garbage-collect dead planes / edges beyond these
   unsigned n_gc = 0;
 
   for (;;) {
@@ -164,7 +176,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       if (idle) {
         if (wq_next >= wq_end && !wq_dry) {
           unsigned long long b = 0;
-          if (wl == 0) b = atomicAdd(&A.counters[CNT_WORK_CURSOR_IDX], (unsigned long long)GRAB);
+          if (wl == 0) b = atomicAdd(&A.counters[cursor_idx], (unsigned long long)GRAB);
           b = __shfl_sync(0xffffffffu, b, 0);
           wq_next = (long long)b;
           wq_end = min((long long)b + GRAB, NP);
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
         if (state == GS_IDLE) {
           const int r = __popc(idle & ((1u << src) - 1u));
           if (wq_next + r < wq_end) {
-            pair = wq_next + r;
+            pair = A.work_list ? (long long)A.work_list[wq_next + r] : wq_next + r;
             state = GS_NEW;
           } else if (wq_dry) {
             state = GS_EXIT;
@@ -240,8 +252,8 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       todo = 0;
       valid = 0;
       list_done = false;
-      gc_next_e = 96;
-      gc_next_p = 56;
+      gc_next_e = GC_E0;
+      gc_next_p = GC_P0;
       state = GS_RUN;
       __syncwarp(gmask);
     }
@@ -293,7 +305,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
           list_done = true;
         }
         base += G;
-        if (nb_p >= MBK_MAX_P && valid) {
+        if (nb_p >= KP && valid) {
           status = ST_vertex_overflow;
           todo = 0;
           state = GS_FINISH;
@@ -374,8 +386,8 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       }
       nb_p = np_new;
       nb_e = ne_new;
-      gc_next_e = max(96, nb_e + 24);
-      gc_next_p = max(56, nb_p + 4);
+      gc_next_e = max(GC_E0, nb_e + 24);
+      gc_next_p = max(GC_P0, nb_p + 4);
       if (lane == 0) n_gc++;
     }
     // ================= C: clip by the next surviving plane (clip_by_plane, :680-774) ============
@@ -512,8 +524,8 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
         }
       }
       if (a1) {  // clear the circular list (64 bytes per cell)
-        if (G >= 8) { if (lane < 8) reinterpret_cast<uint2*>(S.bnext)[lane] = make_uint2(0xffffffffu, 0xffffffffu); }
-        else { reinterpret_cast<uint4*>(S.bnext)[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu); }
+        if (G >= 8) { if (lane < KP / 8) reinterpret_cast<uint2*>(S.bnext)[lane] = make_uint2(0xffffffffu, 0xffffffffu); }
+        else { if (lane < KP / 16) reinterpret_cast<uint4*>(S.bnext)[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu); }
       }
       __syncwarp();
       int nbnd = 0, first = MBK_END;
@@ -555,7 +567,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
         do {
           S.cyc[L++] = (unsigned char)cir;
           cir = S.bnext[cir];
-        } while (cir != first && cir != MBK_END && L < nbnd && L < MBK_MAX_P);
+        } while (cir != first && cir != MBK_END && L < nbnd && L < KP);
         if (cir != first || L != nbnd) st2 = ST_inconsistent_boundary;
       }
     } else
@@ -667,7 +679,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
         do {
           S.cyc[L++] = (unsigned char)cir;
           cir = S.bnext[cir];
-        } while (cir != first && cir != MBK_END && L < MBK_MAX_P);
+        } while (cir != first && cir != MBK_END && L < KP);
       }
     }
     __syncwarp();
@@ -684,7 +696,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
       if (st2 != ST_success)
         status = st2;
       else if (L != 0) {  // first_boundary_ != END_OF_LIST (:754)
-        if (nb_e + L > MBK_MAX_E)
+        if (nb_e + L > KE)
           status = ST_edge_overflow;
         else
           do_new = true;
@@ -709,7 +721,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
           const unsigned char w = max(max(z1, z2), z3);
           const float4 p2 = S.plane[cir], p3 = S.plane[nxt];
           const int slot = nb_v + jj;
-          if (slot + 1 < MBK_MAX_T) {
+          if (slot + 1 < KT) {
             S.ver[slot] = make_uchar4(cur_p, cir, nxt, w);
             if (slot < MBK_CV) S.cof[slot] = cofactors_f32(minors_exact(e, p2, p3));
           }
@@ -721,12 +733,12 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
         if (pm && !perturb) {
           perturb = true;
           const int jp = jb + __ffs(pm) - 1;          // first perturbed vertex
-          const int jo = MBK_MAX_T - 1 - nb_v;        // first overflowing vertex (if < L)
+          const int jo = KT - 1 - nb_v;        // first overflowing vertex (if < L)
           status = (jo < L && jo < jp) ? ST_triangle_overflow : ST_needs_perturb;
         }
       }
       if (do_new) {
-        if (!perturb && nb_v + L + 1 > MBK_MAX_T) status = ST_triangle_overflow;  // nb_v+1 >= 96 (:525)
+        if (!perturb && nb_v + L + 1 > KT) status = ST_triangle_overflow;  // nb_v+1 >= 96 (:525)
         // the new vertices occupy slots [nb_v, nb_v+L): their cache entries are fresh
         const int lo = min(nb_v, 32), hi = min(nb_v + L, 32);
         const unsigned add = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((lo >= 32) ? 0xffffffffu : ((1u << lo) - 1u));
@@ -737,7 +749,7 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
     }
     if (act2 == 1) {
       // a later listed neighbour of this batch would be refused by new_plane (:562-565)
-      if (status == ST_success && nb_p >= MBK_MAX_P && (todo || (valid & ~((2u << k) - 1u)))) status = ST_vertex_overflow;
+      if (status == ST_success && nb_p >= KP && (todo || (valid & ~((2u << k) - 1u)))) status = ST_vertex_overflow;
       if (status != ST_success) {
         todo = 0;
         state = GS_FINISH;
@@ -803,7 +815,16 @@ __global__ void __launch_bounds__(128, 4) k_clip(ClipArgs A) {
           for (int i = lane; i < ew; i += G) o[i] = (i == ew - 1) ? (se[i] & tail_mask) : se[i];
         }
       }
-      if (lane == 0) {
+      // a cell that outgrew the compact caps is not final: the second pass recomputes it at the reference's caps
+      const bool redo = SMALL && (status == ST_triangle_overflow || status == ST_vertex_overflow || status == ST_edge_overflow);
+      if (redo && lane == 0) {
+        const unsigned long long at = atomicAdd(&A.counters[CNT_REDO], 1ull);
+        A.redo_out[at] = (int)pair;
+        A.pair_status[pair] = (signed char)ST_early_return;
+        A.pair_blob[pair] = -1;
+        A.pair_words[pair] = 0;
+      }
+      if (!redo && lane == 0) {
         A.pair_status[pair] = (signed char)status;
         A.pair_blob[pair] = blob_at;
         // low 16 bits: record words; high 16 bits: nb_p (the lean transport format drops 4 * nb_p words)

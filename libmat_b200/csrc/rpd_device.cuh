@@ -121,18 +121,30 @@ __device__ __forceinline__ bool conflict_exact(float4 p1, float4 p2, float4 p3, 
 }
 
 // ---- per-cell shared-memory state ---------------------------------------------------------------
-struct __align__(16) CellS {
-  float4 plane[MBK_MAX_P];          // plane equations (a,b,c,d)
+// KP / KT / KE = capacity in planes / vertices (dual triangles) / edges.  The reference's caps are 64 / 96 / 152
+// (_MAX_P_ / _MAX_T_ / _MAX_E_); the grid-kNN first pass runs with compact caps (more cells resident per SM) and
+// hands the rare cell that outgrows them to a second pass at the reference's caps.
+template <int KP, int KT, int KE>
+struct __align__(16) CellT {
+  float4 plane[KP];                 // plane equations (a,b,c,d)
   float4 c0[4];                     // cull filter: cofactor vectors of the 4 initial (tet) vertices
   float4 cof[MBK_CV];               // conflict filter: cofactor vector of live vertex v (v < MBK_CV)
-  int pnb[MBK_MAX_P];               // p<4: tet-face id; p>=4: neighbour site id of the bisector
-  uchar4 ver[MBK_MAX_T];            // dual triangles (3 plane ids, #adjacent cells)
-  unsigned char bnext[MBK_MAX_P];   // cavity boundary circular list (16-byte aligned: cleared with uint4 stores)
-  unsigned char cyc[MBK_MAX_P];     // the boundary cycle in walk order
-  unsigned char edge[MBK_MAX_E * 3];  // (plane a, plane b, #adjacent cells)
-  unsigned long long adj[MBK_MAX_P];  // grid-kNN mode: directed dual-edge bit matrix of the cavity (zero between clips)
+  int pnb[KP];                      // p<4: tet-face id; p>=4: neighbour site id of the bisector
+  uchar4 ver[KT];                   // dual triangles (3 plane ids, #adjacent cells)
+  unsigned char bnext[KP];          // cavity boundary circular list (16-byte aligned: cleared with vector stores)
+  unsigned char cyc[KP];            // the boundary cycle in walk order
+  unsigned char edge[KE * 3];       // (plane a, plane b, #adjacent cells)
+  unsigned long long adj[KP];       // grid-kNN mode: directed dual-edge bit matrix of the cavity (zero between clips)
 };
+typedef CellT<MBK_MAX_P, MBK_MAX_T, MBK_MAX_E> CellS;
 static_assert(offsetof(CellS, bnext) % 16 == 0, "bnext must be 16-byte aligned");
+// compact caps of the grid-kNN first pass: 2 672 B per cell -> 5 blocks of 16 cells per SM instead of 4
+#define MBK_SMALL_P 48
+#define MBK_SMALL_T 72
+#define MBK_SMALL_E 120
+typedef CellT<MBK_SMALL_P, MBK_SMALL_T, MBK_SMALL_E> CellSmall;
+static_assert(offsetof(CellSmall, bnext) % 16 == 0, "bnext must be 16-byte aligned");
+static_assert(MBK_SMALL_P % 16 == 0 && MBK_MAX_P % 16 == 0, "bnext is cleared 16 bytes at a time");
 
 // compact record size in 4-byte words: header 4 + ver nb_v + planes 4*nb_p + (id2,h) 3*nb_p +
 // edges ceil(3*nb_e/4)

@@ -462,23 +462,25 @@ static void exclusive_scan(mb_ctx* ctx, const int* in, T* out, long long n) {
   MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, out, n, ctx->stream));
 }
 
-template <int G, bool PT>
-static void launch_clip(mb_ctx* ctx, ClipArgs A) {
+template <int G, bool PT, bool SMALL>
+static void launch_clip_pass(mb_ctx* ctx, ClipArgs A, bool second_pass) {
   constexpr int groups = 128 / G;
-  const size_t smem = sizeof(CellS) * groups;
+  typedef CellT<SMALL ? MBK_SMALL_P : MBK_MAX_P, SMALL ? MBK_SMALL_T : MBK_MAX_T, SMALL ? MBK_SMALL_E : MBK_MAX_E> Cell;
+  const size_t smem = sizeof(Cell) * groups;
   static bool attr_set = false;
   if (!attr_set) {
-    MB_CUDA(cudaFuncSetAttribute(k_clip<G, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MB_CUDA(cudaFuncSetAttribute(k_clip<G, PT, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   static int per_sm = 0;
   if (per_sm < 1) {
-    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip<G, PT>, 128, smem));
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip<G, PT, SMALL>, 128, smem));
     if (per_sm < 1) per_sm = 1;
   }
   // persistent grid: every SM fully resident, warps pull chunks of pairs from a global cursor
   long long want = (A.n_pairs + groups - 1) / groups;
   long long grid = std::min<long long>(want, (long long)ctx->sm_count * per_sm);
+  if (second_pass) grid = std::min<long long>(grid, (long long)ctx->sm_count * 2);  // usually nothing to do
   if (grid < 1) grid = 1;
   // cursor granularity: 8 rounds of pairs per grab for large runs, finer for small spans so that every
   // warp still gets >= ~16 grabs (a persistent kernel's tail is one grab long)
@@ -487,11 +489,33 @@ static void launch_clip(mb_ctx* ctx, ClipArgs A) {
     const long long warps = grid * 4;
     long long g = A.n_pairs / (warps * 16);
     g = (g / NG) * NG;
-    A.grab = A.n_pairs_dev ? 0 : (int)std::max<long long>(NG, std::min<long long>(8 * NG, g));  // 0: derived on the device
+    A.grab = (A.n_pairs_dev || A.work_count) ? 0  // 0: derived on the device from the device-resident count
+                                             : (int)std::max<long long>(NG, std::min<long long>(8 * NG, g));
   }
   ctx->n_launches++;
-  k_clip<G, PT><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
+  k_clip<G, PT, SMALL><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
   MB_CUDA(cudaGetLastError());
+}
+
+// given-neighbours mode: one pass at the reference's caps (array positions are part of the contract).
+// grid-kNN mode: compact-caps pass (5 blocks / SM), then the cells it could not hold at the reference's caps.
+template <int G, bool PT>
+static void launch_clip(mb_ctx* ctx, ClipArgs A) {
+  A.redo_out = nullptr;
+  A.work_list = nullptr;
+  A.work_count = nullptr;
+  if (!PT) {
+    launch_clip_pass<G, false, false>(ctx, A, false);
+    return;
+  }
+  ctx->redo_list.reserve((size_t)A.n_pairs + 1);
+  A.redo_out = ctx->redo_list.p;
+  launch_clip_pass<G, PT, true>(ctx, A, false);
+  A.redo_out = nullptr;
+  A.work_list = ctx->redo_list.p;
+  A.work_count = A.counters + CNT_REDO;
+  A.n_pairs_dev = nullptr;
+  launch_clip_pass<G, PT, false>(ctx, A, true);
 }
 
 // Scalars the host needs between stages (pair count, K3 counters, record words) are PUBLISHED by a tiny
@@ -760,6 +784,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
       MB_CUDA(cudaMemsetAsync(c, 0, 4 * sizeof(unsigned long long), s));
       MB_CUDA(cudaMemsetAsync(c + 5, 0, 11 * sizeof(unsigned long long), s));
       MB_CUDA(cudaMemsetAsync(c + CNT_WORK_CURSOR, 0, sizeof(unsigned long long), s));
+      MB_CUDA(cudaMemsetAsync(c + CNT_REDO, 0, 2 * sizeof(unsigned long long), s));  // redo count + second cursor
     }
     MB_CUDA(cudaEventRecord(ev[1], s));
   }
@@ -786,6 +811,8 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   res->n_exact += (long)hc.pad[0];
   res->n_cand_overflow += (long)hc.n_cand_overflow;
   res->n_ovf_tets += (long)hc.n_ovf_tets;
+  res->n_redo += (long)hc.n_redo;
+  res->n_gc += (long)hc.n_gc;
   for (int i = 0; i < 10; i++) res->hist[i] += (long)hc.hist[i];
 
   // ---- gather into (tet, site) order -------------------------------------------------------------
@@ -827,6 +854,7 @@ static void run_prologue(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* re
   res->want_volumes = opts && opts->want_volumes;
   res->n_pairs = res->n_cells = res->n_clips = res->n_culled = res->n_exact = 0;
   res->n_cand_overflow = res->n_ovf_tets = 0;
+  res->n_redo = res->n_gc = 0;
   for (int i = 0; i < 10; i++) res->hist[i] = 0;
 }
 

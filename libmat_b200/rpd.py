@@ -44,6 +44,9 @@ class RpdResult:
         ctx._check(lib.mb_rpd_compact_bytes(handle, C.byref(nb)))
         self.compact_bytes = nb.value
         self.n_spans = int(lib.mb_rpd_spans(handle))
+        a, b = C.c_long(), C.c_long()
+        ctx._check(lib.mb_rpd_clip_passes(handle, C.byref(a), C.byref(b)))
+        self.n_second_pass_cells, self.n_garbage_collections = a.value, b.value
 
     def records(self) -> np.ndarray:
         """Cells sorted by (tet, site) in the ConvexCellTransfer layout (id = index)."""

@@ -62,3 +62,34 @@ def test_heavy_tailed_radii_use_the_pyramid(ctx, O, synth):
     assert res.n_cand_overflow == 0
     tot, mean = _tiles(O, mesh, res.records())
     assert tot < 1e-6 and mean < 1e-4
+
+
+def test_cell_beyond_the_compact_caps_goes_through_the_second_pass(ctx, O, synth):
+    """grid-kNN mode clips with compact per-cell caps first (48 planes / 72 vertices / 120 edges: more cells resident
+    per SM); a cell that outgrows them is recomputed at the reference's caps (64 / 96 / 152).  One big tet, one site
+    surrounded by 40 equal neighbours on a sphere: its power cell has 40 bisector faces and 76 vertices."""
+    verts = np.array([[0, 0, 0], [1000, 0, 0], [0, 1000, 0], [0, 0, 1000]], np.float32)
+    idx = np.array([[0, 1, 2, 3]], np.int32)
+    mesh = synth.TetMesh(verts, idx, np.ones(4, np.int32), np.ones((1, 6), np.int32), np.ones((1, 4), np.int32),
+                         np.arange(4, dtype=np.int32).reshape(1, 4), 4)
+    n = 40
+    i = np.arange(n) + 0.5
+    phi, th = np.arccos(1 - 2 * i / n), np.pi * (1 + 5 ** 0.5) * i  # Fibonacci sphere
+    ring = 200.0 + 60.0 * np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+    c = np.concatenate([[[200.0, 200.0, 200.0]], ring]).astype(np.float32)
+    r = np.full(n + 1, 1.0, np.float32)
+    sites = synth.Sites(np.ascontiguousarray(c.T).ravel(), r * r, np.ones(n + 1, np.uint32), r)
+    ctx.set_mesh(mesh)
+    res = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
+    recs = res.records()
+    assert res.n_second_pass_cells >= 1
+    centre = recs[recs["voro_id"] == 0]
+    assert len(centre) == 1 and centre["status"][0] == 4
+    ap, _, _ = O.reload_active(centre)  # active planes of the centre cell: all 40 bisectors, no tet face (interior)
+    assert int((ap[0, : centre["nb_p"][0]] > 0).sum()) == n
+    assert int(centre["nb_v"][0]) == 2 * n - 4  # simple polytope: V = 2F - 4
+    assert res.status_histogram[4 + 1] == res.n_cells == n + 1
+    # the cells still tile the tet
+    vol = O.cell_volumes(recs).sum()
+    assert abs(vol - 1000.0 ** 3 / 6) / (1000.0 ** 3 / 6) < 1e-5
+    res.free()
