@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
         if (cur_p >= 16) bn[1] = ff;
         if (cur_p >= 32) {
           bn[2] = ff;
-          bn[3] = ff;
+          if (KP > 48) bn[3] = ff;
         }
       }
       int first = MBK_END;

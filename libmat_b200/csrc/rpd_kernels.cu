@@ -497,17 +497,14 @@ static void launch_clip_pass(mb_ctx* ctx, ClipArgs A, bool second_pass) {
   MB_CUDA(cudaGetLastError());
 }
 
-// given-neighbours mode: one pass at the reference's caps (array positions are part of the contract).
-// grid-kNN mode: compact-caps pass (5 blocks / SM), then the cells it could not hold at the reference's caps.
+// Two passes in both modes: compact-caps pass (5 blocks / SM), then the cells it could not hold at the reference's
+// caps.  A cell recomputed by the second pass goes through exactly the single-pass code path, so given-neighbours
+// records (array positions, overflow statuses) stay byte-identical.
 template <int G, bool PT>
 static void launch_clip(mb_ctx* ctx, ClipArgs A) {
   A.redo_out = nullptr;
   A.work_list = nullptr;
   A.work_count = nullptr;
-  if (!PT) {
-    launch_clip_pass<G, false, false>(ctx, A, false);
-    return;
-  }
   ctx->redo_list.reserve((size_t)A.n_pairs + 1);
   A.redo_out = ctx->redo_list.p;
   launch_clip_pass<G, PT, true>(ctx, A, false);
