@@ -149,7 +149,7 @@ __device__ __forceinline__ int warp_argmin(float v, int q) {
 // instantiation with a 2048-entry list; only a list that still exceeds kcap_out AFTER the
 // all-pairs filter is truncated (counted in counters[CNT_CANDOVF], reported by mb_rpd_stats).
 template <int KCAP, int WARPS, bool FROM_LIST>
-__global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? 8 : 1) k_grid_candidates(
+__global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? 6 : 1) k_grid_candidates(
     const float4* __restrict__ vert4, const int4* __restrict__ tet_idx, int tet_first, int tet_count,
     const int* __restrict__ tet_sel, GridDev G, const unsigned* __restrict__ flags, int kcap_out, int* __restrict__ cand_pad,
     int* __restrict__ cand_cnt, int* __restrict__ pair_cnt, unsigned long long* __restrict__ counters,

@@ -2,6 +2,8 @@
 # round-1c profiling: ncu launch list of the default bench command + full captures of the three top kernels
 set -u
 mkdir -p gpurun_out
+( timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1; grep -E "passed|failed" gpurun_out/pytest_gpu.log
+
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
   --log-file gpurun_out/r1c_launches_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
 for K in k_clip; do
