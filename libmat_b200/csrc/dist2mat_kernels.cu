@@ -536,12 +536,14 @@ void d2m_run(mb_ctx* ctx, float* kernel_ms) {
     } else {
       constexpr int CAP = 768, WARPS = 8;
       const size_t smem = (size_t)WARPS * CAP * 8;
-      static bool attr_set = false;
+      static bool attr_set_dev[64] = {false};
+      bool& attr_set = attr_set_dev[ctx->device & 63];  // function attributes are per device
       if (!attr_set) {
         MB_CUDA(cudaFuncSetAttribute(k_dist2mat_q<CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
       }
-      static int per_sm = 0;
+      static int per_sm_dev[64] = {0};
+      int& per_sm = per_sm_dev[ctx->device & 63];
       if (per_sm < 1) {
         MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dist2mat_q<CAP, WARPS>, 32 * WARPS, smem));
         if (per_sm < 1) per_sm = 1;

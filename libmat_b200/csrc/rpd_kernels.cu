@@ -402,7 +402,8 @@ static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan&
   constexpr int WARPS = 4;
   const size_t smem = (size_t)WARPS * (KCAP * 24 + 256);  // float4 pd + float w + int id per entry, + 64-entry queue
   const size_t smem_big = (size_t)GRID_BIG_KCAP * 24 + 256;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};
+  bool& attr_set = attr_set_dev[ctx->device & 63];  // function attributes are per device
   if (!attr_set) {
     MB_CUDA(cudaFuncSetAttribute(k_grid_candidates<GRID_BIG_KCAP, 1, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
@@ -467,12 +468,14 @@ static void launch_clip_pass(mb_ctx* ctx, ClipArgs A, bool second_pass) {
   constexpr int groups = 128 / G;
   typedef CellT<SMALL ? MBK_SMALL_P : MBK_MAX_P, SMALL ? MBK_SMALL_T : MBK_MAX_T, SMALL ? MBK_SMALL_E : MBK_MAX_E> Cell;
   const size_t smem = sizeof(Cell) * groups;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};
+  bool& attr_set = attr_set_dev[ctx->device & 63];  // function attributes are per device
   if (!attr_set) {
     MB_CUDA(cudaFuncSetAttribute(k_clip<G, PT, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  static int per_sm = 0;
+  static int per_sm_dev[64] = {0};
+  int& per_sm = per_sm_dev[ctx->device & 63];
   if (per_sm < 1) {
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip<G, PT, SMALL>, 128, smem));
     if (per_sm < 1) per_sm = 1;

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
   --log-file gpurun_out/r1c_launches_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
 for K in k_clip; do
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 \
   -o gpurun_out/r1c_prof_$K -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$K.log 2>&1
 done
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_grid_candidates -s 4 -c 1 -o gpurun_out/r1c_prof_k_grid_candidates -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_k2.log 2>&1
