@@ -262,6 +262,19 @@ int mb_rpd_topology(mb_rpd_result* res, mb_topo_counts* counts);
 int mb_rpd_fetch_topology(mb_rpd_result* res, int* cell_cc, int* facet_cc, int* site_n_cells, int* site_n_cc,
                           double* site_euler_sum, int* pair_site, int* pair_neigh, int* pair_n_cc);
 
+/* The IO_CUDA result format: Houdini .bgeo V5 (big-endian) of the cell polygons, byte-identical to the
+ * reference's save_convex_cells_houdini (src/IO/IO_CUDA/io_cuda.cxx:152-187 with is_slice_plane = false;
+ * facet loops io_cuda.cxx:21-148; container io_utils.cpp:106-231): every vertex of every cell as a point,
+ * one polygon per active facet (all of them, or with is_boundary_only only half-planes and surface faces
+ * with id < max_sf_fid), primitive attribute "PrimAttr" = site id; 16-bit point indices up to 65 536 points.
+ * `path` is the file to write (the reference derives "../out/<name>/rpd/rpd_<name>_<timestamp>.bgeo").
+ *   mb_rpd_write_bgeo      from compact records in host memory (full or lean; ctx = the context they came from)
+ *   mb_bgeo_write_records  from records in the ConvexCellTransfer layout (no context, no GPU needed) */
+int mb_rpd_write_bgeo(mb_ctx* ctx, const void* blob, const long* cell_offsets, long n_cells, int max_sf_fid,
+                      int is_boundary_only, const char* path, long* n_points, long* n_polygons);
+int mb_bgeo_write_records(const void* records, long n_cells, int max_sf_fid, int is_boundary_only, const char* path,
+                          long* n_points, long* n_polygons);
+
 /* ---------------------------------------------------------------- dist2mat */
 /* spheres float[4*n_sph] = (cx,cy,cz,r) -- r, not r^2 (fix_geo_error.cxx:324-328);
  * samples float[3*n_samples]; offset/count unsigned[n_samples]; prims int[3*n_prims]:

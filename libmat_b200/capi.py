@@ -17,7 +17,7 @@ SYMBOLS = [
     "mb_sink_close", "mb_host_register", "mb_host_unregister", "mb_copy_to_host", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_clip_passes", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
     "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_cell_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
-    "mb_rpd_fetch_emit", "mb_rpd_topology", "mb_rpd_fetch_topology", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
+    "mb_rpd_fetch_emit", "mb_rpd_write_bgeo", "mb_bgeo_write_records", "mb_rpd_topology", "mb_rpd_fetch_topology", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
 ]
 
 # static-filter bounds (reference src/predicate_generator/main.cpp output; include/libmat_b200.h)
@@ -112,6 +112,8 @@ def load() -> C.CDLL:
     lib.mb_rpd_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_long), C.POINTER(vp), C.POINTER(C.c_long)]
     lib.mb_rpd_emit.argtypes = [vp, C.c_int, C.POINTER(EmitCounts)]
     lib.mb_rpd_fetch_emit.argtypes = [vp] + [vp] * 12
+    lib.mb_rpd_write_bgeo.argtypes = [vp, vp, vp, C.c_long, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    lib.mb_bgeo_write_records.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     lib.mb_rpd_topology.argtypes = [vp, C.POINTER(TopoCounts)]
     lib.mb_rpd_fetch_topology.argtypes = [vp] + [vp] * 8
     lib.mb_dist2mat.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_long, vp, vp, vp]
@@ -120,6 +122,18 @@ def load() -> C.CDLL:
     lib.mb_dist2mat_fetch.argtypes = [vp, vp, vp, vp]
     _lib = lib
     return lib
+
+
+def bgeo_write_records(records: np.ndarray, path: str, max_sf_fid: int, is_boundary_only: bool = False):
+    """ConvexCellTransfer records -> Houdini .bgeo (the IO_CUDA result format); host code only, no GPU needed.
+    Returns (n_points, n_polygons)."""
+    lib = load()
+    recs = np.ascontiguousarray(records)
+    a, b = C.c_long(), C.c_long()
+    rc = lib.mb_bgeo_write_records(ptr(recs), len(recs), int(max_sf_fid), int(is_boundary_only), path.encode(), C.byref(a), C.byref(b))
+    if rc != 0:
+        raise LibMatError(f"mb_bgeo_write_records failed ({rc})")
+    return a.value, b.value
 
 
 def ptr(a):

@@ -714,6 +714,34 @@ int mb_rpd_fetch_topology(mb_rpd_result* res, int* cell_cc, int* facet_cc, int* 
   MB_CATCH
 }
 
+// ---- IO_CUDA result format (bgeo.cu) -----------------------------------------------------------------------
+int mb_bgeo_write_records(const void* records, long n_cells, int max_sf_fid, int is_boundary_only, const char* path,
+                          long* n_points, long* n_polygons) {
+  try {
+    if (!records || n_cells < 0 || !path) return MB_ERR_ARG;
+    bgeo_write_records(static_cast<const unsigned char*>(records), n_cells, max_sf_fid, is_boundary_only != 0, path,
+                       n_points, n_polygons);
+  } catch (const MbError& e) {
+    fprintf(stderr, "[libmat_b200] mb_bgeo_write_records: %s\n", e.msg.c_str());
+    return e.code;
+  } catch (...) {
+    return MB_ERR_NOMEM;
+  }
+  return MB_OK;
+}
+
+int mb_rpd_write_bgeo(mb_ctx* ctx, const void* blob, const long* cell_offsets, long n_cells, int max_sf_fid,
+                      int is_boundary_only, const char* path, long* n_points, long* n_polygons) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && blob && cell_offsets && path && n_cells >= 0, MB_ERR_ARG, "bad arguments");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  // expand in slices (full or lean records -> ConvexCellTransfer layout) and feed the writer's cell loop
+  std::vector<unsigned char> recs((size_t)n_cells * MB_RECORD_BYTES);
+  expand_all(ctx, static_cast<const uint32_t*>(blob), reinterpret_cast<const long long*>(cell_offsets), n_cells, 0, recs.data());
+  bgeo_write_records(recs.data(), n_cells, max_sf_fid, is_boundary_only != 0, path, n_points, n_polygons);
+  MB_CATCH
+}
+
 int mb_dist2mat_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples,
                        int n_samples, const unsigned* offset, const unsigned* count,
                        const int* prims, long n_prims) {

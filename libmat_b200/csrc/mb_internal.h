@@ -276,6 +276,10 @@ void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
 void rpd_topology(mb_ctx* ctx, mb_rpd_result* res);  // K6: cell / facet components + Euler sums per power cell
 void rpd_volumes(mb_ctx* ctx, mb_rpd_result* res);  // a12: per-cell / per-site volume + barycentre sums
 
+// ---- bgeo.cu: the IO_CUDA result format (host code) ---------------------------------------------------
+void bgeo_write_records(const unsigned char* recs, long n, int max_sf_fid, bool boundary_only, const char* path,
+                        long* n_points, long* n_polys);
+
 // ---- dist2mat_kernels.cu -------------------------------------------------------------------
 void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples, int n_samples,
                 const unsigned* offset, const unsigned* count, const int* prims, long n_prims);

@@ -275,6 +275,15 @@ class Context:
     def copy_to_host(self, host_array: np.ndarray, d_src: int, nbytes: int):
         self._check(self.lib.mb_copy_to_host(self._ctx, ptr(host_array), C.c_void_p(d_src), int(nbytes)))
 
+    def write_bgeo(self, blob: np.ndarray, offsets: np.ndarray, path: str, max_sf_fid: int, is_boundary_only=False):
+        """compact records (full or lean) in host memory -> Houdini .bgeo, the IO_CUDA result format
+        (save_convex_cells_houdini, io_cuda.cxx:152-187); returns (n_points, n_polygons)"""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        a, b = C.c_long(), C.c_long()
+        self._check(self.lib.mb_rpd_write_bgeo(self._ctx, ptr(np.ascontiguousarray(blob)), ptr(offsets), len(offsets) - 1,
+                                               int(max_sf_fid), int(is_boundary_only), path.encode(), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def expand_compact(self, blob: np.ndarray, offsets: np.ndarray, first_id: int = 0) -> np.ndarray:
         """compact records (full or lean, e.g. gathered from several ranks) -> ConvexCellTransfer records; the
         context must hold the mesh and sites they were computed from"""

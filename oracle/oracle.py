@@ -346,3 +346,24 @@ def topology(em, cell_site, cell_euler):
             for c in comp:
                 facet_cc[c2f[c]] = m
     return {"cell_cc": cell_cc, "facet_cc": facet_cc, "site_stats": site_stats, "pairs": pairs}
+
+
+def ref_bgeo(recs, max_sf_fid, is_boundary_only, work_dir, name="t"):
+    """TEST INFRASTRUCTURE.  The reference's own save_convex_cells_houdini (io_cuda.cxx:152-187, compiled in place in
+    oracle/_ref/libref_bgeo.so) on ConvexCellTransfer records; returns the bytes of the .bgeo it wrote under
+    <work_dir>/../out/<name>/rpd/."""
+    import glob
+    l = ref("bgeo")
+    assert l is not None, "oracle/_ref/libref_bgeo.so not built"
+    recs = np.ascontiguousarray(recs)
+    os.makedirs(work_dir, exist_ok=True)
+    out_dir = os.path.normpath(os.path.join(work_dir, "..", "out", name, "rpd"))
+    for old in glob.glob(os.path.join(out_dir, "*.bgeo")):
+        os.remove(old)
+    rc = l.ref_bgeo_write(_p(recs), C.c_long(len(recs)), C.c_int(int(max_sf_fid)), C.c_int(int(is_boundary_only)),
+                          work_dir.encode(), name.encode())
+    assert rc == 0, rc
+    files = glob.glob(os.path.join(out_dir, "*.bgeo"))
+    assert len(files) == 1, files
+    with open(files[0], "rb") as fh:
+        return fh.read()
