@@ -11,7 +11,9 @@
 // format) or are passed in the ConvexCellTransfer layout.  Compiled without FMA contraction, so the vertex
 // coordinates round exactly like the reference's host build.
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -171,12 +173,7 @@ struct BgeoBuilder {
 
 }  // namespace
 
-// records in the ConvexCellTransfer layout (MB_RECORD_BYTES each)
-void bgeo_write_records(const unsigned char* recs, long n, int max_sf_fid, bool boundary_only, const char* path,
-                        long* n_points, long* n_polys) {
-  BgeoBuilder B;
-  B.max_sf_fid = max_sf_fid;
-  B.boundary_only = boundary_only;
+static void add_records(BgeoBuilder& B, const unsigned char* recs, long n) {
   for (long i = 0; i < n; i++) {
     const unsigned char* r = recs + (size_t)i * MB_RECORD_BYTES;
     CellRef c;
@@ -189,6 +186,34 @@ void bgeo_write_records(const unsigned char* recs, long n, int max_sf_fid, bool 
     c.id2 = reinterpret_cast<const int*>(r + 2464);
     c.id2_stride = 2;
     B.add_cell(c);
+  }
+}
+
+// records in the ConvexCellTransfer layout (MB_RECORD_BYTES each)
+void bgeo_write_records(const unsigned char* recs, long n, int max_sf_fid, bool boundary_only, const char* path,
+                        long* n_points, long* n_polys) {
+  BgeoBuilder B;
+  B.max_sf_fid = max_sf_fid;
+  B.boundary_only = boundary_only;
+  add_records(B, recs, n);
+  B.write(path);
+  if (n_points) *n_points = (long)(B.points.size() / 3);
+  if (n_polys) *n_polys = (long)B.poly_len.size();
+}
+
+// records produced slice by slice (compact -> ConvexCellTransfer expansion of `count` cells starting at `first`
+// into `dst`): the 3 456-byte layout never exists for more than one slice at a time
+void bgeo_write_sliced(long n, const std::function<void(long first, long count, unsigned char* dst)>& expand,
+                       int max_sf_fid, bool boundary_only, const char* path, long* n_points, long* n_polys) {
+  BgeoBuilder B;
+  B.max_sf_fid = max_sf_fid;
+  B.boundary_only = boundary_only;
+  const long slice = 16384;
+  std::vector<unsigned char> buf((size_t)std::min(slice, std::max(n, 1L)) * MB_RECORD_BYTES);
+  for (long first = 0; first < n; first += slice) {
+    const long count = std::min(slice, n - first);
+    expand(first, count, buf.data());
+    add_records(B, buf.data(), count);
   }
   B.write(path);
   if (n_points) *n_points = (long)(B.points.size() / 3);

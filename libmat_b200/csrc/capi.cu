@@ -735,10 +735,12 @@ int mb_rpd_write_bgeo(mb_ctx* ctx, const void* blob, const long* cell_offsets, l
   MB_TRY(ctx)
   MB_REQUIRE(ctx && blob && cell_offsets && path && n_cells >= 0, MB_ERR_ARG, "bad arguments");
   MB_CUDA(cudaSetDevice(ctx->device));
-  // expand in slices (full or lean records -> ConvexCellTransfer layout) and feed the writer's cell loop
-  std::vector<unsigned char> recs((size_t)n_cells * MB_RECORD_BYTES);
-  expand_all(ctx, static_cast<const uint32_t*>(blob), reinterpret_cast<const long long*>(cell_offsets), n_cells, 0, recs.data());
-  bgeo_write_records(recs.data(), n_cells, max_sf_fid, is_boundary_only != 0, path, n_points, n_polygons);
+  // expand slice by slice (full or lean records -> ConvexCellTransfer layout) and feed the writer's cell loop
+  const uint32_t* b = static_cast<const uint32_t*>(blob);
+  const long long* offs = reinterpret_cast<const long long*>(cell_offsets);
+  bgeo_write_sliced(
+      n_cells, [&](long first, long count, unsigned char* dst) { expand_all(ctx, b, offs + first, count, first, dst); },
+      max_sf_fid, is_boundary_only != 0, path, n_points, n_polygons);
   MB_CATCH
 }
 

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -279,6 +280,8 @@ void rpd_volumes(mb_ctx* ctx, mb_rpd_result* res);  // a12: per-cell / per-site 
 // ---- bgeo.cu: the IO_CUDA result format (host code) ---------------------------------------------------
 void bgeo_write_records(const unsigned char* recs, long n, int max_sf_fid, bool boundary_only, const char* path,
                         long* n_points, long* n_polys);
+void bgeo_write_sliced(long n, const std::function<void(long first, long count, unsigned char* dst)>& expand,
+                       int max_sf_fid, bool boundary_only, const char* path, long* n_points, long* n_polys);
 
 // ---- dist2mat_kernels.cu -------------------------------------------------------------------
 void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples, int n_samples,
