@@ -201,6 +201,9 @@ int mb_rpd_count(const mb_rpd_result* res, long* n_cells, long* n_pairs, long* n
  * (truncated: should be 0)  [5] compact result bytes  [6] tets redone by the big-list candidate pass
  * [7] conflict tests the FP32 filter could not decide (evaluated with the FP64 determinant) */
 int mb_rpd_stats(const mb_rpd_result* res, long stats[8]);
+/* test hook: overrides the pairs-per-tet estimate the speculative span launches size their arrays with (0 = learn
+ * it again with a synchronising span); a too small value must only cost a redone span, never change a result */
+int mb_debug_set_pair_hint(mb_ctx* ctx, double pairs_per_tet);
 /* grid-kNN mode internals: cells that outgrew the compact caps of K3's first pass (48 planes / 72 vertices /
  * 120 edges) and were recomputed by the second pass at the reference's caps (64 / 96 / 152), and dead plane /
  * edge garbage collections */

@@ -382,6 +382,12 @@ int mb_rpd_stats(const mb_rpd_result* res, long stats[8]) {
   return MB_OK;
 }
 
+int mb_debug_set_pair_hint(mb_ctx* ctx, double pairs_per_tet) {
+  if (!ctx) return MB_ERR_ARG;
+  ctx->pairs_per_tet_hint = pairs_per_tet;
+  return MB_OK;
+}
+
 int mb_rpd_clip_passes(const mb_rpd_result* res, long* n_second_pass_cells, long* n_garbage_collections) {
   if (!res) return MB_ERR_ARG;
   if (n_second_pass_cells) *n_second_pass_cells = res->n_redo;

@@ -142,3 +142,20 @@ def test_lean_records_expand_to_the_full_records(ctx, cfg1, cfg1_rt, mode):
     opts = capi.RpdOpts(0, 0, 0, 0, 1)
     h = C.c_void_p()
     assert ctx.lib.mb_rpd_run(ctx._ctx, C.byref(opts), C.byref(h)) != 0
+
+
+def test_speculative_capacity_overflow_is_redone(ctx, cfg1_rt):
+    """the speculative span launch sizes its pair arrays from the pairs-per-tet seen so far; an estimate that is far
+    too small must only cost a redone span (one-shot and streamed), never a different result"""
+    mesh, sites, knn, k = cfg1_rt
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, None, 0)
+    want = one_shot(ctx)
+    for hint in (0.05, 1.0):
+        ctx.lib.mb_debug_set_pair_hint(ctx._ctx, hint)
+        same(want, one_shot(ctx))
+        ctx.lib.mb_debug_set_pair_hint(ctx._ctx, hint)
+        got, _ = streamed(ctx, 4)
+        same(want, got)
+    ctx.lib.mb_debug_set_pair_hint(ctx._ctx, 0.0)  # learn again
+    same(want, one_shot(ctx))
