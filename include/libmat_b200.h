@@ -254,15 +254,18 @@ int mb_rpd_fetch_emit(mb_rpd_result* res, int* facet_cell, int* facet_key, unsig
  *                        of a power cell are neighbours iff they share a tet-face id)
  *   facet_cc[n_facets]   for a half-plane facet (site, neigh) of a cell: smallest FACET index of its component
  *                        among the cells carrying that half-plane; -1 for tet-face facets
+ *   edge_cc[n_edges]     for an emitted edge (between two half-planes, key = sorted neighbour pair) of a cell:
+ *                        smallest EDGE index of its component among the cells carrying that key
+ *                        (edge_cc_cells, update_pc_edge_cc_info rpd_update.cxx:507-521)
  *   site_n_cells / site_n_cc / site_euler_sum [n_site]   cells, cell components, double sum of the per-cell
  *                        Euler values in ascending cell id (euler = sum - n_cells, fix_topo.cxx:128-131)
  *   pair_site / pair_neigh / pair_n_cc [n_halfplane_pairs]   one entry per half-plane, sorted by (site, neigh):
  *                        number of components of that facet (is_to_fix_facet_cc: > 1 needs fixing) */
 typedef struct {
-  long n_cells, n_facets, n_sites, n_halfplane_pairs;
+  long n_cells, n_facets, n_sites, n_halfplane_pairs, n_edges;
 } mb_topo_counts;
 int mb_rpd_topology(mb_rpd_result* res, mb_topo_counts* counts);
-int mb_rpd_fetch_topology(mb_rpd_result* res, int* cell_cc, int* facet_cc, int* site_n_cells, int* site_n_cc,
+int mb_rpd_fetch_topology(mb_rpd_result* res, int* cell_cc, int* facet_cc, int* edge_cc, int* site_n_cells, int* site_n_cc,
                           double* site_euler_sum, int* pair_site, int* pair_neigh, int* pair_n_cc);
 
 /* The IO_CUDA result format: Houdini .bgeo V5 (big-endian) of the cell polygons, byte-identical to the

@@ -46,7 +46,8 @@ class EmitCounts(C.Structure):
 
 
 class TopoCounts(C.Structure):
-    _fields_ = [("n_cells", C.c_long), ("n_facets", C.c_long), ("n_sites", C.c_long), ("n_halfplane_pairs", C.c_long)]
+    _fields_ = [("n_cells", C.c_long), ("n_facets", C.c_long), ("n_sites", C.c_long), ("n_halfplane_pairs", C.c_long),
+                ("n_edges", C.c_long)]
 
 
 class LibMatError(RuntimeError):
@@ -116,7 +117,7 @@ def load() -> C.CDLL:
     lib.mb_rpd_write_bgeo.argtypes = [vp, vp, vp, C.c_long, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     lib.mb_bgeo_write_records.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     lib.mb_rpd_topology.argtypes = [vp, C.POINTER(TopoCounts)]
-    lib.mb_rpd_fetch_topology.argtypes = [vp] + [vp] * 8
+    lib.mb_rpd_fetch_topology.argtypes = [vp] + [vp] * 9
     lib.mb_dist2mat.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_long, vp, vp, vp]
     lib.mb_dist2mat_upload.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_long]
     lib.mb_dist2mat_run.argtypes = [vp, C.POINTER(C.c_float)]

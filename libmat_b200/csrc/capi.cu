@@ -348,7 +348,7 @@ void mb_rpd_free(mb_rpd_result* res) {
   res->f_cell.release(); res->f_key.release(); res->v_cell.release(); res->v_lvid.release();
   res->v_key3.release(); res->v_surf.release(); res->e_cell.release(); res->e_key2.release();
   res->e_lvid2.release(); res->f_istet.release(); res->v_pos3.release(); res->c_euler.release();
-  res->t_cell_cc.release(); res->t_facet_cc.release(); res->t_site_n_cells.release(); res->t_site_n_cc.release();
+  res->t_cell_cc.release(); res->t_facet_cc.release(); res->t_edge_cc.release(); res->t_site_n_cells.release(); res->t_site_n_cc.release();
   res->t_pair_site.release(); res->t_pair_neigh.release(); res->t_pair_ncc.release(); res->t_site_euler.release();
   for (cudaEvent_t e : res->evs) {
     if (res->ctx)
@@ -691,13 +691,14 @@ int mb_rpd_topology(mb_rpd_result* res, mb_topo_counts* counts) {
   if (counts) {
     counts->n_cells = res->n_cells;
     counts->n_facets = res->emit_counts.n_facets;
+    counts->n_edges = res->emit_counts.n_edges;
     counts->n_sites = res->n_site;
     counts->n_halfplane_pairs = res->topo_pairs;
   }
   MB_CATCH
 }
 
-int mb_rpd_fetch_topology(mb_rpd_result* res, int* cell_cc, int* facet_cc, int* site_n_cells, int* site_n_cc,
+int mb_rpd_fetch_topology(mb_rpd_result* res, int* cell_cc, int* facet_cc, int* edge_cc, int* site_n_cells, int* site_n_cc,
                           double* site_euler_sum, int* pair_site, int* pair_neigh, int* pair_n_cc) {
   mb_ctx* ctx = res ? res->ctx : nullptr;
   MB_TRY(ctx)
@@ -709,6 +710,7 @@ int mb_rpd_fetch_topology(mb_rpd_result* res, int* cell_cc, int* facet_cc, int* 
   if (have) {
     FETCH(cell_cc, res->t_cell_cc, res->n_cells, int);
     FETCH(facet_cc, res->t_facet_cc, res->emit_counts.n_facets, int);
+    FETCH(edge_cc, res->t_edge_cc, res->emit_counts.n_edges, int);
     FETCH(pair_site, res->t_pair_site, res->topo_pairs, int);
     FETCH(pair_neigh, res->t_pair_neigh, res->topo_pairs, int);
     FETCH(pair_n_cc, res->t_pair_ncc, res->topo_pairs, int);

@@ -193,7 +193,7 @@ struct mb_rpd_result {
   // topology summary (K6)
   bool topo_done = false;
   long topo_pairs = 0;
-  DevBuf<int> t_cell_cc, t_facet_cc, t_site_n_cells, t_site_n_cc, t_pair_site, t_pair_neigh, t_pair_ncc;
+  DevBuf<int> t_cell_cc, t_facet_cc, t_edge_cc, t_site_n_cells, t_site_n_cc, t_pair_site, t_pair_neigh, t_pair_ncc;
   DevBuf<double> t_site_euler;
 };
 

@@ -135,6 +135,36 @@ __global__ void k_topo_facet_pairs(const int* __restrict__ adj_a, const int* __r
   }
 }
 
+// edges (both planes half-planes, key = sorted neighbour pair): for every neighbour pair (c1, c2) the edges with the
+// same key are connected -- edge_cc_cells of update_pc_edge_cc_info (rpd_update.cxx:507-521)
+__global__ void k_topo_edge_pairs(const int* __restrict__ adj_a, const int* __restrict__ adj_b, long n_tet_facets,
+                                  const int* __restrict__ ebegin, const int* __restrict__ e_key2,
+                                  int* __restrict__ parent_edge) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tet_facets) return;
+  const int c1 = adj_a[i];
+  if (c1 < 0) return;
+  const int c2 = adj_b[i];
+  const int b1 = ebegin[c1], e1 = ebegin[c1 + 1], b2 = ebegin[c2], e2 = ebegin[c2 + 1];
+  for (int x = b1; x < e1; x++) {
+    const int k0 = e_key2[2 * x], k1 = e_key2[2 * x + 1];
+    for (int y = b2; y < e2; y++)
+      if (e_key2[2 * y] == k0 && e_key2[2 * y + 1] == k1) {
+        uf_union(parent_edge, x, y);
+        break;
+      }
+  }
+}
+
+// first edge of every cell (K4 emits the edges cell by cell; a cell may have none)
+__global__ void k_topo_edge_begin(const int* __restrict__ e_cell, long n_edges, long n_cells, int* __restrict__ begin) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int c = e_cell[e];
+  if (e == 0 || e_cell[e - 1] != c) begin[c] = (int)e;
+  if (e == n_edges - 1) begin[n_cells] = (int)n_edges;
+}
+
 __global__ void k_topo_cell_sites(const uint32_t* __restrict__ blob, const long long* __restrict__ cell_off, long n_cells,
                                   int* __restrict__ site, int* __restrict__ idx) {
   const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,6 +304,28 @@ void rpd_topology(mb_ctx* ctx, mb_rpd_result* res) {
   }
   ctx->n_launches++;
   k_topo_labels<<<nblk(nf, 256), 256, 0, s>>>(par_f.p, nf, res->f_istet.p, res->t_facet_cc.p);
+  // ---- edges between two half-planes: components inside every (site, neigh_min, neigh_max) set ----------------
+  const long ne = res->emit_counts.n_edges;
+  res->t_edge_cc.reserve((size_t)ne + 1);
+  if (ne > 0) {
+    DevBuf<int> par_e, ebegin;
+    par_e.reserve(ne + 1);
+    ebegin.reserve(nc + 2);
+    MB_CUDA(cudaMemsetAsync(ebegin.p, 0xff, sizeof(int) * (size_t)(nc + 1), s));
+    ctx->n_launches += 3;
+    k_iota<<<nblk(ne, 256), 256, 0, s>>>(par_e.p, ne);
+    k_topo_edge_begin<<<nblk(ne, 256), 256, 0, s>>>(res->e_cell.p, ne, nc, ebegin.p);
+    k_topo_facet_begin_fix<<<nblk(nc, 256), 256, 0, s>>>(ebegin.p, nc);  // cells without edges: empty range
+    if (ntf > 0) {
+      ctx->n_launches++;
+      k_topo_edge_pairs<<<nblk(ntf, 256), 256, 0, s>>>(adj_a.p, adj_b.p, ntf, ebegin.p, res->e_key2.p, par_e.p);
+    }
+    ctx->n_launches++;
+    k_topo_labels<<<nblk(ne, 256), 256, 0, s>>>(par_e.p, ne, nullptr, res->t_edge_cc.p);
+    MB_CUDA(cudaStreamSynchronize(s));
+    par_e.release();
+    ebegin.release();
+  }
   // ---- per-site statistics ---------------------------------------------------------------------------------------
   c_site.reserve(nc); c_idx.reserve(nc); cs_site.reserve(nc); cs_idx.reserve(nc);
   ctx->n_launches++;

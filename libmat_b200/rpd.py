@@ -124,11 +124,12 @@ class RpdResult:
         cnt = capi.TopoCounts()
         self.ctx._check(self.ctx.lib.mb_rpd_topology(self._h, C.byref(cnt)))
         out = {"cell_cc": np.zeros(cnt.n_cells, np.int32), "facet_cc": np.zeros(cnt.n_facets, np.int32),
+               "edge_cc": np.zeros(cnt.n_edges, np.int32),
                "site_n_cells": np.zeros(cnt.n_sites, np.int32), "site_n_cc": np.zeros(cnt.n_sites, np.int32),
                "site_euler_sum": np.zeros(cnt.n_sites, np.float64),
                "pair_site": np.zeros(cnt.n_halfplane_pairs, np.int32), "pair_neigh": np.zeros(cnt.n_halfplane_pairs, np.int32),
                "pair_n_cc": np.zeros(cnt.n_halfplane_pairs, np.int32)}
-        order = ["cell_cc", "facet_cc", "site_n_cells", "site_n_cc", "site_euler_sum", "pair_site", "pair_neigh", "pair_n_cc"]
+        order = ["cell_cc", "facet_cc", "edge_cc", "site_n_cells", "site_n_cc", "site_euler_sum", "pair_site", "pair_neigh", "pair_n_cc"]
         self.ctx._check(self.ctx.lib.mb_rpd_fetch_topology(self._h, *[ptr(out[k]) for k in order]))
         return out
 

@@ -345,7 +345,21 @@ def topology(em, cell_site, cell_euler):
             m = min(c2f[c] for c in comp)
             for c in comp:
                 facet_cc[c2f[c]] = m
-    return {"cell_cc": cell_cc, "facet_cc": facet_cc, "site_stats": site_stats, "pairs": pairs}
+    # e_to_cells -> edge_cc_cells (update_pc_edge_cc_info, rpd_update.cxx:507-521): per (site, neigh_min, neigh_max)
+    edge_cc = None
+    if "edge_cell" in em:
+        e_cell, e_key = em["edge_cell"], em["edge_key"]
+        e_to_cells = defaultdict(dict)
+        for e in range(len(e_cell)):
+            c = int(e_cell[e])
+            e_to_cells[(int(cell_site[c]), int(e_key[e][0]), int(e_key[e][1]))].setdefault(c, e)
+        edge_cc = np.full(len(e_cell), -1, np.int64)
+        for key, c2e in e_to_cells.items():
+            for comp in cc_given_neighbors(set(c2e.keys())):
+                m = min(c2e[c] for c in comp)
+                for c in comp:
+                    edge_cc[c2e[c]] = m
+    return {"cell_cc": cell_cc, "facet_cc": facet_cc, "edge_cc": edge_cc, "site_stats": site_stats, "pairs": pairs}
 
 
 def ref_bgeo(recs, max_sf_fid, is_boundary_only, work_dir, name="t"):

@@ -17,6 +17,7 @@ def check(ctx, O, mesh, sites, knn, k):
     assert np.array_equal(tp["cell_cc"], want["cell_cc"])
     # duplicate half-plane facets of one cell (same neighbour twice) cannot occur for a valid record
     assert np.array_equal(tp["facet_cc"], want["facet_cc"])
+    assert len(tp["edge_cc"]) == len(em["edge_cell"]) and np.array_equal(tp["edge_cc"], want["edge_cc"])
     n_site = sites.n_site
     nc = np.zeros(n_site, np.int64)
     ncc = np.zeros(n_site, np.int64)
