@@ -555,11 +555,14 @@ static bool expand_record(const uint32_t* w, unsigned char* dst, int id, const L
 }
 
 static void expand_all(mb_ctx* ctx, const uint32_t* blob, const long long* offs, long n, long first_id, unsigned char* out) {
-  const LeanTables T = lean_tables(ctx);
+  // the plane tables are only needed (and only fetched from the device) for lean records
+  const bool any_lean = n > 0 && (blob[offs[0] / 4 + 2] & MB_LEAN_FLAG) != 0;
+  LeanTables T;
+  if (any_lean) T = lean_tables(ctx);
   long bad = 0;
 #pragma omp parallel for schedule(static) reduction(+ : bad)
   for (long i = 0; i < n; i++)
-    bad += expand_record(blob + offs[i] / 4, out + (size_t)i * MB_RECORD_BYTES, (int)(first_id + i), &T) ? 0 : 1;
+    bad += expand_record(blob + offs[i] / 4, out + (size_t)i * MB_RECORD_BYTES, (int)(first_id + i), any_lean ? &T : nullptr) ? 0 : 1;
   MB_REQUIRE(bad == 0, MB_ERR_STATE,
              "lean records refer to tets / sites outside the context's resident mesh and sites: expand them with the "
              "context (mesh, tet id base, sites) they were computed from");
