@@ -317,9 +317,10 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5", "d2m"])
     ap.add_argument("--samples", type=int, default=0, help="dist2mat samples (config 3 is 10 000 000)")
     ap.add_argument("--lanes", type=int, default=0)
-    ap.add_argument("--full-records", action="store_true",
-                    help="streamed legs: ship the records WITH their plane equations (default: lean transport format, "
-                         "mb_rpd_opts.lean_records: equations are recomputed from the ids on expansion)")
+    ap.add_argument("--lean", action="store_true",
+                    help="streamed legs: ship the records in the lean transport format (mb_rpd_opts.lean_records: without "
+                         "their plane equations, which the expansion recomputes bit-exactly from the ids).  Default: full "
+                         "compact records; at N=1 the lean variant is measured as well and reported in e2e.lean_records")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the shards reach rank 0")
     ap.add_argument("--chunks", type=int, default=0, help="e2e leg: tet spans of the streamed run (0 = automatic)")
     ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
@@ -469,7 +470,7 @@ def main():
     # "nccl": one-shot run, then an all-gather of the sizes + grouped NCCL send/recv (libmat_b200.dist).
     gather_buf = {"t": None}
     sink_dev = sink_host = None
-    lean = not args.full_records
+    lean = bool(args.lean)
     gather_mode = args.gather if world > 1 else "none"
     if world > 1:
         from libmat_b200.dist import ShardSink
@@ -605,6 +606,21 @@ def main():
             e2e_parts += (tb_ - ta, tc - tb_, time.perf_counter() - tc)
         barrier()
         t_e2e = time.perf_counter() - t0
+        # the same leg with the lean transport format (N = 1): reported next to the headline, never instead of it
+        e2e_lean = None
+        if world == 1 and not lean:
+            ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates, lean=True).free()
+            torch.cuda.synchronize()
+            tl0 = time.perf_counter()
+            for i in range(e2e_steps):
+                set_mesh()
+                upload_sites()
+                res = ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates, lean=True)
+                lean_bytes = res.compact_bytes + 8 * (res.n_cells + 1)
+                res.free()
+            torch.cuda.synchronize()
+            e2e_lean = {"value": cells * e2e_steps / (time.perf_counter() - tl0), "unit": UNIT, "d2h_bytes_per_step": int(lean_bytes),
+                        "note": "records without plane equations (recomputed bit-exactly from the ids on expansion)"}
 
     # ---- max over ranks, totals ------------------------------------------------------------------
     tot = torch.tensor([float(cells), float(pairs), float(rec_bytes), float(listed)], dtype=torch.float64, device=dev)
@@ -650,6 +666,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "records": "lean transport format (ids without plane equations; expansion recomputes them bit-exactly)" if lean
                                else "full compact records",
+                    "lean_records": e2e_lean,
                     "path": ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_host (%d tet spans, D2H of span c "
                              "overlapped with the kernels of span c+1)" % e2e_chunks) if world == 1 else
                             ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_sink into a shared page-locked host segment "
