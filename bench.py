@@ -56,6 +56,16 @@ def measured_traffic(kernel: str, key: str):
         return None, None
 
 
+def measured_pipes(kernel: str, key: str):
+    """pipe utilisation of the same ncu capture (FP64 / FMA / LSU pipes, issue slots, resident warps): what explains
+    the time of a kernel that is not bandwidth-bound"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return d.get(kernel, {}).get(key, {}).get("pipes")
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -527,7 +537,7 @@ def main():
             sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         clip_ms, cand_ms, order_ms = [], [], []
-        cells = pairs = listed = rec_bytes = 0
+        cells = pairs = listed = rec_bytes = n_exact_last = 0
         barrier()
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
@@ -541,6 +551,7 @@ def main():
             order_ms.append(res.kernel_ms["order"])
             cells, pairs, rec_bytes = res.n_cells, res.n_pairs, res.compact_bytes
             listed = res.n_clips + res.n_culled
+            n_exact_last = res.n_exact
             res.free()
         barrier()
         t_wall = time.perf_counter() - t_wall0
@@ -659,9 +670,11 @@ def main():
                          "step_wall_ms": 1e3 * t_wall / args.steps},
             "roofline": {"kernel": "k_clip", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": clip_traffic, "traffic_source": clip_traffic_src,
+                         "ncu_pipes": measured_pipes("k_clip", f"{args.workload}-{mode}") if world == 1 else None,
+                         "exact_predicate_fallbacks_per_step": int(n_exact_last),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_alg,
-                         "note": "latency/FP64-bound irregular kernel; see DESIGN.md and profiles/"},
+                         "note": "latency-bound irregular kernel (not bandwidth-bound: ncu_pipes); see DESIGN.md section 5 and profiles/"},
             "e2e": {"value": total_cells * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "records": "lean transport format (ids without plane equations; expansion recomputes them bit-exactly)" if lean
