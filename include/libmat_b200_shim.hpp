@@ -32,6 +32,14 @@
 
 namespace libmat_b200 {
 
+// the caller's ConvexCellHost must have the capacities and element sizes the records were produced for
+// (src/rpd3d_base/voronoi_defs.h:71-99, voronoi_common.h _MAX_P_/_MAX_T_/_MAX_E_, common_cxx.h:23-43)
+static_assert(sizeof(cuchar4) == 4, "cuchar4 must be 4 packed bytes (vertices are copied as 32-bit words)");
+static_assert(sizeof(ConvexCellHost::ver_data_trans) == MB_MAX_T * sizeof(cuchar4), "_MAX_T_ != 96");
+static_assert(sizeof(ConvexCellHost::clip_data_trans) / sizeof(cfloat5) == MB_MAX_P, "_MAX_P_ != 64");
+static_assert(sizeof(ConvexCellHost::clip_id2_data_trans) / sizeof(cint2) == MB_MAX_P, "_MAX_P_ != 64");
+static_assert(sizeof(ConvexCellHost::edge_data) / sizeof(cuchar3) == MB_MAX_E, "_MAX_E_ != 152");
+
 // compact record (see DESIGN.md "compact cell record") -> ConvexCellHost, the copy_cc rule
 inline void expand_cell(const uint32_t* w, int id, ConvexCellHost& c) {
   const int nb_v = w[2] & 0xff, nb_p = (w[2] >> 8) & 0xff, nb_e = (w[2] >> 16) & 0xff;
