@@ -10,17 +10,26 @@ ordering/compaction (K4 first half), all in libmat_b200.so through the C ABI.
   N = 1   workload = BASELINE.json configs[1]: synthetic Kuhn ball mesh n=32 (196 608 tets, 35 937
           vertices), 10 000 medial spheres, neighbour cap k=80 (given mode: regular-triangulation neighbour lists, the
           reference's semantics; grid mode: the library's own uniform-grid search).
-  N > 1   weak scaling: the global mesh has ~196 608 tets PER GPU (n = 32 / 40 / 51 / 64 for N = 1/2/4/8),
-          10 000*N spheres replicated on every rank, tets sharded in contiguous blocks; every rank
-          runs its shard, then the compact results are gathered on rank 0 with NCCL (grouped
-          send/recv) inside the timed region.  `value` = cells of all ranks / max-over-ranks time.
+  N > 1   tets sharded in contiguous blocks, spheres replicated on every rank.  N = 2 / 4: ~196 608 tets per GPU
+          (n = 40 / 51, 20 000 / 40 000 spheres); N = 8 IS BASELINE.json configs[3], the north-star target:
+          n = 70, 2 058 000 tets (257 250 per GPU), 100 000 spheres.  Every rank's streamed run
+          (mb_rpd_run_to_sink) writes its ordered shard straight into rank 0's HBM over NVLink peer memory
+          (CUDA IPC, copy-engine DMA overlapped with the next tet span); ONE 16-byte-per-rank NCCL all-gather
+          exchanges the shard directory and is the completion barrier -- the payload does not travel through NCCL
+          (`--gather nccl` keeps the all-gather + grouped send/recv path for comparison).
+          `value` = cells of all ranks / max-over-ranks device time.
 
 `value`  : valid cells per second with the inputs resident in HBM (device time, CUDA events on the
            stream the kernels run on, L2 flushed between timed steps).
-`e2e`    : the same through the C ABI with HOST buffers: mb_set_tetmesh + mb_rpd_upload_sites (H2D from
-           pinned memory) + mb_rpd_run + mb_rpd_fetch_compact (D2H) every step, wall clock.
+`e2e`    : the same through the C ABI with HOST buffers, every step: mb_set_tetmesh + mb_rpd_upload_sites (H2D from
+           pinned memory) + mb_rpd_run_to_host (kernels + streamed D2H of the compact records), wall clock.
+`e2e_shim`: (N = 1) the drop-in C++ call itself, compute_clipped_voro_diagram_GPU with the reference's signature,
+           std::vector<ConvexCellHost> construction + expansion included (tests/cxx/shim_driver bench).
+`gpu_reference`: (N = 1) the reference's OWN CUDA build (oracle/_ref/libref_rpd_gpu.so, its flags) timed on the same
+           GPU at config 1 (and config 2 when memory allows), next to this library on the same input.
 `--impl reference` : the reference's own clipping code (oracle/_ref = /root/reference's convex_cell.cu
-           compiled for the host; else the oracle port) on all host threads, on a bounded sample.
+           compiled for the host; else the oracle port) on ALL host threads (OMP_NUM_THREADS is overridden: torchrun
+           sets it to 1), on a bounded sample.
 """
 from __future__ import annotations
 
@@ -39,7 +48,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "rpd_tet_cells_clipped_per_sec"
 UNIT = "cells/s"
-N_FOR_GPUS = {1: 32, 2: 40, 4: 51, 8: 64}
+N_FOR_GPUS = {1: 32, 2: 40, 4: 51, 8: 70}        # N = 8: BASELINE configs[3] (2 058 000 tets)
+SITES_FOR_GPUS = {1: 10000, 2: 20000, 4: 40000, 8: 100000}
+L2_NOTE = "GPU arm: L2 flushed (512 MB write) between timed steps"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -89,7 +100,7 @@ def make_workload(workload: str, n_gpus: int):
         n, ns = 15, 1000
     else:
         n = N_FOR_GPUS.get(n_gpus, int(round(32 * n_gpus ** (1 / 3))))
-        ns = 10000 * n_gpus
+        ns = SITES_FOR_GPUS.get(n_gpus, 10000 * n_gpus)
     mesh = synth.make_ball_mesh(n)
     sites = synth.make_spheres(ns)
     return mesh, sites, n, ns
@@ -168,10 +179,129 @@ def cpu_reference_run(mesh, sites, knn, k, pt, ps, repeats=2):
     impl = "ref" if kind == "reference" else "oracle"
     best, cells = None, 0
     for _ in range(repeats):
-        recs, stat, sec = O.run_pairs(mesh, sites, knn, k, pt, ps, impl=impl, n_threads=0)
+        recs, stat, sec = O.run_pairs(mesh, sites, knn, k, pt, ps, impl=impl, n_threads=host_threads())
         cells = int((recs["status"] == 4).sum())
         best = sec if best is None else min(best, sec)
     return kind, cells, best
+
+
+def host_threads() -> int:
+    """the host cores this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arms override it)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def bench_gpu_reference(ctx, with_cfg2=True):
+    """The reference's own CUDA build on this GPU, next to this library on the SAME input and the same (given-
+    neighbours) semantics.  Reference times: CUDA events around its clip kernel (clipped_voro_cell_test_GPU_param_tet,
+    voronoi.cu:672-706) and the wall clock of its whole entry point compute_clipped_voro_diagram_GPU."""
+    import contextlib
+    import io
+    import torch
+
+    from libmat_b200 import synth
+    from oracle import oracle as O
+
+    out = {}
+    if O.ref("rpd_gpu") is None:
+        return {"unavailable": "oracle/_ref/libref_rpd_gpu.so not built"}
+    for name, n, ns in (("config1", 15, 1000), ("config2", 32, 10000)):
+        if name == "config2":
+            if not with_cfg2:
+                continue
+            free_gpu = torch.cuda.mem_get_info()[0]
+            try:
+                free_host = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+            except (ValueError, OSError):
+                free_host = 0
+            if free_gpu < 60e9 or free_host < 96e9:  # dense e_adjs 2.6 GB, relation 7.9 GB x2, records ~13 GB x2
+                out[name] = {"skipped": f"needs ~35 GB device / ~60 GB host (free: {free_gpu / 1e9:.0f} / {free_host / 1e9:.0f} GB)"}
+                continue
+        mesh = synth.make_ball_mesh(n)
+        sites = synth.make_spheres(ns)
+        knn, k, valid = synth.rt_site_lists(sites)
+        sites.flags[:] = valid.astype(np.uint32)
+        try:
+            t0 = time.perf_counter()
+            got = O.ref_rpd_gpu(mesh, sites, knn, k)  # the reference prints to fd 1: main() has redirected it to stderr
+            t_ref = time.perf_counter() - t0
+            if got is None:
+                out[name] = {"unavailable": "reference CUDA build did not run"}
+                continue
+            if name == "config1":  # a second call: the first one carries context creation
+                got = O.ref_rpd_gpu(mesh, sites, knn, k)
+            recs, ms = got
+            n_ref = len(recs)
+            del recs
+        except Exception as exc:  # noqa: BLE001
+            out[name] = {"error": str(exc)}
+            continue
+        # this library, same semantics (given-neighbours mode, the reference's relation predicate), same box
+        ctx.set_mesh(mesh)
+        ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, knn, k)
+        for _ in range(2):
+            ctx.run().free()
+        r = ctx.run()
+        ours = dict(r.kernel_ms)
+        n_ours = r.n_cells
+        r.free()
+        rf = ctx.run(grid_candidates=True)
+        ours_fast = dict(rf.kernel_ms)
+        rf.free()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ctx.set_mesh(mesh)
+            ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, knn, k)
+            ctx.run_to_host(grid_candidates=True).free()
+        t_ours_call = (time.perf_counter() - t0) / reps
+        out[name] = {
+            "workload": f"n={n}: {mesh.n_tet} tets, {ns} spheres, RT lists site_k={k}",
+            "cells": {"reference": n_ref, "libmat_b200": n_ours, "equal": bool(n_ref == n_ours)},
+            "reference": {"clip_kernel_ms": ms["kernel_ms"], "d2h_ms": ms["d2h_ms"], "call_ms": ms["call_ms"],
+                          "cells_per_s_kernel": n_ref / (ms["kernel_ms"] * 1e-3) if ms["kernel_ms"] > 0 else None,
+                          "cells_per_s_call": n_ref / (ms["call_ms"] * 1e-3),
+                          "what": "unmodified voronoi.cu / convex_cell.cu / knncuda.cu, nvcc -O2 --use_fast_math -DNDEBUG, sm_100"},
+            "libmat_b200": {"clip_kernel_ms": ours["clip"], "candidates_ms_reference_predicate": ours["candidates"],
+                            "candidates_ms_grid": ours_fast["candidates"], "device_total_ms": ours_fast["total"],
+                            "call_ms": 1e3 * t_ours_call,
+                            "cells_per_s_kernel": n_ours / (ours["clip"] * 1e-3), "cells_per_s_call": n_ours / t_ours_call},
+            "speedup": {"clip_kernel": ms["kernel_ms"] / ours["clip"] if ms["kernel_ms"] > 0 else None,
+                        "call": ms["call_ms"] / (1e3 * t_ours_call)},
+        }
+    return out
+
+
+def bench_e2e_shim(mesh, sites, knn, k, reps=3):
+    """the drop-in C++ call with the reference's signature and types (tests/cxx/shim_driver bench): everything the
+    e2e leg times PLUS the std::vector<ConvexCellHost> the caller receives (3 776 B per cell, non-POD)"""
+    import tempfile
+
+    drv = os.path.join(ROOT, "tests", "cxx", "_build", "shim_driver")
+    if not os.path.exists(drv):
+        return {"unavailable": "tests/cxx/_build/shim_driver not prebuilt"}
+    with tempfile.TemporaryDirectory() as td:
+        fin = os.path.join(td, "in.bin")
+        with open(fin, "wb") as f:
+            for a in (mesh.vertices.astype(np.float32), mesh.indices.astype(np.int32), mesh.v_adjs.astype(np.int32),
+                      mesh.e_adj6.astype(np.int32), mesh.f_adjs.astype(np.int32), mesh.f_ids.astype(np.int32),
+                      sites.site_soa, sites.weights, sites.flags, knn.astype(np.int32), np.array([sites.n_site, k], np.int32)):
+                a = np.ascontiguousarray(a)
+                f.write(np.int64(a.size).tobytes())
+                f.write(a.tobytes())
+        env = dict(os.environ)
+        env["OMP_NUM_THREADS"] = str(host_threads())
+        r = subprocess.run([drv, "bench", fin, str(reps)], capture_output=True, text=True, env=env, timeout=600)
+    if r.returncode != 0:
+        return {"error": f"shim_driver rc={r.returncode}: {r.stderr[-300:]}"}
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    d["value"] = d["n_cells"] / (d["call_ms"] * 1e-3)
+    d["unit"] = UNIT
+    d["path"] = ("compute_clipped_voro_diagram_GPU(...) -> std::vector<ConvexCellHost> (include/libmat_b200_shim.hpp): "
+                 "mb_set_tetmesh (dense e_adjs accepted) + mb_rpd_upload_sites + mb_rpd_run_to_host + expansion, median of %d calls" % reps)
+    return d
 
 
 def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
@@ -224,6 +354,8 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
     # fix_geo_error.cxx:149-215 builds one list per face and :300-366 replicates it per sample).  Offsets may
     # point anywhere, so this needs no new entry point -- only a caller that stops replicating.
     try:
+        if n_samples > 2000000:
+            raise RuntimeError("skipped above 2 M samples (the host-side list sharing is a numpy pass over every entry)")
         r_rep = ctx.dist2mat_fetch(want_tie=False)
         ds = synth.share_lists(d)
         tps = [pin(x) for x in (ds.spheres, ds.samples, ds.offset, ds.count, ds.prims)]
@@ -259,9 +391,22 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
         from oracle import oracle as O
         n_cpu = min(n_samples, 400000)
         kind = "reference" if O.ref("d2m") is not None else "port"
-        _, _, sec = O.dist2mat(d, "ref" if kind == "reference" else "oracle", n=n_cpu)
-        out["cpu_baseline"] = {"value": n_cpu / sec, "unit": "queries/s", "cores": os.cpu_count(), "kind": kind,
+        _, _, sec = O.dist2mat(d, "ref" if kind == "reference" else "oracle", n=n_cpu, n_threads=host_threads())
+        out["cpu_baseline"] = {"value": n_cpu / sec, "unit": "queries/s", "cores": host_threads(), "kind": kind,
                                "sample": f"first {n_cpu} samples, reference distance functions + tie rule on all host threads, {sec:.2f} s"}
+        # the reference's own CUDA build on this GPU: its kernel alone (one 32-thread block per sample,
+        # dist2mat.cu:301-304) on resident buffers, and its whole entry point (7 blocking H2D + kernel + 2 D2H)
+        try:
+            ko = O.ref_d2m_gpu(d, kernel_only=True, warmup=1, reps=3)
+            wc = O.ref_d2m_gpu(d)
+            if ko is not None and wc is not None:
+                out["gpu_reference"] = {
+                    "kernel_ms": ko[2], "queries_per_s_kernel": n_samples / (ko[2] * 1e-3),
+                    "call_ms": wc[2], "queries_per_s_call": n_samples / (wc[2] * 1e-3),
+                    "speedup": {"kernel": ko[2] / k_ms, "call": (wc[2] * 1e-3) / t_e2e},
+                    "what": "unmodified dist2mat.cu (ClosestDistanceToLocalMat / compute_closest_dist2mat), nvcc -O2 sm_100, same input"}
+        except Exception as exc:  # noqa: BLE001
+            out["gpu_reference"] = {"error": str(exc)}
     return out
 
 
@@ -286,15 +431,20 @@ def run_reference_arm(args):
     pt, ps = O.tet_sphere_relation(sub, sites, knn, k)  # candidate generation: not timed
     kind = "reference" if O.ref("rpd") is not None else "port"
     impl = "ref" if kind == "reference" else "oracle"
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     cells = 0
     for _ in range(args.warmup):
-        O.run_pairs(sub, sites, knn, k, pt, ps, impl=impl)
+        O.run_pairs(sub, sites, knn, k, pt, ps, impl=impl, n_threads=cores)
+    # the thread count OpenMP really uses now (torchrun's OMP_NUM_THREADS=1 has been overridden by run_pairs)
+    used = int(O.ref("rpd").ref_rpd_max_threads()) if kind == "reference" else cores
+    if cores > 1 and used <= 1:
+        raise SystemExit(f"reference arm would run on 1 of {cores} host threads: refusing to report it as a {cores}-core baseline")
     t_total = 0.0
     for _ in range(args.steps):
-        recs, stat, sec = O.run_pairs(sub, sites, knn, k, pt, ps, impl=impl)
+        recs, stat, sec = O.run_pairs(sub, sites, knn, k, pt, ps, impl=impl, n_threads=cores)
         cells = int((recs["status"] == 4).sum())
         t_total += sec
+    cores = used
     value = cells * args.steps / t_total
     sample = (f"{len(sel)} of {mesh.n_tet} tets (every {stride}th cube), {len(pt)} candidate pairs, {cells} cells "
               f"per step; per-pair clipping loop + record copy timed, candidate generation excluded")
@@ -303,7 +453,9 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args, n, ns, mesh), "mode": f"given-neighbours (regular-triangulation lists, site_k={k}; reference semantics)"},
+        "config": {"workload": workload_name(args, n, ns, mesh), "l2": L2_NOTE},
+        "run": {"mode": f"given-neighbours (regular-triangulation lists, site_k={k}; reference semantics)",
+                "omp_threads": cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -312,7 +464,9 @@ def run_reference_arm(args):
 
 
 def workload_name(args, n, ns, mesh):
-    return (f"{args.workload}: synthetic Kuhn ball mesh n={n} ({mesh.n_tet} tets, {mesh.n_vert} verts), "
+    tag = {15: "cfg1 = BASELINE configs[0]", 32: "cfg2 = BASELINE configs[1]", 70: "cfg4 = BASELINE configs[3]"}.get(
+        n, f"cfg2 weak-scaled to {args.gpus} GPUs")
+    return (f"{tag}: synthetic Kuhn ball mesh n={n} ({mesh.n_tet} tets, {mesh.n_vert} verts), "
             f"{ns} medial spheres, neighbour cap k=80 (grid_k 96 / RT degree <= 80)")
 
 
@@ -335,6 +489,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="e2e leg: tet spans of the streamed run (0 = automatic)")
     ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cfg2", action="store_true", help="gpu_reference: skip the reference CUDA build at config 2 (tens of GB, tens of seconds)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -376,15 +531,19 @@ def main():
     if args.workload == "d2m":
         # dist2mat stand-alone: samples sharded across ranks, medial mesh replicated, no collective
         ctx = Context(local_rank)
-        n_s = (args.samples or 2000000)
+        n_s = (args.samples or 10000000)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
         sub = bench_dist2mat(ctx, n_s, args.steps, args.warmup, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        clocks = sampler.stop() if rank == 0 else None
         vals = torch.tensor([sub["ms_per_step"]], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         if rank == 0:
             sub.update({"value": n_s * world / (vals.item() * 1e-3), "n_gpus": world, "steps": args.steps,
                         "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                        "dtype": "f32", "data": "synthetic", "gpu_launches": args.steps})
+                        "dtype": "f32", "data": "synthetic", "gpu_launches": args.steps, "clocks": clocks})
             emit_line(sub)
         ctx.close()
         if world > 1:
@@ -402,6 +561,8 @@ def main():
             loop.step(sites, to_host=True)
         lat, dev_ms, cells = [], [], []
         iters = 20
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for it in range(iters):
             sites, changed = evolve_sites(sites, it)  # host-side edit (the caller's fix_topo / fix_geo step), untimed
             res, dt = loop.step(sites, to_host=True)  # H2D sites + K1..K4a + streamed D2H of the compact result
@@ -418,7 +579,7 @@ def main():
                            "device_ms_median": float(np.median(dev_ms)), "cells_last": int(cells[-1])},
                 "e2e": {"value": float(np.median(lat)), "unit": "ms", "h2d_bytes_per_step": int(16 * sites.n_site + 4 * sites.n_site),
                         "d2h_bytes_per_step": int(res.compact_bytes + 8 * (res.n_cells + 1))},
-                "gpu_launches": int(ctx.launch_count())}
+                "gpu_launches": int(ctx.launch_count()), "clocks": sampler.stop()}
         emit_line(line)
         ctx.close()
         return
@@ -657,13 +818,12 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, n, ns, mesh),
-                       "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})" + (", grid candidates" if args.grid_candidates else ", reference relation predicate"),
+            "config": {"workload": workload_name(args, n, ns, mesh), "l2": L2_NOTE},
+            "run": {   "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})" + (", grid candidates" if args.grid_candidates else ", reference relation predicate"),
                        "parallelism": f"tet-shards x{world}, sites replicated" + (
                            "" if world == 1 else (", shards streamed into rank 0's HBM over NVLink peer memory (CUDA IPC, copy-engine DMA "
                                                   "overlapped with the next tet span%s) + directory all-gather (NCCL)" % (", lean records" if lean else "") if gather_mode == "p2p"
                                                   else ", NCCL gather to rank 0 (all-gather of sizes + grouped send/recv)")),
-                       "l2": "flushed (512 MB write) between timed steps",
                        "cells_per_step": total_cells, "candidate_pairs_per_step": total_pairs,
                        "pairs_per_sec": total_pairs * args.steps / t_dev},
             "stage_ms": {"candidates": float(np.mean(cand_ms)), "clip": clip_avg_ms, "order": float(np.mean(order_ms)),
@@ -700,14 +860,24 @@ def main():
             rg.free()
             kind, cpu_cells, sec = cpu_reference_run(mesh, sites, knn, k, pt, ps)
             line["cpu_baseline"] = {
-                "value": cpu_cells / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+                "value": cpu_cells / sec, "unit": UNIT, "cores": host_threads(), "kind": kind,
                 "sample": f"all {len(pt)} candidate pairs of the workload (given-neighbours, RT lists site_k={k}), {cpu_cells} cells, "
                           f"best of 2, {sec:.2f} s; clipping loop + record copy timed, candidate generation excluded",
                 "cells_match_gpu_given_mode": bool(cpu_cells == gpu_cells)}
             # second metric of BASELINE.json: dist2mat queries/s (config 3 shape at 1M samples by default;
             # `--workload d2m --samples 10000000` runs the full config)
+            # the drop-in C++ call (reference signature, std::vector<ConvexCellHost> out) and the reference's own CUDA
+            # build on this GPU
             try:
-                line["dist2mat"] = bench_dist2mat(ctx, args.samples or 1000000, max(3, args.steps // 2), 3)
+                line["e2e_shim"] = bench_e2e_shim(mesh, sites, knn, k)
+            except Exception as exc:  # noqa: BLE001
+                line["e2e_shim"] = {"error": str(exc)}
+            try:
+                line["gpu_reference"] = bench_gpu_reference(ctx, with_cfg2=not args.no_ref_cfg2)
+            except Exception as exc:  # noqa: BLE001
+                line["gpu_reference"] = {"error": str(exc)}
+            try:
+                line["dist2mat"] = bench_dist2mat(ctx, args.samples or 10000000, max(3, args.steps // 2), 3)
             except Exception as exc:  # never lose the headline line
                 line["dist2mat"] = {"error": str(exc)}
         emit_line(line)

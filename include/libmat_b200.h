@@ -22,7 +22,7 @@
  *
  * Conventions: every function returns 0 on success or a negative mb_status; the message is
  * available from mb_last_error().  Nothing calls exit().  Inputs are caller-owned host memory,
- * read-only, and may be freed as soon as the call returns.  Results are library-owned handles
+ * read-only, and may be freed as soon as the call returns (the upload calls synchronise their copies).  Results are library-owned handles
  * with explicit free; bulk results use the two-call count -> fetch pattern and the caller
  * allocates the destination.  One mb_ctx per host thread / per GPU; no global state, no files.
  * There is NO CPU fallback: without a usable CUDA device mb_create() fails.
@@ -201,6 +201,18 @@ int mb_rpd_count(const mb_rpd_result* res, long* n_cells, long* n_pairs, long* n
  * (truncated: should be 0)  [5] compact result bytes  [6] tets redone by the big-list candidate pass
  * [7] conflict tests the FP32 filter could not decide (evaluated with the FP64 determinant) */
 int mb_rpd_stats(const mb_rpd_result* res, long stats[8]);
+/* The flagged class: cells / candidate pairs with at least one conflict test whose FP64 determinant fell
+ * under the static-filter bound of src/predicate_generator (main.cpp:52-78),
+ *     |det| < 1.2466136531027298e-13 * maxx * maxy * maxz * max(maxx, maxy, maxz)^2
+ * -- exactly the test of the reference's USE_ARITHMETIC_FILTER branch (convex_cell.cu:479-497), which drops such a
+ * cell as needs_exact_predicates.  The live reference compiles that branch out (voronoi_common.h:32) and so does
+ * this library: the decision stays the FP64 one, the cell is kept, and it carries the flag (bit 30 of word 2 of its
+ * compact record).  Combinatorial differences against another clip order are only legitimate on flagged cells.
+ *   mb_rpd_flagged      counts
+ *   mb_rpd_fetch_flags  cell_flag[n_cells] (order of the records) and / or pair_flag[n_pairs] (order of
+ *                       mb_rpd_fetch_pairs; device-resident results only); either may be NULL */
+int mb_rpd_flagged(const mb_rpd_result* res, long* n_flagged_cells, long* n_flagged_pairs);
+int mb_rpd_fetch_flags(mb_rpd_result* res, unsigned char* cell_flag, unsigned char* pair_flag);
 /* test hook: overrides the pairs-per-tet estimate the speculative span launches size their arrays with (0 = learn
  * it again with a synchronising span); a too small value must only cost a redone span, never change a result */
 int mb_debug_set_pair_hint(mb_ctx* ctx, double pairs_per_tet);

@@ -18,6 +18,7 @@
 // hard-wiring (MB_DEVICE environment variable, default: current device).
 #pragma once
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,7 +45,7 @@ static_assert(sizeof(ConvexCellHost::edge_data) / sizeof(cuchar3) == MB_MAX_E, "
 inline void expand_cell(const uint32_t* w, int id, ConvexCellHost& c) {
   const int nb_v = w[2] & 0xff, nb_p = (w[2] >> 8) & 0xff, nb_e = (w[2] >> 16) & 0xff;
   c.is_active = true;
-  c.status = static_cast<Status>((int)(w[2] >> 24));
+  c.status = static_cast<Status>((int)((w[2] >> 24) & 0x3f));  // bit 30: flagged class, bit 31: lean format
   c.thread_id = id;
   c.voro_id = (int)w[1];
   c.tet_id = (int)w[0];
@@ -71,6 +72,17 @@ inline void expand_cell(const uint32_t* w, int id, ConvexCellHost& c) {
   c.id = id;
 }
 
+// wall milliseconds of the stages of this thread's last compute_clipped_voro_diagram_GPU call:
+// [0] mb_set_tetmesh + mb_rpd_upload_sites (H2D)  [1] mb_rpd_run_to_host (kernels + streamed D2H)
+// [2] std::vector<ConvexCellHost> construction + expansion of the compact records  [3] whole call
+inline double* last_call_ms() {
+  static thread_local double ms[4] = {0, 0, 0, 0};
+  return ms;
+}
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 }  // namespace libmat_b200
 
 #ifndef LIBMAT_B200_NO_REFERENCE_NAMES
@@ -84,6 +96,8 @@ inline std::vector<ConvexCellHost> compute_clipped_voro_diagram_GPU(
     int preferred_tet_k = 0) {
   (void)num_itr_global; (void)v2tets; (void)site_is_transposed; (void)nb_Lloyd_iter; (void)preferred_tet_k;
   std::vector<ConvexCellHost> out;
+  double* ms = libmat_b200::last_call_ms();
+  const double t0 = libmat_b200::now_ms();
   site_cell_vol.assign((size_t)n_site, 0.f);  // voronoi.cu:501-502
   mb_ctx* ctx = libmat_b200::thread_ctx();
   if (!ctx) return out;
@@ -108,12 +122,29 @@ inline std::vector<ConvexCellHost> compute_clipped_voro_diagram_GPU(
   const int* knn = site_knn.empty() ? nullptr : site_knn.data();
   if (mb_rpd_upload_sites(ctx, site.data(), site_weights.data(), site_flags.data(), n_site, knn, site_k))
     return fail("mb_rpd_upload_sites");
+  const double t1 = libmat_b200::now_ms();
   // streamed run: the compact records of tet span c cross PCIe while span c+1 is clipped; on return the whole
   // result sits in the library's pinned host memory (replaces the D2H of n_tet*tet_k ConvexCellTransfer
   // records + the std::map dedup of voronoi.cu:717-769)
   const void* blob_v = nullptr;
   const long* offs = nullptr;
   if (mb_rpd_run_to_host(ctx, &opts, 0, &res, &blob_v, &offs)) return fail("mb_rpd_run_to_host");
+  // A per-tet candidate list of the grid search holds at most 96 sites; a tet with more TRUE candidates would lose
+  // cells (mb_rpd_stats[4], never silent).  The drop-in call then falls back to the reference's own relation
+  // predicate, which has no such cap.
+  long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  mb_rpd_stats(res, st);
+  if (st[4] != 0 && opts.grid_candidates && knn) {
+    std::fprintf(stderr, "[libmat_b200] %ld tets with more than 96 candidate sites: rerunning with the reference's "
+                         "relation predicate (MB_CANDIDATES=reference)\n", st[4]);
+    mb_rpd_free(res);
+    res = nullptr;
+    opts.grid_candidates = 0;
+    if (mb_rpd_run_to_host(ctx, &opts, 0, &res, &blob_v, &offs)) return fail("mb_rpd_run_to_host");
+  } else if (st[4] != 0) {
+    std::fprintf(stderr, "[libmat_b200] WARNING: %ld tets with more than 96 candidate sites were truncated\n", st[4]);
+  }
+  const double t2 = libmat_b200::now_ms();
   long n_cells = 0;
   mb_rpd_count(res, &n_cells, nullptr, nullptr);
   const uint32_t* blob = static_cast<const uint32_t*>(blob_v);
@@ -121,6 +152,11 @@ inline std::vector<ConvexCellHost> compute_clipped_voro_diagram_GPU(
 #pragma omp parallel for schedule(static)
   for (long i = 0; i < n_cells; i++) libmat_b200::expand_cell(blob + offs[i] / 4, (int)i, out[(size_t)i]);
   mb_rpd_free(res);
+  const double t3 = libmat_b200::now_ms();
+  ms[0] = t1 - t0;
+  ms[1] = t2 - t1;
+  ms[2] = t3 - t2;
+  ms[3] = t3 - t0;
   return out;
 }
 #endif

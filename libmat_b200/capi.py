@@ -15,7 +15,7 @@ SYMBOLS = [
     "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_id_base", "mb_set_tet_subset",
     "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_run_to_host", "mb_rpd_run_to_sink", "mb_rpd_expand_compact", "mb_rpd_spans", "mb_sink_create", "mb_sink_destroy", "mb_sink_open",
     "mb_sink_close", "mb_host_register", "mb_host_unregister", "mb_copy_to_host", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
-    "mb_rpd_status_histogram", "mb_rpd_clip_passes", "mb_debug_set_pair_hint", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
+    "mb_rpd_status_histogram", "mb_rpd_clip_passes", "mb_rpd_flagged", "mb_rpd_fetch_flags", "mb_debug_set_pair_hint", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
     "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_cell_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
     "mb_rpd_fetch_emit", "mb_rpd_write_bgeo", "mb_bgeo_write_records", "mb_rpd_topology", "mb_rpd_fetch_topology", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
 ]
@@ -101,6 +101,8 @@ def load() -> C.CDLL:
     lib.mb_rpd_status_histogram.argtypes = [vp, vp]
     lib.mb_rpd_clip_passes.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     lib.mb_debug_set_pair_hint.argtypes = [vp, C.c_double]
+    lib.mb_rpd_flagged.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    lib.mb_rpd_fetch_flags.argtypes = [vp, vp, vp]
     lib.mb_rpd_stats.argtypes = [vp, vp]
     lib.mb_rpd_kernel_ms.argtypes = [vp, vp]
     lib.mb_rpd_fetch_records.argtypes = [vp, vp]

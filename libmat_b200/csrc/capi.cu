@@ -65,6 +65,7 @@ mb_ctx* mb_create(int device, int* err) {
   ctx->stream = ctx->own_stream;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char* v = getenv("MB_D2M_VARIANT")) ctx->d2m_variant = atoi(v);
+  if (const char* v = getenv("MB_NO_CULL")) ctx->no_cull = atoi(v) != 0;
   if (const char* v = getenv("MB_TRACE")) {
     ctx->trace_level = atoi(v);
     ctx->trace_on = ctx->trace_level != 0;
@@ -382,6 +383,32 @@ int mb_rpd_stats(const mb_rpd_result* res, long stats[8]) {
   return MB_OK;
 }
 
+int mb_rpd_flagged(const mb_rpd_result* res, long* n_flagged_cells, long* n_flagged_pairs) {
+  if (!res) return MB_ERR_ARG;
+  if (n_flagged_cells) *n_flagged_cells = res->n_flag_cells;
+  if (n_flagged_pairs) *n_flagged_pairs = res->n_flag_pairs;
+  return MB_OK;
+}
+
+int mb_rpd_fetch_flags(mb_rpd_result* res, unsigned char* cell_flag, unsigned char* pair_flag) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  if (res->host_only) {
+    MB_REQUIRE(!pair_flag, MB_ERR_STATE, "pairs are not kept by a streamed run (mb_rpd_run_to_host)");
+    MB_REQUIRE(res->host_blob, MB_ERR_STATE, "the result lives in a device sink");
+    MB_REQUIRE(!res->sink_owned || res->generation == ctx->stream_generation, MB_ERR_STATE,
+               "streamed result superseded by a later run");
+    if (cell_flag)
+      for (long i = 0; i < res->n_cells; i++)
+        cell_flag[i] = (res->host_blob[res->host_off[i] / 4 + 2] & 0x40000000u) ? 1 : 0;
+    return MB_OK;
+  }
+  rpd_fetch_flags(ctx, res, cell_flag, pair_flag);
+  MB_CATCH
+}
+
 int mb_debug_set_pair_hint(mb_ctx* ctx, double pairs_per_tet) {
   if (!ctx) return MB_ERR_ARG;
   ctx->pairs_per_tet_hint = pairs_per_tet;
@@ -446,7 +473,7 @@ int mb_rpd_fetch_compact(mb_rpd_result* res, void* blob, long* cell_offsets) {
   cudaStream_t s = ctx->stream;
   if (res->host_only) {  // streamed run: the records are already in pinned host memory
     MB_REQUIRE(res->host_blob, MB_ERR_STATE, "the result lives in a device sink");
-    MB_REQUIRE(!res->sink_owned || res->host_blob == ctx->pin_blob.p, MB_ERR_STATE, "streamed result superseded by a later run");
+    MB_REQUIRE(!res->sink_owned || res->generation == ctx->stream_generation, MB_ERR_STATE, "streamed result superseded by a later run");
     if (blob && res->compact_bytes > 0) memcpy(blob, res->host_blob, (size_t)res->compact_bytes);
     if (cell_offsets) memcpy(cell_offsets, res->host_off, sizeof(long long) * ((size_t)res->n_cells + 1));
     return MB_OK;
@@ -505,7 +532,7 @@ static bool expand_record(const uint32_t* w, unsigned char* dst, int id, const L
   const int tet = (int)w[0], site = (int)w[1];
   const int nb_v = w[2] & 0xff, nb_p = (w[2] >> 8) & 0xff, nb_e = (w[2] >> 16) & 0xff;
   const bool lean = (w[2] & MB_LEAN_FLAG) != 0;
-  const int status = (int)((w[2] >> 24) & 0x7f);
+  const int status = (int)((w[2] >> 24) & 0x3f);  // bit 30 = flagged class, bit 31 = lean format
   int32_t* di = reinterpret_cast<int32_t*>(dst);
   di[0] = status;
   di[1] = id;        // thread_id: debug-only in the reference; the cell index here
@@ -589,7 +616,7 @@ int mb_rpd_fetch_records(mb_rpd_result* res, void* dst) {
   const uint32_t* blob;
   if (res->host_only) {
     MB_REQUIRE(res->host_blob, MB_ERR_STATE, "the result lives in a device sink");
-    MB_REQUIRE(!res->sink_owned || res->host_blob == ctx->pin_blob.p, MB_ERR_STATE, "streamed result superseded by a later run");
+    MB_REQUIRE(!res->sink_owned || res->generation == ctx->stream_generation, MB_ERR_STATE, "streamed result superseded by a later run");
     offs = res->host_off;
     blob = res->host_blob;
   } else {

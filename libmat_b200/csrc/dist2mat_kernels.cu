@@ -514,6 +514,8 @@ void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* sampl
   D.n_sph = n_sph;
   D.n_samples = n_samples;
   D.n_prims = n_prims;
+  // header contract: the caller's arrays may be freed on return (copies from pinned memory are truly asynchronous)
+  MB_CUDA(cudaStreamSynchronize(s));
 }
 
 void d2m_run(mb_ctx* ctx, float* kernel_ms) {

@@ -37,6 +37,10 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;  // elements
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }  // locals of a launcher that throws (e.g. out of memory) free their allocations
   void reserve(size_t n) {
     if (n <= cap) return;
     if (p) MB_CUDA(cudaFree(p));
@@ -147,7 +151,7 @@ struct RpdCounters {
   unsigned long long n_gc;         // [18] K3 per-tet mode: dead plane / edge garbage collections
   unsigned long long n_redo;       // [19] grid mode: cells recomputed at the reference's caps by K3's second pass
   unsigned long long work_cursor2; // [20] second pass work distribution
-  unsigned long long reserved[3];
+  unsigned long long reserved[3];  // [21] flagged pairs, [22] flagged valid cells (static-filter class), [23] free
 };
 #define MB_LEAN_FLAG 0x80000000u  // bit 31 of a record's word 2: lean transport format
 #define CNT_OVF_TETS 16
@@ -167,6 +171,8 @@ struct mb_rpd_result {
   mb_ctx* ctx = nullptr;
   long n_pairs = 0, n_cells = 0, n_clips = 0, n_culled = 0, n_cand_overflow = 0, n_ovf_tets = 0, n_exact = 0;
   long n_redo = 0, n_gc = 0;
+  long n_flag_pairs = 0, n_flag_cells = 0;  // flagged class: a conflict |det| under the predicate_generator bound
+  unsigned long long generation = 0;        // streamed results: the context's streamed-run counter when it was produced
   long hist[10] = {0};
   long compact_bytes = 0;
   float ms[4] = {0, 0, 0, 0};
@@ -233,6 +239,8 @@ struct mb_ctx {
   std::vector<float4> h_tet_planes; // host copy of the 4 face planes per tet, fetched on first use
   bool h_tet_planes_valid = false;
   double pairs_per_tet_hint = 0.0;  // grid mode: 1.5 x the largest pairs-per-tet seen (speculative span launches)
+  bool no_cull = false;             // MB_NO_CULL=1 (debug / parity tests): no conservative cull of listed neighbours
+  unsigned long long stream_generation = 0;  // bumped by every streamed run into the context's own pinned buffers
   int trace_level = 0;
   bool trace_on = false;       // MB_TRACE=1: host-side stage timers, printed by mb_destroy
   double trace_us[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -273,6 +281,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res);
 void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res, void* dst_blob,
                      size_t dst_cap_bytes, long long* dst_off, size_t dst_cap_cells);
 void rpd_sync(mb_ctx* ctx, mb_rpd_result* res);
+void rpd_fetch_flags(mb_ctx* ctx, mb_rpd_result* res, unsigned char* cell_flag, unsigned char* pair_flag);
 void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
 void rpd_topology(mb_ctx* ctx, mb_rpd_result* res);  // K6: cell / facet components + Euler sums per power cell
 void rpd_volumes(mb_ctx* ctx, mb_rpd_result* res);  // a12: per-cell / per-site volume + barycentre sums

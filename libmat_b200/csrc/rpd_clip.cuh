@@ -63,6 +63,7 @@ struct ClipArgs {
   int* redo_out;                          // first pass: pairs whose cell outgrew the compact caps
   const int* work_list;                   // second pass: work item -> pair (nullptr: identity)
   const unsigned long long* work_count;   // second pass: number of work items (device-resident)
+  int no_cull;                            // debug (MB_NO_CULL=1): clip by every listed neighbour like the reference does
 };
 
 // indices into RpdCounters viewed as u64[]
@@ -76,6 +77,9 @@ struct ClipArgs {
 #define CNT_WORK_CURSOR_IDX 17
 #define CNT_REDO 19               // cells handed from the compact-caps pass to the full-caps pass
 #define CNT_WORK_CURSOR2_IDX 20   // work cursor of the second pass
+#define CNT_FLAG_PAIRS 21         // pairs with a conflict test under the static-filter bound (flagged class)
+#define CNT_FLAG_CELLS 22         // ... of which valid cells
+#define MB_FLAG_BIT 0x40000000u   // record word 2 / pair_words bit 30: flagged cell
 
 template <int G>
 __device__ __forceinline__ unsigned group_ballot(unsigned gmask, int gshift, bool pred) {
@@ -167,6 +171,10 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
   int nb_v = 0, nb_p = 0, nb_e = 0, status = ST_success;
   int gc_next_e = GC_E0, gc_next_p = GC_P0;         // per-tet mode: garbage-collect dead planes / edges beyond these
   unsigned n_gc = 0;
+  // flagged class (conflict_exact_flag): per lane "one of my tests fell under the static-filter bound"; pm_tet /
+  // pm_bis = largest |normal component| over the tet planes / the bisectors seen so far (bound the filter's eps)
+  bool flagged = false;
+  float pm_tet = 0.f, pm_bis = 0.f;
 
   for (;;) {
     __syncwarp();
@@ -223,7 +231,16 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
                                              : (lane == 2 ? make_uchar4(0, 3, 1, w) : make_uchar4(0, 1, 2, w)));
         // a proper vertex has c.w < 0 (conflict <=> det > 0 <=> vertex on the negative side)
         ok0 = (c.w < 0.f) && isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w);
+        const float4 pl = S.plane[lane];
+        pm_tet = fmaxf(fabsf(pl.x), fmaxf(fabsf(pl.y), fabsf(pl.z)));
+      } else {
+        pm_tet = 0.f;
       }
+      pm_tet = fmaxf(pm_tet, __shfl_xor_sync(gmask, pm_tet, 1));
+      pm_tet = fmaxf(pm_tet, __shfl_xor_sync(gmask, pm_tet, 2));
+      pm_tet = __shfl_sync(gmask, pm_tet, src);
+      pm_bis = 0.f;
+      flagged = false;
       if (lane >= G - 6 || G < 8) {
         // edges (2,3)(1,3)(1,2)(0,3)(0,2)(0,1) with the e_adj of vertex pairs (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
         for (int q = (G < 8 ? lane : lane - (G - 6)); q < 6; q += (G < 8 ? G : 6)) {
@@ -234,7 +251,7 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
           S.edge[3 * q + 2] = (unsigned char)((e6 >> (8 * q)) & 0xff);
         }
       }
-      cull_ok = group_ballot<G>(gmask, gshift, !ok0) == 0;
+      cull_ok = group_ballot<G>(gmask, gshift, !ok0) == 0 && !A.no_cull;
       cvalid = 0xfu;
       nb_v = 4;
       nb_p = 4;
@@ -277,6 +294,8 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
           if (cull_ok) {
             const float n1 = fabsf(eqn.x) + fabsf(eqn.y) + fabsf(eqn.z);
             const float nmax = fmaxf(fabsf(eqn.x), fmaxf(fabsf(eqn.y), fabsf(eqn.z)));
+            // a culled plane must also be clear of the flagged class: |det| >= |s| - 4e-7 T > eps
+            const float eps_up = filter_eps_upper(fmaxf(pm_tet, nmax));
             bool all_out = true;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -284,7 +303,7 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
               const float cw = c.w * eqn.w;
               const float s = fmaf(c.x, eqn.x, fmaf(c.y, eqn.y, fmaf(c.z, eqn.z, cw)));
               const float T = fmaf(fabsf(c.x) + fabsf(c.y) + fabsf(c.z), nmax, fabsf(cw));
-              const float margin = fmaxf(4e-6f * T, 1e-3f * n1 * fabsf(c.w));
+              const float margin = fmaxf(fmaxf(4e-6f * T, 1e-3f * n1 * fabsf(c.w)), fmaf(4e-7f, T, eps_up));
               all_out = all_out && (s < -margin);
             }
             if (all_out) {
@@ -416,25 +435,32 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
     {
       const int vmax = __reduce_max_sync(0xffffffffu, c_act ? nb_v : 0);
       const float nmax = fmaxf(fabsf(e.x), fmaxf(fabsf(e.y), fabsf(e.z)));
+      // flagged-class guard of the FP32 filter: eps <= K M^5 with M over the planes a vertex can involve -- the
+      // bisectors only (eps_b) unless the vertex lies on a tet face (eps_t)
+      const float m_b = fmaxf(pm_bis, nmax);
+      const float eps_b = filter_eps_upper(m_b), eps_t = filter_eps_upper(fmaxf(pm_tet, m_b));
+      if (c_act) pm_bis = m_b;
       for (int vb = 0; vb < vmax; vb += G) {
         const int v = vb + lane;
         bool cf = false;
         if (c_act && v < nb_v) {
           bool decided = false;
+          const uchar4 tv = S.ver[v];
           if (v < MBK_CV && ((cvalid >> v) & 1u)) {
-            // filtered predicate: |s - det_fp64| <= ~3e-7 * T, accepted beyond 4e-6 * T
+            // filtered predicate: |s - det_fp64| <= ~3e-7 * T, accepted beyond 4e-6 * T -- and only when that
+            // also proves |det_fp64| above the static-filter bound (the test cannot be a flagged one)
             const float4 c = S.cof[v];
             const float cw = c.w * e.w;
             const float s = fmaf(c.x, e.x, fmaf(c.y, e.y, fmaf(c.z, e.z, cw)));
             const float T = fmaf(fabsf(c.x) + fabsf(c.y) + fabsf(c.z), nmax, fabsf(cw));
-            if (fabsf(s) > 4e-6f * T) {
+            const float eps_up = min(tv.x, min(tv.y, tv.z)) < 4 ? eps_t : eps_b;
+            if (fabsf(s) > fmaxf(4e-6f * T, fmaf(4e-7f, T, eps_up))) {
               cf = s > 0.f;
               decided = true;
             }
           }
           if (!decided) {
-            const uchar4 tv = S.ver[v];
-            cf = conflict_exact(S.plane[tv.x], S.plane[tv.y], S.plane[tv.z], e);
+            cf = conflict_exact_flag(S.plane[tv.x], S.plane[tv.y], S.plane[tv.z], e, flagged);
             n_exact++;
           }
         }
@@ -760,6 +786,7 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
     if (state == GS_FINISH) {
       long long blob_at = -1;
       int words = 0;
+      const unsigned fbit = group_ballot<G>(gmask, gshift, flagged) ? MB_FLAG_BIT : 0u;
       if (status == ST_success) {
         words = compact_words(nb_v, nb_p, nb_e);
         unsigned long long at = 0;
@@ -780,7 +807,7 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
           if (lane == 0) {
             o[0] = (uint32_t)(t + A.tet_id_base);
             o[1] = (uint32_t)seed_id;
-            o[2] = (uint32_t)nb_v | ((uint32_t)nb_p << 8) | ((uint32_t)nb_e << 16) | ((uint32_t)status << 24);
+            o[2] = (uint32_t)nb_v | ((uint32_t)nb_p << 8) | ((uint32_t)nb_e << 16) | ((uint32_t)status << 24) | fbit;
             o[3] = __float_as_uint(seed.w);
           }
           o += 4;
@@ -828,9 +855,13 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
         A.pair_status[pair] = (signed char)status;
         A.pair_blob[pair] = blob_at;
         // low 16 bits: record words; high 16 bits: nb_p (the lean transport format drops 4 * nb_p words)
-        A.pair_words[pair] = (blob_at >= 0) ? (words | (nb_p << 16)) : 0;
-        if (status == ST_success && blob_at >= 0)
-          n_valid++;
+        // bit 30: flagged class (kept for pairs without a record too: mb_rpd_fetch_flags)
+        A.pair_words[pair] = (int)(((blob_at >= 0) ? (unsigned)(words | (nb_p << 16)) : 0u) | fbit);
+        if (status == ST_success && blob_at >= 0) n_valid++;
+        if (fbit) {  // rare: straight to the global counters
+          atomicAdd(&A.counters[CNT_FLAG_PAIRS], 1ull);
+          if (status == ST_success && blob_at >= 0) atomicAdd(&A.counters[CNT_FLAG_CELLS], 1ull);
+        }
         if (status != ST_success) atomicAdd(&blk_cnt[CNT_HIST + status + 1], 1ull);
       }
       state = GS_IDLE;

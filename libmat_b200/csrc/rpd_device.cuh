@@ -120,6 +120,33 @@ __device__ __forceinline__ bool conflict_exact(float4 p1, float4 p2, float4 p3, 
   return det4_from_minors(m, e) > 0.0;
 }
 
+// ---- the flagged class: the static filter of src/predicate_generator (main.cpp:52-78), consumed by the reference's
+// USE_ARITHMETIC_FILTER branch (convex_cell.cu:479-497; compiled out in the live build, voronoi_common.h:32):
+//   eps = 1.2466136531027298e-13 * maxx * maxy * maxz * max(maxx, maxy, maxz)^2,   flagged <=> |det| < eps
+// with maxx/y/z the largest |normal component| over the vertex's three planes and the new plane.  A cell with a
+// flagged conflict test is one whose combinatorics the FP64 determinant does not certify: the reference's filter build
+// drops it as needs_exact_predicates; here the decision stays the FP64 one (bit-identical to the live reference) and
+// the cell carries a flag (record word 2 bit 30, mb_rpd_fetch_flags).
+#define MBK_FILTER_BOUND_F64 1.2466136531027298e-13
+__device__ __forceinline__ bool conflict_exact_flag(float4 p1, float4 p2, float4 p3, float4 e, bool& flagged) {
+  if (plane_eq(e, p1) || plane_eq(e, p2) || plane_eq(e, p3)) return false;  // :444-451, before the determinant
+  Minors m = minors_exact(p1, p2, p3);
+  const double det = det4_from_minors(m, e);
+  const double maxx = (double)fmaxf(fmaxf(fabsf(p1.x), fabsf(p2.x)), fmaxf(fabsf(p3.x), fabsf(e.x)));
+  const double maxy = (double)fmaxf(fmaxf(fabsf(p1.y), fabsf(p2.y)), fmaxf(fabsf(p3.y), fabsf(e.y)));
+  const double maxz = (double)fmaxf(fmaxf(fabsf(p1.z), fabsf(p2.z)), fmaxf(fabsf(p3.z), fabsf(e.z)));
+  double eps = xdmul(xdmul(xdmul(MBK_FILTER_BOUND_F64, maxx), maxy), maxz);  // literal left-to-right order (:486)
+  const double mm = fmax(maxx, fmax(maxy, maxz));
+  eps = xdmul(eps, xdmul(mm, mm));                                            // :492
+  flagged = flagged || (fabs(det) < eps);
+  return det > 0.0;
+}
+
+// conservative FP32 upper bound of that eps from M >= every |normal component| involved: eps <= K * M^5
+__device__ __forceinline__ float filter_eps_upper(float M) {
+  return (M * M) * (M * M) * (M * 1.2467e-13f) * 1.0001f;
+}
+
 // ---- per-cell shared-memory state ---------------------------------------------------------------
 // KP / KT / KE = capacity in planes / vertices (dual triangles) / edges.  The reference's caps are 64 / 96 / 152
 // (_MAX_P_ / _MAX_T_ / _MAX_E_); the grid-kNN first pass runs with compact caps (more cells resident per SM) and

@@ -303,7 +303,7 @@ void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid) {
   cudaStream_t s = ctx->stream;
   const long n = res->n_cells;
   res->emit_counts = {0, 0, 0};
-  res->emitted = true;
+  res->emitted = n == 0;  // set only once the work below has succeeded
   if (n == 0) return;
   DevBuf<int> cf, cv, ce;
   DevBuf<long long> of, ov, oe;
@@ -341,5 +341,5 @@ void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid) {
                                       res->e_cell.p, res->e_key2.p, res->e_lvid2.p, res->c_euler.p);
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaStreamSynchronize(s));
-  cf.release(); cv.release(); ce.release(); of.release(); ov.release(); oe.release();
+  res->emitted = true;
 }

@@ -181,6 +181,9 @@ void rpd_upload_sites(mb_ctx* ctx, const float* site_soa, const float* site_w,
   S.w_max = wmax;
   S.n_site = n_site;
   MB_CUDA(cudaGetLastError());
+  // the caller may free or overwrite its arrays as soon as this returns (header contract): a copy from pinned
+  // or registered host memory is truly asynchronous, so wait for it (by now the host loops above have hidden it)
+  MB_CUDA(cudaStreamSynchronize(s));
 }
 
 // =============================================================================================
@@ -273,15 +276,19 @@ __global__ void __launch_bounds__(256) k_cand_given(const float4* __restrict__ v
 // ordering + compaction: records leave K3 in arbitrary order in the scratch; two exclusive scans
 // (record words, valid flags) give each valid cell its slot in (tet, site) order.
 // =============================================================================================
-#define PACK_SHIFT 40
+// packed scan element: valid-cell count << 36 | record words.  36 bits of words = 256 GiB of records (more than a
+// B200 holds), 28 bits of cells = 268 M valid cells per span (84 GB of records at ~314 B / cell); rpd_run_span
+// refuses a span beyond either limit instead of wrapping.
+#define PACK_SHIFT 36
 #define PACK_MASK ((1ull << PACK_SHIFT) - 1ull)
+#define PACK_MAX_CELLS ((1ull << (64 - PACK_SHIFT)) - 1ull)
 // pair_words = record words | nb_p << 16 (0 = no record).  LEAN: the transport format without the 4 * nb_p
 // plane-equation words (recomputable from the ids: tet face planes, power bisectors)
 template <bool LEAN>
 struct PackWords {
   __host__ __device__ unsigned long long operator()(int pw) const {
     const int words = pw & 0xffff;
-    const int out = LEAN ? words - 4 * (pw >> 16) : words;
+    const int out = LEAN ? words - 4 * ((pw >> 16) & 0xff) : words;
     return (unsigned long long)out | ((unsigned long long)(words > 0) << PACK_SHIFT);
   }
 };
@@ -303,7 +310,7 @@ __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* 
   const uint32_t* src = scratch + pair_blob[g];
   if (LEAN) {
     // [4 header | nb_v vertices] [4*nb_p plane equations: dropped] [3*nb_p ids | edges]
-    const int nb_p = pw >> 16;
+    const int nb_p = (pw >> 16) & 0xff;
     const int head = 4 + (int)(src[2] & 0xffu);
     const int skip = 4 * nb_p;
     for (int i = lane; i < head; i += 8) blob[dst + i] = (i == 2) ? (src[2] | MB_LEAN_FLAG) : src[i];
@@ -724,6 +731,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     A.scratch = ctx->scratch.p;
     A.scratch_words = ctx->scratch.cap;
     A.counters = reinterpret_cast<unsigned long long*>(ctx->counters.p);
+    A.no_cull = ctx->no_cull ? 1 : 0;
     const bool pt = A.nbr_cnt != nullptr;
     if (G == 4)
       pt ? launch_clip<4, true>(ctx, A) : launch_clip<4, false>(ctx, A);
@@ -775,6 +783,9 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
       }
       return rpd_run_span(ctx, opts, res, sp, grid, blob, cell_off, base_bytes, lean, true);
     }
+    MB_REQUIRE(hc.n_valid <= PACK_MAX_CELLS && hc.blob_words <= PACK_MASK, MB_ERR_ARG,
+               "more valid cells / record words in one tet span than the ordering scan can index: use the streamed run "
+               "(mb_rpd_run_to_host) or a smaller tet range");
     if (hc.blob_words <= ctx->scratch.cap) break;
     // scratch too small: rerun K3 with the measured need (rare; statuses are recomputed)
     scratch_words = (size_t)hc.blob_words + (1u << 20);
@@ -784,7 +795,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
       MB_CUDA(cudaMemsetAsync(c, 0, 4 * sizeof(unsigned long long), s));
       MB_CUDA(cudaMemsetAsync(c + 5, 0, 11 * sizeof(unsigned long long), s));
       MB_CUDA(cudaMemsetAsync(c + CNT_WORK_CURSOR, 0, sizeof(unsigned long long), s));
-      MB_CUDA(cudaMemsetAsync(c + CNT_REDO, 0, 2 * sizeof(unsigned long long), s));  // redo count + second cursor
+      MB_CUDA(cudaMemsetAsync(c + 18, 0, 5 * sizeof(unsigned long long), s));  // gc, redo count, second cursor, flagged pairs / cells
     }
     MB_CUDA(cudaEventRecord(ev[1], s));
   }
@@ -813,6 +824,8 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   res->n_ovf_tets += (long)hc.n_ovf_tets;
   res->n_redo += (long)hc.n_redo;
   res->n_gc += (long)hc.n_gc;
+  res->n_flag_pairs += (long)hc.reserved[0];
+  res->n_flag_cells += (long)hc.reserved[1];
   for (int i = 0; i < 10; i++) res->hist[i] += (long)hc.hist[i];
 
   // ---- gather into (tet, site) order -------------------------------------------------------------
@@ -855,6 +868,7 @@ static void run_prologue(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* re
   res->n_pairs = res->n_cells = res->n_clips = res->n_culled = res->n_exact = 0;
   res->n_cand_overflow = res->n_ovf_tets = 0;
   res->n_redo = res->n_gc = 0;
+  res->n_flag_pairs = res->n_flag_cells = 0;
   for (int i = 0; i < 10; i++) res->hist[i] = 0;
 }
 
@@ -981,6 +995,7 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
   if (own) {
     res->host_blob = reinterpret_cast<const uint32_t*>(ctx->pin_blob.p);
     res->host_off = reinterpret_cast<const long long*>(ctx->pin_off.p);
+    res->generation = ++ctx->stream_generation;  // older handles on the same buffers become stale (MB_ERR_STATE)
   } else {
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, dst_blob) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
@@ -992,6 +1007,37 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
   res->sink_owned = own;
   res->compact_bytes = (long)acc_bytes;
   res->synced = false;
+}
+
+// flagged class: bit 30 of record word 2 (cells) and of pair_words (pairs)
+__global__ void k_cell_flags(const uint32_t* __restrict__ blob, const long long* __restrict__ cell_off, long long n,
+                             unsigned char* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (blob[cell_off[i] / 4 + 2] & MB_FLAG_BIT) ? 1 : 0;
+}
+__global__ void k_pair_flags(const int* __restrict__ pair_words, long long n, unsigned char* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ((unsigned)pair_words[i] & MB_FLAG_BIT) ? 1 : 0;
+}
+
+void rpd_fetch_flags(mb_ctx* ctx, mb_rpd_result* res, unsigned char* cell_flag, unsigned char* pair_flag) {
+  cudaStream_t s = ctx->stream;
+  DevBuf<unsigned char> tmp;
+  tmp.reserve((size_t)std::max(res->n_cells, res->n_pairs) + 1);
+  if (cell_flag && res->n_cells > 0) {
+    ctx->n_launches++;
+    k_cell_flags<<<(unsigned)((res->n_cells + 255) / 256), 256, 0, s>>>(res->blob.p, res->cell_off.p, res->n_cells, tmp.p);
+    MB_CUDA(cudaGetLastError());
+    MB_CUDA(cudaMemcpyAsync(cell_flag, tmp.p, (size_t)res->n_cells, cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+  }
+  if (pair_flag && res->n_pairs > 0) {
+    ctx->n_launches++;
+    k_pair_flags<<<(unsigned)((res->n_pairs + 255) / 256), 256, 0, s>>>(ctx->pair_words.p, res->n_pairs, tmp.p);
+    MB_CUDA(cudaGetLastError());
+    MB_CUDA(cudaMemcpyAsync(pair_flag, tmp.p, (size_t)res->n_pairs, cudaMemcpyDeviceToHost, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+  }
 }
 
 void rpd_sync(mb_ctx* ctx, mb_rpd_result* res) {

@@ -245,7 +245,7 @@ void rpd_topology(mb_ctx* ctx, mb_rpd_result* res) {
   cudaStream_t s = ctx->stream;
   const long nc = res->n_cells, nf = res->emit_counts.n_facets;
   const int n_site = res->n_site;
-  res->topo_done = true;
+  res->topo_done = false;  // set only once the work below has succeeded
   res->topo_pairs = 0;
   res->t_site_n_cells.reserve((size_t)n_site + 1);
   res->t_site_n_cc.reserve((size_t)n_site + 1);
@@ -255,6 +255,7 @@ void rpd_topology(mb_ctx* ctx, mb_rpd_result* res) {
   MB_CUDA(cudaMemsetAsync(res->t_site_euler.p, 0, sizeof(double) * (size_t)n_site, s));
   if (nc == 0 || nf == 0) {
     MB_CUDA(cudaStreamSynchronize(s));
+    res->topo_done = true;
     return;
   }
   DevBuf<unsigned long long> k_in, k_out;
@@ -365,6 +366,5 @@ void rpd_topology(mb_ctx* ctx, mb_rpd_result* res) {
   }
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaStreamSynchronize(s));
-  k_in.release(); k_out.release(); v_in.release(); v_out.release(); adj_a.release(); adj_b.release(); begin.release();
-  c_site.release(); c_idx.release(); cs_site.release(); cs_idx.release(); flag.release(); pos.release(); scal.release(); par_c.release(); par_f.release();
+  res->topo_done = true;
 }

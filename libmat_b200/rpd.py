@@ -47,6 +47,17 @@ class RpdResult:
         a, b = C.c_long(), C.c_long()
         ctx._check(lib.mb_rpd_clip_passes(handle, C.byref(a), C.byref(b)))
         self.n_second_pass_cells, self.n_garbage_collections = a.value, b.value
+        a, b = C.c_long(), C.c_long()
+        ctx._check(lib.mb_rpd_flagged(handle, C.byref(a), C.byref(b)))
+        self.n_flagged_cells, self.n_flagged_pairs = a.value, b.value
+
+    def flags(self, pairs=False):
+        """flagged class (a conflict |det| under the predicate_generator static-filter bound): uint8 per cell in record
+        order, and with pairs=True also per candidate pair in the order of pairs() (one-shot runs only)"""
+        cf = np.zeros(self.n_cells, np.uint8)
+        pf = np.zeros(self.n_pairs, np.uint8) if pairs else None
+        self.ctx._check(self.ctx.lib.mb_rpd_fetch_flags(self._h, ptr(cf), ptr(pf)))
+        return (cf, pf) if pairs else cf
 
     def records(self) -> np.ndarray:
         """Cells sorted by (tet, site) in the ConvexCellTransfer layout (id = index)."""

@@ -161,6 +161,47 @@ def make_ball_mesh(n: int, seed: int = RAN_SEED, jitter: float = 0.2) -> TetMesh
     return TetMesh(verts, idx.astype(np.int32), v_adjs, e_adj6, f_adjs, f_ids, n_sf)
 
 
+def make_box_mesh(n: int, L: float = 1000.0) -> TetMesh:
+    """DEGENERATE test input: the n^3 Kuhn cube mesh on [0,L]^3 without jitter or ball map.  With L / n exactly
+    representable the vertices sit on a lattice; together with make_lattice_spheres the power bisectors pass exactly
+    through mesh vertices and edges, so conflict determinants vanish to rounding level -- the flagged class."""
+    m = n + 1
+    g = np.arange(m, dtype=np.int64)
+    I, J, K = np.meshgrid(g, g, g, indexing="ij")
+    ijk = np.stack([I.ravel(), J.ravel(), K.ravel()], axis=1)
+    verts = (ijk.astype(np.float64) * (L / n)).astype(np.float32)
+    c = np.arange(n, dtype=np.int64)
+    CI, CJ, CK = [a.ravel() for a in np.meshgrid(c, c, c, indexing="ij")]
+    unit = np.eye(3, dtype=np.int64)
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        v0 = np.stack([CI, CJ, CK], axis=1)
+        v1 = v0 + unit[perm[0]]
+        v2 = v1 + unit[perm[1]]
+        v3 = v2 + unit[perm[2]]
+        tets.append(np.stack([(v[:, 0] * m + v[:, 1]) * m + v[:, 2] for v in (v0, v1, v2, v3)], axis=1))
+    idx = np.stack(tets, axis=1).reshape(-1, 4)
+    q = verts.astype(np.float64)[idx]
+    vol = np.einsum("ij,ij->i", np.cross(q[:, 1] - q[:, 0], q[:, 2] - q[:, 0]), q[:, 3] - q[:, 0])
+    flip = vol < 0
+    idx[flip] = idx[flip][:, [0, 2, 1, 3]]
+    v_adjs, e_adj6, f_adjs, f_ids, n_sf = tet_adjacency(idx, m**3)
+    return TetMesh(verts, idx.astype(np.int32), v_adjs, e_adj6, f_adjs, f_ids, n_sf)
+
+
+def make_lattice_spheres(m: int, L: float = 1000.0, r: float = 20.0, jitter: float = 0.0, seed: int = RAN_SEED) -> Sites:
+    """DEGENERATE test input: m^3 equal spheres on a cubic lattice (spacing L / m, first centre at L / (2 m)); with
+    jitter > 0 a fraction of the spacing is added to every centre (near-degenerate instead of exactly degenerate)."""
+    g = (np.arange(m, dtype=np.float64) + 0.5) * (L / m)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    c = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    if jitter > 0:
+        c = c + (2.0 * uniform01(seed, 3 * m**3, stream=9).reshape(-1, 3) - 1.0) * (jitter * L / m)
+    c = c.astype(np.float32)
+    rr = np.full(m**3, r, dtype=np.float32)
+    return Sites(np.ascontiguousarray(c.T).ravel(), (rr * rr).astype(np.float32), np.ones(m**3, dtype=np.uint32), rr)
+
+
 @dataclass
 class Sites:
     """RPD sites in the layout of reference rpd_api.cxx:343-379: SoA x|y|z, weight = r^2."""
@@ -350,7 +391,7 @@ def make_dist2mat(n_samples: int, nu: int = 100, nv: int = 200, seed: int = RAN_
     # two nearest grid spheres of each sample (by centre, in xy-cell neighbourhood -> use KD tree)
     from scipy.spatial import cKDTree
 
-    _, nn = cKDTree(sp[:, :3]).query(samples.astype(np.float64), k=2)
+    _, nn = cKDTree(sp[:, :3]).query(samples.astype(np.float64), k=2, workers=-1)
     nn = nn.astype(np.int64)
     # per-sample list = unique prims incident to either sphere (ascending prim id), then the 2 spheres.
     # The prim part depends on the unordered sphere pair only: build it once per distinct pair, then
@@ -377,9 +418,17 @@ def make_dist2mat(n_samples: int, nu: int = 100, nv: int = 200, seed: int = RAN_
     offset = np.concatenate([[0], np.cumsum(count)[:-1]]).astype(np.int64)
     total = int(count.sum())
     prims = np.empty((total, 3), dtype=np.int32)
-    smp = np.repeat(np.arange(n_samples), cnt_u)
-    pos_u = np.arange(smp.size) - np.repeat(np.cumsum(cnt_u) - cnt_u, cnt_u)
-    prims[offset[smp] + pos_u] = prim_all[pl_prim[pl_start[pinv[smp]] + pos_u]]
+    # replicate: sample i's run starts at offset[i] = (exclusive sum of cnt_u)[i] + 2 i, so with smp = owner of the
+    # m-th replicated entry: dst = m + 2 smp, src = pl_start[pinv[smp]] + (m - excl[smp])   (few passes over ~23 n rows)
+    excl = np.cumsum(cnt_u) - cnt_u
+    m_idx = np.arange(int(cnt_u.sum()), dtype=np.int64)
+    smp = np.repeat(np.arange(n_samples, dtype=np.int64), cnt_u)
+    src = np.repeat(pl_start[pinv] - excl, cnt_u)
+    src += m_idx
+    m_idx += 2 * smp
+    del smp
+    prims[m_idx] = prim_all[pl_prim[src]]
+    del src, m_idx
     tail = offset + cnt_u
     prims[tail] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 0]], axis=1)
     prims[tail + 1] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 1]], axis=1)

@@ -65,11 +65,12 @@ def ref(name):
     if name not in _refs:
         l = _load(os.path.join(HERE, "_ref", f"libref_{name}.so"))
         if l is not None:
-            if name == "rpd":
+            if name in ("rpd", "rpd_filter"):
                 l.ref_rpd_run_pairs.restype = C.c_double
             if name == "d2m":
                 l.ref_d2m_run_host.restype = C.c_double
                 l.ref_d2m_run_gpu.restype = C.c_double
+                l.ref_d2m_kernel_ms.restype = C.c_double
                 for f in ("ref_d2m_sphere", "ref_d2m_cone", "ref_d2m_slab"):
                     getattr(l, f).restype = C.c_float
             if name == "rpd_gpu":
@@ -107,9 +108,9 @@ def run_pairs(mesh, sites, site_knn, site_k, pair_tet, pair_site, impl="oracle",
     if impl == "oracle":
         fn = lib().orc_rpd_run_pairs
     else:
-        r = ref("rpd")
+        r = ref("rpd_filter" if impl == "ref_filter" else "rpd")
         if r is None:
-            raise RuntimeError("oracle/_ref/libref_rpd.so not built")
+            raise RuntimeError("oracle/_ref/libref_rpd%s.so not built" % ("_filter" if impl == "ref_filter" else ""))
         fn = r.ref_rpd_run_pairs
     sec = fn(_p(verts), _p(idx), C.c_int(mesh.n_tet), _p(v_adjs), _p(e6), _p(fa), _p(fi), _p(ss),
              _p(sw), _p(sf), C.c_int(sites.n_site), _p(knn), C.c_int(site_k), _p(pt), _p(ps),
@@ -117,6 +118,25 @@ def run_pairs(mesh, sites, site_knn, site_k, pair_tet, pair_site, impl="oracle",
     if want_vol:
         return recs, stat, sec, vol, bary
     return recs, stat, sec
+
+
+def flagged_pairs(mesh, sites, site_knn, site_k, pair_tet, pair_site, impl="oracle"):
+    """The flagged class per candidate pair (uint8): some conflict test of the pair's clipping had
+    |det| < 1.2466136531027298e-13 * maxx*maxy*maxz*max^2 (predicate_generator/main.cpp:52-78).
+    impl='ref': the reference's own USE_ARITHMETIC_FILTER build (status needs_exact_predicates, convex_cell.cu:479-497);
+    impl='oracle': the plain-C restatement."""
+    if impl == "ref":
+        _, stat, _ = run_pairs(mesh, sites, site_knn, site_k, pair_tet, pair_site, impl="ref_filter")
+        return (stat == STATUS["needs_exact_predicates"]).astype(np.uint8)
+    n = int(len(pair_tet))
+    out = np.zeros(n, np.uint8)
+    lib().orc_rpd_flagged_pairs(
+        _p(_c(mesh.vertices, np.float32)), _p(_c(mesh.indices, np.int32)), C.c_int(mesh.n_tet), _p(_c(mesh.v_adjs, np.int32)),
+        _p(_c(mesh.e_adj6, np.int32)), _p(_c(mesh.f_adjs, np.int32)), _p(_c(mesh.f_ids, np.int32)),
+        _p(_c(sites.site_soa, np.float32)), _p(_c(sites.weights, np.float32)), _p(_c(sites.flags, np.uint32)),
+        C.c_int(sites.n_site), _p(_c(site_knn, np.int32)), C.c_int(site_k), _p(_c(pair_tet, np.int32)),
+        _p(_c(pair_site, np.int32)), C.c_long(n), _p(out))
+    return out
 
 
 def tet_sphere_relation(mesh, sites, site_knn, site_k, cap=None):
@@ -133,6 +153,49 @@ def tet_sphere_relation(mesh, sites, site_knn, site_k, cap=None):
         if n >= 0:
             return pt[:n].copy(), ps[:n].copy()
         cap = -n
+
+
+def ref_rpd_gpu(mesh, sites, site_knn, site_k):
+    """The reference's own CUDA build (oracle/_ref/libref_rpd_gpu.so: voronoi.cu + convex_cell.cu + knncuda.cu compiled
+    in place with the reference's --use_fast_math) through its real entry point compute_clipped_voro_diagram_GPU
+    (voronoi.cu:455-795).  Needs a GPU and the dense e_adjs table; memory-feasible up to config 2.  Returns
+    (records of the valid cells sorted by (tet, site), {"call_ms", "kernel_ms", "d2h_ms"}) or None without the build /
+    a device.  The reference prints to stdout and appends record.csv in the CWD."""
+    l = ref("rpd_gpu")
+    if l is None:
+        return None
+    e = _c(mesh.dense_e_adjs(), np.int32)
+    ms = C.c_double(0)
+    n = l.ref_rpd_gpu_run(
+        _p(_c(mesh.vertices, np.float32)), C.c_int(mesh.n_vert), _p(_c(mesh.indices, np.int32)), C.c_int(mesh.n_tet),
+        _p(_c(mesh.v_adjs, np.int32)), _p(e), C.c_long(e.size), _p(_c(mesh.f_adjs, np.int32)), _p(_c(mesh.f_ids, np.int32)),
+        _p(_c(sites.site_soa, np.float32)), _p(_c(sites.weights, np.float32)), _p(_c(sites.flags, np.uint32)),
+        C.c_int(sites.n_site), _p(_c(site_knn, np.int32)), C.c_int(site_k), C.byref(ms))
+    if n < 0:
+        return None
+    recs = np.zeros(n, dtype=RECORD_DTYPE)
+    l.ref_rpd_gpu_fetch(_p(recs))
+    k_ms, d_ms = C.c_double(-1), C.c_double(-1)
+    l.ref_rpd_gpu_last_ms(C.byref(k_ms), C.byref(d_ms))
+    return recs, {"call_ms": ms.value, "kernel_ms": k_ms.value, "d2h_ms": d_ms.value}
+
+
+def ref_d2m_gpu(inp, kernel_only=False, warmup=1, reps=3):
+    """The reference's dist2mat on the GPU: its whole entry point compute_closest_dist2mat (7 H2D + kernel + 2 D2H,
+    dist2mat.cu:280-315) or, kernel_only, its kernel ClosestDistanceToLocalMat alone on resident buffers.
+    Returns (result, closest_id, milliseconds) or None without the build / a device."""
+    l = ref("d2m")
+    if l is None:
+        return None
+    n = len(inp.samples)
+    res = np.zeros(n, np.float32)
+    cid = np.zeros(n, np.int32)
+    sph = _c(inp.spheres, np.float32)
+    pr = _c(inp.prims, np.int32)
+    args = (_p(sph), C.c_int(len(sph)), _p(_c(inp.samples, np.float32)), C.c_int(n), _p(_c(inp.offset, np.uint32)),
+            _p(_c(inp.count, np.uint32)), _p(pr), C.c_long(len(pr)), _p(res), _p(cid))
+    ms = l.ref_d2m_kernel_ms(*args, C.c_int(warmup), C.c_int(reps)) if kernel_only else l.ref_d2m_run_gpu(*args)
+    return None if ms < 0 else (res, cid, ms)
 
 
 def reload_active(recs, impl="oracle"):

@@ -104,4 +104,52 @@ double ref_d2m_run_gpu(const float* spheres, int n_sph, const float* samples, in
   return 1e3 * ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
 }
 
+// The reference's kernel alone (ClosestDistanceToLocalMat, dist2mat.cu:195-278, in its own launch shape: one
+// 32-thread block per sample, :301-304) on resident buffers: `warmup` untimed + `reps` timed launches between CUDA
+// events.  Returns the mean milliseconds per launch (<0 without a device); results of the last launch are copied out.
+double ref_d2m_kernel_ms(const float* spheres, int n_sph, const float* samples, int n_samples,
+                         const unsigned* offset, const unsigned* count, const int* prims, long n_prims,
+                         float* result, int* closest_id, int warmup, int reps) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1.0;
+  GpuBuffer<float4> b_sph(n_sph);
+  GpuBuffer<float3> b_smp(n_samples);
+  GpuBuffer<uint> b_off(n_samples), b_cnt(n_samples);
+  GpuBuffer<int3> b_pr(n_prims);
+  GpuBuffer<float> b_res(n_samples);
+  GpuBuffer<int> b_id(n_samples);
+  memcpy(b_sph.HPtr(), spheres, sizeof(float4) * (size_t)n_sph);
+  memcpy(b_smp.HPtr(), samples, sizeof(float3) * (size_t)n_samples);
+  memcpy(b_off.HPtr(), offset, sizeof(uint) * (size_t)n_samples);
+  memcpy(b_cnt.HPtr(), count, sizeof(uint) * (size_t)n_samples);
+  memcpy(b_pr.HPtr(), prims, sizeof(int3) * (size_t)n_prims);
+  for (int i = 0; i < n_samples; i++) {
+    b_res.HPtr()[i] = 1e28f;
+    b_id.HPtr()[i] = -1;
+  }
+  b_sph.H2D(); b_smp.H2D(); b_off.H2D(); b_cnt.H2D(); b_pr.H2D(); b_res.H2D(); b_id.H2D();
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float total = 0.f;
+  for (int it = 0; it < warmup + reps; it++) {
+    cudaEventRecord(e0);
+    ClosestDistanceToLocalMat<<<n_samples, kWarpSize>>>(b_smp.DPtr(), b_sph.DPtr(), b_pr.DPtr(), b_off.DPtr(),
+                                                        b_cnt.DPtr(), b_res.DPtr(), b_id.DPtr());
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (it >= warmup) total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (cudaGetLastError() != cudaSuccess) return -2.0;
+  b_res.D2H();
+  b_id.D2H();
+  if (result) memcpy(result, b_res.HPtr(), sizeof(float) * (size_t)n_samples);
+  if (closest_id) memcpy(closest_id, b_id.HPtr(), sizeof(int) * (size_t)n_samples);
+  return reps > 0 ? (double)total / reps : 0.0;
+}
+
 }  // extern "C"

@@ -7,7 +7,31 @@
 // compute_clipped_voro_diagram_GPU (voronoi.cu:455-795) through a C wrapper, so that on the GPU
 // box the product can be checked against -- and timed beside -- the unmodified reference.
 // Needs a GPU at run time; memory-feasible at config 1 (and marginally config 2), SURVEY section 6.
+#include <cuda_runtime.h>
+
+#include <vector>
+
+// The reference brackets its clip kernel and its D2H with CUDA event pairs (voronoi.cu:672-706, 713-734) but never
+// reads them (its record.csv timings come from a 10 ms-resolution Stopwatch).  Both pairs end with
+// cudaEventDestroy(start); cudaEventDestroy(stop): this hook reads the elapsed time of each pair on the way out, so
+// the unmodified source yields its own kernel-only and D2H milliseconds.
+static std::vector<float> g_ref_event_ms;
+static cudaEvent_t g_ref_pending_start = nullptr;
+static inline cudaError_t ref_hook_event_destroy(cudaEvent_t e) {
+  if (!g_ref_pending_start) {
+    g_ref_pending_start = e;
+    return cudaSuccess;
+  }
+  float ms = -1.f;
+  cudaEventElapsedTime(&ms, g_ref_pending_start, e);
+  g_ref_event_ms.push_back(ms);
+  cudaEventDestroy(g_ref_pending_start);
+  g_ref_pending_start = nullptr;
+  return cudaEventDestroy(e);
+}
+#define cudaEventDestroy(e) ref_hook_event_destroy(e)
 #include "voronoi.cu"
+#undef cudaEventDestroy
 #include "convex_cell.cu"
 #include "knncuda.cu"
 #include "voronoi_defs.cxx"
@@ -40,12 +64,20 @@ long ref_rpd_gpu_run(const float* verts_aos, int n_vert, const int* idx_aos, int
   std::vector<int> knn(site_knn, site_knn + (size_t)(site_k + 1) * n_site);
   std::vector<float> vol;
   struct timespec t0, t1;
+  g_ref_event_ms.clear();
   clock_gettime(CLOCK_MONOTONIC, &t0);
   g_cells = compute_clipped_voro_diagram_GPU(0, vertices, indices, v2tets, va, ea, fa, fi, site,
                                              n_site, w, fl, knn, site_k, vol, true);
   clock_gettime(CLOCK_MONOTONIC, &t1);
   if (ms_out) *ms_out = 1e3 * ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
   return (long)g_cells.size();
+}
+
+// CUDA-event milliseconds of the last run: [0] the clip kernel clipped_voro_cell_test_GPU_param_tet alone
+// (voronoi.cu:672-706), [1] the D2H of all ConvexCellTransfer records (:713-734); <0 when not captured
+void ref_rpd_gpu_last_ms(double* kernel_ms, double* d2h_ms) {
+  if (kernel_ms) *kernel_ms = g_ref_event_ms.size() > 0 ? g_ref_event_ms[0] : -1.0;
+  if (d2h_ms) *d2h_ms = g_ref_event_ms.size() > 1 ? g_ref_event_ms[1] : -1.0;
 }
 
 // copy the cells out in the ConvexCellTransfer layout (orc_record)

@@ -56,6 +56,7 @@ typedef struct {
   uint8_t edge[ORC_MAX_E][3];
   uint8_t bnext[ORC_MAX_P];
   int status;
+  int flagged; /* some conflict |det| fell under the static-filter bound (the USE_ARITHMETIC_FILTER test) */
   int nb_v, nb_r, nb_p, nb_e;
   uint8_t first_boundary;
   int voro_id, tet_id;
@@ -82,6 +83,7 @@ static void cell_init(cell_t* c, int seed, const float* pts, int pitch, const fl
   c->seed = (f4){pts[seed], pts[seed + pitch], pts[seed + 2 * pitch], w[seed]};
   c->tet_id = tid;
   c->status = ORC_success;
+  c->flagged = 0;
   for (int i = 0; i < 4; i++) {
     f4 v[3];
     for (int j = 0; j < 3; j++) {
@@ -139,12 +141,23 @@ static int new_plane(cell_t* c, int seed_id) {
 
 static int f4eq(f4 a, f4 b) { return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w; }
 
-/* convex_cell.cu:437-500 (USE_ARITHMETIC_FILTER off, voronoi_common.h:32) */
-static int in_conflict(const cell_t* c, const uint8_t* v, f4 e) {
+static double dmax4(double a, double b, double c, double d) { return fmax(fmax(a, b), fmax(c, d)); }
+
+/* convex_cell.cu:437-500.  USE_ARITHMETIC_FILTER is off in the live build (voronoi_common.h:32), so the decision is
+ * the FP64 sign; the filter test of :479-497 (bound from predicate_generator/main.cpp:52-78) is evaluated on the
+ * side and only RECORDED in c->flagged -- the flagged class of SURVEY 8a. */
+static int in_conflict(cell_t* c, const uint8_t* v, f4 e) {
   f4 p1 = c->clip[v[0]], p2 = c->clip[v[1]], p3 = c->clip[v[2]];
   if (f4eq(e, p1) || f4eq(e, p2) || f4eq(e, p3)) return 0;
   double det = det4x4d(p1.x, p2.x, p3.x, e.x, p1.y, p2.y, p3.y, e.y, p1.z, p2.z, p3.z, e.z, p1.w,
                        p2.w, p3.w, e.w);
+  double maxx = dmax4(fabs((double)p1.x), fabs((double)p2.x), fabs((double)p3.x), fabs((double)e.x));
+  double maxy = dmax4(fabs((double)p1.y), fabs((double)p2.y), fabs((double)p3.y), fabs((double)e.y));
+  double maxz = dmax4(fabs((double)p1.z), fabs((double)p2.z), fabs((double)p3.z), fabs((double)e.z));
+  double eps = 1.2466136531027298e-13 * maxx * maxy * maxz;
+  double max_max = fmax(fmax(maxx, maxy), maxz);
+  eps *= (max_max * max_max);
+  if (fabs(det) < eps) c->flagged = 1;
   return det > 0.0;
 }
 
@@ -431,6 +444,35 @@ double orc_rpd_run_pairs(const float* verts_aos, const int* idx_aos, int n_tet, 
   free(vol_t);
   free(bary_t);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* the flagged class per candidate pair: the clipping of run_pair with the static-filter test recorded.  Equals the
+ * per-pair status needs_exact_predicates of the reference built with USE_ARITHMETIC_FILTER (oracle/_ref/
+ * libref_rpd_filter.so): that build stops a cell at its first flagged clip, this one records it and goes on --
+ * the tests up to that clip are the same ones. */
+void orc_rpd_flagged_pairs(const float* verts_aos, const int* idx_aos, int n_tet, const int* v_adjs,
+                           const int* e_adj6, const int* f_adjs, const int* f_ids, const float* site_soa,
+                           const float* site_w, const unsigned* site_flags, int n_site, const int* site_knn,
+                           int site_k, const int* pair_tet, const int* pair_site, long n_pairs, uint8_t* flagged) {
+  (void)n_tet;
+#pragma omp parallel
+  {
+    cell_t* c = (cell_t*)malloc(sizeof(cell_t));
+    orc_record* rec = (orc_record*)malloc(sizeof(orc_record));
+    float* vol = (float*)calloc((size_t)n_site, sizeof(float));
+    float* bary = (float*)calloc(3 * (size_t)n_site, sizeof(float));
+#pragma omp for schedule(dynamic, 256)
+    for (long p = 0; p < n_pairs; p++) {
+      c->flagged = 0;
+      run_pair(c, verts_aos, idx_aos, v_adjs, e_adj6, f_adjs, f_ids, site_soa, site_w, site_flags, n_site, site_knn,
+               site_k, pair_tet[p], pair_site[p], p, rec, 0, bary, vol);
+      flagged[p] = (uint8_t)(c->flagged != 0);
+    }
+    free(c);
+    free(rec);
+    free(vol);
+    free(bary);
+  }
 }
 
 /* a3: knncuda.cu:21-94 (compute_distances: ssd += tmp*tmp over x,y,z then 13 zero terms)

@@ -4,7 +4,11 @@
 // /root/reference, included in place at build time), then runs the reference's own
 // ConvexCellHost::reload_active / cal_cell_euler on the returned cells.
 //   shim_driver rpd <in.bin> <out.bin>     |   shim_driver d2m <in.bin> <out.bin>
+//   shim_driver bench <in.bin> <reps>      times the drop-in call itself (bench.py's e2e_shim leg): the input carries
+//                                          the compact e_adj6; the dense e_adjs table the reference signature wants
+//                                          (io.cxx:264) is built here, once, like a LibMAT caller holds it
 // Built by tests/cxx/Makefile into tests/cxx/_build/ (git-ignored, travels to the GPU box).
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -28,8 +32,60 @@ static void wr(FILE* f, const T* p, int64_t n) {
   if (n) fwrite(p, sizeof(T), (size_t)n, f);
 }
 
+// bench mode: the whole drop-in call, std::vector<ConvexCellHost> result included, `reps` times
+static int bench_rpd(const char* path, int reps) {
+  FILE* in = fopen(path, "rb");
+  if (!in) return 3;
+  auto vertices = rd<float>(in);
+  auto indices = rd<int>(in);
+  auto v_adjs = rd<int>(in);
+  auto e6 = rd<int>(in);
+  auto f_adjs = rd<int>(in);
+  auto f_ids = rd<int>(in);
+  auto site = rd<float>(in);
+  auto w = rd<float>(in);
+  auto flags = rd<uint>(in);
+  auto knn = rd<int>(in);
+  auto meta = rd<int>(in);  // n_site, site_k
+  fclose(in);
+  const long long n_vert = (long long)vertices.size() / 3, n_tet = (long long)indices.size() / 4;
+  std::vector<int> e_adjs((size_t)(n_vert * (n_vert + 1) / 2 + 1), -1);
+  static const int ep[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+  for (long long t = 0; t < n_tet; t++)
+    for (int e = 0; e < 6; e++) {
+      const long long a = indices[4 * t + ep[e][0]], b = indices[4 * t + ep[e][1]];
+      const long long vmin = std::min(a, b), vmax = std::max(a, b);
+      e_adjs[(size_t)((vmin + 1) * n_vert - vmin * (vmin + 1) / 2 - (n_vert - vmax))] = e6[6 * t + e];
+    }
+  std::map<int, std::set<int>> v2tets;
+  std::vector<float> vol;
+  std::vector<double> total, up, run, expand;
+  size_t n_cells = 0;
+  for (int r = 0; r < reps + 1; r++) {  // the first call (context creation, first-run allocations) is not timed
+    std::vector<ConvexCellHost> cells = compute_clipped_voro_diagram_GPU(
+        0, vertices, indices, v2tets, v_adjs, e_adjs, f_adjs, f_ids, site, meta[0], w, flags, knn, meta[1], vol, true);
+    n_cells = cells.size();
+    const double* ms = libmat_b200::last_call_ms();
+    if (r > 0) {
+      up.push_back(ms[0]);
+      run.push_back(ms[1]);
+      expand.push_back(ms[2]);
+      total.push_back(ms[3]);
+    }
+  }
+  auto med = [](std::vector<double> v) {
+    std::sort(v.begin(), v.end());
+    return v.empty() ? 0.0 : v[v.size() / 2];
+  };
+  printf("{\"n_cells\": %zu, \"reps\": %d, \"call_ms\": %.3f, \"upload_ms\": %.3f, \"run_to_host_ms\": %.3f, "
+         "\"convexcellhost_ms\": %.3f, \"bytes_convexcellhost\": %zu}\n",
+         n_cells, reps, med(total), med(up), med(run), med(expand), n_cells * sizeof(ConvexCellHost));
+  return n_cells > 0 ? 0 : 4;
+}
+
 int main(int argc, char** argv) {
   if (argc < 4) return 2;
+  if (std::string(argv[1]) == "bench") return bench_rpd(argv[2], atoi(argv[3]));
   FILE* in = fopen(argv[2], "rb");
   FILE* out = fopen(argv[3], "wb");
   if (!in || !out) return 3;

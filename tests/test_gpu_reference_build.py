@@ -1,0 +1,61 @@
+"""The reference's OWN CUDA build on the B200 (oracle/_ref/libref_rpd_gpu.so, libref_d2m.so: the reference sources
+compiled in place with its own flags, --use_fast_math and FMA contraction included) as a parity target next to its host
+build and this library -- what LibMAT users actually run (SURVEY 2.1 / 8c "host-shim == device build on config 1")."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_cuda_build_vs_host_build_vs_library_cfg1(ctx, O, cfg1, cfg1_oracle, capfd):
+    if O.ref("rpd_gpu") is None or O.ref("rpd") is None:
+        pytest.skip("oracle/_ref not built")
+    mesh, sites, knn, k = cfg1
+    pt, ps, _, _ = cfg1_oracle
+    out = O.ref_rpd_gpu(mesh, sites, knn, k)
+    capfd.readouterr()  # the reference prints its launch shape
+    assert out is not None, "the reference CUDA build did not run"
+    dev, ms = out
+    assert ms["kernel_ms"] > 0 and ms["d2h_ms"] > 0
+    host, _, _ = O.run_pairs(mesh, sites, knn, k, pt, ps, impl="ref")
+    host = host[host["status"] == 4]
+    ctx.set_mesh(mesh)
+    mine = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, knn, k).records()
+    # the device build (FMA-contracted, fast-math division) returns the same cells in the same order ...
+    assert len(dev) == len(host) == len(mine)
+    for f in ("voro_id", "tet_id", "id"):
+        assert np.array_equal(dev[f], host[f]) and np.array_equal(dev[f], mine[f]), f
+    # ... with the same combinatorics: any difference would have to be a flagged cell, and config 1 has none
+    fr = O.flagged_pairs(mesh, sites, knn, k, pt, ps, "oracle")
+    assert fr.sum() == 0
+    d = O.defined_equal(host, dev)
+    for f in ("status", "nb_v", "nb_p", "nb_e", "ver", "id2", "edge"):
+        assert d[f] == 0, d
+    assert d["cells_compared"] == len(host)
+    # plane equations: FMA contraction / fast-math change the last bits of a bisector's d at most
+    ip = np.arange(64)[None, :] < host["nb_p"][:, None]
+    a, b = host["clip"][..., :4][ip], dev["clip"][..., :4][ip]
+    assert np.allclose(a, b, rtol=2e-6, atol=0) or np.max(np.abs(a - b) / np.maximum(np.abs(a), 1.0)) < 2e-6
+    # the library is byte-identical to the HOST build (checked elsewhere) -- and therefore combinatorially to this one
+    d2 = O.defined_equal(dev, mine)
+    for f in ("status", "nb_v", "nb_p", "nb_e", "ver", "id2", "edge"):
+        assert d2[f] == 0, d2
+    print(f"reference CUDA build, config 1: kernel {ms['kernel_ms']:.2f} ms, D2H {ms['d2h_ms']:.2f} ms, call {ms['call_ms']:.0f} ms")
+
+
+def test_reference_dist2mat_kernel_vs_library(ctx, O, synth):
+    if O.ref("d2m") is None:
+        pytest.skip("oracle/_ref not built")
+    d = synth.make_dist2mat(200000)
+    out = O.ref_d2m_gpu(d)
+    assert out is not None, "the reference dist2mat CUDA build did not run"
+    rr, rc, _ = out
+    ko = O.ref_d2m_gpu(d, kernel_only=True, warmup=1, reps=2)
+    assert ko is not None and np.array_equal(ko[0].view(np.uint32), rr.view(np.uint32)) and np.array_equal(ko[1], rc)
+    r, cid, tie = ctx.compute_closest_dist2mat(d.spheres, d.samples, d.offset, d.count, d.prims)
+    rel = np.abs(r - rr) / np.maximum(np.abs(rr), 1e-3)
+    assert rel.max() <= 1e-6, rel.max()
+    assert not ((cid != rc) & (tie == 0)).any()
+    # device build vs host build of the reference itself: same tolerance class
+    rh, ch, _ = O.dist2mat(d, "ref")
+    assert (np.abs(rh - rr) / np.maximum(np.abs(rr), 1e-3)).max() <= 1e-6
