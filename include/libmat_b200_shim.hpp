@@ -18,6 +18,10 @@
 // hard-wiring (MB_DEVICE environment variable, default: current device).
 #pragma once
 
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -148,6 +152,22 @@ inline std::vector<ConvexCellHost> compute_clipped_voro_diagram_GPU(
   long n_cells = 0;
   mb_rpd_count(res, &n_cells, nullptr, nullptr);
   const uint32_t* blob = static_cast<const uint32_t*>(blob_v);
+  // 3 776 B per ConvexCellHost: the vector is GBs of fresh pages (config 2: 2.9 GB) whose first touch -- one page fault
+  // and one kernel-side zero fill each -- would otherwise happen serially inside resize().  Touch them from all
+  // threads first (transparent huge pages where the kernel grants them), then construct.
+  out.reserve((size_t)n_cells);
+  if (n_cells > 4096) {
+    char* base = reinterpret_cast<char*>(out.data());
+    const size_t bytes = (size_t)n_cells * sizeof(ConvexCellHost);
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    {
+      const size_t a = ((size_t)base + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+      if (a < (size_t)base + bytes) madvise(reinterpret_cast<void*>(a), (((size_t)base + bytes - a) >> 21) << 21, MADV_HUGEPAGE);
+    }
+#endif
+#pragma omp parallel for schedule(static)
+    for (long off = 0; off < (long)bytes; off += 4096) base[off] = 0;
+  }
   out.resize((size_t)n_cells);
 #pragma omp parallel for schedule(static)
   for (long i = 0; i < n_cells; i++) libmat_b200::expand_cell(blob + offs[i] / 4, (int)i, out[(size_t)i]);

@@ -110,6 +110,87 @@ __device__ __forceinline__ float4 cofactors_f32(const Minors& m) {
   return make_float4((float)m.m234, (float)(-m.m134), (float)m.m124, (float)(-m.m123));
 }
 
+// Garbage collection of dead planes / inactive edges (per-tet candidate lists only; see B2 in k_clip).  Rare path, kept
+// out of line: all lanes of ONE group call it together.
+template <int G, class CellS>
+__device__ __noinline__ void cell_gc(CellS& S, int lane, unsigned gmask, int gshift, int nb_v, int& nb_p, int& nb_e) {
+  unsigned long long am = 0xFull;
+  for (int v = lane; v < nb_v; v += G) {
+    const uchar4 tv = S.ver[v];
+    am |= (1ull << tv.x) | (1ull << tv.y) | (1ull << tv.z);
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) am |= __shfl_xor_sync(gmask, am, o);
+  int ne_new = 0;
+  for (int eb = 0; eb < nb_e; eb += G) {
+    const int ei = eb + lane;
+    bool keep = false;
+    unsigned char a = 0, b = 0, z = 0;
+    if (ei < nb_e) {
+      a = S.edge[3 * ei];
+      b = S.edge[3 * ei + 1];
+      z = S.edge[3 * ei + 2];
+      if (((am >> a) & 1ull) && ((am >> b) & 1ull)) {
+        int shared = 0;
+        for (int v = 0; v < nb_v; v++) {
+          const uchar4 tv = S.ver[v];
+          const bool ha = tv.x == a || tv.y == a || tv.z == a, hb = tv.x == b || tv.y == b || tv.z == b;
+          shared += (ha && hb);
+        }
+        keep = shared >= 2;
+      }
+    }
+    const unsigned m = group_ballot<G>(gmask, gshift, keep);
+    __syncwarp(gmask);  // every lane has read its entry; writes below go to indices <= eb
+    if (keep) {
+      const int pos = ne_new + __popc(m & ((1u << lane) - 1u));
+      S.edge[3 * pos] = (unsigned char)__popcll(am & ((1ull << a) - 1ull));
+      S.edge[3 * pos + 1] = (unsigned char)__popcll(am & ((1ull << b) - 1ull));
+      S.edge[3 * pos + 2] = z;
+    }
+    ne_new += __popc(m);
+    __syncwarp(gmask);
+  }
+  for (int v = lane; v < nb_v; v += G) {
+    uchar4 tv = S.ver[v];
+    tv.x = (unsigned char)__popcll(am & ((1ull << tv.x) - 1ull));
+    tv.y = (unsigned char)__popcll(am & ((1ull << tv.y) - 1ull));
+    tv.z = (unsigned char)__popcll(am & ((1ull << tv.z) - 1ull));
+    S.ver[v] = tv;
+  }
+  int np_new = 0;
+  for (int pb = 0; pb < nb_p; pb += G) {
+    const int pi = pb + lane;
+    const bool keep = pi < nb_p && ((am >> pi) & 1ull);
+    float4 pl = make_float4(0, 0, 0, 0);
+    int nbp = 0;
+    if (keep) {
+      pl = S.plane[pi];
+      nbp = S.pnb[pi];
+    }
+    const unsigned m = group_ballot<G>(gmask, gshift, keep);
+    __syncwarp(gmask);
+    if (keep) {
+      const int pos = np_new + __popc(m & ((1u << lane) - 1u));
+      S.plane[pos] = pl;
+      S.pnb[pos] = nbp;
+    }
+    np_new += __popc(m);
+    __syncwarp(gmask);
+  }
+  nb_p = np_new;
+  nb_e = ne_new;
+}
+
+// The FP64 determinant + static-filter test is the RARE path of the conflict predicate (~1 test in 3 000): kept out of
+// line so that the hot loop stays small -- the kernel is sensitive to its instruction footprint (stall_no_instruction).
+// bit 0: in conflict, bit 1: flagged
+__device__ __noinline__ int conflict_exact_flag_ool(float4 p1, float4 p2, float4 p3, float4 e) {
+  bool fl = false;
+  const bool c = conflict_exact_flag(p1, p2, p3, e, fl);
+  return (c ? 1 : 0) | (fl ? 2 : 0);
+}
+
 // PT = per-tet candidate lists (grid-kNN mode).  There array positions are not part of the contract
 // (SURVEY 8a canonical form), so the order-defining serial replay of C2 is replaced by a
 // group-cooperative partition + adjacency-bit-matrix cavity boundary; every predicate decision and
@@ -328,6 +409,8 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
           status = ST_vertex_overflow;
           todo = 0;
           state = GS_FINISH;
+        } else if (todo == 0 && (list_done || base >= list_len)) {
+          state = GS_FINISH;  // nothing left to clip: the record is written in this same iteration
         }
       }
     }
@@ -339,72 +422,7 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
     // voronoi_defs.cxx:92-103) are dropped and the survivors renumbered.  Tet faces keep indices
     // 0..3; the canonical form (active planes / edges, vertices) is unchanged.  Rare path.
     if (per_tet && state == GS_RUN && todo != 0 && (nb_e >= gc_next_e || nb_p >= gc_next_p)) {
-      unsigned long long am = 0xFull;
-      for (int v = lane; v < nb_v; v += G) {
-        const uchar4 tv = S.ver[v];
-        am |= (1ull << tv.x) | (1ull << tv.y) | (1ull << tv.z);
-      }
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) am |= __shfl_xor_sync(gmask, am, o);
-      int ne_new = 0;
-      for (int eb = 0; eb < nb_e; eb += G) {
-        const int ei = eb + lane;
-        bool keep = false;
-        unsigned char a = 0, b = 0, z = 0;
-        if (ei < nb_e) {
-          a = S.edge[3 * ei];
-          b = S.edge[3 * ei + 1];
-          z = S.edge[3 * ei + 2];
-          if (((am >> a) & 1ull) && ((am >> b) & 1ull)) {
-            int shared = 0;
-            for (int v = 0; v < nb_v; v++) {
-              const uchar4 tv = S.ver[v];
-              const bool ha = tv.x == a || tv.y == a || tv.z == a, hb = tv.x == b || tv.y == b || tv.z == b;
-              shared += (ha && hb);
-            }
-            keep = shared >= 2;
-          }
-        }
-        const unsigned m = group_ballot<G>(gmask, gshift, keep);
-        __syncwarp(gmask);  // every lane has read its entry; writes below go to indices <= eb
-        if (keep) {
-          const int pos = ne_new + __popc(m & ((1u << lane) - 1u));
-          S.edge[3 * pos] = (unsigned char)__popcll(am & ((1ull << a) - 1ull));
-          S.edge[3 * pos + 1] = (unsigned char)__popcll(am & ((1ull << b) - 1ull));
-          S.edge[3 * pos + 2] = z;
-        }
-        ne_new += __popc(m);
-        __syncwarp(gmask);
-      }
-      for (int v = lane; v < nb_v; v += G) {
-        uchar4 tv = S.ver[v];
-        tv.x = (unsigned char)__popcll(am & ((1ull << tv.x) - 1ull));
-        tv.y = (unsigned char)__popcll(am & ((1ull << tv.y) - 1ull));
-        tv.z = (unsigned char)__popcll(am & ((1ull << tv.z) - 1ull));
-        S.ver[v] = tv;
-      }
-      int np_new = 0;
-      for (int pb = 0; pb < nb_p; pb += G) {
-        const int pi = pb + lane;
-        const bool keep = pi < nb_p && ((am >> pi) & 1ull);
-        float4 pl = make_float4(0, 0, 0, 0);
-        int nbp = 0;
-        if (keep) {
-          pl = S.plane[pi];
-          nbp = S.pnb[pi];
-        }
-        const unsigned m = group_ballot<G>(gmask, gshift, keep);
-        __syncwarp(gmask);
-        if (keep) {
-          const int pos = np_new + __popc(m & ((1u << lane) - 1u));
-          S.plane[pos] = pl;
-          S.pnb[pos] = nbp;
-        }
-        np_new += __popc(m);
-        __syncwarp(gmask);
-      }
-      nb_p = np_new;
-      nb_e = ne_new;
+      cell_gc<G, CellS>(S, lane, gmask, gshift, nb_v, nb_p, nb_e);
       gc_next_e = max(GC_E0, nb_e + 24);
       gc_next_p = max(GC_P0, nb_p + 4);
       if (lane == 0) n_gc++;
@@ -460,13 +478,15 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
             }
           }
           if (!decided) {
-            cf = conflict_exact_flag(S.plane[tv.x], S.plane[tv.y], S.plane[tv.z], e, flagged);
+            const int r2 = conflict_exact_flag_ool(S.plane[tv.x], S.plane[tv.y], S.plane[tv.z], e);
+            cf = (r2 & 1) != 0;
+            flagged = flagged || (r2 & 2) != 0;
             n_exact++;
           }
         }
         const unsigned m = (__ballot_sync(0xffffffffu, cf) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
         nb_r += __popc(m);
-        if (vb < 64)  // G divides 64: a round never straddles the two words
+        if (KT <= 64 || vb < 64)  // G divides 64: a round never straddles the two words
           f0 |= (unsigned long long)m << vb;
         else
           f1 |= m << (vb - 64);
@@ -500,19 +520,26 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
         // kept vertices of the tail
         unsigned long long k0 = ~f0;
         unsigned k1 = ~f1;
-        if (nv_new < 64) k0 &= ~((1ull << nv_new) - 1ull); else { k0 = 0; k1 &= ~((1u << (nv_new - 64)) - 1u); }
-        if (nb_v < 64) { k0 &= (1ull << nb_v) - 1ull; k1 = 0; } else if (nb_v < 96) k1 &= (1u << (nb_v - 64)) - 1u;
+        if (KT <= 64) {
+          k0 &= ~((1ull << nv_new) - 1ull);  // nv_new < nb_v <= 64
+          if (nb_v < 64) k0 &= (1ull << nb_v) - 1ull;
+          k1 = 0;
+        } else {
+          if (nv_new < 64) k0 &= ~((1ull << nv_new) - 1ull); else { k0 = 0; k1 &= ~((1u << (nv_new - 64)) - 1u); }
+          if (nb_v < 64) { k0 &= (1ull << nb_v) - 1ull; k1 = 0; } else if (nb_v < 96) k1 &= (1u << (nb_v - 64)) - 1u;
+        }
         for (int vb = 0; vb < hmax; vb += G) {
           const int v = vb + lane;
-          const bool fv = v < 64 ? ((f0 >> v) & 1ull) : ((f1 >> (v - 64)) & 1u);
+          const bool fv = (KT <= 64 || v < 64) ? ((f0 >> (v & 63)) & 1ull) : ((f1 >> (v - 64)) & 1u);
           const bool mv = a1 && v < nv_new && fv;
           bool pvalid = false;
           if (mv) {
             // rank among the removed vertices of the head
-            int i = v < 64 ? __popcll(f0 & ((1ull << v) - 1ull)) : (__popcll(f0) + __popc(f1 & ((1u << (v - 64)) - 1u)));
+            int i = (KT <= 64 || v < 64) ? __popcll(f0 & ((1ull << (v & 63)) - 1ull))
+                                         : (__popcll(f0) + __popc(f1 & ((1u << (v - 64)) - 1u)));
             int partner;
             const int pc0 = __popcll(k0);
-            if (i < pc0) {
+            if (KT <= 64 || i < pc0) {
               unsigned long long kk = k0;
               for (; i > 0; i--) kk &= kk - 1ull;
               partner = __ffsll((long long)kk) - 1;
@@ -781,6 +808,8 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
         state = GS_FINISH;
       }
     }
+    // the last plane of the list has been dealt with (clipped or dropped): finish in this same iteration
+    if (c_act && state == GS_RUN && todo == 0 && (list_done || base >= list_len)) state = GS_FINISH;
     __syncwarp();
     // ================= D: write the record (copy(), convex_cell.cu:933-949) =======================
     if (state == GS_FINISH) {

@@ -165,9 +165,9 @@ struct __align__(16) CellT {
 };
 typedef CellT<MBK_MAX_P, MBK_MAX_T, MBK_MAX_E> CellS;
 static_assert(offsetof(CellS, bnext) % 16 == 0, "bnext must be 16-byte aligned");
-// compact caps of the grid-kNN first pass: 2 672 B per cell -> 5 blocks of 16 cells per SM instead of 4
+// compact caps of the first pass: 2 640 B per cell -> 5 blocks of 16 cells per SM instead of 4
 #define MBK_SMALL_P 48
-#define MBK_SMALL_T 72
+#define MBK_SMALL_T 64   // <= 64: the conflict flags of a clip fit one 64-bit word (the second word's code is compiled out)
 #define MBK_SMALL_E 120
 typedef CellT<MBK_SMALL_P, MBK_SMALL_T, MBK_SMALL_E> CellSmall;
 static_assert(offsetof(CellSmall, bnext) % 16 == 0, "bnext must be 16-byte aligned");
