@@ -239,6 +239,7 @@ struct mb_ctx {
   std::vector<float4> h_tet_planes; // host copy of the 4 face planes per tet, fetched on first use
   bool h_tet_planes_valid = false;
   double pairs_per_tet_hint = 0.0;  // grid mode: 1.5 x the largest pairs-per-tet seen (speculative span launches)
+  int clip_variant = 0;             // MB_CLIP_VARIANT=1 (A/B tests): grid-kNN first pass with the state-machine kernel k_clip
   bool no_cull = false;             // MB_NO_CULL=1 (debug / parity tests): no conservative cull of listed neighbours
   unsigned long long stream_generation = 0;  // bumped by every streamed run into the context's own pinned buffers
   int trace_level = 0;

@@ -9,6 +9,7 @@
 
 #include "mb_internal.h"
 #include "rpd_clip.cuh"
+#include "rpd_clip2.cuh"
 #include "rpd_grid.cuh"
 
 // =============================================================================================
@@ -507,6 +508,37 @@ static void launch_clip_pass(mb_ctx* ctx, ClipArgs A, bool second_pass) {
   MB_CUDA(cudaGetLastError());
 }
 
+// grid-kNN mode, first pass: the batch-synchronous compact-caps kernel (rpd_clip2.cuh)
+template <int G, int NB>
+static void launch_clip_tiny(mb_ctx* ctx, ClipArgs A) {
+  constexpr int groups = 128 / G;
+  const size_t smem = sizeof(CellTiny) * groups;
+  static bool attr_set_dev[64] = {false};
+  bool& attr_set = attr_set_dev[ctx->device & 63];
+  if (!attr_set) {
+    MB_CUDA(cudaFuncSetAttribute(k_clip_tiny<G, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  static int per_sm_dev[64] = {0};
+  int& per_sm = per_sm_dev[ctx->device & 63];
+  if (per_sm < 1) {
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip_tiny<G, NB>, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  const long long want = (A.n_pairs + groups - 1) / groups;
+  long long grid = std::max<long long>(1, std::min<long long>(want, (long long)ctx->sm_count * per_sm));
+  {
+    constexpr int NG = 32 / G;
+    const long long warps = grid * 4;
+    long long g = A.n_pairs / (warps * 16);
+    g = (g / NG) * NG;
+    A.grab = A.n_pairs_dev ? 0 : (int)std::max<long long>(NG, std::min<long long>(8 * NG, g));
+  }
+  ctx->n_launches++;
+  k_clip_tiny<G, NB><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
+  MB_CUDA(cudaGetLastError());
+}
+
 // Two passes in both modes: compact-caps pass (5 blocks / SM), then the cells it could not hold at the reference's
 // caps.  A cell recomputed by the second pass goes through exactly the single-pass code path, so given-neighbours
 // records (array positions, overflow statuses) stay byte-identical.
@@ -517,7 +549,16 @@ static void launch_clip(mb_ctx* ctx, ClipArgs A) {
   A.work_count = nullptr;
   ctx->redo_list.reserve((size_t)A.n_pairs + 1);
   A.redo_out = ctx->redo_list.p;
-  launch_clip_pass<G, PT, true>(ctx, A, false);
+  if constexpr (PT && (G == 8 || G == 4)) {
+    if (ctx->clip_variant == 0)
+      launch_clip_tiny<G, 6>(ctx, A);
+    else if (ctx->clip_variant == 2)
+      launch_clip_tiny<G, 5>(ctx, A);
+    else
+      launch_clip_pass<G, PT, true>(ctx, A, false);
+  } else {
+    launch_clip_pass<G, PT, true>(ctx, A, false);
+  }
   A.redo_out = nullptr;
   A.work_list = ctx->redo_list.p;
   A.work_count = A.counters + CNT_REDO;

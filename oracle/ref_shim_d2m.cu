@@ -9,7 +9,42 @@
 #include <omp.h>
 #include <time.h>
 
+// per-(sample, primitive) evaluation of the reference's distance functions ON THE DEVICE (its own device build):
+// lets a test compare device and host builds of the reference primitive by primitive
+__global__ void ref_eval_prims_kernel(const float3* pos, const float4* spheres, const int3* prims, int n, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int3 prim = prims[i];
+  float dist = 1e16f;
+  if (prim.x == -1 && prim.y == -1)
+    dist = distance_to_sphere(pos[i], spheres[prim.z]);
+  else if (prim.x == -1 && prim.y != -1)
+    dist = compute_distance_to_cone(pos[i], spheres[prim.y], spheres[prim.z]);
+  else if (prim.x != -1)
+    dist = compute_distance_to_slab(pos[i], spheres[prim.x], spheres[prim.y], spheres[prim.z]);
+  out[i] = dist;
+}
+
 extern "C" {
+
+// n (position, primitive) pairs evaluated by the reference's device code; returns 0, <0 without a device
+int ref_d2m_eval_prims_gpu(const float* spheres, int n_sph, const float* pos, const int* prims, int n, float* out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1;
+  float4* d_s; float3* d_p; int3* d_q; float* d_o;
+  cudaMalloc(&d_s, sizeof(float4) * (size_t)n_sph);
+  cudaMalloc(&d_p, sizeof(float3) * (size_t)n);
+  cudaMalloc(&d_q, sizeof(int3) * (size_t)n);
+  cudaMalloc(&d_o, sizeof(float) * (size_t)n);
+  cudaMemcpy(d_s, spheres, sizeof(float4) * (size_t)n_sph, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_p, pos, sizeof(float3) * (size_t)n, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_q, prims, sizeof(int3) * (size_t)n, cudaMemcpyHostToDevice);
+  ref_eval_prims_kernel<<<(n + 127) / 128, 128>>>(d_p, d_s, d_q, n, d_o);
+  const cudaError_t e = cudaMemcpy(out, d_o, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d_s); cudaFree(d_p); cudaFree(d_q); cudaFree(d_o);
+  return e == cudaSuccess ? 0 : -2;
+}
+
 
 float ref_d2m_sphere(const float* p, const float* s) {
   return distance_to_sphere(make_float3(p[0], p[1], p[2]), make_float4(s[0], s[1], s[2], s[3]));

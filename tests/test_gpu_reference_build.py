@@ -23,8 +23,9 @@ def test_reference_cuda_build_vs_host_build_vs_library_cfg1(ctx, O, cfg1, cfg1_o
     mine = ctx.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, knn, k).records()
     # the device build (FMA-contracted, fast-math division) returns the same cells in the same order ...
     assert len(dev) == len(host) == len(mine)
-    for f in ("voro_id", "tet_id", "id"):
+    for f in ("voro_id", "tet_id"):
         assert np.array_equal(dev[f], host[f]) and np.array_equal(dev[f], mine[f]), f
+    assert np.array_equal(dev["id"], mine["id"]) and np.array_equal(dev["id"], np.arange(len(dev)))  # voronoi.cu:766-768
     # ... with the same combinatorics: any difference would have to be a flagged cell, and config 1 has none
     fr = O.flagged_pairs(mesh, sites, knn, k, pt, ps, "oracle")
     assert fr.sum() == 0
