@@ -1,5 +1,7 @@
 """dev: where does the reference's dist2mat DEVICE build differ from its host build / this library?"""
 import ctypes as C
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from libmat_b200 import synth
 from libmat_b200.rpd import Context

@@ -33,10 +33,14 @@ def test_reference_cuda_build_vs_host_build_vs_library_cfg1(ctx, O, cfg1, cfg1_o
     for f in ("status", "nb_v", "nb_p", "nb_e", "ver", "id2", "edge"):
         assert d[f] == 0, d
     assert d["cells_compared"] == len(host)
-    # plane equations: FMA contraction / fast-math change the last bits of a bisector's d at most
+    # plane equations: FMA contraction / fast-math division move the last bits (relative to the plane's own scale: a
+    # cancelling normal component of a sliver tet can lose all its relative accuracy)
     ip = np.arange(64)[None, :] < host["nb_p"][:, None]
-    a, b = host["clip"][..., :4][ip], dev["clip"][..., :4][ip]
-    assert np.allclose(a, b, rtol=2e-6, atol=0) or np.max(np.abs(a - b) / np.maximum(np.abs(a), 1.0)) < 2e-6
+    a, b = host["clip"][..., :4][ip].astype(np.float64), dev["clip"][..., :4][ip].astype(np.float64)
+    nscale = np.abs(a[:, :3]).max(axis=1)
+    assert np.max(np.abs(a[:, :3] - b[:, :3]).max(axis=1) / nscale) < 1e-5
+    assert np.max(np.abs(a[:, 3] - b[:, 3]) / np.maximum(np.abs(a[:, 3]), 1000.0 * nscale)) < 1e-5
+    print(f"reference device vs host build: {100.0 * np.mean((a == b).all(axis=1)):.2f} % of the planes bit-identical")
     # the library is byte-identical to the HOST build (checked elsewhere) -- and therefore combinatorially to this one
     d2 = O.defined_equal(dev, mine)
     for f in ("status", "nb_v", "nb_p", "nb_e", "ver", "id2", "edge"):
