@@ -22,12 +22,13 @@ struct f3 {
 __device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ f3 sub3(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 __device__ __forceinline__ float len3(f3 v) { return sqrtf(dot3(v, v)); }
-// clamp = fmaxf(a, fminf(f, b)): a NaN f becomes b (cuda_helper_math.h:932-934)
-// Written with explicit ordered compares: nvcc turns fmaxf(0, fminf(t, 1)) into a .sat modifier,
-// and .sat maps NaN to 0 whereas the reference's host build maps it to 1 (SURVEY KAT-2b).
+// clamp(t, 0, 1) = fmaxf(0, fminf(t, 1)) (cuda_helper_math.h:932-934) as the reference's DEVICE build evaluates it:
+// nvcc lowers it to a saturate modifier, and .sat maps a NaN t to +0 (IEEE fminf / fmaxf -- the reference's host
+// compile -- would give 1).  t is NaN for nested spheres (dist2mat.cu:61): the reference then returns the distance to
+// the larger sphere.  Written with explicit compares so that the semantics do not depend on the compiler's lowering.
 __device__ __forceinline__ float clampf(float f, float a, float b) {
-  const float m = (f < b) ? f : b;  // fminf(f, b): NaN f -> b
-  return (a > m) ? a : m;           // fmaxf(a, m)
+  const float m = (f < b) ? f : b;         // NaN f -> b here ...
+  return (f != f) ? a : ((a > m) ? a : m);  // ... and a in the end, like .sat
 }
 // lerp(a,b,t) = b + t*(a-b) (cuda_helper_math.h:911-913)
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return b + t * (a - b); }

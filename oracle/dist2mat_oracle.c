@@ -20,7 +20,10 @@ typedef struct {
 static float dotf(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; } /* helper_math:1015 */
 static f3 sub3(f3 a, f3 b) { return (f3){a.x - b.x, a.y - b.y, a.z - b.z}; }
 static float length3(f3 v) { return sqrtf(dotf(v, v)); } /* :1047 */
-static float clampf(float f, float a, float b) { return fmaxf(a, fminf(f, b)); } /* :932-934 */
+/* cuda_helper_math.h:932-934 clamp = fmaxf(a, fminf(f, b)) AS THE REFERENCE'S DEVICE BUILD EVALUATES IT: nvcc lowers
+ * clamp(t, 0, 1) to a saturate modifier, which maps a NaN t to +0 (IEEE fminf/fmaxf would give 1).  t is NaN for
+ * nested spheres (dist2mat.cu:61); verified against the device build on the B200 (tests/test_gpu_reference_build.py). */
+static float clampf(float f, float a, float b) { return (f != f) ? a : fmaxf(a, fminf(f, b)); }
 static float lerpf(float a, float b, float t) { return b + t * (a - b); } /* :911-913 */
 
 /* dist2mat.cu:5-8 */

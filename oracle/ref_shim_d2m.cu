@@ -4,7 +4,27 @@
 // Its distance functions are __host__ __device__ (dist2mat.cu:5-193), so this TU can call them
 // on the host (IEEE, -ffp-contract=off) as the CPU oracle / CPU baseline, and on a GPU box it
 // can also run the reference's own kernel through compute_closest_dist2mat (dist2mat.cu:280-315).
+//
+// ONE deliberate difference between the host compile of this file and the reference's device build, found by running
+// both on the B200 (tests/test_gpu_reference_build.py): clamp(t, 0.f, 1.f) = fmaxf(0, fminf(t, 1))
+// (cuda_helper_math.h:932-934) is compiled by nvcc for the device into a SATURATE modifier, and .sat maps NaN to +0,
+// whereas IEEE fminf/fmaxf on the host map it to 1.  t IS NaN whenever the two spheres of a cone are nested
+// ((D*D - 4AF)(R1*R1 - A) R1*R1 < 0, dist2mat.cu:61): the device build then returns the distance to the LARGER
+// sphere (the true envelope), the host build the distance to the smaller one.  What LibMAT runs is the device
+// build, so the host functions below are made to follow it: inside the reference's source, clamp is routed to
+// ref_clamp_sat (device semantics).  Nothing else differs beyond last-bit rounding (FMA contraction, libm powf).
+#include <cub/cub.cuh>  // everything dist2mat.cu includes is pulled in first (include-guarded) ...
+#include "dist2mat.h"   // ... so that the macro below only touches the body of dist2mat.cu
+static inline __host__ __device__ float ref_clamp_sat(float f, float a, float b) {
+#ifdef __CUDA_ARCH__
+  return fmaxf(a, fminf(f, b));  // the device compiler's own lowering (.sat)
+#else
+  return (f != f) ? a : fmaxf(a, fminf(f, b));
+#endif
+}
+#define clamp(f, a, b) ref_clamp_sat(f, a, b)
 #include "dist2mat.cu"
+#undef clamp
 
 #include <omp.h>
 #include <time.h>

