@@ -481,10 +481,12 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5", "d2m"])
     ap.add_argument("--samples", type=int, default=0, help="dist2mat samples (config 3 is 10 000 000)")
     ap.add_argument("--lanes", type=int, default=0)
-    ap.add_argument("--lean", action="store_true",
-                    help="streamed legs: ship the records in the lean transport format (mb_rpd_opts.lean_records: without "
-                         "their plane equations, which the expansion recomputes bit-exactly from the ids).  Default: full "
-                         "compact records; at N=1 the lean variant is measured as well and reported in e2e.lean_records")
+    ap.add_argument("--records", default="slim", choices=["full", "lean", "slim"],
+                    help="transport format of the streamed legs (mb_rpd_opts.lean_records).  full: compact records with "
+                         "their plane equations; lean: without them; slim (default): additionally one neighbour id per "
+                         "bisector instead of three id words per plane.  The host expansion (mb_rpd_fetch_records / "
+                         "mb_rpd_expand_compact) restores all of it bit-exactly from the ids; at N=1 the full-record leg is "
+                         "measured as well and reported in e2e.full_records")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the shards reach rank 0")
     ap.add_argument("--chunks", type=int, default=0, help="e2e leg: tet spans of the streamed run (0 = automatic)")
     ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
@@ -641,7 +643,7 @@ def main():
     # "nccl": one-shot run, then an all-gather of the sizes + grouped NCCL send/recv (libmat_b200.dist).
     gather_buf = {"t": None}
     sink_dev = sink_host = None
-    lean = bool(args.lean)
+    lean = {"full": 0, "lean": 1, "slim": 2}[args.records]
     gather_mode = args.gather if world > 1 else "none"
     if world > 1:
         from libmat_b200.dist import ShardSink
@@ -778,21 +780,21 @@ def main():
             e2e_parts += (tb_ - ta, tc - tb_, time.perf_counter() - tc)
         barrier()
         t_e2e = time.perf_counter() - t0
-        # the same leg with the lean transport format (N = 1): reported next to the headline, never instead of it
+        # the same leg with FULL compact records (N = 1), reported next to the headline
         e2e_lean = None
-        if world == 1 and not lean:
-            ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates, lean=True).free()
+        if world == 1 and lean:
+            ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates, lean=0).free()
             torch.cuda.synchronize()
             tl0 = time.perf_counter()
             for i in range(e2e_steps):
                 set_mesh()
                 upload_sites()
-                res = ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates, lean=True)
+                res = ctx.run_to_host(n_chunks=args.chunks, lanes_per_cell=args.lanes, grid_candidates=args.grid_candidates, lean=0)
                 lean_bytes = res.compact_bytes + 8 * (res.n_cells + 1)
                 res.free()
             torch.cuda.synchronize()
             e2e_lean = {"value": cells * e2e_steps / (time.perf_counter() - tl0), "unit": UNIT, "d2h_bytes_per_step": int(lean_bytes),
-                        "note": "records without plane equations (recomputed bit-exactly from the ids on expansion)"}
+                        "note": "full compact records (plane equations and ids stored, nothing to recompute on expansion)"}
 
     # ---- max over ranks, totals ------------------------------------------------------------------
     tot = torch.tensor([float(cells), float(pairs), float(rec_bytes), float(listed)], dtype=torch.float64, device=dev)
@@ -822,7 +824,7 @@ def main():
             "run": {   "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})" + (", grid candidates" if args.grid_candidates else ", reference relation predicate"),
                        "parallelism": f"tet-shards x{world}, sites replicated" + (
                            "" if world == 1 else (", shards streamed into rank 0's HBM over NVLink peer memory (CUDA IPC, copy-engine DMA "
-                                                  "overlapped with the next tet span%s) + directory all-gather (NCCL)" % (", lean records" if lean else "") if gather_mode == "p2p"
+                                                  "overlapped with the next tet span, %s records) + directory all-gather (NCCL)" % args.records if gather_mode == "p2p"
                                                   else ", NCCL gather to rank 0 (all-gather of sizes + grouped send/recv)")),
                        "cells_per_step": total_cells, "candidate_pairs_per_step": total_pairs,
                        "pairs_per_sec": total_pairs * args.steps / t_dev},
@@ -837,9 +839,11 @@ def main():
                          "note": "latency-bound irregular kernel (not bandwidth-bound: ncu_pipes); see DESIGN.md section 5 and profiles/"},
             "e2e": {"value": total_cells * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "records": "lean transport format (ids without plane equations; expansion recomputes them bit-exactly)" if lean
-                               else "full compact records",
-                    "lean_records": e2e_lean,
+                    "records": {"full": "full compact records",
+                                "lean": "lean transport format (ids without plane equations; the expansion recomputes them bit-exactly)",
+                                "slim": "slim transport format (vertices, one neighbour id per bisector, edges; the host expansion "
+                                        "recomputes plane equations and plane ids bit-exactly: tests/test_gpu_stream.py)"}[args.records],
+                    "full_records": e2e_lean,
                     "path": ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_host (%d tet spans, D2H of span c "
                              "overlapped with the kernels of span c+1)" % e2e_chunks) if world == 1 else
                             ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_sink into a shared page-locked host segment "

@@ -122,7 +122,11 @@ typedef struct {
                            the listed neighbours in list order, so valid cells are byte-identical
                            whenever the lists contain every true power neighbour (regular-triangulation
                            lists do); only the set of empty no_intersection pairs differs */
-  int lean_records;     /* streamed runs only (mb_rpd_run_to_host / _to_sink): 1 = the records travel WITHOUT their
+  int lean_records;     /* streamed runs only: 0 = full compact records; 2 = SLIM: like 1, and the three id words per
+                           plane shrink to one neighbour site id per bisector (tet-face ids and adjacency counts are
+                           functions of the tet id): 16 + 4 nb_v + 4 (nb_p - 4) + 3 nb_e bytes, ~2.6x fewer than
+                           full.  Bits 31 and 29 of record word 2 mark it.
+                           (mb_rpd_run_to_host / _to_sink): 1 = the records travel WITHOUT their
                            plane equations (16 of ~28 bytes per plane, ~38 % of a record): a tet-face plane is a
                            function of (tet, face), a power bisector of (seed, neighbour) -- the ids stay.  Bit 31
                            of record word 2 marks the format; mb_rpd_fetch_records / mb_rpd_expand_compact

@@ -49,7 +49,7 @@ static_assert(sizeof(ConvexCellHost::edge_data) / sizeof(cuchar3) == MB_MAX_E, "
 inline void expand_cell(const uint32_t* w, int id, ConvexCellHost& c) {
   const int nb_v = w[2] & 0xff, nb_p = (w[2] >> 8) & 0xff, nb_e = (w[2] >> 16) & 0xff;
   c.is_active = true;
-  c.status = static_cast<Status>((int)((w[2] >> 24) & 0x3f));  // bit 30: flagged class, bit 31: lean format
+  c.status = static_cast<Status>((int)((w[2] >> 24) & 0xf));  // bits 29 / 31: transport format, bit 30: flagged class
   c.thread_id = id;
   c.voro_id = (int)w[1];
   c.tet_id = (int)w[0];

@@ -20,6 +20,12 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-fmad=false", "-Xcompiler", "-fPIC,-fopenmp,-O2,-ffp-contract=off", "-Xptxas", "-v"]
 
 
+# dist2mat is pinned against the reference's DEVICE build (nvcc's default FMA contraction on the reference's own
+# expressions): its slab solve is ill-conditioned, and only the same contraction reproduces the same roots
+# (tests/test_gpu_reference_build.py).  The RPD sources stay non-fused (explicit __f*_rn; host-build parity).
+FMAD_SOURCES = {"dist2mat_kernels.cu"}
+
+
 def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
@@ -37,7 +43,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         o = os.path.join(CSRC, s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        flags = list(NVCC_FLAGS)
+        if s in FMAD_SOURCES:  # see FMAD_SOURCES
+            flags[flags.index("-fmad=false")] = "-fmad=true"
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, p in procs:

@@ -501,6 +501,8 @@ static inline float4 bisector_host(const float4& A, const float4& B) {
 
 struct LeanTables {
   const float4* tet_planes = nullptr;  // 4 per tet of the resident mesh
+  const int4* tet_fid = nullptr;       // f_ids / f_adjs per tet (slim records)
+  const int4* tet_fadj = nullptr;
   const float4* site4 = nullptr;
   int n_tet = 0, n_site = 0, tet_id_base = 0;
 };
@@ -511,14 +513,20 @@ static LeanTables lean_tables(mb_ctx* ctx) {
   if (!ctx->h_tet_planes_valid) {
     ctx->h_tet_planes.resize((size_t)M.n_tet * 4);
     if (M.n_tet > 0) {
+      ctx->h_tet_fid.resize((size_t)M.n_tet);
+      ctx->h_tet_fadj.resize((size_t)M.n_tet);
       MB_CUDA(cudaMemcpy2DAsync(ctx->h_tet_planes.data(), 4 * sizeof(float4), M.tet_geo.p, 8 * sizeof(float4),
                                 4 * sizeof(float4), (size_t)M.n_tet, cudaMemcpyDeviceToHost, ctx->stream));
+      MB_CUDA(cudaMemcpyAsync(ctx->h_tet_fid.data(), M.tet_fid.p, sizeof(int4) * (size_t)M.n_tet, cudaMemcpyDeviceToHost, ctx->stream));
+      MB_CUDA(cudaMemcpyAsync(ctx->h_tet_fadj.data(), M.tet_fadj.p, sizeof(int4) * (size_t)M.n_tet, cudaMemcpyDeviceToHost, ctx->stream));
       MB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     ctx->h_tet_planes_valid = true;
   }
   LeanTables T;
   T.tet_planes = ctx->h_tet_planes.data();
+  T.tet_fid = ctx->h_tet_fid.data();
+  T.tet_fadj = ctx->h_tet_fadj.data();
   T.site4 = ctx->h_site4.data();
   T.n_tet = M.n_tet;
   T.n_site = (int)ctx->h_site4.size();
@@ -533,7 +541,8 @@ static bool expand_record(const uint32_t* w, unsigned char* dst, int id, const L
   const int tet = (int)w[0], site = (int)w[1];
   const int nb_v = w[2] & 0xff, nb_p = (w[2] >> 8) & 0xff, nb_e = (w[2] >> 16) & 0xff;
   const bool lean = (w[2] & MB_LEAN_FLAG) != 0;
-  const int status = (int)((w[2] >> 24) & 0x3f);  // bit 30 = flagged class, bit 31 = lean format
+  const bool slim = lean && (w[2] & MB_SLIM_FLAG) != 0;
+  const int status = (int)((w[2] >> 24) & 0xf);  // bit 29 = slim format, bit 30 = flagged class, bit 31 = lean format
   int32_t* di = reinterpret_cast<int32_t*>(dst);
   di[0] = status;
   di[1] = id;        // thread_id: debug-only in the reference; the cell index here
@@ -550,19 +559,40 @@ static bool expand_record(const uint32_t* w, unsigned char* dst, int id, const L
   const uint32_t* pl = p;
   if (!lean) p += 4 * nb_p;
   const uint32_t* meta = p;
-  p += 3 * nb_p;
+  p += slim ? (nb_p - 4) : 3 * nb_p;
   if (lean) {
     if (!T) return false;
     const int tl = tet - T->tet_id_base;
     if (tl < 0 || tl >= T->n_tet || site < 0 || site >= T->n_site) return false;
   }
   for (int i = 0; i < nb_p; i++) {
+    uint32_t m3[3];  // (id2.x, id2.y, h) of plane i
+    if (slim) {
+      // tet faces: (f_id, -1, (uchar) f_adj); bisectors: (min, max) of (seed, neighbour), h = 1 -- what K3 stored
+      if (i < 4) {
+        const int4 fi = T->tet_fid[tet - T->tet_id_base], fa = T->tet_fadj[tet - T->tet_id_base];
+        const int id = i == 0 ? fi.x : (i == 1 ? fi.y : (i == 2 ? fi.z : fi.w));
+        const int ad = i == 0 ? fa.x : (i == 1 ? fa.y : (i == 2 ? fa.z : fa.w));
+        const float h = (float)(unsigned)(unsigned char)ad;
+        m3[0] = (uint32_t)id;
+        m3[1] = (uint32_t)-1;
+        memcpy(&m3[2], &h, 4);
+      } else {
+        const int nb = (int)meta[i - 4];
+        const float h = 1.f;
+        m3[0] = (uint32_t)(site < nb ? site : nb);
+        m3[1] = (uint32_t)(site < nb ? nb : site);
+        memcpy(&m3[2], &h, 4);
+      }
+    } else {
+      memcpy(m3, meta + 3 * i, 12);
+    }
     if (lean) {
       float4 eq;
       if (i < 4) {
         eq = T->tet_planes[(size_t)(tet - T->tet_id_base) * 4 + i];
       } else {
-        const int a = (int)meta[3 * i], b = (int)meta[3 * i + 1];
+        const int a = (int)m3[0], b = (int)m3[1];
         const int nb = (a == site) ? b : a;  // id2 = (min, max) of (seed, neighbour)
         if (nb < 0 || nb >= T->n_site) return false;
         eq = bisector_host(T->site4[site], T->site4[nb]);
@@ -571,8 +601,8 @@ static bool expand_record(const uint32_t* w, unsigned char* dst, int id, const L
     } else {
       memcpy(dst + 416 + 32 * i, pl + 4 * i, 16);
     }
-    memcpy(dst + 416 + 32 * i + 16, meta + 3 * i + 2, 4);  // h
-    memcpy(dst + 2464 + 8 * i, meta + 3 * i, 8);            // id2
+    memcpy(dst + 416 + 32 * i + 16, &m3[2], 4);  // h
+    memcpy(dst + 2464 + 8 * i, m3, 8);            // id2
   }
   memcpy(dst + 2976, p, 3 * (size_t)nb_e);
   const float m1 = -1.f;

@@ -32,7 +32,7 @@ __device__ __forceinline__ float clampf(float f, float a, float b) {
 }
 // lerp(a,b,t) = b + t*(a-b) (cuda_helper_math.h:911-913)
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return b + t * (a - b); }
-__device__ __forceinline__ float sq(float x) { return x * x; }  // powf(x, 2.f)
+__device__ __forceinline__ float sq(float x) { return powf(x, 2.f); }  // literally, like dist2mat.cu:96,100,...
 
 // dist2mat.cu:5-8
 __device__ __forceinline__ float d_sphere(f3 p, float4 sp) {

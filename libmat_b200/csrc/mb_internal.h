@@ -153,7 +153,8 @@ struct RpdCounters {
   unsigned long long work_cursor2; // [20] second pass work distribution
   unsigned long long reserved[3];  // [21] flagged pairs, [22] flagged valid cells (static-filter class), [23] free
 };
-#define MB_LEAN_FLAG 0x80000000u  // bit 31 of a record's word 2: lean transport format
+#define MB_LEAN_FLAG 0x80000000u  // bit 31 of a record's word 2: lean transport format (no plane equations)
+#define MB_SLIM_FLAG 0x20000000u  // bit 29 (with bit 31): slim transport format (plane ids reduced to the neighbour id)
 #define CNT_OVF_TETS 16
 #define CNT_WORK_CURSOR 17
 
@@ -188,7 +189,7 @@ struct mb_rpd_result {
   const uint32_t* host_blob = nullptr;
   const long long* host_off = nullptr;
   int n_spans = 1;
-  bool lean = false;       // records travel without plane equations (mb_rpd_opts.lean_records)
+  int lean = 0;            // transport format of a streamed run: 0 full, 1 lean, 2 slim (mb_rpd_opts.lean_records)
   bool sink_owned = true;  // host_blob points into the context's own pinned buffer (else caller memory)
   // emission (K4)
   bool emitted = false;
@@ -237,6 +238,7 @@ struct mb_ctx {
   unsigned long long publish_seq = 0;
   std::vector<float4> h_site4;      // host copy of the sites (lean records: bisectors are recomputed on expansion)
   std::vector<float4> h_tet_planes; // host copy of the 4 face planes per tet, fetched on first use
+  std::vector<int4> h_tet_fid, h_tet_fadj;  // host copies of f_ids / f_adjs (slim records: tet-face plane ids)
   bool h_tet_planes_valid = false;
   double pairs_per_tet_hint = 0.0;  // grid mode: 1.5 x the largest pairs-per-tet seen (speculative span launches)
   int clip_variant = 0;             // MB_CLIP_VARIANT=1 (A/B tests): grid-kNN first pass with the state-machine kernel k_clip

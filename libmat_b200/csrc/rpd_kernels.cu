@@ -285,16 +285,19 @@ __global__ void __launch_bounds__(256) k_cand_given(const float4* __restrict__ v
 #define PACK_MAX_CELLS ((1ull << (64 - PACK_SHIFT)) - 1ull)
 // pair_words = record words | nb_p << 16 (0 = no record).  LEAN: the transport format without the 4 * nb_p
 // plane-equation words (recomputable from the ids: tet face planes, power bisectors)
-template <bool LEAN>
+// SLIM (LEAN == 2): additionally the 3 id words per plane shrink to ONE word per bisector (the neighbour site id;
+// seed, tet-face ids and adjacency counts are functions of the header): words - 7 nb_p + (nb_p - 4)
+template <int LEAN>
 struct PackWords {
   __host__ __device__ unsigned long long operator()(int pw) const {
     const int words = pw & 0xffff;
-    const int out = LEAN ? words - 4 * ((pw >> 16) & 0xff) : words;
+    const int nb_p = (pw >> 16) & 0xff;
+    const int out = words == 0 ? 0 : (LEAN == 2 ? words - 6 * nb_p - 4 : (LEAN == 1 ? words - 4 * nb_p : words));
     return (unsigned long long)out | ((unsigned long long)(words > 0) << PACK_SHIFT);
   }
 };
 
-template <bool LEAN>
+template <int LEAN>
 __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* __restrict__ pair_blob,
                          const int* __restrict__ pair_words, const unsigned long long* __restrict__ packed_off,
                          long long n_pairs, uint32_t* __restrict__ blob, long long* __restrict__ cell_off,
@@ -309,7 +312,17 @@ __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* 
   const unsigned long long pk = packed_off[g];
   const long long dst = (long long)(pk & PACK_MASK);
   const uint32_t* src = scratch + pair_blob[g];
-  if (LEAN) {
+  if (LEAN == 2) {
+    // [4 header | nb_v vertices] [plane equations: dropped] [ids: one neighbour id per bisector] [edges]
+    const int nb_p = (pw >> 16) & 0xff;
+    const int head = 4 + (int)(src[2] & 0xffu);
+    const uint32_t seed = src[1];
+    for (int i = lane; i < head; i += 8) blob[dst + i] = (i == 2) ? (src[2] | MB_LEAN_FLAG | MB_SLIM_FLAG) : src[i];
+    const uint32_t* meta = src + head + 4 * nb_p;
+    for (int i = 4 + lane; i < nb_p; i += 8) blob[dst + head + i - 4] = (meta[3 * i] == seed) ? meta[3 * i + 1] : meta[3 * i];
+    const int e0 = head + 7 * nb_p, shift = 6 * nb_p + 4;
+    for (int i = e0 + lane; i < words; i += 8) blob[dst + i - shift] = src[i];
+  } else if (LEAN == 1) {
     // [4 header | nb_v vertices] [4*nb_p plane equations: dropped] [3*nb_p ids | edges]
     const int nb_p = (pw >> 16) & 0xff;
     const int head = 4 + (int)(src[2] & 0xffu);
@@ -658,7 +671,7 @@ struct SpanStats {
 // to res->evs.  Returns with the ordering kernels enqueued (not synchronised).
 static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res, const TetSpan& sp,
                               const GridDev* grid, DevBuf<uint32_t>& blob, DevBuf<long long>& cell_off,
-                              long long base_bytes, bool lean, bool force_sync = false) {
+                              long long base_bytes, int lean, bool force_sync = false) {
   TetMeshDev& M = ctx->mesh;
   SitesDev& S = ctx->sites;
   cudaStream_t s = ctx->stream;
@@ -793,13 +806,18 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
       unsigned long long* outp = reinterpret_cast<unsigned long long*>(word_off.p);
       size_t tmp = 0;
       ctx->n_launches += 2;
-      if (lean) {
-        cub::TransformInputIterator<unsigned long long, PackWords<true>, const int*> in(ctx->pair_words.p, PackWords<true>());
+      if (lean == 2) {
+        cub::TransformInputIterator<unsigned long long, PackWords<2>, const int*> in(ctx->pair_words.p, PackWords<2>());
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, outp, n_pairs + 1, s));
+        ctx->cub_tmp.reserve(tmp);
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, outp, n_pairs + 1, s));
+      } else if (lean == 1) {
+        cub::TransformInputIterator<unsigned long long, PackWords<1>, const int*> in(ctx->pair_words.p, PackWords<1>());
         MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, outp, n_pairs + 1, s));
         ctx->cub_tmp.reserve(tmp);
         MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, outp, n_pairs + 1, s));
       } else {
-        cub::TransformInputIterator<unsigned long long, PackWords<false>, const int*> in(ctx->pair_words.p, PackWords<false>());
+        cub::TransformInputIterator<unsigned long long, PackWords<0>, const int*> in(ctx->pair_words.p, PackWords<0>());
         MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, outp, n_pairs + 1, s));
         ctx->cub_tmp.reserve(tmp);
         MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, outp, n_pairs + 1, s));
@@ -875,12 +893,16 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     blob.reserve((size_t)total_words + 4);
     if (total_words > 0) {
       ctx->n_launches++;
-      if (lean)
-        k_gather<true><<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
+      if (lean == 2)
+        k_gather<2><<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
+            ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, reinterpret_cast<const unsigned long long*>(word_off.p),
+            n_pairs, blob.p, cell_off.p, total_words, st.n_cells, base_bytes);
+      else if (lean == 1)
+        k_gather<1><<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
             ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, reinterpret_cast<const unsigned long long*>(word_off.p),
             n_pairs, blob.p, cell_off.p, total_words, st.n_cells, base_bytes);
       else
-        k_gather<false><<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
+        k_gather<0><<<(unsigned)((n_pairs * 8 + 255) / 256), 256, 0, s>>>(
             ctx->scratch.p, ctx->pair_blob.p, ctx->pair_words.p, reinterpret_cast<const unsigned long long*>(word_off.p),
             n_pairs, blob.p, cell_off.p, total_words, st.n_cells, base_bytes);
       MB_CUDA(cudaGetLastError());
@@ -927,7 +949,7 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   MB_REQUIRE(!(opts && opts->lean_records), MB_ERR_ARG,
              "lean_records is a transport format of the streamed runs (mb_rpd_run_to_host / mb_rpd_run_to_sink)");
   const SpanStats st = rpd_run_span(ctx, opts, res, sp, (grid_cands && t_count > 0) ? &G : nullptr, res->blob,
-                                    res->cell_off, 0, false);
+                                    res->cell_off, 0, 0);
   // fold K1 into the candidate stage: replace the span's start event by e0
   ctx->ev_pool.push_back(res->evs[0]);
   res->evs[0] = e0;
@@ -952,7 +974,8 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
 void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res, void* dst_blob,
                      size_t dst_cap_bytes, long long* dst_off, size_t dst_cap_cells) {
   const bool own = dst_blob == nullptr;
-  const bool lean = opts && opts->lean_records;
+  const int lean = opts ? opts->lean_records : 0;
+  MB_REQUIRE(lean >= 0 && lean <= 2, MB_ERR_ARG, "lean_records must be 0 (full), 1 (lean) or 2 (slim)");
   res->lean = lean;
   int t_first, t_count;
   run_prologue(ctx, opts, res, t_first, t_count);
@@ -966,7 +989,19 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     }
   }
   cudaStream_t cs = ctx->copy_stream;
-  if (n_chunks <= 0) n_chunks = std::max(1, std::min(32, (t_count + 32767) / 32768));
+  if (n_chunks <= 0) {
+    // automatic span count.  Host destinations: the PCIe copy is the long pole, so spans are short (~32k tets) and
+    // the first bytes leave early.  Device destinations (this GPU or a peer over NVLink): the copy is ~10x faster
+    // than the kernels, so only the last span's copy is exposed and fewer, longer spans waste less on kernel tails
+    // and launch gaps (~0.1-0.2 ms per span).
+    bool dev_dst = false;
+    if (dst_blob) {
+      cudaPointerAttributes pa;
+      dev_dst = cudaPointerGetAttributes(&pa, dst_blob) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+      (void)cudaGetLastError();
+    }
+    n_chunks = dev_dst ? std::max(1, std::min(8, (t_count + 98303) / 98304)) : std::max(1, std::min(32, (t_count + 32767) / 32768));
+  }
   n_chunks = std::max(1, std::min(n_chunks, std::max(1, t_count)));
   const bool grid_cands = !ctx->sites.given || (opts && opts->grid_candidates);
   GridDev G;

@@ -161,6 +161,19 @@ def make_ball_mesh(n: int, seed: int = RAN_SEED, jitter: float = 0.2) -> TetMesh
     return TetMesh(verts, idx.astype(np.int32), v_adjs, e_adj6, f_adjs, f_ids, n_sf)
 
 
+def fake_feature_edges(mesh: TetMesh, every: int = 7) -> np.ndarray:
+    """A synthetic TetMesh::tet_es2fe_map (reference input_types.h; consumed at rpd_update.cxx:209-259): rows
+    (tet, lf_min, lf_max, fe_type, fe_id, fe_line_id) for the tet edge between the two local faces lf_min < lf_max of
+    every `every`-th tet that has two boundary faces; fe_type alternates SE = 1 / CE = 2, five edges per line."""
+    rows = []
+    nb = (mesh.f_adjs == 1)
+    for t in np.flatnonzero(nb.sum(axis=1) >= 2)[::every]:
+        lf = np.flatnonzero(nb[t])[:2]
+        k = len(rows)
+        rows.append((int(t), int(lf[0]), int(lf[1]), 1 + k % 2, k, k // 5))
+    return np.array(rows, dtype=np.int32).reshape(-1, 6)
+
+
 def make_box_mesh(n: int, L: float = 1000.0) -> TetMesh:
     """DEGENERATE test input: the n^3 Kuhn cube mesh on [0,L]^3 without jitter or ball map.  With L / n exactly
     representable the vertices sit on a lattice; together with make_lattice_spheres the power bisectors pass exactly

@@ -331,6 +331,47 @@ def emit(recs, max_surf_fid):
     return out
 
 
+def feature_edges(recs, fe_map):
+    """TEST INFRASTRUCTURE.  Restates the feature-edge part of get_all_voro_info (rpd_update.cxx:209-259) per cell:
+    an ACTIVE edge whose two planes are tet faces and whose (tet, lf_min, lf_max) is in TetMesh::tet_es2fe_map is a
+    covered sharp (SE = 1) or concave (CE = 2) edge; its end vertices are the two vertices lying on both planes
+    (convert_e_lfids_to_lvids :44-71); every end vertex that also lies on a half-plane records the sharp line's end
+    position under (cell, lvid, neighbour of its FIRST half-plane, fe_line_id) (:237-252).
+    Returns rows (site, kind, cell, lv1, lv2, fe_line_id, fe_id), end_rows (site, cell, lvid, neigh, line), end_pos."""
+    fe = {(int(r[0]), int(r[1]), int(r[2])): (int(r[3]), int(r[4]), int(r[5])) for r in np.asarray(fe_map).reshape(-1, 6)}
+    _, ae, _ = reload_active(recs, "oracle")
+    pos = vertex_coordinates(recs)
+    rows, end = set(), {}
+    tets_with_fe = {k[0] for k in fe}
+    for c in np.flatnonzero(np.isin(recs["tet_id"], list(tets_with_fe))):
+        r = recs[c]
+        site, tet = int(r["voro_id"]), int(r["tet_id"])
+        for e in range(int(r["nb_e"])):
+            if not ae[c, e]:
+                continue
+            a, b = int(r["edge"][e][0]), int(r["edge"][e][1])
+            if r["id2"][a][1] != -1 or r["id2"][b][1] != -1:
+                continue
+            lo, hi = min(a, b), max(a, b)
+            if (tet, lo, hi) not in fe:
+                continue
+            kind, fe_id, line = fe[(tet, lo, hi)]
+            lvs = sorted(v for v in range(int(r["nb_v"])) if lo in r["ver"][v][:3] and hi in r["ver"][v][:3])
+            assert len(lvs) == 2
+            rows.add((site, kind, int(c), lvs[0], lvs[1], line, fe_id))
+            for lv in lvs:
+                for i in range(3):
+                    hp = r["id2"][int(r["ver"][lv][i])]
+                    if hp[1] == -1:
+                        continue
+                    neigh = int(hp[1]) if int(hp[0]) == site else int(hp[0])
+                    end[(site, int(c), lv, neigh, line)] = pos[c, lv, :3].copy()
+                    break
+    keys = sorted(end)
+    return {"rows": np.array(sorted(rows), np.int32).reshape(-1, 7), "end_rows": np.array(keys, np.int32).reshape(-1, 5),
+            "end_pos": np.array([end[k] for k in keys], np.float32).reshape(-1, 3)}
+
+
 def topology(em, cell_site, cell_euler):
     """TEST INFRASTRUCTURE.  Restates the remainder of update_power_cells per power cell, literally with
     dict / set / BFS like the reference:
@@ -423,6 +464,39 @@ def topology(em, cell_site, cell_euler):
                 for c in comp:
                     edge_cc[c2e[c]] = m
     return {"cell_cc": cell_cc, "facet_cc": facet_cc, "edge_cc": edge_cc, "site_stats": site_stats, "pairs": pairs}
+
+
+_UPDATE_WIDTH = {"facets": (3, 0), "tfids": (3, 0), "surf": (3, 3), "vertices": (7, 3), "edges": (6, 0), "e2cells": (4, 0),
+                 "neighbours": (3, 0), "cc": (3, 0), "facet_cc": (4, 0), "edge_cc": (5, 0), "fe": (7, 0), "fe_end": (5, 3)}
+
+
+def ref_update(recs, n_site, max_surf_fid, fe_map=None):
+    """TEST INFRASTRUCTURE.  The reference's own update_power_cells (src/rpd3d_base/rpd_update.cxx:568-639 ->
+    get_all_voro_info :80-340, update_pc_cc_info, update_pc_facet_cc_info, update_pc_edge_cc_info) compiled in place
+    (oracle/_ref/libref_update.so) on success records with id = index.  fe_map: int rows (tet, lf_min, lf_max, fe_type,
+    fe_id, fe_line_id) = TetMesh::tet_es2fe_map.  Returns a dict of the flattened PowerCell containers (row layouts in
+    oracle/ref_shim_update.cpp) + "cell_euler"; integer rows as int arrays [n, width], positions as float64 [n, 3]."""
+    l = ref("update")
+    assert l is not None, "oracle/_ref/libref_update.so not built"
+    l.ref_update_get.restype = C.c_long
+    recs = np.ascontiguousarray(recs)
+    fe = np.zeros((0, 6), np.int32) if fe_map is None else np.ascontiguousarray(fe_map, dtype=np.int32).reshape(-1, 6)
+    rc = l.ref_update_run(_p(recs), C.c_long(len(recs)), C.c_int(int(n_site)), C.c_int(int(max_surf_fid)), _p(fe), C.c_long(len(fe)))
+    assert rc == 0
+    out = {}
+    for what, (w, vw) in _UPDATE_WIDTH.items():
+        n = l.ref_update_get(what.encode(), None, None, C.c_long(0))
+        rows = np.zeros((n, w), np.int32)
+        vals = np.zeros((n, 3), np.float64) if vw else None
+        if n:
+            l.ref_update_get(what.encode(), _p(rows), _p(vals) if vw else None, C.c_long(n))
+        out[what] = rows
+        if vw:
+            out[what + "_pos"] = vals
+    eu = np.zeros(len(recs), np.float32)
+    l.ref_update_cell_euler(_p(eu))
+    out["cell_euler"] = eu
+    return out
 
 
 def ref_bgeo(recs, max_sf_fid, is_boundary_only, work_dir, name="t"):

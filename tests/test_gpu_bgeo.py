@@ -8,7 +8,7 @@ from libmat_b200 import capi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("lean", [False, True])
+@pytest.mark.parametrize("lean", [0, 1, 2])
 def test_bgeo_from_streamed_run(ctx, O, cfg1_rt, tmp_path, lean):
     mesh, sites, knn, k = cfg1_rt
     ctx.set_mesh(mesh)

@@ -164,16 +164,16 @@ def test_cfg4_full_run_sampled_against_reference(ctx, O, synth):
 
 def test_dist2mat_10M_sampled_against_reference(ctx, O, synth):
     """BASELINE configs[2] at full size: 10 000 000 samples, 20 000 spheres, 60 000 slabs, 30 000 cones through
-    mb_dist2mat_upload / run / fetch; every 25th sample is recomputed with the reference's own distance functions and
-    tie rule (ref_d2m_run_host).  Distances within 1e-6 relative, argmin ids equal apart from flagged ties."""
+    mb_dist2mat_upload / run / fetch; every 25th sample is recomputed by the reference's own CUDA kernel (bit-identical
+    on >= 99.9 %) and by the plain-C oracle (within 1e-6 wherever the reference's host and device arithmetic agree);
+    argmin ids equal apart from flagged ties."""
     n = int(os.environ.get("MB_TEST_D2M_SAMPLES", "10000000"))
     d = synth.make_dist2mat(n)
     r, cid, tie = ctx.compute_closest_dist2mat(d.spheres, d.samples, d.offset, d.count, d.prims)
     assert len(r) == n and np.isfinite(r).all() and (cid >= 0).all() and (cid < d.count.astype(np.int64)).all()
     pick = np.arange(0, n, 25)
     sub = synth.Dist2MatInput(d.spheres, d.samples[pick], d.offset[pick], d.count[pick], d.prims, d.n_cones, d.n_slabs)
-    ro, co, _ = O.dist2mat(sub, "ref" if O.ref("d2m") is not None else "oracle")
-    rel = np.abs(r[pick] - ro) / np.maximum(np.abs(ro), 1e-3)
-    assert rel.max() <= 1e-6, rel.max()
-    assert (r[pick].view(np.uint32) == ro.view(np.uint32)).mean() > 0.99
-    assert not ((cid[pick] != co) & (tie[pick] == 0)).any()
+    from test_gpu_dist2mat import check_against_builds
+    # the reference's CUDA kernel is run on the strided sample itself (its lists point into the full prims array)
+    info = check_against_builds(O, sub, r[pick], cid[pick], tie[pick])
+    print("dist2mat 10M, every 25th sample:", info)

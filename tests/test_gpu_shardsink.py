@@ -47,7 +47,7 @@ def _worker(rank, world, port, kind, out_dir):
             np.savez(os.path.join(out_dir, f"got_{kind}_{n_chunks}.npz"), blob=blob, offs=offs)
         dist.barrier()
     # lean transport format through the sink; rank 0 (which holds the whole mesh + sites) expands all shards
-    res, directory = sink.run(n_chunks=2, lean=True)
+    res, directory = sink.run(n_chunks=2, lean=2)  # slim transport format
     res.free()
     if rank == 0:
         blob, offs = sink.read_host(directory)

@@ -114,11 +114,13 @@ def test_shard_upload_with_tet_id_base(ctx, cfg1_rt):
     assert pt.min() >= first and pt.max() < first + count
 
 
+@pytest.mark.parametrize("fmt,ratio", [(1, 0.75), (2, 0.45)])
 @pytest.mark.parametrize("mode", ["grid", "given"])
-def test_lean_records_expand_to_the_full_records(ctx, cfg1, cfg1_rt, mode):
-    """lean transport format (records without plane equations): the host expansion recomputes tet-face planes and
-    power bisectors from the ids and must reproduce the full-format records byte for byte -- plane equations
-    included -- in both modes, through fetch_records and through expand_compact"""
+def test_lean_records_expand_to_the_full_records(ctx, cfg1, cfg1_rt, mode, fmt, ratio):
+    """lean (1: records without plane equations) and slim (2: also one neighbour id per bisector instead of three id
+    words per plane) transport formats: the host expansion recomputes tet-face planes, power bisectors and plane ids
+    and must reproduce the full-format records byte for byte -- plane equations included -- in both modes, through
+    fetch_records and through expand_compact"""
     mesh, sites, knn, k = cfg1_rt if mode == "grid" else cfg1
     ctx.set_mesh(mesh)
     ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, None if mode == "grid" else knn, 0 if mode == "grid" else k)
@@ -126,9 +128,9 @@ def test_lean_records_expand_to_the_full_records(ctx, cfg1, cfg1_rt, mode):
     want = full.records()
     full_bytes = full.compact_bytes
     full.free()
-    res = ctx.run_to_host(n_chunks=3, lean=True)
+    res = ctx.run_to_host(n_chunks=3, lean=fmt)
     assert res.n_cells == len(want)
-    assert res.compact_bytes < 0.75 * full_bytes
+    assert res.compact_bytes < ratio * full_bytes
     got = res.records()
     blob, offs = res.host_compact()
     got2 = ctx.expand_compact(blob, offs)
