@@ -263,6 +263,24 @@ int mb_rpd_fetch_emit(mb_rpd_result* res, int* facet_cell, int* facet_key, unsig
                       int* vert_surf_fid, int* edge_cell, int* edge_key2, int* edge_lvid2,
                       float* cell_euler);
 
+/* The rest of get_all_voro_info's per-cell emission:
+ *   mb_rpd_fetch_facet_centroids  float[3 * n_facets]: for a tet-face facet with id <= max_surf_fid the pc_face centroid
+ *       of cell_to_surfv2fid (get_cell_v2surffid, rpd_update.cxx:20-42, 129-133: mean of the face loop's vertices in
+ *       the loop order of reload_pc_explicit, float); zero for every other facet.  Needs mb_rpd_emit.
+ *   mb_set_feature_edges  TetMesh::tet_es2fe_map for the resident mesh: n rows (tet, lf_min, lf_max, fe_type, fe_id,
+ *       fe_line_id), lf = local face 0..3, fe_type 1 = sharp (SE) / 2 = concave (CE) (input_types.h:13-17).  Reset by
+ *       mb_set_tetmesh; n = 0 clears.  Subsequent mb_rpd_emit calls then also produce the covered feature edges
+ *       (rpd_update.cxx:209-259):
+ *   mb_rpd_feature_edge_count / mb_rpd_fetch_feature_edges
+ *       hit6   int[6 * n_hits]  (cell, fe_type, lv1 < lv2, fe_line_id, fe_id)   = se_covered_lvids / ce_covered_lvids
+ *       end4   int[8 * n_hits]  two rows (cell, lvid, neigh, fe_line_id) per hit: the end vertex's FIRST half-plane
+ *                               neighbour (se_line_endpos key), neigh = -1 when the vertex lies on no half-plane
+ *       end_pos3 float[6 * n_hits]  the end vertices' positions (zero where neigh = -1) */
+int mb_rpd_fetch_facet_centroids(mb_rpd_result* res, float* centroid3);
+int mb_set_feature_edges(mb_ctx* ctx, const int* rows6, long n);
+int mb_rpd_feature_edge_count(const mb_rpd_result* res, long* n_hits);
+int mb_rpd_fetch_feature_edges(mb_rpd_result* res, int* hit6, int* end4, float* end_pos3);
+
 /* K6 power-cell topology summary = the rest of update_power_cells after get_all_voro_info
  * (rpd_update.cxx:303-316 cell_neighbors, :497-503 cc_cells, :439-470 facet_cc_cells) and the sums
  * check_cc_and_euler consumes (fix_topo.cxx:81-144, 150-235, 310-380); needs mb_rpd_emit first.
@@ -303,7 +321,12 @@ int mb_bgeo_write_records(const void* records, long n_cells, int max_sf_fid, int
  * (-1,-1,s) sphere, (-1,a,b) cone, (a,b,c) slab (dist2mat.cu:233-246).
  * result float[n_samples], closest_id int[n_samples] = index within the sample's list
  * (empty list -> 1e16f, -1).  tie_flag (nullable) unsigned char[n_samples]: 1 where the two best
- * distances differ by < 1e-6 relative (the flagged-tie class). */
+ * distances differ by < 1e-6 relative to max(|distance|, |sample coordinates|) (the flagged-tie class: closer than
+ * the float resolution of |p - c| - r, where the FMA-contracted device build and an IEEE evaluation of the
+ * reference's expressions can rank them differently).
+ * Arithmetic: the reference's expressions evaluated like its DEVICE build (nvcc FMA contraction, clamp(t,0,1) as a
+ * saturate: NaN -> 0): bit-identical to the reference's own CUDA kernel on 99.97 % of 200 000 samples, the rest
+ * within 1e-6 (tests/test_gpu_reference_build.py). */
 int mb_dist2mat(mb_ctx* ctx, const float* spheres, int n_sph, const float* samples, int n_samples,
                 const unsigned* offset, const unsigned* count, const int* prims, long n_prims,
                 float* result, int* closest_id, unsigned char* tie_flag);

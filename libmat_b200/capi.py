@@ -17,7 +17,8 @@ SYMBOLS = [
     "mb_sink_close", "mb_host_register", "mb_host_unregister", "mb_copy_to_host", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_clip_passes", "mb_rpd_flagged", "mb_rpd_fetch_flags", "mb_debug_set_pair_hint", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
     "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_cell_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
-    "mb_rpd_fetch_emit", "mb_rpd_write_bgeo", "mb_bgeo_write_records", "mb_rpd_topology", "mb_rpd_fetch_topology", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
+    "mb_rpd_fetch_emit", "mb_rpd_fetch_facet_centroids", "mb_set_feature_edges", "mb_rpd_feature_edge_count",
+    "mb_rpd_fetch_feature_edges", "mb_rpd_write_bgeo", "mb_bgeo_write_records", "mb_rpd_topology", "mb_rpd_fetch_topology", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
 ]
 
 # static-filter bounds (reference src/predicate_generator/main.cpp output; include/libmat_b200.h)
@@ -116,6 +117,10 @@ def load() -> C.CDLL:
     lib.mb_rpd_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_long), C.POINTER(vp), C.POINTER(C.c_long)]
     lib.mb_rpd_emit.argtypes = [vp, C.c_int, C.POINTER(EmitCounts)]
     lib.mb_rpd_fetch_emit.argtypes = [vp] + [vp] * 12
+    lib.mb_rpd_fetch_facet_centroids.argtypes = [vp, vp]
+    lib.mb_set_feature_edges.argtypes = [vp, vp, C.c_long]
+    lib.mb_rpd_feature_edge_count.argtypes = [vp, C.POINTER(C.c_long)]
+    lib.mb_rpd_fetch_feature_edges.argtypes = [vp, vp, vp, vp]
     lib.mb_rpd_write_bgeo.argtypes = [vp, vp, vp, C.c_long, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     lib.mb_bgeo_write_records.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     lib.mb_rpd_topology.argtypes = [vp, C.POINTER(TopoCounts)]

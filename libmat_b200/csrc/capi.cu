@@ -86,6 +86,7 @@ void mb_destroy(mb_ctx* ctx) {
   ctx->spare_blob.release();
   ctx->spare_cell_off.release();
   TetMeshDev& M = ctx->mesh;
+  M.fe_table.release(); M.fe_rows.release();
   M.vert4.release(); M.tet_idx.release(); M.tet_fadj.release(); M.tet_fid.release(); M.tet_e6.release(); M.tet_geo.release(); M.tet_vadj.release(); M.tet_sel.release();
   SitesDev& S = ctx->sites;
   S.site4.release(); S.flags.release(); S.nbr.release(); S.knn_staging.release(); S.soa_staging.release();
@@ -348,6 +349,7 @@ void mb_rpd_free(mb_rpd_result* res) {
   }
   res->blob.release(); res->cell_off.release(); res->site_vol.release(); res->site_bary.release(); res->cell_vol.release();
   res->f_cell.release(); res->f_key.release(); res->v_cell.release(); res->v_lvid.release();
+  res->f_centroid3.release(); res->fe_hit6.release(); res->fe_end4.release(); res->fe_end_pos3.release();
   res->v_key3.release(); res->v_surf.release(); res->e_cell.release(); res->e_key2.release();
   res->e_lvid2.release(); res->f_istet.release(); res->v_pos3.release(); res->c_euler.release();
   res->t_cell_cc.release(); res->t_facet_cc.release(); res->t_edge_cc.release(); res->t_site_n_cells.release(); res->t_site_n_cc.release();
@@ -738,6 +740,63 @@ int mb_rpd_fetch_emit(mb_rpd_result* res, int* facet_cell, int* facet_key, unsig
   FETCH(edge_key2, res->e_key2, 2 * c.n_edges, int);
   FETCH(edge_lvid2, res->e_lvid2, 2 * c.n_edges, int);
   FETCH(cell_euler, res->c_euler, res->n_cells, float);
+  MB_CUDA(cudaStreamSynchronize(s));
+  MB_CATCH
+}
+
+int mb_rpd_fetch_facet_centroids(mb_rpd_result* res, float* centroid3) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx && centroid3, MB_ERR_ARG, "null argument");
+  MB_REQUIRE(res->emitted, MB_ERR_STATE, "mb_rpd_emit must be called first");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  FETCH(centroid3, res->f_centroid3, 3 * res->emit_counts.n_facets, float);
+  MB_CUDA(cudaStreamSynchronize(s));
+  MB_CATCH
+}
+
+int mb_set_feature_edges(mb_ctx* ctx, const int* rows6, long n) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && n >= 0 && (n == 0 || rows6), MB_ERR_ARG, "bad arguments");
+  TetMeshDev& M = ctx->mesh;
+  MB_REQUIRE(M.n_tet > 0, MB_ERR_STATE, "mb_set_tetmesh first (it clears the feature-edge map)");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  M.n_fe = 0;
+  if (n == 0) return MB_OK;
+  std::vector<int> table((size_t)M.n_tet * 6, -1);
+  for (long i = 0; i < n; i++) {
+    const int t = rows6[6 * i], a = rows6[6 * i + 1], b = rows6[6 * i + 2];
+    MB_REQUIRE(t >= 0 && t < M.n_tet && a >= 0 && a < b && b < 4, MB_ERR_ARG,
+               "feature-edge rows are (tet, lf_min < lf_max in 0..3, fe_type, fe_id, fe_line_id)");
+    table[(size_t)t * 6 + (a == 0 ? b - 1 : (a == 1 ? b + 1 : 5))] = (int)i;
+  }
+  M.fe_table.reserve(table.size());
+  M.fe_rows.reserve(6 * (size_t)n);
+  MB_CUDA(cudaMemcpyAsync(M.fe_table.p, table.data(), sizeof(int) * table.size(), cudaMemcpyHostToDevice, ctx->stream));
+  MB_CUDA(cudaMemcpyAsync(M.fe_rows.p, rows6, sizeof(int) * 6 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  M.n_fe = n;
+  MB_CATCH
+}
+
+int mb_rpd_feature_edge_count(const mb_rpd_result* res, long* n_hits) {
+  if (!res || !n_hits) return MB_ERR_ARG;
+  if (!res->emitted) return MB_ERR_STATE;
+  *n_hits = res->n_fe_hits;
+  return MB_OK;
+}
+
+int mb_rpd_fetch_feature_edges(mb_rpd_result* res, int* hit6, int* end4, float* end_pos3) {
+  mb_ctx* ctx = res ? res->ctx : nullptr;
+  MB_TRY(ctx)
+  MB_REQUIRE(res && ctx, MB_ERR_ARG, "null result");
+  MB_REQUIRE(res->emitted, MB_ERR_STATE, "mb_rpd_emit must be called first");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  FETCH(hit6, res->fe_hit6, 6 * res->n_fe_hits, int);
+  FETCH(end4, res->fe_end4, 8 * res->n_fe_hits, int);
+  FETCH(end_pos3, res->fe_end_pos3, 6 * res->n_fe_hits, float);
   MB_CUDA(cudaStreamSynchronize(s));
   MB_CATCH
 }

@@ -226,6 +226,15 @@ __device__ __forceinline__ float funkey(unsigned k) {
   return __uint_as_float(u);
 }
 
+// The flagged-tie class: the two best distances of a sample differ by less than 1e-6 relative to the larger of the
+// distances and the sample's own coordinates.  A signed distance |p - c| - r is a cancelling difference of terms of
+// the coordinates' size, so two correct evaluations of it (FMA-contracted or not) differ by ~1 ulp OF THE COORDINATES,
+// however small the distance itself is; two candidates closer than that cannot be ranked.
+__device__ __forceinline__ unsigned char tie_flag(float best, float second, const float* __restrict__ p) {
+  const float scale = fmaxf(fmaxf(fabsf(best), fabsf(second)), fmaxf(fabsf(p[0]), fmaxf(fabsf(p[1]), fabsf(p[2]))));
+  return (second - best) <= 1e-6f * scale && second < 1e15f;
+}
+
 __global__ void __launch_bounds__(256) k_dist2mat(const float* __restrict__ samples,
                                                   const float4* __restrict__ spheres,
                                                   const int* __restrict__ prims,
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(256) k_dist2mat(const float* __restrict__ samp
     if (lane == 0) {
       result[smp] = red;
       closest_id[smp] = win_id;
-      if (tie) tie[smp] = (sec - red) <= 1e-6f * fmaxf(fabsf(red), fabsf(sec)) && sec < 1e15f;
+      if (tie) tie[smp] = tie_flag(red, sec, samples + 3 * (size_t)smp);
     }
   }
 }
@@ -327,7 +336,7 @@ __device__ __forceinline__ void d2m_sample_direct(int smp, int lane, const float
   if (lane == 0) {
     result[smp] = red;
     closest_id[smp] = win_id;
-    if (tie) tie[smp] = (sec - red) <= 1e-6f * fmaxf(fabsf(red), fabsf(sec)) && sec < 1e15f;
+    if (tie) tie[smp] = tie_flag(red, sec, samples + 3 * (size_t)smp);
   }
 }
 
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_dist2mat_q(const float* __restri
         }
         result[smp] = m;
         closest_id[smp] = id;
-        if (tie) tie[smp] = (sec - m) <= 1e-6f * fmaxf(fabsf(m), fabsf(sec)) && sec < 1e15f;
+        if (tie) tie[smp] = tie_flag(m, sec, samples + 3 * (size_t)smp);
       }
       __syncwarp();
       s0 = s1;

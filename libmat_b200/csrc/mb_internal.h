@@ -109,6 +109,9 @@ struct TetMeshDev {
   DevBuf<float4> tet_geo;  // per tet: 4 face planes + 4 vertex cofactor vectors (k_tet_geometry)  128 B / tet
   int range_first = 0, range_count = -1;
   int tet_id_base = 0;     // records carry tet id + base (a rank that uploaded only its shard of the tets)
+  DevBuf<int> fe_table;    // optional: 6 row indices per tet into fe_rows (-1 = none): TetMesh::tet_es2fe_map
+  DevBuf<int> fe_rows;     // (tet, lf_min, lf_max, fe_type, fe_id, fe_line_id) per feature edge (mb_set_feature_edges)
+  long n_fe = 0;
   DevBuf<int> tet_sel;     // optional ascending list of tet ids to process (mb_set_tet_subset)
   int n_sel = 0;
   const int* sel_ptr() const { return n_sel > 0 ? tet_sel.p : nullptr; }
@@ -196,7 +199,11 @@ struct mb_rpd_result {
   mb_emit_counts emit_counts = {0, 0, 0};
   DevBuf<int> f_cell, f_key, v_cell, v_lvid, v_key3, v_surf, e_cell, e_key2, e_lvid2;
   DevBuf<unsigned char> f_istet;
-  DevBuf<float> v_pos3, c_euler;
+  DevBuf<float> v_pos3, c_euler, f_centroid3;
+  // feature-edge hits of the emission (rpd_update.cxx:209-259), when mb_set_feature_edges supplied the map
+  long n_fe_hits = 0;
+  DevBuf<int> fe_hit6, fe_end4;
+  DevBuf<float> fe_end_pos3;
   // topology summary (K6)
   bool topo_done = false;
   long topo_pairs = 0;

@@ -103,6 +103,63 @@ __device__ __forceinline__ bool vertex_key(const CellView& c, int t, int max_sur
   return true;
 }
 
+// vertex coordinates, compute_vertex_coordinates voronoi_defs.cxx:33-49 (exact float operation order, perspective divide)
+__device__ __forceinline__ void vertex_pos(const CellView& c, int t, float out[3]) {
+  const uint32_t v = c.ver[t];
+  const float* P = reinterpret_cast<const float*>(c.plane);
+  const float* p1 = P + 4 * (v & 0xff);
+  const float* p2 = P + 4 * ((v >> 8) & 0xff);
+  const float* p3 = P + 4 * ((v >> 16) & 0xff);
+  const float rx = -det3_exact(p1[3], p1[1], p1[2], p2[3], p2[1], p2[2], p3[3], p3[1], p3[2]);
+  const float ry = -det3_exact(p1[0], p1[3], p1[2], p2[0], p2[3], p2[2], p3[0], p3[3], p3[2]);
+  const float rz = -det3_exact(p1[0], p1[1], p1[3], p2[0], p2[1], p2[3], p3[0], p3[1], p3[3]);
+  const float rw = det3_exact(p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+  out[0] = __fdiv_rn(rx, rw);
+  out[1] = __fdiv_rn(ry, rw);
+  out[2] = __fdiv_rn(rz, rw);
+}
+
+// Centroid of the face loop of an active plane = the pc_face centroid of get_cell_v2surffid (rpd_update.cxx:20-42):
+// the loop's vertices in the cyclic order of reload_pc_explicit's walk (voronoi_defs.cxx:141-182 -- start at the
+// first vertex referencing the plane, go on with the vertex whose previous plane is this one's next plane), summed
+// sequentially in float and divided by the count (cplus3 / cdivide3, common_cxx.h:119-127).
+__device__ void face_loop_centroid(const CellView& c, int plane, float out[3]) {
+  // entry of vertex t that is `plane` (0..2), or -1
+  auto slot = [&](int t) {
+    const uint32_t v = c.ver[t];
+    return (int)(v & 0xff) == plane ? 0 : ((int)((v >> 8) & 0xff) == plane ? 1 : ((int)((v >> 16) & 0xff) == plane ? 2 : -1));
+  };
+  int m = 0, first = -1;
+  for (int t = 0; t < c.nb_v; t++)
+    if (slot(t) >= 0) {
+      if (first < 0) first = t;
+      m++;
+    }
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  int i = first, n = 0;
+  while (n < m && i >= 0) {
+    float p[3];
+    vertex_pos(c, i, p);
+    sx = __fadd_rn(sx, p[0]);
+    sy = __fadd_rn(sy, p[1]);
+    sz = __fadd_rn(sz, p[2]);
+    n++;
+    const int want = (int)((c.ver[i] >> (8 * ((slot(i) + 1) % 3))) & 0xff);
+    int nxt = -1;
+    for (int j = 0; j < c.nb_v && nxt < 0; j++) {
+      const int sj = slot(j);
+      if (sj >= 0 && (int)((c.ver[j] >> (8 * ((sj + 2) % 3))) & 0xff) == want) nxt = j;
+    }
+    i = nxt;
+  }
+  out[0] = __fdiv_rn(sx, (float)m);
+  out[1] = __fdiv_rn(sy, (float)m);
+  out[2] = __fdiv_rn(sz, (float)m);
+}
+
+// slot of the tet edge between local faces a < b in the per-tet feature-edge table: (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
+__device__ __forceinline__ int fe_slot(int a, int b) { return a == 0 ? b - 1 : (a == 1 ? b + 1 : 5); }
+
 template <bool WRITE>
 __global__ void k_emit(const uint32_t* __restrict__ blob, const long long* __restrict__ cell_off, long n_cells,
                        int max_surf_fid, int* __restrict__ cnt_f, int* __restrict__ cnt_v, int* __restrict__ cnt_e,
@@ -111,17 +168,22 @@ __global__ void k_emit(const uint32_t* __restrict__ blob, const long long* __res
                        unsigned char* __restrict__ f_istet, int* __restrict__ v_cell, int* __restrict__ v_lvid,
                        int* __restrict__ v_key3, float* __restrict__ v_pos3, int* __restrict__ v_surf,
                        int* __restrict__ e_cell, int* __restrict__ e_key2, int* __restrict__ e_lvid2,
-                       float* __restrict__ c_euler) {
+                       float* __restrict__ c_euler, float* __restrict__ f_centroid3,
+                       // feature edges (rpd_update.cxx:209-259): per-tet table of 6 row indices into fe_rows (or -1)
+                       const int* __restrict__ fe_table, const int* __restrict__ fe_rows6, int tet_id_base,
+                       int* __restrict__ cnt_fe, const long long* __restrict__ off_fe, int* __restrict__ fe_hit6,
+                       int* __restrict__ fe_end4, float* __restrict__ fe_end_pos3) {
   const long cell = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= n_cells) return;
   const CellView c = view(blob + cell_off[cell] / 4);
   const unsigned long long ap = active_planes(c);
-  int nf = 0, nv = 0, ne = 0;
-  long long of = 0, ov = 0, oe = 0;
+  int nf = 0, nv = 0, ne = 0, nfe = 0;
+  long long of = 0, ov = 0, oe = 0, ofe = 0;
   if (WRITE) {
     of = off_f[cell];
     ov = off_v[cell];
     oe = off_e[cell];
+    if (fe_table) ofe = off_fe[cell];
   }
   // facets (rpd_update.cxx:121-140)
   for (int p = 0; p < c.nb_p; p++) {
@@ -131,6 +193,12 @@ __global__ void k_emit(const uint32_t* __restrict__ blob, const long long* __res
       f_cell[of + nf] = (int)cell;
       f_key[of + nf] = bis ? neigh_of(c, p) : (int)c.meta[3 * p];
       f_istet[of + nf] = bis ? 0 : 1;
+      // pc_face centroid of a surface facet (cell_to_surfv2fid, rpd_update.cxx:129-133); zero for the others
+      float ctr[3] = {0.f, 0.f, 0.f};
+      if (!bis && (int)c.meta[3 * p] <= max_surf_fid) face_loop_centroid(c, p, ctr);
+      f_centroid3[3 * (of + nf) + 0] = ctr[0];
+      f_centroid3[3 * (of + nf) + 1] = ctr[1];
+      f_centroid3[3 * (of + nf) + 2] = ctr[2];
     }
     nf++;
   }
@@ -139,24 +207,16 @@ __global__ void k_emit(const uint32_t* __restrict__ blob, const long long* __res
     int key[3], surf;
     if (!vertex_key(c, t, max_surf_fid, key, surf)) continue;
     if (WRITE) {
-      const uint32_t v = c.ver[t];
-      const float* P = reinterpret_cast<const float*>(c.plane);
-      const float* p1 = P + 4 * (v & 0xff);
-      const float* p2 = P + 4 * ((v >> 8) & 0xff);
-      const float* p3 = P + 4 * ((v >> 16) & 0xff);
-      // compute_vertex_coordinates, voronoi_defs.cxx:33-49 (exact float operation order)
-      const float rx = -det3_exact(p1[3], p1[1], p1[2], p2[3], p2[1], p2[2], p3[3], p3[1], p3[2]);
-      const float ry = -det3_exact(p1[0], p1[3], p1[2], p2[0], p2[3], p2[2], p3[0], p3[3], p3[2]);
-      const float rz = -det3_exact(p1[0], p1[1], p1[3], p2[0], p2[1], p2[3], p3[0], p3[1], p3[3]);
-      const float rw = det3_exact(p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+      float pos[3];
+      vertex_pos(c, t, pos);
       v_cell[ov + nv] = (int)cell;
       v_lvid[ov + nv] = t;
       v_key3[3 * (ov + nv) + 0] = key[0];
       v_key3[3 * (ov + nv) + 1] = key[1];
       v_key3[3 * (ov + nv) + 2] = key[2];
-      v_pos3[3 * (ov + nv) + 0] = __fdiv_rn(rx, rw);
-      v_pos3[3 * (ov + nv) + 1] = __fdiv_rn(ry, rw);
-      v_pos3[3 * (ov + nv) + 2] = __fdiv_rn(rz, rw);
+      v_pos3[3 * (ov + nv) + 0] = pos[0];
+      v_pos3[3 * (ov + nv) + 1] = pos[1];
+      v_pos3[3 * (ov + nv) + 2] = pos[2];
       v_surf[ov + nv] = surf;
     }
     nv++;
@@ -168,6 +228,44 @@ __global__ void k_emit(const uint32_t* __restrict__ blob, const long long* __res
     if (!edge_active(c, ap, e, v0, v1)) continue;
     if (WRITE) sum_e += 1. / (double)c.edge[3 * e + 2];
     const int a = c.edge[3 * e], b = c.edge[3 * e + 1];
+    // covered feature edge: both planes are tet faces (local faces 0..3) and the tet edge is in tet_es2fe_map
+    if (fe_table && !is_bisector(c, a) && !is_bisector(c, b)) {
+      const int lo = min(a, b), hi = max(a, b);
+      const int row = fe_table[(size_t)(c.tet - tet_id_base) * 6 + fe_slot(lo, hi)];
+      if (row >= 0) {
+        if (WRITE) {
+          // (cell, kind, lv1 < lv2, fe_line_id, fe_id) -- se_covered_lvids / ce_covered_lvids -- and per end vertex
+          // its FIRST half-plane's neighbour + position (se_line_endpos; neigh = -1: the vertex lies on no half-plane)
+          int* h = fe_hit6 + 6 * (ofe + nfe);
+          h[0] = (int)cell;
+          h[1] = fe_rows6[6 * row + 3];
+          h[2] = v0;
+          h[3] = v1;
+          h[4] = fe_rows6[6 * row + 5];
+          h[5] = fe_rows6[6 * row + 4];
+          for (int k = 0; k < 2; k++) {
+            const int lv = k == 0 ? v0 : v1;
+            const uint32_t v = c.ver[lv];
+            int neigh = -1;
+            for (int i = 0; i < 3 && neigh == -1; i++) {
+              const int pl = (int)((v >> (8 * i)) & 0xff);
+              if (is_bisector(c, pl)) neigh = neigh_of(c, pl);
+            }
+            int* en = fe_end4 + 4 * (2 * (ofe + nfe) + k);
+            en[0] = (int)cell;
+            en[1] = lv;
+            en[2] = neigh;
+            en[3] = fe_rows6[6 * row + 5];
+            float pos[3] = {0.f, 0.f, 0.f};
+            if (neigh != -1) vertex_pos(c, lv, pos);
+            fe_end_pos3[3 * (2 * (ofe + nfe) + k) + 0] = pos[0];
+            fe_end_pos3[3 * (2 * (ofe + nfe) + k) + 1] = pos[1];
+            fe_end_pos3[3 * (2 * (ofe + nfe) + k) + 2] = pos[2];
+          }
+        }
+        nfe++;
+      }
+    }
     if (!is_bisector(c, a) || !is_bisector(c, b)) continue;
     if (WRITE) {
       int k0 = neigh_of(c, a), k1 = neigh_of(c, b);
@@ -191,6 +289,7 @@ __global__ void k_emit(const uint32_t* __restrict__ blob, const long long* __res
     cnt_f[cell] = nf;
     cnt_v[cell] = nv;
     cnt_e[cell] = ne;
+    if (fe_table) cnt_fe[cell] = nfe;
   }
 }
 
@@ -305,27 +404,42 @@ void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid) {
   res->emit_counts = {0, 0, 0};
   res->emitted = n == 0;  // set only once the work below has succeeded
   if (n == 0) return;
-  DevBuf<int> cf, cv, ce;
-  DevBuf<long long> of, ov, oe;
+  DevBuf<int> cf, cv, ce, cfe;
+  DevBuf<long long> of, ov, oe, ofe;
   cf.reserve(n + 1); cv.reserve(n + 1); ce.reserve(n + 1);
   of.reserve(n + 1); ov.reserve(n + 1); oe.reserve(n + 1);
   MB_CUDA(cudaMemsetAsync(cf.p + n, 0, sizeof(int), s));
   MB_CUDA(cudaMemsetAsync(cv.p + n, 0, sizeof(int), s));
   MB_CUDA(cudaMemsetAsync(ce.p + n, 0, sizeof(int), s));
+  const TetMeshDev& M = ctx->mesh;
+  const int* fe_table = M.n_fe > 0 ? M.fe_table.p : nullptr;
+  if (fe_table) {
+    cfe.reserve(n + 1);
+    ofe.reserve(n + 1);
+    MB_CUDA(cudaMemsetAsync(cfe.p + n, 0, sizeof(int), s));
+  }
   const unsigned blocks = (unsigned)((n + 127) / 128);
   ctx->n_launches++;
   k_emit<false><<<blocks, 128, 0, s>>>(res->blob.p, res->cell_off.p, n, max_surf_fid, cf.p, cv.p, ce.p, nullptr,
                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, fe_table,
+                                       M.fe_rows.p, M.tet_id_base, cfe.p, nullptr, nullptr, nullptr, nullptr);
   MB_CUDA(cudaGetLastError());
   scan_ll(ctx, cf.p, of.p, n + 1);
   scan_ll(ctx, cv.p, ov.p, n + 1);
   scan_ll(ctx, ce.p, oe.p, n + 1);
-  long long tot[3];
+  if (fe_table) scan_ll(ctx, cfe.p, ofe.p, n + 1);
+  long long tot[4] = {0, 0, 0, 0};
   MB_CUDA(cudaMemcpyAsync(&tot[0], of.p + n, sizeof(long long), cudaMemcpyDeviceToHost, s));
   MB_CUDA(cudaMemcpyAsync(&tot[1], ov.p + n, sizeof(long long), cudaMemcpyDeviceToHost, s));
   MB_CUDA(cudaMemcpyAsync(&tot[2], oe.p + n, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  if (fe_table) MB_CUDA(cudaMemcpyAsync(&tot[3], ofe.p + n, sizeof(long long), cudaMemcpyDeviceToHost, s));
   MB_CUDA(cudaStreamSynchronize(s));
+  res->n_fe_hits = (long)tot[3];
+  res->f_centroid3.reserve(3 * tot[0] + 1);
+  res->fe_hit6.reserve(6 * tot[3] + 1);
+  res->fe_end4.reserve(8 * tot[3] + 1);
+  res->fe_end_pos3.reserve(6 * tot[3] + 1);
   res->emit_counts.n_facets = (long)tot[0];
   res->emit_counts.n_vertices = (long)tot[1];
   res->emit_counts.n_edges = (long)tot[2];
@@ -338,7 +452,9 @@ void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid) {
   k_emit<true><<<blocks, 128, 0, s>>>(res->blob.p, res->cell_off.p, n, max_surf_fid, nullptr, nullptr, nullptr,
                                       of.p, ov.p, oe.p, res->f_cell.p, res->f_key.p, res->f_istet.p,
                                       res->v_cell.p, res->v_lvid.p, res->v_key3.p, res->v_pos3.p, res->v_surf.p,
-                                      res->e_cell.p, res->e_key2.p, res->e_lvid2.p, res->c_euler.p);
+                                      res->e_cell.p, res->e_key2.p, res->e_lvid2.p, res->c_euler.p, res->f_centroid3.p,
+                                      fe_table, M.fe_rows.p, M.tet_id_base, nullptr, ofe.p, res->fe_hit6.p,
+                                      res->fe_end4.p, res->fe_end_pos3.p);
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaStreamSynchronize(s));
   res->emitted = true;

@@ -108,6 +108,7 @@ void rpd_upload_mesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int*
   M.range_count = -1;
   M.n_sel = 0;
   M.tet_id_base = 0;
+  M.n_fe = 0;  // the feature-edge map belongs to a mesh
   ctx->h_tet_planes_valid = false;
 }
 

@@ -128,6 +128,18 @@ class RpdResult:
         order = ["facet_cell", "facet_key", "facet_is_tet", "vert_cell", "vert_lvid", "vert_key",
                  "vert_pos", "vert_surf_fid", "edge_cell", "edge_key", "edge_lvid", "cell_euler"]
         self.ctx._check(self.ctx.lib.mb_rpd_fetch_emit(self._h, *[ptr(out[k]) for k in order]))
+        # pc_face centroids of the surface facets (cell_to_surfv2fid) and, when the context holds a feature-edge map,
+        # the covered sharp / concave edges of rpd_update.cxx:209-259
+        out["facet_centroid"] = np.zeros((nf, 3), np.float32)
+        if nf:
+            self.ctx._check(self.ctx.lib.mb_rpd_fetch_facet_centroids(self._h, ptr(out["facet_centroid"])))
+        nh = C.c_long(0)
+        self.ctx._check(self.ctx.lib.mb_rpd_feature_edge_count(self._h, C.byref(nh)))
+        out["fe_hit"] = np.zeros((nh.value, 6), np.int32)
+        out["fe_end"] = np.zeros((2 * nh.value, 4), np.int32)
+        out["fe_end_pos"] = np.zeros((2 * nh.value, 3), np.float32)
+        if nh.value:
+            self.ctx._check(self.ctx.lib.mb_rpd_fetch_feature_edges(self._h, ptr(out["fe_hit"]), ptr(out["fe_end"]), ptr(out["fe_end_pos"])))
         return out
 
     def topology(self) -> dict:
@@ -208,6 +220,14 @@ class Context:
 
     def set_mesh(self, mesh):
         self.set_tetmesh(mesh.vertices, mesh.indices, mesh.v_adjs, mesh.f_adjs, mesh.f_ids, e_adj6=mesh.e_adj6)
+
+    def set_feature_edges(self, rows6=None):
+        """TetMesh::tet_es2fe_map of the resident mesh: rows (tet, lf_min, lf_max, fe_type, fe_id, fe_line_id); None clears"""
+        if rows6 is None or len(rows6) == 0:
+            self._check(self.lib.mb_set_feature_edges(self._ctx, None, 0))
+        else:
+            r = _c(rows6, np.int32).reshape(-1, 6)
+            self._check(self.lib.mb_set_feature_edges(self._ctx, ptr(r), len(r)))
 
     def set_tet_range(self, first: int, count: int):
         self._check(self.lib.mb_set_tet_range(self._ctx, int(first), int(count)))
