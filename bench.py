@@ -350,6 +350,49 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg},
            "e2e": {"value": n_samples / t_e2e, "unit": "queries/s",
                    "h2d_bytes_per_step": int(sum(x.nbytes for x in hp)), "d2h_bytes_per_step": int(8 * n_samples)}}
+    # ---- f3: the candidate lists built on the device (mb_dist2mat_by_face): the caller hands over what the reference
+    # STARTS from -- medial mesh, (surface fid, site) incidence, samples + their surface-face id -- instead of one
+    # private int3 list per sample.  Everything is inside the timed region: medial mesh + incidence upload, list
+    # construction on the device, 16 B per sample H2D, kernel, 8 B per sample D2H.
+    try:
+        smp_h, fid_h = pin(d.samples), pin(d.sample_fid)
+        sph_h, mf_h, me_h, fs_h = pin(d.spheres), pin(d.mm_faces), pin(d.mm_edges), pin(d.fid_sites)
+
+        def by_face_call():
+            ctx.dist2mat_set_medial_mesh(sph_h.numpy(), mf_h.numpy(), me_h.numpy())
+            ctx.dist2mat_set_face_sites(fs_h.numpy(), d.n_fid)
+            ctx._check(ctx.lib.mb_dist2mat_by_face(ctx._ctx, smp_h.numpy().ctypes.data, fid_h.numpy().ctypes.data, n_samples,
+                                                   res_h.numpy().ctypes.data, cid_h.numpy().ctypes.data, None, None))
+
+        by_face_call()
+        off_l, _ = ctx.dist2mat_face_lists()
+        ms3 = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ms3.append(ctx.dist2mat_run())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            by_face_call()
+        torch.cuda.synchronize()
+        t_bf = (time.perf_counter() - t0) / e_steps
+        k3 = float(np.mean(ms3))
+        n_list = int(off_l[-1])
+        per_sample = float(np.mean(off_l[d.sample_fid.astype(np.int64) + 1] - off_l[d.sample_fid.astype(np.int64)]))
+        b_alg3 = n_samples * (12 + 4 + 8) + n_list * 12 + len(d.spheres) * 16
+        h2d3 = int(smp_h.numpy().nbytes + fid_h.numpy().nbytes + sph_h.numpy().nbytes + mf_h.numpy().nbytes + me_h.numpy().nbytes + fs_h.numpy().nbytes)
+        out["by_face"] = {
+            "what": "mb_dist2mat_set_medial_mesh + mb_dist2mat_set_face_sites + mb_dist2mat_by_face: per-surface-face lists built on "
+                    "the device in the reference's order (fix_geo_error.cxx:149-215), samples carry a face id",
+            "value": n_samples / (k3 * 1e-3), "unit": "queries/s", "ms_per_step": k3, "prims_per_sample": per_sample,
+            "list_entries_on_device": n_list, "surface_faces": int(d.n_fid),
+            "roofline": {"bound": "hbm", "achieved": b_alg3 / (k3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": b_alg3 / (k3 * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": b_alg3},
+            "e2e": {"value": n_samples / t_bf, "unit": "queries/s", "h2d_bytes_per_step": h2d3, "d2h_bytes_per_step": int(8 * n_samples),
+                    "ms": 1e3 * t_bf}}
+    except Exception as exc:  # noqa: BLE001
+        out["by_face"] = {"error": str(exc)}
     # the same query with every distinct list stored once (samples of one surface face share their list:
     # fix_geo_error.cxx:149-215 builds one list per face and :300-366 replicates it per sample).  Offsets may
     # point anywhere, so this needs no new entry point -- only a caller that stops replicating.

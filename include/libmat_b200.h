@@ -337,6 +337,36 @@ int mb_dist2mat_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float
 int mb_dist2mat_run(mb_ctx* ctx, float* kernel_ms);
 int mb_dist2mat_fetch(mb_ctx* ctx, float* result, int* closest_id, unsigned char* tie_flag);
 
+/* ---------------------------------------------------------------- dist2mat with device-built candidate lists
+ * Replaces, for callers that have the medial mesh and the samples' surface-face ids, the CPU list construction and
+ * the replicated upload of the reference (gather_point_to_sites fix_geo_error.cxx:149-178, gather_point_to_slab_and_cone
+ * :180-215, load_and_compute_sample_dist2mat_gpubuffer :300-366: one private int3 list per sample, ~290 B / sample):
+ * the per-surface-face lists are built once on the device and a sample costs 16 bytes (position + face id).
+ *   mb_dist2mat_set_medial_mesh   spheres (cx,cy,cz,r) + medial faces (3 sphere ids each, MedialMesh::faces) + medial
+ *                                 edges (2 sphere ids each, MedialMesh::edges); a sphere's faces_ / edges_ sets are the
+ *                                 faces / edges that list it
+ *   mb_dist2mat_set_face_sites    (surface fid, site) rows in any order, duplicates allowed = the union of every power
+ *                                 cell's cell_to_surfv2fid; n_fid = number of surface faces.  Site ids index spheres.
+ *   mb_dist2mat_set_face_sites_from_rpd   the same, taken on the device from an RPD result after mb_rpd_emit (K4's
+ *                                 surface facets): RPD -> K4 -> dist2mat lists without a host round trip
+ *   mb_dist2mat_by_face           samples + their surface-face id -> result / closest_id exactly as mb_dist2mat would
+ *                                 return them for the reference's lists (per site in ascending id: its slabs in
+ *                                 ascending face id, its cones in ascending edge id, the sphere; no de-duplication;
+ *                                 a face no cell touches has an empty list -> 1e16f, -1), and closest_prim3 (nullable):
+ *                                 the winning primitive's int3 (samples_clostprim, fix_geo_error.cxx:368-380)
+ *   mb_dist2mat_upload_by_face / mb_dist2mat_run / mb_dist2mat_fetch: the resident split of the same call
+ *   mb_dist2mat_fetch_face_lists  the device-built CSR (n_fid + 1 offsets in prims, then the int3 prims) for inspection */
+int mb_dist2mat_set_medial_mesh(mb_ctx* ctx, const float* spheres, int n_sph, const int* mm_faces, int n_faces,
+                                const int* mm_edges, int n_edges);
+int mb_dist2mat_set_face_sites(mb_ctx* ctx, const int* fid_site_rows, long n_rows, int n_fid);
+int mb_dist2mat_set_face_sites_from_rpd(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
+int mb_dist2mat_upload_by_face(mb_ctx* ctx, const float* samples, const int* sample_fid, int n_samples);
+int mb_dist2mat_by_face(mb_ctx* ctx, const float* samples, const int* sample_fid, int n_samples, float* result,
+                        int* closest_id, int* closest_prim3, unsigned char* tie_flag);
+int mb_dist2mat_fetch_closest_prims(mb_ctx* ctx, int* closest_prim3);
+int mb_dist2mat_face_list_size(mb_ctx* ctx, long* n_fid, long* n_prims);
+int mb_dist2mat_fetch_face_lists(mb_ctx* ctx, long long* list_off, int* prims3);
+
 #ifdef __cplusplus
 }
 #endif

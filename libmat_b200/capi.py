@@ -19,6 +19,8 @@ SYMBOLS = [
     "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_cell_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
     "mb_rpd_fetch_emit", "mb_rpd_fetch_facet_centroids", "mb_set_feature_edges", "mb_rpd_feature_edge_count",
     "mb_rpd_fetch_feature_edges", "mb_rpd_write_bgeo", "mb_bgeo_write_records", "mb_rpd_topology", "mb_rpd_fetch_topology", "mb_dist2mat", "mb_dist2mat_upload", "mb_dist2mat_run", "mb_dist2mat_fetch",
+    "mb_dist2mat_set_medial_mesh", "mb_dist2mat_set_face_sites", "mb_dist2mat_set_face_sites_from_rpd", "mb_dist2mat_upload_by_face",
+    "mb_dist2mat_by_face", "mb_dist2mat_fetch_closest_prims", "mb_dist2mat_face_list_size", "mb_dist2mat_fetch_face_lists",
 ]
 
 # static-filter bounds (reference src/predicate_generator/main.cpp output; include/libmat_b200.h)
@@ -129,6 +131,14 @@ def load() -> C.CDLL:
     lib.mb_dist2mat_upload.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_long]
     lib.mb_dist2mat_run.argtypes = [vp, C.POINTER(C.c_float)]
     lib.mb_dist2mat_fetch.argtypes = [vp, vp, vp, vp]
+    lib.mb_dist2mat_set_medial_mesh.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int]
+    lib.mb_dist2mat_set_face_sites.argtypes = [vp, vp, C.c_long, C.c_int]
+    lib.mb_dist2mat_set_face_sites_from_rpd.argtypes = [vp, vp, C.c_int]
+    lib.mb_dist2mat_upload_by_face.argtypes = [vp, vp, vp, C.c_int]
+    lib.mb_dist2mat_by_face.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.mb_dist2mat_fetch_closest_prims.argtypes = [vp, vp]
+    lib.mb_dist2mat_face_list_size.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    lib.mb_dist2mat_fetch_face_lists.argtypes = [vp, vp, vp]
     _lib = lib
     return lib
 

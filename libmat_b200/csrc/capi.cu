@@ -910,4 +910,80 @@ int mb_dist2mat(mb_ctx* ctx, const float* spheres, int n_sph, const float* sampl
   return mb_dist2mat_fetch(ctx, result, closest_id, tie_flag);
 }
 
+int mb_dist2mat_set_medial_mesh(mb_ctx* ctx, const float* spheres, int n_sph, const int* mm_faces, int n_faces,
+                                const int* mm_edges, int n_edges) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && spheres && n_sph > 0 && n_faces >= 0 && n_edges >= 0, MB_ERR_ARG, "bad medial mesh");
+  MB_REQUIRE((n_faces == 0 || mm_faces) && (n_edges == 0 || mm_edges), MB_ERR_ARG, "null medial faces / edges");
+  for (long i = 0; i < 3L * n_faces; i++) MB_REQUIRE(mm_faces[i] >= 0 && mm_faces[i] < n_sph, MB_ERR_ARG, "medial face refers to a sphere out of range");
+  for (long i = 0; i < 2L * n_edges; i++) MB_REQUIRE(mm_edges[i] >= 0 && mm_edges[i] < n_sph, MB_ERR_ARG, "medial edge refers to a sphere out of range");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  d2m_set_medial_mesh(ctx, spheres, n_sph, mm_faces, n_faces, mm_edges, n_edges);
+  MB_CATCH
+}
+
+int mb_dist2mat_set_face_sites(mb_ctx* ctx, const int* fid_site_rows, long n_rows, int n_fid) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && n_rows >= 0 && n_fid >= 0 && (n_rows == 0 || fid_site_rows), MB_ERR_ARG, "bad arguments");
+  for (long i = 0; i < n_rows; i++)
+    MB_REQUIRE(fid_site_rows[2 * i] >= 0 && fid_site_rows[2 * i] < n_fid && fid_site_rows[2 * i + 1] >= 0 &&
+                   fid_site_rows[2 * i + 1] < ctx->d2m.n_sph, MB_ERR_ARG, "(fid, site) row out of range");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  d2m_set_face_sites(ctx, fid_site_rows, n_rows, n_fid);
+  MB_CATCH
+}
+
+int mb_dist2mat_set_face_sites_from_rpd(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && res && res->ctx == ctx && max_surf_fid >= 0, MB_ERR_ARG, "bad arguments");
+  MB_REQUIRE(!res->host_only, MB_ERR_STATE, "needs a device-resident result (mb_rpd_run)");
+  MB_REQUIRE(res->n_site <= ctx->d2m.n_sph, MB_ERR_ARG, "RPD site ids must index the medial spheres");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  d2m_set_face_sites_from_rpd(ctx, res, max_surf_fid);
+  MB_CATCH
+}
+
+int mb_dist2mat_upload_by_face(mb_ctx* ctx, const float* samples, const int* sample_fid, int n_samples) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && n_samples >= 0 && (n_samples == 0 || (samples && sample_fid)), MB_ERR_ARG, "bad arguments");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  d2m_upload_by_face(ctx, samples, sample_fid, n_samples);
+  MB_CATCH
+}
+
+int mb_dist2mat_fetch_closest_prims(mb_ctx* ctx, int* closest_prim3) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && closest_prim3, MB_ERR_ARG, "null argument");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  d2m_fetch_closest_prims(ctx, closest_prim3);
+  MB_CATCH
+}
+
+int mb_dist2mat_by_face(mb_ctx* ctx, const float* samples, const int* sample_fid, int n_samples, float* result,
+                        int* closest_id, int* closest_prim3, unsigned char* tie_flag) {
+  int rc = mb_dist2mat_upload_by_face(ctx, samples, sample_fid, n_samples);
+  if (rc) return rc;
+  rc = mb_dist2mat_run(ctx, nullptr);
+  if (rc) return rc;
+  rc = mb_dist2mat_fetch(ctx, result, closest_id, tie_flag);
+  if (rc || !closest_prim3) return rc;
+  return mb_dist2mat_fetch_closest_prims(ctx, closest_prim3);
+}
+
+int mb_dist2mat_face_list_size(mb_ctx* ctx, long* n_fid, long* n_prims) {
+  if (!ctx) return MB_ERR_ARG;
+  if (!ctx->d2m_lists.have_lists) return MB_ERR_STATE;
+  if (n_fid) *n_fid = ctx->d2m_lists.n_fid;
+  if (n_prims) *n_prims = ctx->d2m.n_prims;
+  return MB_OK;
+}
+
+int mb_dist2mat_fetch_face_lists(mb_ctx* ctx, long long* list_off, int* prims3) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  d2m_fetch_face_lists(ctx, list_off, prims3);
+  MB_CATCH
+}
+
 }  // extern "C"

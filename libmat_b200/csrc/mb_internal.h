@@ -223,6 +223,20 @@ struct D2MDev {
   DevBuf<unsigned char> tie;
 };
 
+// f3: device-built dist2mat candidate lists (dist2mat_lists.cu)
+struct D2MLists {
+  bool have_mesh = false, have_lists = false;
+  int n_faces = 0, n_edges = 0, n_fid = 0;
+  long n_sf = 0, n_se = 0, n_fs = 0;
+  DevBuf<int> mm_faces, mm_edges;              // medial faces (3 sphere ids) / edges (2 sphere ids)
+  DevBuf<unsigned long long> sf_keys, se_keys; // sorted (sphere << 32 | face id) / (sphere << 32 | edge id)
+  DevBuf<int> sf_first, se_first;              // CSR row starts per sphere
+  DevBuf<unsigned long long> fs_keys;          // sorted unique (surface fid << 32 | site)
+  DevBuf<int> fs_first;                        // CSR row starts per surface fid
+  DevBuf<long long> list_off;                  // per surface fid: start of its primitive list in D2MDev::prims
+  DevBuf<int> sample_fid;
+};
+
 struct mb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;      // the stream in use (own_stream unless mb_set_stream)
@@ -233,6 +247,7 @@ struct mb_ctx {
   TetMeshDev mesh;
   SitesDev sites;
   D2MDev d2m;
+  D2MLists d2m_lists;
   int d2m_variant = 0;  // 0 = queue-compacted kernel, 1 = warp-per-sample kernel (MB_D2M_VARIANT, A/B only)
   PinBuf pin_in, pin_out;
   // streamed runs: second stream + double-buffered span results + pinned destination
@@ -307,3 +322,10 @@ void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* sampl
                 const unsigned* offset, const unsigned* count, const int* prims, long n_prims);
 void d2m_run(mb_ctx* ctx, float* kernel_ms);
 void d2m_fetch(mb_ctx* ctx, float* result, int* closest_id, unsigned char* tie_flag);
+// ---- dist2mat_lists.cu (f3) ----------------------------------------------------------------------
+void d2m_set_medial_mesh(mb_ctx* ctx, const float* spheres, int n_sph, const int* faces, int n_faces, const int* edges, int n_edges);
+void d2m_set_face_sites(mb_ctx* ctx, const int* fid_site_rows, long n_rows, int n_fid);
+void d2m_set_face_sites_from_rpd(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
+void d2m_upload_by_face(mb_ctx* ctx, const float* samples, const int* sample_fid, int n_samples);
+void d2m_fetch_closest_prims(mb_ctx* ctx, int* prim3);
+void d2m_fetch_face_lists(mb_ctx* ctx, long long* list_off, int* prims3);

@@ -357,6 +357,46 @@ class Context:
         self._check(self.lib.mb_dist2mat_fetch(self._ctx, ptr(res), ptr(cid), ptr(tie)))
         return res, cid, tie
 
+    # ---- f3: candidate lists built on the device (fix_geo_error.cxx:149-215 semantics) --------------------
+    def dist2mat_set_medial_mesh(self, spheres, mm_faces, mm_edges):
+        sp = _c(spheres, np.float32).reshape(-1)
+        mf = _c(mm_faces, np.int32).reshape(-1)
+        me = _c(mm_edges, np.int32).reshape(-1)
+        self._check(self.lib.mb_dist2mat_set_medial_mesh(self._ctx, ptr(sp), sp.size // 4, ptr(mf), mf.size // 3, ptr(me), me.size // 2))
+
+    def dist2mat_set_face_sites(self, fid_site_rows, n_fid):
+        r = _c(fid_site_rows, np.int32).reshape(-1, 2)
+        self._check(self.lib.mb_dist2mat_set_face_sites(self._ctx, ptr(r), len(r), int(n_fid)))
+
+    def dist2mat_set_face_sites_from_rpd(self, res: "RpdResult", max_surf_fid: int):
+        self._check(self.lib.mb_dist2mat_set_face_sites_from_rpd(self._ctx, res._h, int(max_surf_fid)))
+
+    def dist2mat_upload_by_face(self, samples, sample_fid):
+        sm = _c(samples, np.float32).reshape(-1)
+        fi = _c(sample_fid, np.int32)
+        self._d2m_n = fi.size
+        self._check(self.lib.mb_dist2mat_upload_by_face(self._ctx, ptr(sm), ptr(fi), fi.size))
+
+    def dist2mat_closest_prims(self):
+        out = np.zeros((self._d2m_n, 3), np.int32)
+        if self._d2m_n:
+            self._check(self.lib.mb_dist2mat_fetch_closest_prims(self._ctx, ptr(out)))
+        return out
+
+    def dist2mat_by_face(self, samples, sample_fid, want_tie=True):
+        """samples + surface-face ids against the device-built per-face lists: (result, closest_id[, tie], closest_prim3)"""
+        self.dist2mat_upload_by_face(samples, sample_fid)
+        self.dist2mat_run()
+        return (*self.dist2mat_fetch(want_tie), self.dist2mat_closest_prims())
+
+    def dist2mat_face_lists(self):
+        a, b = C.c_long(), C.c_long()
+        self._check(self.lib.mb_dist2mat_face_list_size(self._ctx, C.byref(a), C.byref(b)))
+        off = np.zeros(a.value + 1, np.int64)
+        prims = np.zeros((b.value, 3), np.int32)
+        self._check(self.lib.mb_dist2mat_fetch_face_lists(self._ctx, ptr(off), ptr(prims)))
+        return off, prims
+
     def compute_closest_dist2mat(self, spheres, samples, offset, count, prims, want_tie=True):
         """Argument meaning of compute_closest_dist2mat (reference dist2mat.h:19-24):
         returns (results, closest_mat_id[, tie_flag])."""

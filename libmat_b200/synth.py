@@ -332,6 +332,56 @@ class Dist2MatInput:
     prims: np.ndarray  # int32 [n_prims,3]  (-1,-1,s) sphere / (-1,a,b) cone / (a,b,c) slab
     n_cones: int = 0
     n_slabs: int = 0
+    # the same workload in the form the reference STARTS from (fix_geo_error.cxx:149-215): the medial mesh, every
+    # sample's surface-face id and the (surface fid, site) incidence of the power cells -- the input of the
+    # device-built lists (mb_dist2mat_by_face).  Synthetic surface face = the unordered pair of a sample's two nearest
+    # spheres; its sites are those two spheres.
+    mm_faces: np.ndarray = None  # int32 [n_slabs,3]
+    mm_edges: np.ndarray = None  # int32 [n_cones,2]
+    sample_fid: np.ndarray = None  # int32 [n_samples]
+    fid_sites: np.ndarray = None  # int32 [2*n_fid,2] rows (fid, site)
+    n_fid: int = 0
+
+
+def reference_face_lists(n_sph: int, mm_faces, mm_edges, fid_sites, n_fid: int):
+    """The per-surface-face primitive lists exactly as the reference assembles them per sample
+    (gather_point_to_sites fix_geo_error.cxx:149-178 + gather_point_to_slab_and_cone :180-215): for each site of the face
+    in ascending id -- its medial faces in ascending face id (MedialSphere::faces_ is a std::set), its medial edges in
+    ascending edge id as (-1, a, b), then the sphere (-1, -1, site); nothing de-duplicated.  Returns the CSR
+    (offsets int64 [n_fid+1], prims int32 [n,3]).  Host restatement used by tests and by the bench's replicated leg."""
+    mm_faces = np.asarray(mm_faces, np.int64).reshape(-1, 3)
+    mm_edges = np.asarray(mm_edges, np.int64).reshape(-1, 2)
+    faces_of = [[] for _ in range(n_sph)]
+    edges_of = [[] for _ in range(n_sph)]
+    for f, tri in enumerate(mm_faces):
+        for s in set(tri.tolist()):
+            faces_of[s].append(f)
+    for e, ed in enumerate(mm_edges):
+        for s in set(ed.tolist()):
+            edges_of[s].append(e)
+    sites_of = [set() for _ in range(n_fid)]
+    for f, s in np.asarray(fid_sites, np.int64).reshape(-1, 2):
+        sites_of[f].add(int(s))
+    off, prims = [0], []
+    for f in range(n_fid):
+        for s in sorted(sites_of[f]):
+            prims.extend(mm_faces[faces_of[s]].tolist())
+            prims.extend([[-1, int(a), int(b)] for a, b in mm_edges[edges_of[s]]])
+            prims.append([-1, -1, s])
+        off.append(len(prims))
+    return np.asarray(off, np.int64), np.asarray(prims, np.int32).reshape(-1, 3)
+
+
+def replicate_lists(list_off, list_prims, sample_fid):
+    """one private copy of its face's list per sample, like load_and_compute_sample_dist2mat_gpubuffer
+    (fix_geo_error.cxx:300-366): (offset uint32, count uint32, prims int32 [n,3])"""
+    fid = np.asarray(sample_fid, np.int64)
+    cnt = (list_off[fid + 1] - list_off[fid]).astype(np.int64)
+    offset = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int64)
+    rows = np.repeat(np.arange(len(fid)), cnt)
+    pos = np.arange(int(cnt.sum())) - np.repeat(offset, cnt)
+    prims = list_prims[list_off[fid][rows] + pos]
+    return offset.astype(np.uint32), cnt.astype(np.uint32), np.ascontiguousarray(prims, dtype=np.int32)
 
 
 def make_dist2mat(n_samples: int, nu: int = 100, nv: int = 200, seed: int = RAN_SEED,
@@ -445,7 +495,10 @@ def make_dist2mat(n_samples: int, nu: int = 100, nv: int = 200, seed: int = RAN_
     tail = offset + cnt_u
     prims[tail] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 0]], axis=1)
     prims[tail + 1] = np.stack([np.full(n_samples, -1), np.full(n_samples, -1), nn[:, 1]], axis=1)
-    return Dist2MatInput(spheres, samples, offset.astype(np.uint32), count.astype(np.uint32), prims, n_co, n_sl)
+    fid_sites = np.stack([np.repeat(np.arange(n_up), 2), np.stack([ua, ub], axis=1).ravel()], axis=1).astype(np.int32)
+    return Dist2MatInput(spheres, samples, offset.astype(np.uint32), count.astype(np.uint32), prims, n_co, n_sl,
+                         mm_faces=tri.astype(np.int32), mm_edges=edges.astype(np.int32), sample_fid=pinv.astype(np.int32),
+                         fid_sites=fid_sites, n_fid=int(n_up))
 
 
 def share_lists(d: Dist2MatInput) -> Dist2MatInput:
