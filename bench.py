@@ -601,29 +601,56 @@ def main():
         from libmat_b200.loop import RpdLoop, evolve_sites
         mesh, sites, n, ns = make_workload("cfg2", 1)
         ctx = Context(local_rank)
+        from libmat_b200 import capi
         loop = RpdLoop(ctx, mesh)
+        fmt = {"full": 0, "lean": 1, "slim": 2}[args.records]
         for _ in range(args.warmup):
-            loop.step(sites, to_host=True)
+            loop.step(sites, to_host=True, lean=fmt)
         lat, dev_ms, cells = [], [], []
+        inc_lat, inc_frac, inc_bytes, merge_ms = [], [], [], []
         iters = 20
         sampler = ClockSampler(local_rank)
         sampler.start()
+        # the caller's copy of the result (what RPD3D_GPU::powercells / merge_convex_cells keep, rpd_api.cxx:432-479)
+        r0, _, _ = loop.step_incremental(sites, to_host=True, lean=fmt)
+        hb, ho = r0.host_compact()
+        host_blob, host_offs = hb.copy(), ho.copy()
         for it in range(iters):
             sites, changed = evolve_sites(sites, it)  # host-side edit (the caller's fix_topo / fix_geo step), untimed
-            res, dt = loop.step(sites, to_host=True)  # H2D sites + K1..K4a + streamed D2H of the compact result
+            # incremental: H2D sites + K1 + K2 on all tets + K3 on the affected tets + streamed D2H of their records
+            ri, tets, dti = loop.step_incremental(sites, to_host=True, lean=fmt)
+            inc_lat.append(dti * 1e3)
+            inc_frac.append(len(tets) / mesh.n_tet)
+            inc_bytes.append(ri.compact_bytes)
+            pb, po = ri.host_compact()
+            tm = time.perf_counter()
+            host_blob, host_offs = capi.merge_compact(host_blob, host_offs, pb, po, tets)
+            merge_ms.append(1e3 * (time.perf_counter() - tm))
+            # full recompute of the same iteration (the checker, and round 1's number)
+            res, dt = loop.step(sites, to_host=True, lean=fmt)  # H2D sites + K1..K4a + streamed D2H of the compact result
             lat.append(dt * 1e3)
             dev_ms.append(res.kernel_ms["total"])
             cells.append(res.n_cells)
-        line = {"metric": "rpd_loop_iteration_latency_ms", "value": float(np.median(lat)), "unit": "ms", "n_gpus": 1,
-                "steps": iters, "warmup": args.warmup, "ms_per_step": float(np.mean(lat)), "higher_is_better": False,
+            fb, fo = res.host_compact()
+            if not (np.array_equal(fo, host_offs) and np.array_equal(fb, host_blob)):
+                raise SystemExit(f"cfg5: incremental result differs from the full recompute at iteration {it}")
+        line = {"metric": "rpd_loop_iteration_latency_ms", "value": float(np.median(inc_lat)), "unit": "ms", "n_gpus": 1,
+                "steps": iters, "warmup": args.warmup, "ms_per_step": float(np.mean(inc_lat)), "higher_is_better": False,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
                 "config": {"workload": f"cfg5: 20 iterations on the resident config-2 mesh ({mesh.n_tet} tets), "
                                        f"{ns} -> {sites.n_site} spheres (0.5 % inserted + 0.5 % updated per iteration), "
-                                       "full exact recompute in grid-kNN mode every iteration, result streamed to pinned host memory",
-                           "latency_ms": {"min": float(np.min(lat)), "median": float(np.median(lat)), "max": float(np.max(lat))},
-                           "device_ms_median": float(np.median(dev_ms)), "cells_last": int(cells[-1])},
-                "e2e": {"value": float(np.median(lat)), "unit": "ms", "h2d_bytes_per_step": int(16 * sites.n_site + 4 * sites.n_site),
-                        "d2h_bytes_per_step": int(res.compact_bytes + 8 * (res.n_cells + 1))},
+                                       "incremental recompute (mb_rpd_run_incremental: K2 on all tets, K3 on the tets whose candidate "
+                                       f"list changed), {args.records} records streamed to pinned host memory; every iteration is "
+                                       "checked byte for byte against a full recompute"},
+                "incremental": {"latency_ms": {"min": float(np.min(inc_lat)), "median": float(np.median(inc_lat)), "max": float(np.max(inc_lat))},
+                                "affected_tet_fraction": {"min": float(np.min(inc_frac)), "median": float(np.median(inc_frac)), "max": float(np.max(inc_frac))},
+                                "d2h_bytes_median": int(np.median(inc_bytes)),
+                                "host_merge_ms_median": float(np.median(merge_ms)),
+                                "identical_to_full_recompute": True},
+                "full_recompute": {"latency_ms": {"min": float(np.min(lat)), "median": float(np.median(lat)), "max": float(np.max(lat))},
+                                   "device_ms_median": float(np.median(dev_ms)), "cells_last": int(cells[-1])},
+                "e2e": {"value": float(np.median(inc_lat)), "unit": "ms", "h2d_bytes_per_step": int(16 * sites.n_site + 4 * sites.n_site),
+                        "d2h_bytes_per_step": int(np.median(inc_bytes))},
                 "gpu_launches": int(ctx.launch_count()), "clocks": sampler.stop()}
         emit_line(line)
         ctx.close()

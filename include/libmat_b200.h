@@ -168,6 +168,28 @@ int mb_rpd_sync(mb_ctx* ctx, mb_rpd_result* res); /* waits, reads back the count
 int mb_rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result** out,
                        const void** host_blob, const long** host_cell_offsets);
 
+/* Incremental recompute for the MATTopo loop (BASELINE configs[4]; replaces RPD3D_GPU::calculate_partial's ring
+ * selection, rpd_api.cxx:147-313, triangulation.cxx:442-549, load_partial_tet_given_spheres :482-535, which need the
+ * CGAL regular triangulation).  Call it after mb_rpd_upload_sites (grid-kNN mode, whole mesh) instead of mb_rpd_run:
+ * the candidate lists of ALL tets are recomputed (K1 + K2) and compared with the previous incremental run's; only the
+ * tets whose list changed or lists a changed site -- the AFFECTED tets, an exact set: every other tet's records are
+ * bit-for-bit those of the previous run -- are clipped.  *out holds the records of the affected tets only (global tet
+ * ids, (tet, site) order); the caller replaces those tets' records in its previous result (merge_convex_cells,
+ * rpd_api.cxx:432-479).  The first call (or the first after mb_set_tetmesh / a change of grid_k) affects every tet.
+ * to_host = 1 streams the records to pinned host memory like mb_rpd_run_to_host (host_blob / host_cell_offsets as
+ * there); 0 keeps them on the device like mb_rpd_run.  Existing sites keep their ids across calls; new sites are
+ * appended.  mb_rpd_fetch_affected_tets: the ascending ids of the tets of the last incremental run. */
+int mb_rpd_run_incremental(mb_ctx* ctx, const mb_rpd_opts* opts, int to_host, int n_chunks, mb_rpd_result** out,
+                           long* n_affected_tets, const void** host_blob, const long** host_cell_offsets);
+int mb_rpd_fetch_affected_tets(mb_ctx* ctx, int* tet_ids);
+/* host-side merge of compact records (no GPU, no context): prev = the caller's previous result, patch = the records of
+ * an incremental run, affected_tets = its ascending tet ids.  out_offs needs n_prev + n_patch + 1 entries, out_blob
+ * prev bytes + patch bytes (NULL: only count).  Works on full and transport-format (lean / slim) records alike, as
+ * long as prev and patch use the same format. */
+int mb_rpd_merge_compact(const void* prev_blob, const long* prev_offs, long n_prev, const void* patch_blob,
+                         const long* patch_offs, long n_patch, const int* affected_tets, long n_affected, void* out_blob,
+                         long* out_offs, long* n_out, long* out_bytes);
+
 /* The same streamed run into CALLER memory of fixed capacity (MB_ERR_NOMEM if it does not fit): sink_blob /
  * sink_cell_offsets may be pinned or registered host memory (mb_host_register: e.g. a shared-memory segment
  * that every rank of a multi-GPU job writes its tet shard into, all PCIe links in parallel), device memory of

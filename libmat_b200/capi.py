@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libmat_b200.so")
 # every symbol include/libmat_b200.h declares
 SYMBOLS = [
     "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_id_base", "mb_set_tet_subset",
-    "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_run_to_host", "mb_rpd_run_to_sink", "mb_rpd_expand_compact", "mb_rpd_spans", "mb_sink_create", "mb_sink_destroy", "mb_sink_open",
+    "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_run_to_host", "mb_rpd_run_incremental", "mb_rpd_fetch_affected_tets", "mb_rpd_merge_compact", "mb_rpd_run_to_sink", "mb_rpd_expand_compact", "mb_rpd_spans", "mb_sink_create", "mb_sink_destroy", "mb_sink_open",
     "mb_sink_close", "mb_host_register", "mb_host_unregister", "mb_copy_to_host", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_clip_passes", "mb_rpd_flagged", "mb_rpd_fetch_flags", "mb_debug_set_pair_hint", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
     "mb_rpd_fetch_compact", "mb_rpd_site_volumes", "mb_rpd_cell_volumes", "mb_rpd_device_buffers", "mb_rpd_emit",
@@ -100,6 +100,9 @@ def load() -> C.CDLL:
     lib.mb_host_unregister.argtypes = [vp, vp]
     lib.mb_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
     lib.mb_rpd_run_to_host.argtypes = [vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.mb_rpd_run_incremental.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_long), C.POINTER(vp), C.POINTER(vp)]
+    lib.mb_rpd_fetch_affected_tets.argtypes = [vp, vp]
+    lib.mb_rpd_merge_compact.argtypes = [vp, vp, C.c_long, vp, vp, C.c_long, vp, C.c_long, vp, vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     lib.mb_rpd_count.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]
     lib.mb_rpd_status_histogram.argtypes = [vp, vp]
     lib.mb_rpd_clip_passes.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
@@ -153,6 +156,25 @@ def bgeo_write_records(records: np.ndarray, path: str, max_sf_fid: int, is_bound
     if rc != 0:
         raise LibMatError(f"mb_bgeo_write_records failed ({rc})")
     return a.value, b.value
+
+
+def merge_compact(prev_blob, prev_offs, patch_blob, patch_offs, affected_tets):
+    """mb_rpd_merge_compact: (blob uint32, offsets int64) of the previous result with the affected tets' records replaced"""
+    lib = load()
+    po = np.ascontiguousarray(prev_offs, np.int64)
+    qo = np.ascontiguousarray(patch_offs, np.int64)
+    pb = np.ascontiguousarray(prev_blob)
+    qb = np.ascontiguousarray(patch_blob)
+    aff = np.ascontiguousarray(affected_tets, np.int32)
+    n_prev, n_patch = len(po) - 1, len(qo) - 1
+    out_off = np.zeros(n_prev + n_patch + 1, np.int64)
+    out = np.zeros((int(po[-1]) + int(qo[-1])) // 4 + 1, np.uint32)
+    n, nb = C.c_long(0), C.c_long(0)
+    rc = lib.mb_rpd_merge_compact(ptr(pb), ptr(po), n_prev, ptr(qb), ptr(qo), n_patch, ptr(aff), len(aff), ptr(out), ptr(out_off),
+                                  C.byref(n), C.byref(nb))
+    if rc != 0:
+        raise LibMatError(f"mb_rpd_merge_compact failed ({rc})")
+    return out[: nb.value // 4], out_off[: n.value + 1]
 
 
 def ptr(a):

@@ -3,6 +3,7 @@
 // error: include/common_cuda.h:6-7, src/rpd3d/voronoi.cu:31-37, include/cuda_utils.h:18-25).
 #include <omp.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <new>
 
@@ -233,6 +234,115 @@ int mb_rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rp
   run_streamed(ctx, opts, n_chunks, out, nullptr, 0, nullptr, 0);
   if (host_blob) *host_blob = (*out)->host_blob;
   if (host_cell_offsets) *host_cell_offsets = reinterpret_cast<const long*>((*out)->host_off);
+  MB_CATCH
+}
+
+int mb_rpd_run_incremental(mb_ctx* ctx, const mb_rpd_opts* opts, int to_host, int n_chunks, mb_rpd_result** out,
+                           long* n_affected_tets, const void** host_blob, const long** host_cell_offsets) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && out, MB_ERR_ARG, "null argument");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  const int n_aff = rpd_incremental_select(ctx, opts);  // leaves the affected tets as the context's subset
+  if (n_affected_tets) *n_affected_tets = n_aff;
+  TetMeshDev& M = ctx->mesh;
+  if (n_aff == 0) {  // nothing changed: an empty result (n_sel = 0 would mean "all tets")
+    M.range_first = 0;
+    M.range_count = 0;
+  }
+  struct Restore {  // whatever happens, later runs see the whole mesh again
+    TetMeshDev& M;
+    ~Restore() {
+      M.n_sel = 0;
+      M.range_first = 0;
+      M.range_count = -1;
+    }
+  } restore{M};
+  if (to_host) {
+    run_streamed(ctx, opts, n_chunks, out, nullptr, 0, nullptr, 0);
+    if (host_blob) *host_blob = (*out)->host_blob;
+    if (host_cell_offsets) *host_cell_offsets = reinterpret_cast<const long*>((*out)->host_off);
+  } else {
+    mb_rpd_result* res = new mb_rpd_result();
+    *out = res;
+    res->ctx = ctx;
+    ctx->live_results.push_back(res);
+    ctx->spare_blob.move_to(res->blob);
+    ctx->spare_cell_off.move_to(res->cell_off);
+    try {
+      rpd_run(ctx, opts, res);
+      rpd_sync(ctx, res);
+    } catch (...) {
+      mb_rpd_free(res);
+      *out = nullptr;
+      throw;
+    }
+  }
+  MB_CATCH
+}
+
+// Host-side counterpart of merge_convex_cells (rpd_api.cxx:432-479) on compact records: the previous result with the
+// records of the affected tets replaced by the patch's.  Both inputs are in (tet, site) order, so is the output.
+int mb_rpd_merge_compact(const void* prev_blob, const long* prev_offs, long n_prev, const void* patch_blob,
+                         const long* patch_offs, long n_patch, const int* affected_tets, long n_affected, void* out_blob,
+                         long* out_offs, long* n_out, long* out_bytes) {
+  if (!prev_offs || !patch_offs || !out_offs || (n_prev && !prev_blob) || (n_patch && !patch_blob) || (n_affected && !affected_tets))
+    return MB_ERR_ARG;
+  const unsigned char* pb = static_cast<const unsigned char*>(prev_blob);
+  const unsigned char* qb = static_cast<const unsigned char*>(patch_blob);
+  unsigned char* ob = static_cast<unsigned char*>(out_blob);
+  auto tet_of = [](const unsigned char* b, long off) {
+    int t;
+    memcpy(&t, b + off, 4);
+    return t;
+  };
+  long i = 0, j = 0, a = 0, n = 0, at = 0;
+  out_offs[0] = 0;
+  while (i < n_prev || j < n_patch) {
+    const int tp = i < n_prev ? tet_of(pb, prev_offs[i]) : 0x7fffffff;
+    const int tq = j < n_patch ? tet_of(qb, patch_offs[j]) : 0x7fffffff;
+    while (a < n_affected && affected_tets[a] < tp) a++;
+    if (i < n_prev && a < n_affected && affected_tets[a] == tp) {  // superseded record: skip the whole tet run
+      i++;
+      continue;
+    }
+    if (tq <= tp && j < n_patch) {  // the patch's tets are affected ones: they never tie with a surviving record
+      long j1 = j;
+      while (j1 < n_patch && tet_of(qb, patch_offs[j1]) == tq) j1++;
+      const long bytes = patch_offs[j1] - patch_offs[j];
+      if (ob) memcpy(ob + at, qb + patch_offs[j], (size_t)bytes);
+      for (long k = j; k < j1; k++) out_offs[++n] = at + (patch_offs[k + 1] - patch_offs[j]);
+      at += bytes;
+      j = j1;
+    } else {
+      // a run of surviving records: up to the next affected tet / the next patch tet
+      long i1 = i;
+      const int stop = std::min(a < n_affected ? affected_tets[a] : 0x7fffffff, tq);
+      while (i1 < n_prev && tet_of(pb, prev_offs[i1]) < stop) i1++;
+      if (i1 == i) i1 = i + 1;
+      const long bytes = prev_offs[i1] - prev_offs[i];
+      if (ob) memcpy(ob + at, pb + prev_offs[i], (size_t)bytes);
+      for (long k = i; k < i1; k++) out_offs[++n] = at + (prev_offs[k + 1] - prev_offs[i]);
+      at += bytes;
+      i = i1;
+    }
+  }
+  if (n_out) *n_out = n;
+  if (out_bytes) *out_bytes = at;
+  return MB_OK;
+}
+
+int mb_rpd_fetch_affected_tets(mb_ctx* ctx, int* tet_ids) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx && tet_ids, MB_ERR_ARG, "null argument");
+  MB_REQUIRE(ctx->inc_valid, MB_ERR_STATE, "mb_rpd_run_incremental first");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  const int n = ctx->inc_n_affected;
+  if (n == ctx->inc_n_tet) {
+    for (int i = 0; i < n; i++) tet_ids[i] = i;  // first run / after a reset: every tet
+  } else if (n > 0) {
+    MB_CUDA(cudaMemcpyAsync(tet_ids, ctx->inc_affected.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   MB_CATCH
 }
 

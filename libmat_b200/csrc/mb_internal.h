@@ -289,6 +289,12 @@ struct mb_ctx {
   DevBuf<float4> grid_site4;
   DevBuf<float> grid_wmax0, grid_wmax1;
   float site_bbox[6] = {0, 0, 0, 0, 0, 0};  // min xyz, max xyz of the site centres (host-computed)
+  // incremental recompute (mb_rpd_run_incremental): the candidate lists and sites of the previous run
+  DevBuf<int> inc_cand_pad, inc_cand_cnt, inc_affected, inc_flag, inc_pos;
+  DevBuf<float4> inc_site4;
+  DevBuf<unsigned> inc_flags;
+  int inc_n_tet = 0, inc_n_site = 0, inc_kcap = 0, inc_n_affected = 0;
+  bool inc_valid = false;
   // result buffers recycled between runs (cudaMalloc / cudaFree synchronise the device): a freed
   // result parks its blob / offset buffers here and the next run takes them back
   DevBuf<uint32_t> spare_blob;
@@ -306,6 +312,9 @@ void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res);
 void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_result* res, void* dst_blob,
                      size_t dst_cap_bytes, long long* dst_off, size_t dst_cap_cells);
 void rpd_sync(mb_ctx* ctx, mb_rpd_result* res);
+// f2 / config 5: finds the tets whose cells can have changed since the previous incremental run and leaves them as the
+// context's tet subset (returns their number; all tets on the first call or after a mesh / capacity change)
+int rpd_incremental_select(mb_ctx* ctx, const mb_rpd_opts* opts);
 void rpd_fetch_flags(mb_ctx* ctx, mb_rpd_result* res, unsigned char* cell_flag, unsigned char* pair_flag);
 void rpd_emit(mb_ctx* ctx, mb_rpd_result* res, int max_surf_fid);
 void rpd_topology(mb_ctx* ctx, mb_rpd_result* res);  // K6: cell / facet components + Euler sums per power cell

@@ -936,6 +936,105 @@ static void run_prologue(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* re
   for (int i = 0; i < 10; i++) res->hist[i] = 0;
 }
 
+// =============================================================================================
+// f2 / config 5: incremental recompute without neighbour rings.
+//   reference: RPD3D_GPU::calculate_partial (src/rpd3d_api/rpd_api.cxx:147-313) rebuilds the CGAL regular triangulation,
+//   takes the changed spheres + their 1-ring (+ 2-ring as clip-only sites, triangulation.cxx:442-549), recomputes the
+//   tets of those spheres' previous cells (load_partial_tet_given_spheres :482-535) and merges (:432-479).
+//   here: the cells of a tet are a function of the tet and of its candidate list (site ids + their centres / weights /
+//   flags) -- nothing else.  K2 costs a fraction of K3, so the candidate lists of ALL tets are recomputed with the new
+//   sites and compared with the previous run's: a tet is AFFECTED iff its list differs or lists a changed site.  That
+//   set is exact (every other tet's records are bit-for-bit those of the previous run) and needs no triangulation.
+// =============================================================================================
+__global__ void k_inc_affected(int n_tet, int kcap, const int* __restrict__ cnt, const int* __restrict__ pad,
+                               const int* __restrict__ pcnt, const int* __restrict__ ppad,
+                               const float4* __restrict__ site4, const unsigned* __restrict__ flags,
+                               const float4* __restrict__ psite4, const unsigned* __restrict__ pflags, int n_prev_site,
+                               int* __restrict__ flag_out) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= n_tet) return;
+  const int n = cnt[t];
+  bool diff = n != pcnt[t];
+  for (int i = lane; i < n && !diff; i += 32) {
+    const int s = pad[(size_t)t * kcap + i];
+    if (s != ppad[(size_t)t * kcap + i] || s >= n_prev_site) {
+      diff = true;
+    } else {
+      const float4 a = site4[s], b = psite4[s];
+      diff = __float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y) ||
+             __float_as_uint(a.z) != __float_as_uint(b.z) || __float_as_uint(a.w) != __float_as_uint(b.w) ||
+             flags[s] != pflags[s];
+    }
+  }
+  const bool any = __any_sync(0xffffffffu, diff);
+  if (lane == 0) flag_out[t] = any ? 1 : 0;
+}
+
+__global__ void k_inc_compact(int n_tet, const int* __restrict__ flag, const int* __restrict__ pos, int* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_tet && flag[t]) out[pos[t]] = t;
+}
+
+int rpd_incremental_select(mb_ctx* ctx, const mb_rpd_opts* opts) {
+  TetMeshDev& M = ctx->mesh;
+  SitesDev& S = ctx->sites;
+  cudaStream_t s = ctx->stream;
+  MB_REQUIRE(M.n_tet > 0 && S.n_site > 0, MB_ERR_STATE, "mesh and sites first");
+  MB_REQUIRE(!S.given, MB_ERR_STATE, "the incremental recompute runs in grid-kNN mode (upload the sites without site_knn)");
+  M.n_sel = 0;
+  M.range_first = 0;
+  M.range_count = -1;
+  const int n_tet = M.n_tet;
+  // candidate lists of ALL tets with the new sites (K1 + K2)
+  ctx->counters.reserve(1);
+  MB_CUDA(cudaMemsetAsync(ctx->counters.p, 0, sizeof(RpdCounters), s));
+  ctx->tet_cnt.reserve((size_t)n_tet + 1);
+  const GridDev G = grid_build(ctx);
+  const TetSpan all = {0, n_tet, nullptr};
+  grid_candidates(ctx, G, all, opts ? opts->grid_k : 0);
+  const int kcap = ctx->cand_kcap;
+  const bool have_prev = ctx->inc_valid && ctx->inc_n_tet == n_tet && ctx->inc_kcap == kcap;
+  int n_aff = n_tet;
+  ctx->inc_affected.reserve((size_t)n_tet + 1);
+  if (have_prev) {
+    ctx->inc_flag.reserve((size_t)n_tet + 1);
+    ctx->inc_pos.reserve((size_t)n_tet + 1);
+    ctx->n_launches += 4;
+    k_inc_affected<<<(unsigned)(((size_t)n_tet * 32 + 255) / 256), 256, 0, s>>>(
+        n_tet, kcap, ctx->cand_cnt.p, ctx->cand_pad.p, ctx->inc_cand_cnt.p, ctx->inc_cand_pad.p, S.site4.p, S.flags.p,
+        ctx->inc_site4.p, ctx->inc_flags.p, ctx->inc_n_site, ctx->inc_flag.p);
+    MB_CUDA(cudaMemsetAsync(ctx->inc_flag.p + n_tet, 0, sizeof(int), s));
+    exclusive_scan<int>(ctx, ctx->inc_flag.p, ctx->inc_pos.p, (long long)n_tet + 1);
+    k_inc_compact<<<(n_tet + 255) / 256, 256, 0, s>>>(n_tet, ctx->inc_flag.p, ctx->inc_pos.p, ctx->inc_affected.p);
+    MB_CUDA(cudaGetLastError());
+    MB_CUDA(cudaMemcpyAsync(&n_aff, ctx->inc_pos.p + n_tet, sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  // this run's lists and sites become the reference point of the next one
+  ctx->inc_cand_pad.reserve((size_t)n_tet * kcap);
+  ctx->inc_cand_cnt.reserve((size_t)n_tet + 1);
+  ctx->inc_site4.reserve((size_t)S.n_site);
+  ctx->inc_flags.reserve((size_t)S.n_site);
+  // (the comparison above has been enqueued before these copies on the same stream)
+  MB_CUDA(cudaMemcpyAsync(ctx->inc_cand_pad.p, ctx->cand_pad.p, sizeof(int) * (size_t)n_tet * kcap, cudaMemcpyDeviceToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(ctx->inc_cand_cnt.p, ctx->cand_cnt.p, sizeof(int) * (size_t)n_tet, cudaMemcpyDeviceToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(ctx->inc_site4.p, S.site4.p, sizeof(float4) * (size_t)S.n_site, cudaMemcpyDeviceToDevice, s));
+  MB_CUDA(cudaMemcpyAsync(ctx->inc_flags.p, S.flags.p, sizeof(unsigned) * (size_t)S.n_site, cudaMemcpyDeviceToDevice, s));
+  MB_CUDA(cudaStreamSynchronize(s));
+  ctx->inc_n_tet = n_tet;
+  ctx->inc_n_site = S.n_site;
+  ctx->inc_kcap = kcap;
+  ctx->inc_valid = true;
+  ctx->inc_n_affected = n_aff;
+  if (have_prev) {
+    // the affected tets become the context's subset (device-resident list, ascending)
+    M.tet_sel.reserve((size_t)std::max(n_aff, 1));
+    if (n_aff > 0) MB_CUDA(cudaMemcpyAsync(M.tet_sel.p, ctx->inc_affected.p, sizeof(int) * (size_t)n_aff, cudaMemcpyDeviceToDevice, s));
+    MB_CUDA(cudaStreamSynchronize(s));
+    M.n_sel = n_aff;
+  }
+  return n_aff;
+}
+
 void rpd_run(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res) {
   int t_first, t_count;
   run_prologue(ctx, opts, res, t_first, t_count);

@@ -72,3 +72,43 @@ class RpdLoop:
             self.last.free()
         self.last = res
         return res, dt
+
+    def step_incremental(self, sites: synth.Sites, to_host=False, **opts):
+        """upload the sites and clip only the AFFECTED tets (mb_rpd_run_incremental: the tets whose candidate list
+        changed since the previous incremental step -- exact, no neighbour rings, no CGAL).  Returns
+        (RpdResult of the affected tets, ascending affected tet ids, seconds end to end); merge the patch into the
+        previous result with capi.merge_compact (the counterpart of merge_convex_cells, rpd_api.cxx:432-479)."""
+        ctx = self.ctx
+        t0 = time.perf_counter()
+        ctx.upload_sites(sites.site_soa, sites.weights, sites.flags)
+        res, tets = ctx.run_incremental(to_host=to_host, **opts)
+        dt = time.perf_counter() - t0
+        if self.last is not None:
+            self.last.free()
+        self.last = res
+        return res, tets, dt
+
+
+def site_rings(pair_site, pair_neigh, seeds, n_site: int, depth: int = 2):
+    """1-ring / 2-ring of `seeds` in the restricted power diagram, from the half-plane pairs K6 emits
+    (mb_rpd_fetch_topology: pair_site / pair_neigh = every (site, neighbour) sharing a bisector facet inside the mesh)
+    -- the neighbour source that replaces get_RT_partial_spheres_and_neighbors (triangulation.cxx:442-549) for callers
+    that want the reference's N + 1-ring + 2-ring site selection (rpd_api.cxx:54-63).  Returns a list of id arrays,
+    ring 0 = the seeds."""
+    adj = [[] for _ in range(n_site)]
+    for s, n in zip(np.asarray(pair_site).tolist(), np.asarray(pair_neigh).tolist()):
+        if 0 <= n < n_site:
+            adj[s].append(n)
+    seen = set(int(s) for s in seeds)
+    rings = [np.array(sorted(seen), np.int64)]
+    frontier = set(seen)
+    for _ in range(depth):
+        nxt = set()
+        for s in frontier:
+            for n in adj[s]:
+                if n not in seen:
+                    nxt.add(n)
+        seen |= nxt
+        rings.append(np.array(sorted(nxt), np.int64))
+        frontier = nxt
+    return rings

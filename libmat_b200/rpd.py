@@ -269,6 +269,19 @@ class Context:
         self._check(self.lib.mb_rpd_run_to_host(self._ctx, C.byref(opts), int(n_chunks), C.byref(h), C.byref(bp), C.byref(op)))
         return RpdResult(self, h, host_ptrs=(bp.value, op.value))
 
+    def run_incremental(self, to_host=False, n_chunks=0, lanes_per_cell=0, grid_k=0, lean=0):
+        """mb_rpd_run_incremental: clips only the tets whose candidate list changed since the previous incremental
+        run.  Returns (RpdResult of the affected tets, ascending affected tet ids)."""
+        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), 0, 0, int(lean) if to_host else 0)
+        h, bp, op = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        na = C.c_long(0)
+        self._check(self.lib.mb_rpd_run_incremental(self._ctx, C.byref(opts), int(bool(to_host)), int(n_chunks), C.byref(h),
+                                                    C.byref(na), C.byref(bp), C.byref(op)))
+        tets = np.zeros(na.value, np.int32)
+        if na.value:
+            self._check(self.lib.mb_rpd_fetch_affected_tets(self._ctx, ptr(tets)))
+        return RpdResult(self, h, host_ptrs=(bp.value, op.value) if to_host else None), tets
+
     def run_to_sink(self, sink_blob_ptr: int, cap_bytes: int, sink_off_ptr: int, cap_cells: int, n_chunks=0,
                     lanes_per_cell=0, grid_k=0, grid_candidates=False, lean=False) -> RpdResult:
         """streamed run into caller memory (mb_rpd_run_to_sink): pinned / registered host memory, device memory

@@ -80,3 +80,33 @@ def test_product_never_imports_oracle():
             assert not bad.search(open(path).read()), f"{path} reaches into oracle/"
     for path in glob.glob(os.path.join(ROOT, "include", "*")):
         assert not bad.search(open(path).read()), f"{path} reaches into oracle/"
+
+
+def test_merge_compact_host_helper():
+    """mb_rpd_merge_compact (no GPU): previous records with the affected tets' runs replaced by the patch"""
+    import numpy as np
+    from libmat_b200 import capi
+    rng = np.random.default_rng(1)
+
+    def make(tc):
+        blob, offs = [], [0]
+        for t, c in tc:
+            for k in range(c):
+                n = int(rng.integers(5, 12))
+                blob += [t, 100 * t + k] + list(rng.integers(0, 1000, n - 2))
+                offs.append(offs[-1] + 4 * n)
+        return np.array(blob, np.uint32), np.array(offs, np.int64)
+
+    def split(b, o):
+        return [tuple(b[o[i] // 4:o[i + 1] // 4].tolist()) for i in range(len(o) - 1)]
+
+    pb, po = make([(t, int(rng.integers(1, 4))) for t in range(12)])
+    aff = np.array([0, 2, 5, 9, 11], np.int32)
+    qb, qo = make([(0, 2), (2, 1), (5, 3), (11, 1)])  # tet 9 loses all its cells
+    ob, oo = capi.merge_compact(pb, po, qb, qo, aff)
+    want = []
+    for t in range(12):
+        want += [r for r in (split(qb, qo) if t in aff else split(pb, po)) if r[0] == t]
+    assert split(ob, oo) == want
+    ob, oo = capi.merge_compact(pb, po, np.zeros(0, np.uint32), np.zeros(1, np.int64), np.zeros(0, np.int32))
+    assert np.array_equal(ob, pb) and np.array_equal(oo, po)

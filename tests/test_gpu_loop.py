@@ -76,3 +76,53 @@ def test_loop_streamed_step_equals_device_step(synth):
         b2, o2 = res2.host_compact()
         assert np.array_equal(want[0], b2) and np.array_equal(want[1], o2)
     c.close()
+
+
+def test_incremental_run_equals_full_recompute(O, synth):
+    """mb_rpd_run_incremental: the records of the affected tets merged into the previous result (mb_rpd_merge_compact)
+    are byte-identical to a full recompute, iteration after iteration; unaffected tets really are untouched; an
+    iteration without changes affects nothing"""
+    from libmat_b200 import capi
+    from libmat_b200.loop import RpdLoop, evolve_sites, site_rings
+    from libmat_b200.rpd import Context
+    mesh = synth.make_ball_mesh(12)
+    sites = synth.make_spheres(1500)
+    a, b = Context(0), Context(0)
+    loop = RpdLoop(a, mesh)
+    b.set_mesh(mesh)
+    res, tets, _ = loop.step_incremental(sites)
+    assert len(tets) == mesh.n_tet  # first call: everything
+    blob, offs = res.compact()
+    blob = blob[: res.compact_bytes // 4].copy()
+    fractions = []
+    for it in range(4):
+        prev_sites = sites
+        sites, changed = evolve_sites(sites, it, frac_insert=0.003, frac_update=0.003)
+        res, tets, _ = loop.step_incremental(sites, to_host=(it % 2 == 1), n_chunks=2)
+        fractions.append(len(tets) / mesh.n_tet)
+        assert 0 < len(tets) < mesh.n_tet and (np.diff(tets) > 0).all()
+        pb, po = res.host_compact() if it % 2 == 1 else res.compact()
+        pb = pb[: res.compact_bytes // 4]
+        assert np.isin(pb[po[:-1] // 4].astype(np.int64), tets).all()
+        blob, offs = capi.merge_compact(blob, offs, pb, po, tets)
+        full = b.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
+        fb, fo = full.compact()
+        assert np.array_equal(offs, fo) and np.array_equal(blob, fb[: full.compact_bytes // 4]), it
+        # the tets of the changed spheres' previous / new cells are among the affected ones
+        recs = full.records()
+        touched = np.unique(recs["tet_id"][np.isin(recs["voro_id"], changed)])
+        assert np.isin(touched, tets).all()
+        full.free()
+    assert max(fractions) < 0.6
+    # nothing changed -> nothing affected, empty patch
+    res, tets, _ = loop.step_incremental(sites)
+    assert len(tets) == 0 and res.n_cells == 0
+    # the neighbour rings of the changed spheres from K6's half-plane pairs (the reference's N + 1-ring + 2-ring)
+    full = b.compute_clipped_voro_diagram(sites.site_soa, sites.weights, sites.flags, None, 0)
+    full.emit(mesh.n_surf_faces - 1)
+    tp = full.topology()
+    rings = site_rings(tp["pair_site"], tp["pair_neigh"], changed, sites.n_site)
+    assert len(rings) == 3 and len(rings[1]) > 0 and len(rings[2]) > 0
+    a.close()
+    b.close()
+    print("incremental: affected-tet fractions per iteration", [round(f, 3) for f in fractions])
