@@ -328,6 +328,16 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
     k_ms = float(np.mean(ms))
     b_alg = n_samples * (12 + 8 + 8) + n_prims * 12 + len(d.spheres) * 16
     peak, peak_src = hbm_peak()
+    # secondary, compute roofline: algorithmic FP32 flops (~12 per sphere, ~60 per cone, ~300 per
+    # slab evaluation incl. its share of boundary-cone fallbacks) against the FFMA peak measured on this device
+    try:
+        fp32_peak, fp64_peak = ctx.measure_peaks()
+    except Exception:  # noqa: BLE001
+        fp32_peak = fp64_peak = None
+    n_sl_eval = int((d.prims[:, 0] != -1).sum())
+    n_co_eval = int(((d.prims[:, 0] == -1) & (d.prims[:, 1] != -1)).sum())
+    n_sp_eval = n_prims - n_sl_eval - n_co_eval
+    flops_alg = 300.0 * n_sl_eval + 60.0 * n_co_eval + 12.0 * n_sp_eval
     # e2e: the reference-facing call with host buffers (7 H2D + kernel + 2 D2H, like dist2mat.cu:287-307)
     res_h = torch.empty(n_samples, dtype=torch.float32).pin_memory()
     cid_h = torch.empty(n_samples, dtype=torch.int32).pin_memory()
@@ -347,7 +357,13 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
            "roofline": {"kernel": "k_dist2mat", "bound": "hbm", "achieved": b_alg / (k_ms * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": b_alg / (k_ms * 1e-3) / 1e9 / peak,
                         "traffic": measured_traffic("k_dist2mat_q", f"d2m-{n_samples}")[0],
-                        "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg},
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
+                        "compute": None if not fp32_peak else {
+                            "bound": "fp32 issue", "achieved": flops_alg / (k_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                            "frac": flops_alg / (k_ms * 1e-3) / 1e12 / fp32_peak, "fp64_peak_tflops": fp64_peak,
+                            "algorithmic_flops_per_launch": flops_alg,
+                            "note": "peaks measured on this device with FFMA / DFMA loops (mb_measure_peaks); flops per "
+                                    "primitive evaluation: slab 300, cone 60, sphere 12"}},
            "e2e": {"value": n_samples / t_e2e, "unit": "queries/s",
                    "h2d_bytes_per_step": int(sum(x.nbytes for x in hp)), "d2h_bytes_per_step": int(8 * n_samples)}}
     # ---- f3: the candidate lists built on the device (mb_dist2mat_by_face): the caller hands over what the reference
@@ -904,6 +920,7 @@ def main():
                          "frac": achieved / peak, "traffic": clip_traffic, "traffic_source": clip_traffic_src,
                          "ncu_pipes": measured_pipes("k_clip", f"{args.workload}-{mode}") if world == 1 else None,
                          "exact_predicate_fallbacks_per_step": int(n_exact_last),
+                         "measured_peaks_tflops": dict(zip(("fp32", "fp64"), ctx.measure_peaks())) if world == 1 else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_alg,
                          "note": "latency-bound irregular kernel (not bandwidth-bound: ncu_pipes); see DESIGN.md section 5 and profiles/"},

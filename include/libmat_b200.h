@@ -84,6 +84,9 @@ const char* mb_version(void);
 #define MB_FILTER_BOUND_F64 1.2466136531027298e-13
 #define MB_FILTER_BOUND_F32 6.6876506e-05f
 void mb_predicate_bounds(double* bound_f64, float* bound_f32);
+/* measured FFMA / DFMA throughput of the device in TFLOP/s (instrumentation: the compute roofline bench.py reports
+ * for the issue-bound kernels next to the HBM one) */
+int mb_measure_peaks(mb_ctx* ctx, double* fp32_tflops, double* fp64_tflops);
 /* number of CUDA kernels this context has launched since mb_create (instrumentation) */
 int mb_launch_count(const mb_ctx* ctx, unsigned long long* n_launches);
 

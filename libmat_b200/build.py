@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmat_b200.so")
-SOURCES = ["capi.cu", "rpd_kernels.cu", "rpd_emit.cu", "rpd_topo.cu", "dist2mat_kernels.cu", "dist2mat_lists.cu", "bgeo.cu"]
+SOURCES = ["capi.cu", "rpd_kernels.cu", "rpd_emit.cu", "rpd_topo.cu", "dist2mat_kernels.cu", "dist2mat_lists.cu", "peaks.cu", "bgeo.cu"]
 HEADERS = ["mb_internal.h", "rpd_device.cuh", "rpd_clip.cuh", "rpd_clip2.cuh", "rpd_grid.cuh",
            os.path.join("..", "..", "include", "libmat_b200.h")]
 
@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 # dist2mat is pinned against the reference's DEVICE build (nvcc's default FMA contraction on the reference's own
 # expressions): its slab solve is ill-conditioned, and only the same contraction reproduces the same roots
 # (tests/test_gpu_reference_build.py).  The RPD sources stay non-fused (explicit __f*_rn; host-build parity).
-FMAD_SOURCES = {"dist2mat_kernels.cu"}
+FMAD_SOURCES = {"dist2mat_kernels.cu", "peaks.cu"}
 
 
 def needs_build() -> bool:

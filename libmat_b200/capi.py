@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libmat_b200.so")
 
 # every symbol include/libmat_b200.h declares
 SYMBOLS = [
-    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_id_base", "mb_set_tet_subset",
+    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_measure_peaks", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_id_base", "mb_set_tet_subset",
     "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_run_to_host", "mb_rpd_run_incremental", "mb_rpd_fetch_affected_tets", "mb_rpd_merge_compact", "mb_rpd_run_to_sink", "mb_rpd_expand_compact", "mb_rpd_spans", "mb_sink_create", "mb_sink_destroy", "mb_sink_open",
     "mb_sink_close", "mb_host_register", "mb_host_unregister", "mb_copy_to_host", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_clip_passes", "mb_rpd_flagged", "mb_rpd_fetch_flags", "mb_debug_set_pair_hint", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     lib.mb_rpd_fetch_pairs.argtypes = [vp, vp, vp, vp]
     lib.mb_set_stream.argtypes = [vp, vp]
     lib.mb_launch_count.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    lib.mb_measure_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.mb_rpd_compact_bytes.argtypes = [vp, C.POINTER(C.c_long)]
     lib.mb_rpd_fetch_compact.argtypes = [vp, vp, vp]
     lib.mb_rpd_site_volumes.argtypes = [vp, vp, vp]

@@ -547,6 +547,14 @@ int mb_rpd_kernel_ms(const mb_rpd_result* res, float ms[4]) {
   return MB_OK;
 }
 
+int mb_measure_peaks(mb_ctx* ctx, double* fp32_tflops, double* fp64_tflops) {
+  MB_TRY(ctx)
+  MB_REQUIRE(ctx, MB_ERR_ARG, "null context");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  peaks_measure(ctx, fp32_tflops, fp64_tflops);
+  MB_CATCH
+}
+
 int mb_launch_count(const mb_ctx* ctx, unsigned long long* n_launches) {
   if (!ctx || !n_launches) return MB_ERR_ARG;
   *n_launches = ctx->n_launches;

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -331,6 +332,7 @@ void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* sampl
                 const unsigned* offset, const unsigned* count, const int* prims, long n_prims);
 void d2m_run(mb_ctx* ctx, float* kernel_ms);
 void d2m_fetch(mb_ctx* ctx, float* result, int* closest_id, unsigned char* tie_flag);
+void peaks_measure(mb_ctx* ctx, double* fp32_tflops, double* fp64_tflops);  // peaks.cu
 // ---- dist2mat_lists.cu (f3) ----------------------------------------------------------------------
 void d2m_set_medial_mesh(mb_ctx* ctx, const float* spheres, int n_sph, const int* faces, int n_faces, const int* edges, int n_edges);
 void d2m_set_face_sites(mb_ctx* ctx, const int* fid_site_rows, long n_rows, int n_fid);

@@ -189,6 +189,12 @@ class Context:
         """run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)"""
         self._check(self.lib.mb_set_stream(self._ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
 
+    def measure_peaks(self):
+        """(FP32 TFLOP/s, FP64 TFLOP/s) measured with FFMA / DFMA loops on this device"""
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self.lib.mb_measure_peaks(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def launch_count(self) -> int:
         n = C.c_ulonglong(0)
         self._check(self.lib.mb_launch_count(self._ctx, C.byref(n)))
