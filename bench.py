@@ -938,7 +938,11 @@ def main():
                              % (e2e_chunks, ", slabs first-touched on the GPU's NUMA node" if getattr(sink_host, "numa_pinned", False) else "")
                              if sink_host is not None else "mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run + gather + D2H on rank 0"),
                     "stage_ms": {"set_tetmesh": 1e3 * e2e_parts[0] / e2e_steps, "upload_sites": 1e3 * e2e_parts[1] / e2e_steps,
-                                 "run_to_host": 1e3 * e2e_parts[2] / e2e_steps}},
+                                 "run_to_host": 1e3 * e2e_parts[2] / e2e_steps},
+                    # achieved device->host rate over the streamed run: per rank (its own PCIe link) and summed over the
+                    # box (N > 1: the ranks share the host's PCIe root ports / memory controllers)
+                    "d2h_gbs": {"per_rank": d2h / max(world, 1) / (e2e_parts[2] / e2e_steps) / 1e9,
+                                "box_aggregate": d2h / (e2e_parts[2] / e2e_steps) / 1e9}},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -101,6 +101,16 @@ int mb_launch_count(const mb_ctx* ctx, unsigned long long* n_launches);
 int mb_set_tetmesh(mb_ctx* ctx, const float* verts_aos, int n_vert, const int* idx_aos, int n_tet,
                    const int* v_adjs, const int* e_adjs_dense, const int* e_adj6,
                    const int* f_adjs, const int* f_ids);
+/* The mesh adjacency arrays mb_set_tetmesh takes, computed from the tet indices alone: the sparse counterpart of
+ * load_tet_adj_info (src/IO/IO_CXX/io.cxx:238-335), whose dense n_vert (n_vert + 1) / 2 + 1 edge table (io.cxx:264)
+ * is 2.6 GB at 36 k vertices and overflows int at 46 341.  Host code, no context, no GPU.
+ *   v_adjs int[n_vert], e_adj6 int[6 * n_tet] (the e_adj6 form of mb_set_tetmesh), f_adjs / f_ids int[4 * n_tet] in
+ *   tet_faces_lvid order; any output may be NULL.  f_ids: a boundary face gets boundary_sf_fids[k], k = its rank in
+ *   (tet, local face) scan order (the surface-mesh facet id the reference finds through tet_vs2sf_fids, :306-313),
+ *   or k itself when boundary_sf_fids is NULL; an interior face gets n_sf_facets + the rank of its first visit in
+ *   scan order (:314-325).  *n_boundary_faces receives the number of boundary faces. */
+int mb_tet_adjacency(const int* idx_aos, int n_tet, int n_vert, const int* boundary_sf_fids, int n_sf_facets, int* v_adjs,
+                     int* e_adj6, int* f_adjs, int* f_ids, int* n_boundary_faces);
 /* restrict subsequent mb_rpd3d calls to tets [first, first+count) (multi-GPU tet shards). */
 int mb_set_tet_range(mb_ctx* ctx, int first, int count);
 /* the tet ids stored in the result become (index in the uploaded arrays + base): a rank of a multi-GPU job

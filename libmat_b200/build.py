@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmat_b200.so")
-SOURCES = ["capi.cu", "rpd_kernels.cu", "rpd_emit.cu", "rpd_topo.cu", "dist2mat_kernels.cu", "dist2mat_lists.cu", "peaks.cu", "bgeo.cu"]
+SOURCES = ["capi.cu", "rpd_kernels.cu", "rpd_emit.cu", "rpd_topo.cu", "dist2mat_kernels.cu", "dist2mat_lists.cu", "peaks.cu", "adjacency.cu", "bgeo.cu"]
 HEADERS = ["mb_internal.h", "rpd_device.cuh", "rpd_clip.cuh", "rpd_clip2.cuh", "rpd_grid.cuh",
            os.path.join("..", "..", "include", "libmat_b200.h")]
 

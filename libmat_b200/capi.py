@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libmat_b200.so")
 
 # every symbol include/libmat_b200.h declares
 SYMBOLS = [
-    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_measure_peaks", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_id_base", "mb_set_tet_subset",
+    "mb_create", "mb_destroy", "mb_last_error", "mb_version", "mb_predicate_bounds", "mb_tet_adjacency", "mb_measure_peaks", "mb_launch_count", "mb_set_stream", "mb_rpd_fetch_pairs", "mb_set_tetmesh", "mb_set_tet_range", "mb_set_tet_id_base", "mb_set_tet_subset",
     "mb_rpd3d", "mb_rpd_upload_sites", "mb_rpd_run", "mb_rpd_run_to_host", "mb_rpd_run_incremental", "mb_rpd_fetch_affected_tets", "mb_rpd_merge_compact", "mb_rpd_run_to_sink", "mb_rpd_expand_compact", "mb_rpd_spans", "mb_sink_create", "mb_sink_destroy", "mb_sink_open",
     "mb_sink_close", "mb_host_register", "mb_host_unregister", "mb_copy_to_host", "mb_rpd_sync", "mb_rpd_free", "mb_rpd_count",
     "mb_rpd_status_histogram", "mb_rpd_clip_passes", "mb_rpd_flagged", "mb_rpd_fetch_flags", "mb_debug_set_pair_hint", "mb_rpd_stats", "mb_rpd_kernel_ms", "mb_rpd_fetch_records", "mb_rpd_compact_bytes",
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     lib.mb_rpd_fetch_pairs.argtypes = [vp, vp, vp, vp]
     lib.mb_set_stream.argtypes = [vp, vp]
     lib.mb_launch_count.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    lib.mb_tet_adjacency.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int)]
     lib.mb_measure_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.mb_rpd_compact_bytes.argtypes = [vp, C.POINTER(C.c_long)]
     lib.mb_rpd_fetch_compact.argtypes = [vp, vp, vp]
@@ -157,6 +158,30 @@ def bgeo_write_records(records: np.ndarray, path: str, max_sf_fid: int, is_bound
     if rc != 0:
         raise LibMatError(f"mb_bgeo_write_records failed ({rc})")
     return a.value, b.value
+
+
+def tet_adjacency(indices, n_vert, boundary_sf_fids=None, n_sf_facets=None):
+    """mb_tet_adjacency: (v_adjs, e_adj6 [n_tet,6], f_adjs [n_tet,4], f_ids [n_tet,4], n_boundary_faces) from the tet
+    indices -- load_tet_adj_info (io.cxx:238-335) without the dense edge table; host code"""
+    lib = load()
+    idx = np.ascontiguousarray(indices, np.int32).reshape(-1, 4)
+    n_tet = len(idx)
+    v = np.zeros(n_vert, np.int32)
+    e6 = np.zeros((n_tet, 6), np.int32)
+    fa = np.zeros((n_tet, 4), np.int32)
+    fi = np.zeros((n_tet, 4), np.int32)
+    nb = C.c_int(0)
+    bs = None if boundary_sf_fids is None else np.ascontiguousarray(boundary_sf_fids, np.int32)
+    if n_sf_facets is None:
+        # default numbering: boundary faces 0..n_b-1, interior faces after them
+        rc = lib.mb_tet_adjacency(ptr(idx), n_tet, int(n_vert), None, 0, None, None, ptr(fa), None, C.byref(nb))
+        if rc != 0:
+            raise LibMatError(f"mb_tet_adjacency failed ({rc})")
+        n_sf_facets = nb.value
+    rc = lib.mb_tet_adjacency(ptr(idx), n_tet, int(n_vert), ptr(bs), int(n_sf_facets), ptr(v), ptr(e6), ptr(fa), ptr(fi), C.byref(nb))
+    if rc != 0:
+        raise LibMatError(f"mb_tet_adjacency failed ({rc})")
+    return v, e6, fa, fi, nb.value
 
 
 def merge_compact(prev_blob, prev_offs, patch_blob, patch_offs, affected_tets):

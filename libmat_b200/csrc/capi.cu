@@ -547,6 +547,20 @@ int mb_rpd_kernel_ms(const mb_rpd_result* res, float ms[4]) {
   return MB_OK;
 }
 
+int mb_tet_adjacency(const int* idx_aos, int n_tet, int n_vert, const int* boundary_sf_fids, int n_sf_facets, int* v_adjs,
+                     int* e_adj6, int* f_adjs, int* f_ids, int* n_boundary_faces) {
+  try {
+    if (!idx_aos || n_tet <= 0 || n_vert <= 0) return MB_ERR_ARG;
+    tet_adjacency(idx_aos, n_tet, n_vert, boundary_sf_fids, n_sf_facets, v_adjs, e_adj6, f_adjs, f_ids, n_boundary_faces);
+  } catch (const MbError& e) {
+    fprintf(stderr, "[libmat_b200] mb_tet_adjacency: %s\n", e.msg.c_str());
+    return e.code;
+  } catch (...) {
+    return MB_ERR_NOMEM;
+  }
+  return MB_OK;
+}
+
 int mb_measure_peaks(mb_ctx* ctx, double* fp32_tflops, double* fp64_tflops) {
   MB_TRY(ctx)
   MB_REQUIRE(ctx, MB_ERR_ARG, "null context");

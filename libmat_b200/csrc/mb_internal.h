@@ -333,6 +333,8 @@ void d2m_upload(mb_ctx* ctx, const float* spheres, int n_sph, const float* sampl
 void d2m_run(mb_ctx* ctx, float* kernel_ms);
 void d2m_fetch(mb_ctx* ctx, float* result, int* closest_id, unsigned char* tie_flag);
 void peaks_measure(mb_ctx* ctx, double* fp32_tflops, double* fp64_tflops);  // peaks.cu
+void tet_adjacency(const int* idx, int n_tet, int n_vert, const int* boundary_sf_fids, int n_sf_facets, int* v_adjs,
+                   int* e_adj6, int* f_adjs, int* f_ids, int* n_boundary);  // adjacency.cu (host code)
 // ---- dist2mat_lists.cu (f3) ----------------------------------------------------------------------
 void d2m_set_medial_mesh(mb_ctx* ctx, const float* spheres, int n_sph, const int* faces, int n_faces, const int* edges, int n_edges);
 void d2m_set_face_sites(mb_ctx* ctx, const int* fid_site_rows, long n_rows, int n_fid);

@@ -1089,6 +1089,7 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     }
   }
   cudaStream_t cs = ctx->copy_stream;
+  bool decreasing = false;
   if (n_chunks <= 0) {
     // automatic span count.  Host destinations: the PCIe copy is the long pole, so spans are short (~32k tets) and
     // the first bytes leave early.  Device destinations (this GPU or a peer over NVLink): the copy is ~10x faster
@@ -1100,7 +1101,12 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
       dev_dst = cudaPointerGetAttributes(&pa, dst_blob) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
       (void)cudaGetLastError();
     }
-    n_chunks = dev_dst ? std::max(1, std::min(8, (t_count + 98303) / 98304)) : std::max(1, std::min(32, (t_count + 32767) / 32768));
+    // Only the LAST span's copy is exposed, so device destinations use a few spans of DECREASING size (4 : 3 : 2 : 1
+    // when there are four): every copy still hides behind the next, shorter span's kernels and the exposed tail is
+    // a tenth of the result.
+    decreasing = dev_dst;
+    const int per_span = lean ? 65536 : 32768;  // slim / lean records: the kernels are the long pole, fewer spans
+    n_chunks = dev_dst ? std::max(1, std::min(4, (t_count + 49151) / 49152)) : std::max(1, std::min(32, (t_count + per_span - 1) / per_span));
   }
   n_chunks = std::max(1, std::min(n_chunks, std::max(1, t_count)));
   const bool grid_cands = !ctx->sites.given || (opts && opts->grid_candidates);
@@ -1120,8 +1126,14 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     MB_CUDA(cudaMemcpyAsync(dst_off, &hs->zero, sizeof(long long), cudaMemcpyDefault, cs));
   }
   for (int c = 0; c < n_chunks; c++) {
-    const int c_first = (int)((long long)t_count * c / n_chunks);
-    const int c_count = (int)((long long)t_count * (c + 1) / n_chunks) - c_first;
+    // span c = tets [cut(c), cut(c+1)): equal sizes, or weights n, n-1, ..., 1 (cut(c) = t_count * (1 - tri(n-c)/tri(n)))
+    auto cut = [&](int k) -> long long {
+      if (!decreasing) return (long long)t_count * k / n_chunks;
+      const long long tri_n = (long long)n_chunks * (n_chunks + 1) / 2, rest = (long long)(n_chunks - k) * (n_chunks - k + 1) / 2;
+      return (long long)t_count * (tri_n - rest) / tri_n;
+    };
+    const int c_first = (int)cut(c);
+    const int c_count = (int)cut(c + 1) - c_first;
     const TetSpan sp = ctx->mesh.n_sel > 0 ? TetSpan{0, c_count, ctx->mesh.tet_sel.p + c_first}
                                            : TetSpan{t_first + c_first, c_count, nullptr};
     const int b = c & 1;

@@ -55,3 +55,26 @@ def test_dist2mat_input(synth):
     kinds = np.where(d.prims[:, 1] == -1, 0, np.where(d.prims[:, 0] == -1, 1, 2))
     assert set(np.unique(kinds)) == {0, 1, 2}
     assert d.prims.max() < len(d.spheres)
+
+
+def test_library_tet_adjacency_equals_generator(synth):
+    """mb_tet_adjacency (f4: the sparse load_tet_adj_info, io.cxx:238-335) against the restatement in synth.tet_adjacency,
+    on a full mesh and on an arbitrary sub-mesh (partial-tet calls, rpd_api.cxx:254-281)"""
+    import numpy as np
+    from libmat_b200 import capi
+    mesh = synth.make_ball_mesh(9)
+    v, e6, fa, fi, nb = capi.tet_adjacency(mesh.indices, mesh.n_vert)
+    assert nb == mesh.n_surf_faces
+    assert np.array_equal(v, mesh.v_adjs) and np.array_equal(e6, mesh.e_adj6)
+    assert np.array_equal(fa, mesh.f_adjs) and np.array_equal(fi, mesh.f_ids)
+    sub = mesh.indices[::3]
+    want = synth.tet_adjacency(sub, mesh.n_vert)
+    got = capi.tet_adjacency(sub, mesh.n_vert)
+    for a, b in zip(got[:4], want[:4]):
+        assert np.array_equal(a, np.asarray(b).reshape(a.shape))
+    assert got[4] == want[4]
+    # caller-supplied surface facet ids for the boundary faces, interior ids after n_sf_facets
+    perm = np.random.default_rng(0).permutation(nb).astype(np.int32)
+    _, _, _, fi2, _ = capi.tet_adjacency(mesh.indices, mesh.n_vert, boundary_sf_fids=perm, n_sf_facets=nb + 7)
+    b = mesh.f_adjs == 1
+    assert np.array_equal(fi2[b], perm) and np.array_equal(fi2[~b], mesh.f_ids[~b] + 7)
