@@ -1090,23 +1090,23 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
   }
   cudaStream_t cs = ctx->copy_stream;
   bool decreasing = false;
+  {
+    cudaPointerAttributes pa;
+    decreasing = dst_blob && cudaPointerGetAttributes(&pa, dst_blob) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+    (void)cudaGetLastError();
+  }
   if (n_chunks <= 0) {
     // automatic span count.  Host destinations: the PCIe copy is the long pole, so spans are short (~32k tets) and
     // the first bytes leave early.  Device destinations (this GPU or a peer over NVLink): the copy is ~10x faster
     // than the kernels, so only the last span's copy is exposed and fewer, longer spans waste less on kernel tails
     // and launch gaps (~0.1-0.2 ms per span).
-    bool dev_dst = false;
-    if (dst_blob) {
-      cudaPointerAttributes pa;
-      dev_dst = cudaPointerGetAttributes(&pa, dst_blob) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
-      (void)cudaGetLastError();
-    }
-    // Only the LAST span's copy is exposed, so device destinations use a few spans of DECREASING size (4 : 3 : 2 : 1
-    // when there are four): every copy still hides behind the next, shorter span's kernels and the exposed tail is
-    // a tenth of the result.
-    decreasing = dev_dst;
+    // Every span costs ~0.1-0.3 ms of kernel tails and launch gaps and only the LAST span's copy is exposed, so a
+    // device destination gets two spans of sizes 2 : 1 (measured: three equal spans 2.48 ms, four decreasing ones
+    // 2.81 ms per step at N = 2); callers that know how contended the destination's ingress is pass n_chunks
+    // (libmat_b200.dist.ShardSink: one span up to two ranks).
+    const bool dev_dst = decreasing;
     const int per_span = lean ? 65536 : 32768;  // slim / lean records: the kernels are the long pole, fewer spans
-    n_chunks = dev_dst ? std::max(1, std::min(4, (t_count + 49151) / 49152)) : std::max(1, std::min(32, (t_count + per_span - 1) / per_span));
+    n_chunks = dev_dst ? (t_count >= 65536 ? 2 : 1) : std::max(1, std::min(32, (t_count + per_span - 1) / per_span));
   }
   n_chunks = std::max(1, std::min(n_chunks, std::max(1, t_count)));
   const bool grid_cands = !ctx->sites.given || (opts && opts->grid_candidates);

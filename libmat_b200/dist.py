@@ -185,6 +185,10 @@ class ShardSink:
     def run(self, n_chunks=0, **kw):
         """every rank: streamed run of its shard into its slab; returns (result handle, directory [world, 2])"""
         blob_ptr, off_ptr = self.slab(self.rank)
+        if n_chunks == 0 and self.kind == "device":
+            # spans exist to hide the transfer behind the kernels; into a peer's HBM the whole shard takes ~0.1 ms
+            # unless many ranks converge on the destination's NVLink ingress at once
+            n_chunks = 1 if self.world <= 2 else 2
         res = self.ctx.run_to_sink(blob_ptr, self.cap_bytes, off_ptr, self.cap_cells + 1, n_chunks=n_chunks, **kw)
         mine = torch.tensor([res.compact_bytes, res.n_cells], dtype=torch.int64)
         if self.world > 1:
