@@ -146,6 +146,14 @@ typedef struct {
                            recompute the equations on the host with the reference's literal arithmetic
                            (tri2plane common_cuda.h:248-254, new_plane convex_cell.cu:561-592): expanded records
                            are byte-identical to the full format's */
+  int security_radius;  /* given-neighbours mode only, for neighbour lists sorted by distance (the reference's kNN lists,
+                           not its regular-triangulation lists): 1 = the security-radius early exit the live reference
+                           comments out (is_security_radius_reached convex_cell.cu:240-268, used at :1285-1296): a cell
+                           stops clipping at the first listed neighbour whose bisector lies beyond twice its farthest
+                           vertex, and a cell whose LAST listed neighbour does not reach that radius is dropped as
+                           security_radius_not_reached (:1304-1316; counted in mb_rpd_status_histogram).  grid-kNN
+                           mode needs no such exit: its per-tet candidate lists already hold only the sites that can
+                           reach the tet */
 } mb_rpd_opts;
 
 /* site_soa float[3*n_site] = x.. | y.. | z.. (rpd_api.cxx:363-365), site_w float[n_site] = r^2,

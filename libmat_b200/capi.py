@@ -41,7 +41,7 @@ RECORD_DTYPE = np.dtype({
 
 class RpdOpts(C.Structure):
     _fields_ = [("lanes_per_cell", C.c_int), ("grid_k", C.c_int), ("want_volumes", C.c_int),
-                ("grid_candidates", C.c_int), ("lean_records", C.c_int)]
+                ("grid_candidates", C.c_int), ("lean_records", C.c_int), ("security_radius", C.c_int)]
 
 
 class EmitCounts(C.Structure):

@@ -64,6 +64,7 @@ struct ClipArgs {
   const int* work_list;                   // second pass: work item -> pair (nullptr: identity)
   const unsigned long long* work_count;   // second pass: number of work items (device-resident)
   int no_cull;                            // debug (MB_NO_CULL=1): clip by every listed neighbour like the reference does
+  int security_radius;                    // given-neighbours mode: the reference's security-radius exit (a9), opt-in
 };
 
 // indices into RpdCounters viewed as u64[]
@@ -182,6 +183,35 @@ __device__ __noinline__ void cell_gc(CellS& S, int lane, unsigned gmask, int gsh
   nb_e = ne_new;
 }
 
+// a9: is_security_radius_reached (convex_cell.cu:240-268, the weighted variant), group-cooperative: lanes over the cell's
+// vertices for v_dist = max |vertex - seed|^2 (compute_vertex_coordinates :319-351 in its literal float order), then
+// d2 = |foot of the bisector on the segment seed-neighbour - seed|^2; reached iff d2 > 4 v_dist.  Opt-in path
+// (mb_rpd_opts.security_radius), out of line.
+template <int G, class CellS>
+__device__ __noinline__ bool security_radius_reached(const CellS& S, int lane, unsigned gmask, int nb_v, float4 seed, float4 B) {
+  float vd = 0.f;
+  for (int v = lane; v < nb_v; v += G) {
+    const uchar4 tv = S.ver[v];
+    const float4 p1 = S.plane[tv.x], p2 = S.plane[tv.y], p3 = S.plane[tv.z];
+    const float rx = -det3_exact(p1.w, p1.y, p1.z, p2.w, p2.y, p2.z, p3.w, p3.y, p3.z);
+    const float ry = -det3_exact(p1.x, p1.w, p1.z, p2.x, p2.w, p2.z, p3.x, p3.w, p3.z);
+    const float rz = -det3_exact(p1.x, p1.y, p1.w, p2.x, p2.y, p2.w, p3.x, p3.y, p3.w);
+    const float rw = det3_exact(p1.x, p1.y, p1.z, p2.x, p2.y, p2.z, p3.x, p3.y, p3.z);
+    const float dx = xfsub(__fdiv_rn(rx, rw), seed.x), dy = xfsub(__fdiv_rn(ry, rw), seed.y), dz = xfsub(__fdiv_rn(rz, rw), seed.z);
+    const float d2 = dot3_exact(dx, dy, dz, dx, dy, dz);
+    vd = d2 > vd ? d2 : vd;  // max(d2, v_dist): a NaN d2 is ignored, like the reference's max
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) vd = fmaxf(vd, __shfl_xor_sync(gmask, vd, o));
+  const float fx = xfsub(seed.x, B.x), fy = xfsub(seed.y, B.y), fz = xfsub(seed.z, B.z);
+  const float r2_diff = xfsub(seed.w, B.w);
+  const float dd = dot3_exact(fx, fy, fz, fx, fy, fz);
+  const float w = __fdiv_rn(xfsub(dd, r2_diff), xfmul(2.f, dd));
+  const float px = xfsub(xfadd(xfmul(w, fx), B.x), seed.x), py = xfsub(xfadd(xfmul(w, fy), B.y), seed.y),
+              pz = xfsub(xfadd(xfmul(w, fz), B.z), seed.z);
+  return dot3_exact(px, py, pz, px, py, pz) > xfmul(4.f, vd);
+}
+
 // The FP64 determinant + static-filter test is the RARE path of the conflict predicate (~1 test in 3 000): kept out of
 // line so that the hot loop stays small -- the kernel is sensitive to its instruction footprint (stall_no_instruction).
 // bit 0: in conflict, bit 1: flagged
@@ -256,6 +286,9 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
   // pm_bis = largest |normal component| over the tet planes / the bisectors seen so far (bound the filter's eps)
   bool flagged = false;
   float pm_tet = 0.f, pm_bis = 0.f;
+  // a9 (given-neighbours mode, opt-in): radius reached / last listed neighbour seen so far
+  bool sr_reached = false;
+  int last_nb = -1;
 
   for (;;) {
     __syncwarp();
@@ -332,7 +365,9 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
           S.edge[3 * q + 2] = (unsigned char)((e6 >> (8 * q)) & 0xff);
         }
       }
-      cull_ok = group_ballot<G>(gmask, gshift, !ok0) == 0 && !A.no_cull;
+      cull_ok = group_ballot<G>(gmask, gshift, !ok0) == 0 && !A.no_cull && !(!PT && A.security_radius);
+      sr_reached = false;
+      last_nb = -1;
       cvalid = 0xfu;
       nb_v = 4;
       nb_p = 4;
@@ -808,11 +843,25 @@ __global__ void __launch_bounds__(128, SMALL ? 5 : 4) k_clip(ClipArgs A) {
         state = GS_FINISH;
       }
     }
+    // a9: after every listed neighbour, has the security radius been reached?  (convex_cell.cu:1285-1296)
+    if (!PT && A.security_radius && c_act && state == GS_RUN && status == ST_success) {
+      last_nb = nbk;
+      if (security_radius_reached<G, CellS>(S, lane, gmask, nb_v, seed, A.site4[nbk])) {
+        sr_reached = true;
+        todo = 0;
+        list_done = true;
+      }
+    }
     // the last plane of the list has been dealt with (clipped or dropped): finish in this same iteration
     if (c_act && state == GS_RUN && todo == 0 && (list_done || base >= list_len)) state = GS_FINISH;
     __syncwarp();
     // ================= D: write the record (copy(), convex_cell.cu:933-949) =======================
     if (state == GS_FINISH) {
+      // a9: a cell whose last listed neighbour does not reach the security radius (convex_cell.cu:1304-1316)
+      if (!PT && A.security_radius && status == ST_success && !sr_reached) {
+        if (last_nb < 0 || !security_radius_reached<G, CellS>(S, lane, gmask, nb_v, seed, A.site4[last_nb]))
+          status = ST_security_radius_not_reached;
+      }
       long long blob_at = -1;
       int words = 0;
       const unsigned fbit = group_ballot<G>(gmask, gshift, flagged) ? MB_FLAG_BIT : 0u;

@@ -787,6 +787,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     A.scratch_words = ctx->scratch.cap;
     A.counters = reinterpret_cast<unsigned long long*>(ctx->counters.p);
     A.no_cull = ctx->no_cull ? 1 : 0;
+    A.security_radius = (opts && opts->security_radius && S.given) ? 1 : 0;
     const bool pt = A.nbr_cnt != nullptr;
     if (G == 4)
       pt ? launch_clip<4, true>(ctx, A) : launch_clip<4, false>(ctx, A);

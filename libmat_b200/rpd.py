@@ -260,8 +260,8 @@ class Context:
         self._n_site = sw.size
         self._check(self.lib.mb_rpd_upload_sites(self._ctx, ptr(ss), ptr(sw), ptr(sf), sw.size, ptr(knn), int(site_k)))
 
-    def run(self, lanes_per_cell=0, grid_k=0, want_volumes=False, grid_candidates=False) -> RpdResult:
-        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), int(want_volumes), int(grid_candidates), 0)
+    def run(self, lanes_per_cell=0, grid_k=0, want_volumes=False, grid_candidates=False, security_radius=False) -> RpdResult:
+        opts = capi.RpdOpts(int(lanes_per_cell), int(grid_k), int(want_volumes), int(grid_candidates), 0, int(security_radius))
         h = C.c_void_p()
         self._check(self.lib.mb_rpd_run(self._ctx, C.byref(opts), C.byref(h)))
         self._check(self.lib.mb_rpd_sync(self._ctx, h))

@@ -289,10 +289,11 @@ def rt_site_lists(sites: Sites) -> tuple[np.ndarray, int, np.ndarray]:
     return out, site_k, deg > 0
 
 
-def knn_site_lists(sites: Sites, k: int) -> tuple[np.ndarray, int]:
+def knn_site_lists(sites: Sites, k: int, by_distance: bool = False) -> tuple[np.ndarray, int]:
     """Brute-force k nearest centres per site (Euclidean), stored in the reference's
     (site_k+1) x n_site layout: ascending site id per column, -1 padded, last row all -1
-    (reference triangulation.cxx:237-258)."""
+    (reference triangulation.cxx:237-258).  by_distance: keep the columns in order of increasing distance instead
+    (the order of the reference's original kNN lists, which its security-radius exit assumes)."""
     from scipy.spatial import cKDTree
 
     c = sites.centers().astype(np.float64)
@@ -302,7 +303,9 @@ def knn_site_lists(sites: Sites, k: int) -> tuple[np.ndarray, int]:
     out = np.full((k + 1, n), -1, dtype=np.int32)
     for s in range(n):
         lst = nn[s]
-        lst = np.sort(lst[lst != s][:k])
+        lst = lst[lst != s][:k]
+        if not by_distance:
+            lst = np.sort(lst)
         out[: lst.size, s] = lst
     return out, k
 

@@ -83,6 +83,11 @@ def _c(a, dt):
     return np.ascontiguousarray(a, dtype=dt)
 
 
+def set_security_radius(on: bool):
+    """a9: the oracle port's security-radius option (the blocks the live reference comments out); tests only"""
+    lib().orc_set_security_radius(C.c_int(int(on)))
+
+
 def run_pairs(mesh, sites, site_knn, site_k, pair_tet, pair_site, impl="oracle", n_threads=0,
               want_vol=False):
     """Run the per-(tet,site) clipping of the reference kernel body on the CPU.

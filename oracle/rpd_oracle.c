@@ -350,6 +350,32 @@ static int bary_and_volume(cell_t* c, float* bary, int pitch, float* vol) {
   return 1;
 }
 
+/* convex_cell.cu:240-268 (the weighted variant): has the cell's security radius been reached by neighbour B?
+ * v_dist = largest squared distance of a cell vertex from the seed; d2 = squared distance from the seed to the point
+ * where the bisector of (seed, B) crosses the segment seed-B; reached iff d2 > 4 v_dist. */
+static int security_radius_reached(cell_t* c, f4 B) {
+  float v_dist = 0;
+  for (int i = 0; i < c->nb_v; i++) {
+    f4 pc = vertex_coordinates(c, c->ver[i], 1);
+    f4 diff = minus4(pc, c->seed);
+    float d2 = dot3(diff, diff);
+    v_dist = d2 > v_dist ? d2 : v_dist;
+  }
+  f4 diff = minus4(c->seed, B);
+  float r2_diff = c->seed.w - B.w;
+  float w = (dot3(diff, diff) - r2_diff) / (2 * dot3(diff, diff));
+  f4 ph = plus4((f4){w * diff.x, w * diff.y, w * diff.z, w * diff.w}, B);
+  f4 vp = minus4(ph, c->seed);
+  float d2 = dot3(vp, vp);
+  return d2 > 4 * v_dist;
+}
+
+/* the security-radius option of the kernel body, restored from the blocks the live reference comments out
+ * (convex_cell.cu:1285-1296: leave the neighbour loop once the radius is reached; :1304-1316: a cell whose LAST listed
+ * neighbour does not reach it ends as security_radius_not_reached).  Only meaningful for distance-sorted lists. */
+static int g_security_radius = 0;
+void orc_set_security_radius(int on) { g_security_radius = on; }
+
 /* kernel body convex_cell.cu:1166-1337 + copy :933-949 */
 static void run_pair(cell_t* c, const float* verts_aos, const int* idx_aos, const int* v_adjs,
                      const int* e_adj6, const int* f_adjs, const int* f_ids, const float* site_soa,
@@ -362,13 +388,28 @@ static void run_pair(cell_t* c, const float* verts_aos, const int* idx_aos, cons
   if (site_flags[seed] == 0) return;
   cell_init(c, seed, site_soa, n_site, site_w, t, verts_aos, idx_aos + 4 * (size_t)t, v_adjs,
             e_adj6 + 6 * (size_t)t, f_adjs + 4 * (size_t)t, f_ids + 4 * (size_t)t);
+  int last_nb = -1, reached = 0;
   for (int v = 0; v <= site_k - 1; v++) {
     int nb = site_knn[seed + (size_t)v * n_site];
     if (nb == -1) break;
+    last_nb = nb;
     clip_by_plane(c, nb);
     if (c->status != ORC_success) {
       if (stat) *stat = c->status;
       return; /* record stays early_return, :1279-1283 */
+    }
+    if (g_security_radius &&
+        security_radius_reached(c, (f4){site_soa[nb], site_soa[nb + n_site], site_soa[nb + 2 * (size_t)n_site], site_w[nb]})) {
+      reached = 1;
+      break; /* :1285-1296 */
+    }
+  }
+  if (g_security_radius && !reached && c->status != ORC_no_intersection) { /* :1304-1316 */
+    if (last_nb < 0 || !security_radius_reached(c, (f4){site_soa[last_nb], site_soa[last_nb + n_site],
+                                                        site_soa[last_nb + 2 * (size_t)n_site], site_w[last_nb]})) {
+      c->status = ORC_security_radius_not_reached;
+      if (stat) *stat = c->status;
+      return; /* not a success record: dropped by the host filter (voronoi.cu:749) */
     }
   }
   if (c->status != ORC_no_intersection) {

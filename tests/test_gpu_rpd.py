@@ -386,3 +386,42 @@ def test_tet_subset_equals_full_restricted(ctx, O, cfg1_rt, mode):
         ctx.set_tet_subset(np.array([5, 3], np.int32))
     again = ctx.compute_clipped_voro_diagram(*args)
     assert again.n_cells == len(full)
+
+
+def test_security_radius_exit(ctx, O, synth):
+    """a9 (opt-in): distance-sorted kNN lists with the security-radius early exit the live reference comments out
+    (is_security_radius_reached convex_cell.cu:240-268, used at :1285-1296 and :1304-1316): same cells, byte for byte, and
+    the same per-pair statuses -- security_radius_not_reached included -- as the oracle port with the option on; far
+    fewer clips than walking the whole list"""
+    mesh = synth.make_ball_mesh(8)
+    sites = synth.make_spheres(400)
+    knn, k = synth.knn_site_lists(sites, 60, by_distance=True)
+    pt, ps = O.tet_sphere_relation(mesh, sites, knn, k)
+    O.set_security_radius(True)
+    try:
+        ra, sa, _ = O.run_pairs(mesh, sites, knn, k, pt, ps)
+    finally:
+        O.set_security_radius(False)
+    rb, sb, _ = O.run_pairs(mesh, sites, knn, k, pt, ps)
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, knn, k)
+    res = ctx.run(security_radius=True)
+    assert res.n_pairs == len(pt)
+    assert_defined_equal(O, ra[ra["status"] == 4], res.records())
+    assert np.array_equal(res.status_histogram, expected_hist(ra, sa))
+    plain = ctx.run()
+    assert res.n_clips <= plain.n_clips and res.status_histogram[4] > 0  # exits happen; most tet-restricted cells
+    # never reach the radius of an UNRESTRICTED cell within 60 neighbours -- why the reference switched the test off
+    # a list cut so short that the radius cannot be reached: cells are dropped with the reference's status
+    knn2, k2 = synth.knn_site_lists(sites, 3, by_distance=True)
+    pt2, ps2 = O.tet_sphere_relation(mesh, sites, knn2, k2)
+    O.set_security_radius(True)
+    try:
+        r2, s2, _ = O.run_pairs(mesh, sites, knn2, k2, pt2, ps2)
+    finally:
+        O.set_security_radius(False)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, knn2, k2)
+    res2 = ctx.run(security_radius=True)
+    assert np.array_equal(res2.status_histogram, expected_hist(r2, s2))
+    assert res2.status_histogram[4] > 0  # security_radius_not_reached (status 3) occurs
+    assert_defined_equal(O, r2[r2["status"] == 4], res2.records())
