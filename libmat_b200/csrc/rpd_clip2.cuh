@@ -42,7 +42,11 @@ struct __align__(16) CellTiny {
 static_assert(offsetof(CellTiny, bnext) % 16 == 0, "bnext must be 16-byte aligned");
 static_assert(sizeof(CellTiny) % 16 == 0, "cells are 16-byte aligned");
 
-template <int G, int NB>
+// PT = true: per-tet candidate lists (grid-kNN mode), hole-filling clip.  PT = false: per-site neighbour lists
+// (given-neighbours mode): the same batch-synchronous structure, but the order-defining bookkeeping of clip_by_plane --
+// swap partition (convex_cell.cu:706-721) and compute_boundary (:618-678) -- is replayed literally by one lane per
+// group, so array positions, and with them the records, stay byte-identical to the reference.
+template <int G, int NB, bool PT>
 __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
   constexpr int KP = MBK_TINY_P, KT = MBK_TINY_T, KE = MBK_TINY_E;
   constexpr int NG = 32 / G;
@@ -58,7 +62,8 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
   CellTiny& S = cells[threadIdx.x / G];
   __shared__ unsigned long long blk_cnt[16];
   if (threadIdx.x < 16) blk_cnt[threadIdx.x] = 0;
-  for (int i = lane; i < KP; i += G) S.adj[i] = 0u;
+  if (PT)
+    for (int i = lane; i < KP; i += G) S.adj[i] = 0u;
   __syncthreads();
 
   const long long NP = A.n_pairs_dev ? min((long long)*A.n_pairs_dev, A.n_pairs) : A.n_pairs;
@@ -128,9 +133,14 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
         pm_tet = fmaxf(pm_tet, __shfl_xor_sync(gmask, pm_tet, 2));
         pm_tet = __shfl_sync(gmask, pm_tet, src);
         cull_ok = group_ballot<G>(gmask, gshift, !ok0) == 0 && !A.no_cull;
-        const int tl = A.pair_local[pair];
-        list = A.nbr + (size_t)tl * A.nbr_stride;
-        list_len = A.nbr_cnt[tl];
+        if (PT) {
+          const int tl = A.pair_local[pair];
+          list = A.nbr + (size_t)tl * A.nbr_stride;
+          list_len = A.nbr_cnt[tl];
+        } else {
+          list = A.nbr + (size_t)seed_id * A.nbr_stride;
+          list_len = A.nbr_stride;
+        }
       }
       __syncwarp();
       // ================= scan batches of G candidates, clip by the survivors =============================
@@ -142,7 +152,9 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
         if (alive && status == ST_success && base < list_len) {
           const int j = base + lane;
           nb = (j < list_len) ? list[j] : -1;
-          bool cand = (nb >= 0 && nb != seed_id);  // the list is the tet's candidate set; skip the seed
+          // PT: the list is the tet's candidate set, skip the seed.  !PT: the first -1 terminates the list (:1259)
+          bool cand = PT ? (nb >= 0 && nb != seed_id) : (nb >= 0);
+          const bool is_end = !PT && (j < list_len) && (nb == -1);
           const bool valid_nb = cand;
           if (cand) {
             eqn = bisector_exact(seed, A.site4[nb]);
@@ -167,7 +179,16 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
             }
           }
           todo = group_ballot<G>(gmask, gshift, cand);
-          const unsigned valid = group_ballot<G>(gmask, gshift, valid_nb);
+          unsigned valid = group_ballot<G>(gmask, gshift, valid_nb);
+          if (!PT) {
+            const unsigned end_mask = group_ballot<G>(gmask, gshift, is_end);
+            if (end_mask) {
+              const unsigned before = (1u << (__ffs(end_mask) - 1)) - 1u;
+              todo &= before;
+              valid &= before;
+              list_len = 0;  // nothing beyond the terminator
+            }
+          }
           // a plane beyond the compact cap: let the full-caps pass decide (it applies the reference's 64-plane rule)
           if (nb_p + __popc(todo) > KP || (nb_p >= KP && valid)) {
             status = ST_vertex_overflow;
@@ -218,7 +239,7 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
                 }
               }
               const unsigned m = (__ballot_sync(0xffffffffu, cf) >> gshift) & glow;
-              if (cf) {
+              if (PT && cf) {
                 S.rm[nb_r + __popc(m & ((1u << lane) - 1u))] = (unsigned char)v;
                 atomicOr(&S.adj[tv.x], 1u << tv.y);
                 atomicOr(&S.adj[tv.y], 1u << tv.z);
@@ -240,6 +261,83 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
             if (lane < 2) reinterpret_cast<uint4*>(S.bnext)[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
           }
           __syncwarp();
+          int L = 0, st2 = ST_success;
+          if (!PT) {
+            // ---- C2 (given-neighbours mode): one lane per group replays the reference's serial bookkeeping
+            if (a1 && lane == 0) {
+              // swap partition, convex_cell.cu:706-721 (the cofactor cache follows the vertices)
+              int nv = nb_v, i = 0;
+              unsigned f = f0;
+              while (i < nv) {
+                if ((f >> i) & 1u) {
+                  nv--;
+                  const unsigned fn = (f >> nv) & 1u;
+                  const uchar4 tmp = S.ver[i];
+                  S.ver[i] = S.ver[nv];
+                  S.ver[nv] = tmp;
+                  S.cof[i] = S.cof[nv];
+                  f = (f & ~(1u << i)) | (fn << i);
+                } else
+                  i++;
+              }
+              // cavity boundary, compute_boundary convex_cell.cu:618-678
+              int first = MBK_END;
+              int r = nb_r, tt = nv, fails = 0;
+              while (r > 0) {
+                const uchar4 tv = S.ver[tt];
+                const unsigned char pl[3] = {tv.x, tv.y, tv.z};
+                bool in_border[3], opp[3];
+#pragma unroll
+                for (int q = 0; q < 3; q++) in_border[q] = S.bnext[pl[q]] != MBK_END;
+#pragma unroll
+                for (int q = 0; q < 3; q++) opp[q] = S.bnext[pl[(q + 1) % 3]] == pl[q];
+                bool simple = true;
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                  if (!opp[q] && !opp[(q + 1) % 3] && in_border[(q + 1) % 3]) simple = false;
+                if (!opp[0] && !opp[1] && !opp[2]) {
+                  if (first == MBK_END) {
+#pragma unroll
+                    for (int q = 0; q < 3; q++) S.bnext[pl[q]] = pl[(q + 1) % 3];
+                    first = pl[0];
+                  } else
+                    simple = false;
+                }
+                if (!simple) {
+                  tt++;
+                  if (tt == nv + r) tt = nv;
+                  if (++fails >= r) {  // a full round without progress: the reference spins until nb_iter > 65535
+                    st2 = ST_inconsistent_boundary;
+                    break;
+                  }
+                  continue;
+                }
+                fails = 0;
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                  if (!opp[q]) S.bnext[pl[q]] = pl[(q + 1) % 3];
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                  if (opp[q] && opp[(q + 1) % 3]) {
+                    const unsigned char pm = pl[(q + 1) % 3];
+                    if (first == pm) first = S.bnext[pm];
+                    S.bnext[pm] = MBK_END;
+                  }
+                const uchar4 tmp = S.ver[tt];
+                S.ver[tt] = S.ver[nv + r - 1];
+                S.ver[nv + r - 1] = tmp;
+                tt = nv;
+                r--;
+              }
+              if (st2 == ST_success && first != MBK_END) {
+                int cir = first;
+                do {
+                  S.cyc[L++] = (unsigned char)cir;
+                  cir = S.bnext[cir];
+                } while (cir != first && cir != MBK_END && L < KP);
+              }
+            }
+          } else {
           // ---- C2: cavity boundary = directed edges a->b of removed triangles whose twin b->a is absent
           const int rmax = __reduce_max_sync(0xffffffffu, c_act ? nb_r : 0);
           int nbnd = 0, first = MBK_END;
@@ -276,7 +374,6 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
           }
           // the cycle, from its smallest plane id; a boundary that is not ONE simple cycle is the reference's
           // inconsistent_boundary (:626-629)
-          int L = 0, st2 = ST_success;
           if (a1 && lane == 0 && first != MBK_END) {
             int cir = first;
             do {
@@ -284,6 +381,7 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
               cir = S.bnext[cir];
             } while (cir != first && cir != MBK_END && L < nbnd && L < KP);
             if (cir != first || L != nbnd) st2 = ST_inconsistent_boundary;
+          }
           }
           __syncwarp();
           L = __shfl_sync(0xffffffffu, L, src);
@@ -325,7 +423,8 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
                 const unsigned char z3 = edge_z(min(cir, nxt), max(cir, nxt), hf4, e6);
                 const unsigned char w = max(max(z1, z2), z3);
                 const float4 p2 = S.plane[cir], p3 = S.plane[nxt];
-                const int slot = jj < nb_r ? (int)S.rm[jj] : nb_v + (jj - nb_r);
+                // PT: the jj-th hole, then the tail.  !PT: the partition has compacted the survivors: append
+                const int slot = PT ? (jj < nb_r ? (int)S.rm[jj] : nb_v + (jj - nb_r)) : (nb_v - nb_r) + jj;
                 S.ver[slot] = make_uchar4(cur_p, cir, nxt, w);
                 S.cof[slot] = cofactors_f32(minors_exact(e, p2, p3));
                 // is_vertex_perturb (:274-316): w-component of the vertex == 0
@@ -337,7 +436,7 @@ __global__ void __launch_bounds__(128, NB) k_clip_tiny(ClipArgs A) {
             if (do_new) {
               nb_e += L;
               if (perturb) status = ST_needs_perturb;
-              if (L < nb_r && lane == 0) {
+              if (PT && L < nb_r && lane == 0) {
                 // more vertices removed than created: move live tail vertices into the holes rm[L .. nb_r) that lie
                 // below the new count (holes ascending, sources descending: they never cross)
                 int srcv = nb_v - 1;

@@ -523,20 +523,20 @@ static void launch_clip_pass(mb_ctx* ctx, ClipArgs A, bool second_pass) {
 }
 
 // grid-kNN mode, first pass: the batch-synchronous compact-caps kernel (rpd_clip2.cuh)
-template <int G, int NB>
+template <int G, int NB, bool PT>
 static void launch_clip_tiny(mb_ctx* ctx, ClipArgs A) {
   constexpr int groups = 128 / G;
   const size_t smem = sizeof(CellTiny) * groups;
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[ctx->device & 63];
   if (!attr_set) {
-    MB_CUDA(cudaFuncSetAttribute(k_clip_tiny<G, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MB_CUDA(cudaFuncSetAttribute(k_clip_tiny<G, NB, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   static int per_sm_dev[64] = {0};
   int& per_sm = per_sm_dev[ctx->device & 63];
   if (per_sm < 1) {
-    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip_tiny<G, NB>, 128, smem));
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip_tiny<G, NB, PT>, 128, smem));
     if (per_sm < 1) per_sm = 1;
   }
   const long long want = (A.n_pairs + groups - 1) / groups;
@@ -549,7 +549,7 @@ static void launch_clip_tiny(mb_ctx* ctx, ClipArgs A) {
     A.grab = A.n_pairs_dev ? 0 : (int)std::max<long long>(NG, std::min<long long>(8 * NG, g));
   }
   ctx->n_launches++;
-  k_clip_tiny<G, NB><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
+  k_clip_tiny<G, NB, PT><<<(unsigned)grid, 128, smem, ctx->stream>>>(A);
   MB_CUDA(cudaGetLastError());
 }
 
@@ -563,13 +563,15 @@ static void launch_clip(mb_ctx* ctx, ClipArgs A) {
   A.work_count = nullptr;
   ctx->redo_list.reserve((size_t)A.n_pairs + 1);
   A.redo_out = ctx->redo_list.p;
-  if constexpr (PT && (G == 8 || G == 4)) {
-    if (ctx->clip_variant == 0)
-      launch_clip_tiny<G, 6>(ctx, A);
-    else if (ctx->clip_variant == 2)
-      launch_clip_tiny<G, 5>(ctx, A);
-    else
+  if constexpr (G == 8 || G == 4) {
+    // first pass: the batch-synchronous compact-caps kernel (rpd_clip2.cuh) in both modes; the state-machine kernel
+    // k_clip keeps the opt-in security-radius exit (a9) and the A/B switch MB_CLIP_VARIANT=1
+    if (ctx->clip_variant == 1 || A.security_radius)
       launch_clip_pass<G, PT, true>(ctx, A, false);
+    else if (ctx->clip_variant == 2)
+      launch_clip_tiny<G, 5, PT>(ctx, A);
+    else
+      launch_clip_tiny<G, 6, PT>(ctx, A);
   } else {
     launch_clip_pass<G, PT, true>(ctx, A, false);
   }
