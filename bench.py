@@ -374,11 +374,18 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
         smp_h, fid_h = pin(d.samples), pin(d.sample_fid)
         sph_h, mf_h, me_h, fs_h = pin(d.spheres), pin(d.mm_faces), pin(d.mm_edges), pin(d.fid_sites)
 
+        bf_stage = {}
+
         def by_face_call():
+            ta = time.perf_counter()
             ctx.dist2mat_set_medial_mesh(sph_h.numpy(), mf_h.numpy(), me_h.numpy())
+            tb = time.perf_counter()
             ctx.dist2mat_set_face_sites(fs_h.numpy(), d.n_fid)
+            tc = time.perf_counter()
             ctx._check(ctx.lib.mb_dist2mat_by_face(ctx._ctx, smp_h.numpy().ctypes.data, fid_h.numpy().ctypes.data, n_samples,
                                                    res_h.numpy().ctypes.data, cid_h.numpy().ctypes.data, None, None))
+            td = time.perf_counter()
+            bf_stage.update(set_medial_mesh=1e3 * (tb - ta), set_face_sites=1e3 * (tc - tb), by_face=1e3 * (td - tc))
 
         by_face_call()
         off_l, _ = ctx.dist2mat_face_lists()
@@ -406,7 +413,7 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
             "roofline": {"bound": "hbm", "achieved": b_alg3 / (k3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": b_alg3 / (k3 * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": b_alg3},
             "e2e": {"value": n_samples / t_bf, "unit": "queries/s", "h2d_bytes_per_step": h2d3, "d2h_bytes_per_step": int(8 * n_samples),
-                    "ms": 1e3 * t_bf}}
+                    "ms": 1e3 * t_bf, "stage_ms_last_call": dict(bf_stage)}}
     except Exception as exc:  # noqa: BLE001
         out["by_face"] = {"error": str(exc)}
     # the same query with every distinct list stored once (samples of one surface face share their list:

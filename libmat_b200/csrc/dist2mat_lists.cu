@@ -171,8 +171,8 @@ void sort_keys(mb_ctx* ctx, DevBuf<unsigned long long>& a, DevBuf<unsigned long 
 long unique_keys(mb_ctx* ctx, DevBuf<unsigned long long>& keys, long n) {
   if (n <= 0) return 0;
   cudaStream_t s = ctx->stream;
-  DevBuf<int> flag, pos;
-  DevBuf<unsigned long long> out;
+  DevBuf<int>&flag = ctx->d2m_lists.tmp_flag, &pos = ctx->d2m_lists.tmp_pos;
+  DevBuf<unsigned long long>& out = ctx->d2m_lists.tmp_out;
   flag.reserve((size_t)n + 1);
   pos.reserve((size_t)n + 1);
   out.reserve((size_t)n);
@@ -213,7 +213,7 @@ void d2m_set_medial_mesh(mb_ctx* ctx, const float* spheres, int n_sph, const int
   L.se_keys.reserve(2 * (size_t)n_edges + 1);
   L.sf_first.reserve((size_t)n_sph + 2);
   L.se_first.reserve((size_t)n_sph + 2);
-  DevBuf<unsigned long long> tmp;
+  DevBuf<unsigned long long>& tmp = L.tmp_keys;
   ctx->n_launches += 4;
   if (n_faces) k_inc_keys<<<nb(3L * n_faces, 256), 256, 0, s>>>(L.mm_faces.p, n_faces, 3, L.sf_keys.p);
   if (n_edges) k_inc_keys<<<nb(2L * n_edges, 256), 256, 0, s>>>(L.mm_edges.p, n_edges, 2, L.se_keys.p);
@@ -236,12 +236,12 @@ static void build_face_lists(mb_ctx* ctx, long n_keys, int n_fid) {
   D2MDev& D = ctx->d2m;
   cudaStream_t s = ctx->stream;
   MB_REQUIRE(L.have_mesh, MB_ERR_STATE, "mb_dist2mat_set_medial_mesh first");
-  DevBuf<unsigned long long> tmp;
+  DevBuf<unsigned long long>& tmp = L.tmp_keys;
   sort_keys(ctx, L.fs_keys, tmp, n_keys);
   L.n_fs = unique_keys(ctx, L.fs_keys, n_keys);
   L.n_fid = n_fid;
   L.fs_first.reserve((size_t)n_fid + 2);
-  DevBuf<int> len;
+  DevBuf<int>& len = L.tmp_len;
   len.reserve((size_t)n_fid + 2);
   L.list_off.reserve((size_t)n_fid + 2);
   ctx->n_launches += 4;
@@ -270,7 +270,7 @@ void d2m_set_face_sites(mb_ctx* ctx, const int* fid_site_rows, long n_rows, int 
   D2MLists& L = ctx->d2m_lists;
   cudaStream_t s = ctx->stream;
   L.fs_keys.reserve((size_t)n_rows + 1);
-  DevBuf<int> rows;
+  DevBuf<int>& rows = L.tmp_rows;
   rows.reserve(2 * (size_t)n_rows + 2);
   if (n_rows) {
     MB_CUDA(cudaMemcpyAsync(rows.p, fid_site_rows, sizeof(int) * 2 * (size_t)n_rows, cudaMemcpyHostToDevice, s));
@@ -323,7 +323,7 @@ void d2m_fetch_closest_prims(mb_ctx* ctx, int* prim3) {
   D2MDev& D = ctx->d2m;
   cudaStream_t s = ctx->stream;
   if (D.n_samples <= 0) return;
-  DevBuf<int> out;
+  DevBuf<int>& out = ctx->d2m_lists.tmp_prim3;
   out.reserve(3 * (size_t)D.n_samples);
   ctx->n_launches++;
   k_closest_prim<<<nb(D.n_samples, 256), 256, 0, s>>>(D.closest.p, D.offset.p, D.prims.p, D.n_samples, out.p);

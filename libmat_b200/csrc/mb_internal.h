@@ -236,6 +236,9 @@ struct D2MLists {
   DevBuf<int> fs_first;                        // CSR row starts per surface fid
   DevBuf<long long> list_off;                  // per surface fid: start of its primitive list in D2MDev::prims
   DevBuf<int> sample_fid;
+  // scratch kept between calls (cudaMalloc / cudaFree synchronise the device and cost far more than the kernels here)
+  DevBuf<unsigned long long> tmp_keys, tmp_out;
+  DevBuf<int> tmp_flag, tmp_pos, tmp_len, tmp_rows, tmp_prim3;
 };
 
 struct mb_ctx {

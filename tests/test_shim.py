@@ -85,7 +85,8 @@ def test_shim_dist2mat_matches_oracle(O, synth):
         with open(fout, "rb") as f:
             res = _r(f, np.float32)
             cid = _r(f, np.int32)
+    # the shim returns no tie flags: take them from the oracle's runner-up distance (scale-aware, as the kernel's)
     ro, co, _, sec = O.dist2mat(d, "oracle", want_second=True)
-    assert np.max(np.abs(res - ro) / np.maximum(np.abs(ro), 1e-3)) <= 1e-6
-    tie = (sec - ro) <= 1e-6 * np.maximum(np.abs(ro), np.abs(sec))
-    assert not np.any((cid != co) & ~tie)
+    tie = ((sec - ro) <= 1e-6 * np.maximum(np.maximum(np.abs(ro), np.abs(sec)), 0.1)).astype(np.uint8)
+    from test_gpu_dist2mat import check_against_builds
+    check_against_builds(O, d, res, cid, tie, min_bitwise=0.98)
