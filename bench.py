@@ -975,13 +975,15 @@ def main():
             except Exception as exc:  # noqa: BLE001
                 line["e2e_shim"] = {"error": str(exc)}
             try:
-                line["gpu_reference"] = bench_gpu_reference(ctx, with_cfg2=not args.no_ref_cfg2)
-            except Exception as exc:  # noqa: BLE001
-                line["gpu_reference"] = {"error": str(exc)}
-            try:
                 line["dist2mat"] = bench_dist2mat(ctx, args.samples or 10000000, max(3, args.steps // 2), 3)
             except Exception as exc:  # never lose the headline line
                 line["dist2mat"] = {"error": str(exc)}
+            # last: the reference's CUDA build at config 2 allocates ~10 GB of dense matrices in this process and the
+            # legs measured after it ran several times slower (by_face e2e 131 ms instead of 17 ms)
+            try:
+                line["gpu_reference"] = bench_gpu_reference(ctx, with_cfg2=not args.no_ref_cfg2)
+            except Exception as exc:  # noqa: BLE001
+                line["gpu_reference"] = {"error": str(exc)}
         emit_line(line)
     for sk in (sink_dev, sink_host):
         if sk is not None:
