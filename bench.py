@@ -14,9 +14,10 @@ ordering/compaction (K4 first half), all in libmat_b200.so through the C ABI.
           (n = 40 / 51, 20 000 / 40 000 spheres); N = 8 IS BASELINE.json configs[3], the north-star target:
           n = 70, 2 058 000 tets (257 250 per GPU), 100 000 spheres.  Every rank's streamed run
           (mb_rpd_run_to_sink) writes its ordered shard straight into rank 0's HBM over NVLink peer memory
-          (CUDA IPC, copy-engine DMA overlapped with the next tet span); ONE 16-byte-per-rank NCCL all-gather
-          exchanges the shard directory and is the completion barrier -- the payload does not travel through NCCL
-          (`--gather nccl` keeps the all-gather + grouped send/recv path for comparison).
+          (CUDA IPC, copy-engine DMA overlapped with the next tet span); the shard directory (bytes, cells per rank)
+          goes through a shared-memory mailbox the ranks spin on, which is also the completion barrier -- neither
+          payload nor directory travels through NCCL (a 16-byte all-gather per step cost 130-250 us;
+          `--gather nccl` keeps the all-gather + grouped send/recv path for comparison).
           `value` = cells of all ranks / max-over-ranks device time.
 
 `value`  : valid cells per second with the inputs resident in HBM (device time, CUDA events on the
@@ -555,6 +556,7 @@ def main():
                          "measured as well and reported in e2e.full_records")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the shards reach rank 0")
     ap.add_argument("--chunks", type=int, default=0, help="e2e leg: tet spans of the streamed run (0 = automatic)")
+    ap.add_argument("--sweep-chunks", default="", help="N>1: also time the streamed sinks with these span counts, e.g. 1,2,3,4")
     ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cfg2", action="store_true", help="gpu_reference: skip the reference CUDA build at config 2 (tens of GB, tens of seconds)")
@@ -732,7 +734,7 @@ def main():
     # ---- multi-GPU result gather on rank 0 -----------------------------------------------------------------
     # default ("p2p"): every rank's streamed run writes its ordered shard straight into rank 0's HBM through a
     # CUDA-IPC peer mapping -- tet span c crosses NVLink by copy-engine DMA while span c+1 is clipped -- and
-    # one 16-byte-per-rank NCCL all-gather exchanges the shard directory (and is the completion barrier).
+    # the shard directory goes through a shared-memory mailbox (also the completion barrier).
     # "nccl": one-shot run, then an all-gather of the sizes + grouped NCCL send/recv (libmat_b200.dist).
     gather_buf = {"t": None}
     sink_dev = sink_host = None
@@ -840,7 +842,7 @@ def main():
             if world > 1:
                 if sink_host is not None:
                     # every rank streams its shard into the shared pinned host segment (all PCIe links in
-                    # parallel); after the directory all-gather the whole result is in rank 0's address space
+                    # parallel); after the directory exchange the whole result is in rank 0's address space
                     res, directory = sink_host.run(n_chunks=args.chunks, lanes_per_cell=args.lanes, lean=lean)
                     d2h = int(directory[:, 0].sum() + 8 * (directory[:, 1].sum() + world))
                     e2e_chunks = int(res.n_spans)
@@ -889,6 +891,27 @@ def main():
             e2e_lean = {"value": cells * e2e_steps / (time.perf_counter() - tl0), "unit": UNIT, "d2h_bytes_per_step": int(lean_bytes),
                         "note": "full compact records (plane equations and ids stored, nothing to recompute on expansion)"}
 
+    # ---- optional: span-count sweep of the streamed sinks (N > 1), same timing rules, one process ----------
+    span_sweep = None
+    if world > 1 and args.sweep_chunks:
+        span_sweep = {}
+        with torch.cuda.stream(stream):
+            for kind, sk in (("device", sink_dev), ("host", sink_host)):
+                if sk is None:
+                    continue
+                for nc in [int(x) for x in args.sweep_chunks.split(",")]:
+                    for _ in range(2):
+                        sk.run(n_chunks=nc, lanes_per_cell=args.lanes, lean=lean)[0].free()
+                    barrier()
+                    ts = time.perf_counter()
+                    for _ in range(args.steps):
+                        flush.zero_()
+                        sk.run(n_chunks=nc, lanes_per_cell=args.lanes, lean=lean)[0].free()
+                    barrier()
+                    tt = torch.tensor([time.perf_counter() - ts], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    span_sweep[f"{kind}:{nc}"] = 1e3 * tt.item() / args.steps  # wall ms per step incl. the L2 flush (~0.1 ms)
+
     # ---- max over ranks, totals ------------------------------------------------------------------
     tot = torch.tensor([float(cells), float(pairs), float(rec_bytes), float(listed)], dtype=torch.float64, device=dev)
     mx = torch.tensor([t_dev, t_e2e, t_wall, float(np.mean(clip_ms))], dtype=torch.float64, device=dev)
@@ -917,7 +940,7 @@ def main():
             "run": {   "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})" + (", grid candidates" if args.grid_candidates else ", reference relation predicate"),
                        "parallelism": f"tet-shards x{world}, sites replicated" + (
                            "" if world == 1 else (", shards streamed into rank 0's HBM over NVLink peer memory (CUDA IPC, copy-engine DMA "
-                                                  "overlapped with the next tet span, %s records) + directory all-gather (NCCL)" % args.records if gather_mode == "p2p"
+                                                  "overlapped with the next tet span, %s records) + shared-memory directory mailbox" % args.records if gather_mode == "p2p"
                                                   else ", NCCL gather to rank 0 (all-gather of sizes + grouped send/recv)")),
                        "cells_per_step": total_cells, "candidate_pairs_per_step": total_pairs,
                        "pairs_per_sec": total_pairs * args.steps / t_dev},
@@ -941,7 +964,7 @@ def main():
                     "path": ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_host (%d tet spans, D2H of span c "
                              "overlapped with the kernels of span c+1)" % e2e_chunks) if world == 1 else
                             ("mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run_to_sink into a shared page-locked host segment "
-                             "(every rank streams its tet shard over its own PCIe link, %d spans each%s) + directory all-gather"
+                             "(every rank streams its tet shard over its own PCIe link, %d spans each%s) + shared-memory directory mailbox"
                              % (e2e_chunks, ", slabs first-touched on the GPU's NUMA node" if getattr(sink_host, "numa_pinned", False) else "")
                              if sink_host is not None else "mb_set_tetmesh + mb_rpd_upload_sites + mb_rpd_run + gather + D2H on rank 0"),
                     "stage_ms": {"set_tetmesh": 1e3 * e2e_parts[0] / e2e_steps, "upload_sites": 1e3 * e2e_parts[1] / e2e_steps,
@@ -953,6 +976,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if span_sweep:
+            line["span_sweep_wall_ms"] = span_sweep
         if world == 1 and not args.no_cpu_baseline:
             # CPU baseline: the reference's clipping code on the candidate pairs of a given-mode run
             ctx.upload_sites(h["site"], h["w"], h["flags"], knn, k)

@@ -1118,6 +1118,11 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
   MB_CUDA(cudaEventRecord(e0, s));
   if (grid_cands && t_count > 0) G = grid_build(ctx);
   long long acc_bytes = 0, acc_cells = 0;
+  // MB_TRACE=2: device timeline of the spans (kernels done / copy done, ms after the run's first event)
+  std::vector<cudaEvent_t> tl;
+  std::vector<long long> tl_bytes;
+  const bool timeline = ctx->trace_level >= 2;
+  const double wall0 = timeline ? now_us() : 0.0;
   // own destination: kept from the previous run; first run sizes it from the first span
   if (own) {
     if (!ctx->pin_off.p) ctx->pin_off.reserve_keep(sizeof(long long) * 1024, 0);
@@ -1173,11 +1178,35 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
       MB_CUDA(cudaMemcpyAsync(out_off + acc_cells, ctx->span_off[b].p, sizeof(long long) * (size_t)(st.n_cells + 1),
                               cudaMemcpyDefault, cs));
     MB_CUDA(cudaEventRecord(ctx->ev_copied[b], cs));
+    if (timeline) {
+      cudaEvent_t a, d;
+      MB_CUDA(cudaEventCreate(&a));
+      MB_CUDA(cudaEventCreate(&d));
+      MB_CUDA(cudaEventRecord(a, s));
+      MB_CUDA(cudaEventRecord(d, cs));
+      tl.push_back(a);
+      tl.push_back(d);
+      tl_bytes.push_back(bytes);
+    }
     acc_bytes += bytes;
     acc_cells += st.n_cells;
   }
   MB_CUDA(cudaStreamSynchronize(cs));
   MB_CUDA(cudaStreamSynchronize(s));
+  if (timeline) {
+    std::string line = "[libmat_b200 trace] spans (kernels done / copy done ms, MB):";
+    for (size_t i = 0; i + 1 < tl.size(); i += 2) {
+      float ka = 0.f, kd = 0.f;
+      cudaEventElapsedTime(&ka, e0, tl[i]);
+      cudaEventElapsedTime(&kd, e0, tl[i + 1]);
+      char buf[96];
+      snprintf(buf, sizeof buf, " [%.3f / %.3f, %.1f]", ka, kd, tl_bytes[i / 2] / 1e6);
+      line += buf;
+      cudaEventDestroy(tl[i]);
+      cudaEventDestroy(tl[i + 1]);
+    }
+    fprintf(stderr, "%s  host: start %.0f us (epoch mod 1e7), wall %.0f us\n", line.c_str(), std::fmod(wall0, 1e7), now_us() - wall0);
+  }
   trace_flush(ctx, "run_to_host");
   res->n_spans = n_chunks;
   res->host_only = true;
