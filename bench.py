@@ -556,6 +556,7 @@ def main():
                          "measured as well and reported in e2e.full_records")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the shards reach rank 0")
     ap.add_argument("--chunks", type=int, default=0, help="e2e leg: tet spans of the streamed run (0 = automatic)")
+    ap.add_argument("--equal-shards", action="store_true", help="N>1: equal-size tet shards instead of work-balanced ones")
     ap.add_argument("--sweep-chunks", default="", help="N>1: also time the streamed sinks with these span counts, e.g. 1,2,3,4")
     ap.add_argument("--grid-candidates", action="store_true", help="given mode: pairs from the grid search")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -711,15 +712,17 @@ def main():
         h["knn"] = None
     site_k = k if mode == "given" else 0
 
+    my = {"range": shard(mesh.n_tet, rank, world), "balanced": False}  # replaced by work-balanced cuts below (N > 1)
+
     def set_mesh():
         ctx.set_tetmesh(h["verts"], h["idx"], h["v_adjs"], h["f_adjs"], h["f_ids"], e_adj6=h["e6"])
-        first, count = shard(mesh.n_tet, rank, world)
+        first, count = my["range"]
         if world > 1:
             ctx.set_tet_range(first, count)
 
     def set_mesh_shard():
         """e2e leg, N > 1: a rank uploads only ITS tets (global vertices) and keeps global tet ids"""
-        first, count = shard(mesh.n_tet, rank, world)
+        first, count = my["range"]
         ctx.set_tetmesh(h["verts"], h["idx"][first:first + count], h["v_adjs"], h["f_adjs"][first:first + count],
                         h["f_ids"][first:first + count], e_adj6=h["e6"][first:first + count])
         ctx.set_tet_id_base(first)
@@ -741,7 +744,32 @@ def main():
     lean = {"full": 0, "lean": 1, "slim": 2}[args.records]
     gather_mode = args.gather if world > 1 else "none"
     if world > 1:
-        from libmat_b200.dist import ShardSink
+        from libmat_b200.dist import ShardSink, balanced_shards, rebalance_cuts
+        if not args.equal_shards:
+            # equal-SIZE slabs of a ball differ by 1.5x in work (outer-shell tets hold one or two cells): cut the tet
+            # order into shards of equal estimated work from the per-tet cell counts of one untimed run -- the
+            # statistics an iteration loop has from its previous iteration anyway (libmat_b200.dist.balanced_shards)
+            r0 = ctx.run(lanes_per_cell=args.lanes)
+            pt0, _, st0 = r0.pairs()
+            r0.free()
+            f0, c0 = my["range"]
+            cuts, tet_w = balanced_shards(mesh.n_tet, f0, np.bincount(pt0[st0 == 4] - f0, minlength=c0), device=dev)
+            for _ in range(3):
+                # measured refinement (interior cells cost more than outer-shell cells): per-rank kernel time of two
+                # untimed runs -> new cuts
+                ctx.set_tet_range(int(cuts[rank]), int(cuts[rank + 1] - cuts[rank]))
+                ms_r = []
+                for _ in range(2):
+                    rb = ctx.run(lanes_per_cell=args.lanes)
+                    ms_r.append(sum(rb.kernel_ms[key] for key in ("candidates", "clip", "order")))
+                    rb.free()
+                tm = torch.zeros(world, dtype=torch.float64, device=dev)
+                tm[rank] = min(ms_r)
+                dist.all_reduce(tm)
+                cuts = rebalance_cuts(cuts, tet_w, tm.cpu().numpy())
+            my["range"] = (int(cuts[rank]), int(cuts[rank + 1] - cuts[rank]))
+            my["balanced"] = True
+            ctx.set_tet_range(*my["range"])
         r0 = ctx.run(lanes_per_cell=args.lanes)
         t = torch.tensor([r0.compact_bytes, r0.n_cells], dtype=torch.int64, device=dev)
         r0.free()
@@ -923,7 +951,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        first, count = shard(mesh.n_tet, rank, world)
+        first, count = my["range"]
         b_alg = algorithmic_bytes(count, mesh.n_vert, ns, pairs, listed, rec_bytes)  # rank 0's launch
         clip_avg_ms = float(np.mean(clip_ms))
         achieved = b_alg / (clip_avg_ms * 1e-3) / 1e9
@@ -938,7 +966,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args, n, ns, mesh), "l2": L2_NOTE},
             "run": {   "mode": "grid-kNN (uniform-grid per-tet search)" if mode == "grid" else f"given-neighbours (RT lists, site_k={k})" + (", grid candidates" if args.grid_candidates else ", reference relation predicate"),
-                       "parallelism": f"tet-shards x{world}, sites replicated" + (
+                       "parallelism": f"tet-shards x{world}" + (" (contiguous, cut for equal work: per-tet cell counts of one untimed run + 3 measured refinements)" if my["balanced"] else "") + ", sites replicated" + (
                            "" if world == 1 else (", shards streamed into rank 0's HBM over NVLink peer memory (CUDA IPC, copy-engine DMA "
                                                   "overlapped with the next tet span, %s records) + shared-memory directory mailbox" % args.records if gather_mode == "p2p"
                                                   else ", NCCL gather to rank 0 (all-gather of sizes + grouped send/recv)")),

@@ -4,7 +4,7 @@ set -u
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
-MB_TRACE=2 timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --sweep-chunks 1,2,3,4,6 > gpurun_out/r2s_bench_n$N.json 2> gpurun_out/r2s_bench_n$N.err
+MB_TRACE=2 timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --sweep-chunks ${SWEEP:-1,2,3,4,6} > gpurun_out/r2s_bench_n$N.json 2> gpurun_out/r2s_bench_n$N.err
 python - <<PY
 import json
 f="r2s_bench_n$N"

@@ -80,3 +80,51 @@ def test_rebase_offsets():
     c = np.array([0])
     out = rebase_offsets([a, c, b], [30, 0, 5])
     assert out.tolist() == [0, 10, 30, 35]
+
+
+def _balanced_worker(rank, world, port, q):
+    import numpy as np
+    import torch.distributed as dist
+
+    from libmat_b200.dist import balanced_shards, shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n = 1001
+    cells = (np.arange(n) % 7 + (np.arange(n) > 600) * 9).astype(np.int64)  # heavier tail
+    first, count = shard(n, rank, world)
+    cuts, _ = balanced_shards(n, first, cells[first:first + count])
+    q.put((rank, cuts.tolist()))
+    dist.destroy_process_group()
+
+
+def test_balanced_shards_world2():
+    """work-balanced contiguous shards: every rank computes the same cuts; the heavier tail gets fewer tets"""
+    import numpy as np
+    import torch.multiprocessing as mp
+
+    from libmat_b200.dist import balanced_cuts
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29641
+    ps = [ctx.Process(target=_balanced_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(timeout=60)
+    assert got[0] == got[1]
+    cuts = got[0]
+    n = 1001
+    cells = (np.arange(n) % 7 + (np.arange(n) > 600) * 9).astype(np.int64)
+    assert cuts[0] == 0 and cuts[-1] == n and cuts[1] > n // 2
+    w = cells + 1.5
+    assert abs(w[:cuts[1]].sum() - w[cuts[1]:].sum()) <= 2 * w.max()  # the cut falls within one tet of the midpoint
+    # measured rebalancing: the second half really costs 3x per unit of weight -> the cut moves right
+    from libmat_b200.dist import rebalance_cuts
+    true_cost = w * np.where(np.arange(n) > 600, 3.0, 1.0)
+    c = np.array(cuts)
+    for _ in range(4):
+        c = rebalance_cuts(c, w, np.array([true_cost[c[0]:c[1]].sum(), true_cost[c[1]:c[2]].sum()]))
+    assert c[1] > cuts[1] and abs(true_cost[:c[1]].sum() - true_cost[c[1]:].sum()) <= 0.02 * true_cost.sum()
+    # pure function: degenerate inputs
+    assert balanced_cuts(np.zeros(0), 4).tolist() == [0, 0, 0, 0, 0]
+    assert balanced_cuts(np.ones(3), 8)[-1] == 3 and (np.diff(balanced_cuts(np.ones(3), 8)) >= 0).all()
