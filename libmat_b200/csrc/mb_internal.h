@@ -155,12 +155,13 @@ struct RpdCounters {
   unsigned long long n_gc;         // [18] K3 per-tet mode: dead plane / edge garbage collections
   unsigned long long n_redo;       // [19] grid mode: cells recomputed at the reference's caps by K3's second pass
   unsigned long long work_cursor2; // [20] second pass work distribution
-  unsigned long long reserved[3];  // [21] flagged pairs, [22] flagged valid cells (static-filter class), [23] free
+  unsigned long long reserved[3];  // [21] flagged pairs, [22] flagged valid cells (static-filter class), [23] CNT_FB_TETS
 };
 #define MB_LEAN_FLAG 0x80000000u  // bit 31 of a record's word 2: lean transport format (no plane equations)
 #define MB_SLIM_FLAG 0x20000000u  // bit 29 (with bit 31): slim transport format (plane ids reduced to the neighbour id)
 #define CNT_OVF_TETS 16
 #define CNT_WORK_CURSOR 17
+#define CNT_FB_TETS 23  // grid mode: tets the cluster search handed back to the per-tet search
 
 // mapped pinned host memory the kernels publish stage scalars into (rpd_kernels.cu: publish)
 struct HostScalars {
@@ -267,6 +268,7 @@ struct mb_ctx {
   std::vector<int4> h_tet_fid, h_tet_fadj;  // host copies of f_ids / f_adjs (slim records: tet-face plane ids)
   bool h_tet_planes_valid = false;
   double pairs_per_tet_hint = 0.0;  // grid mode: 1.5 x the largest pairs-per-tet seen (speculative span launches)
+  int k2_variant = 0;               // MB_K2_VARIANT=1 (A/B tests): per-tet candidate search instead of the cluster search
   int clip_variant = 0;             // MB_CLIP_VARIANT=1 (A/B tests): grid-kNN first pass with the state-machine kernel k_clip
   bool no_cull = false;             // MB_NO_CULL=1 (debug / parity tests): no conservative cull of listed neighbours
   unsigned long long stream_generation = 0;  // bumped by every streamed run into the context's own pinned buffers
@@ -278,6 +280,7 @@ struct mb_ctx {
   DevBuf<int> tet_cnt, tet_off, pair_tet, pair_site, pair_local, cand_pad;
   DevBuf<int> redo_list;           // grid mode: pairs whose cell outgrew the compact caps of K3's first pass
   DevBuf<int> cand_cnt;            // grid mode: #candidates per tet (cand_pad holds the lists)
+  DevBuf<int> fb_list;             // grid mode: tets the cluster search handed back to the per-tet search
   DevBuf<int> ovf_list;            // grid mode: tets whose survivor list overflowed the fast pass
   int cand_kcap = 0;               // grid mode: row stride of cand_pad
   DevBuf<long long> word_off;      // ordering: exclusive scan of pair_words

@@ -132,6 +132,59 @@ __device__ __forceinline__ int warp_argmin(float v, int q) {
   return __shfl_sync(0xffffffffu, q, __ffs(who) - 1);
 }
 
+// all-pairs domination on the survivor list + ascending-id rank sort + output (shared by the per-tet and the
+// cluster kernel); s_pd / s_w / s_id hold cnt entries of the calling warp
+__device__ __forceinline__ void grid_finish_candidates(float4* s_pd, float* s_w, int* s_id, int cnt, int lane, int warp,
+                                                       int kcap_out, const unsigned* __restrict__ flags,
+                                                       int* __restrict__ cand_pad, int* __restrict__ cand_cnt,
+                                                       int* __restrict__ pair_cnt, unsigned long long* __restrict__ counters) {
+  __syncwarp();
+  // ---- all-pairs domination on the survivors ---------------------------------------------------
+  int n_keep = 0;
+  for (int b = 0; b < cnt; b += 32) {
+    const int a2 = b + lane;
+    bool keep = false;
+    if (a2 < cnt) {
+      keep = true;
+      const float4 e = s_pd[a2];
+      const float wa = s_w[a2];
+      for (int m = 0; m < cnt && keep; m++)
+        if (m != a2 && dominates(s_pd[m], s_w[m], e, wa)) keep = false;
+    }
+    __syncwarp();
+    // removed entries get id = INT_MAX so that the rank sort pushes them to the tail; their
+    // s_pd stays (a dominated site may still dominate others: domination is transitive)
+    if (a2 < cnt && !keep) s_id[a2] = 0x7fffffff;
+    n_keep += __popc(__ballot_sync(0xffffffffu, keep));
+  }
+  __syncwarp();
+  if (n_keep > kcap_out) {
+    if (lane == 0) atomicAdd(&counters[4], 1ull);  // truncated: reported, never silent
+  }
+  int n_flag = 0;
+  for (int b = 0; b < cnt; b += 32) {
+    const int a2 = b + lane;
+    bool fl = false;
+    if (a2 < cnt) {
+      const int id = s_id[a2];
+      if (id != 0x7fffffff) {
+        int rank = 0;
+        for (int m = 0; m < cnt; m++) rank += (s_id[m] < id);
+        if (rank < kcap_out) {
+          cand_pad[(size_t)warp * kcap_out + rank] = id;
+          fl = flags[id] == 1u;
+        }
+      }
+    }
+    n_flag += __popc(__ballot_sync(0xffffffffu, fl));
+  }
+  if (lane == 0) {
+    cand_cnt[warp] = min(n_keep, kcap_out);
+    pair_cnt[warp] = n_flag;
+  }
+  __syncwarp();
+}
+
 // One warp per tet, ONE walk over the grid:
 //   seed     the 27 fine cells around the centroid give a first U(T) = min_s max_i pd_s(p_i) and the
 //            KERNEL SET K: the best site seen for each of the 4 vertices and for U (<= 5 sites).
@@ -145,15 +198,18 @@ __device__ __forceinline__ int warp_argmin(float v, int q) {
 // of every tet vertex passes both tests, so the final list does not depend on the walk order.
 // Output: padded list [t_local][kcap_out] of ALL candidates (the neighbour list of every cell of
 // the tet), cand_cnt[t_local], pair_cnt[t_local] = number of flagged candidates (cells to clip).
-// A tet whose survivor list exceeds KCAP goes to ovf_list and is redone by the FROM_LIST
+// A tet whose survivor list exceeds KCAP goes to ovf_list and is redone by the SRC = 1
 // instantiation with a 2048-entry list; only a list that still exceeds kcap_out AFTER the
 // all-pairs filter is truncated (counted in counters[CNT_CANDOVF], reported by mb_rpd_stats).
-template <int KCAP, int WARPS, bool FROM_LIST>
+// SRC: 0 = the tets of the span, 1 = ovf_list (big-list pass, truncating), 2 = fb_list (tets the cluster kernel
+// below handed back; survivor overflow still goes on to ovf_list).
+template <int KCAP, int WARPS, int SRC>
 __global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? 6 : 1) k_grid_candidates(
     const float4* __restrict__ vert4, const int4* __restrict__ tet_idx, int tet_first, int tet_count,
     const int* __restrict__ tet_sel, GridDev G, const unsigned* __restrict__ flags, int kcap_out, int* __restrict__ cand_pad,
     int* __restrict__ cand_cnt, int* __restrict__ pair_cnt, unsigned long long* __restrict__ counters,
-    int* __restrict__ ovf_list) {
+    int* __restrict__ ovf_list, const int* __restrict__ fb_list) {
+  constexpr bool FROM_LIST = SRC == 1;
   extern __shared__ __align__(16) unsigned char grid_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4* s_pd = reinterpret_cast<float4*>(grid_smem) + (size_t)wib * KCAP;
@@ -165,9 +221,9 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? 6 : 1) k_grid_candida
   const int R = G.R, R1 = G.R1;
   const float H1 = 4.f * G.h;
   const int n1 = R1 * R1 * R1;
-  const int n_work = FROM_LIST ? (int)counters[CNT_OVF_TETS] : tet_count;
+  const int n_work = SRC == 1 ? (int)counters[CNT_OVF_TETS] : SRC == 2 ? (int)counters[CNT_FB_TETS] : tet_count;
   for (int work = blockIdx.x * WARPS + wib; work < n_work; work += gridDim.x * WARPS) {
-    const int warp = FROM_LIST ? ovf_list[work] : work;  // local tet index
+    const int warp = SRC == 1 ? ovf_list[work] : SRC == 2 ? fb_list[work] : work;  // local tet index
     const int t = tet_sel ? tet_sel[warp] : tet_first + warp;  // global tet id
     const int4 vi = tet_idx[t];
     const float4 p0 = vert4[vi.x], p1 = vert4[vi.y], p2 = vert4[vi.z], p3 = vert4[vi.w];
@@ -433,51 +489,266 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == 4 ? 6 : 1) k_grid_candida
       cnt = KCAP;  // 2048 survivors of the streaming filter: give up on the rest (counted below)
       if (lane == 0) atomicAdd(&counters[4], 1ull);
     }
-    __syncwarp();
-    // ---- all-pairs domination on the survivors ---------------------------------------------------
-    int n_keep = 0;
-    for (int b = 0; b < cnt; b += 32) {
-      const int a2 = b + lane;
-      bool keep = false;
-      if (a2 < cnt) {
-        keep = true;
-        const float4 e = s_pd[a2];
-        const float wa = s_w[a2];
-        for (int m = 0; m < cnt && keep; m++)
-          if (m != a2 && dominates(s_pd[m], s_w[m], e, wa)) keep = false;
-      }
-      __syncwarp();
-      // removed entries get id = INT_MAX so that the rank sort pushes them to the tail; their
-      // s_pd stays (a dominated site may still dominate others: domination is transitive)
-      if (a2 < cnt && !keep) s_id[a2] = 0x7fffffff;
-      n_keep += __popc(__ballot_sync(0xffffffffu, keep));
+    grid_finish_candidates(s_pd, s_w, s_id, cnt, lane, warp, kcap_out, flags, cand_pad, cand_cnt, pair_cnt, counters);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cluster variant of the search: neighbouring tets share almost all of their candidates (the 6 tets of a Kuhn cube
+// see the same ~40 spheres), so ONE warp walks the grid once for a cluster of GRID_CT consecutive tets and then
+// filters the cluster's list per tet -- the walk, the cheap L_s test and the site loads are paid once per cluster.
+//
+// Cluster bound: g_c, R_c = centre and radius of a ball holding every vertex of the cluster.  For a site s
+//   ub_s = (|s - g_c| + R_c)^2 - w_s  >=  max over the ball of pd_s  >=  max_i pd_s(p_i) of every tet T of the cluster
+// so U_c = min_s ub_s >= U(T), and every candidate of T (L_s(T) <= U(T), header of this file) satisfies
+//   (max(0, |s - g_c| - R_c))^2 - w_s <= U_c.
+// Those sites form the cluster list (shared memory).  Per tet: exact 4-vertex power distances of the whole list ->
+// exact U(T) and kernel set (the owner of every vertex of T is in the list), the per-tet L_s <= U(T) test, kernel-set
+// domination, then the same all-pairs pass as the per-tet kernel.
+// A cluster that cannot be handled here (no site within 4 rings, box wider than 10 cells, list longer than
+// GRID_KC: incoherent tet order or heavy-tailed radii) hands its tets to fb_list -> k_grid_candidates<.., 2>.
+#define GRID_CT 6
+#define GRID_KC 128
+
+__device__ __forceinline__ float warp_max(float v) {
+  return grid_funkey(__reduce_max_sync(0xffffffffu, grid_fkey(v)));
+}
+
+template <int KCAP, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 6) k_grid_candidates_cluster(
+    const float4* __restrict__ vert4, const int4* __restrict__ tet_idx, int tet_first, int tet_count, GridDev G,
+    const unsigned* __restrict__ flags, int kcap_out, int* __restrict__ cand_pad, int* __restrict__ cand_cnt,
+    int* __restrict__ pair_cnt, unsigned long long* __restrict__ counters, int* __restrict__ ovf_list,
+    int* __restrict__ fb_list) {
+  extern __shared__ __align__(16) unsigned char grid_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr size_t PER_WARP = (size_t)GRID_KC * 36 + (size_t)KCAP * 24;
+  unsigned char* base = grid_smem + (size_t)wib * PER_WARP;
+  float4* c_site = reinterpret_cast<float4*>(base);       // cluster list: site (x, y, z, w)
+  float4* c_pd = c_site + GRID_KC;                         // ... its 4 vertex power distances for the current tet
+  float4* s_pd = c_pd + GRID_KC;                           // survivor list of the current tet
+  float* s_w = reinterpret_cast<float*>(s_pd + KCAP);
+  int* s_id = reinterpret_cast<int*>(s_w + KCAP);
+  int* c_id = s_id + KCAP;                                 // cluster list: original site id
+  const int R = G.R;
+  const float wall = fmaxf(G.wmax_all, 0.f);
+  const int n_clusters = (tet_count + GRID_CT - 1) / GRID_CT;
+  for (int cl = blockIdx.x * WARPS + wib; cl < n_clusters; cl += gridDim.x * WARPS) {
+    const int t0 = cl * GRID_CT, nt = min(GRID_CT, tet_count - t0);
+    // ---- ball around the cluster's vertices --------------------------------------------------------------------
+    const bool has = lane < 4 * nt;
+    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has) {
+      const int4 vi = tet_idx[tet_first + t0 + (lane >> 2)];
+      const int c = lane & 3;
+      pv = vert4[c == 0 ? vi.x : c == 1 ? vi.y : c == 2 ? vi.z : vi.w];
     }
-    __syncwarp();
-    if (n_keep > kcap_out) {
-      if (lane == 0) atomicAdd(&counters[4], 1ull);  // truncated: reported, never silent
+    float sx = has ? pv.x : 0.f, sy = has ? pv.y : 0.f, sz = has ? pv.z : 0.f;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
     }
-    int n_flag = 0;
-    for (int b = 0; b < cnt; b += 32) {
-      const int a2 = b + lane;
-      bool fl = false;
-      if (a2 < cnt) {
-        const int id = s_id[a2];
-        if (id != 0x7fffffff) {
-          int rank = 0;
-          for (int m = 0; m < cnt; m++) rank += (s_id[m] < id);
-          if (rank < kcap_out) {
-            cand_pad[(size_t)warp * kcap_out + rank] = id;
-            fl = flags[id] == 1u;
-          }
+    const float inv_n = 1.f / (float)(4 * nt);
+    const float gx = sx * inv_n, gy = sy * inv_n, gz = sz * inv_n;
+    const float4 g4 = make_float4(gx, gy, gz, 0.f);
+    const float Rc = sqrtf(warp_max(has ? pd_plain(g4, pv) : 0.f)) * 1.0001f + 1e-3f;
+    const int ci = min(R - 1, max(0, (int)floorf((gx - G.minx) * G.inv_h)));
+    const int cj = min(R - 1, max(0, (int)floorf((gy - G.miny) * G.inv_h)));
+    const int ck = min(R - 1, max(0, (int)floorf((gz - G.minz) * G.inv_h)));
+    // ---- seed: U_c from rings of cells around the centre ---------------------------------------------------------
+    float bvu = INFINITY;
+    float U = INFINITY;
+    for (int ar = 1; ar <= 4 && !isfinite(U); ar++) {
+      const int sd = 2 * ar + 1, nb = sd * sd * sd;
+      for (int b = 0; b < nb; b += 32) {
+        const int n = b + lane;
+        if (n < nb) {
+          const int di = n / (sd * sd) - ar, dj = (n / sd) % sd - ar, dk = n % sd - ar;
+          const int i = ci + di, j = cj + dj, k = ck + dk;
+          if (max(abs(di), max(abs(dj), abs(dk))) == ar || ar == 1)
+            if (i >= 0 && j >= 0 && k >= 0 && i < R && j < R && k < R) {
+              const int c = (i * R + j) * R + k;
+              for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) {
+                const float4 s = G.site4[q];
+                const float r = sqrtf(pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4)) * 1.0001f + Rc;
+                bvu = fminf(bvu, r * r - s.w);
+              }
+            }
         }
       }
-      n_flag += __popc(__ballot_sync(0xffffffffu, fl));
+      U = warp_min(bvu);
     }
-    if (lane == 0) {
-      cand_cnt[warp] = min(n_keep, kcap_out);
-      pair_cnt[warp] = n_flag;
+    float Ue = U + 4e-6f * (fabsf(U) + 2.f * wall) + 1e-3f;
+    const float rho = Rc + sqrtf(fmaxf(0.f, Ue + wall)) * 1.0001f;
+    const int a = (int)ceilf(rho * G.inv_h * 1.0001f);
+    const int side = 2 * a + 1;
+    int L = 0;
+    bool fallback = !isfinite(U) || side > 10;
+    if (!fallback) {
+      // ---- one walk over the (2a+1)^2 rows of cells; passing sites go to the cluster list -------------------------
+      const int nrows = side * side;
+      const int k0 = max(0, ck - a), k1 = min(R - 1, ck + a);
+      const float lz = G.minz + k0 * G.h, hz = G.minz + (k1 + 1) * G.h;
+      const float dz = fmaxf(0.f, fmaxf(lz - gz, gz - hz));
+      for (int b = 0; b < nrows; b += 32) {
+        const int n = b + lane;
+        int qb = 0, qe = 0;
+        if (n < nrows) {
+          const int i = ci - a + n / side, j = cj - a + n % side;
+          if (i >= 0 && j >= 0 && i < R && j < R) {
+            const float lx = G.minx + i * G.h, ly = G.miny + j * G.h;
+            const float dx = fmaxf(0.f, fmaxf(lx - gx, gx - (lx + G.h)));
+            const float dy = fmaxf(0.f, fmaxf(ly - gy, gy - (ly + G.h)));
+            const float d = fmaxf(0.f, sqrtf(dx * dx + dy * dy + dz * dz) * 0.9999f - Rc);
+            if (d * d - wall <= Ue) {
+              const int c0 = (i * R + j) * R + k0;
+              qb = G.cell_off[c0];
+              qe = G.cell_off[c0 + (k1 - k0) + 1];
+            }
+          }
+        }
+        // the runs of the 32 lanes walked flattened, 32 sites per step
+        const int len = max(qe - qb, 0);
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int f0 = 0; f0 < total; f0 += 32) {
+          const int f = f0 + lane;
+          int lo = 0;
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+            if (v <= f) lo += step;
+          }
+          lo = min(lo, 31);
+          const int o_incl = __shfl_sync(0xffffffffu, incl, lo), o_len = __shfl_sync(0xffffffffu, len, lo);
+          const int o_qb = __shfl_sync(0xffffffffu, qb, lo);
+          bool pass = false;
+          int q = 0;
+          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (f < total) {
+            q = o_qb + (f - (o_incl - o_len));
+            s = G.site4[q];
+            const float dg2 = pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4);
+            const float sq = sqrtf(dg2);
+            const float r = sq * 1.0001f + Rc;
+            bvu = fminf(bvu, r * r - s.w);
+            const float d = fmaxf(0.f, sq * 0.9999f - Rc);
+            pass = d * d - s.w - 4e-6f * (dg2 + s.w) <= Ue;
+          }
+          const unsigned mk = __ballot_sync(0xffffffffu, pass);
+          if (pass) {
+            const int pos = L + __popc(mk & ((1u << lane) - 1u));
+            if (pos < GRID_KC) {
+              c_site[pos] = s;
+              c_id[pos] = G.sorted_id[q];
+            }
+          }
+          L += __popc(mk);
+        }
+        U = fminf(U, warp_min(bvu));
+        Ue = U + 4e-6f * (fabsf(U) + 2.f * wall) + 1e-3f;
+      }
+      fallback = L > GRID_KC;
+    }
+    if (fallback) {
+      unsigned long long at = 0;
+      if (lane == 0) at = atomicAdd(&counters[CNT_FB_TETS], (unsigned long long)nt);
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (lane < nt) fb_list[at + lane] = t0 + lane;
+      continue;
     }
     __syncwarp();
+    // ---- per tet: exact distances of the list, U(T), kernel set, filters, all-pairs ---------------------------------
+    for (int ti = 0; ti < nt; ti++) {
+      const int warp = t0 + ti;  // local tet index
+      const int4 vi = tet_idx[tet_first + warp];
+      const float4 p0 = vert4[vi.x], p1 = vert4[vi.y], p2 = vert4[vi.z], p3 = vert4[vi.w];
+      const float4 t4 = make_float4(0.25f * (p0.x + p1.x + p2.x + p3.x), 0.25f * (p0.y + p1.y + p2.y + p3.y),
+                                    0.25f * (p0.z + p1.z + p2.z + p3.z), 0.f);
+      const float Rt2 = fmaxf(fmaxf(pd_plain(t4, p0), pd_plain(t4, p1)), fmaxf(pd_plain(t4, p2), pd_plain(t4, p3)));
+      const float Rt = sqrtf(Rt2) * 1.0001f + 1e-3f;
+      float bv0 = INFINITY, bv1 = INFINITY, bv2 = INFINITY, bv3 = INFINITY, bvt = INFINITY;
+      int bq0 = -1, bq1 = -1, bq2 = -1, bq3 = -1, bqt = -1;
+      for (int b = 0; b < L; b += 32) {
+        const int i = b + lane;
+        if (i < L) {
+          const float4 e = pd4(c_site[i], p0, p1, p2, p3);
+          c_pd[i] = e;
+          const float m = fmaxf(fmaxf(e.x, e.y), fmaxf(e.z, e.w));
+          if (e.x < bv0) { bv0 = e.x; bq0 = i; }
+          if (e.y < bv1) { bv1 = e.y; bq1 = i; }
+          if (e.z < bv2) { bv2 = e.z; bq2 = i; }
+          if (e.w < bv3) { bv3 = e.w; bq3 = i; }
+          if (m < bvt) { bvt = m; bqt = i; }
+        }
+      }
+      __syncwarp();
+      int kq[5];
+      kq[0] = warp_argmin(bv0, bq0);
+      kq[1] = warp_argmin(bv1, bq1);
+      kq[2] = warp_argmin(bv2, bq2);
+      kq[3] = warp_argmin(bv3, bq3);
+      kq[4] = warp_argmin(bvt, bqt);
+      const float Ut = warp_min(bvt);
+      const float Uet = Ut + 4e-6f * (fabsf(Ut) + 2.f * wall) + 1e-3f;
+      float4 kE[5];
+      float kW[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        if (kq[k] >= 0) {
+          kE[k] = c_pd[kq[k]];
+          kW[k] = c_site[kq[k]].w;
+        } else {
+          kE[k] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+          kW[k] = 0.f;
+        }
+      }
+      int cnt = 0;
+      for (int b = 0; b < L; b += 32) {
+        const int i = b + lane;
+        bool ok = false;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        float w = 0.f;
+        if (i < L) {
+          const float4 s = c_site[i];
+          e = c_pd[i];
+          w = s.w;
+          const float dg2 = pd_plain(make_float4(s.x, s.y, s.z, 0.f), t4);
+          const float d = fmaxf(0.f, sqrtf(dg2) * 0.9999f - Rt);
+          ok = d * d - w - 4e-6f * (dg2 + w) <= Uet;
+#pragma unroll
+          for (int kk = 0; kk < 5; kk++) ok = ok && !dominates(kE[kk], kW[kk], e, w);
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const int pos = cnt + __popc(mk & ((1u << lane) - 1u));
+          if (pos < KCAP) {
+            s_id[pos] = c_id[i];
+            s_pd[pos] = e;
+            s_w[pos] = w;
+          }
+        }
+        cnt += __popc(mk);
+      }
+      if (cnt > KCAP) {  // survivors do not fit: the big-list pass redoes the tet
+        if (lane == 0) {
+          const unsigned long long at = atomicAdd(&counters[CNT_OVF_TETS], 1ull);
+          ovf_list[at] = warp;
+          cand_cnt[warp] = 0;
+          pair_cnt[warp] = 0;
+        }
+        __syncwarp();
+        continue;
+      }
+      grid_finish_candidates(s_pd, s_w, s_id, cnt, lane, warp, kcap_out, flags, cand_pad, cand_cnt, pair_cnt, counters);
+    }
   }
 }
 

@@ -427,23 +427,38 @@ static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan&
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[ctx->device & 63];  // function attributes are per device
   if (!attr_set) {
-    MB_CUDA(cudaFuncSetAttribute(k_grid_candidates<GRID_BIG_KCAP, 1, true>,
+    MB_CUDA(cudaFuncSetAttribute(k_grid_candidates<GRID_BIG_KCAP, 1, 1>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
     attr_set = true;
   }
-  // fast pass: one warp per tet.  The cost per tet varies several-fold, so the hardware block scheduler
-  // balances better than a static stride: plain grid up to 64 waves, strided beyond
-  const int want = (sp.count + WARPS - 1) / WARPS;
-  const int blocks = std::max(1, std::min(want, ctx->sm_count * 6 * 64));
-  ctx->n_launches++;
-  k_grid_candidates<KCAP, WARPS, false><<<blocks, 32 * WARPS, smem, s>>>(
-      M.vert4.p, M.tet_idx.p, sp.first, sp.count, sp.sel, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
-      ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p);
+  if (sp.sel == nullptr && ctx->k2_variant != 1) {
+    // fast pass, cluster search: one warp per GRID_CT consecutive tets (one grid walk per cluster); clusters it cannot
+    // handle come back through fb_list to the per-tet search (usually none -> the second launch returns at once)
+    const int n_clusters = (sp.count + GRID_CT - 1) / GRID_CT;
+    const int blocks_c = std::max(1, std::min((n_clusters + WARPS - 1) / WARPS, ctx->sm_count * 6 * 64));
+    const size_t smem_c = (size_t)WARPS * ((size_t)GRID_KC * 36 + (size_t)KCAP * 24);
+    ctx->n_launches += 2;
+    k_grid_candidates_cluster<KCAP, WARPS><<<blocks_c, 32 * WARPS, smem_c, s>>>(
+        M.vert4.p, M.tet_idx.p, sp.first, sp.count, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p, ctx->cand_cnt.p,
+        ctx->tet_cnt.p, cnt, ctx->ovf_list.p, ctx->fb_list.p);
+    k_grid_candidates<KCAP, WARPS, 2><<<ctx->sm_count * 6, 32 * WARPS, smem, s>>>(
+        M.vert4.p, M.tet_idx.p, sp.first, sp.count, sp.sel, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
+        ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p, ctx->fb_list.p);
+  } else {
+    // fast pass: one warp per tet.  The cost per tet varies several-fold, so the hardware block scheduler
+    // balances better than a static stride: plain grid up to 64 waves, strided beyond
+    const int want = (sp.count + WARPS - 1) / WARPS;
+    const int blocks = std::max(1, std::min(want, ctx->sm_count * 6 * 64));
+    ctx->n_launches++;
+    k_grid_candidates<KCAP, WARPS, 0><<<blocks, 32 * WARPS, smem, s>>>(
+        M.vert4.p, M.tet_idx.p, sp.first, sp.count, sp.sel, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
+        ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p, ctx->fb_list.p);
+  }
   // overflow pass: reads the number of handed-over tets on the device (usually zero -> returns)
   ctx->n_launches++;
-  k_grid_candidates<GRID_BIG_KCAP, 1, true><<<ctx->sm_count * 2, 32, smem_big, s>>>(
+  k_grid_candidates<GRID_BIG_KCAP, 1, 1><<<ctx->sm_count * 2, 32, smem_big, s>>>(
       M.vert4.p, M.tet_idx.p, sp.first, sp.count, sp.sel, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
-      ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p);
+      ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p, ctx->fb_list.p);
   MB_CUDA(cudaGetLastError());
 }
 
@@ -455,6 +470,7 @@ static void grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan& sp, in
   ctx->cand_pad.reserve((size_t)sp.count * kcap);
   ctx->cand_cnt.reserve((size_t)sp.count + 1);
   ctx->ovf_list.reserve((size_t)sp.count + 1);
+  ctx->fb_list.reserve((size_t)sp.count + GRID_CT);
   if (grid_k > 0 && grid_k <= 32)
     launch_grid_candidates<32>(ctx, G, sp, kcap);
   else if (kcap == 96)
