@@ -514,8 +514,8 @@ __device__ __forceinline__ float warp_max(float v) {
   return grid_funkey(__reduce_max_sync(0xffffffffu, grid_fkey(v)));
 }
 
-template <int KCAP, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 6) k_grid_candidates_cluster(
+template <int KCAP, int WARPS, int CT, int NB>
+__global__ void __launch_bounds__(32 * WARPS, NB) k_grid_candidates_cluster(
     const float4* __restrict__ vert4, const int4* __restrict__ tet_idx, int tet_first, int tet_count, GridDev G,
     const unsigned* __restrict__ flags, int kcap_out, int* __restrict__ cand_pad, int* __restrict__ cand_cnt,
     int* __restrict__ pair_cnt, unsigned long long* __restrict__ counters, int* __restrict__ ovf_list,
@@ -532,9 +532,9 @@ __global__ void __launch_bounds__(32 * WARPS, 6) k_grid_candidates_cluster(
   int* c_id = s_id + KCAP;                                 // cluster list: original site id
   const int R = G.R;
   const float wall = fmaxf(G.wmax_all, 0.f);
-  const int n_clusters = (tet_count + GRID_CT - 1) / GRID_CT;
+  const int n_clusters = (tet_count + CT - 1) / CT;
   for (int cl = blockIdx.x * WARPS + wib; cl < n_clusters; cl += gridDim.x * WARPS) {
-    const int t0 = cl * GRID_CT, nt = min(GRID_CT, tet_count - t0);
+    const int t0 = cl * CT, nt = min(CT, tet_count - t0);
     // ---- ball around the cluster's vertices --------------------------------------------------------------------
     const bool has = lane < 4 * nt;
     float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);

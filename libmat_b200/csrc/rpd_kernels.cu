@@ -434,13 +434,18 @@ static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan&
   if (sp.sel == nullptr && ctx->k2_variant != 1) {
     // fast pass, cluster search: one warp per GRID_CT consecutive tets (one grid walk per cluster); clusters it cannot
     // handle come back through fb_list to the per-tet search (usually none -> the second launch returns at once)
-    const int n_clusters = (sp.count + GRID_CT - 1) / GRID_CT;
-    const int blocks_c = std::max(1, std::min((n_clusters + WARPS - 1) / WARPS, ctx->sm_count * 6 * 64));
     const size_t smem_c = (size_t)WARPS * ((size_t)GRID_KC * 36 + (size_t)KCAP * 24);
     ctx->n_launches += 2;
-    k_grid_candidates_cluster<KCAP, WARPS><<<blocks_c, 32 * WARPS, smem_c, s>>>(
-        M.vert4.p, M.tet_idx.p, sp.first, sp.count, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p, ctx->cand_cnt.p,
-        ctx->tet_cnt.p, cnt, ctx->ovf_list.p, ctx->fb_list.p);
+    auto launch_c = [&](auto kern, int ct) {
+      const int n_clusters = (sp.count + ct - 1) / ct;
+      const int blocks_c = std::max(1, std::min((n_clusters + WARPS - 1) / WARPS, ctx->sm_count * 6 * 64));
+      kern<<<blocks_c, 32 * WARPS, smem_c, s>>>(M.vert4.p, M.tet_idx.p, sp.first, sp.count, G, ctx->sites.flags.p, kcap_out,
+                                                ctx->cand_pad.p, ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p,
+                                                ctx->fb_list.p);
+    };
+    // (measured at config 2 / config 4: clusters of 6 tets 0.42 / 3.5 ms, of 4 tets 0.47 ms, of 8 tets 0.53 / 6.1 ms --
+    // 8 straddles two Kuhn cubes; 8 blocks per SM instead of 6: no change)
+    launch_c(k_grid_candidates_cluster<KCAP, WARPS, GRID_CT, 6>, GRID_CT);
     k_grid_candidates<KCAP, WARPS, 2><<<ctx->sm_count * 6, 32 * WARPS, smem, s>>>(
         M.vert4.p, M.tet_idx.p, sp.first, sp.count, sp.sel, G, ctx->sites.flags.p, kcap_out, ctx->cand_pad.p,
         ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p, ctx->fb_list.p);
@@ -470,7 +475,7 @@ static void grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan& sp, in
   ctx->cand_pad.reserve((size_t)sp.count * kcap);
   ctx->cand_cnt.reserve((size_t)sp.count + 1);
   ctx->ovf_list.reserve((size_t)sp.count + 1);
-  ctx->fb_list.reserve((size_t)sp.count + GRID_CT);
+  ctx->fb_list.reserve((size_t)sp.count + 8);
   if (grid_k > 0 && grid_k <= 32)
     launch_grid_candidates<32>(ctx, G, sp, kcap);
   else if (kcap == 96)
