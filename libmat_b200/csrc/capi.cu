@@ -69,6 +69,7 @@ mb_ctx* mb_create(int device, int* err) {
   if (const char* v = getenv("MB_NO_CULL")) ctx->no_cull = atoi(v) != 0;
   if (const char* v = getenv("MB_CLIP_VARIANT")) ctx->clip_variant = atoi(v);
   if (const char* v = getenv("MB_K2_VARIANT")) ctx->k2_variant = atoi(v);
+  if (const char* v = getenv("MB_STREAM_VARIANT")) ctx->stream_variant = atoi(v);
   if (const char* v = getenv("MB_TRACE")) {
     ctx->trace_level = atoi(v);
     ctx->trace_on = ctx->trace_level != 0;

@@ -170,6 +170,7 @@ struct HostScalars {
   long long total_words;
   RpdCounters counters;
   long long zero;
+  long long cut_off[40];   // staged streamed run: pair offsets at the span cuts (k_publish_cuts)
   unsigned long long seq;  // written last by every publish kernel; the host spins on it
 };
 
@@ -268,6 +269,7 @@ struct mb_ctx {
   std::vector<int4> h_tet_fid, h_tet_fadj;  // host copies of f_ids / f_adjs (slim records: tet-face plane ids)
   bool h_tet_planes_valid = false;
   double pairs_per_tet_hint = 0.0;  // grid mode: 1.5 x the largest pairs-per-tet seen (speculative span launches)
+  int stream_variant = 0;           // MB_STREAM_VARIANT=1 (A/B tests): streamed runs redo K2 per span instead of once up front
   int k2_variant = 0;               // MB_K2_VARIANT=1 (A/B tests): per-tet candidate search instead of the cluster search
   int clip_variant = 0;             // MB_CLIP_VARIANT=1 (A/B tests): grid-kNN first pass with the state-machine kernel k_clip
   bool no_cull = false;             // MB_NO_CULL=1 (debug / parity tests): no conservative cull of listed neighbours

@@ -532,9 +532,12 @@ __global__ void __launch_bounds__(32 * WARPS, NB) k_grid_candidates_cluster(
   int* c_id = s_id + KCAP;                                 // cluster list: original site id
   const int R = G.R;
   const float wall = fmaxf(G.wmax_all, 0.f);
-  const int n_clusters = (tet_count + CT - 1) / CT;
+  // clusters are aligned to GLOBAL tet ids divisible by CT, whatever the span's first tet: the 6 tets of a Kuhn cube
+  // stay together in every span / shard (a cluster straddling two cubes has a ball 1.5x as wide and overflows the list)
+  const int shift = tet_first % CT;
+  const int n_clusters = (tet_count + shift + CT - 1) / CT;
   for (int cl = blockIdx.x * WARPS + wib; cl < n_clusters; cl += gridDim.x * WARPS) {
-    const int t0 = cl * CT, nt = min(CT, tet_count - t0);
+    const int t0 = max(0, cl * CT - shift), nt = min((cl + 1) * CT - shift, tet_count) - t0;
     // ---- ball around the cluster's vertices --------------------------------------------------------------------
     const bool has = lane < 4 * nt;
     float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -302,7 +302,14 @@ template <int LEAN>
 __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* __restrict__ pair_blob,
                          const int* __restrict__ pair_words, const unsigned long long* __restrict__ packed_off,
                          long long n_pairs, uint32_t* __restrict__ blob, long long* __restrict__ cell_off,
-                         long long total_words, long long n_cells, long long base_bytes) {
+                         long long total_words, long long n_cells, long long base_bytes,
+                         const unsigned long long* __restrict__ total_dev = nullptr) {
+  // total_dev: the packed scan total still on the device (the gather is launched before the host has seen it)
+  if (total_dev) {
+    const unsigned long long v = *total_dev;
+    total_words = (long long)(v & PACK_MASK);
+    n_cells = (long long)(v >> PACK_SHIFT);
+  }
   // 8 lanes per record
   const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int lane = threadIdx.x & 7;
@@ -352,9 +359,39 @@ __global__ void k_publish_k3(const uint32_t* __restrict__ counters, const unsign
   if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(&hs->seq) = seq;
 }
 
+// staged streamed run: the pair offsets at the span cuts and the candidate-stage counters, one launch
+struct CutList {
+  int n;
+  int tet[36];
+};
+__global__ void k_publish_cuts(const int* __restrict__ tet_off, CutList cuts, const uint32_t* __restrict__ counters,
+                               HostScalars* __restrict__ hs, unsigned long long seq) {
+  if ((int)threadIdx.x < cuts.n) hs->cut_off[threadIdx.x] = tet_off[cuts.tet[threadIdx.x]];
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&hs->counters);
+  for (int i = threadIdx.x; i < (int)(sizeof(RpdCounters) / 4); i += blockDim.x) dst[i] = counters[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(&hs->seq) = seq;
+}
+
 // =============================================================================================
 // K1 host side: grid build (counting sort by cell + max-weight pyramid), K2 launch
 // =============================================================================================
+// Zero-fill by a KERNEL, not cudaMemsetAsync: the driver runs small memsets on a copy engine, where they queue behind
+// the bulk D2H copy of the previous tet span (measured: every span that overlapped a 27 MB host copy ran 0.2-0.4 ms
+// late -- its counter / tail-word memsets were waiting on the copy engine).
+__global__ void k_zero_u32(unsigned* __restrict__ p, size_t n_words) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+static void dev_zero(mb_ctx* ctx, void* p, size_t bytes) {
+  if (bytes == 0) return;
+  const size_t n = bytes / 4;  // every caller zeroes whole 4-byte words
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+  ctx->n_launches++;
+  k_zero_u32<<<std::max(1, blocks), 256, 0, ctx->stream>>>(reinterpret_cast<unsigned*>(p), n);
+  MB_CUDA(cudaGetLastError());
+}
+
 static GridDev grid_build(mb_ctx* ctx) {
   SitesDev& S = ctx->sites;
   cudaStream_t s = ctx->stream;
@@ -380,7 +417,7 @@ static GridDev grid_build(mb_ctx* ctx) {
   ctx->grid_site4.reserve(S.n_site);
   ctx->grid_wmax0.reserve(nc);
   ctx->grid_wmax1.reserve(n1);
-  MB_CUDA(cudaMemsetAsync(ctx->grid_cnt.p, 0, sizeof(int) * ((size_t)nc + 1), s));
+  dev_zero(ctx, ctx->grid_cnt.p, sizeof(int) * ((size_t)nc + 1));
   ctx->n_launches++;
   k_grid_count<<<(S.n_site + 255) / 256, 256, 0, s>>>(S.site4.p, S.n_site, G, ctx->grid_cnt.p, ctx->grid_cell_of.p);
   {
@@ -390,7 +427,7 @@ static GridDev grid_build(mb_ctx* ctx) {
     ctx->n_launches += 2;  // DeviceScanInitKernel + DeviceScanKernel
     MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, ctx->grid_cnt.p, ctx->grid_off.p, nc + 1, s));
   }
-  MB_CUDA(cudaMemsetAsync(ctx->grid_cnt.p, 0, sizeof(int) * ((size_t)nc + 1), s));
+  dev_zero(ctx, ctx->grid_cnt.p, sizeof(int) * ((size_t)nc + 1));
   ctx->n_launches++;
   k_grid_scatter<<<(S.n_site + 255) / 256, 256, 0, s>>>(S.site4.p, S.n_site, ctx->grid_cell_of.p,
                                                         ctx->grid_off.p, ctx->grid_cnt.p, ctx->grid_sorted_id.p);
@@ -437,7 +474,7 @@ static void launch_grid_candidates(mb_ctx* ctx, const GridDev& G, const TetSpan&
     const size_t smem_c = (size_t)WARPS * ((size_t)GRID_KC * 36 + (size_t)KCAP * 24);
     ctx->n_launches += 2;
     auto launch_c = [&](auto kern, int ct) {
-      const int n_clusters = (sp.count + ct - 1) / ct;
+      const int n_clusters = (sp.count + sp.first % ct + ct - 1) / ct;  // aligned to global tet ids (see the kernel)
       const int blocks_c = std::max(1, std::min((n_clusters + WARPS - 1) / WARPS, ctx->sm_count * 6 * 64));
       kern<<<blocks_c, 32 * WARPS, smem_c, s>>>(M.vert4.p, M.tet_idx.p, sp.first, sp.count, G, ctx->sites.flags.p, kcap_out,
                                                 ctx->cand_pad.p, ctx->cand_cnt.p, ctx->tet_cnt.p, cnt, ctx->ovf_list.p,
@@ -709,7 +746,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     res->evs.push_back(ev[i]);
   }
   ctx->counters.reserve(1);
-  MB_CUDA(cudaMemsetAsync(ctx->counters.p, 0, sizeof(RpdCounters), s));
+  dev_zero(ctx, ctx->counters.p, sizeof(RpdCounters));
   MB_CUDA(cudaEventRecord(ev[0], s));
 
   // ---- K2: candidate (tet, site) pairs ---------------------------------------------------------
@@ -730,7 +767,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     } else {
       grid_candidates(ctx, *grid, sp, opts ? opts->grid_k : 0);  // fills tet_cnt + cand_list pad
     }
-    MB_CUDA(cudaMemsetAsync(ctx->tet_cnt.p + t_count, 0, sizeof(int), s));
+    dev_zero(ctx, ctx->tet_cnt.p + t_count, sizeof(int));
     exclusive_scan<int>(ctx, ctx->tet_cnt.p, ctx->tet_off.p, (long long)t_count + 1);
     if (spec) {
       // SPECULATIVE: the pair count stays on the device; arrays are sized by the pairs-per-tet seen so far
@@ -776,7 +813,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   for (int attempt = 0; attempt < 2 && n_pairs > 0; attempt++) {
     ctx->scratch.reserve(scratch_words);
     if (spec)  // entries beyond the true pair count are never written by K3: they must read as "no record"
-      MB_CUDA(cudaMemsetAsync(ctx->pair_words.p, 0, sizeof(int) * (size_t)(n_pairs + 1), s));
+      dev_zero(ctx, ctx->pair_words.p, sizeof(int) * (size_t)(n_pairs + 1));
     ClipArgs A;
     A.vert4 = M.vert4.p;
     A.tet_idx = M.tet_idx.p;
@@ -826,7 +863,7 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     // one exclusive scan over packed (valid count << 40 | record words) gives every pair both its cell
     // index and its word offset in (tet, site) order
     word_off.reserve((size_t)n_pairs + 1);
-    MB_CUDA(cudaMemsetAsync(ctx->pair_words.p + n_pairs, 0, sizeof(int), s));
+    dev_zero(ctx, ctx->pair_words.p + n_pairs, sizeof(int));
     {
       unsigned long long* outp = reinterpret_cast<unsigned long long*>(word_off.p);
       size_t tmp = 0;
@@ -876,10 +913,10 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
     MB_REQUIRE(attempt == 0, MB_ERR_NOMEM, "compact scratch overflow after resize");
     {  // reset K3's counters only (the candidate-stage counters [4] and [16] stay)
       unsigned long long* c = reinterpret_cast<unsigned long long*>(ctx->counters.p);
-      MB_CUDA(cudaMemsetAsync(c, 0, 4 * sizeof(unsigned long long), s));
-      MB_CUDA(cudaMemsetAsync(c + 5, 0, 11 * sizeof(unsigned long long), s));
-      MB_CUDA(cudaMemsetAsync(c + CNT_WORK_CURSOR, 0, sizeof(unsigned long long), s));
-      MB_CUDA(cudaMemsetAsync(c + 18, 0, 5 * sizeof(unsigned long long), s));  // gc, redo count, second cursor, flagged pairs / cells
+      dev_zero(ctx, c, 4 * sizeof(unsigned long long));
+      dev_zero(ctx, c + 5, 11 * sizeof(unsigned long long));
+      dev_zero(ctx, c + CNT_WORK_CURSOR, sizeof(unsigned long long));
+      dev_zero(ctx, c + 18, 5 * sizeof(unsigned long long));  // gc, redo count, second cursor, flagged pairs / cells
     }
     MB_CUDA(cudaEventRecord(ev[1], s));
   }
@@ -910,6 +947,9 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   res->n_gc += (long)hc.n_gc;
   res->n_flag_pairs += (long)hc.reserved[0];
   res->n_flag_cells += (long)hc.reserved[1];
+  if (ctx->trace_level >= 2)
+    fprintf(stderr, "[libmat_b200 trace] span of %d tets: %lld pairs, %llu tets handed back by the cluster search, %llu to the big-list pass, %llu redo cells\n",
+            t_count, n_pairs, hc.reserved[2], hc.n_ovf_tets, hc.n_redo);
   for (int i = 0; i < 10; i++) res->hist[i] += (long)hc.hist[i];
 
   // ---- gather into (tet, site) order -------------------------------------------------------------
@@ -937,6 +977,223 @@ static SpanStats rpd_run_span(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_resul
   st.total_words = total_words;
   MB_CUDA(cudaEventRecord(ev[3], s));
   TRACE(6);  // launch gather
+  return st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Staged streamed run (grid candidates).  Every launch of a small kernel costs ~7 us of stream time here (launch
+// throughput, measured), and a tet span that goes through K2 -> K3 -> ordering takes 16 launches: three spans cost
+// 0.5 ms more than one.  So the candidate stage runs ONCE for all tets of the run (rpd_candidates_all: K2, the pair
+// offsets, the pair arrays; the pair offsets at the span cuts come back in one synchronisation) and only K3 + the
+// ordering are cut into spans -- pair ranges that end on tet boundaries (rpd_clip_range: 8 launches, one wait).
+// ---------------------------------------------------------------------------------------------------------------
+static long long rpd_candidates_all(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res, const TetSpan& sp,
+                                    const GridDev& grid, const std::vector<int>& cut_tets, std::vector<long long>& cut_pairs) {
+  cudaStream_t s = ctx->stream;
+  const int t_count = sp.count;
+  HostScalars* hs = host_scalars(ctx);
+  double tr_ = ctx->trace_on ? now_us() : 0.0;
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; i++) {
+    ev[i] = take_event(ctx);
+    res->evs.push_back(ev[i]);
+  }
+  ctx->counters.reserve(1);
+  dev_zero(ctx, ctx->counters.p, sizeof(RpdCounters));
+  MB_CUDA(cudaEventRecord(ev[0], s));
+  ctx->tet_cnt.reserve((size_t)t_count + 1);
+  ctx->tet_off.reserve((size_t)t_count + 1);
+  grid_candidates(ctx, grid, sp, opts ? opts->grid_k : 0);
+  dev_zero(ctx, ctx->tet_cnt.p + t_count, sizeof(int));
+  exclusive_scan<int>(ctx, ctx->tet_cnt.p, ctx->tet_off.p, (long long)t_count + 1);
+  CutList cl;
+  cl.n = (int)cut_tets.size();
+  MB_REQUIRE(cl.n >= 2 && cl.n <= 36, MB_ERR_ARG, "bad span count");
+  for (int i = 0; i < cl.n; i++) cl.tet[i] = cut_tets[i];
+  ctx->n_launches++;
+  k_publish_cuts<<<1, 64, 0, s>>>(ctx->tet_off.p, cl, reinterpret_cast<const uint32_t*>(ctx->counters.p), hs, ++ctx->publish_seq);
+  MB_CUDA(cudaGetLastError());
+  TRACE(0);
+  wait_published(ctx);
+  TRACE(1);
+  cut_pairs.assign(hs->cut_off, hs->cut_off + cl.n);
+  const long long n_pairs = cut_pairs.back();
+  const RpdCounters hc = hs->counters;
+  res->n_cand_overflow += (long)hc.n_cand_overflow;
+  res->n_ovf_tets += (long)hc.n_ovf_tets;
+  if (ctx->trace_level >= 2)
+    fprintf(stderr, "[libmat_b200 trace] candidates of %d tets: %lld pairs, %llu tets handed back by the cluster search, %llu to the big-list pass\n",
+            t_count, n_pairs, hc.reserved[2], hc.n_ovf_tets);
+  ctx->pair_tet.reserve((size_t)n_pairs + 1);
+  ctx->pair_site.reserve((size_t)n_pairs + 1);
+  ctx->pair_local.reserve((size_t)n_pairs + 1);
+  ctx->pair_status.reserve((size_t)n_pairs + 1);
+  ctx->pair_blob.reserve((size_t)n_pairs + 1);
+  ctx->pair_words.reserve((size_t)n_pairs + 1);
+  ctx->word_off.reserve((size_t)n_pairs + cl.n + 2);
+  if (n_pairs > 0) grid_fill_pairs(ctx, sp, n_pairs);
+  for (int i = 1; i < 4; i++) MB_CUDA(cudaEventRecord(ev[i], s));
+  if (t_count > 0)
+    ctx->pairs_per_tet_hint = std::max(ctx->pairs_per_tet_hint, 1.5 * (double)n_pairs / (double)t_count);
+  res->n_pairs += (long)n_pairs;
+  return n_pairs;
+}
+
+// K3 + ordering of the pairs [p0, p1) of the run prepared by rpd_candidates_all (range index c of the run)
+static SpanStats rpd_clip_range(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res, const TetSpan& sp, long long p0,
+                                long long p1, int c, DevBuf<uint32_t>& blob, DevBuf<long long>& cell_off,
+                                long long base_bytes, int lean) {
+  TetMeshDev& M = ctx->mesh;
+  SitesDev& S = ctx->sites;
+  cudaStream_t s = ctx->stream;
+  const long long n_pairs = p1 - p0;
+  const int G = opts && opts->lanes_per_cell ? opts->lanes_per_cell : 8;
+  HostScalars* hs = host_scalars(ctx);
+  double tr_ = ctx->trace_on ? now_us() : 0.0;
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; i++) {
+    ev[i] = take_event(ctx);
+    res->evs.push_back(ev[i]);
+  }
+  MB_CUDA(cudaEventRecord(ev[0], s));
+  MB_CUDA(cudaEventRecord(ev[1], s));
+  SpanStats st;
+  st.n_pairs = n_pairs;
+  cell_off.reserve(1);
+  if (n_pairs == 0) {
+    MB_CUDA(cudaEventRecord(ev[2], s));
+    MB_CUDA(cudaMemcpyAsync(cell_off.p, &base_bytes, sizeof(long long), cudaMemcpyHostToDevice, s));
+    MB_CUDA(cudaEventRecord(ev[3], s));
+    return st;
+  }
+  // scratch this range may use: typical record ~80 words; retried with the exact need if it overflows.  (Not the whole
+  // of ctx->scratch, which a one-shot run may have grown to the size of the full result: the range's destination
+  // buffer is sized by this bound.)
+  // (+ the bump allocator's granularity: every cell group of the persistent grid holds a partly used 4 KB chunk)
+  size_t scratch_words = (size_t)n_pairs * 96 + (size_t)ctx->sm_count * 8 * 16 * CLIP_CHUNK_WORDS + (1u << 20);
+  RpdCounters hc;
+  long long total_words = 0;
+  unsigned long long* word_off = reinterpret_cast<unsigned long long*>(ctx->word_off.p) + p0 + c;  // own slot per range
+  for (int attempt = 0; attempt < 2; attempt++) {
+    ctx->scratch.reserve(scratch_words);
+    dev_zero(ctx, ctx->counters.p, sizeof(RpdCounters));
+    ClipArgs A;
+    A.vert4 = M.vert4.p;
+    A.tet_idx = M.tet_idx.p;
+    A.tet_fadj = M.tet_fadj.p;
+    A.tet_fid = M.tet_fid.p;
+    A.tet_e6 = M.tet_e6.p;
+    A.tet_geo = M.tet_geo.p;
+    A.tet_vadj = M.tet_vadj.p;
+    A.site4 = S.site4.p;
+    A.n_site = S.n_site;
+    if (S.given) {  // given-neighbours semantics with pairs from the grid search: the listed neighbours, in list order
+      A.nbr = S.nbr.p;
+      A.nbr_stride = S.site_k;
+      A.nbr_cnt = nullptr;
+    } else {
+      A.nbr = ctx->cand_pad.p;
+      A.nbr_stride = ctx->cand_kcap;
+      A.nbr_cnt = ctx->cand_cnt.p;
+    }
+    A.tet_first = sp.first;
+    A.tet_id_base = M.tet_id_base;
+    A.pair_tet = ctx->pair_tet.p + p0;
+    A.pair_site = ctx->pair_site.p + p0;
+    A.pair_local = ctx->pair_local.p + p0;
+    A.n_pairs = n_pairs;
+    A.n_pairs_dev = nullptr;
+    A.pair_status = ctx->pair_status.p + p0;
+    A.pair_blob = ctx->pair_blob.p + p0;
+    A.pair_words = ctx->pair_words.p + p0;
+    A.scratch = ctx->scratch.p;
+    A.scratch_words = scratch_words;
+    A.counters = reinterpret_cast<unsigned long long*>(ctx->counters.p);
+    A.no_cull = ctx->no_cull ? 1 : 0;
+    A.security_radius = 0;
+    const bool pt = A.nbr_cnt != nullptr;
+    if (G == 4)
+      pt ? launch_clip<4, true>(ctx, A) : launch_clip<4, false>(ctx, A);
+    else if (G == 8)
+      pt ? launch_clip<8, true>(ctx, A) : launch_clip<8, false>(ctx, A);
+    else if (G == 16)
+      pt ? launch_clip<16, true>(ctx, A) : launch_clip<16, false>(ctx, A);
+    else
+      pt ? launch_clip<32, true>(ctx, A) : launch_clip<32, false>(ctx, A);
+    MB_CUDA(cudaEventRecord(ev[2], s));
+    {
+      // exclusive scan over packed (valid count | record words): out[n_pairs] (the total) does not depend on in[n_pairs]
+      size_t tmp = 0;
+      ctx->n_launches += 2;
+      const int* in_words = ctx->pair_words.p + p0;
+      if (lean == 2) {
+        cub::TransformInputIterator<unsigned long long, PackWords<2>, const int*> in(in_words, PackWords<2>());
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, word_off, n_pairs + 1, s));
+        ctx->cub_tmp.reserve(tmp);
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, word_off, n_pairs + 1, s));
+      } else if (lean == 1) {
+        cub::TransformInputIterator<unsigned long long, PackWords<1>, const int*> in(in_words, PackWords<1>());
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, word_off, n_pairs + 1, s));
+        ctx->cub_tmp.reserve(tmp);
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, word_off, n_pairs + 1, s));
+      } else {
+        cub::TransformInputIterator<unsigned long long, PackWords<0>, const int*> in(in_words, PackWords<0>());
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, word_off, n_pairs + 1, s));
+        ctx->cub_tmp.reserve(tmp);
+        MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, word_off, n_pairs + 1, s));
+      }
+    }
+    ctx->n_launches++;
+    k_publish_k3<<<1, 64, 0, s>>>(reinterpret_cast<const uint32_t*>(ctx->counters.p), word_off + n_pairs, nullptr, hs,
+                                  ++ctx->publish_seq);
+    MB_CUDA(cudaGetLastError());
+    // the gather goes out BEFORE the host has seen the totals (they stay on the device: total_dev): the stream does not
+    // idle through the host's wake-up, which takes up to ~0.1 ms while a bulk D2H copy is crossing PCIe.  Its output is
+    // bounded by the scratch K3 wrote, so the destination is sized by the scratch capacity.
+    cell_off.reserve((size_t)n_pairs + 1);
+    blob.reserve(scratch_words + 4);
+    {
+      ctx->n_launches++;
+      const unsigned nb = (unsigned)((n_pairs * 8 + 255) / 256);
+      if (lean == 2)
+        k_gather<2><<<nb, 256, 0, s>>>(ctx->scratch.p, ctx->pair_blob.p + p0, ctx->pair_words.p + p0, word_off, n_pairs, blob.p,
+                                       cell_off.p, 0, 0, base_bytes, word_off + n_pairs);
+      else if (lean == 1)
+        k_gather<1><<<nb, 256, 0, s>>>(ctx->scratch.p, ctx->pair_blob.p + p0, ctx->pair_words.p + p0, word_off, n_pairs, blob.p,
+                                       cell_off.p, 0, 0, base_bytes, word_off + n_pairs);
+      else
+        k_gather<0><<<nb, 256, 0, s>>>(ctx->scratch.p, ctx->pair_blob.p + p0, ctx->pair_words.p + p0, word_off, n_pairs, blob.p,
+                                       cell_off.p, 0, 0, base_bytes, word_off + n_pairs);
+      MB_CUDA(cudaGetLastError());
+    }
+    MB_CUDA(cudaEventRecord(ev[3], s));
+    TRACE(2);
+    wait_published(ctx);
+    TRACE(3);
+    hc = hs->counters;
+    total_words = hs->total_words & PACK_MASK;
+    MB_REQUIRE(hc.n_valid <= PACK_MAX_CELLS && hc.blob_words <= PACK_MASK, MB_ERR_ARG,
+               "more valid cells / record words in one span than the ordering scan can index: use more spans");
+    if (hc.blob_words <= scratch_words) break;
+    scratch_words = (size_t)hc.blob_words + (1u << 20);  // scratch too small: K3 + ordering + gather again (rare)
+    MB_REQUIRE(attempt == 0, MB_ERR_NOMEM, "compact scratch overflow after resize");
+  }
+  st.n_cells = (long long)hc.n_valid;
+  st.total_words = total_words;
+  res->n_cells += (long)hc.n_valid;
+  res->n_clips += (long)hc.n_clips;
+  res->n_culled += (long)hc.n_culled;
+  res->n_exact += (long)hc.pad[0];
+  res->n_redo += (long)hc.n_redo;
+  res->n_gc += (long)hc.n_gc;
+  res->n_flag_pairs += (long)hc.reserved[0];
+  res->n_flag_cells += (long)hc.reserved[1];
+  for (int i = 0; i < 10; i++) res->hist[i] += (long)hc.hist[i];
+  if (st.n_cells == 0) {
+    MB_CUDA(cudaMemcpyAsync(cell_off.p, &base_bytes, sizeof(long long), cudaMemcpyHostToDevice, s));
+    MB_CUDA(cudaEventRecord(ev[3], s));
+  }
+  TRACE(6);
   return st;
 }
 
@@ -1011,7 +1268,7 @@ int rpd_incremental_select(mb_ctx* ctx, const mb_rpd_opts* opts) {
   const int n_tet = M.n_tet;
   // candidate lists of ALL tets with the new sites (K1 + K2)
   ctx->counters.reserve(1);
-  MB_CUDA(cudaMemsetAsync(ctx->counters.p, 0, sizeof(RpdCounters), s));
+  dev_zero(ctx, ctx->counters.p, sizeof(RpdCounters));
   ctx->tet_cnt.reserve((size_t)n_tet + 1);
   const GridDev G = grid_build(ctx);
   const TetSpan all = {0, n_tet, nullptr};
@@ -1027,7 +1284,7 @@ int rpd_incremental_select(mb_ctx* ctx, const mb_rpd_opts* opts) {
     k_inc_affected<<<(unsigned)(((size_t)n_tet * 32 + 255) / 256), 256, 0, s>>>(
         n_tet, kcap, ctx->cand_cnt.p, ctx->cand_pad.p, ctx->inc_cand_cnt.p, ctx->inc_cand_pad.p, S.site4.p, S.flags.p,
         ctx->inc_site4.p, ctx->inc_flags.p, ctx->inc_n_site, ctx->inc_flag.p);
-    MB_CUDA(cudaMemsetAsync(ctx->inc_flag.p + n_tet, 0, sizeof(int), s));
+    dev_zero(ctx, ctx->inc_flag.p + n_tet, sizeof(int));
     exclusive_scan<int>(ctx, ctx->inc_flag.p, ctx->inc_pos.p, (long long)n_tet + 1);
     k_inc_compact<<<(n_tet + 255) / 256, 256, 0, s>>>(n_tet, ctx->inc_flag.p, ctx->inc_pos.p, ctx->inc_affected.p);
     MB_CUDA(cudaGetLastError());
@@ -1129,7 +1386,8 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     // 2.81 ms per step at N = 2); callers that know how contended the destination's ingress is pass n_chunks
     // (libmat_b200.dist.ShardSink: one span up to two ranks).
     const bool dev_dst = decreasing;
-    const int per_span = lean ? 65536 : 32768;  // slim / lean records: the kernels are the long pole, fewer spans
+    // (measured at config 2 with the staged run, slim records: 3 / 4 / 6 / 8 spans -> 2.81 / 2.72 / 2.70 / 2.79 ms)
+    const int per_span = lean ? 40000 : 32768;
     n_chunks = dev_dst ? (t_count >= 65536 ? 2 : 1) : std::max(1, std::min(32, (t_count + per_span - 1) / per_span));
   }
   n_chunks = std::max(1, std::min(n_chunks, std::max(1, t_count)));
@@ -1154,22 +1412,35 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     hs->zero = 0;
     MB_CUDA(cudaMemcpyAsync(dst_off, &hs->zero, sizeof(long long), cudaMemcpyDefault, cs));
   }
+  // span c = tets [cut(c), cut(c+1)): equal sizes, or weights n, n-1, ..., 1 (cut(c) = t_count * (1 - tri(n-c)/tri(n)))
+  auto cut = [&](int k) -> long long {
+    if (!decreasing) return (long long)t_count * k / n_chunks;
+    const long long tri_n = (long long)n_chunks * (n_chunks + 1) / 2, rest = (long long)(n_chunks - k) * (n_chunks - k + 1) / 2;
+    return (long long)t_count * (tri_n - rest) / tri_n;
+  };
+  // staged: the candidate stage once for all tets, K3 + ordering per span (see rpd_candidates_all)
+  const bool staged = grid_cands && t_count > 0 && ctx->stream_variant != 1 && !(opts && opts->security_radius);
+  const TetSpan sp_all = ctx->mesh.n_sel > 0 ? TetSpan{0, t_count, ctx->mesh.tet_sel.p} : TetSpan{t_first, t_count, nullptr};
+  std::vector<long long> cut_pairs;
+  if (staged) {
+    std::vector<int> cut_tets;
+    for (int c = 0; c <= n_chunks; c++) cut_tets.push_back((int)cut(c));
+    rpd_candidates_all(ctx, opts, res, sp_all, G, cut_tets, cut_pairs);
+    ctx->ev_pool.push_back(res->evs[0]);
+    res->evs[0] = e0;
+  }
   for (int c = 0; c < n_chunks; c++) {
-    // span c = tets [cut(c), cut(c+1)): equal sizes, or weights n, n-1, ..., 1 (cut(c) = t_count * (1 - tri(n-c)/tri(n)))
-    auto cut = [&](int k) -> long long {
-      if (!decreasing) return (long long)t_count * k / n_chunks;
-      const long long tri_n = (long long)n_chunks * (n_chunks + 1) / 2, rest = (long long)(n_chunks - k) * (n_chunks - k + 1) / 2;
-      return (long long)t_count * (tri_n - rest) / tri_n;
-    };
     const int c_first = (int)cut(c);
     const int c_count = (int)cut(c + 1) - c_first;
     const TetSpan sp = ctx->mesh.n_sel > 0 ? TetSpan{0, c_count, ctx->mesh.tet_sel.p + c_first}
                                            : TetSpan{t_first + c_first, c_count, nullptr};
     const int b = c & 1;
     if (c >= 2) MB_CUDA(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));  // span c-2 has left the buffer
-    const SpanStats st = rpd_run_span(ctx, opts, res, sp, (grid_cands && c_count > 0) ? &G : nullptr,
-                                      ctx->span_blob[b], ctx->span_off[b], acc_bytes, lean);
-    if (c == 0) {
+    const SpanStats st = staged ? rpd_clip_range(ctx, opts, res, sp_all, cut_pairs[c], cut_pairs[c + 1], c, ctx->span_blob[b],
+                                                 ctx->span_off[b], acc_bytes, lean)
+                                : rpd_run_span(ctx, opts, res, sp, (grid_cands && c_count > 0) ? &G : nullptr,
+                                               ctx->span_blob[b], ctx->span_off[b], acc_bytes, lean);
+    if (c == 0 && !staged) {
       ctx->ev_pool.push_back(res->evs[0]);
       res->evs[0] = e0;
     }
@@ -1291,6 +1562,20 @@ void rpd_sync(mb_ctx* ctx, mb_rpd_result* res) {
         MB_CUDA(cudaEventElapsedTime(&ms, res->evs[i + k], res->evs[i + k + 1]));
         acc[k] += ms;
       }
+    if (ctx->trace_level >= 2 && res->evs.size() > 4) {
+      std::string line = "[libmat_b200 trace] span stages (candidates / clip / order ms, offset of span start):";
+      for (size_t i = 0; i + 3 < res->evs.size(); i += 4) {
+        float a = 0, b = 0, c = 0, o = 0;
+        cudaEventElapsedTime(&a, res->evs[i], res->evs[i + 1]);
+        cudaEventElapsedTime(&b, res->evs[i + 1], res->evs[i + 2]);
+        cudaEventElapsedTime(&c, res->evs[i + 2], res->evs[i + 3]);
+        cudaEventElapsedTime(&o, res->evs[0], res->evs[i]);
+        char buf[96];
+        snprintf(buf, sizeof buf, " [%.3f / %.3f / %.3f @ %.3f]", a, b, c, o);
+        line += buf;
+      }
+      fprintf(stderr, "%s\n", line.c_str());
+    }
     res->ms[0] = acc[0];
     res->ms[1] = acc[1];
     res->ms[2] = acc[2];
