@@ -139,28 +139,48 @@ __device__ __forceinline__ void grid_finish_candidates(float4* s_pd, float* s_w,
                                                        int* __restrict__ cand_pad, int* __restrict__ cand_cnt,
                                                        int* __restrict__ pair_cnt, unsigned long long* __restrict__ counters) {
   __syncwarp();
-  // ---- all-pairs domination on the survivors ---------------------------------------------------
+  // ---- all-pairs domination on the survivors, one lane per ORDERED PAIR (a, m): a list of 8 survivors keeps all 32
+  // lanes busy for 2 steps instead of 8 lanes for 8.  A removed entry gets id = INT_MAX (several lanes may write the
+  // same value) so that the rank sort pushes it to the tail; its s_pd stays -- a dominated site may still dominate
+  // others (domination is transitive), so the outcome does not depend on the order of the tests.
+  const int npair = cnt * cnt;
+  const unsigned magic = (65536u + (unsigned)cnt - 1u) / (unsigned)max(cnt, 1);  // a = p / cnt by multiply + fix-up (cnt <= 2048)
+  for (int p0 = 0; p0 < npair; p0 += 32) {
+    const int p = p0 + lane;
+    if (p < npair) {
+      int a = cnt <= 96 ? (int)(((unsigned)p * magic) >> 16) : p / cnt;
+      if (a * cnt > p) a--;
+      else if ((a + 1) * cnt <= p) a++;
+      const int m = p - a * cnt;
+      if (m != a && dominates(s_pd[m], s_w[m], s_pd[a], s_w[a])) s_id[a] = 0x7fffffff;
+    }
+  }
+  __syncwarp();
   int n_keep = 0;
   for (int b = 0; b < cnt; b += 32) {
     const int a2 = b + lane;
-    bool keep = false;
-    if (a2 < cnt) {
-      keep = true;
-      const float4 e = s_pd[a2];
-      const float wa = s_w[a2];
-      for (int m = 0; m < cnt && keep; m++)
-        if (m != a2 && dominates(s_pd[m], s_w[m], e, wa)) keep = false;
-    }
-    __syncwarp();
-    // removed entries get id = INT_MAX so that the rank sort pushes them to the tail; their
-    // s_pd stays (a dominated site may still dominate others: domination is transitive)
-    if (a2 < cnt && !keep) s_id[a2] = 0x7fffffff;
-    n_keep += __popc(__ballot_sync(0xffffffffu, keep));
+    n_keep += __popc(__ballot_sync(0xffffffffu, a2 < cnt && s_id[a2] != 0x7fffffff));
   }
-  __syncwarp();
   if (n_keep > kcap_out) {
     if (lane == 0) atomicAdd(&counters[4], 1ull);  // truncated: reported, never silent
   }
+  // ---- rank of every kept id among the kept ids (ascending site id), pair-parallel as well; the weights are no
+  // longer needed: their slots hold the rank counters
+  int* s_rank = reinterpret_cast<int*>(s_w);
+  for (int b = lane; b < cnt; b += 32) s_rank[b] = 0;
+  __syncwarp();
+  for (int p0 = 0; p0 < npair; p0 += 32) {
+    const int p = p0 + lane;
+    if (p < npair) {
+      int a = cnt <= 96 ? (int)(((unsigned)p * magic) >> 16) : p / cnt;
+      if (a * cnt > p) a--;
+      else if ((a + 1) * cnt <= p) a++;
+      const int m = p - a * cnt;
+      const int ida = s_id[a];
+      if (ida != 0x7fffffff && s_id[m] < ida) atomicAdd(&s_rank[a], 1);
+    }
+  }
+  __syncwarp();
   int n_flag = 0;
   for (int b = 0; b < cnt; b += 32) {
     const int a2 = b + lane;
@@ -168,8 +188,7 @@ __device__ __forceinline__ void grid_finish_candidates(float4* s_pd, float* s_w,
     if (a2 < cnt) {
       const int id = s_id[a2];
       if (id != 0x7fffffff) {
-        int rank = 0;
-        for (int m = 0; m < cnt; m++) rank += (s_id[m] < id);
+        const int rank = s_rank[a2];
         if (rank < kcap_out) {
           cand_pad[(size_t)warp * kcap_out + rank] = id;
           fl = flags[id] == 1u;
