@@ -21,6 +21,22 @@ def shard(n_tet: int, rank: int, world: int) -> tuple[int, int]:
     return first, base + (1 if rank < rem else 0)
 
 
+def allreduce_site_volumes(vol: np.ndarray, bary_soa: np.ndarray, group=None, device=None):
+    """Per-site volume and barycentre sums of a sharded run: every rank passes the arrays of ITS tets
+    (RpdResult.site_volumes() of a run with want_volumes=True -- the atomicAdd targets of get_cell_volume_and_barycenter,
+    convex_cell.cu:1073-1160) and gets the sums over all ranks.  One all-reduce of 16 bytes per site; with the nccl
+    backend pass device= so that the reduction runs over NVLink."""
+    t = torch.from_numpy(np.concatenate([np.asarray(vol, np.float32).ravel(), np.asarray(bary_soa, np.float32).ravel()]))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t = t.cpu()
+    a = t.numpy()
+    n = np.asarray(vol).size
+    return a[:n].copy(), a[n:].copy()
+
+
 def balanced_cuts(cells_per_tet: np.ndarray, world: int, tet_cost: float = 1.5) -> np.ndarray:
     """Cut points (world + 1 ascending tet indices, cuts[0] = 0, cuts[-1] = n_tet) of contiguous tet shards of equal
     estimated WORK instead of equal size: work(tet) = tet_cost + its number of cells (the neighbour search costs

@@ -92,6 +92,9 @@ def _balanced_worker(rank, world, port, q):
     cells = (np.arange(n) % 7 + (np.arange(n) > 600) * 9).astype(np.int64)  # heavier tail
     first, count = shard(n, rank, world)
     cuts, _ = balanced_shards(n, first, cells[first:first + count])
+    from libmat_b200.dist import allreduce_site_volumes
+    vol, bary = allreduce_site_volumes(np.full(5, rank + 1.0, np.float32), np.arange(15, dtype=np.float32) * (rank + 1))
+    assert np.allclose(vol, 3.0) and np.allclose(bary, np.arange(15) * 3.0)
     q.put((rank, cuts.tolist()))
     dist.destroy_process_group()
 

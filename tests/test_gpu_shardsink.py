@@ -54,6 +54,14 @@ def _worker(rank, world, port, kind, out_dir):
         recs = ctx.expand_compact(blob.view(np.uint32) if blob.size % 4 == 0 else blob, offs)
         np.save(os.path.join(out_dir, f"lean_{kind}.npy"), recs)
     dist.barrier()
+    # per-site volume / barycentre sums of the shards add up to the single-process sums
+    from libmat_b200.dist import allreduce_site_volumes
+    rv = ctx.run(want_volumes=True)
+    vol, bary = allreduce_site_volumes(*rv.site_volumes())
+    rv.free()
+    if rank == 0:
+        np.savez(os.path.join(out_dir, f"vol_{kind}.npz"), vol=vol, bary=bary)
+    dist.barrier()
     # a sink that is too small is an error, not a truncation
     small = ShardSink(ctx, 4096, 8, kind=kind, tag=f"mb_test_small_{port}")
     try:
@@ -75,6 +83,9 @@ def test_two_rank_sink_equals_single_process(ctx, synth, tmp_path, kind):
     sites = synth.make_spheres(600)
     ctx.set_mesh(mesh)
     ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, None, 0)
+    rv = ctx.run(want_volumes=True)
+    want_vol, want_bary = rv.site_volumes()
+    rv.free()
     res = ctx.run()
     blob, offs = res.compact()
     want_blob = blob[: res.compact_bytes // 4].view(np.uint8).copy()
@@ -99,3 +110,7 @@ def test_two_rank_sink_equals_single_process(ctx, synth, tmp_path, kind):
         assert np.array_equal(got["blob"], want_blob)
     lean = np.load(tmp_path / f"lean_{kind}.npy")
     assert lean.tobytes() == want_recs.tobytes()
+    v = np.load(tmp_path / f"vol_{kind}.npz")
+    # float atomics in a different order: 1e-4 of the largest sum
+    assert np.abs(v["vol"] - want_vol).max() <= 1e-4 * np.abs(want_vol).max()
+    assert np.abs(v["bary"] - want_bary).max() <= 1e-4 * np.abs(want_bary).max()

@@ -161,3 +161,48 @@ def test_speculative_capacity_overflow_is_redone(ctx, cfg1_rt):
         same(want, got)
     ctx.lib.mb_debug_set_pair_hint(ctx._ctx, 0.0)  # learn again
     same(want, one_shot(ctx))
+
+
+def test_unaligned_ranges_concatenate_grid_mode(ctx, cfg1_rt):
+    """work-balanced shards start anywhere: tet ranges whose first tet is not a multiple of the K2 cluster size, one-shot
+    and streamed, must concatenate to the full grid-mode result byte for byte (offsets rebased)"""
+    mesh, sites, knn, k = cfg1_rt
+    ctx.set_mesh(mesh)
+    ctx.upload_sites(sites.site_soa, sites.weights, sites.flags, None, 0)
+    full = one_shot(ctx)
+    cuts = [0, 1237, 1238, 5003, 11111, mesh.n_tet]
+    for how in ("one_shot", "streamed"):
+        blobs, n_cells, n_pairs, base, offs = [], 0, 0, 0, [np.zeros(1, np.int64)]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            ctx.set_tet_range(a, b - a)
+            part = one_shot(ctx) if how == "one_shot" else streamed(ctx, 3)[0]
+            blobs.append(part[0])
+            offs.append(part[1][1:] + base)
+            base += int(part[1][-1])
+            n_cells += part[2]
+            n_pairs += part[3]
+        ctx.set_tet_range(0, -1)
+        assert n_cells == full[2] and n_pairs == full[3]
+        assert np.array_equal(np.concatenate(offs), full[1])
+        assert np.array_equal(np.concatenate(blobs), full[0])
+
+
+def test_cluster_search_equals_per_tet_search(cfg1_rt, monkeypatch):
+    """K2: the cluster search (one grid walk per 6 tets) and the per-tet search (MB_K2_VARIANT=1) produce the same
+    candidate pairs and, from them, the same records"""
+    from libmat_b200.rpd import Context
+    mesh, sites, knn, k = cfg1_rt
+    out = []
+    for variant in ("0", "1"):
+        monkeypatch.setenv("MB_K2_VARIANT", variant)
+        c = Context(0)
+        c.set_mesh(mesh)
+        c.upload_sites(sites.site_soa, sites.weights, sites.flags, None, 0)
+        r = c.run()
+        pt, ps, st = r.pairs()
+        blob, offs = r.compact()
+        out.append((pt.copy(), ps.copy(), st.copy(), blob[: r.compact_bytes // 4].copy(), offs.copy()))
+        r.free()
+        c.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
