@@ -70,6 +70,7 @@ mb_ctx* mb_create(int device, int* err) {
   if (const char* v = getenv("MB_CLIP_VARIANT")) ctx->clip_variant = atoi(v);
   if (const char* v = getenv("MB_K2_VARIANT")) ctx->k2_variant = atoi(v);
   if (const char* v = getenv("MB_STREAM_VARIANT")) ctx->stream_variant = atoi(v);
+  if (const char* v = getenv("MB_DEBUG_SMALL_SCRATCH")) ctx->debug_small_scratch = atoi(v);
   if (const char* v = getenv("MB_TRACE")) {
     ctx->trace_level = atoi(v);
     ctx->trace_on = ctx->trace_level != 0;

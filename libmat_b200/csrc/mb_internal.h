@@ -269,7 +269,8 @@ struct mb_ctx {
   std::vector<int4> h_tet_fid, h_tet_fadj;  // host copies of f_ids / f_adjs (slim records: tet-face plane ids)
   bool h_tet_planes_valid = false;
   double pairs_per_tet_hint = 0.0;  // grid mode: 1.5 x the largest pairs-per-tet seen (speculative span launches)
-  int stream_variant = 0;           // MB_STREAM_VARIANT=1 (A/B tests): streamed runs redo K2 per span instead of once up front
+  int debug_small_scratch = 0;      // MB_DEBUG_SMALL_SCRATCH=1 (tests): the pipelined ranges get a scratch bound they overflow
+  int stream_variant = 0;           // MB_STREAM_VARIANT (A/B tests): 1 = streamed runs redo K2 per span instead of once up front, 2 = staged but one range at a time
   int k2_variant = 0;               // MB_K2_VARIANT=1 (A/B tests): per-tet candidate search instead of the cluster search
   int clip_variant = 0;             // MB_CLIP_VARIANT=1 (A/B tests): grid-kNN first pass with the state-machine kernel k_clip
   bool no_cull = false;             // MB_NO_CULL=1 (debug / parity tests): no conservative cull of listed neighbours
@@ -282,6 +283,7 @@ struct mb_ctx {
   DevBuf<int> tet_cnt, tet_off, pair_tet, pair_site, pair_local, cand_pad;
   DevBuf<int> redo_list;           // grid mode: pairs whose cell outgrew the compact caps of K3's first pass
   DevBuf<int> cand_cnt;            // grid mode: #candidates per tet (cand_pad holds the lists)
+  DevBuf<unsigned long long> acc_words;  // pipelined streamed run: record words of the run's earlier ranges
   DevBuf<int> fb_list;             // grid mode: tets the cluster search handed back to the per-tet search
   DevBuf<int> ovf_list;            // grid mode: tets whose survivor list overflowed the fast pass
   int cand_kcap = 0;               // grid mode: row stride of cand_pad

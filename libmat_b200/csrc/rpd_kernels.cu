@@ -303,13 +303,16 @@ __global__ void k_gather(const uint32_t* __restrict__ scratch, const long long* 
                          const int* __restrict__ pair_words, const unsigned long long* __restrict__ packed_off,
                          long long n_pairs, uint32_t* __restrict__ blob, long long* __restrict__ cell_off,
                          long long total_words, long long n_cells, long long base_bytes,
-                         const unsigned long long* __restrict__ total_dev = nullptr) {
-  // total_dev: the packed scan total still on the device (the gather is launched before the host has seen it)
+                         const unsigned long long* __restrict__ total_dev = nullptr,
+                         const unsigned long long* __restrict__ base_words_dev = nullptr) {
+  // total_dev: the packed scan total still on the device (the gather is launched before the host has seen it);
+  // base_words_dev: the record words of the run's earlier ranges, accumulated on the device by k_publish_range
   if (total_dev) {
     const unsigned long long v = *total_dev;
     total_words = (long long)(v & PACK_MASK);
     n_cells = (long long)(v >> PACK_SHIFT);
   }
+  if (base_words_dev) base_bytes = (long long)(*base_words_dev * 4ull);
   // 8 lanes per record
   const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int lane = threadIdx.x & 7;
@@ -372,6 +375,26 @@ __global__ void k_publish_cuts(const int* __restrict__ tet_off, CutList cuts, co
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(&hs->seq) = seq;
+}
+
+// pipelined ranges: K3's counters and the scan total to the range's host slot, the total added to the run's device
+// accumulator (the next range's gather reads it as its base offset)
+__global__ void k_publish_range(const uint32_t* __restrict__ counters, const unsigned long long* __restrict__ total,
+                                unsigned long long* __restrict__ acc_words, HostScalars* __restrict__ hs,
+                                unsigned long long seq) {
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&hs->counters);
+  for (int i = threadIdx.x; i < (int)(sizeof(RpdCounters) / 4); i += blockDim.x) dst[i] = counters[i];
+  if (threadIdx.x == 0) {
+    const unsigned long long v = total ? *total : 0ull;
+    hs->total_words = (long long)v;
+    *acc_words += (v & PACK_MASK);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(&hs->seq) = seq;
+}
+__global__ void k_base_offset(const unsigned long long* __restrict__ acc_words, long long* __restrict__ cell_off) {
+  cell_off[0] = (long long)(*acc_words * 4ull);
 }
 
 // =============================================================================================
@@ -689,8 +712,9 @@ static void wait_published(mb_ctx* ctx) {
 
 static HostScalars* host_scalars(mb_ctx* ctx) {
   if (!ctx->hs) {
-    MB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->hs), sizeof(HostScalars), cudaHostAllocMapped));
-    memset(ctx->hs, 0, sizeof(HostScalars));
+    // slot 0: the one-at-a-time publishes; slots 1-2: the pipelined ranges of the staged streamed run
+    MB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->hs), 4 * sizeof(HostScalars), cudaHostAllocMapped));
+    memset(ctx->hs, 0, 4 * sizeof(HostScalars));
   }
   return ctx->hs;
 }
@@ -1197,6 +1221,182 @@ static SpanStats rpd_clip_range(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_res
   return st;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined form of rpd_clip_range: range c+1 is ENQUEUED before the host waits for range c, so the stream never idles
+// through a host round trip and the launches of the small kernels are issued while the previous range's K3 runs.
+// What the host used to hand over between ranges now stays on the device: the base offset of a range's cell offsets
+// is the device accumulator of the earlier ranges' record words (k_publish_range adds, k_gather reads), the totals
+// reach the host through one of two mapped slots.  A range that overflows its scratch bound makes range_collect
+// return false: the caller drains the stream and redoes the run with the one-range-at-a-time path (rare).
+// ---------------------------------------------------------------------------------------------------------------
+struct RangeJob {
+  long long p0 = 0, p1 = 0;
+  int c = 0;
+  size_t scratch_words = 0;
+  unsigned long long seq = 0;
+  HostScalars* slot = nullptr;
+};
+
+static RangeJob range_enqueue(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res, const TetSpan& sp, long long p0,
+                              long long p1, int c, DevBuf<uint32_t>& blob, DevBuf<long long>& cell_off, int lean) {
+  TetMeshDev& M = ctx->mesh;
+  SitesDev& S = ctx->sites;
+  cudaStream_t s = ctx->stream;
+  RangeJob J;
+  J.p0 = p0;
+  J.p1 = p1;
+  J.c = c;
+  const long long n_pairs = p1 - p0;
+  const int G = opts && opts->lanes_per_cell ? opts->lanes_per_cell : 8;
+  J.slot = host_scalars(ctx) + 1 + (c & 1);
+  double tr_ = ctx->trace_on ? now_us() : 0.0;
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; i++) {
+    ev[i] = take_event(ctx);
+    res->evs.push_back(ev[i]);
+  }
+  MB_CUDA(cudaEventRecord(ev[0], s));
+  MB_CUDA(cudaEventRecord(ev[1], s));
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(ctx->acc_words.p);
+  dev_zero(ctx, ctx->counters.p, sizeof(RpdCounters));
+  if (n_pairs == 0) {
+    cell_off.reserve(1);
+    MB_CUDA(cudaEventRecord(ev[2], s));
+    ctx->n_launches += 2;
+    k_base_offset<<<1, 1, 0, s>>>(acc, cell_off.p);
+    J.seq = ++ctx->publish_seq;
+    k_publish_range<<<1, 64, 0, s>>>(reinterpret_cast<const uint32_t*>(ctx->counters.p), nullptr, acc, J.slot, J.seq);
+    MB_CUDA(cudaGetLastError());
+    MB_CUDA(cudaEventRecord(ev[3], s));
+    return J;
+  }
+  J.scratch_words = (size_t)n_pairs * 96 + (size_t)ctx->sm_count * 8 * 16 * CLIP_CHUNK_WORDS + (1u << 20);
+  if (ctx->debug_small_scratch) J.scratch_words = (size_t)n_pairs * 8 + 4096;  // tests: force the overflow fallback
+  ctx->scratch.reserve(J.scratch_words);
+  unsigned long long* word_off = reinterpret_cast<unsigned long long*>(ctx->word_off.p) + p0 + c;
+  ClipArgs A;
+  A.vert4 = M.vert4.p;
+  A.tet_idx = M.tet_idx.p;
+  A.tet_fadj = M.tet_fadj.p;
+  A.tet_fid = M.tet_fid.p;
+  A.tet_e6 = M.tet_e6.p;
+  A.tet_geo = M.tet_geo.p;
+  A.tet_vadj = M.tet_vadj.p;
+  A.site4 = S.site4.p;
+  A.n_site = S.n_site;
+  if (S.given) {
+    A.nbr = S.nbr.p;
+    A.nbr_stride = S.site_k;
+    A.nbr_cnt = nullptr;
+  } else {
+    A.nbr = ctx->cand_pad.p;
+    A.nbr_stride = ctx->cand_kcap;
+    A.nbr_cnt = ctx->cand_cnt.p;
+  }
+  A.tet_first = sp.first;
+  A.tet_id_base = M.tet_id_base;
+  A.pair_tet = ctx->pair_tet.p + p0;
+  A.pair_site = ctx->pair_site.p + p0;
+  A.pair_local = ctx->pair_local.p + p0;
+  A.n_pairs = n_pairs;
+  A.n_pairs_dev = nullptr;
+  A.pair_status = ctx->pair_status.p + p0;
+  A.pair_blob = ctx->pair_blob.p + p0;
+  A.pair_words = ctx->pair_words.p + p0;
+  A.scratch = ctx->scratch.p;
+  A.scratch_words = J.scratch_words;
+  A.counters = reinterpret_cast<unsigned long long*>(ctx->counters.p);
+  A.no_cull = ctx->no_cull ? 1 : 0;
+  A.security_radius = 0;
+  const bool pt = A.nbr_cnt != nullptr;
+  if (G == 4)
+    pt ? launch_clip<4, true>(ctx, A) : launch_clip<4, false>(ctx, A);
+  else if (G == 8)
+    pt ? launch_clip<8, true>(ctx, A) : launch_clip<8, false>(ctx, A);
+  else if (G == 16)
+    pt ? launch_clip<16, true>(ctx, A) : launch_clip<16, false>(ctx, A);
+  else
+    pt ? launch_clip<32, true>(ctx, A) : launch_clip<32, false>(ctx, A);
+  MB_CUDA(cudaEventRecord(ev[2], s));
+  {
+    size_t tmp = 0;
+    ctx->n_launches += 2;
+    const int* in_words = ctx->pair_words.p + p0;
+    if (lean == 2) {
+      cub::TransformInputIterator<unsigned long long, PackWords<2>, const int*> in(in_words, PackWords<2>());
+      MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, word_off, n_pairs + 1, s));
+      ctx->cub_tmp.reserve(tmp);
+      MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, word_off, n_pairs + 1, s));
+    } else if (lean == 1) {
+      cub::TransformInputIterator<unsigned long long, PackWords<1>, const int*> in(in_words, PackWords<1>());
+      MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, word_off, n_pairs + 1, s));
+      ctx->cub_tmp.reserve(tmp);
+      MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, word_off, n_pairs + 1, s));
+    } else {
+      cub::TransformInputIterator<unsigned long long, PackWords<0>, const int*> in(in_words, PackWords<0>());
+      MB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, word_off, n_pairs + 1, s));
+      ctx->cub_tmp.reserve(tmp);
+      MB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, word_off, n_pairs + 1, s));
+    }
+  }
+  cell_off.reserve((size_t)n_pairs + 1);
+  blob.reserve(J.scratch_words + 4);
+  ctx->n_launches += 3;
+  k_base_offset<<<1, 1, 0, s>>>(acc, cell_off.p);  // a range without valid cells still has its first offset
+  const unsigned nb = (unsigned)((n_pairs * 8 + 255) / 256);
+  if (lean == 2)
+    k_gather<2><<<nb, 256, 0, s>>>(ctx->scratch.p, ctx->pair_blob.p + p0, ctx->pair_words.p + p0, word_off, n_pairs, blob.p,
+                                   cell_off.p, 0, 0, 0, word_off + n_pairs, acc);
+  else if (lean == 1)
+    k_gather<1><<<nb, 256, 0, s>>>(ctx->scratch.p, ctx->pair_blob.p + p0, ctx->pair_words.p + p0, word_off, n_pairs, blob.p,
+                                   cell_off.p, 0, 0, 0, word_off + n_pairs, acc);
+  else
+    k_gather<0><<<nb, 256, 0, s>>>(ctx->scratch.p, ctx->pair_blob.p + p0, ctx->pair_words.p + p0, word_off, n_pairs, blob.p,
+                                   cell_off.p, 0, 0, 0, word_off + n_pairs, acc);
+  J.seq = ++ctx->publish_seq;
+  k_publish_range<<<1, 64, 0, s>>>(reinterpret_cast<const uint32_t*>(ctx->counters.p), word_off + n_pairs, acc, J.slot, J.seq);
+  MB_CUDA(cudaGetLastError());
+  MB_CUDA(cudaEventRecord(ev[3], s));
+  TRACE(2);
+  return J;
+}
+
+// waits for the range's publish; false = the range overflowed its scratch bound (nothing was accumulated)
+static bool range_collect(mb_ctx* ctx, mb_rpd_result* res, const RangeJob& J, SpanStats& st) {
+  double tr_ = ctx->trace_on ? now_us() : 0.0;
+  const volatile unsigned long long* seq = &J.slot->seq;
+  const double t0 = now_us();
+  while (*seq != J.seq) {
+    if (now_us() - t0 > 20000.0) {
+      MB_CUDA(cudaStreamSynchronize(ctx->stream));
+      break;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  MB_CUDA(cudaGetLastError());
+  TRACE(3);
+  const RpdCounters hc = J.slot->counters;
+  const long long total_words = J.slot->total_words & PACK_MASK;
+  st = SpanStats();
+  st.n_pairs = J.p1 - J.p0;
+  if (st.n_pairs == 0) return true;
+  MB_REQUIRE(hc.n_valid <= PACK_MAX_CELLS && hc.blob_words <= PACK_MASK, MB_ERR_ARG,
+             "more valid cells / record words in one span than the ordering scan can index: use more spans");
+  if (hc.blob_words > J.scratch_words) return false;
+  st.n_cells = (long long)hc.n_valid;
+  st.total_words = total_words;
+  res->n_cells += (long)hc.n_valid;
+  res->n_clips += (long)hc.n_clips;
+  res->n_culled += (long)hc.n_culled;
+  res->n_exact += (long)hc.pad[0];
+  res->n_redo += (long)hc.n_redo;
+  res->n_gc += (long)hc.n_gc;
+  res->n_flag_pairs += (long)hc.reserved[0];
+  res->n_flag_cells += (long)hc.reserved[1];
+  for (int i = 0; i < 10; i++) res->hist[i] += (long)hc.hist[i];
+  return true;
+}
+
 static void run_prologue(mb_ctx* ctx, const mb_rpd_opts* opts, mb_rpd_result* res, int& t_first, int& t_count) {
   TetMeshDev& M = ctx->mesh;
   SitesDev& S = ctx->sites;
@@ -1429,7 +1629,112 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     ctx->ev_pool.push_back(res->evs[0]);
     res->evs[0] = e0;
   }
-  for (int c = 0; c < n_chunks; c++) {
+  // hand the ordered records of span c (in span_blob / span_off [c & 1], complete at ev_gathered[c & 1]) to the copy stream
+  std::vector<cudaEvent_t> tl_k;  // trace: "kernels done" events, recorded right behind a span's last kernel
+  auto deliver = [&](int c, const SpanStats& st) {
+    const int b = c & 1;
+    const long long bytes = st.total_words * 4;
+    // pinned destination large enough for this span (first run: extrapolate from the spans so far)
+    const size_t need_blob = (size_t)(acc_bytes + bytes), need_off = sizeof(long long) * (size_t)(acc_cells + st.n_cells + 1);
+    if (!own) {
+      if (need_blob > dst_cap_bytes || (size_t)(acc_cells + st.n_cells + 1) > dst_cap_cells) {
+        MB_CUDA(cudaStreamSynchronize(cs));
+        MB_CUDA(cudaStreamSynchronize(s));
+        throw MbError{MB_ERR_NOMEM, "sink too small: needs more than " + std::to_string(need_blob) + " bytes / " +
+                                        std::to_string(acc_cells + st.n_cells + 1) + " offsets"};
+      }
+    } else if (need_blob > ctx->pin_blob.cap || need_off > ctx->pin_off.cap) {
+      MB_CUDA(cudaStreamSynchronize(cs));  // earlier spans have landed: safe to move them
+      const double scale = 1.1 * (double)t_count / (double)std::max<long long>(1, cut(c + 1));
+      ctx->pin_blob.reserve_keep(std::max(need_blob, (size_t)(need_blob * scale)), (size_t)acc_bytes);
+      ctx->pin_off.reserve_keep(std::max(need_off, (size_t)(need_off * scale)), sizeof(long long) * (size_t)(acc_cells + 1));
+    }
+    MB_CUDA(cudaStreamWaitEvent(cs, ctx->ev_gathered[b], 0));
+    unsigned char* out_blob = own ? (unsigned char*)ctx->pin_blob.p : (unsigned char*)dst_blob;
+    long long* out_off = own ? reinterpret_cast<long long*>(ctx->pin_off.p) : dst_off;
+    if (bytes > 0)
+      MB_CUDA(cudaMemcpyAsync(out_blob + acc_bytes, ctx->span_blob[b].p, (size_t)bytes, cudaMemcpyDefault, cs));
+    if (st.n_cells > 0)
+      MB_CUDA(cudaMemcpyAsync(out_off + acc_cells, ctx->span_off[b].p, sizeof(long long) * (size_t)(st.n_cells + 1),
+                              cudaMemcpyDefault, cs));
+    MB_CUDA(cudaEventRecord(ctx->ev_copied[b], cs));
+    if (timeline) {
+      cudaEvent_t d;
+      MB_CUDA(cudaEventCreate(&d));
+      MB_CUDA(cudaEventRecord(d, cs));
+      tl.push_back(tl_k[c]);
+      tl.push_back(d);
+      tl_bytes.push_back(bytes);
+    }
+    acc_bytes += bytes;
+    acc_cells += st.n_cells;
+  };
+  auto mark_gathered = [&](int c) {
+    MB_CUDA(cudaEventRecord(ctx->ev_gathered[c & 1], s));
+    if (timeline) {
+      cudaEvent_t a;
+      MB_CUDA(cudaEventCreate(&a));
+      MB_CUDA(cudaEventRecord(a, s));
+      tl_k.push_back(a);
+    }
+  };
+  // pipelined ranges (staged runs): range c+1 is enqueued before the host waits for range c (see range_enqueue)
+  bool pipelined = staged && ctx->stream_variant != 2;
+  if (pipelined) {
+    const size_t evs_before = res->evs.size();
+    // range-accumulated statistics, restored if the run has to be redone
+    const long snap[8] = {res->n_cells, res->n_clips, res->n_culled, res->n_exact, res->n_redo, res->n_gc, res->n_flag_pairs,
+                          res->n_flag_cells};
+    long snap_hist[10];
+    for (int i = 0; i < 10; i++) snap_hist[i] = res->hist[i];
+    ctx->acc_words.reserve(2);
+    dev_zero(ctx, ctx->acc_words.p, 2 * sizeof(unsigned long long));
+    std::vector<RangeJob> jobs((size_t)n_chunks);
+    bool ok = true;
+    SpanStats st;
+    for (int c = 0; c < n_chunks && ok; c++) {
+      const int b = c & 1;
+      if (c >= 2) MB_CUDA(cudaStreamWaitEvent(s, ctx->ev_copied[b], 0));  // span c-2 has left the buffer
+      jobs[(size_t)c] = range_enqueue(ctx, opts, res, sp_all, cut_pairs[(size_t)c], cut_pairs[(size_t)c + 1], c,
+                                      ctx->span_blob[b], ctx->span_off[b], lean);
+      mark_gathered(c);
+      if (c >= 1) {
+        ok = range_collect(ctx, res, jobs[(size_t)c - 1], st);
+        if (ok) deliver(c - 1, st);
+      }
+    }
+    if (ok) {
+      ok = range_collect(ctx, res, jobs[(size_t)n_chunks - 1], st);
+      if (ok) deliver(n_chunks - 1, st);
+    }
+    if (!ok) {
+      // a range overflowed its scratch bound: drain, forget the partial run, redo it one range at a time (that path
+      // grows the scratch and retries by itself)
+      MB_CUDA(cudaStreamSynchronize(s));
+      MB_CUDA(cudaStreamSynchronize(cs));
+      res->n_cells = snap[0];
+      res->n_clips = snap[1];
+      res->n_culled = snap[2];
+      res->n_exact = snap[3];
+      res->n_redo = snap[4];
+      res->n_gc = snap[5];
+      res->n_flag_pairs = snap[6];
+      res->n_flag_cells = snap[7];
+      for (int i = 0; i < 10; i++) res->hist[i] = snap_hist[i];
+      while (res->evs.size() > evs_before) {
+        ctx->ev_pool.push_back(res->evs.back());
+        res->evs.pop_back();
+      }
+      for (cudaEvent_t e : tl) cudaEventDestroy(e);
+      for (size_t k = tl.size() / 2; k < tl_k.size(); k++) cudaEventDestroy(tl_k[k]);
+      tl.clear();
+      tl_k.clear();
+      tl_bytes.clear();
+      acc_bytes = acc_cells = 0;
+      pipelined = false;
+    }
+  }
+  for (int c = 0; c < n_chunks && !pipelined; c++) {
     const int c_first = (int)cut(c);
     const int c_count = (int)cut(c + 1) - c_first;
     const TetSpan sp = ctx->mesh.n_sel > 0 ? TetSpan{0, c_count, ctx->mesh.tet_sel.p + c_first}
@@ -1444,44 +1749,8 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
       ctx->ev_pool.push_back(res->evs[0]);
       res->evs[0] = e0;
     }
-    const long long bytes = st.total_words * 4;
-    // pinned destination large enough for this span (first run: extrapolate from the spans so far)
-    const size_t need_blob = (size_t)(acc_bytes + bytes), need_off = sizeof(long long) * (size_t)(acc_cells + st.n_cells + 1);
-    if (!own) {
-      if (need_blob > dst_cap_bytes || (size_t)(acc_cells + st.n_cells + 1) > dst_cap_cells) {
-        MB_CUDA(cudaStreamSynchronize(cs));
-        MB_CUDA(cudaStreamSynchronize(s));
-        throw MbError{MB_ERR_NOMEM, "sink too small: needs more than " + std::to_string(need_blob) + " bytes / " +
-                                        std::to_string(acc_cells + st.n_cells + 1) + " offsets"};
-      }
-    } else if (need_blob > ctx->pin_blob.cap || need_off > ctx->pin_off.cap) {
-      MB_CUDA(cudaStreamSynchronize(cs));  // earlier spans have landed: safe to move them
-      const double scale = 1.1 * (double)t_count / (double)std::max(1, c_first + c_count);
-      ctx->pin_blob.reserve_keep(std::max(need_blob, (size_t)(need_blob * scale)), (size_t)acc_bytes);
-      ctx->pin_off.reserve_keep(std::max(need_off, (size_t)(need_off * scale)), sizeof(long long) * (size_t)(acc_cells + 1));
-    }
-    MB_CUDA(cudaEventRecord(ctx->ev_gathered[b], s));
-    MB_CUDA(cudaStreamWaitEvent(cs, ctx->ev_gathered[b], 0));
-    unsigned char* out_blob = own ? (unsigned char*)ctx->pin_blob.p : (unsigned char*)dst_blob;
-    long long* out_off = own ? reinterpret_cast<long long*>(ctx->pin_off.p) : dst_off;
-    if (bytes > 0)
-      MB_CUDA(cudaMemcpyAsync(out_blob + acc_bytes, ctx->span_blob[b].p, (size_t)bytes, cudaMemcpyDefault, cs));
-    if (st.n_cells > 0)
-      MB_CUDA(cudaMemcpyAsync(out_off + acc_cells, ctx->span_off[b].p, sizeof(long long) * (size_t)(st.n_cells + 1),
-                              cudaMemcpyDefault, cs));
-    MB_CUDA(cudaEventRecord(ctx->ev_copied[b], cs));
-    if (timeline) {
-      cudaEvent_t a, d;
-      MB_CUDA(cudaEventCreate(&a));
-      MB_CUDA(cudaEventCreate(&d));
-      MB_CUDA(cudaEventRecord(a, s));
-      MB_CUDA(cudaEventRecord(d, cs));
-      tl.push_back(a);
-      tl.push_back(d);
-      tl_bytes.push_back(bytes);
-    }
-    acc_bytes += bytes;
-    acc_cells += st.n_cells;
+    mark_gathered(c);
+    deliver(c, st);
   }
   MB_CUDA(cudaStreamSynchronize(cs));
   MB_CUDA(cudaStreamSynchronize(s));

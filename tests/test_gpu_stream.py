@@ -206,3 +206,23 @@ def test_cluster_search_equals_per_tet_search(cfg1_rt, monkeypatch):
         c.close()
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("env", [{"MB_DEBUG_SMALL_SCRATCH": "1"}, {"MB_STREAM_VARIANT": "2"}, {"MB_STREAM_VARIANT": "1"}])
+def test_streamed_run_variants_and_overflow_fallback(cfg1_rt, monkeypatch, env):
+    """the pipelined staged run, forced to overflow its scratch bound (-> drained and redone one range at a time), the
+    unpipelined staged run and the per-span run all deliver the one-shot result"""
+    from libmat_b200.rpd import Context
+    mesh, sites, knn, k = cfg1_rt
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    c = Context(0)
+    c.set_mesh(mesh)
+    c.upload_sites(sites.site_soa, sites.weights, sites.flags, None, 0)
+    want = one_shot(c)
+    for n_chunks in (1, 3, 6):
+        got, _ = streamed(c, n_chunks)
+        same(want, got)
+        got, _ = streamed(c, n_chunks, lean=2)
+        assert got[2] == want[2] and got[3] == want[3] and np.array_equal(got[4], want[4])
+    c.close()
