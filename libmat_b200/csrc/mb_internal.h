@@ -270,7 +270,7 @@ struct mb_ctx {
   bool h_tet_planes_valid = false;
   double pairs_per_tet_hint = 0.0;  // grid mode: 1.5 x the largest pairs-per-tet seen (speculative span launches)
   int debug_small_scratch = 0;      // MB_DEBUG_SMALL_SCRATCH=1 (tests): the pipelined ranges get a scratch bound they overflow
-  int stream_variant = 0;           // MB_STREAM_VARIANT (A/B tests): 1 = streamed runs redo K2 per span instead of once up front, 2 = staged but one range at a time
+  int stream_variant = 0;           // MB_STREAM_VARIANT (A/B tests): 1 = streamed runs redo K2 per span instead of once up front, 3 = staged with host-pipelined ranges
   int k2_variant = 0;               // MB_K2_VARIANT=1 (A/B tests): per-tet candidate search instead of the cluster search
   int clip_variant = 0;             // MB_CLIP_VARIANT=1 (A/B tests): grid-kNN first pass with the state-machine kernel k_clip
   bool no_cull = false;             // MB_NO_CULL=1 (debug / parity tests): no conservative cull of listed neighbours

@@ -208,10 +208,11 @@ def test_cluster_search_equals_per_tet_search(cfg1_rt, monkeypatch):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("env", [{"MB_DEBUG_SMALL_SCRATCH": "1"}, {"MB_STREAM_VARIANT": "2"}, {"MB_STREAM_VARIANT": "1"}])
+@pytest.mark.parametrize("env", [{"MB_STREAM_VARIANT": "3", "MB_DEBUG_SMALL_SCRATCH": "1"}, {"MB_STREAM_VARIANT": "3"},
+                                 {"MB_STREAM_VARIANT": "1"}])
 def test_streamed_run_variants_and_overflow_fallback(cfg1_rt, monkeypatch, env):
-    """the pipelined staged run, forced to overflow its scratch bound (-> drained and redone one range at a time), the
-    unpipelined staged run and the per-span run all deliver the one-shot result"""
+    """the host-pipelined staged run (opt-in) -- also forced to overflow its scratch bound, which drains it and redoes
+    the run one range at a time -- and the per-span run deliver the one-shot result, like the default staged run"""
     from libmat_b200.rpd import Context
     mesh, sites, knn, k = cfg1_rt
     for key, val in env.items():
