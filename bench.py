@@ -2,7 +2,7 @@
 """bench.py -- the driver's measurement contract for the RPD3D hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--mode grid|given] [--workload cfg2|cfg4|weak]
+                    [--mode grid|given] [--workload cfg1|cfg2|cfg4|cfg5|d2m] [--records full|lean|slim]
 
 A "step" = one full restricted power diagram of the workload: candidate search (K1+K2), clipping (K3),
 ordering/compaction (K4 first half), all in libmat_b200.so through the C ABI.
@@ -10,7 +10,9 @@ ordering/compaction (K4 first half), all in libmat_b200.so through the C ABI.
   N = 1   workload = BASELINE.json configs[1]: synthetic Kuhn ball mesh n=32 (196 608 tets, 35 937
           vertices), 10 000 medial spheres, neighbour cap k=80 (given mode: regular-triangulation neighbour lists, the
           reference's semantics; grid mode: the library's own uniform-grid search).
-  N > 1   tets sharded in contiguous blocks, spheres replicated on every rank.  N = 2 / 4: ~196 608 tets per GPU
+  N > 1   tets sharded in contiguous blocks of equal estimated WORK (libmat_b200.dist.balanced_shards from the per-tet cell
+          counts of one untimed run + three measured refinements; --equal-shards for equal sizes), spheres replicated
+          on every rank.  N = 2 / 4: ~196 608 tets per GPU
           (n = 40 / 51, 20 000 / 40 000 spheres); N = 8 IS BASELINE.json configs[3], the north-star target:
           n = 70, 2 058 000 tets (257 250 per GPU), 100 000 spheres.  Every rank's streamed run
           (mb_rpd_run_to_sink) writes its ordered shard straight into rank 0's HBM over NVLink peer memory
