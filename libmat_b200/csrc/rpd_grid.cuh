@@ -581,6 +581,7 @@ __global__ void __launch_bounds__(32 * WARPS, NB) k_grid_candidates_cluster(
     const int ck = min(R - 1, max(0, (int)floorf((gz - G.minz) * G.inv_h)));
     // ---- seed: U_c from rings of cells around the centre ---------------------------------------------------------
     float bvu = INFINITY;
+    int bqu = -1;
     float U = INFINITY;
     for (int ar = 1; ar <= 4 && !isfinite(U); ar++) {
       const int sd = 2 * ar + 1, nb = sd * sd * sd;
@@ -595,12 +596,24 @@ __global__ void __launch_bounds__(32 * WARPS, NB) k_grid_candidates_cluster(
               for (int q = G.cell_off[c]; q < G.cell_off[c + 1]; q++) {
                 const float4 s = G.site4[q];
                 const float r = sqrtf(pd_plain(make_float4(s.x, s.y, s.z, 0.f), g4)) * 1.0001f + Rc;
-                bvu = fminf(bvu, r * r - s.w);
+                const float ub = r * r - s.w;
+                if (ub < bvu) {
+                  bvu = ub;
+                  bqu = q;
+                }
               }
             }
         }
       }
       U = warp_min(bvu);
+    }
+    if (isfinite(U)) {
+      // the ball bound of the best seed is loose when the seed sits off-centre: its EXACT maximum over the cluster's
+      // vertices (the lanes still hold them) is an upper bound of U(T) of every tet as well, and usually 10-20 % lower
+      const float4 sb = G.site4[warp_argmin(bvu, bqu)];
+      const float ex = warp_max(has ? pd_plain(sb, pv) : -INFINITY);
+      U = fminf(U, ex);
+      bvu = fminf(bvu, U);
     }
     float Ue = U + 4e-6f * (fabsf(U) + 2.f * wall) + 1e-3f;
     const float rho = Rc + sqrtf(fmaxf(0.f, Ue + wall)) * 1.0001f;
