@@ -345,14 +345,18 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
     res_h = torch.empty(n_samples, dtype=torch.float32).pin_memory()
     cid_h = torch.empty(n_samples, dtype=torch.int32).pin_memory()
     e_steps = max(3, min(steps, 5))
+    # (every call returns with the results in host memory, so each one is timed by itself; the median is reported and
+    # all of them listed: on some boxes the first call after another leg's large pinned allocations takes several times
+    # as long as the rest)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
+    t_calls = []
+    for _ in range(e_steps + 1):
+        t0 = time.perf_counter()
         ctx._check(ctx.lib.mb_dist2mat(ctx._ctx, hp[0].ctypes.data, len(d.spheres), hp[1].ctypes.data, n_samples,
                                        hp[2].ctypes.data, hp[3].ctypes.data, hp[4].ctypes.data, n_prims,
                                        res_h.numpy().ctypes.data, cid_h.numpy().ctypes.data, None))
-    torch.cuda.synchronize()
-    t_e2e = (time.perf_counter() - t0) / e_steps
+        t_calls.append(time.perf_counter() - t0)
+    t_e2e = float(np.median(t_calls[1:]))
     out = {"metric": "dist2mat_queries_per_sec", "value": n_samples / (k_ms * 1e-3), "unit": "queries/s",
            "ms_per_step": k_ms,
            "config": {"workload": f"config 3 shape: {n_samples} samples, {len(d.spheres)} spheres, {d.n_slabs} slabs, "
@@ -368,7 +372,8 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
                             "note": "peaks measured on this device with FFMA / DFMA loops (mb_measure_peaks); flops per "
                                     "primitive evaluation: slab 300, cone 60, sphere 12"}},
            "e2e": {"value": n_samples / t_e2e, "unit": "queries/s",
-                   "h2d_bytes_per_step": int(sum(x.nbytes for x in hp)), "d2h_bytes_per_step": int(8 * n_samples)}}
+                   "h2d_bytes_per_step": int(sum(x.nbytes for x in hp)), "d2h_bytes_per_step": int(8 * n_samples),
+                   "ms_median": 1e3 * t_e2e, "ms_calls": [round(1e3 * t, 2) for t in t_calls[1:]]}}
     # ---- f3: the candidate lists built on the device (mb_dist2mat_by_face): the caller hands over what the reference
     # STARTS from -- medial mesh, (surface fid, site) incidence, samples + their surface-face id -- instead of one
     # private int3 list per sample.  Everything is inside the timed region: medial mesh + incidence upload, list
@@ -398,11 +403,12 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
             torch.cuda.synchronize()
             ms3.append(ctx.dist2mat_run())
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
+        t_calls3 = []
+        for _ in range(e_steps + 1):
+            t0 = time.perf_counter()
             by_face_call()
-        torch.cuda.synchronize()
-        t_bf = (time.perf_counter() - t0) / e_steps
+            t_calls3.append(time.perf_counter() - t0)
+        t_bf = float(np.median(t_calls3[1:]))
         k3 = float(np.mean(ms3))
         n_list = int(off_l[-1])
         per_sample = float(np.mean(off_l[d.sample_fid.astype(np.int64) + 1] - off_l[d.sample_fid.astype(np.int64)]))
@@ -416,7 +422,8 @@ def bench_dist2mat(ctx, n_samples, steps, warmup, with_cpu=True):
             "roofline": {"bound": "hbm", "achieved": b_alg3 / (k3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": b_alg3 / (k3 * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": b_alg3},
             "e2e": {"value": n_samples / t_bf, "unit": "queries/s", "h2d_bytes_per_step": h2d3, "d2h_bytes_per_step": int(8 * n_samples),
-                    "ms": 1e3 * t_bf, "stage_ms_last_call": dict(bf_stage)}}
+                    "ms": 1e3 * t_bf, "ms_calls": [round(1e3 * t, 2) for t in t_calls3[1:]],
+                    "stage_ms_last_call": dict(bf_stage)}}
     except Exception as exc:  # noqa: BLE001
         out["by_face"] = {"error": str(exc)}
     # the same query with every distinct list stored once (samples of one surface face share their list:
