@@ -1615,7 +1615,15 @@ void rpd_run_to_host(mb_ctx* ctx, const mb_rpd_opts* opts, int n_chunks, mb_rpd_
     MB_CUDA(cudaMemcpyAsync(dst_off, &hs->zero, sizeof(long long), cudaMemcpyDefault, cs));
   }
   // span c = tets [cut(c), cut(c+1)): equal sizes, or weights n, n-1, ..., 1 (cut(c) = t_count * (1 - tri(n-c)/tri(n)))
+  // Host destinations with >= 4 spans: the first and the last span are half as long as the others -- the first bytes
+  // leave early (what matters when the D2H is the long pole) and the exposed copy of the last span is short (what
+  // matters when the kernels are).
   auto cut = [&](int k) -> long long {
+    if (!decreasing && n_chunks >= 4) {
+      const long long units = 2LL * n_chunks - 2;  // in half-spans: 1 + 2 (n - 2) + 1
+      const long long at = k == 0 ? 0 : (k == n_chunks ? units : 2LL * k - 1);
+      return (long long)t_count * at / units;
+    }
     if (!decreasing) return (long long)t_count * k / n_chunks;
     const long long tri_n = (long long)n_chunks * (n_chunks + 1) / 2, rest = (long long)(n_chunks - k) * (n_chunks - k + 1) / 2;
     return (long long)t_count * (tri_n - rest) / tri_n;
