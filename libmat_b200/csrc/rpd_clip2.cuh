@@ -25,7 +25,7 @@
 
 #define MBK_TINY_P 24
 #define MBK_TINY_T 32
-#define MBK_TINY_E 72
+#define MBK_TINY_E 96
 
 struct __align__(16) CellTiny {
   float4 plane[MBK_TINY_P];
