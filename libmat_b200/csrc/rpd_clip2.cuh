@@ -14,7 +14,7 @@
 //     creates compacts the tail afterwards;
 //   * the directed dual edges of the removed triangles are marked in the adjacency bit matrix inside the conflict
 //     loop itself (one pass less);
-//   * compact caps (24 planes / 32 vertices / 72 edges, 1.7 KB per cell): every vertex has a cofactor-filter entry,
+//   * compact caps (24 planes / 32 vertices / 96 edges, 1.7 KB per cell): every vertex has a cofactor-filter entry,
 //     the conflict flags fit 32 bits, no garbage collection code.  A cell that outgrows them is handed to k_clip at the
 //     reference's caps (redo list), exactly like k_clip's own compact pass does.
 // Decisions (filtered predicate -> FP64 det4x4, flagged class), plane equations and the stored triples
