@@ -178,9 +178,11 @@ int mb_rpd_sync(mb_ctx* ctx, mb_rpd_result* res); /* waits, reads back the count
 
 /* Streamed variant of mb_rpd_run + mb_rpd_sync + mb_rpd_fetch_compact for callers that want the result in
  * HOST memory (what compute_clipped_voro_diagram_GPU returns, voronoi.cu:717-769): the processed tets are
- * cut into n_chunks contiguous spans (0 = automatic, ~48k tets each) and the ordered compact records of
- * span c are copied to library-owned pinned host memory on a second stream while span c+1 is searched and
- * clipped, so the PCIe transfer hides behind the kernels.  On return the complete result -- identical to
+ * cut into n_chunks contiguous spans (0 = automatic: ~40k tets each for the lean / slim transport formats, ~32k for
+ * full records, first and last span half as long) and the ordered compact records of span c are copied to
+ * library-owned pinned host memory on a second stream while span c+1 is clipped, so the PCIe transfer hides behind
+ * the kernels.  With grid candidates the neighbour search runs once for all tets up front and only the clipping and
+ * ordering are cut into spans.  On return the complete result -- identical to
  * the one-shot run's mb_rpd_fetch_compact output -- is at *host_blob / *host_cell_offsets (n_cells+1 byte
  * offsets), valid until the next streamed run on this context or mb_destroy.  The result handle carries the
  * counters (mb_rpd_count / _stats / _kernel_ms) and serves mb_rpd_fetch_records / mb_rpd_fetch_compact from
